@@ -1,0 +1,187 @@
+/*
+ * klt_b200.h -- C ABI of libkltb200.so: the B200 (sm_100a) implementation of PyFeatureTrack's KLT hot path.
+ *
+ * This is the drop-in boundary.  The reference's "plugin" layer for this path is its two Cython
+ * extension modules plus the SciPy call in convolve.py; each entry point below names the reference
+ * interface it replaces (file:line into TimSC/PyFeatureTrack).  The Python modules in
+ * pyfeaturetrack_b200/ (klt, convolve, pyramid, selectGoodFeatures, trackFeatures, goodFeaturesUtils,
+ * trackFeaturesUtils) are thin ctypes shims over these functions; INTEGRATION.md shows the binding a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative klt_status;
+ *     klt_last_error(ctx) returns a human-readable message for the last failure on that context.
+ *   - no exceptions or exit() cross the ABI; the caller owns every host buffer; the library owns device
+ *     memory behind opaque handles.
+ *   - one klt_ctx per (GPU, stream).  A context is not thread-safe; distinct contexts may run concurrently.
+ *   - pointer arguments documented "host or device" are classified with cudaPointerGetAttributes; host
+ *     buffers are copied with cudaMemcpyAsync on the context's stream (pinned memory from
+ *     klt_host_alloc makes those copies truly asynchronous).
+ *   - there is NO CPU fallback: without a CUDA device klt_ctx_create fails with KLT_ERR_CUDA.
+ *   - images are row-major; `pitch` arguments are in ELEMENTS, not bytes.
+ */
+#ifndef KLT_B200_H
+#define KLT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KLT_B200_ABI_VERSION 1
+#define KLT_MAX_TAPS 71   /* convolve.py:28 maxKernelWidth */
+#define KLT_MAX_LEVELS 8
+
+/* error codes (return values) */
+typedef enum klt_status {
+    KLT_OK = 0,
+    KLT_ERR_INVALID = -1,     /* bad argument */
+    KLT_ERR_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+    KLT_ERR_NOMEM = -3,
+    KLT_ERR_UNSUPPORTED = -4, /* e.g. even-length kernel, border smaller than window half-size + 1 */
+    KLT_ERR_ASSERT = -5       /* the reference would raise AssertionError (trackFeaturesUtils.pyx:35) */
+} klt_status;
+
+/* feature status codes == kltState (klt.py:23-29) */
+#define KLT_TRACKED 0
+#define KLT_NOT_FOUND (-1)
+#define KLT_SMALL_DET (-2)
+#define KLT_MAX_ITERATIONS (-3)
+#define KLT_OOB (-4)
+#define KLT_LARGE_RESIDUE (-5)
+
+/* arithmetic mode of the convolution / pyramid kernels */
+#define KLT_PRECISION_FAST 0   /* fp32 FMA accumulation (<= 1e-6 relative-to-max of the reference images) */
+#define KLT_PRECISION_STRICT 1 /* fp64 accumulation in SciPy's exact operation order: bit-identical images */
+
+typedef struct klt_ctx klt_ctx; /* one per (device, stream) */
+typedef struct klt_pyr klt_pyr; /* a batch of image pyramids: intensity, gradx, grady for every level */
+
+/* One 1-D kernel, as produced by _computeKernels (convolve.py:27-93).  Computed on the host. */
+typedef struct klt_kernel1d {
+    int32_t n;                 /* odd, <= KLT_MAX_TAPS */
+    int32_t reserved;
+    double taps[KLT_MAX_TAPS]; /* convolution taps, index 0 = leftmost */
+} klt_kernel1d;
+
+/* The kernels one pyramid build uses (the reference's kernel cache can hand a stale kernel to any of
+ * these roles, convolve.py:236,258 -- so they are per call, not per context). */
+typedef struct klt_taps {
+    klt_kernel1d smooth;     /* gauss(sigma = smooth_sigma_fact * max(window))      trackFeatures.py:166 */
+    klt_kernel1d pyramid;    /* gauss(sigma = subsampling * pyramid_sigma_fact)     pyramid.py:42,60     */
+    klt_kernel1d grad_gauss; /* gauss(grad_sigma)                                   convolve.py:245-246  */
+    klt_kernel1d grad_deriv; /* gaussderiv(grad_sigma)                                                   */
+} klt_taps;
+
+/* The fields of KLT_TrackingContext (klt.py:44-73) read by selection and tracking. */
+typedef struct klt_params {
+    int32_t window_width, window_height;
+    int32_t n_levels, subsampling;
+    double borderx, bordery;      /* Python floats in the reference (quirk Q1: true division) */
+    int32_t mindist, min_eigenvalue;
+    int32_t n_skipped_pixels;
+    int32_t max_iterations;
+    float min_determinant, min_displacement, step_factor;
+    int32_t has_max_residue;      /* 0 == tc.max_residue is None (klt.py:57) */
+    float max_residue;
+    int32_t retain_trackers;
+    int32_t lighting_insensitive; /* must be 0: the reference raises (trackFeaturesUtils.pyx:434-437) */
+    int32_t reserved[8];
+} klt_params;
+
+/* ---- library / context ------------------------------------------------------------------------- */
+int klt_abi_version(void);
+/* stream: a cudaStream_t to launch on (e.g. torch.cuda.current_stream().cuda_stream) or NULL to let
+ * the context create its own non-blocking stream. */
+int klt_ctx_create(int device, void *stream, klt_ctx **out);
+int klt_ctx_destroy(klt_ctx *ctx);
+const char *klt_last_error(const klt_ctx *ctx); /* ctx may be NULL: message of the last failed klt_ctx_create */
+int klt_sync(klt_ctx *ctx);                     /* cudaStreamSynchronize on the context's stream */
+void *klt_ctx_stream(klt_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t klt_launch_count(const klt_ctx *ctx);
+/* pinned host memory for asynchronous copies */
+int klt_host_alloc(size_t bytes, void **out);
+int klt_host_free(void *p);
+/* device memory helpers for callers that want device-resident inputs without torch */
+int klt_device_alloc(klt_ctx *ctx, size_t bytes, void **out);
+int klt_device_free(klt_ctx *ctx, void *p);
+int klt_memcpy(klt_ctx *ctx, void *dst, const void *src, size_t bytes); /* async on the ctx stream, any direction */
+/* device timing on the context's stream: start/stop record CUDA events, elapsed synchronises */
+int klt_timer_start(klt_ctx *ctx);
+int klt_timer_stop(klt_ctx *ctx);
+int klt_timer_elapsed_ms(klt_ctx *ctx, float *ms);
+
+/* ---- operator level: replaces scipy.ndimage.convolve1d pairs behind convolve.py -------------------
+ * klt_convolve_separable_f32  == _convolveSeparate(img, hk, vk)         convolve.py:208-214
+ * klt_smooth_f32              == KLTComputeSmoothedImage's convolution  convolve.py:254-264
+ * klt_gradients_f32           == KLTComputeGradients                    convolve.py:226-248
+ * in/out: float32 [h][w] contiguous, host or device.  Reflect ('half-sample symmetric') borders. */
+int klt_convolve_separable_f32(klt_ctx *ctx, const float *in, int w, int h, const klt_kernel1d *hk,
+                               const klt_kernel1d *vk, int precision, float *out);
+int klt_smooth_f32(klt_ctx *ctx, const float *in, int w, int h, const klt_kernel1d *gauss, int precision, float *out);
+int klt_gradients_f32(klt_ctx *ctx, const float *in, int w, int h, const klt_kernel1d *gauss,
+                      const klt_kernel1d *deriv, int precision, float *gradx, float *grady);
+
+/* ---- pyramids: replaces ComputeImagePyramids (trackFeatures.py:146-196) and KLTPyramid (pyramid.py:14-77)
+ * A klt_pyr holds `batch` independent images' three pyramids in one device allocation.
+ * level dims follow pyramid.py:60-64: w_i = int(w_{i-1}/ss).                                           */
+int klt_pyr_create(klt_ctx *ctx, int w, int h, int n_levels, int subsampling, int batch, klt_pyr **out);
+int klt_pyr_destroy(klt_ctx *ctx, klt_pyr *pyr);
+int klt_pyr_dims(const klt_pyr *pyr, int level, int *w, int *h, int *pitch);
+size_t klt_pyr_bytes(const klt_pyr *pyr);
+/* frames: uint8 [batch][h][pitch] (host or device), frame_stride in elements between images.
+ * = img.convert("F") -> smooth -> KLTPyramid.Compute -> KLTComputeGradients per level, for every image. */
+int klt_pyr_build_u8(klt_ctx *ctx, klt_pyr *pyr, const uint8_t *frames, size_t pitch, size_t frame_stride,
+                     const klt_taps *taps, int precision);
+/* same from float32 images (host or device).  already_smoothed != 0: the images ARE level 0 (pyramid.py:56 takes
+ * the smoothed image as level 0 by reference); == 0: they are first smoothed with taps->smooth like the u8 path. */
+int klt_pyr_build_f32(klt_ctx *ctx, klt_pyr *pyr, const float *images, size_t pitch, size_t frame_stride,
+                      const klt_taps *taps, int precision, int already_smoothed);
+/* which: 0 = intensity, 1 = gradx, 2 = grady.  out: float32 [h_level][w_level] contiguous, host or device. */
+int klt_pyr_download(klt_ctx *ctx, const klt_pyr *pyr, int image, int which, int level, float *out);
+/* device pointer of a level (for callers that keep working on the device) */
+int klt_pyr_level_ptr(const klt_pyr *pyr, int image, int which, int level, const float **ptr);
+
+/* ---- selection: replaces goodFeaturesUtils.ScanImageForGoodFeatures (goodFeaturesUtils.pyx:35-73),
+ * the sort (selectGoodFeatures.py:234-236) and _enforceMinimumDistance (selectGoodFeatures.py:45-135).
+ * klt_scan_good_features: gradx/grady float32 [h][w] (host or device) -> val float32 [ny][nx]
+ *   (row-major over y in [by, h-by) step s, x in [bx, w-bx) step s), exactly the reference's pointlistval order. */
+int klt_scan_good_features(klt_ctx *ctx, const float *gradx, const float *grady, int w, int h, int borderx,
+                           int bordery, int window_hw, int window_hh, int n_skipped_pixels, float *val);
+/* klt_select_good_features: full selection on level-0 gradients of image `image` of a pyramid batch
+ * (pass pyr) or on explicit gradient images (pyr == NULL).  x, y, val: n_features host arrays.
+ * replace == 0: SELECTING_ALL (all slots overwritten; unfilled slots get x=y=-1, val=KLT_NOT_FOUND);
+ * replace == 1: REPLACING_SOME (slots with val >= 0 are kept and pre-marked, only val < 0 slots are filled).
+ * n_consumed (optional): how many sorted candidates the greedy walk looked at. */
+int klt_select_good_features(klt_ctx *ctx, const klt_params *params, const klt_pyr *pyr, int image,
+                             const float *gradx, const float *grady, int w, int h, int n_features, int replace,
+                             double *x, double *y, int32_t *val, int64_t *n_consumed);
+
+/* ---- tracking: replaces KLTTrackFeatures' per-feature loop (trackFeatures.py:250-346), _trackFeature
+ * (:67-136) and trackFeaturesUtils.trackFeatureIterateCKLT / extractImagePatch* / _compute* / _solveEquation
+ * (trackFeaturesUtils.pyx:14-51,61-128,246-340,393-459).
+ * pyr1/pyr2: pyramids of the first/second images (same geometry and batch).  x, y, val: [batch][n_per_image]
+ * host or device arrays, updated in place exactly like the reference mutates the feature list
+ * (lost features: x=y=-1, val=status; tracked: val=0).  Features with val < 0 are skipped.
+ * n_iterations (optional, host): total Newton iterations executed. */
+int klt_track_features(klt_ctx *ctx, const klt_params *params, const klt_pyr *pyr1, const klt_pyr *pyr2,
+                       int n_per_image, double *x, double *y, int32_t *val, int64_t *n_iterations);
+/* trackFeaturesUtils.extractImagePatchSlow(img, x, y, height, width) (trackFeaturesUtils.pyx:14-18):
+ * img float32 [h][w] host or device, out float32 [height][width] host. */
+int klt_extract_patch(klt_ctx *ctx, const float *img, int w, int h, float x, float y, int height, int width,
+                      float *out);
+
+/* ---- whole-call convenience: KLTTrackFeatures(tc, img1, img2, fl) for `batch` independent frame pairs with
+ * HOST (ideally pinned) or device uint8 frames: upload, two pyramid builds, tracking, download.
+ * pyr1/pyr2 are caller-provided scratch pyramids of matching geometry (reused across calls). */
+int klt_track_pairs_u8(klt_ctx *ctx, const klt_params *params, const klt_taps *taps, int precision, klt_pyr *pyr1,
+                       klt_pyr *pyr2, const uint8_t *frames1, const uint8_t *frames2, size_t pitch,
+                       size_t frame_stride, int n_per_image, double *x, double *y, int32_t *val);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KLT_B200_H */

@@ -1,0 +1,275 @@
+"""ctypes binding of libkltb200.so (include/klt_b200.h).  There is no CPU fallback: if the CUDA library is
+missing or no B200 is present, every entry point raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "libkltb200.so")
+
+KLT_MAX_TAPS = 71
+PRECISION_FAST, PRECISION_STRICT = 0, 1
+KLT_ERR_INVALID, KLT_ERR_CUDA, KLT_ERR_NOMEM, KLT_ERR_UNSUPPORTED, KLT_ERR_ASSERT = -1, -2, -3, -4, -5
+
+
+class KLTB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libkltb200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Kernel1D(C.Structure):
+    _fields_ = [("n", C.c_int32), ("reserved", C.c_int32), ("taps", C.c_double * KLT_MAX_TAPS)]
+
+    @classmethod
+    def from_taps(cls, taps):
+        k = cls()
+        taps = [float(t) for t in taps]
+        if len(taps) > KLT_MAX_TAPS:
+            raise ValueError("kernel longer than %d taps" % KLT_MAX_TAPS)
+        k.n = len(taps)
+        for i, t in enumerate(taps):
+            k.taps[i] = t
+        return k
+
+
+class Taps(C.Structure):
+    _fields_ = [("smooth", Kernel1D), ("pyramid", Kernel1D), ("grad_gauss", Kernel1D), ("grad_deriv", Kernel1D)]
+
+
+class Params(C.Structure):
+    _fields_ = [("window_width", C.c_int32), ("window_height", C.c_int32), ("n_levels", C.c_int32),
+                ("subsampling", C.c_int32), ("borderx", C.c_double), ("bordery", C.c_double),
+                ("mindist", C.c_int32), ("min_eigenvalue", C.c_int32), ("n_skipped_pixels", C.c_int32),
+                ("max_iterations", C.c_int32), ("min_determinant", C.c_float), ("min_displacement", C.c_float),
+                ("step_factor", C.c_float), ("has_max_residue", C.c_int32), ("max_residue", C.c_float),
+                ("retain_trackers", C.c_int32), ("lighting_insensitive", C.c_int32), ("reserved", C.c_int32 * 8)]
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/klt_b200.h declares
+_vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
+_fp, _dp, _ip, _u8p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p   # raw addresses: host OR device pointers
+SIGNATURES = {
+    "klt_abi_version": (_i, []),
+    "klt_ctx_create": (_i, [_i, _vp, C.POINTER(_vp)]),
+    "klt_ctx_destroy": (_i, [_vp]),
+    "klt_last_error": (C.c_char_p, [_vp]),
+    "klt_sync": (_i, [_vp]),
+    "klt_ctx_stream": (_vp, [_vp]),
+    "klt_launch_count": (C.c_int64, [_vp]),
+    "klt_host_alloc": (_i, [_sz, C.POINTER(_vp)]),
+    "klt_host_free": (_i, [_vp]),
+    "klt_device_alloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
+    "klt_device_free": (_i, [_vp, _vp]),
+    "klt_memcpy": (_i, [_vp, _vp, _vp, _sz]),
+    "klt_timer_start": (_i, [_vp]),
+    "klt_timer_stop": (_i, [_vp]),
+    "klt_timer_elapsed_ms": (_i, [_vp, C.POINTER(C.c_float)]),
+    "klt_convolve_separable_f32": (_i, [_vp, _fp, _i, _i, C.POINTER(Kernel1D), C.POINTER(Kernel1D), _i, _fp]),
+    "klt_smooth_f32": (_i, [_vp, _fp, _i, _i, C.POINTER(Kernel1D), _i, _fp]),
+    "klt_gradients_f32": (_i, [_vp, _fp, _i, _i, C.POINTER(Kernel1D), C.POINTER(Kernel1D), _i, _fp, _fp]),
+    "klt_pyr_create": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp)]),
+    "klt_pyr_destroy": (_i, [_vp, _vp]),
+    "klt_pyr_dims": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "klt_pyr_bytes": (_sz, [_vp]),
+    "klt_pyr_build_u8": (_i, [_vp, _vp, _u8p, _sz, _sz, C.POINTER(Taps), _i]),
+    "klt_pyr_build_f32": (_i, [_vp, _vp, _fp, _sz, _sz, C.POINTER(Taps), _i, _i]),
+    "klt_pyr_download": (_i, [_vp, _vp, _i, _i, _i, _fp]),
+    "klt_pyr_level_ptr": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),
+    "klt_scan_good_features": (_i, [_vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _fp]),
+    "klt_select_good_features": (_i, [_vp, C.POINTER(Params), _vp, _i, _fp, _fp, _i, _i, _i, _i, _dp, _dp, _ip,
+                                      C.POINTER(C.c_int64)]),
+    "klt_track_features": (_i, [_vp, C.POINTER(Params), _vp, _vp, _i, _dp, _dp, _ip, C.POINTER(C.c_int64)]),
+    "klt_extract_patch": (_i, [_vp, _fp, _i, _i, C.c_float, C.c_float, _i, _i, _fp]),
+    "klt_track_pairs_u8": (_i, [_vp, C.POINTER(Params), C.POINTER(Taps), _i, _vp, _vp, _u8p, _u8p, _sz, _sz, _i,
+                                _dp, _dp, _ip]),
+}
+
+
+def lib():
+    """Loads libkltb200.so (built by pyfeaturetrack_b200/build.py).  Raises if it is missing -- never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIBPATH):
+            raise ImportError("%s not found: run `python -m pyfeaturetrack_b200.build` (needs nvcc). "
+                              "There is no CPU fallback." % _LIBPATH)
+        L = C.CDLL(_LIBPATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def ptr(a):
+    """Address of a numpy array's data, or an int device pointer passed through."""
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a)
+
+
+class Pyramid:
+    """Owns one klt_pyr (a batch of 3-component pyramids in device memory)."""
+
+    def __init__(self, ctx, w, h, n_levels, subsampling, batch=1):
+        self.ctx = ctx
+        self.w, self.h, self.n_levels, self.subsampling, self.batch = w, h, n_levels, subsampling, batch
+        hnd = C.c_void_p()
+        ctx.check(lib().klt_pyr_create(ctx.handle, w, h, n_levels, subsampling, batch, C.byref(hnd)))
+        self.handle = hnd
+        self.dims = []
+        for l in range(n_levels):
+            a, b, c = C.c_int(), C.c_int(), C.c_int()
+            lib().klt_pyr_dims(self.handle, l, C.byref(a), C.byref(b), C.byref(c))
+            self.dims.append((a.value, b.value, c.value))
+
+    def build_u8(self, frames, taps, precision, pitch=None, frame_stride=None):
+        """frames: uint8 ndarray [batch, h, w] / [h, w] or a raw pointer."""
+        if isinstance(frames, np.ndarray):
+            assert frames.dtype == np.uint8 and frames.flags.c_contiguous
+            pitch = frames.shape[-1] if pitch is None else pitch
+            frame_stride = frames.shape[-1] * frames.shape[-2] if frame_stride is None else frame_stride
+        self.ctx.check(lib().klt_pyr_build_u8(self.ctx.handle, self.handle, ptr(frames), pitch, frame_stride,
+                                              C.byref(taps), precision))
+        self._keep = frames   # keep host memory alive until the stream has consumed it
+
+    def build_f32(self, images, taps, precision, already_smoothed, pitch=None, frame_stride=None):
+        if isinstance(images, np.ndarray):
+            assert images.dtype == np.float32 and images.flags.c_contiguous
+            pitch = images.shape[-1] if pitch is None else pitch
+            frame_stride = images.shape[-1] * images.shape[-2] if frame_stride is None else frame_stride
+        self.ctx.check(lib().klt_pyr_build_f32(self.ctx.handle, self.handle, ptr(images), pitch, frame_stride,
+                                               C.byref(taps), precision, 1 if already_smoothed else 0))
+        self._keep = images
+
+    def download(self, which, level, image=0):
+        w, h, _ = self.dims[level]
+        out = np.empty((h, w), np.float32)
+        self.ctx.check(lib().klt_pyr_download(self.ctx.handle, self.handle, image, which, level, out.ctypes.data))
+        return out
+
+    def level_ptr(self, which, level, image=0):
+        p = C.c_void_p()
+        lib().klt_pyr_level_ptr(self.handle, image, which, level, C.byref(p))
+        return p.value
+
+    def nbytes(self):
+        return lib().klt_pyr_bytes(self.handle)
+
+    def close(self):
+        if self.handle:
+            lib().klt_pyr_destroy(self.ctx.handle, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """One klt_ctx = one (GPU, stream)."""
+
+    def __init__(self, device=0, stream=None):
+        hnd = C.c_void_p()
+        rc = lib().klt_ctx_create(device, stream, C.byref(hnd))
+        if rc != 0:
+            raise KLTB200Error(rc, lib().klt_last_error(None).decode())
+        self.handle = hnd
+        self.device = device
+        self._pyr_cache = {}
+
+    def check(self, rc):
+        if rc != 0:
+            msg = lib().klt_last_error(self.handle).decode()
+            if rc == KLT_ERR_ASSERT:
+                raise AssertionError(msg)
+            raise KLTB200Error(rc, msg)
+
+    def sync(self):
+        self.check(lib().klt_sync(self.handle))
+
+    def launch_count(self):
+        return lib().klt_launch_count(self.handle)
+
+    def timer_start(self):
+        self.check(lib().klt_timer_start(self.handle))
+
+    def timer_stop(self):
+        self.check(lib().klt_timer_stop(self.handle))
+
+    def timer_elapsed_ms(self):
+        ms = C.c_float()
+        self.check(lib().klt_timer_elapsed_ms(self.handle, C.byref(ms)))
+        return ms.value
+
+    def scratch_pyramid(self, w, h, n_levels, subsampling, batch=1, slot=0):
+        """Cached scratch pyramids (avoids cudaMalloc per call)."""
+        key = (w, h, n_levels, subsampling, batch, slot)
+        p = self._pyr_cache.get(key)
+        if p is None:
+            if len(self._pyr_cache) > 16:
+                self._pyr_cache.clear()
+            p = self._pyr_cache[key] = Pyramid(self, w, h, n_levels, subsampling, batch)
+        return p
+
+    def host_alloc(self, nbytes):
+        p = C.c_void_p()
+        rc = lib().klt_host_alloc(nbytes, C.byref(p))
+        if rc != 0:
+            raise KLTB200Error(rc, "klt_host_alloc failed")
+        return p.value
+
+    def pinned_array(self, shape, dtype):
+        """numpy array over pinned host memory (freed with the process)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        addr = self.host_alloc(max(n, 1))
+        buf = (C.c_char * max(n, 1)).from_address(addr)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        self.check(lib().klt_device_alloc(self.handle, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, p):
+        self.check(lib().klt_device_free(self.handle, p))
+
+    def memcpy(self, dst, src, nbytes):
+        self.check(lib().klt_memcpy(self.handle, ptr(dst), ptr(src), nbytes))
+
+    def close(self):
+        if self.handle:
+            for p in self._pyr_cache.values():
+                p.close()
+            self._pyr_cache.clear()
+            lib().klt_ctx_destroy(self.handle)
+            self.handle = None
+
+
+_default_ctx = None
+_default_device = None
+
+
+def set_device(device):
+    """Selects the GPU the drop-in modules use (default: $KLT_B200_DEVICE, else $LOCAL_RANK, else 0)."""
+    global _default_ctx, _default_device
+    if _default_ctx is not None and _default_ctx.device != device:
+        _default_ctx.close()
+        _default_ctx = None
+    _default_device = device
+
+
+def default_ctx():
+    global _default_ctx, _default_device
+    if _default_ctx is None:
+        if _default_device is None:
+            _default_device = int(os.environ.get("KLT_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        _default_ctx = Context(_default_device)
+    return _default_ctx

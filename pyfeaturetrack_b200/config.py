@@ -1,0 +1,42 @@
+"""Arithmetic-mode switches of the B200 implementation (there is nothing like this in the reference).
+
+strict : convolutions accumulate in float64 in SciPy's exact operation order -> images, selected features,
+         tracked positions and status codes are bit-identical to the reference's.
+fast   : float32 FMA convolutions (images within ~5e-7 relative-to-max of the reference's); tracking then
+         agrees to ~1e-4 px.  Selection order is sensitive to the last bit of the gradients,
+         so selection and the operator-level functions default to strict; tracking defaults to fast.
+"""
+import os
+
+from . import _capi
+
+_MODES = {"fast": _capi.PRECISION_FAST, "strict": _capi.PRECISION_STRICT}
+
+operator_precision = os.environ.get("KLT_B200_OPERATOR_PRECISION", "strict")
+select_precision = os.environ.get("KLT_B200_SELECT_PRECISION", "strict")
+track_precision = os.environ.get("KLT_B200_TRACK_PRECISION", "fast")
+
+
+def set_precision(track=None, select=None, operator=None):
+    global track_precision, select_precision, operator_precision
+    for v in (track, select, operator):
+        if v is not None and v not in _MODES:
+            raise ValueError("precision must be 'fast' or 'strict'")
+    if track is not None:
+        track_precision = track
+    if select is not None:
+        select_precision = select
+    if operator is not None:
+        operator_precision = operator
+
+
+def operator_precision_code():
+    return _MODES[operator_precision]
+
+
+def select_precision_code():
+    return _MODES[select_precision]
+
+
+def track_precision_code():
+    return _MODES[track_precision]

@@ -1,0 +1,458 @@
+// C ABI of libkltb200.so (see include/klt_b200.h): contexts, pyramids and the entry points that the Python
+// shims in pyfeaturetrack_b200/ bind with ctypes.  Host-side orchestration only; kernels live in
+// klt_conv.cu, klt_select.cu and klt_track.cu.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "klt_common.cuh"
+
+static thread_local std::string g_create_error;
+
+int klt_fail(klt_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+bool klt_is_device_ptr(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int klt_ws_reserve(klt_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->ws_bytes) return KLT_OK;
+    if (ctx->ws) { KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); KLT_CUDA(ctx, cudaFree(ctx->ws)); ctx->ws = nullptr; ctx->ws_bytes = 0; }
+    const size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMalloc(&ctx->ws, want);
+    if (e != cudaSuccess) return klt_fail(ctx, KLT_ERR_NOMEM, "cudaMalloc(%zu) for workspace failed: %s", want, cudaGetErrorString(e));
+    ctx->ws_bytes = want;
+    return KLT_OK;
+}
+
+int klt_pinned_reserve(klt_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_bytes) return KLT_OK;
+    if (ctx->pinned) { KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); KLT_CUDA(ctx, cudaFreeHost(ctx->pinned)); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
+    cudaError_t e = cudaMallocHost(&ctx->pinned, bytes);
+    if (e != cudaSuccess) return klt_fail(ctx, KLT_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    ctx->pinned_bytes = bytes;
+    return KLT_OK;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" {
+
+int klt_abi_version(void) { return KLT_B200_ABI_VERSION; }
+
+int klt_ctx_create(int device, void *stream, klt_ctx **out) {
+    if (!out) return klt_fail(nullptr, KLT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return klt_fail(nullptr, KLT_ERR_CUDA, "no CUDA device available (%s); libkltb200 has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= count) return klt_fail(nullptr, KLT_ERR_INVALID, "device %d out of range (%d devices)", device, count);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return klt_fail(nullptr, KLT_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    klt_ctx *ctx = new klt_ctx();
+    ctx->device = device;
+    ctx->launches = 0;
+    ctx->ws = nullptr; ctx->ws_bytes = 0; ctx->pinned = nullptr; ctx->pinned_bytes = 0;
+    ctx->own_stream = stream == nullptr;
+    if (stream) ctx->stream = (cudaStream_t)stream;
+    else if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete ctx;
+        return klt_fail(nullptr, KLT_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->num_sms = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        // the library carries sm_100a code only; fail loudly instead of at the first launch
+        std::string name = prop.name;
+        if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return klt_fail(nullptr, KLT_ERR_UNSUPPORTED, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU", device, name.c_str(), prop.major, prop.minor);
+    }
+    *out = ctx;
+    return KLT_OK;
+}
+
+int klt_ctx_destroy(klt_ctx *ctx) {
+    if (!ctx) return KLT_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return KLT_OK;
+}
+
+const char *klt_last_error(const klt_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int klt_sync(klt_ctx *ctx) {
+    KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KLT_OK;
+}
+void *klt_ctx_stream(klt_ctx *ctx) { return (void *)ctx->stream; }
+int64_t klt_launch_count(const klt_ctx *ctx) { return ctx->launches; }
+
+int klt_host_alloc(size_t bytes, void **out) {
+    if (!out) return KLT_ERR_INVALID;
+    return cudaMallocHost(out, bytes) == cudaSuccess ? KLT_OK : KLT_ERR_NOMEM;
+}
+int klt_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? KLT_OK : KLT_ERR_CUDA; }
+int klt_device_alloc(klt_ctx *ctx, size_t bytes, void **out) {
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) return klt_fail(ctx, KLT_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return KLT_OK;
+}
+int klt_device_free(klt_ctx *ctx, void *p) {
+    KLT_CUDA(ctx, cudaFree(p));
+    return KLT_OK;
+}
+int klt_memcpy(klt_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    KLT_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+    return KLT_OK;
+}
+int klt_timer_start(klt_ctx *ctx) { KLT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream)); return KLT_OK; }
+int klt_timer_stop(klt_ctx *ctx) { KLT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream)); return KLT_OK; }
+int klt_timer_elapsed_ms(klt_ctx *ctx, float *ms) {
+    KLT_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    KLT_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return KLT_OK;
+}
+
+// ---- operator level ---------------------------------------------------------------------------------------
+// Stages host images in the workspace when needed.  Layout: [in][out0][out1].
+static int stage_in(klt_ctx *ctx, const float *in, size_t n, size_t slot, size_t nslots, const float **dev) {
+    const size_t plane = align_up(n * sizeof(float), 256);
+    int rc = klt_ws_reserve(ctx, nslots * plane);
+    if (rc) return rc;
+    float *d = (float *)((char *)ctx->ws + slot * plane);
+    KLT_CUDA(ctx, cudaMemcpyAsync(d, in, n * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    *dev = d;
+    return KLT_OK;
+}
+
+int klt_convolve_separable_f32(klt_ctx *ctx, const float *in, int w, int h, const klt_kernel1d *hk,
+                               const klt_kernel1d *vk, int precision, float *out) {
+    if (!ctx || !in || !out || w <= 0 || h <= 0) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)w * h, plane = align_up(n * sizeof(float), 256);
+    int rc = klt_ws_reserve(ctx, 2 * plane);
+    if (rc) return rc;
+    const float *din = in;
+    float *dout = out;
+    const bool in_host = !klt_is_device_ptr(in), out_host = !klt_is_device_ptr(out);
+    if (in_host && (rc = stage_in(ctx, in, n, 0, 2, &din))) return rc;
+    if (out_host) dout = (float *)((char *)ctx->ws + plane);
+    if ((rc = klt_launch_conv_sep_f32(ctx, din, w, 0, dout, w, 0, w, h, 1, hk, vk, precision))) return rc;
+    if (out_host) {
+        KLT_CUDA(ctx, cudaMemcpyAsync(out, dout, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return KLT_OK;
+}
+
+int klt_smooth_f32(klt_ctx *ctx, const float *in, int w, int h, const klt_kernel1d *gauss, int precision, float *out) {
+    return klt_convolve_separable_f32(ctx, in, w, h, gauss, gauss, precision, out);
+}
+
+int klt_gradients_f32(klt_ctx *ctx, const float *in, int w, int h, const klt_kernel1d *gauss, const klt_kernel1d *deriv,
+                      int precision, float *gradx, float *grady) {
+    if (!ctx || !in || !gradx || !grady || w <= 0 || h <= 0) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)w * h, plane = align_up(n * sizeof(float), 256);
+    int rc = klt_ws_reserve(ctx, 3 * plane);
+    if (rc) return rc;
+    const float *din = in;
+    const bool in_host = !klt_is_device_ptr(in), out_host = !klt_is_device_ptr(gradx);
+    if (out_host != !klt_is_device_ptr(grady)) return klt_fail(ctx, KLT_ERR_INVALID, "gradx and grady must both be host or both be device");
+    if (in_host && (rc = stage_in(ctx, in, n, 0, 3, &din))) return rc;
+    float *dgx = out_host ? (float *)((char *)ctx->ws + plane) : gradx;
+    float *dgy = out_host ? (float *)((char *)ctx->ws + 2 * plane) : grady;
+    if ((rc = klt_launch_grad_pair(ctx, din, w, 0, dgx, dgy, w, 0, w, h, 1, gauss, deriv, precision))) return rc;
+    if (out_host) {
+        KLT_CUDA(ctx, cudaMemcpyAsync(gradx, dgx, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        KLT_CUDA(ctx, cudaMemcpyAsync(grady, dgy, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return KLT_OK;
+}
+
+// ---- pyramids -----------------------------------------------------------------------------------------------
+int klt_pyr_create(klt_ctx *ctx, int w, int h, int n_levels, int subsampling, int batch, klt_pyr **out) {
+    if (!ctx || !out || w <= 0 || h <= 0 || batch <= 0) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    if (n_levels < 1 || n_levels > KLT_MAX_LEVELS) return klt_fail(ctx, KLT_ERR_INVALID, "n_levels %d out of range 1..%d", n_levels, KLT_MAX_LEVELS);
+    if (subsampling != 2 && subsampling != 4 && subsampling != 8 && subsampling != 16 && subsampling != 32)
+        return klt_fail(ctx, KLT_ERR_INVALID, "Pyramid's subsampling must be either 2, 4, 8, 16, or 32");   // pyramid.py:17-20
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    klt_pyr *p = new klt_pyr();
+    p->w = w; p->h = h; p->n_levels = n_levels; p->ss = subsampling; p->batch = batch;
+    size_t off = 0;
+    int lw = w, lh = h;
+    for (int l = 0; l < n_levels; l++) {
+        if (lw < 1 || lh < 1) { delete p; return klt_fail(ctx, KLT_ERR_INVALID, "pyramid level %d is empty", l); }
+        p->lv[l].w = lw; p->lv[l].h = lh; p->lv[l].pitch = (lw + 3) & ~3; p->lv[l].off = off;
+        off += align_up((size_t)p->lv[l].pitch * lh, 64);    // 256-byte aligned levels
+        lw /= subsampling; lh /= subsampling;               // int(n / ss), pyramid.py:63-64
+    }
+    p->plane_floats = off;
+    const size_t bytes = 3 * (size_t)batch * off * sizeof(float);
+    cudaError_t e = cudaMalloc(&p->base, bytes);
+    if (e != cudaSuccess) { delete p; return klt_fail(ctx, KLT_ERR_NOMEM, "cudaMalloc(%zu) for pyramid failed: %s", bytes, cudaGetErrorString(e)); }
+    *out = p;
+    return KLT_OK;
+}
+
+int klt_pyr_destroy(klt_ctx *ctx, klt_pyr *pyr) {
+    if (!pyr) return KLT_OK;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    cudaFree(pyr->base);
+    delete pyr;
+    return KLT_OK;
+}
+
+int klt_pyr_dims(const klt_pyr *pyr, int level, int *w, int *h, int *pitch) {
+    if (!pyr || level < 0 || level >= pyr->n_levels) return KLT_ERR_INVALID;
+    if (w) *w = pyr->lv[level].w;
+    if (h) *h = pyr->lv[level].h;
+    if (pitch) *pitch = pyr->lv[level].pitch;
+    return KLT_OK;
+}
+size_t klt_pyr_bytes(const klt_pyr *pyr) { return pyr ? 3 * (size_t)pyr->batch * pyr->plane_floats * sizeof(float) : 0; }
+
+static int check_taps(klt_ctx *ctx, const klt_taps *t) {
+    if (!t) return klt_fail(ctx, KLT_ERR_INVALID, "taps is NULL");
+    return KLT_OK;
+}
+
+// levels 1..L-1 and all gradients, given level 0 intensity already in place
+static int build_rest(klt_ctx *ctx, klt_pyr *p, const klt_taps *taps, int precision) {
+    int rc;
+    const size_t stride = p->plane_floats;
+    for (int l = 1; l < p->n_levels; l++) {
+        const LevelDesc &a = p->lv[l - 1], &b = p->lv[l];
+        if ((rc = klt_launch_pyr_down(ctx, p->level(0, 0, l - 1), a.pitch, stride, a.w, a.h, p->level(0, 0, l), b.pitch, stride,
+                                      b.w, b.h, p->ss, p->batch, &taps->pyramid, precision))) return rc;
+    }
+    for (int l = 0; l < p->n_levels; l++) {
+        const LevelDesc &a = p->lv[l];
+        if ((rc = klt_launch_grad_pair(ctx, p->level(0, 0, l), a.pitch, stride, p->level(1, 0, l), p->level(2, 0, l), a.pitch,
+                                       stride, a.w, a.h, p->batch, &taps->grad_gauss, &taps->grad_deriv, precision))) return rc;
+    }
+    return KLT_OK;
+}
+
+int klt_pyr_build_u8(klt_ctx *ctx, klt_pyr *p, const uint8_t *frames, size_t pitch, size_t frame_stride,
+                     const klt_taps *taps, int precision) {
+    if (!ctx || !p || !frames) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    int rc;
+    if ((rc = check_taps(ctx, taps))) return rc;
+    if (pitch < (size_t)p->w) return klt_fail(ctx, KLT_ERR_INVALID, "pitch %zu smaller than width %d", pitch, p->w);
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint8_t *dframes = frames;
+    if (!klt_is_device_ptr(frames)) {
+        const size_t bytes = (size_t)(p->batch - 1) * frame_stride + (size_t)(p->h - 1) * pitch + p->w;
+        if ((rc = klt_ws_reserve(ctx, bytes))) return rc;
+        KLT_CUDA(ctx, cudaMemcpyAsync(ctx->ws, frames, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        dframes = (const uint8_t *)ctx->ws;
+    }
+    // img.convert("F") + KLTComputeSmoothedImage (trackFeatures.py:165-166): one fused kernel, u8 in, f32 out
+    if ((rc = klt_launch_conv_sep_u8(ctx, dframes, pitch, frame_stride, p->level(0, 0, 0), p->lv[0].pitch, p->plane_floats,
+                                     p->w, p->h, p->batch, &taps->smooth, &taps->smooth, precision))) return rc;
+    return build_rest(ctx, p, taps, precision);
+}
+
+int klt_pyr_build_f32(klt_ctx *ctx, klt_pyr *p, const float *images, size_t pitch, size_t frame_stride,
+                      const klt_taps *taps, int precision, int already_smoothed) {
+    if (!ctx || !p || !images) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    int rc;
+    if ((rc = check_taps(ctx, taps))) return rc;
+    if (pitch < (size_t)p->w) return klt_fail(ctx, KLT_ERR_INVALID, "pitch %zu smaller than width %d", pitch, p->w);
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (already_smoothed) {
+        for (int b = 0; b < p->batch; b++)
+            KLT_CUDA(ctx, cudaMemcpy2DAsync(p->level(0, b, 0), p->lv[0].pitch * sizeof(float), images + (size_t)b * frame_stride,
+                                            pitch * sizeof(float), p->w * sizeof(float), p->h, cudaMemcpyDefault, ctx->stream));
+        return build_rest(ctx, p, taps, precision);
+    }
+    const float *dimg = images;
+    if (!klt_is_device_ptr(images)) {
+        const size_t elems = (size_t)(p->batch - 1) * frame_stride + (size_t)(p->h - 1) * pitch + p->w;
+        if ((rc = klt_ws_reserve(ctx, elems * sizeof(float)))) return rc;
+        KLT_CUDA(ctx, cudaMemcpyAsync(ctx->ws, images, elems * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        dimg = (const float *)ctx->ws;
+    }
+    if ((rc = klt_launch_conv_sep_f32(ctx, dimg, pitch, frame_stride, p->level(0, 0, 0), p->lv[0].pitch, p->plane_floats, p->w,
+                                      p->h, p->batch, &taps->smooth, &taps->smooth, precision))) return rc;
+    return build_rest(ctx, p, taps, precision);
+}
+
+int klt_pyr_download(klt_ctx *ctx, const klt_pyr *p, int image, int which, int level, float *out) {
+    if (!ctx || !p || !out || image < 0 || image >= p->batch || which < 0 || which > 2 || level < 0 || level >= p->n_levels)
+        return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    const LevelDesc &a = p->lv[level];
+    KLT_CUDA(ctx, cudaMemcpy2DAsync(out, a.w * sizeof(float), p->level(which, image, level), a.pitch * sizeof(float),
+                                    a.w * sizeof(float), a.h, cudaMemcpyDefault, ctx->stream));
+    KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KLT_OK;
+}
+
+int klt_pyr_level_ptr(const klt_pyr *p, int image, int which, int level, const float **ptr) {
+    if (!p || !ptr || image < 0 || image >= p->batch || which < 0 || which > 2 || level < 0 || level >= p->n_levels) return KLT_ERR_INVALID;
+    *ptr = p->level(which, image, level);
+    return KLT_OK;
+}
+
+// ---- selection ----------------------------------------------------------------------------------------------
+int klt_scan_good_features(klt_ctx *ctx, const float *gradx, const float *grady, int w, int h, int borderx, int bordery,
+                           int window_hw, int window_hh, int n_skipped_pixels, float *val) {
+    if (!ctx || !gradx || !grady || !val || w <= 0 || h <= 0 || n_skipped_pixels < 0) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    if (borderx < window_hw + 1 || bordery < window_hh + 1)
+        return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "border (%d,%d) smaller than window half-size + 1: the reference reads out of bounds here", borderx, bordery);
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int step = n_skipped_pixels + 1;
+    int nx = 0, ny = 0;
+    if (w - borderx > borderx) nx = (w - 2 * borderx + step - 1) / step;
+    if (h - bordery > bordery) ny = (h - 2 * bordery + step - 1) / step;
+    const size_t n = (size_t)w * h, plane = align_up(n * sizeof(float), 256);
+    int rc = klt_ws_reserve(ctx, 6 * plane);
+    if (rc) return rc;
+    char *wsp = (char *)ctx->ws;
+    float *dval = (float *)(wsp + 3 * plane);
+    const float *dgx = gradx, *dgy = grady;
+    if (!klt_is_device_ptr(gradx)) {
+        float *d = (float *)(wsp + 4 * plane);
+        KLT_CUDA(ctx, cudaMemcpyAsync(d, gradx, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        dgx = d;
+    }
+    if (!klt_is_device_ptr(grady)) {
+        float *d = (float *)(wsp + 5 * plane);
+        KLT_CUDA(ctx, cudaMemcpyAsync(d, grady, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        dgy = d;
+    }
+    if ((rc = klt_launch_scan(ctx, dgx, dgy, w, w, h, borderx, bordery, window_hw, window_hh, n_skipped_pixels, dval, nx, ny))) return rc;
+    if ((size_t)nx * ny)
+        KLT_CUDA(ctx, cudaMemcpyAsync(val, dval, (size_t)nx * ny * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KLT_OK;
+}
+
+int klt_select_good_features(klt_ctx *ctx, const klt_params *params, const klt_pyr *pyr, int image, const float *gradx,
+                             const float *grady, int w, int h, int n_features, int replace, double *x, double *y,
+                             int32_t *val, int64_t *n_consumed) {
+    if (!ctx || !params || !x || !y || !val || n_features < 0) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (pyr) {
+        if (image < 0 || image >= pyr->batch) return klt_fail(ctx, KLT_ERR_INVALID, "image index out of range");
+        return klt_select_device(ctx, params, pyr->level(1, image, 0), pyr->level(2, image, 0), pyr->lv[0].pitch, pyr->w, pyr->h,
+                                 n_features, replace, x, y, val, n_consumed);
+    }
+    if (!gradx || !grady || w <= 0 || h <= 0) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    if (!klt_is_device_ptr(gradx) || !klt_is_device_ptr(grady))
+        return klt_fail(ctx, KLT_ERR_INVALID, "explicit gradient images must be device pointers (use a pyramid or klt_device_alloc)");
+    return klt_select_device(ctx, params, gradx, grady, w, w, h, n_features, replace, x, y, val, n_consumed);
+}
+
+// ---- tracking -----------------------------------------------------------------------------------------------
+static int check_track_args(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const klt_pyr *p2) {
+    if (p->lighting_insensitive) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "lighting_insensitive: Not implemented (trackFeaturesUtils.pyx:435)");
+    if (p1->w != p2->w || p1->h != p2->h || p1->n_levels != p2->n_levels || p1->ss != p2->ss || p1->batch != p2->batch)
+        return klt_fail(ctx, KLT_ERR_INVALID, "pyramids differ in geometry");
+    if (p->n_levels != p1->n_levels || p->subsampling != p1->ss)
+        return klt_fail(ctx, KLT_ERR_INVALID, "params (levels %d, subsampling %d) do not match the pyramids (%d, %d)", p->n_levels, p->subsampling, p1->n_levels, p1->ss);
+    if (p->window_width < 3 || p->window_height < 3 || !(p->window_width & 1) || !(p->window_height & 1))
+        return klt_fail(ctx, KLT_ERR_INVALID, "window must be odd and >= 3");
+    if (p->window_width != p->window_height)
+        return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "non-square tracking windows corrupt memory in the reference (quirk Q10); refused");
+    return KLT_OK;
+}
+
+int klt_track_features(klt_ctx *ctx, const klt_params *params, const klt_pyr *pyr1, const klt_pyr *pyr2, int n_per_image,
+                       double *x, double *y, int32_t *val, int64_t *n_iterations) {
+    if (!ctx || !params || !pyr1 || !pyr2 || !x || !y || !val || n_per_image < 0) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    int rc;
+    if ((rc = check_track_args(ctx, params, pyr1, pyr2))) return rc;
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t total = (size_t)n_per_image * pyr1->batch;
+    const bool host = !klt_is_device_ptr(x);
+    if (host != !klt_is_device_ptr(y) || host != !klt_is_device_ptr(val)) return klt_fail(ctx, KLT_ERR_INVALID, "x, y, val must all be host or all be device");
+    const size_t fbytes = align_up(total * sizeof(double), 256);
+    if ((rc = klt_ws_reserve(ctx, 3 * fbytes + 256))) return rc;
+    char *wsp = (char *)ctx->ws;
+    unsigned long long *iters = (unsigned long long *)wsp;
+    int *aflag = (int *)(wsp + 8);
+    double *dx = x, *dy = y;
+    int32_t *dval = val;
+    KLT_CUDA(ctx, cudaMemsetAsync(wsp, 0, 16, ctx->stream));
+    if (host) {
+        dx = (double *)(wsp + 256); dy = (double *)(wsp + 256 + fbytes); dval = (int32_t *)(wsp + 256 + 2 * fbytes);
+        KLT_CUDA(ctx, cudaMemcpyAsync(dx, x, total * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        KLT_CUDA(ctx, cudaMemcpyAsync(dy, y, total * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        KLT_CUDA(ctx, cudaMemcpyAsync(dval, val, total * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if ((rc = klt_launch_track(ctx, params, pyr1, pyr2, n_per_image, dx, dy, dval, iters, aflag))) return rc;
+    if (host) {
+        KLT_CUDA(ctx, cudaMemcpyAsync(x, dx, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        KLT_CUDA(ctx, cudaMemcpyAsync(y, dy, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        KLT_CUDA(ctx, cudaMemcpyAsync(val, dval, total * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (host || n_iterations) {
+        unsigned long long res[2] = {0, 0};
+        KLT_CUDA(ctx, cudaMemcpyAsync(res, wsp, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (n_iterations) *n_iterations = (int64_t)res[0];
+        if ((int)(res[1] & 0xffffffffull))
+            return klt_fail(ctx, KLT_ERR_ASSERT, "a feature window leaves the image at a pyramid level: the reference raises AssertionError (trackFeaturesUtils.pyx:35)");
+    }
+    return KLT_OK;
+}
+
+int klt_extract_patch(klt_ctx *ctx, const float *img, int w, int h, float x, float y, int height, int width, float *out) {
+    if (!ctx || !img || !out || w <= 0 || h <= 0 || width < 1 || height < 1) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)w * h, plane = align_up(n * sizeof(float), 256), pbytes = align_up((size_t)width * height * sizeof(float), 256);
+    int rc = klt_ws_reserve(ctx, plane + pbytes + 256);
+    if (rc) return rc;
+    char *wsp = (char *)ctx->ws;
+    const float *dimg = img;
+    if (!klt_is_device_ptr(img)) {
+        KLT_CUDA(ctx, cudaMemcpyAsync(wsp, img, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        dimg = (const float *)wsp;
+    }
+    float *dout = (float *)(wsp + plane);
+    int *dok = (int *)(wsp + plane + pbytes);
+    if ((rc = klt_launch_extract_patch(ctx, dimg, w, w, h, x, y, height, width, dout, dok))) return rc;
+    int ok = 0;
+    KLT_CUDA(ctx, cudaMemcpyAsync(out, dout, (size_t)width * height * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    KLT_CUDA(ctx, cudaMemcpyAsync(&ok, dok, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!ok) return klt_fail(ctx, KLT_ERR_ASSERT, "patch out of bounds (trackFeaturesUtils.pyx:35)");
+    return KLT_OK;
+}
+
+int klt_track_pairs_u8(klt_ctx *ctx, const klt_params *params, const klt_taps *taps, int precision, klt_pyr *pyr1,
+                       klt_pyr *pyr2, const uint8_t *frames1, const uint8_t *frames2, size_t pitch, size_t frame_stride,
+                       int n_per_image, double *x, double *y, int32_t *val) {
+    int rc;
+    // NOTE: both builds may stage host frames through the (single) workspace; stream order makes that safe.
+    if ((rc = klt_pyr_build_u8(ctx, pyr1, frames1, pitch, frame_stride, taps, precision))) return rc;
+    if ((rc = klt_pyr_build_u8(ctx, pyr2, frames2, pitch, frame_stride, taps, precision))) return rc;
+    return klt_track_features(ctx, params, pyr1, pyr2, n_per_image, x, y, val, nullptr);
+}
+
+}  // extern "C"

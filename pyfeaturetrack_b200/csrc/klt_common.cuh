@@ -1,0 +1,112 @@
+// Internal declarations shared by the translation units of libkltb200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/klt_b200.h"
+
+#define KLT_NUM_SMS_B200 148
+
+// Kernel taps passed BY VALUE as a kernel parameter (constant bank): no global state, no symbol copies.
+// c[j] is the tap that multiplies in[x + j - r]  (convolution: c[j] = taps[n-1-j]).
+struct TapsF {
+    int n, r, sym;   // sym: +1 symmetric, -1 antisymmetric, 0 general (SciPy's DBL_EPSILON test)
+    float c[KLT_MAX_TAPS];
+};
+struct TapsD {
+    int n, r, sym;
+    int pad;
+    double c[KLT_MAX_TAPS];
+};
+
+struct LevelDesc {
+    int w, h, pitch;          // pitch in floats (multiple of 4)
+    size_t off;               // offset in floats of image 0 inside the component plane
+};
+
+struct klt_pyr {
+    int w, h, n_levels, ss, batch;
+    LevelDesc lv[KLT_MAX_LEVELS];
+    size_t plane_floats;      // floats of ONE image's ONE component over all levels
+    float *base;              // [which(3)][image(batch)][plane_floats]
+    __host__ __device__ inline float *level(int which, int image, int l) const {
+        return base + ((size_t)which * batch + image) * plane_floats + lv[l].off;
+    }
+};
+
+struct klt_ctx {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    std::string err;
+    int64_t launches;
+    cudaEvent_t ev0, ev1;
+    // grow-only device workspace
+    void *ws;
+    size_t ws_bytes;
+    // small pinned staging area
+    void *pinned;
+    size_t pinned_bytes;
+    int num_sms;
+};
+
+int klt_fail(klt_ctx *ctx, int code, const char *fmt, ...);
+#define KLT_CUDA(ctx, call)                                                                           \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return klt_fail(ctx, KLT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                                      \
+    } while (0)
+#define KLT_CHECK_LAUNCH(ctx)                   \
+    do {                                        \
+        (ctx)->launches++;                      \
+        KLT_CUDA(ctx, cudaGetLastError());      \
+    } while (0)
+
+int klt_ws_reserve(klt_ctx *ctx, size_t bytes);          // grow-only workspace
+int klt_pinned_reserve(klt_ctx *ctx, size_t bytes);
+bool klt_is_device_ptr(const void *p);
+
+int klt_make_taps(klt_ctx *ctx, const klt_kernel1d *k, TapsF *f, TapsD *d);
+
+// ---- launchers (klt_conv.cu) -- all pointers are DEVICE pointers, pitches in elements ----------------
+// separable convolution out = vk_v( hk_h(in) ), batched over `batch` images
+int klt_launch_conv_sep_f32(klt_ctx *ctx, const float *in, size_t in_pitch, size_t in_stride, float *out,
+                            size_t out_pitch, size_t out_stride, int w, int h, int batch, const klt_kernel1d *hk,
+                            const klt_kernel1d *vk, int precision);
+int klt_launch_conv_sep_u8(klt_ctx *ctx, const uint8_t *in, size_t in_pitch, size_t in_stride, float *out,
+                           size_t out_pitch, size_t out_stride, int w, int h, int batch, const klt_kernel1d *hk,
+                           const klt_kernel1d *vk, int precision);
+// gradient pair: gx = g_v(d_h(in)), gy = d_v(g_h(in))
+int klt_launch_grad_pair(klt_ctx *ctx, const float *in, size_t in_pitch, size_t in_stride, float *gx, float *gy,
+                         size_t out_pitch, size_t out_stride, int w, int h, int batch, const klt_kernel1d *g,
+                         const klt_kernel1d *d, int precision);
+// pyramid step: out[y][x] = smooth(in)[ss*y+ss/2][ss*x+ss/2], only sampled outputs are evaluated
+int klt_launch_pyr_down(klt_ctx *ctx, const float *in, size_t in_pitch, size_t in_stride, int w, int h, float *out,
+                        size_t out_pitch, size_t out_stride, int ow, int oh, int ss, int batch,
+                        const klt_kernel1d *g, int precision);
+
+// ---- klt_select.cu -----------------------------------------------------------------------------------
+int klt_launch_scan(klt_ctx *ctx, const float *gx, const float *gy, size_t pitch, int w, int h, int bx, int by,
+                    int hw, int hh, int skip, float *val_dev /* [ny][nx] */, int nx, int ny);
+int klt_select_device(klt_ctx *ctx, const klt_params *p, const float *gx, const float *gy, size_t pitch, int w,
+                      int h, int n_features, int replace, double *x, double *y, int32_t *val, int64_t *n_consumed);
+
+// ---- klt_track.cu ------------------------------------------------------------------------------------
+int klt_launch_track(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const klt_pyr *p2, int n_per_image,
+                     double *x_dev, double *y_dev, int32_t *val_dev, unsigned long long *iters_dev, int *assert_dev);
+int klt_launch_extract_patch(klt_ctx *ctx, const float *img, size_t pitch, int w, int h, float x, float y,
+                             int height, int width, float *out_dev, int *ok_dev);
+
+__host__ __device__ static inline int klt_reflect(int i, int n) {
+    // scipy 'reflect' (half-sample symmetric); loop handles kernels wider than the image
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) {
+        if (i < 0) i = -i - 1;
+        if (i >= n) i = 2 * n - i - 1;
+    }
+    return i;
+}

@@ -1,0 +1,255 @@
+// Pyramidal Lucas-Kanade tracking: one warp per feature, all pyramid levels in one launch (sm_100a).
+//
+// Replaces the per-feature loop of KLTTrackFeatures (trackFeatures.py:250-346), _trackFeature (:67-136)
+// and the Cython inner loops trackFeatureIterateCKLT / extractImagePatchOptimised /
+// _computeIntensityDifference / _computeGradientSum / _compute2by2GradientMatrix / _compute2by1ErrorVector /
+// _solveEquation (trackFeaturesUtils.pyx:20-51,61-128,246-340,393-459).
+//
+// Arithmetic follows the reference's operand types EXACTLY (taken from the Cython-generated C):
+//   * bilinear sample: three products in double, the (ax*ay)*I11 product in float, summed left to right in
+//     double, rounded to float once;
+//   * gradient sums, products and the five window sums in float32 without FMA contraction; the window
+//     sums run SEQUENTIALLY in row-major order (one lane per sum), because float addition order is part
+//     of the reference's result;
+//   * 2x2 solve in float32 with separately rounded products;
+//   * the Python-level re-check uses doubles and hw = width/2 = 3.5 (true division, quirk Q2);
+//   * the residue uses NumPy's float32 pairwise summation order.
+// Given bit-identical pyramids (STRICT mode) the positions and status codes are bit-identical to the
+// reference's; with FAST pyramids they agree to ~1e-4 px.
+#include "klt_common.cuh"
+
+#define KLT_INTERNAL_ASSERT (-100)
+
+struct TrackArgs {
+    klt_pyr p1, p2;
+    int w, h;               // window
+    int n_levels, ss;
+    int max_iterations;
+    float small_det, th, step_factor;
+    int has_max_residue;
+    float max_residue;
+    int retain;
+    double borderx, bordery;
+    int n_per_image, total;
+};
+
+// bilinear sample with the reference's mixed precision (trackFeaturesUtils.pyx:44-47)
+__device__ __forceinline__ float bilerp_ref(const float *__restrict__ p, int pitch, float ax, float ay) {
+    const double dax = (double)ax, day = (double)ay;
+    const double omx = __dsub_rn(1.0, dax), omy = __dsub_rn(1.0, day);
+    const float i00 = p[0], i01 = p[1], i10 = p[pitch], i11 = p[pitch + 1];
+    double v = __dmul_rn(__dmul_rn(omx, omy), (double)i00);
+    v = __dadd_rn(v, __dmul_rn(__dmul_rn(dax, omy), (double)i01));
+    v = __dadd_rn(v, __dmul_rn(__dmul_rn(omx, day), (double)i10));
+    v = __dadd_rn(v, (double)__fmul_rn(__fmul_rn(ax, ay), i11));
+    return __double2float_rn(v);
+}
+
+// NumPy FLOAT_pairwise_sum (numpy/_core/src/umath/loops_utils.h.src), executed by one lane.
+__device__ float np_pairwise_sum(const float *a, int n) {
+    if (n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < n; i++) res = __fadd_rn(res, a[i]);
+        return res;
+    } else if (n <= 128) {
+        float r[8];
+        int i;
+#pragma unroll
+        for (i = 0; i < 8; i++) r[i] = a[i];
+        for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] = __fadd_rn(r[j], a[i + j]);
+        }
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; i++) res = __fadd_rn(res, a[i]);
+        return res;
+    } else {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        return __fadd_rn(np_pairwise_sum(a, n2), np_pairwise_sum(a + n2, n - n2));
+    }
+}
+
+// Shared memory per warp: T, Tgx, Tgy (templates) + 5 product arrays, each n = w*h floats.
+__global__ void __launch_bounds__(128)
+lk_track_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ xs, double *__restrict__ ys,
+                int *__restrict__ vals, unsigned long long *__restrict__ iters_total, int *__restrict__ assert_flag) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (f >= A.total) return;
+    if (vals[f] < 0) return;                                  // trackFeatures.py:253
+    const int n = A.w * A.h;
+    float *T = smem + (size_t)warp * 8 * n;
+    float *Tgx = T + n, *Tgy = T + 2 * n, *S = T + 3 * n;     // S: 5 arrays of products / |diff|
+    const int image = f / A.n_per_image;
+    const int hw = A.w / 2, hh = A.h / 2;
+    const double ss = (double)A.ss;
+
+    double xloc = xs[f], yloc = ys[f];
+    for (int r = A.n_levels - 1; r >= 0; r--) { xloc = __ddiv_rn(xloc, ss); yloc = __ddiv_rn(yloc, ss); }   // :260-262
+    double xout = xloc, yout = yloc;
+    int st = KLT_TRACKED;
+    unsigned int my_iters = 0;
+
+    for (int r = A.n_levels - 1; r >= 0; r--) {
+        xloc = __dmul_rn(xloc, ss); yloc = __dmul_rn(yloc, ss);
+        xout = __dmul_rn(xout, ss); yout = __dmul_rn(yout, ss);
+        const int nc = A.p1.lv[r].w, nr = A.p1.lv[r].h, pitch = A.p1.lv[r].pitch;
+        const float *I1 = A.p1.level(0, image, r), *GX1 = A.p1.level(1, image, r), *GY1 = A.p1.level(2, image, r);
+        const float *I2 = A.p2.level(0, image, r), *GX2 = A.p2.level(1, image, r), *GY2 = A.p2.level(2, image, r);
+
+        // ---- _trackFeature: templates at (x1,y1) (trackFeatures.py:102-104) ----
+        const float x1 = __double2float_rn(xloc), y1 = __double2float_rn(yloc);
+        {
+            const int ix = (int)x1, iy = (int)y1;
+            if (!(ix - hw >= 0 && iy - hh >= 0 && ix + hw + 2 <= nc && iy + hh + 2 <= nr)) {   // pyx:35
+                if (lane == 0) { atomicExch(assert_flag, 1); }
+                st = KLT_INTERNAL_ASSERT;
+                break;
+            }
+            const float ax = __double2float_rn(__dsub_rn((double)x1, (double)ix));
+            const float ay = __double2float_rn(__dsub_rn((double)y1, (double)iy));
+            for (int k = lane; k < n; k += 32) {
+                const int j = k / A.w, i = k - j * A.w;
+                const size_t o = (size_t)(iy + j - hh) * pitch + (ix + i - hw);
+                T[k] = bilerp_ref(I1 + o, pitch, ax, ay);
+                Tgx[k] = bilerp_ref(GX1 + o, pitch, ax, ay);
+                Tgy[k] = bilerp_ref(GY1 + o, pitch, ax, ay);
+            }
+        }
+        __syncwarp();
+
+        // ---- trackFeatureIterateCKLT (pyx:393-459), float32 state ----
+        float x2 = __double2float_rn(xout), y2 = __double2float_rn(yout);
+        int status = KLT_TRACKED, iteration = 0;
+        const float fhw = (float)hw, fhh = (float)hh, fnc = (float)nc, fnr = (float)nr;
+        while (true) {
+            if (__fsub_rn(x2, fhw) < 0.f || __fsub_rn(fnc, __fadd_rn(x2, fhw)) < 1.001f ||
+                __fsub_rn(y2, fhh) < 0.f || __fsub_rn(fnr, __fadd_rn(y2, fhh)) < 1.001f) { status = KLT_OOB; break; }
+            const int ix = (int)x2, iy = (int)y2;
+            const float ax = __double2float_rn(__dsub_rn((double)x2, (double)ix));
+            const float ay = __double2float_rn(__dsub_rn((double)y2, (double)iy));
+            for (int k = lane; k < n; k += 32) {
+                const int j = k / A.w, i = k - j * A.w;
+                const size_t o = (size_t)(iy + j - hh) * pitch + (ix + i - hw);
+                const float diff = __fsub_rn(T[k], bilerp_ref(I2 + o, pitch, ax, ay));       // pyx:61-88
+                const float gx = __fadd_rn(Tgx[k], bilerp_ref(GX2 + o, pitch, ax, ay));      // -jacobian[:,0], pyx:107-128
+                const float gy = __fadd_rn(Tgy[k], bilerp_ref(GY2 + o, pitch, ax, ay));
+                S[k] = __fmul_rn(gx, gx);
+                S[n + k] = __fmul_rn(gx, gy);
+                S[2 * n + k] = __fmul_rn(gy, gy);
+                S[3 * n + k] = __fmul_rn(diff, gx);
+                S[4 * n + k] = __fmul_rn(diff, gy);
+            }
+            __syncwarp();
+            float acc = 0.f;                      // lanes 0..4: one sequential float32 sum each (pyx:246-305)
+            if (lane < 5) {
+                const float *s = S + lane * n;
+#pragma unroll 7
+                for (int k = 0; k < n; k++) acc = __fadd_rn(acc, s[k]);
+            }
+            __syncwarp();
+            const float gxx = __shfl_sync(0xffffffffu, acc, 0), gxy = __shfl_sync(0xffffffffu, acc, 1),
+                        gyy = __shfl_sync(0xffffffffu, acc, 2);
+            const float ex = __fmul_rn(__shfl_sync(0xffffffffu, acc, 3), A.step_factor),
+                        ey = __fmul_rn(__shfl_sync(0xffffffffu, acc, 4), A.step_factor);
+            const float det = __fsub_rn(__fmul_rn(gxx, gyy), __fmul_rn(gxy, gxy));            // pyx:318-340
+            if (det < A.small_det) { status = KLT_SMALL_DET; break; }
+            const float dx = __fdiv_rn(__fsub_rn(__fmul_rn(gyy, ex), __fmul_rn(gxy, ey)), det);
+            const float dy = __fdiv_rn(__fsub_rn(__fmul_rn(gxx, ey), __fmul_rn(gxy, ex)), det);
+            x2 = __fadd_rn(x2, dx); y2 = __fadd_rn(y2, dy);
+            iteration++;
+            if (!((fabsf(dx) >= A.th || fabsf(dy) >= A.th) && iteration < A.max_iterations)) break;
+        }
+        my_iters += iteration;
+
+        // ---- back in _trackFeature (trackFeatures.py:108-136): doubles, hw = width/2 ----
+        const double x2d = (double)x2, y2d = (double)y2, hwd = A.w / 2.0, hhd = A.h / 2.0;
+        if (__dsub_rn(x2d, hwd) < 0.0 || __dsub_rn((double)nc, __dadd_rn(x2d, hwd)) < 1.001 ||
+            __dsub_rn(y2d, hhd) < 0.0 || __dsub_rn((double)nr, __dadd_rn(y2d, hhd)) < 1.001) status = KLT_OOB;
+        if (status == KLT_TRACKED && A.has_max_residue) {
+            const int ix = (int)x2, iy = (int)y2;
+            const float ax = __double2float_rn(__dsub_rn((double)x2, (double)ix));
+            const float ay = __double2float_rn(__dsub_rn((double)y2, (double)iy));
+            for (int k = lane; k < n; k += 32) {
+                const int j = k / A.w, i = k - j * A.w;
+                const size_t o = (size_t)(iy + j - hh) * pitch + (ix + i - hw);
+                S[k] = fabsf(__fsub_rn(T[k], bilerp_ref(I2 + o, pitch, ax, ay)));
+            }
+            __syncwarp();
+            float res = 0.f;
+            if (lane == 0) res = __fdiv_rn(np_pairwise_sum(S, n), (float)n);
+            res = __shfl_sync(0xffffffffu, res, 0);
+            if (res > A.max_residue) status = KLT_LARGE_RESIDUE;
+            __syncwarp();
+        }
+        xout = x2d; yout = y2d;
+        if (A.retain) st = KLT_TRACKED;
+        else if (status == KLT_SMALL_DET || status == KLT_OOB || status == KLT_LARGE_RESIDUE) st = status;
+        else if (iteration >= A.max_iterations) st = KLT_MAX_ITERATIONS;
+        else st = KLT_TRACKED;
+        if (st == KLT_SMALL_DET || st == KLT_OOB) break;                                     // :284-285
+    }
+
+    if (lane == 0) {
+        if (my_iters) atomicAdd(iters_total, (unsigned long long)my_iters);
+        if (st == KLT_INTERNAL_ASSERT) return;   // host raises; feature left untouched
+        const int W0 = A.p1.lv[0].w, H0 = A.p1.lv[0].h;
+        const bool oob = xout < A.borderx || xout > __dsub_rn((double)(W0 - 1), A.borderx) || yout < A.bordery ||
+                         yout > __dsub_rn((double)(H0 - 1), A.bordery);                      // _outOfBounds :140-141
+        if (st == KLT_OOB || oob) { xs[f] = -1.0; ys[f] = -1.0; vals[f] = KLT_OOB; }
+        else if (st == KLT_SMALL_DET || st == KLT_LARGE_RESIDUE || st == KLT_MAX_ITERATIONS) { xs[f] = -1.0; ys[f] = -1.0; vals[f] = st; }
+        else { xs[f] = xout; ys[f] = yout; vals[f] = KLT_TRACKED; }
+    }
+}
+
+int klt_launch_track(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const klt_pyr *p2, int n_per_image,
+                     double *x_dev, double *y_dev, int32_t *val_dev, unsigned long long *iters_dev, int *assert_dev) {
+    TrackArgs A;
+    A.p1 = *p1; A.p2 = *p2;
+    A.w = p->window_width; A.h = p->window_height;
+    A.n_levels = p->n_levels; A.ss = p->subsampling;
+    A.max_iterations = p->max_iterations;
+    A.small_det = p->min_determinant; A.th = p->min_displacement; A.step_factor = p->step_factor;
+    A.has_max_residue = p->has_max_residue; A.max_residue = p->max_residue;
+    A.retain = p->retain_trackers;
+    A.borderx = p->borderx; A.bordery = p->bordery;
+    A.n_per_image = n_per_image; A.total = n_per_image * p1->batch;
+    if (A.total <= 0) return KLT_OK;
+    const int n = A.w * A.h;
+    int warps = 4;
+    size_t smem = (size_t)warps * 8 * n * sizeof(float);
+    while (smem > 200 * 1024 && warps > 1) { warps /= 2; smem = (size_t)warps * 8 * n * sizeof(float); }
+    if (smem > 200 * 1024) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "tracking window %dx%d too large", A.w, A.h);
+    KLT_CUDA(ctx, cudaFuncSetAttribute(lk_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const int blocks = (A.total + warps - 1) / warps;
+    lk_track_kernel<<<blocks, warps * 32, smem, ctx->stream>>>(A, x_dev, y_dev, val_dev, iters_dev, assert_dev);
+    KLT_CHECK_LAUNCH(ctx);
+    return KLT_OK;
+}
+
+// trackFeaturesUtils.extractImagePatchSlow (pyx:14-18) for operator-level parity tests.
+__global__ void extract_patch_kernel(const float *__restrict__ img, int pitch, int nc, int nr, float x, float y,
+                                     int height, int width, float *__restrict__ out, int *__restrict__ ok) {
+    const int ix = (int)x, iy = (int)y, hw = width / 2, hh = height / 2;
+    if (!(ix - hw >= 0 && iy - hh >= 0 && ix + hw + 2 <= nc && iy + hh + 2 <= nr)) {
+        if (threadIdx.x == 0) *ok = 0;
+        return;
+    }
+    if (threadIdx.x == 0) *ok = 1;
+    const float ax = __double2float_rn(__dsub_rn((double)x, (double)ix));
+    const float ay = __double2float_rn(__dsub_rn((double)y, (double)iy));
+    for (int k = threadIdx.x; k < width * height; k += blockDim.x) {
+        const int j = k / width, i = k - j * width;
+        out[k] = bilerp_ref(img + (size_t)(iy + j - hh) * pitch + (ix + i - hw), pitch, ax, ay);
+    }
+}
+
+int klt_launch_extract_patch(klt_ctx *ctx, const float *img, size_t pitch, int w, int h, float x, float y, int height,
+                             int width, float *out_dev, int *ok_dev) {
+    extract_patch_kernel<<<1, 128, 0, ctx->stream>>>(img, (int)pitch, w, h, x, y, height, width, out_dev, ok_dev);
+    KLT_CHECK_LAUNCH(ctx);
+    return KLT_OK;
+}

@@ -1,0 +1,169 @@
+"""Drop-in for the reference's selectGoodFeatures.py.  KLTSelectGoodFeatures(tc, img, nFeatures) keeps its
+signature and return convention (a fresh list of KLT_Feature); the work -- smoothing, gradients, summed-area
+tables, min-eigenvalue map, descending sort and greedy minimum-distance suppression -- runs on the GPU
+(klt_pyr_build_u8 + klt_select_good_features)."""
+from __future__ import print_function
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from . import config
+from . import convolve
+from .klt import KLT_Feature, KLTCountRemainingFeatures, kltState, _fix_window
+from .error import KLTError, KLTWarning
+from .klt_util import KLTComputeSmoothSigma
+
+
+class selectionMode:
+    SELECTING_ALL = 1
+    REPLACING_SOME = 2
+
+
+KLT_verbose = 1
+
+
+def _image_size(img):
+    if isinstance(img, np.ndarray):
+        return img.shape[1], img.shape[0]
+    return img.size
+
+
+def _image_u8_or_f32(img):
+    """PIL 'L' images and uint8 arrays go to the GPU as bytes (img.convert("F") is exact for them);
+    anything else is converted to float32 the way the reference does (selectGoodFeatures.py:190)."""
+    if isinstance(img, np.ndarray):
+        a = img
+    elif getattr(img, "mode", None) == "L":
+        a = np.asarray(img)
+    else:
+        a = np.asarray(img.convert("F"))
+    if a.dtype == np.uint8:
+        return np.ascontiguousarray(a), True
+    return np.ascontiguousarray(a, np.float32), False
+
+
+def make_params(tc):
+    p = _capi.Params()
+    p.window_width, p.window_height = int(tc.window_width), int(tc.window_height)
+    p.n_levels, p.subsampling = int(tc.nPyramidLevels), int(tc.subsampling)
+    p.borderx, p.bordery = float(tc.borderx), float(tc.bordery)
+    p.mindist, p.min_eigenvalue = int(tc.mindist), int(tc.min_eigenvalue)
+    p.n_skipped_pixels = int(tc.nSkippedPixels)
+    p.max_iterations = int(tc.max_iterations)
+    p.min_determinant, p.min_displacement, p.step_factor = tc.min_determinant, tc.min_displacement, tc.step_factor
+    p.has_max_residue = 0 if tc.max_residue is None else 1
+    p.max_residue = 0.0 if tc.max_residue is None else tc.max_residue
+    p.retain_trackers = 1 if tc.retainTrackers else 0
+    p.lighting_insensitive = 1 if tc.lighting_insensitive else 0
+    return p
+
+
+def _reset_affine(feat):
+    feat.aff_img = None
+    feat.aff_img_gradx = None
+    feat.aff_img_grady = None
+    feat.aff_x = -1.0
+    feat.aff_y = -1.0
+    feat.aff_Axx = 1.0
+    feat.aff_Ayx = 0.0
+    feat.aff_Axy = 0.0
+    feat.aff_Ayy = 1.0
+
+
+def _select_on_device(tc, pyr, nFeatures, featurelist, overwriteAllFeatures):
+    """Scan + sort + _enforceMinimumDistance on level-0 gradients of `pyr` (selectGoodFeatures.py:215-246)."""
+    ctx = pyr.ctx
+    x = np.full(nFeatures, -1.0)
+    y = np.full(nFeatures, -1.0)
+    val = np.full(nFeatures, kltState.KLT_NOT_FOUND, np.int32)
+    if not overwriteAllFeatures:
+        for i, feat in enumerate(featurelist):
+            x[i], y[i], val[i] = feat.x, feat.y, feat.val
+    old_val = val.copy()
+    params = make_params(tc)
+    consumed = C.c_int64()
+    ctx.check(_capi.lib().klt_select_good_features(ctx.handle, C.byref(params), pyr.handle, 0, None, None, 0, 0,
+                                                  nFeatures, 0 if overwriteAllFeatures else 1, x.ctypes.data,
+                                                  y.ctypes.data, val.ctypes.data, C.byref(consumed)))
+    xi = x.astype(np.int32)
+    yi = y.astype(np.int32)
+    for i, feat in enumerate(featurelist):
+        if overwriteAllFeatures:
+            if val[i] >= 0:
+                feat.x, feat.y, feat.val = xi[i], yi[i], int(val[i])       # np.int32 / int, quirk Q13
+            else:
+                feat.x, feat.y, feat.val = -1, -1, kltState.KLT_NOT_FOUND   # C-KLT's fill (quirk Q6)
+            _reset_affine(feat)
+        elif old_val[i] < 0 and val[i] >= 0:
+            feat.x, feat.y, feat.val = xi[i], yi[i], int(val[i])
+            _reset_affine(feat)
+    return featurelist
+
+
+def _selection_pyramid(tc, img):
+    """float image -> (optional) smooth -> gradients, as a 1-level device pyramid (selectGoodFeatures.py:181-197)."""
+    ctx = _capi.default_ctx()
+    ncols, nrows = _image_size(img)
+    a, is_u8 = _image_u8_or_f32(img)
+    taps = _capi.Taps()
+    one = _capi.Kernel1D.from_taps([1.0])
+    taps.pyramid = one
+    if tc.smoothBeforeSelecting:
+        gauss, _ = convolve._kernels_for_smoothing(KLTComputeSmoothSigma(tc))
+        taps.smooth = _capi.Kernel1D.from_taps(gauss)
+    else:
+        taps.smooth = one
+    g, d = convolve._kernels_for_gradients(tc.grad_sigma)
+    taps.grad_gauss, taps.grad_deriv = _capi.Kernel1D.from_taps(g), _capi.Kernel1D.from_taps(d)
+    pyr = ctx.scratch_pyramid(ncols, nrows, 1, 2, 1, slot="select")
+    prec = config.select_precision_code()
+    if tc.smoothBeforeSelecting:
+        if is_u8:
+            pyr.build_u8(a, taps, prec)
+        else:
+            pyr.build_f32(a, taps, prec, already_smoothed=False)
+    else:
+        pyr.build_f32(np.ascontiguousarray(a, np.float32), taps, prec, already_smoothed=True)
+    return pyr
+
+
+def _KLTSelectGoodFeatures(tc, img, nFeatures, mode, featurelist=None):
+    overwriteAllFeatures = (mode == selectionMode.SELECTING_ALL)
+    if featurelist is None:
+        featurelist = [KLT_Feature() for i in range(nFeatures)]
+    _fix_window(tc, "Tracking context")
+    if mode == selectionMode.REPLACING_SOME and tc.sequentialMode and tc.pyramid_last is not None:
+        pyr = tc.pyramid_last.pyr          # level-0 gradients of the last tracked image (selectGoodFeatures.py:176-179)
+    else:
+        pyr = _selection_pyramid(tc, img)
+    if tc.mindist < 0:
+        KLTWarning("(_KLTSelectGoodFeatures) Tracking context field tc.mindist is negative ({0}); setting to zero".format(tc.mindist))
+        tc.mindist = 0
+    return _select_on_device(tc, pyr, len(featurelist), featurelist, overwriteAllFeatures)
+
+
+def KLTSelectGoodFeatures(tc, img, nFeatures):
+    ncols, nrows = _image_size(img)
+    if KLT_verbose >= 1:
+        print("(KLT) Selecting the {0} best features from a {1} by {2} image...  ".format(nFeatures, ncols, nrows))
+    fl = _KLTSelectGoodFeatures(tc, img, nFeatures, selectionMode.SELECTING_ALL)
+    if KLT_verbose >= 1:
+        print("\n\t{0} features found.\n".format(KLTCountRemainingFeatures(fl)))
+        if tc.writeInternalImages:
+            print("\tWrote images to 'kltimg_sgfrlf*.pgm'.\n")
+    return fl
+
+
+def KLTReplaceLostFeatures(tc, img, fl):
+    """C-KLT's KLTReplaceLostFeatures: refill the slots of lost features (val < 0) with the best new features that
+    keep mindist from the survivors.  The reference has only the mode constant (selectGoodFeatures.py:11-13) and
+    _enforceMinimumDistance(..., overwriteAllFeatures=False), which this follows."""
+    nLost = len(fl) - KLTCountRemainingFeatures(fl)
+    ncols, nrows = _image_size(img)
+    if KLT_verbose >= 1:
+        print("(KLT) Attempting to replace {0} features in a {1} by {2} image...  ".format(nLost, ncols, nrows))
+    if nLost > 0:
+        _KLTSelectGoodFeatures(tc, img, len(fl), selectionMode.REPLACING_SOME, fl)
+    if KLT_verbose >= 1:
+        print("\n\t{0} features replaced.".format(nLost - len(fl) + KLTCountRemainingFeatures(fl)))

@@ -1,0 +1,156 @@
+"""Drop-in for the reference's trackFeatures.py.  KLTTrackFeatures(tc, img1, img2, featurelist) keeps its
+signature, mutates the feature list in place and returns None; pyramids and the Lucas-Kanade loop run on the GPU
+(klt_pyr_build_u8 + klt_track_features)."""
+from __future__ import print_function
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from . import config
+from . import convolve
+from . import selectGoodFeatures as _sgf
+from .klt import KLTCountRemainingFeatures, kltState, _fix_window
+from .error import KLTError, KLTWarning
+from .klt_util import KLTComputeSmoothSigma
+from .pyramid import DevicePyramid
+from .selectGoodFeatures import KLT_verbose, make_params, _image_size, _image_u8_or_f32
+
+
+def _outOfBounds(x, y, ncols, nrows, borderx, bordery):
+    return x < borderx or x > ncols - 1 - borderx or y < bordery or y > nrows - 1 - bordery
+
+
+def _taps_for_one_image(tc):
+    """Replays the kernel-cache lookups ComputeImagePyramids performs for ONE image (trackFeatures.py:165-172):
+    smooth, then (L-1) pyramid smooths, then L gradient calls.  A stale-cache hit (convolve.py:236,258) therefore
+    yields the same taps the reference would use."""
+    taps = _capi.Taps()
+    gauss, _ = convolve._kernels_for_smoothing(KLTComputeSmoothSigma(tc))
+    taps.smooth = _capi.Kernel1D.from_taps(gauss)
+    taps.pyramid = _capi.Kernel1D.from_taps([1.0])
+    for _i in range(1, tc.nPyramidLevels):
+        gauss, _ = convolve._kernels_for_smoothing(int(tc.subsampling) * tc.pyramid_sigma_fact)
+        taps.pyramid = _capi.Kernel1D.from_taps(gauss)
+    for _i in range(tc.nPyramidLevels):
+        g, d = convolve._kernels_for_gradients(tc.grad_sigma)
+    taps.grad_gauss, taps.grad_deriv = _capi.Kernel1D.from_taps(g), _capi.Kernel1D.from_taps(d)
+    return taps
+
+
+class _PyramidSet(object):
+    """The three pyramids of one image on the device + the KLTPyramid-like views the reference API exposes."""
+
+    def __init__(self, pyr):
+        self.pyr = pyr
+        self.img = DevicePyramid(pyr, 0)
+        self.gradx = DevicePyramid(pyr, 1)
+        self.grady = DevicePyramid(pyr, 2)
+
+
+def _build_pyramids(tc, img, pyr):
+    a, is_u8 = _image_u8_or_f32(img)
+    taps = _taps_for_one_image(tc)
+    prec = config.track_precision_code()
+    if is_u8:
+        pyr.build_u8(a, taps, prec)
+    else:
+        pyr.build_f32(a, taps, prec, already_smoothed=False)
+    return _PyramidSet(pyr)
+
+
+def ComputeImagePyramids(tc, img1, img2):
+    """-> pyramid1, pyramid1_gradx, pyramid1_grady, pyramid2, pyramid2_gradx, pyramid2_grady (trackFeatures.py:146-196).
+    The pyramids live on the device; `.img[i]` downloads a level on demand."""
+    ctx = _capi.default_ctx()
+    ncols, nrows = _image_size(img1)
+    L, ss = int(tc.nPyramidLevels), int(float(tc.subsampling))
+    if tc.sequentialMode and tc.pyramid_last is not None:
+        pyramid1 = tc.pyramid_last
+        if pyramid1.ncols[0] != ncols or pyramid1.nrows[0] != nrows:
+            KLTError("(KLTTrackFeatures) Size of incoming image ({0} by {1}) is different from size of previous image ({2} by {3})".format(
+                ncols, nrows, pyramid1.ncols[0], pyramid1.nrows[0]))
+        assert tc.pyramid_last_gradx is not None
+        assert tc.pyramid_last_grady is not None
+        set1 = _PyramidSet.__new__(_PyramidSet)
+        set1.pyr, set1.img, set1.gradx, set1.grady = pyramid1.pyr, pyramid1, tc.pyramid_last_gradx, tc.pyramid_last_grady
+        # the second image must not overwrite the pyramid that is still in use
+        pyr2 = _capi.Pyramid(ctx, ncols, nrows, L, ss, 1) if not hasattr(tc, "_klt_spare") or tc._klt_spare is None or \
+            (tc._klt_spare.w, tc._klt_spare.h, tc._klt_spare.n_levels, tc._klt_spare.subsampling) != (ncols, nrows, L, ss) \
+            else tc._klt_spare
+    else:
+        if tc.sequentialMode:
+            pyr1 = _capi.Pyramid(ctx, ncols, nrows, L, ss, 1)
+            pyr2 = _capi.Pyramid(ctx, ncols, nrows, L, ss, 1)
+        else:
+            pyr1 = ctx.scratch_pyramid(ncols, nrows, L, ss, 1, slot="track1")
+            pyr2 = ctx.scratch_pyramid(ncols, nrows, L, ss, 1, slot="track2")
+        set1 = _build_pyramids(tc, img1, pyr1)
+    set2 = _build_pyramids(tc, img2, pyr2)
+    return set1.img, set1.gradx, set1.grady, set2.img, set2.gradx, set2.grady
+
+
+def _features_to_arrays(featurelist):
+    n = len(featurelist)
+    x = np.empty(n)
+    y = np.empty(n)
+    val = np.empty(n, np.int32)
+    for i, feat in enumerate(featurelist):
+        v = feat.val
+        val[i] = v
+        if v >= 0:
+            x[i], y[i] = feat.x, feat.y
+        else:
+            x[i] = y[i] = -1.0
+    return x, y, val
+
+
+def _clear_affine(feat):
+    feat.aff_img = None
+    feat.aff_img_gradx = None
+    feat.aff_img_grady = None
+
+
+def KLTTrackFeatures(tc, img1, img2, featurelist):
+    assert _image_size(img1) == _image_size(img2)
+    ncols, nrows = _image_size(img1)
+    if KLT_verbose >= 1:
+        print("(KLT) Tracking {0} features in a {1} by {2} image...  ".format(
+            KLTCountRemainingFeatures(featurelist), ncols, nrows))
+    _fix_window(tc, "Tracking context")
+    if tc.lighting_insensitive:
+        raise Exception("Not implemented")                      # trackFeaturesUtils.pyx:435
+    if tc.affineConsistencyCheck >= 0:
+        # the reference dies here with NameError: _KLTCreateFloatImage is undefined (trackFeatures.py:356)
+        raise NameError("name '_KLTCreateFloatImage' is not defined (affine consistency check is not implemented in the reference)")
+
+    pyramid1, pyramid1_gradx, pyramid1_grady, pyramid2, pyramid2_gradx, pyramid2_grady = ComputeImagePyramids(tc, img1, img2)
+    ctx = pyramid1.pyr.ctx
+    x, y, val = _features_to_arrays(featurelist)
+    was_live = val >= 0
+    params = make_params(tc)
+    ctx.check(_capi.lib().klt_track_features(ctx.handle, C.byref(params), pyramid1.pyr.handle, pyramid2.pyr.handle,
+                                            len(featurelist), x.ctypes.data, y.ctypes.data, val.ctypes.data, None))
+    xs, ys, vals = x.tolist(), y.tolist(), val.tolist()
+    for i, feat in enumerate(featurelist):
+        if not was_live[i]:
+            continue                                             # trackFeatures.py:253
+        v = vals[i]
+        if v == kltState.KLT_TRACKED:
+            feat.x, feat.y, feat.val = xs[i], ys[i], kltState.KLT_TRACKED
+        else:
+            feat.x, feat.y, feat.val = -1.0, -1.0, v
+            if hasattr(feat, "aff_img"):
+                _clear_affine(feat)
+
+    if tc.sequentialMode:
+        if tc.pyramid_last is not None and tc.pyramid_last is not pyramid2:
+            tc._klt_spare = tc.pyramid_last.pyr                  # recycle the older pyramid's device memory
+        tc.pyramid_last = pyramid2
+        tc.pyramid_last_gradx = pyramid2_gradx
+        tc.pyramid_last_grady = pyramid2_grady
+
+    if KLT_verbose >= 1:
+        print("\n\t{0} features successfully tracked.".format(KLTCountRemainingFeatures(featurelist)))
+        if tc.writeInternalImages:
+            print("\tWrote images to 'kltimg_tf*.pgm'.")

@@ -1,0 +1,69 @@
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return np.load(os.path.join(GOLDEN_DIR, "reference_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def img01():
+    from PIL import Image
+    return (np.array(Image.open(os.path.join(GOLDEN_DIR, "img0.pgm"))),
+            np.array(Image.open(os.path.join(GOLDEN_DIR, "img1.pgm"))))
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import klt_oracle
+    klt_oracle.lib()
+    return klt_oracle
+
+
+def load_reference():
+    """The unmodified reference from oracle/_ref (sourceless .pyc + Cython .so, see oracle/build_ref.py), or None."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "klt.pyc")):
+        return None
+    import importlib
+    warnings.simplefilter("ignore")
+    saved = list(sys.path)
+    sys.path.insert(0, ref_dir)
+    try:
+        mods = {}
+        for name in ("error", "klt_util", "convolve", "klt", "pyramid", "goodFeaturesUtils", "trackFeaturesUtils",
+                     "selectGoodFeatures", "trackFeatures"):
+            mods[name] = importlib.import_module(name)
+    finally:
+        sys.path[:] = saved
+    mods["selectGoodFeatures"].KLT_verbose = 0
+    mods["trackFeatures"].KLT_verbose = 0
+    return mods
+
+
+@pytest.fixture(scope="session")
+def reference():
+    mods = load_reference()
+    if mods is None:
+        pytest.skip("oracle/_ref not built (python oracle/build_ref.py needs /root/reference)")
+    return mods
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx():
+    from pyfeaturetrack_b200 import _capi
+    return _capi.default_ctx()      # raises loudly if the CUDA library or the GPU is missing

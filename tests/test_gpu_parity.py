@@ -1,0 +1,358 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI (ctypes shims in
+pyfeaturetrack_b200), against the CPU oracle on the same seeded inputs and against the reference's golden vectors.
+
+Bars (BASELINE.json north_star): STRICT mode is bit-exact everywhere (images, eigen map, selection, positions, status
+codes).  FAST mode: images within 1e-5 relative-to-max, positions within 1e-3 px, status codes >= 99.9 %."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5        # images, relative to the image's max |value|
+POS_TOL = 1e-3        # px
+STATUS_MATCH = 0.999
+
+
+def P(oracle, **kw):
+    return oracle.Params(**kw)
+
+
+def fl(golden, key):
+    a = golden[key]
+    return a[0], a[1], a[2].astype(np.int32)
+
+
+def make_tc(**kw):
+    from pyfeaturetrack_b200 import klt
+    tc = klt.KLT_TrackingContext()
+    for k, v in kw.items():
+        setattr(tc, k, v)
+    tc.KLTUpdateTCBorder()
+    return tc
+
+
+def fl_arrays(featurelist):
+    return (np.array([float(f.x) for f in featurelist]), np.array([float(f.y) for f in featurelist]),
+            np.array([int(f.val) for f in featurelist], np.int32))
+
+
+def assert_features_equal(got, want):
+    assert np.array_equal(np.asarray(got[2], np.int64), np.asarray(want[2], np.int64))
+    assert np.array_equal(np.asarray(got[0], np.float64), np.asarray(want[0], np.float64))
+    assert np.array_equal(np.asarray(got[1], np.float64), np.asarray(want[1], np.float64))
+
+
+def assert_features_close(got, want):
+    gv, wv = np.asarray(got[2]), np.asarray(want[2])
+    match = np.mean(gv == wv)
+    assert match >= STATUS_MATCH, "status match %.4f" % match
+    both = (gv == 0) & (wv == 0)
+    err = np.maximum(np.abs(np.asarray(got[0])[both] - np.asarray(want[0])[both]),
+                     np.abs(np.asarray(got[1])[both] - np.asarray(want[1])[both]))
+    assert err.size == 0 or err.max() <= POS_TOL, "max position error %g px" % err.max()
+
+
+@pytest.fixture(autouse=True)
+def _quiet():
+    from pyfeaturetrack_b200 import selectGoodFeatures, trackFeatures, config
+    selectGoodFeatures.KLT_verbose = 0
+    trackFeatures.KLT_verbose = 0
+    config.set_precision(track="fast", select="strict", operator="strict")
+    yield
+
+
+# ---- convolution operators -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sigma", [0.7, 1.0, 1.5, 1.8, 3.6, 7.2])
+@pytest.mark.parametrize("shape", [(77, 123), (240, 320), (33, 40)])
+def test_smooth_and_gradients(gpu_ctx, oracle, sigma, shape):
+    from pyfeaturetrack_b200 import convolve, config
+    rng = np.random.default_rng(int(sigma * 10) + shape[0])
+    img = (rng.random(shape) * 255).astype(np.float32)
+    cache = oracle.KernelCache()
+    want_s = oracle.smooth(img, sigma, cache)
+    want_gx, want_gy = oracle.gradients(img, sigma, cache)
+    convolve._computeKernels(sigma)
+    config.set_precision(operator="strict")
+    assert np.array_equal(convolve.KLTComputeSmoothedImage(img, sigma), want_s)
+    gx, gy = convolve.KLTComputeGradients(img, sigma)
+    assert np.array_equal(gx, want_gx) and np.array_equal(gy, want_gy)
+    config.set_precision(operator="fast")
+    s = convolve.KLTComputeSmoothedImage(img, sigma)
+    gx, gy = convolve.KLTComputeGradients(img, sigma)
+    assert np.abs(s - want_s).max() <= REL_TOL * np.abs(want_s).max()
+    assert np.abs(gx - want_gx).max() <= REL_TOL * max(np.abs(want_gx).max(), np.abs(want_s).max())
+    assert np.abs(gy - want_gy).max() <= REL_TOL * max(np.abs(want_gy).max(), np.abs(want_s).max())
+
+
+def test_golden_images(gpu_ctx, golden, img01):
+    from pyfeaturetrack_b200 import convolve, pyramid
+    convolve._computeKernels(0.7)
+    sm = convolve.KLTComputeSmoothedImage(img01[0].astype(np.float32), 0.7)
+    assert np.array_equal(sm, golden["A_smooth"])
+    convolve._computeKernels(1.0)
+    gx, gy = convolve.KLTComputeGradients(sm, 1.0)
+    assert np.array_equal(gx, golden["A_gradx"]) and np.array_equal(gy, golden["A_grady"])
+    p = pyramid.KLTPyramid(320, 240, 4, 2)
+    p.Compute(sm, 0.9)
+    assert p.img[0] is sm
+    assert np.array_equal(p.img[1], golden["A_pyr1"])
+    assert p.ncols == [320, 80.0] and p.nrows == [240, 60.0]
+
+
+def test_general_kernel_and_wide_kernel(gpu_ctx, oracle):
+    """Non-symmetric taps take SciPy's general branch; a kernel wider than the image exercises repeated reflection."""
+    from pyfeaturetrack_b200 import convolve
+    rng = np.random.default_rng(3)
+    img = (rng.random((20, 31)) * 100).astype(np.float32)
+    hk = rng.random(7)
+    vk = rng.random(5)
+    assert np.array_equal(convolve._convolveSeparate(img, hk, vk), oracle.conv_separable(img, hk, vk))
+    g, d = oracle.compute_kernels(7.2)       # 43 / 51 taps on a 20-row image
+    assert np.array_equal(convolve._convolveSeparate(img, d, g), oracle.conv_separable(img, d, g))
+
+
+# ---- pyramids ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [dict(shape=(240, 320), L=2, ss=4), dict(shape=(480, 640), L=3, ss=2),
+                                 dict(shape=(270, 350), L=2, ss=8), dict(shape=(203, 301), L=3, ss=2),
+                                 dict(shape=(120, 160), L=1, ss=2)])
+def test_pyramid_build_u8(gpu_ctx, oracle, cfg):
+    from pyfeaturetrack_b200 import _capi, trackFeatures
+    rng = np.random.default_rng(cfg["L"] * 7 + cfg["ss"])
+    H, W = cfg["shape"]
+    batch = 3
+    frames = (rng.random((batch, H, W)) * 255).astype(np.uint8)
+    p = P(oracle, nPyramidLevels=cfg["L"], subsampling=cfg["ss"])
+    tc = make_tc(nPyramidLevels=cfg["L"], subsampling=cfg["ss"])
+    pyr = _capi.Pyramid(gpu_ctx, W, H, cfg["L"], cfg["ss"], batch)
+    for prec in (_capi.PRECISION_STRICT, _capi.PRECISION_FAST):
+        pyr.build_u8(frames, trackFeatures._taps_for_one_image(tc), prec)
+        for b in range(batch):
+            want = oracle.image_pyramids(p, frames[b])
+            for which in range(3):
+                for lvl in range(cfg["L"]):
+                    got = pyr.download(which, lvl, b)
+                    ref = want[which][lvl]
+                    assert got.shape == ref.shape
+                    if prec == _capi.PRECISION_STRICT:
+                        assert np.array_equal(got, ref), (b, which, lvl)
+                    else:
+                        assert np.abs(got - ref).max() <= REL_TOL * 255.0, (b, which, lvl)
+    pyr.close()
+
+
+# ---- selection -----------------------------------------------------------------------------------------------------
+def test_scan_bit_exact(gpu_ctx, oracle, golden):
+    from pyfeaturetrack_b200 import goodFeaturesUtils
+    px, py, pv = goodFeaturesUtils.ScanImageForGoodFeatures(golden["A_gradx"], golden["A_grady"], 30.0, 30.0, 3.5, 3.5, 0)
+    assert np.array_equal(np.array(pv, np.float32).reshape(180, 260), golden["A_scan_val"])
+    assert list(px[:5]) == list(golden["A_scan_x0"]) and list(py[:5]) == list(golden["A_scan_y0"])
+    assert isinstance(px[0], np.int32) and isinstance(pv[0], float)
+    rng = np.random.default_rng(1)
+    gx = (rng.standard_normal((150, 211)) * 20).astype(np.float32)
+    gy = (rng.standard_normal((150, 211)) * 20).astype(np.float32)
+    for (b, hw, skip) in ((8, 3, 0), (12, 7, 1), (9, 2, 3)):
+        xs, ys, val = goodFeaturesUtils.scan_values(gx, gy, b, b, hw, hw, skip)
+        want, wxs, wys = oracle.scan_good_features(gx, gy, b, b, hw, hw, skip)
+        assert np.array_equal(xs, wxs) and np.array_equal(ys, wys) and np.array_equal(val, want)
+    with pytest.raises(ValueError):
+        goodFeaturesUtils.ScanImageForGoodFeatures(gx.astype(np.float64), gy, 8, 8, 3, 3, 0)
+
+
+@pytest.mark.parametrize("n", [50, 100])
+def test_config_A_dropin_api(gpu_ctx, golden, img01, n):
+    """example1.py's flow through the drop-in modules, PIL images in, feature list out."""
+    from PIL import Image
+    from pyfeaturetrack_b200 import selectGoodFeatures as sgf, trackFeatures as tf, config
+    config.set_precision(track="strict")
+    tc = make_tc(max_residue=10.0)
+    i0, i1 = Image.fromarray(img01[0]), Image.fromarray(img01[1])
+    featurelist = sgf.KLTSelectGoodFeatures(tc, i0, n)
+    assert_features_equal(fl_arrays(featurelist), fl(golden, "A_sel%d" % n))
+    assert isinstance(featurelist[0].x, np.int32) and isinstance(featurelist[0].val, int)
+    assert featurelist[0].aff_Axx == 1.0 and featurelist[0].aff_img is None
+    assert tf.KLTTrackFeatures(tc, i0, i1, featurelist) is None
+    assert_features_equal(fl_arrays(featurelist), fl(golden, "A_trk%d" % n))
+    assert isinstance(featurelist[0].x, float)
+    tf.KLTTrackFeatures(tc, i1, i0, featurelist)
+    assert_features_equal(fl_arrays(featurelist), fl(golden, "A_trk%d_back" % n))
+    # fast pyramids: tolerance instead of bit equality
+    config.set_precision(track="fast")
+    featurelist = sgf.KLTSelectGoodFeatures(tc, i0, n)
+    tf.KLTTrackFeatures(tc, i0, i1, featurelist)
+    assert_features_close(fl_arrays(featurelist), fl(golden, "A_trk%d" % n))
+
+
+def test_selection_variants(gpu_ctx, golden, img01):
+    from pyfeaturetrack_b200 import selectGoodFeatures as sgf
+    tc = make_tc(nSkippedPixels=2, mindist=15, min_eigenvalue=500)
+    assert_features_equal(fl_arrays(sgf.KLTSelectGoodFeatures(tc, img01[0], 40)), fl(golden, "A_sel40_skip2"))
+    tc = make_tc(smoothBeforeSelecting=False)
+    assert_features_equal(fl_arrays(sgf.KLTSelectGoodFeatures(tc, img01[0], 40)), fl(golden, "A_sel40_nosmooth"))
+    # flat image: candidates run out (quirk Q6) -> C-KLT fill
+    tc = make_tc()
+    fl_ = sgf.KLTSelectGoodFeatures(tc, np.full((120, 160), 77, np.uint8), 10)
+    assert all(f.val == -1 and f.x == -1 and f.y == -1 for f in fl_)
+
+
+def test_tracking_variants_strict(gpu_ctx, golden, img01):
+    from pyfeaturetrack_b200 import selectGoodFeatures as sgf, trackFeatures as tf, config
+    config.set_precision(track="strict")
+    tc = make_tc()
+    f = sgf.KLTSelectGoodFeatures(tc, img01[0], 60)
+    tf.KLTTrackFeatures(tc, img01[0], img01[1], f)
+    assert_features_equal(fl_arrays(f), fl(golden, "A_trk60_nores"))
+    tc = make_tc(retainTrackers=True)
+    f = sgf.KLTSelectGoodFeatures(tc, img01[0], 60)
+    tf.KLTTrackFeatures(tc, img01[0], img01[1], f)
+    assert_features_equal(fl_arrays(f), fl(golden, "A_trk60_retain"))
+
+
+def test_sequential_mode_with_replacement(gpu_ctx, golden, img01):
+    from pyfeaturetrack_b200 import selectGoodFeatures as sgf, trackFeatures as tf, config
+    config.set_precision(track="strict")
+    tc = make_tc(max_residue=10.0, sequentialMode=True)
+    f = sgf.KLTSelectGoodFeatures(tc, img01[0], 80)
+    want = golden["A_seq80"]
+    k = 0
+    for a, b in ((0, 1), (1, 0), (0, 1)):
+        tf.KLTTrackFeatures(tc, img01[a], img01[b], f)
+        assert_features_equal(fl_arrays(f), (want[k][0], want[k][1], want[k][2]))
+        k += 1
+        sgf.KLTReplaceLostFeatures(tc, img01[b], f)
+        assert_features_equal(fl_arrays(f), (want[k][0], want[k][1], want[k][2]))
+        k += 1
+    assert tc.pyramid_last.img[0].shape == (240, 320)      # NumPy view of the device pyramid on demand
+    import pickle
+    pickle.loads(pickle.dumps(f))
+    pickle.loads(pickle.dumps(tc))
+
+
+def _synth(seed, shape=(480, 640), shift=(1.7, -3.3)):
+    from pyfeaturetrack_b200 import synth
+    return synth.frame_pair(shape[0], shape[1], seed=seed, shift=shift)
+
+
+def test_synthetic_goldens(gpu_ctx, golden):
+    from pyfeaturetrack_b200 import selectGoodFeatures as sgf, trackFeatures as tf, config
+    config.set_precision(track="strict")
+    imgs = _synth(0)
+    tc = make_tc(max_residue=10.0, nPyramidLevels=3, subsampling=2)
+    f = sgf.KLTSelectGoodFeatures(tc, imgs[0], 300)
+    assert_features_equal(fl_arrays(f), fl(golden, "S640_sel300"))
+    tf.KLTTrackFeatures(tc, imgs[0], imgs[1], f)
+    assert_features_equal(fl_arrays(f), fl(golden, "S640_trk300"))
+    imgs = _synth(1)
+    tc = make_tc(window_width=15, window_height=15, nPyramidLevels=2, subsampling=4, max_residue=8.0)
+    f = sgf.KLTSelectGoodFeatures(tc, imgs[0], 200)
+    assert_features_equal(fl_arrays(f), fl(golden, "S640w15_sel200"))
+    tf.KLTTrackFeatures(tc, imgs[0], imgs[1], f)
+    assert_features_equal(fl_arrays(f), fl(golden, "S640w15_trk200"))
+    # every status code
+    imgs = _synth(2, (240, 320), (6.2, -9.4))
+    tc = make_tc(nPyramidLevels=2, subsampling=2, max_residue=5.0, max_iterations=4, min_determinant=2000.0)
+    f = sgf.KLTSelectGoodFeatures(tc, imgs[0], 150)
+    assert_features_equal(fl_arrays(f), fl(golden, "H320_sel150"))
+    tf.KLTTrackFeatures(tc, imgs[0], imgs[1], f)
+    assert_features_equal(fl_arrays(f), fl(golden, "H320_trk150"))
+    imgs = _synth(3, (240, 320))
+    tc = make_tc(nPyramidLevels=2, subsampling=2, min_determinant=3.0e7)
+    f = sgf.KLTSelectGoodFeatures(tc, imgs[0], 120)
+    tf.KLTTrackFeatures(tc, imgs[0], imgs[1], f)
+    assert_features_equal(fl_arrays(f), fl(golden, "D320_trk120"))
+
+
+def test_patch_and_assert(gpu_ctx, golden):
+    from pyfeaturetrack_b200 import trackFeaturesUtils
+    assert np.array_equal(trackFeaturesUtils.extractImagePatchSlow(golden["A_smooth"], 100.3, 57.8, 7, 7), golden["A_patch"])
+    with pytest.raises(AssertionError):
+        trackFeaturesUtils.extractImagePatchSlow(golden["A_smooth"], 2.5, 57.8, 7, 7)
+
+
+def test_feature_near_border_raises_like_reference(gpu_ctx, img01):
+    from pyfeaturetrack_b200 import klt, trackFeatures as tf
+    tc = make_tc()
+    f = klt.KLT_Feature()
+    f.x, f.y, f.val = 5.0, 100.0, 0       # window leaves the image at level 1: reference asserts (pyx:35)
+    with pytest.raises(AssertionError):
+        tf.KLTTrackFeatures(tc, img01[0], img01[1], [f])
+
+
+# ---- full-size configs against the oracle -------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [dict(name="B", shape=(1080, 1920), n=1000, L=3, ss=2, w=7),
+                                 dict(name="C", shape=(2160, 3840), n=10000, L=4, ss=2, w=7),
+                                 dict(name="E-translational", shape=(1080, 1920), n=1000, L=3, ss=2, w=15)])
+def test_full_size_configs(gpu_ctx, oracle, cfg):
+    from pyfeaturetrack_b200 import selectGoodFeatures as sgf, trackFeatures as tf, config
+    H, W = cfg["shape"]
+    imgs = _synth(0, (H, W))
+    kw = dict(nPyramidLevels=cfg["L"], subsampling=cfg["ss"], window_width=cfg["w"], window_height=cfg["w"], max_residue=10.0)
+    p = P(oracle, **kw)
+    tc = make_tc(**kw)
+    assert tc.borderx == p.borderx
+    want_sel = oracle.select_good_features(p, imgs[0], cfg["n"])
+    f = sgf.KLTSelectGoodFeatures(tc, imgs[0], cfg["n"])
+    assert_features_equal(fl_arrays(f), want_sel)
+    want_trk = oracle.track_features(p, imgs[0], imgs[1], *want_sel)[:3]
+    config.set_precision(track="strict")
+    tf.KLTTrackFeatures(tc, imgs[0], imgs[1], f)
+    assert_features_equal(fl_arrays(f), want_trk)
+    assert (want_trk[2] == 0).mean() > 0.95
+    config.set_precision(track="fast")
+    f = sgf.KLTSelectGoodFeatures(tc, imgs[0], cfg["n"])
+    tf.KLTTrackFeatures(tc, imgs[0], imgs[1], f)
+    assert_features_close(fl_arrays(f), want_trk)
+
+
+def test_batched_pairs_match_single(gpu_ctx, oracle):
+    """klt_track_pairs_u8 over a batch of independent pairs == the same pairs one by one (the multi-GPU shard unit)."""
+    from pyfeaturetrack_b200 import _capi, trackFeatures, selectGoodFeatures as sgf
+    H, W, B, n = 240, 320, 4, 64
+    tc = make_tc(nPyramidLevels=2, subsampling=2, max_residue=10.0)
+    p = P(oracle, nPyramidLevels=2, subsampling=2, max_residue=10.0)
+    f1 = np.empty((B, H, W), np.uint8)
+    f2 = np.empty((B, H, W), np.uint8)
+    xs = np.empty((B, n)); ys = np.empty((B, n)); vs = np.empty((B, n), np.int32)
+    want = []
+    for b in range(B):
+        a, c = _synth(20 + b, (H, W))
+        f1[b], f2[b] = a, c
+        sel = oracle.select_good_features(p, a, n)
+        xs[b], ys[b], vs[b] = sel
+        want.append(oracle.track_features(p, a, c, *sel)[:3])
+    taps = trackFeatures._taps_for_one_image(tc)
+    params = sgf.make_params(tc)
+    p1 = _capi.Pyramid(gpu_ctx, W, H, 2, 2, B)
+    p2 = _capi.Pyramid(gpu_ctx, W, H, 2, 2, B)
+    gpu_ctx.check(_capi.lib().klt_track_pairs_u8(gpu_ctx.handle, C.byref(params), C.byref(taps), _capi.PRECISION_STRICT,
+                                                 p1.handle, p2.handle, f1.ctypes.data, f2.ctypes.data, W, W * H, n,
+                                                 xs.ctypes.data, ys.ctypes.data, vs.ctypes.data))
+    for b in range(B):
+        assert_features_equal((xs[b], ys[b], vs[b]), want[b])
+    p1.close(); p2.close()
+
+
+def test_properties_full_size(gpu_ctx):
+    """Size-independent properties at 1080p: identity tracking, idempotent selection, linearity of the convolution."""
+    from pyfeaturetrack_b200 import selectGoodFeatures as sgf, trackFeatures as tf, convolve, config
+    imgs = _synth(4, (1080, 1920))
+    tc = make_tc(nPyramidLevels=3, subsampling=2, max_residue=10.0)
+    f = sgf.KLTSelectGoodFeatures(tc, imgs[0], 1000)
+    x0, y0, v0 = fl_arrays(f)
+    assert (v0 > 0).all()
+    d = np.maximum(np.abs(x0[:, None] - x0[None, :]), np.abs(y0[:, None] - y0[None, :]))
+    np.fill_diagonal(d, 1e9)
+    assert d.min() >= tc.mindist                      # Chebyshev min distance holds
+    assert (np.diff(v0) <= 0).all()                   # best first
+    g = sgf.KLTSelectGoodFeatures(tc, imgs[0], 1000)
+    assert_features_equal(fl_arrays(g), (x0, y0, v0))   # deterministic
+    tf.KLTTrackFeatures(tc, imgs[0], imgs[0], f)      # an image against itself: nothing moves, nothing is lost
+    x1, y1, v1 = fl_arrays(f)
+    assert (v1 == 0).all() and np.array_equal(x1, x0) and np.array_equal(y1, y0)
+    config.set_precision(operator="fast")
+    a = imgs[0].astype(np.float32)
+    b = imgs[1].astype(np.float32)
+    convolve._computeKernels(1.0)
+    sa, sb, sab = (convolve.KLTComputeSmoothedImage(z, 1.0) for z in (a, b, a + b))
+    assert np.abs(sab - (sa + sb)).max() <= 1e-4 * 510
