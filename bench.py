@@ -1,0 +1,504 @@
+#!/usr/bin/env python
+"""bench.py -- KLT hot-path throughput on B200 (contract: see the task statement / DESIGN.md section "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W                    # this implementation
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own CPU implementation
+
+Workload (BASELINE.json configs[1], SURVEY 8(d) "config B"): synthetic textured 1920x1080 frame pairs, 1000 features,
+3 pyramid levels, subsampling 2, 7x7 window, max_residue 10, translational LK, non-sequential KLTTrackFeatures
+(two pyramid builds + tracking per pair).
+
+One "step" = one pass of the hot path over one batch of `--pairs` independent frame pairs per GPU:
+    value   : frames already resident in HBM (uint8), features resident; build pyramid(img1), build pyramid(img2), track.
+    e2e     : the same through the C ABI call klt_track_pairs_u8 with HOST (pinned) frames and HOST feature arrays:
+              host->device copies of the frames and features and the device->host copy of the results are inside
+              the timed region.
+Multi-GPU: independent pairs are sharded over ranks, no data-path collective (weak scaling: `--pairs` per GPU).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "B": dict(name="B: synthetic 1080p frame pairs, 1000 features, 3 levels, ss=2, 7x7, translational LK",
+              H=1080, W=1920, n=1000, L=3, ss=2, win=7, max_residue=10.0),
+    "C": dict(name="C: synthetic 4K frame pairs, 10000 features, 4 levels, ss=2, 7x7", H=2160, W=3840, n=10000, L=4,
+              ss=2, win=7, max_residue=10.0),
+    "A": dict(name="A: 320x240 synthetic stand-in for example1.py, 100 features, default context", H=240, W=320, n=100,
+              L=2, ss=4, win=7, max_residue=10.0),
+}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def make_inputs(wl, n_distinct, seed0=0):
+    """n_distinct seeded synthetic pairs (SURVEY 8(d) generator) -> list of (frame1, frame2) uint8 arrays."""
+    from pyfeaturetrack_b200 import synth
+    return [synth.frame_pair(wl["H"], wl["W"], seed=seed0 + s) for s in range(n_distinct)]
+
+
+def tc_for(wl, klt_mod):
+    tc = klt_mod.KLT_TrackingContext()
+    tc.window_width = tc.window_height = wl["win"]
+    tc.nPyramidLevels, tc.subsampling = wl["L"], wl["ss"]
+    tc.max_residue = wl["max_residue"]
+    tc.KLTUpdateTCBorder()
+    return tc
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def algorithmic_bytes_per_pair(wl, iters_per_pair):
+    """DESIGN.md 'Algorithmic bytes': compulsory traffic of each kernel of the pipeline, per frame pair."""
+    P = []
+    w, h = wl["W"], wl["H"]
+    for _ in range(wl["L"]):
+        P.append(w * h)
+        w, h = w // wl["ss"], h // wl["ss"]
+    per_frame = 5 * P[0] + sum(4 * (P[i - 1] + P[i]) for i in range(1, wl["L"])) + sum(12 * p for p in P)
+    win = (wl["win"] + 1) ** 2 * 4 * 3
+    lk = wl["n"] * wl["L"] * win + iters_per_pair * win
+    return 2 * per_frame + lk, per_frame, lk
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from pyfeaturetrack_b200 import _capi, klt, trackFeatures, selectGoodFeatures as sgf, config
+    sgf.KLT_verbose = 0
+    trackFeatures.KLT_verbose = 0
+    _capi.set_device(local)
+    ctx = _capi.default_ctx()
+    lib = _capi.lib()
+    wl = WORKLOADS[args.workload]
+    H, W, n, L, ss = wl["H"], wl["W"], wl["n"], wl["L"], wl["ss"]
+    B = args.pairs
+    prec = _capi.PRECISION_STRICT if args.precision == "strict" else _capi.PRECISION_FAST
+    config.set_precision(track=args.precision)
+
+    # ---- inputs: a few distinct seeded pairs (different per rank), tiled to the batch; features selected on the GPU
+    tc = tc_for(wl, klt)
+    distinct = make_inputs(wl, args.distinct, seed0=1000 * rank)
+    taps = trackFeatures._taps_for_one_image(tc)
+    params = sgf.make_params(tc)
+    f1 = ctx.pinned_array((B, H, W), np.uint8)
+    f2 = ctx.pinned_array((B, H, W), np.uint8)
+    x0 = ctx.pinned_array((B, n), np.float64)
+    y0 = ctx.pinned_array((B, n), np.float64)
+    v0 = ctx.pinned_array((B, n), np.int32)
+    sel = []
+    for (a, b) in distinct:
+        fl = sgf.KLTSelectGoodFeatures(tc, a, n)
+        sel.append((np.array([float(f.x) for f in fl]), np.array([float(f.y) for f in fl]),
+                    np.array([f.val for f in fl], np.int32)))
+    for i in range(B):
+        a, b = distinct[i % len(distinct)]
+        f1[i], f2[i] = a, b
+        x0[i], y0[i], v0[i] = sel[i % len(distinct)]
+    frame_bytes = B * H * W
+    feat_bytes = B * n * (8 + 8 + 4)
+    d_f1, d_f2 = ctx.device_alloc(frame_bytes), ctx.device_alloc(frame_bytes)
+    d_x0, d_y0, d_v0 = ctx.device_alloc(B * n * 8), ctx.device_alloc(B * n * 8), ctx.device_alloc(B * n * 4)
+    d_x, d_y, d_v = ctx.device_alloc(B * n * 8), ctx.device_alloc(B * n * 8), ctx.device_alloc(B * n * 4)
+    ctx.memcpy(d_f1, f1, frame_bytes); ctx.memcpy(d_f2, f2, frame_bytes)
+    ctx.memcpy(d_x0, x0, B * n * 8); ctx.memcpy(d_y0, y0, B * n * 8); ctx.memcpy(d_v0, v0, B * n * 4)
+    p1 = _capi.Pyramid(ctx, W, H, L, ss, B)
+    p2 = _capi.Pyramid(ctx, W, H, L, ss, B)
+    ctx.sync()
+
+    def step_device():
+        # features are mutated in place by tracking: restore them (device->device, part of the step)
+        ctx.memcpy(d_x, d_x0, B * n * 8); ctx.memcpy(d_y, d_y0, B * n * 8); ctx.memcpy(d_v, d_v0, B * n * 4)
+        ctx.check(lib.klt_pyr_build_u8(ctx.handle, p1.handle, d_f1, W, W * H, C.byref(taps), prec))
+        ctx.check(lib.klt_pyr_build_u8(ctx.handle, p2.handle, d_f2, W, W * H, C.byref(taps), prec))
+        ctx.check(lib.klt_track_features(ctx.handle, C.byref(params), p1.handle, p2.handle, n, d_x, d_y, d_v, None))
+
+    hx = ctx.pinned_array((B, n), np.float64)
+    hy = ctx.pinned_array((B, n), np.float64)
+    hv = ctx.pinned_array((B, n), np.int32)
+
+    def step_e2e():
+        hx[:] = x0; hy[:] = y0; hv[:] = v0
+        ctx.check(lib.klt_track_pairs_u8(ctx.handle, C.byref(params), C.byref(taps), prec, p1.handle, p2.handle,
+                                         f1.ctypes.data, f2.ctypes.data, W, W * H, n, hx.ctypes.data, hy.ctypes.data,
+                                         hv.ctypes.data))
+
+    def barrier():
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        l0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        ctx.timer_start()
+        for _ in range(steps):
+            fn()
+        ctx.timer_stop()
+        ms = ctx.timer_elapsed_ms()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        launches = ctx.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms, wall], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1])
+        return ms, wall, launches
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dev_ms, dev_wall, launches = timed(step_device, args.steps, args.warmup)
+    # tracked count and iterations of one step (for the metric and the LK byte estimate)
+    it = C.c_int64()
+    ctx.memcpy(d_x, d_x0, B * n * 8); ctx.memcpy(d_y, d_y0, B * n * 8); ctx.memcpy(d_v, d_v0, B * n * 4)
+    ctx.check(lib.klt_track_features(ctx.handle, C.byref(params), p1.handle, p2.handle, n, d_x, d_y, d_v, C.byref(it)))
+    ctx.memcpy(hv, d_v, B * n * 4)
+    ctx.sync()
+    tracked = int((hv == 0).sum())
+    e2e_steps = max(3, args.steps // 2)
+    e2e_ms, e2e_wall, _ = timed(step_e2e, e2e_steps, max(3, args.warmup // 2))
+    e2e_tracked = int((hv == 0).sum())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel durations, measured live with CUDA events on the launching stream (separate pass) ----
+    ctx.profile_reset()
+    ctx.profile(True)
+    for _ in range(max(3, args.steps // 4)):
+        step_device()
+    ctx.profile(False)
+    prof = ctx.profile_read()
+    barrier()
+
+    # ---- aggregate over ranks ----
+    if world > 1:
+        t = torch.tensor([tracked, e2e_tracked], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        tracked_all, e2e_tracked_all = float(t[0]), float(t[1])
+    else:
+        tracked_all, e2e_tracked_all = float(tracked), float(e2e_tracked)
+    pairs_all = B * world
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    kernels = {}
+    for name, r in prof.items():
+        if r["launches"]:
+            kernels[name] = {"ms_per_launch": r["ms"] / r["launches"], "launches_per_step": r["launches"] / max(3, args.steps // 4),
+                             "gbps": (r["bytes"] / r["launches"]) / (r["ms"] / r["launches"] * 1e-3) / 1e9 if r["bytes"] else None,
+                             "bytes_per_launch": r["bytes"] / r["launches"]}
+    total_kernel_ms = sum(r["ms"] for r in prof.values())
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])[0] if prof else None
+    roof = None
+    if dom and prof[dom]["bytes"]:
+        r = prof[dom]
+        ach = (r["bytes"] / r["launches"]) / (r["ms"] / r["launches"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "share_of_step": round(r["ms"] / total_kernel_ms, 3),
+                "bytes_per_launch": r["bytes"] / r["launches"], "ms_per_launch": r["ms"] / r["launches"]}
+    step_s = dev_ms * 1e-3 / args.steps
+    e2e_s = e2e_ms * 1e-3 / e2e_steps
+    bytes_pair, bytes_frame, bytes_lk = algorithmic_bytes_per_pair(wl, it.value / B)
+    out = {
+        "metric": "tracked_features_per_sec", "value": round(tracked_all / step_s, 1), "unit": "tracked features/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fast" else "f64-accumulate/f32",
+        "data": "synthetic",
+        "frame_pairs_per_sec": round(pairs_all / step_s, 2),
+        "config": {"workload": wl["name"], "pairs_per_step_per_gpu": B, "features_per_pair": n, "distinct_pairs": args.distinct,
+                   "precision": args.precision, "parallelism": "independent frame pairs sharded %d-way, no collective" % world,
+                   "l2": "no flush needed: each step streams %.0f MB of pyramids per GPU (> 126 MB L2); inputs %.0f MB" %
+                         ((p1.nbytes() + p2.nbytes()) / 1e6, 2 * frame_bytes / 1e6)},
+        "e2e": {"value": round(e2e_tracked_all / e2e_s, 1), "unit": "tracked features/s",
+                "frame_pairs_per_sec": round(pairs_all / e2e_s, 2), "ms_per_step": round(e2e_ms / e2e_steps, 4),
+                "h2d_bytes_per_step": 2 * frame_bytes + feat_bytes, "d2h_bytes_per_step": feat_bytes,
+                "api": "klt_track_pairs_u8 (C ABI) with pinned host frames and host feature arrays"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "kernels": kernels,
+        "pipeline": {"algorithmic_bytes_per_pair": bytes_pair, "algorithmic_bytes_per_frame_build": bytes_frame,
+                     "lk_bytes_per_pair": bytes_lk, "achieved_gbps": round(bytes_pair * B / step_s / 1e9, 1),
+                     "frac_of_hbm_peak": round(bytes_pair * B / step_s / 1e9 / peak, 4),
+                     "newton_iterations_per_pair": it.value / B, "tracked_fraction": tracked / float(B * n),
+                     "wall_ms_per_step": round(dev_wall / args.steps, 4)},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(wl, distinct, sel, budget_s=args.cpu_budget)
+    if world == 1 and args.api_pairs > 0:
+        out["api_single_pair"] = api_single_pair(wl, distinct, klt, sgf, trackFeatures, args.api_pairs)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def api_single_pair(wl, distinct, klt, sgf, tf, reps):
+    """The drop-in Python call a reference user makes, one pair per call: PIL images in, feature list mutated in place."""
+    from PIL import Image
+    tc = tc_for(wl, klt)
+    i1, i2 = Image.fromarray(distinct[0][0]), Image.fromarray(distinct[0][1])
+    base = sgf.KLTSelectGoodFeatures(tc, i1, wl["n"])
+    import copy
+    ts = []
+    tracked = 0
+    for r in range(reps + 2):
+        fl = copy.deepcopy(base)
+        t0 = time.perf_counter()
+        tf.KLTTrackFeatures(tc, i1, i2, fl)
+        dt = time.perf_counter() - t0
+        if r >= 2:
+            ts.append(dt)
+            tracked = sum(1 for f in fl if f.val == 0)
+    return {"call": "KLTTrackFeatures(tc, img1, img2, fl) with PIL images", "ms_per_pair": round(1e3 * float(np.mean(ts)), 3),
+            "frame_pairs_per_sec": round(1.0 / float(np.mean(ts)), 1), "tracked_features_per_sec": round(tracked / float(np.mean(ts)), 1)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def _ref_worker(q_in, q_out, wl_key):
+    """One process = one core running the unmodified reference (oracle/_ref) on the pairs it is handed."""
+    from oracle import ref_loader
+    ref_loader.install()
+    import klt as rklt
+    import selectGoodFeatures as rsgf
+    import trackFeatures as rtf
+    from PIL import Image
+    rsgf.KLT_verbose = 0
+    rtf.KLT_verbose = 0
+    wl = WORKLOADS[wl_key]
+    tc = tc_for(wl, rklt)
+    while True:
+        job = q_in.get()
+        if job is None:
+            break
+        a, b, (x, y, v) = job
+        fl = []
+        for i in range(len(x)):
+            f = rklt.KLT_Feature()
+            f.x, f.y, f.val = x[i], y[i], int(v[i])
+            f.aff_img = f.aff_img_gradx = f.aff_img_grady = None
+            fl.append(f)
+        i1, i2 = Image.fromarray(a), Image.fromarray(b)
+        t0 = time.perf_counter()
+        rtf.KLTTrackFeatures(tc, i1, i2, fl)
+        dt = time.perf_counter() - t0
+        q_out.put((dt, sum(1 for f in fl if f.val == 0)))
+
+
+def _oracle_select(wl, frame):
+    from oracle import klt_oracle as O
+    p = O.Params(window_width=wl["win"], window_height=wl["win"], nPyramidLevels=wl["L"], subsampling=wl["ss"],
+                 max_residue=wl["max_residue"])
+    return O.select_good_features(p, frame, wl["n"])
+
+
+def reference_available():
+    from oracle import ref_loader
+    return ref_loader.available()
+
+
+def run_reference_pool(wl_key, jobs, procs):
+    """Runs `jobs` = [(frame1, frame2, features)] on `procs` worker processes; returns (wall_s, tracked, per_call_s)."""
+    import multiprocessing as mp
+    mpc = mp.get_context("spawn")
+    q_in, q_out = mpc.Queue(), mpc.Queue()
+    ws = [mpc.Process(target=_ref_worker, args=(q_in, q_out, wl_key)) for _ in range(procs)]
+    for w in ws:
+        w.start()
+    # warm each worker (imports, kernel cache) with one untimed job
+    for _ in range(procs):
+        q_in.put(jobs[0])
+    for _ in range(procs):
+        q_out.get()
+    t0 = time.perf_counter()
+    for j in jobs:
+        q_in.put(j)
+    res = [q_out.get() for _ in jobs]
+    wall = time.perf_counter() - t0
+    for _ in ws:
+        q_in.put(None)
+    for w in ws:
+        w.join()
+    return wall, sum(r[1] for r in res), [r[0] for r in res]
+
+
+def cpu_baseline(wl, distinct, sel, budget_s=20.0):
+    """Reference CPU path timed on this box, bounded sample (a reported baseline, not the target)."""
+    wl_key = [k for k, v in WORKLOADS.items() if v is wl][0]
+    if reference_available():
+        per = 0.8 * (wl["H"] * wl["W"]) / (1080.0 * 1920.0)
+        npairs = int(max(2, min(24, budget_s / max(per, 1e-3))))
+        jobs = [(distinct[i % len(distinct)][0], distinct[i % len(distinct)][1], sel[i % len(distinct)]) for i in range(npairs)]
+        wall, tracked, per_call = run_reference_pool(wl_key, jobs, 1)
+        return {"value": round(tracked / wall, 1), "unit": "tracked features/s", "frame_pairs_per_sec": round(npairs / wall, 3),
+                "cores": 1, "kind": "reference",
+                "sample": "%d pairs of the same workload through the unmodified reference's KLTTrackFeatures (oracle/_ref: "
+                          "reference .py byte-compiled + its Cython modules), one process = one core (the reference is "
+                          "single-threaded); mean %.3f s per pair" % (npairs, float(np.mean(per_call)))}
+    from oracle import klt_oracle as O
+    p = O.Params(window_width=wl["win"], window_height=wl["win"], nPyramidLevels=wl["L"], subsampling=wl["ss"],
+                 max_residue=wl["max_residue"])
+    t0 = time.perf_counter()
+    npairs = tracked = 0
+    while time.perf_counter() - t0 < budget_s / 2 or npairs < 2:
+        a, b = distinct[npairs % len(distinct)]
+        r = O.track_features(p, a, b, *sel[npairs % len(distinct)])
+        tracked += int((r[2] == 0).sum())
+        npairs += 1
+    wall = time.perf_counter() - t0
+    return {"value": round(tracked / wall, 1), "unit": "tracked features/s", "frame_pairs_per_sec": round(npairs / wall, 3),
+            "cores": 1, "kind": "port", "sample": "%d pairs through the scalar C oracle (oracle/klt_oracle.c)" % npairs}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation on all host cores (rank 0 only)."""
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, args.ref_procs if args.ref_procs > 0 else cores))
+    distinct = make_inputs(wl, min(args.distinct, 2), seed0=0)
+    sel = [_oracle_select(wl, a) for (a, b) in distinct]
+    per_step = procs                           # one pair per worker per step: a bounded sample of the workload
+    steps, warmup = args.steps, args.warmup
+    if reference_available():
+        jobs = [(distinct[i % len(distinct)][0], distinct[i % len(distinct)][1], sel[i % len(distinct)])
+                for i in range(per_step * steps)]
+        # the pool's own warm-up (one job per worker) stands in for the W warm-up steps
+        wall, tracked, per_call = run_reference_pool(args.workload, jobs, procs)
+        kind = "reference"
+        sample = ("%d steps x %d pairs (one per worker process) through the unmodified reference's KLTTrackFeatures "
+                  "(oracle/_ref); %d processes on %d host cores; mean %.3f s per call" %
+                  (steps, per_step, procs, cores, float(np.mean(per_call))))
+    else:
+        from oracle import klt_oracle as O
+        p = O.Params(window_width=wl["win"], window_height=wl["win"], nPyramidLevels=wl["L"], subsampling=wl["ss"],
+                     max_residue=wl["max_residue"])
+        t0 = time.perf_counter()
+        tracked = 0
+        per_step = 1
+        for i in range(steps):
+            r = O.track_features(p, distinct[0][0], distinct[0][1], *sel[0])
+            tracked += int((r[2] == 0).sum())
+        wall = time.perf_counter() - t0
+        kind, procs = "port", 1
+        sample = "%d pairs through the scalar C oracle (oracle/klt_oracle.c), 1 core" % steps
+    value = tracked / wall
+    out = {"impl": "reference", "metric": "tracked_features_per_sec", "value": round(value, 1), "unit": "tracked features/s",
+           "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(1e3 * wall / steps, 2),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 accumulate in SciPy)",
+           "data": "synthetic", "frame_pairs_per_sec": round(per_step * steps / wall, 3),
+           "config": {"workload": wl["name"], "pairs_per_step": per_step, "features_per_pair": wl["n"]},
+           "cpu_baseline": {"value": round(value, 1), "unit": "tracked features/s", "cores": procs, "kind": kind, "sample": sample},
+           "e2e": {"value": round(value, 1), "unit": "tracked features/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=16, help="independent frame pairs per step per GPU")
+    ap.add_argument("--distinct", type=int, default=4, help="distinct seeded pairs generated per rank (tiled to --pairs)")
+    ap.add_argument("--precision", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--api-pairs", type=int, default=10)
+    ap.add_argument("--ref-procs", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

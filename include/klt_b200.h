@@ -114,6 +114,14 @@ int klt_timer_start(klt_ctx *ctx);
 int klt_timer_stop(klt_ctx *ctx);
 int klt_timer_elapsed_ms(klt_ctx *ctx, float *ms);
 
+/* per-kernel device timing: while enabled, every kernel launch is bracketed by CUDA events on the context's stream.
+ * klt_profile_get returns, per kernel name, the summed duration, launch count and summed ALGORITHMIC bytes
+ * (each launch's compulsory traffic: inputs read once + outputs written once).  Used by bench.py's roofline. */
+int klt_profile_enable(klt_ctx *ctx, int on);
+int klt_profile_reset(klt_ctx *ctx);
+int klt_profile_count(klt_ctx *ctx);
+int klt_profile_get(klt_ctx *ctx, int index, const char **name, double *total_ms, int64_t *launches, double *bytes);
+
 /* ---- operator level: replaces scipy.ndimage.convolve1d pairs behind convolve.py -------------------
  * klt_convolve_separable_f32  == _convolveSeparate(img, hk, vk)         convolve.py:208-214
  * klt_smooth_f32              == KLTComputeSmoothedImage's convolution  convolve.py:254-264

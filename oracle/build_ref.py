@@ -9,9 +9,10 @@ into oracle/_ref/ (git-ignored, but shipped to the GPU box by gpurun):
 
   * goodFeaturesUtils.pyx, trackFeaturesUtils.pyx  - exactly what the reference's setup.py builds;
   * klt.py, convolve.py, pyramid.py, klt_util.py, error.py, selectGoodFeatures.py, trackFeatures.py
-    - byte-compiled unmodified by CPython itself (py_compile) into SOURCELESS .pyc modules, so the
+    - byte-compiled unmodified by CPython itself (py_compile) into SOURCELESS bytecode files
+      (<name>.refbc = a .pyc under another suffix, because the gpurun snapshot drops *.pyc), so the
       interpreter executes exactly the reference's bytecode at exactly the reference's speed
-      ("the reference as executed under Python 3").
+      ("the reference as executed under Python 3").  oracle/ref_loader.py imports them.
 
 Intermediate C files (which quote source lines in comments) go to a temp dir and are discarded.
 The two PGM fixtures are NOT copied; tests/golden/ holds what the tests need.
@@ -31,7 +32,7 @@ PY = ["klt.py", "convolve.py", "pyramid.py", "klt_util.py", "error.py",
 
 def _target(f):
     base, ext = os.path.splitext(f)
-    return base + (sysconfig.get_config_var("EXT_SUFFIX") if ext == ".pyx" else ".pyc")
+    return base + (sysconfig.get_config_var("EXT_SUFFIX") if ext == ".pyx" else ".refbc")
 
 
 def up_to_date():
@@ -81,7 +82,7 @@ def build(force=False, verbose=False):
         for f in PYX:
             shutil.copy(os.path.join(tmp, _target(f)), os.path.join(OUT, _target(f)))
         import py_compile
-        for f in PY:   # sourceless bytecode: "<name>.pyc" next to the extension modules is importable as <name>
+        for f in PY:   # sourceless bytecode next to the extension modules; imported through oracle/ref_loader.py
             py_compile.compile(os.path.join(REF, f), cfile=os.path.join(OUT, _target(f)),
                                dfile="<reference>/" + f, doraise=True, optimize=0,
                                invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)

@@ -68,6 +68,11 @@ SIGNATURES = {
     "klt_timer_start": (_i, [_vp]),
     "klt_timer_stop": (_i, [_vp]),
     "klt_timer_elapsed_ms": (_i, [_vp, C.POINTER(C.c_float)]),
+    "klt_profile_enable": (_i, [_vp, _i]),
+    "klt_profile_reset": (_i, [_vp]),
+    "klt_profile_count": (_i, [_vp]),
+    "klt_profile_get": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64),
+                             C.POINTER(C.c_double)]),
     "klt_convolve_separable_f32": (_i, [_vp, _fp, _i, _i, C.POINTER(Kernel1D), C.POINTER(Kernel1D), _i, _fp]),
     "klt_smooth_f32": (_i, [_vp, _fp, _i, _i, C.POINTER(Kernel1D), _i, _fp]),
     "klt_gradients_f32": (_i, [_vp, _fp, _i, _i, C.POINTER(Kernel1D), C.POINTER(Kernel1D), _i, _fp, _fp]),
@@ -207,6 +212,21 @@ class Context:
         ms = C.c_float()
         self.check(lib().klt_timer_elapsed_ms(self.handle, C.byref(ms)))
         return ms.value
+
+    def profile(self, on):
+        self.check(lib().klt_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_reset(self):
+        self.check(lib().klt_profile_reset(self.handle))
+
+    def profile_read(self):
+        """{kernel name: dict(ms=total, launches=n, bytes=algorithmic bytes)}"""
+        out = {}
+        for i in range(lib().klt_profile_count(self.handle)):
+            name, ms, n, b = C.c_char_p(), C.c_double(), C.c_int64(), C.c_double()
+            self.check(lib().klt_profile_get(self.handle, i, C.byref(name), C.byref(ms), C.byref(n), C.byref(b)))
+            out[name.value.decode()] = dict(ms=ms.value, launches=n.value, bytes=b.value)
+        return out
 
     def scratch_pyramid(self, w, h, n_levels, subsampling, batch=1, slot=0):
         """Cached scratch pyramids (avoids cudaMalloc per call)."""

@@ -46,7 +46,68 @@ int klt_pinned_reserve(klt_ctx *ctx, size_t bytes) {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+int klt_prof_begin(klt_ctx *ctx, const char *name, double bytes) {
+    if (!ctx->profiling) return -1;
+    int rec = -1;
+    for (size_t i = 0; i < ctx->prof.size(); i++)
+        if (ctx->prof[i].name == name) { rec = (int)i; break; }
+    if (rec < 0) { ctx->prof.push_back(KltProfRec{name, 0.0, 0.0, 0}); rec = (int)ctx->prof.size() - 1; }
+    ctx->prof[rec].bytes += bytes;
+    ctx->prof[rec].count += 1;
+    KltProfPending pd;
+    pd.rec = rec;
+    for (cudaEvent_t *e : {&pd.e0, &pd.e1}) {
+        if (!ctx->prof_pool.empty()) { *e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+        else cudaEventCreate(e);
+    }
+    cudaEventRecord(pd.e0, ctx->stream);
+    ctx->prof_pending.push_back(pd);
+    return (int)ctx->prof_pending.size() - 1;
+}
+void klt_prof_end(klt_ctx *ctx, int token) {
+    if (token < 0) return;
+    cudaEventRecord(ctx->prof_pending[token].e1, ctx->stream);
+}
+static void prof_resolve(klt_ctx *ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &pd : ctx->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pd.e0, pd.e1) == cudaSuccess) ctx->prof[pd.rec].ms += ms;
+        ctx->prof_pool.push_back(pd.e0);
+        ctx->prof_pool.push_back(pd.e1);
+    }
+    ctx->prof_pending.clear();
+}
+
 extern "C" {
+
+int klt_profile_enable(klt_ctx *ctx, int on) {
+    if (!ctx) return KLT_ERR_INVALID;
+    prof_resolve(ctx);
+    ctx->profiling = on != 0;
+    return KLT_OK;
+}
+int klt_profile_reset(klt_ctx *ctx) {
+    if (!ctx) return KLT_ERR_INVALID;
+    prof_resolve(ctx);
+    ctx->prof.clear();
+    return KLT_OK;
+}
+int klt_profile_count(klt_ctx *ctx) {
+    if (!ctx) return KLT_ERR_INVALID;
+    prof_resolve(ctx);
+    return (int)ctx->prof.size();
+}
+int klt_profile_get(klt_ctx *ctx, int index, const char **name, double *total_ms, int64_t *launches, double *bytes) {
+    if (!ctx || index < 0 || index >= (int)ctx->prof.size()) return KLT_ERR_INVALID;
+    const KltProfRec &r = ctx->prof[index];
+    if (name) *name = r.name.c_str();
+    if (total_ms) *total_ms = r.ms;
+    if (launches) *launches = r.count;
+    if (bytes) *bytes = r.bytes;
+    return KLT_OK;
+}
+
 
 int klt_abi_version(void) { return KLT_B200_ABI_VERSION; }
 
@@ -62,6 +123,7 @@ int klt_ctx_create(int device, void *stream, klt_ctx **out) {
     if ((e = cudaSetDevice(device)) != cudaSuccess) return klt_fail(nullptr, KLT_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     klt_ctx *ctx = new klt_ctx();
     ctx->device = device;
+    ctx->profiling = false;
     ctx->launches = 0;
     ctx->ws = nullptr; ctx->ws_bytes = 0; ctx->pinned = nullptr; ctx->pinned_bytes = 0;
     ctx->own_stream = stream == nullptr;
@@ -89,7 +151,8 @@ int klt_ctx_create(int device, void *stream, klt_ctx **out) {
 int klt_ctx_destroy(klt_ctx *ctx) {
     if (!ctx) return KLT_OK;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    prof_resolve(ctx);
+    for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaEventDestroy(ctx->ev0);

@@ -36,7 +36,21 @@ struct klt_pyr {
     }
 };
 
+// Per-kernel device timing (klt_profile_* in klt_b200.h): CUDA events recorded on the context's stream around
+// every launch while profiling is enabled; resolved lazily.
+struct KltProfRec {
+    std::string name;
+    double bytes;       // algorithmic bytes of all launches (compulsory reads + writes of that kernel)
+    double ms;
+    long count;
+};
+struct KltProfPending { int rec; cudaEvent_t e0, e1; };
+
 struct klt_ctx {
+    bool profiling;
+    std::vector<KltProfRec> prof;
+    std::vector<KltProfPending> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
     int device;
     cudaStream_t stream;
     bool own_stream;
@@ -64,6 +78,16 @@ int klt_fail(klt_ctx *ctx, int code, const char *fmt, ...);
     do {                                        \
         (ctx)->launches++;                      \
         KLT_CUDA(ctx, cudaGetLastError());      \
+    } while (0)
+// bracket a kernel launch: `bytes` = that launch's algorithmic bytes (inputs read once + outputs written once)
+int klt_prof_begin(klt_ctx *ctx, const char *name, double bytes);
+void klt_prof_end(klt_ctx *ctx, int token);
+#define KLT_LAUNCH(ctx, name, bytes, ...)                       \
+    do {                                                        \
+        const int tok__ = klt_prof_begin(ctx, name, bytes);     \
+        __VA_ARGS__;                                            \
+        klt_prof_end(ctx, tok__);                               \
+        KLT_CHECK_LAUNCH(ctx);                                  \
     } while (0)
 
 int klt_ws_reserve(klt_ctx *ctx, size_t bytes);          // grow-only workspace

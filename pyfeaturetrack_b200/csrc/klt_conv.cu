@@ -188,14 +188,17 @@ static int launch_conv_sep(klt_ctx *ctx, const InT *in, size_t in_pitch, size_t 
     while (smem_for(TW, TH) > kMaxSmem && TW > 32) TW /= 2;
     size_t smem = smem_for(TW, TH);
     dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH, batch), block(32, 8);
+    const double bytes = (double)(sizeof(InT) + sizeof(float)) * w * h * batch;
+    const bool u8 = sizeof(InT) == 1;
     if (precision == KLT_PRECISION_STRICT) {
         if ((rc = set_smem(ctx, conv_sep_kernel<InT, true>))) return rc;
-        conv_sep_kernel<InT, true><<<grid, block, smem, ctx->stream>>>(in, in_pitch, in_stride, out, out_pitch, out_stride, w, h, TW, TH, hd, vd);
+        KLT_LAUNCH(ctx, u8 ? "conv_sep_u8_strict" : "conv_sep_f32_strict", bytes,
+                   (conv_sep_kernel<InT, true><<<grid, block, smem, ctx->stream>>>(in, in_pitch, in_stride, out, out_pitch, out_stride, w, h, TW, TH, hd, vd)));
     } else {
         if ((rc = set_smem(ctx, conv_sep_kernel<InT, false>))) return rc;
-        conv_sep_kernel<InT, false><<<grid, block, smem, ctx->stream>>>(in, in_pitch, in_stride, out, out_pitch, out_stride, w, h, TW, TH, hf, vf);
+        KLT_LAUNCH(ctx, u8 ? "conv_sep_u8" : "conv_sep_f32", bytes,
+                   (conv_sep_kernel<InT, false><<<grid, block, smem, ctx->stream>>>(in, in_pitch, in_stride, out, out_pitch, out_stride, w, h, TW, TH, hf, vf)));
     }
-    KLT_CHECK_LAUNCH(ctx);
     return KLT_OK;
 }
 
@@ -224,14 +227,16 @@ int klt_launch_grad_pair(klt_ctx *ctx, const float *in, size_t in_pitch, size_t 
     while (smem_for(TW, TH) > kMaxSmem && TW > 32) TW /= 2;
     size_t smem = smem_for(TW, TH);
     dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH, batch), block(32, 8);
+    const double bytes = 12.0 * w * h * batch;
     if (precision == KLT_PRECISION_STRICT) {
         if ((rc = set_smem(ctx, grad_pair_kernel<true>))) return rc;
-        grad_pair_kernel<true><<<grid, block, smem, ctx->stream>>>(in, in_pitch, in_stride, gx, gy, out_pitch, out_stride, w, h, TW, TH, gd, dd);
+        KLT_LAUNCH(ctx, "grad_pair_strict", bytes,
+                   (grad_pair_kernel<true><<<grid, block, smem, ctx->stream>>>(in, in_pitch, in_stride, gx, gy, out_pitch, out_stride, w, h, TW, TH, gd, dd)));
     } else {
         if ((rc = set_smem(ctx, grad_pair_kernel<false>))) return rc;
-        grad_pair_kernel<false><<<grid, block, smem, ctx->stream>>>(in, in_pitch, in_stride, gx, gy, out_pitch, out_stride, w, h, TW, TH, gf, df);
+        KLT_LAUNCH(ctx, "grad_pair", bytes,
+                   (grad_pair_kernel<false><<<grid, block, smem, ctx->stream>>>(in, in_pitch, in_stride, gx, gy, out_pitch, out_stride, w, h, TW, TH, gf, df)));
     }
-    KLT_CHECK_LAUNCH(ctx);
     return KLT_OK;
 }
 
@@ -252,13 +257,15 @@ int klt_launch_pyr_down(klt_ctx *ctx, const float *in, size_t in_pitch, size_t i
     if (smem_for(TW, TH) > kMaxSmem) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "pyramid kernel too wide for shared memory");
     size_t smem = smem_for(TW, TH);
     dim3 grid((ow + TW - 1) / TW, (oh + TH - 1) / TH, batch), block(32, 8);
+    const double bytes = 4.0 * ((double)w * h + (double)ow * oh) * batch;
     if (precision == KLT_PRECISION_STRICT) {
         if ((rc = set_smem(ctx, pyr_down_kernel<true>))) return rc;
-        pyr_down_kernel<true><<<grid, block, smem, ctx->stream>>>(in, in_pitch, in_stride, w, h, out, out_pitch, out_stride, ow, oh, ss, TW, TH, gd);
+        KLT_LAUNCH(ctx, "pyr_down_strict", bytes,
+                   (pyr_down_kernel<true><<<grid, block, smem, ctx->stream>>>(in, in_pitch, in_stride, w, h, out, out_pitch, out_stride, ow, oh, ss, TW, TH, gd)));
     } else {
         if ((rc = set_smem(ctx, pyr_down_kernel<false>))) return rc;
-        pyr_down_kernel<false><<<grid, block, smem, ctx->stream>>>(in, in_pitch, in_stride, w, h, out, out_pitch, out_stride, ow, oh, ss, TW, TH, gf);
+        KLT_LAUNCH(ctx, "pyr_down", bytes,
+                   (pyr_down_kernel<false><<<grid, block, smem, ctx->stream>>>(in, in_pitch, in_stride, w, h, out, out_pitch, out_stride, ow, oh, ss, TW, TH, gf)));
     }
-    KLT_CHECK_LAUNCH(ctx);
     return KLT_OK;
 }

@@ -225,8 +225,7 @@ int klt_launch_track(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const
     if (smem > 200 * 1024) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "tracking window %dx%d too large", A.w, A.h);
     KLT_CUDA(ctx, cudaFuncSetAttribute(lk_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const int blocks = (A.total + warps - 1) / warps;
-    lk_track_kernel<<<blocks, warps * 32, smem, ctx->stream>>>(A, x_dev, y_dev, val_dev, iters_dev, assert_dev);
-    KLT_CHECK_LAUNCH(ctx);
+    KLT_LAUNCH(ctx, "lk_track", 0.0, (lk_track_kernel<<<blocks, warps * 32, smem, ctx->stream>>>(A, x_dev, y_dev, val_dev, iters_dev, assert_dev)));
     return KLT_OK;
 }
 

@@ -35,24 +35,11 @@ def oracle():
 
 
 def load_reference():
-    """The unmodified reference from oracle/_ref (sourceless .pyc + Cython .so, see oracle/build_ref.py), or None."""
-    ref_dir = os.path.join(ROOT, "oracle", "_ref")
-    if not os.path.exists(os.path.join(ref_dir, "klt.pyc")):
+    """The unmodified reference from oracle/_ref (sourceless bytecode + Cython .so, see oracle/build_ref.py), or None."""
+    from oracle import ref_loader
+    if not ref_loader.available():
         return None
-    import importlib
-    warnings.simplefilter("ignore")
-    saved = list(sys.path)
-    sys.path.insert(0, ref_dir)
-    try:
-        mods = {}
-        for name in ("error", "klt_util", "convolve", "klt", "pyramid", "goodFeaturesUtils", "trackFeaturesUtils",
-                     "selectGoodFeatures", "trackFeatures"):
-            mods[name] = importlib.import_module(name)
-    finally:
-        sys.path[:] = saved
-    mods["selectGoodFeatures"].KLT_verbose = 0
-    mods["trackFeatures"].KLT_verbose = 0
-    return mods
+    return ref_loader.load()
 
 
 @pytest.fixture(scope="session")
