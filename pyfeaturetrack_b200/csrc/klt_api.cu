@@ -303,19 +303,27 @@ static int check_taps(klt_ctx *ctx, const klt_taps *t) {
     return KLT_OK;
 }
 
-// levels 1..L-1 and all gradients, given level 0 intensity already in place
-static int build_rest(klt_ctx *ctx, klt_pyr *p, const klt_taps *taps, int precision) {
+// levels 1..L-1 and all gradients, given level 0 intensity already in place (level0_grad_done: the fused level-0
+// kernel has already written gradx/grady of level 0).  FAST precision takes the warp-streaming kernels where they
+// cover the configuration; everything else runs the generic tiled kernels.
+static int build_rest(klt_ctx *ctx, klt_pyr *p, const klt_taps *taps, int precision, bool level0_grad_done = false) {
     int rc;
     const size_t stride = p->plane_floats;
+    const bool fast = precision == KLT_PRECISION_FAST;
     for (int l = 1; l < p->n_levels; l++) {
         const LevelDesc &a = p->lv[l - 1], &b = p->lv[l];
-        if ((rc = klt_launch_pyr_down(ctx, p->level(0, 0, l - 1), a.pitch, stride, a.w, a.h, p->level(0, 0, l), b.pitch, stride,
-                                      b.w, b.h, p->ss, p->batch, &taps->pyramid, precision))) return rc;
+        rc = fast ? klt_stream_down2(ctx, p, l, taps) : 0;
+        if (rc < 0) return rc;
+        if (rc == 0 && (rc = klt_launch_pyr_down(ctx, p->level(0, 0, l - 1), a.pitch, stride, a.w, a.h, p->level(0, 0, l), b.pitch,
+                                                 stride, b.w, b.h, p->ss, p->batch, &taps->pyramid, precision))) return rc;
     }
-    for (int l = 0; l < p->n_levels; l++) {
+    for (int l = level0_grad_done ? 1 : 0; l < p->n_levels; l++) {
         const LevelDesc &a = p->lv[l];
-        if ((rc = klt_launch_grad_pair(ctx, p->level(0, 0, l), a.pitch, stride, p->level(1, 0, l), p->level(2, 0, l), a.pitch,
-                                       stride, a.w, a.h, p->batch, &taps->grad_gauss, &taps->grad_deriv, precision))) return rc;
+        rc = fast ? klt_stream_grad(ctx, p, l, taps) : 0;
+        if (rc < 0) return rc;
+        if (rc == 0 && (rc = klt_launch_grad_pair(ctx, p->level(0, 0, l), a.pitch, stride, p->level(1, 0, l), p->level(2, 0, l),
+                                                  a.pitch, stride, a.w, a.h, p->batch, &taps->grad_gauss, &taps->grad_deriv,
+                                                  precision))) return rc;
     }
     return KLT_OK;
 }
@@ -334,7 +342,13 @@ int klt_pyr_build_u8(klt_ctx *ctx, klt_pyr *p, const uint8_t *frames, size_t pit
         KLT_CUDA(ctx, cudaMemcpyAsync(ctx->ws, frames, bytes, cudaMemcpyHostToDevice, ctx->stream));
         dframes = (const uint8_t *)ctx->ws;
     }
-    // img.convert("F") + KLTComputeSmoothedImage (trackFeatures.py:165-166): one fused kernel, u8 in, f32 out
+    if (precision == KLT_PRECISION_FAST) {
+        // fused u8 -> smoothed image + gradient pair of level 0 (one read of the frame, three writes)
+        rc = klt_stream_level0(ctx, dframes, pitch, frame_stride, p, taps);
+        if (rc < 0) return rc;
+        if (rc == 1) return build_rest(ctx, p, taps, precision, true);
+    }
+    // img.convert("F") + KLTComputeSmoothedImage (trackFeatures.py:165-166): one kernel, u8 in, f32 out
     if ((rc = klt_launch_conv_sep_u8(ctx, dframes, pitch, frame_stride, p->level(0, 0, 0), p->lv[0].pitch, p->plane_floats,
                                      p->w, p->h, p->batch, &taps->smooth, &taps->smooth, precision))) return rc;
     return build_rest(ctx, p, taps, precision);

@@ -113,6 +113,11 @@ int klt_launch_pyr_down(klt_ctx *ctx, const float *in, size_t in_pitch, size_t i
                         size_t out_pitch, size_t out_stride, int ow, int oh, int ss, int batch,
                         const klt_kernel1d *g, int precision);
 
+// ---- klt_stream.cu: warp-streaming FAST-path kernels; return 1 = launched, 0 = configuration not covered ----
+int klt_stream_level0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t frame_stride, klt_pyr *p, const klt_taps *taps);
+int klt_stream_grad(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps);
+int klt_stream_down2(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps);
+
 // ---- klt_select.cu -----------------------------------------------------------------------------------
 int klt_launch_scan(klt_ctx *ctx, const float *gx, const float *gy, size_t pitch, int w, int h, int bx, int by,
                     int hw, int hh, int skip, float *val_dev /* [ny][nx] */, int nx, int ny);
