@@ -5,58 +5,59 @@
 // ~70 FMA/clk of its 128 -- the kernel is as much issue-bound as HBM-bound, so the design goal is to spend issue slots
 // on FMAs only:
 //   * one WARP owns a strip of columns and marches down the rows of its segment; every lane owns 4 adjacent columns;
-//   * vertical filters never touch memory: each lane keeps the (2r+1) partially accumulated output rows of its 4 columns
+//   * vertical filters never touch memory: each lane keeps the 2r partially accumulated output rows of its 4 columns
 //     in registers; a new input row updates them with one FMA each, and the FMA's destination register performs the
 //     shift (acc[m] = fma(c, v, acc[m+1])), so there are no moves and no unrolling by the kernel length;
-//   * horizontal filters get the 3-5 neighbour columns from the adjacent lanes with warp shuffles (no shared memory,
-//     no block barriers); lanes 0 and 31 are halo lanes whose own outputs are discarded (30/32 = 94 % efficiency);
+//   * horizontal filters get the neighbour columns from the adjacent lanes with warp shuffles (float rows) or from the
+//     neighbour quads through L1 (u8 rows); no shared memory, no block barriers; lanes 0 and 31 are halo lanes whose own
+//     outputs are discarded (30/32 = 94 % efficiency);
 //   * no vertical halo recomputation inside a segment (a 2-D tile design recomputes ~30 %); segments overlap by the
 //     filter radii only (warm-up rows);
-//   * loads and stores are 128-bit (32-bit for the u8 frame: 4 pixels), coalesced along the warp's strip.
+//   * loads and stores are 128-bit (32-bit for the u8 frame: 4 pixels), coalesced along the warp's strip; the next
+//     row is loaded one iteration ahead and an L2 prefetch runs a few rows further ahead.
 //
 // Borders: the reference filters with SciPy's mode='reflect' (half-sample symmetric).  A SYMMETRIC filter commutes with
 // that extension, so the fused level-0 kernel simply reads the u8 frame through reflected row/column indices and treats
 // the smoothed image on the extended domain as the reflect-extension of the smoothed image (exact in real arithmetic,
 // ~1e-7 relative in fp32).  Decimation does not commute with it, so levels >= 1 run as two streaming kernels (decimate,
 // then gradients) and the gradient kernel reflects its input indices directly.
+// Widths are required to be multiples of 4: then every aligned quad of columns is either fully inside the image or
+// fully outside, and an outside quad is the element-reversed quad at the mirrored position -- all loads stay
+// branch-free 32/128-bit loads.
 //
-// These kernels serve KLT_PRECISION_FAST only.  STRICT (bit-exact) mode and unusual kernel radii use klt_conv.cu.
+// These kernels serve KLT_PRECISION_FAST only.  STRICT (bit-exact) mode and configurations not covered here
+// (other radii, widths not divisible by 4, subsampling 4/8) use the generic tiled kernels of klt_conv.cu.
 #include "klt_common.cuh"
 
 #define WARPS_PER_CTA 4
 #define FULLMASK 0xffffffffu
+#define PREFETCH_ROWS 6
 
 struct StreamTaps {
-    // c[j] multiplies in[x + j - r] (convolution order), zero padded
-    float s[9];      // smoothing (level 0) or pyramid gauss; up to 9 / 11 taps
-    float p[11];
-    float g[7];      // gradient gauss / deriv, radius 3
+    // c[j] multiplies in[x + j - r] (convolution order), zero padded and centred in a fixed-radius slot
+    float s[9];      // level-0 smoothing gauss (radius <= 4)
+    float p[11];     // pyramid gauss (radius 5)
+    float g[7];      // gradient gauss / deriv (radius 3)
     float d[7];
 };
 
+// single reflection (|overshoot| < n is guaranteed by the launchers)
+__device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i - 1 : (i >= n ? 2 * n - i - 1 : i); }
+// quad starting at column c (multiple of 4), W % 4 == 0: position of the quad to load and whether to reverse it
+// (quads further than one quad beyond the image only feed discarded outputs; their address is clamped into the image)
+__device__ __forceinline__ int mirror_quad(int c, int W, bool &rev) {
+    rev = c < 0 || c >= W;
+    const int m = c < 0 ? -c - 4 : (c >= W ? 2 * W - c - 4 : c);
+    return min(max(m, 0), W - 4);
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ float u8_to_f32(unsigned int word, int byte) {
     // 0x4B000000 | b is the float 8388608 + b; exact for b in 0..255, and runs on the ALU/FMA pipes (no I2F)
-    const unsigned int sel = 0x7650u | (unsigned int)byte;   // result byte0 = word.byte, bytes1..3 = 0x4B0000
-    return __uint_as_float(__byte_perm(word, 0x4B000000u, sel)) - 8388608.0f;
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u | (unsigned int)byte)) - 8388608.0f;
 }
 
-__device__ __forceinline__ unsigned int load_u8_quad(const unsigned char *__restrict__ row, int c, int W, bool fast) {
-    if (fast) return __ldg(reinterpret_cast<const unsigned int *>(row + c));
-    unsigned int w = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) w |= (unsigned int)row[klt_reflect(c + i, W)] << (8 * i);
-    return w;
-}
-
-__device__ __forceinline__ float4 load_f32_quad(const float *__restrict__ row, int c, int W, bool fast) {
-    if (fast) return __ldg(reinterpret_cast<const float4 *>(row + c));
-    float4 v;
-    v.x = row[klt_reflect(c, W)]; v.y = row[klt_reflect(c + 1, W)];
-    v.z = row[klt_reflect(c + 2, W)]; v.w = row[klt_reflect(c + 3, W)];
-    return v;
-}
-
-// vertical accumulate-and-shift: acc[m] <- acc[m+1] + c[2R-m]*v ; returns the completed output (old acc[0] + c[2R]*v)
+// vertical accumulate-and-shift: returns the completed output row value; acc[m] <- acc[m+1] + c[2R-1-m]*v
 template <int R>
 __device__ __forceinline__ float vacc(float (&acc)[2 * R], const float *c, float v) {
     const float out = fmaf(c[2 * R], v, acc[0]);
@@ -67,12 +68,17 @@ __device__ __forceinline__ float vacc(float (&acc)[2 * R], const float *c, float
 }
 
 // ---- gradient stage shared by the level-0 kernel and the gradient-only kernel -----------------------------------
-// s[0..3] = this lane's 4 columns of the (smoothed) image row; neighbours come from lanes +-1.
 struct GradState {
     float ax[4][6], ay[4][6];   // pending gx / gy rows (radius 3)
 };
-
-__device__ __forceinline__ void grad_row(GradState &st, const StreamTaps &T, const float (&s)[4], float (&gx)[4], float (&gy)[4]) {
+__device__ __forceinline__ void grad_init(GradState &st) {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int m = 0; m < 6; m++) { st.ax[i][m] = 0.f; st.ay[i][m] = 0.f; }
+}
+// s[0..3] = this lane's 4 columns of the (smoothed) image row; neighbours come from lanes +-1.
+__device__ __forceinline__ void grad_row(GradState &st, const StreamTaps &T, const float (&s)[4], float4 &gx, float4 &gy) {
     float e[10];                 // columns c-3 .. c+6
     e[0] = __shfl_up_sync(FULLMASK, s[1], 1);
     e[1] = __shfl_up_sync(FULLMASK, s[2], 1);
@@ -81,28 +87,21 @@ __device__ __forceinline__ void grad_row(GradState &st, const StreamTaps &T, con
     e[7] = __shfl_down_sync(FULLMASK, s[0], 1);
     e[8] = __shfl_down_sync(FULLMASK, s[1], 1);
     e[9] = __shfl_down_sync(FULLMASK, s[2], 1);
+    float ox[4], oy[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         float hd = T.d[0] * e[i], hg = T.g[0] * e[i];
 #pragma unroll
         for (int j = 1; j < 7; j++) { hd = fmaf(T.d[j], e[i + j], hd); hg = fmaf(T.g[j], e[i + j], hg); }
-        gx[i] = vacc<3>(st.ax[i], T.g, hd);      // gx = gauss_v( deriv_h )
-        gy[i] = vacc<3>(st.ay[i], T.d, hg);      // gy = deriv_v( gauss_h )
+        ox[i] = vacc<3>(st.ax[i], T.g, hd);      // gx = gauss_v( deriv_h )
+        oy[i] = vacc<3>(st.ay[i], T.d, hg);      // gy = deriv_v( gauss_h )
     }
-}
-
-__device__ __forceinline__ void store_quad(float *__restrict__ row, int c, int W, const float (&v)[4]) {
-    if (c + 3 < W) {
-        *reinterpret_cast<float4 *>(row + c) = make_float4(v[0], v[1], v[2], v[3]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            if (c + i < W) row[c + i] = v[i];
-    }
+    gx = make_float4(ox[0], ox[1], ox[2], ox[3]);
+    gy = make_float4(oy[0], oy[1], oy[2], oy[3]);
 }
 
 // ---- level 0: u8 frame -> smoothed image, gradx, grady -----------------------------------------------------------
-// Lane l of a warp owns columns c = x0 + 4*(l-1) .. c+3 where x0 = 120*strip; lanes 1..30 store outputs.
+// Lane l of a warp owns columns c = 120*strip + 4*(l-1) .. c+3; lanes 1..30 store outputs.
 template <int RS>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 stream_level0_kernel(const unsigned char *__restrict__ frames, size_t pitch, size_t frame_stride, float *__restrict__ img,
@@ -114,14 +113,15 @@ stream_level0_kernel(const unsigned char *__restrict__ frames, size_t pitch, siz
     const int ys = blockIdx.y * rows_per_seg, ye = min(H, ys + rows_per_seg);
     const int c = strip * 120 + 4 * (lane - 1);
     const unsigned char *src = frames + (size_t)blockIdx.z * frame_stride;
-    const size_t ob = (size_t)blockIdx.z * out_stride;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | pitch) & 3) == 0;
-    const bool fast = aligned && c >= 0 && c + 3 < W;
-    // halo lanes also need the quad beyond them for the horizontal smooth
-    const bool edge = lane == 0 || lane == 31;
-    const int ce = lane == 0 ? c - 4 : c + 4;
-    const bool fast_e = aligned && ce >= 0 && ce + 3 < W;
+    // own quad and the two neighbour quads (through L1: the neighbour lanes load them as their own)
+    bool rv0, rvl, rvr;
+    const int m0 = mirror_quad(c, W, rv0), ml = mirror_quad(c - 4, W, rvl), mr = mirror_quad(c + 4, W, rvr);
+    const unsigned int sel0 = rv0 ? 0x0123u : 0x3210u, sell = rvl ? 0x0123u : 0x3210u, selr = rvr ? 0x0123u : 0x3210u;
     const bool writer = lane >= 1 && lane <= 30 && c < W;
+    const size_t ooff = (size_t)blockIdx.z * out_stride + (size_t)c;
+    float *p_img = img + ooff + (size_t)ys * out_pitch;   // next row to store
+    float *p_gx = gxo + ooff + (size_t)ys * out_pitch;
+    float *p_gy = gyo + ooff + (size_t)ys * out_pitch;
 
     float sa[4][2 * RS];
 #pragma unroll
@@ -129,57 +129,57 @@ stream_level0_kernel(const unsigned char *__restrict__ frames, size_t pitch, siz
 #pragma unroll
         for (int m = 0; m < 2 * RS; m++) sa[i][m] = 0.f;
     GradState gs;
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int m = 0; m < 6; m++) { gs.ax[i][m] = 0.f; gs.ay[i][m] = 0.f; }
+    grad_init(gs);
 
-    const int t0 = ys - 3 - RS, t1 = ye + 3 + RS;       // input rows [t0, t1)
-    unsigned int wq = load_u8_quad(src + (size_t)klt_reflect(t0, H) * pitch, c, W, fast);
-    unsigned int we = edge ? load_u8_quad(src + (size_t)klt_reflect(t0, H) * pitch, ce, W, fast_e) : 0u;
+    const int t0 = ys - 3 - RS, t1 = ye + 3 + RS;       // input rows [t0, t1) of the reflect-extended frame
+    const unsigned char *row = src + (size_t)reflect1(t0, H) * pitch;
+    unsigned int w0 = __ldg(reinterpret_cast<const unsigned int *>(row + m0));
+    unsigned int wl = __ldg(reinterpret_cast<const unsigned int *>(row + ml));
+    unsigned int wr = __ldg(reinterpret_cast<const unsigned int *>(row + mr));
     for (int t = t0; t < t1; t++) {
-        const unsigned int w_cur = wq, e_cur = we;
-        if (t + 1 < t1) {                                // software prefetch of the next row
-            const unsigned char *nrow = src + (size_t)klt_reflect(t + 1, H) * pitch;
-            wq = load_u8_quad(nrow, c, W, fast);
-            if (edge) we = load_u8_quad(nrow, ce, W, fast_e);
-        }
-        // ---- horizontal smooth ----
+        // ---- consume the row loaded one iteration ago, then immediately issue the next row's loads ----
+        const unsigned int q0 = __byte_perm(w0, 0u, sel0), ql = __byte_perm(wl, 0u, sell), qr = __byte_perm(wr, 0u, selr);
         float u[4 + 2 * RS];                             // columns c-RS .. c+3+RS
-        float f[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) f[i] = u8_to_f32(w_cur, i);
+        for (int i = 0; i < 4; i++) u[RS + i] = u8_to_f32(q0, i);
 #pragma unroll
-        for (int i = 0; i < 4; i++) u[RS + i] = f[i];
-#pragma unroll
-        for (int k = 0; k < RS; k++) {                   // left neighbours: lane-1's f[4-RS+k]; right: lane+1's f[k]
-            u[k] = __shfl_up_sync(FULLMASK, f[4 - RS + k], 1);
-            u[RS + 4 + k] = __shfl_down_sync(FULLMASK, f[k], 1);
+        for (int k = 0; k < RS; k++) {
+            u[k] = u8_to_f32(ql, 4 - RS + k);
+            u[RS + 4 + k] = u8_to_f32(qr, k);
         }
-        if (edge) {
-#pragma unroll
-            for (int k = 0; k < RS; k++) {
-                if (lane == 0) u[k] = u8_to_f32(e_cur, 4 - RS + k);
-                else u[RS + 4 + k] = u8_to_f32(e_cur, k);
-            }
+        {
+            const int tn = min(t + 1, t1 - 1);
+            const unsigned char *nrow = src + (size_t)reflect1(tn, H) * pitch;
+            w0 = __ldg(reinterpret_cast<const unsigned int *>(nrow + m0));
+            wl = __ldg(reinterpret_cast<const unsigned int *>(nrow + ml));
+            wr = __ldg(reinterpret_cast<const unsigned int *>(nrow + mr));
+            const int tp = t + PREFETCH_ROWS;
+            if (tp < t1) prefetch_l2(src + (size_t)reflect1(tp, H) * pitch + m0);
         }
+        // ---- horizontal + vertical smooth: completes smoothed row r = t - RS ----
         float s[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             float h = T.s[0] * u[i];
 #pragma unroll
             for (int j = 1; j < 2 * RS + 1; j++) h = fmaf(T.s[j], u[i + j], h);
-            s[i] = vacc<RS>(sa[i], T.s, h);              // vertical smooth: completes row t - RS
+            s[i] = vacc<RS>(sa[i], T.s, h);
         }
         const int r = t - RS;
-        if (r < ys - 3) continue;                        // vertical smooth still warming up
-        if (writer && r >= ys && r < ye) store_quad(img + ob + (size_t)r * out_pitch, c, W, s);
-        float gx[4], gy[4];
-        grad_row(gs, T, s, gx, gy);
-        const int q = r - 3;
-        if (writer && q >= ys) {                         // q < ye by construction
-            store_quad(gxo + ob + (size_t)q * out_pitch, c, W, gx);
-            store_quad(gyo + ob + (size_t)q * out_pitch, c, W, gy);
+        if (r < ys - 3) continue;                        // vertical smooth still warming up (warp-uniform)
+        if (r >= ys && r < ye) {
+            if (writer) *reinterpret_cast<float4 *>(p_img) = make_float4(s[0], s[1], s[2], s[3]);
+            p_img += out_pitch;
+        }
+        float4 gx, gy;
+        grad_row(gs, T, s, gx, gy);                      // completes gradient row q = r - 3
+        if (r - 3 >= ys) {                               // q < ye by construction
+            if (writer) {
+                *reinterpret_cast<float4 *>(p_gx) = gx;
+                *reinterpret_cast<float4 *>(p_gy) = gy;
+            }
+            p_gx += out_pitch;
+            p_gy += out_pitch;
         }
     }
 }
@@ -195,35 +195,66 @@ stream_grad_kernel(const float *__restrict__ in, int in_pitch, size_t in_stride,
     const int ys = blockIdx.y * rows_per_seg, ye = min(H, ys + rows_per_seg);
     const int c = strip * 120 + 4 * (lane - 1);
     const float *src = in + (size_t)blockIdx.z * in_stride;
-    const size_t ob = (size_t)blockIdx.z * out_stride;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (in_pitch & 3) == 0;
-    const bool fast = aligned && c >= 0 && c + 3 < W;
+    bool rev;
+    const int m0 = mirror_quad(c, W, rev);
+    const bool warp_rev = __any_sync(FULLMASK, rev);      // interior warps skip the reversal code entirely
     const bool writer = lane >= 1 && lane <= 30 && c < W;
+    const size_t ooff = (size_t)blockIdx.z * out_stride + (size_t)c + (size_t)ys * out_pitch;
+    float *p_gx = gxo + ooff, *p_gy = gyo + ooff;
     GradState gs;
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int m = 0; m < 6; m++) { gs.ax[i][m] = 0.f; gs.ay[i][m] = 0.f; }
+    grad_init(gs);
     const int t0 = ys - 3, t1 = ye + 3;
-    float4 nxt = load_f32_quad(src + (size_t)klt_reflect(t0, H) * in_pitch, c, W, fast);
+    float4 nxt = __ldg(reinterpret_cast<const float4 *>(src + (size_t)reflect1(t0, H) * in_pitch + m0));
     for (int t = t0; t < t1; t++) {
-        const float4 cur = nxt;
-        if (t + 1 < t1) nxt = load_f32_quad(src + (size_t)klt_reflect(t + 1, H) * in_pitch, c, W, fast);
-        const float s[4] = {cur.x, cur.y, cur.z, cur.w};
-        float gx[4], gy[4];
+        float s[4] = {nxt.x, nxt.y, nxt.z, nxt.w};
+        if (warp_rev && rev) { s[0] = nxt.w; s[1] = nxt.z; s[2] = nxt.y; s[3] = nxt.x; }
+        {
+            const int tn = min(t + 1, t1 - 1);
+            nxt = __ldg(reinterpret_cast<const float4 *>(src + (size_t)reflect1(tn, H) * in_pitch + m0));
+            const int tp = t + PREFETCH_ROWS;
+            if (tp < t1) prefetch_l2(src + (size_t)reflect1(tp, H) * in_pitch + m0);
+        }
+        float4 gx, gy;
         grad_row(gs, T, s, gx, gy);
-        const int q = t - 3;
-        if (writer && q >= ys) {
-            store_quad(gxo + ob + (size_t)q * out_pitch, c, W, gx);
-            store_quad(gyo + ob + (size_t)q * out_pitch, c, W, gy);
+        if (t - 3 >= ys) {
+            if (writer) {
+                *reinterpret_cast<float4 *>(p_gx) = gx;
+                *reinterpret_cast<float4 *>(p_gy) = gy;
+            }
+            p_gx += out_pitch;
+            p_gy += out_pitch;
         }
     }
 }
 
 // ---- pyramid step for subsampling 2: out[Y][X] = smooth11(in)[2Y+1][2X+1] -----------------------------------------
-// Lane owns output columns X..X+3 (X = 128*strip + 4*lane) = input columns 2X..2X+7; it needs 2X-4 .. 2X+12.
-// Vertical: input rows arrive in (even, odd) pairs; output Y completes with even row 2Y+6.  Five partial outputs are
-// pending per column; 11 FMAs per column per output row, no moves.
+// Lane l owns output columns X..X+3, X = 120*strip + 4*(l-1), i.e. input columns ci = 2X .. ci+7; it needs ci-4 .. ci+12.
+// Lanes 0 and 31 only feed their neighbours.  Vertical: input rows arrive in (even, odd) pairs; output Y completes with
+// even row 2Y+6.  Five partial outputs are pending per column; 11 FMAs per column per output row, no moves.
+struct RowPair { float4 ea, eb, oa, ob; };   // even row: quads at ci, ci+4; odd row: the same
+
+__device__ __forceinline__ void down2_hrow(const StreamTaps &T, float4 a, float4 b, bool warp_rev, bool rva, bool rvb,
+                                           float (&h)[4]) {
+    if (warp_rev) {                                  // warp-uniform: only warps touching an image edge reverse quads
+        if (rva) a = make_float4(a.w, a.z, a.y, a.x);
+        if (rvb) b = make_float4(b.w, b.z, b.y, b.x);
+    }
+    float e[17];                                     // input columns ci-4 .. ci+12
+    e[4] = a.x; e[5] = a.y; e[6] = a.z; e[7] = a.w; e[8] = b.x; e[9] = b.y; e[10] = b.z; e[11] = b.w;
+    e[0] = __shfl_up_sync(FULLMASK, b.x, 1); e[1] = __shfl_up_sync(FULLMASK, b.y, 1);
+    e[2] = __shfl_up_sync(FULLMASK, b.z, 1); e[3] = __shfl_up_sync(FULLMASK, b.w, 1);
+    e[12] = __shfl_down_sync(FULLMASK, a.x, 1); e[13] = __shfl_down_sync(FULLMASK, a.y, 1);
+    e[14] = __shfl_down_sync(FULLMASK, a.z, 1); e[15] = __shfl_down_sync(FULLMASK, a.w, 1);
+    e[16] = __shfl_down_sync(FULLMASK, b.x, 1);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {                    // output column X+i is centred on input column ci + 2i + 1
+        float acc = T.p[0] * e[2 * i];
+#pragma unroll
+        for (int j = 1; j < 11; j++) acc = fmaf(T.p[j], e[2 * i + j], acc);
+        h[i] = acc;
+    }
+}
+
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 stream_down2_kernel(const float *__restrict__ in, int in_pitch, size_t in_stride, int W, int H, float *__restrict__ out,
                     int out_pitch, size_t out_stride, int OW, int OH, int rows_per_seg, int n_strips,
@@ -232,14 +263,13 @@ stream_down2_kernel(const float *__restrict__ in, int in_pitch, size_t in_stride
     const int strip = blockIdx.x * WARPS_PER_CTA + warp;
     if (strip >= n_strips) return;
     const int ys = blockIdx.y * rows_per_seg, ye = min(OH, ys + rows_per_seg);
-    const int X = strip * 128 + 4 * lane;
+    const int X = strip * 120 + 4 * (lane - 1);
     const int ci = 2 * X;
     const float *src = in + (size_t)blockIdx.z * in_stride;
-    float *dst = out + (size_t)blockIdx.z * out_stride;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (in_pitch & 3) == 0;
-    const bool fast0 = aligned && ci >= 0 && ci + 3 < W, fast1 = aligned && ci + 7 < W;
-    const bool fastl = aligned && ci - 4 >= 0 && ci - 1 < W;
-    const bool fastr0 = aligned && ci + 11 < W, fastr1 = aligned && ci + 15 < W;
+    bool rva, rvb;
+    const int ma = mirror_quad(ci, W, rva), mb = mirror_quad(ci + 4, W, rvb);
+    const bool writer = lane >= 1 && lane <= 30 && X < OW;
+    float *p_out = out + (size_t)blockIdx.z * out_stride + (size_t)ys * out_pitch + X;
 
     float P[4][5];
 #pragma unroll
@@ -247,59 +277,55 @@ stream_down2_kernel(const float *__restrict__ in, int in_pitch, size_t in_stride
 #pragma unroll
         for (int m = 0; m < 5; m++) P[i][m] = 0.f;
 
-    // horizontal 11-tap at the 4 sampled columns of one input row (reflect-mapped row index)
-    auto hrow = [&](int r, float (&h)[4]) {
-        const float *row = src + (size_t)klt_reflect(r, H) * in_pitch;
-        const float4 a = load_f32_quad(row, ci, W, fast0), b = load_f32_quad(row, ci + 4, W, fast1);
-        float e[17];                                     // input columns ci-4 .. ci+12
-        e[4] = a.x; e[5] = a.y; e[6] = a.z; e[7] = a.w; e[8] = b.x; e[9] = b.y; e[10] = b.z; e[11] = b.w;
-        e[0] = __shfl_up_sync(FULLMASK, b.x, 1); e[1] = __shfl_up_sync(FULLMASK, b.y, 1);
-        e[2] = __shfl_up_sync(FULLMASK, b.z, 1); e[3] = __shfl_up_sync(FULLMASK, b.w, 1);
-        e[12] = __shfl_down_sync(FULLMASK, a.x, 1); e[13] = __shfl_down_sync(FULLMASK, a.y, 1);
-        e[14] = __shfl_down_sync(FULLMASK, a.z, 1); e[15] = __shfl_down_sync(FULLMASK, a.w, 1);
-        e[16] = __shfl_down_sync(FULLMASK, b.x, 1);
-        if (lane == 0) {
-            const float4 l = load_f32_quad(row, ci - 4, W, fastl);
-            e[0] = l.x; e[1] = l.y; e[2] = l.z; e[3] = l.w;
-        } else if (lane == 31) {
-            const float4 r0 = load_f32_quad(row, ci + 8, W, fastr0);
-            e[12] = r0.x; e[13] = r0.y; e[14] = r0.z; e[15] = r0.w;
-            e[16] = fastr1 ? row[ci + 12] : row[klt_reflect(ci + 12, W)];
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) {                    // output column X+i is centred on input column ci + 2i + 1
-            float acc = T.p[0] * e[2 * i];               // e index of (ci + 2i + 1 - 5) = 2i
-#pragma unroll
-            for (int j = 1; j < 11; j++) acc = fmaf(T.p[j], e[2 * i + j], acc);
-            h[i] = acc;
-        }
+    auto load_pair = [&](int j, RowPair &rp) {
+        const float *re = src + (size_t)reflect1(2 * j, H) * in_pitch, *ro = src + (size_t)reflect1(2 * j + 1, H) * in_pitch;
+        rp.ea = __ldg(reinterpret_cast<const float4 *>(re + ma)); rp.eb = __ldg(reinterpret_cast<const float4 *>(re + mb));
+        rp.oa = __ldg(reinterpret_cast<const float4 *>(ro + ma)); rp.ob = __ldg(reinterpret_cast<const float4 *>(ro + mb));
     };
-
     // c[j] multiplies in[2Y+1 + j - 5]; input row r contributes to output Y with j = r - 2Y + 4
-    const int j0 = ys - 3;                               // first pair index: even row 2*j0 completes output j0-3 (discarded)
-    for (int j = j0; j < ye + 3; j++) {
+    const int j0 = ys - 2, j1 = ye + 3;                  // pair j: rows 2j, 2j+1; even row 2j completes output Y = j - 3
+    const bool warp_rev = __any_sync(FULLMASK, rva || rvb);
+    auto step = [&](const RowPair &cur, int j) {
         float he[4], ho[4];
-        hrow(2 * j, he);
-        hrow(2 * j + 1, ho);
-        const int Y = j - 3;
+        down2_hrow(T, cur.ea, cur.eb, warp_rev, rva, rvb, he);
+        down2_hrow(T, cur.oa, cur.ob, warp_rev, rva, rvb, ho);
         float o[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            // even row 2j: outputs Y=j-3..j+2 with j_tap = 10, 8, 6, 4, 2, 0
+            // even row 2j: outputs Y=j-3..j+2 take taps 10, 8, 6, 4, 2, 0; odd row 2j+1: Y=j-2..j+2 take 9, 7, 5, 3, 1
             o[i] = fmaf(T.p[10], he[i], P[i][0]);
-            const float t0 = fmaf(T.p[8], he[i], P[i][1]);
-            const float t1 = fmaf(T.p[6], he[i], P[i][2]);
-            const float t2 = fmaf(T.p[4], he[i], P[i][3]);
-            const float t3 = fmaf(T.p[2], he[i], P[i][4]);
-            const float t4 = T.p[0] * he[i];
-            // odd row 2j+1: outputs Y=j-2..j+2 with j_tap = 9, 7, 5, 3, 1
-            P[i][0] = fmaf(T.p[9], ho[i], t0);
-            P[i][1] = fmaf(T.p[7], ho[i], t1);
-            P[i][2] = fmaf(T.p[5], ho[i], t2);
-            P[i][3] = fmaf(T.p[3], ho[i], t3);
-            P[i][4] = fmaf(T.p[1], ho[i], t4);
+            const float a0 = fmaf(T.p[8], he[i], P[i][1]);
+            const float a1 = fmaf(T.p[6], he[i], P[i][2]);
+            const float a2 = fmaf(T.p[4], he[i], P[i][3]);
+            const float a3 = fmaf(T.p[2], he[i], P[i][4]);
+            const float a4 = T.p[0] * he[i];
+            P[i][0] = fmaf(T.p[9], ho[i], a0);
+            P[i][1] = fmaf(T.p[7], ho[i], a1);
+            P[i][2] = fmaf(T.p[5], ho[i], a2);
+            P[i][3] = fmaf(T.p[3], ho[i], a3);
+            P[i][4] = fmaf(T.p[1], ho[i], a4);
         }
-        if (Y >= ys && Y < ye && X < OW) store_quad(dst + (size_t)Y * out_pitch, X, OW, o);
+        if (j - 3 >= ys) {                               // Y = j - 3 < ye by construction
+            if (writer) *reinterpret_cast<float4 *>(p_out) = make_float4(o[0], o[1], o[2], o[3]);
+            p_out += out_pitch;
+        }
+        if (j + 3 < j1) {
+            prefetch_l2(src + (size_t)reflect1(2 * j + 6, H) * in_pitch + ma);
+            prefetch_l2(src + (size_t)reflect1(2 * j + 7, H) * in_pitch + ma);
+        }
+    };
+    // two row-pair buffers, loop unrolled by two: each buffer is reloaded right after it has been consumed, one full
+    // step before its next use, without register-to-register copies
+    RowPair A, B;
+    load_pair(j0, A);
+    load_pair(min(j0 + 1, j1 - 1), B);
+    for (int j = j0; j < j1; j += 2) {
+        step(A, j);
+        load_pair(min(j + 2, j1 - 1), A);
+        if (j + 1 < j1) {
+            step(B, j + 1);
+            load_pair(min(j + 3, j1 - 1), B);
+        }
     }
 }
 
@@ -335,6 +361,7 @@ static bool is_symmetric(const klt_kernel1d *k) {
         if (fabs(k->taps[i] - k->taps[k->n - 1 - i]) > 2.220446049250313e-16) return false;
     return true;
 }
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // Returns 1 if the streaming kernel was launched, 0 if the configuration is not covered (caller falls back), <0 on error.
 int klt_stream_level0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t frame_stride, klt_pyr *p,
@@ -348,7 +375,8 @@ int klt_stream_level0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t 
     if (!fill_taps(&taps->grad_gauss, T.g, 7) || !fill_taps(&taps->grad_deriv, T.d, 7)) return 0;
     for (int j = 0; j < 11; j++) T.p[j] = 0.f;
     const int W = p->w, H = p->h;
-    if (W < 16 || H < 16) return 0;
+    if (W < 16 || H < 16 || (W & 3)) return 0;
+    if ((reinterpret_cast<uintptr_t>(frames) & 3) || (pitch & 3) || (frame_stride & 3)) return 0;
     const int n_strips = (W + 119) / 120;
     const int strip_ctas = (n_strips + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     int rows = 0;
@@ -383,7 +411,7 @@ int klt_stream_grad(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps) {
     for (int j = 0; j < 9; j++) T.s[j] = 0.f;
     for (int j = 0; j < 11; j++) T.p[j] = 0.f;
     const LevelDesc &a = p->lv[level];
-    if (a.w < 16 || a.h < 8) return 0;
+    if (a.w < 16 || a.h < 8 || (a.w & 3) || !aligned16(p->level(0, 0, level)) || (p->plane_floats & 3)) return 0;
     const int n_strips = (a.w + 119) / 120;
     const int strip_ctas = (n_strips + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const int rows = pick_rows_per_seg(ctx, stream_grad_kernel, a.h, strip_ctas, p->batch, 24);
@@ -403,8 +431,9 @@ int klt_stream_down2(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps) 
     for (int j = 0; j < 9; j++) T.s[j] = 0.f;
     for (int j = 0; j < 7; j++) { T.g[j] = 0.f; T.d[j] = 0.f; }
     const LevelDesc &a = p->lv[level - 1], &b = p->lv[level];
-    if (b.w < 8 || b.h < 8 || a.w < 16) return 0;
-    const int n_strips = (b.w + 127) / 128;
+    if (b.w < 8 || b.h < 8 || a.w < 32 || a.h < 16 || (a.w & 3) || (b.w & 3)) return 0;
+    if (!aligned16(p->level(0, 0, level - 1)) || !aligned16(p->level(0, 0, level)) || (p->plane_floats & 3)) return 0;
+    const int n_strips = (b.w + 119) / 120;
     const int strip_ctas = (n_strips + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const int rows = pick_rows_per_seg(ctx, stream_down2_kernel, b.h, strip_ctas, p->batch, 24);
     dim3 grid(strip_ctas, (b.h + rows - 1) / rows, p->batch), block(WARPS_PER_CTA * 32);
