@@ -265,6 +265,7 @@ int klt_pyr_create(klt_ctx *ctx, int w, int h, int n_levels, int subsampling, in
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
     klt_pyr *p = new klt_pyr();
     p->w = w; p->h = h; p->n_levels = n_levels; p->ss = subsampling; p->batch = batch;
+    p->precision = KLT_PRECISION_STRICT;
     size_t off = 0;
     int lw = w, lh = h;
     for (int l = 0; l < n_levels; l++) {
@@ -335,6 +336,7 @@ int klt_pyr_build_u8(klt_ctx *ctx, klt_pyr *p, const uint8_t *frames, size_t pit
     if ((rc = check_taps(ctx, taps))) return rc;
     if (pitch < (size_t)p->w) return klt_fail(ctx, KLT_ERR_INVALID, "pitch %zu smaller than width %d", pitch, p->w);
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    p->precision = precision;
     const uint8_t *dframes = frames;
     if (!klt_is_device_ptr(frames)) {
         const size_t bytes = (size_t)(p->batch - 1) * frame_stride + (size_t)(p->h - 1) * pitch + p->w;
@@ -361,6 +363,7 @@ int klt_pyr_build_f32(klt_ctx *ctx, klt_pyr *p, const float *images, size_t pitc
     if ((rc = check_taps(ctx, taps))) return rc;
     if (pitch < (size_t)p->w) return klt_fail(ctx, KLT_ERR_INVALID, "pitch %zu smaller than width %d", pitch, p->w);
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    p->precision = precision;
     if (already_smoothed) {
         for (int b = 0; b < p->batch; b++)
             KLT_CUDA(ctx, cudaMemcpy2DAsync(p->level(0, b, 0), p->lv[0].pitch * sizeof(float), images + (size_t)b * frame_stride,

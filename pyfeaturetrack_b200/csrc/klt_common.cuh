@@ -28,6 +28,7 @@ struct LevelDesc {
 
 struct klt_pyr {
     int w, h, n_levels, ss, batch;
+    int precision;            // KLT_PRECISION_* of the last build (selects the tracking kernel's arithmetic)
     LevelDesc lv[KLT_MAX_LEVELS];
     size_t plane_floats;      // floats of ONE image's ONE component over all levels
     float *base;              // [which(3)][image(batch)][plane_floats]

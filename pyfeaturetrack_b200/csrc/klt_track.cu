@@ -205,8 +205,177 @@ lk_track_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ xs, do
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// FAST tracking kernel (used when the pyramids were built in KLT_PRECISION_FAST): same algorithm and status logic,
+// float32 bilinear weights and shuffle reductions instead of the reference's exact operation order.
+// Mapping: one LANE per window ROW, G = 8 (W <= 7) or 16 (W <= 15) lanes per feature, 32/G features per warp.
+// A lane loads the W+1 source pixels of its two source rows once per patch (horizontally adjacent samples share
+// corners: 2.3 loads per sample instead of 4), keeps its row of the three templates in registers, accumulates the five
+// window sums over its row with FMAs, and the G lanes of a feature combine them with log2(G) shuffle steps.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void patch_row(const float *__restrict__ img, int pitch, int ix, int iy, int j, float w00,
+                                          float w01, float w10, float w11, float (&out)[W]) {
+    const float *p = img + (size_t)(iy + j - W / 2) * pitch + (ix - W / 2);
+    float a0[W + 1], a1[W + 1];
+#pragma unroll
+    for (int i = 0; i < W + 1; i++) { a0[i] = __ldg(p + i); a1[i] = __ldg(p + pitch + i); }
+#pragma unroll
+    for (int i = 0; i < W; i++) out[i] = fmaf(w11, a1[i + 1], fmaf(w10, a1[i], fmaf(w01, a0[i + 1], w00 * a0[i])));
+}
+
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int W>
+__global__ void __launch_bounds__(128)
+lk_track_rows_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ xs, double *__restrict__ ys,
+                     int *__restrict__ vals, unsigned long long *__restrict__ iters_total, int *__restrict__ assert_flag) {
+    constexpr int G = W <= 7 ? 8 : 16;
+    constexpr int FPW = 32 / G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = (blockIdx.x * (blockDim.x >> 5) + warp) * FPW + lane / G;
+    const int j = lane % G;                       // window row handled by this lane
+    const bool row_ok = j < W;
+    bool alive = f < A.total;
+    if (alive) alive = vals[f] >= 0;              // trackFeatures.py:253
+    if (!__any_sync(0xffffffffu, alive)) return;
+    const int image = alive ? f / A.n_per_image : 0;
+    constexpr int hw = W / 2;
+    const double ss = (double)A.ss;
+    double xloc = alive ? xs[f] : 0.0, yloc = alive ? ys[f] : 0.0;
+    for (int r = A.n_levels - 1; r >= 0; r--) { xloc /= ss; yloc /= ss; }
+    double xout = xloc, yout = yloc;
+    int st = KLT_TRACKED;
+    unsigned int my_iters = 0;
+    const bool was_alive = alive;
+
+    for (int r = A.n_levels - 1; r >= 0; r--) {
+        xloc *= ss; yloc *= ss; xout *= ss; yout *= ss;
+        const int nc = A.p1.lv[r].w, nr = A.p1.lv[r].h, pitch = A.p1.lv[r].pitch;
+        const float *I1 = A.p1.level(0, image, r), *GX1 = A.p1.level(1, image, r), *GY1 = A.p1.level(2, image, r);
+        const float *I2 = A.p2.level(0, image, r), *GX2 = A.p2.level(1, image, r), *GY2 = A.p2.level(2, image, r);
+        float T[W], Tgx[W], Tgy[W];
+        {
+            const float x1 = (float)xloc, y1 = (float)yloc;
+            const int ix = (int)x1, iy = (int)y1;
+            if (alive && !(ix - hw >= 0 && iy - hw >= 0 && ix + hw + 2 <= nc && iy + hw + 2 <= nr)) {   // pyx:35
+                if (j == 0) atomicExch(assert_flag, 1);
+                st = KLT_INTERNAL_ASSERT;
+                alive = false;
+            }
+            if (alive && row_ok) {
+                const float ax = x1 - (float)ix, ay = y1 - (float)iy;
+                const float w11 = ax * ay, w01 = ax - w11, w10 = ay - w11, w00 = 1.f - ax - ay + w11;
+                patch_row<W>(I1, pitch, ix, iy, j, w00, w01, w10, w11, T);
+                patch_row<W>(GX1, pitch, ix, iy, j, w00, w01, w10, w11, Tgx);
+                patch_row<W>(GY1, pitch, ix, iy, j, w00, w01, w10, w11, Tgy);
+            } else {
+#pragma unroll
+                for (int i = 0; i < W; i++) { T[i] = 0.f; Tgx[i] = 0.f; Tgy[i] = 0.f; }
+            }
+        }
+        float x2 = (float)xout, y2 = (float)yout;
+        int status = KLT_TRACKED, iteration = 0;
+        const float fnc = (float)nc, fnr = (float)nr, fhw = (float)hw;
+        bool iterating = alive;
+        while (__any_sync(0xffffffffu, iterating)) {
+            if (iterating && (x2 - fhw < 0.f || fnc - (x2 + fhw) < 1.001f || y2 - fhw < 0.f || fnr - (y2 + fhw) < 1.001f)) {
+                status = KLT_OOB;
+                iterating = false;
+            }
+            float gxx = 0.f, gxy = 0.f, gyy = 0.f, ex = 0.f, ey = 0.f;
+            if (iterating && row_ok) {
+                const int ix = (int)x2, iy = (int)y2;
+                const float ax = x2 - (float)ix, ay = y2 - (float)iy;
+                const float w11 = ax * ay, w01 = ax - w11, w10 = ay - w11, w00 = 1.f - ax - ay + w11;
+                float P[W], Px[W], Py[W];
+                patch_row<W>(I2, pitch, ix, iy, j, w00, w01, w10, w11, P);
+                patch_row<W>(GX2, pitch, ix, iy, j, w00, w01, w10, w11, Px);
+                patch_row<W>(GY2, pitch, ix, iy, j, w00, w01, w10, w11, Py);
+#pragma unroll
+                for (int i = 0; i < W; i++) {
+                    const float diff = T[i] - P[i], gx = Tgx[i] + Px[i], gy = Tgy[i] + Py[i];
+                    gxx = fmaf(gx, gx, gxx); gxy = fmaf(gx, gy, gxy); gyy = fmaf(gy, gy, gyy);
+                    ex = fmaf(diff, gx, ex); ey = fmaf(diff, gy, ey);
+                }
+            }
+            gxx = group_sum<G>(gxx); gxy = group_sum<G>(gxy); gyy = group_sum<G>(gyy);
+            ex = group_sum<G>(ex) * A.step_factor; ey = group_sum<G>(ey) * A.step_factor;
+            if (iterating) {
+                const float det = __fsub_rn(__fmul_rn(gxx, gyy), __fmul_rn(gxy, gxy));
+                if (det < A.small_det) {
+                    status = KLT_SMALL_DET;
+                    iterating = false;
+                } else {
+                    const float dx = __fdiv_rn(__fsub_rn(__fmul_rn(gyy, ex), __fmul_rn(gxy, ey)), det);
+                    const float dy = __fdiv_rn(__fsub_rn(__fmul_rn(gxx, ey), __fmul_rn(gxy, ex)), det);
+                    x2 += dx; y2 += dy;
+                    iteration++;
+                    if (!((fabsf(dx) >= A.th || fabsf(dy) >= A.th) && iteration < A.max_iterations)) iterating = false;
+                }
+            }
+        }
+        my_iters += iteration;
+        if (alive) {
+            const double x2d = (double)x2, y2d = (double)y2, hwd = W / 2.0;
+            if (x2d - hwd < 0.0 || (double)nc - (x2d + hwd) < 1.001 || y2d - hwd < 0.0 || (double)nr - (y2d + hwd) < 1.001)
+                status = KLT_OOB;
+        }
+        const bool need_res = alive && status == KLT_TRACKED && A.has_max_residue;
+        if (__any_sync(0xffffffffu, need_res)) {
+            float res = 0.f;
+            if (need_res && row_ok) {
+                const int ix = (int)x2, iy = (int)y2;
+                const float ax = x2 - (float)ix, ay = y2 - (float)iy;
+                const float w11 = ax * ay, w01 = ax - w11, w10 = ay - w11, w00 = 1.f - ax - ay + w11;
+                float P[W];
+                patch_row<W>(I2, pitch, ix, iy, j, w00, w01, w10, w11, P);
+#pragma unroll
+                for (int i = 0; i < W; i++) res += fabsf(T[i] - P[i]);
+            }
+            res = group_sum<G>(res) / (float)(W * W);
+            if (need_res && res > A.max_residue) status = KLT_LARGE_RESIDUE;
+        }
+        if (alive) {
+            xout = (double)x2; yout = (double)y2;
+            if (A.retain) st = KLT_TRACKED;
+            else if (status == KLT_SMALL_DET || status == KLT_OOB || status == KLT_LARGE_RESIDUE) st = status;
+            else if (iteration >= A.max_iterations) st = KLT_MAX_ITERATIONS;
+            else st = KLT_TRACKED;
+            if (st == KLT_SMALL_DET || st == KLT_OOB) alive = false;                           // :284-285
+        }
+    }
+    if (was_alive && j == 0) {
+        if (my_iters) atomicAdd(iters_total, (unsigned long long)my_iters);
+        if (st == KLT_INTERNAL_ASSERT) return;
+        const int W0 = A.p1.lv[0].w, H0 = A.p1.lv[0].h;
+        const bool oob = xout < A.borderx || xout > (double)(W0 - 1) - A.borderx || yout < A.bordery ||
+                         yout > (double)(H0 - 1) - A.bordery;
+        if (st == KLT_OOB || oob) { xs[f] = -1.0; ys[f] = -1.0; vals[f] = KLT_OOB; }
+        else if (st == KLT_SMALL_DET || st == KLT_LARGE_RESIDUE || st == KLT_MAX_ITERATIONS) { xs[f] = -1.0; ys[f] = -1.0; vals[f] = st; }
+        else { xs[f] = xout; ys[f] = yout; vals[f] = KLT_TRACKED; }
+    }
+}
+
+template <int W>
+static int launch_rows(klt_ctx *ctx, const TrackArgs &A, double *x, double *y, int32_t *v, unsigned long long *it, int *af) {
+    constexpr int FPW = 32 / (W <= 7 ? 8 : 16);
+    const int per_block = 4 * FPW;
+    const int blocks = (A.total + per_block - 1) / per_block;
+    KLT_LAUNCH(ctx, "lk_track_rows", 0.0, (lk_track_rows_kernel<W><<<blocks, 128, 0, ctx->stream>>>(A, x, y, v, it, af)));
+    return KLT_OK;
+}
+
 int klt_launch_track(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const klt_pyr *p2, int n_per_image,
                      double *x_dev, double *y_dev, int32_t *val_dev, unsigned long long *iters_dev, int *assert_dev) {
+    // bit-exact arithmetic only pays off on bit-exact (STRICT) pyramids
+    const bool exact = p1->precision == KLT_PRECISION_STRICT && p2->precision == KLT_PRECISION_STRICT;
     TrackArgs A;
     A.p1 = *p1; A.p2 = *p2;
     A.w = p->window_width; A.h = p->window_height;
@@ -218,6 +387,18 @@ int klt_launch_track(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const
     A.borderx = p->borderx; A.bordery = p->bordery;
     A.n_per_image = n_per_image; A.total = n_per_image * p1->batch;
     if (A.total <= 0) return KLT_OK;
+    if (!exact && A.w == A.h) {          // FAST pyramids: float32 row-per-lane kernel for the common window sizes
+        switch (A.w) {
+            case 3: return launch_rows<3>(ctx, A, x_dev, y_dev, val_dev, iters_dev, assert_dev);
+            case 5: return launch_rows<5>(ctx, A, x_dev, y_dev, val_dev, iters_dev, assert_dev);
+            case 7: return launch_rows<7>(ctx, A, x_dev, y_dev, val_dev, iters_dev, assert_dev);
+            case 9: return launch_rows<9>(ctx, A, x_dev, y_dev, val_dev, iters_dev, assert_dev);
+            case 11: return launch_rows<11>(ctx, A, x_dev, y_dev, val_dev, iters_dev, assert_dev);
+            case 13: return launch_rows<13>(ctx, A, x_dev, y_dev, val_dev, iters_dev, assert_dev);
+            case 15: return launch_rows<15>(ctx, A, x_dev, y_dev, val_dev, iters_dev, assert_dev);
+            default: break;               // larger windows: the generic (exact-order) kernel below
+        }
+    }
     const int n = A.w * A.h;
     int warps = 4;
     size_t smem = (size_t)warps * 8 * n * sizeof(float);
