@@ -134,6 +134,10 @@ int klt_ctx_create(int device, void *stream, klt_ctx **out) {
     }
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 16; i++) cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->compute_done, cudaEventDisableTiming);
+    ctx->frames_dev = nullptr; ctx->frames_bytes = 0;
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->num_sms = prop.multiProcessorCount;
@@ -154,6 +158,10 @@ int klt_ctx_destroy(klt_ctx *ctx) {
     prof_resolve(ctx);
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->frames_dev) cudaFree(ctx->frames_dev);
+    cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->chunk_ev[i]);
+    cudaEventDestroy(ctx->compute_done);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
@@ -307,26 +315,44 @@ static int check_taps(klt_ctx *ctx, const klt_taps *t) {
 // levels 1..L-1 and all gradients, given level 0 intensity already in place (level0_grad_done: the fused level-0
 // kernel has already written gradx/grady of level 0).  FAST precision takes the warp-streaming kernels where they
 // cover the configuration; everything else runs the generic tiled kernels.
-static int build_rest(klt_ctx *ctx, klt_pyr *p, const klt_taps *taps, int precision, bool level0_grad_done = false) {
+static int build_rest(klt_ctx *ctx, klt_pyr *p, const klt_taps *taps, int precision, bool level0_grad_done = false,
+                      int first = 0, int count = -1) {
+    if (count < 0) count = p->batch;
     int rc;
     const size_t stride = p->plane_floats;
     const bool fast = precision == KLT_PRECISION_FAST;
     for (int l = 1; l < p->n_levels; l++) {
         const LevelDesc &a = p->lv[l - 1], &b = p->lv[l];
-        rc = fast ? klt_stream_down2(ctx, p, l, taps) : 0;
+        rc = fast ? klt_stream_down2(ctx, p, l, taps, first, count) : 0;
         if (rc < 0) return rc;
-        if (rc == 0 && (rc = klt_launch_pyr_down(ctx, p->level(0, 0, l - 1), a.pitch, stride, a.w, a.h, p->level(0, 0, l), b.pitch,
-                                                 stride, b.w, b.h, p->ss, p->batch, &taps->pyramid, precision))) return rc;
+        if (rc == 0 && (rc = klt_launch_pyr_down(ctx, p->level(0, first, l - 1), a.pitch, stride, a.w, a.h, p->level(0, first, l),
+                                                 b.pitch, stride, b.w, b.h, p->ss, count, &taps->pyramid, precision))) return rc;
     }
     for (int l = level0_grad_done ? 1 : 0; l < p->n_levels; l++) {
         const LevelDesc &a = p->lv[l];
-        rc = fast ? klt_stream_grad(ctx, p, l, taps) : 0;
+        rc = fast ? klt_stream_grad(ctx, p, l, taps, first, count) : 0;
         if (rc < 0) return rc;
-        if (rc == 0 && (rc = klt_launch_grad_pair(ctx, p->level(0, 0, l), a.pitch, stride, p->level(1, 0, l), p->level(2, 0, l),
-                                                  a.pitch, stride, a.w, a.h, p->batch, &taps->grad_gauss, &taps->grad_deriv,
-                                                  precision))) return rc;
+        if (rc == 0 && (rc = klt_launch_grad_pair(ctx, p->level(0, first, l), a.pitch, stride, p->level(1, first, l),
+                                                  p->level(2, first, l), a.pitch, stride, a.w, a.h, count, &taps->grad_gauss,
+                                                  &taps->grad_deriv, precision))) return rc;
     }
     return KLT_OK;
+}
+
+// device frames -> pyramids for images [first, first+count); dframes points at image `first`
+static int build_u8_device(klt_ctx *ctx, klt_pyr *p, const uint8_t *dframes, size_t pitch, size_t frame_stride,
+                           const klt_taps *taps, int precision, int first, int count) {
+    int rc;
+    if (precision == KLT_PRECISION_FAST) {
+        // fused u8 -> smoothed image + gradient pair of level 0 (one read of the frame, three writes)
+        rc = klt_stream_level0(ctx, dframes, pitch, frame_stride, p, taps, first, count);
+        if (rc < 0) return rc;
+        if (rc == 1) return build_rest(ctx, p, taps, precision, true, first, count);
+    }
+    // img.convert("F") + KLTComputeSmoothedImage (trackFeatures.py:165-166): one kernel, u8 in, f32 out
+    if ((rc = klt_launch_conv_sep_u8(ctx, dframes, pitch, frame_stride, p->level(0, first, 0), p->lv[0].pitch, p->plane_floats,
+                                     p->w, p->h, count, &taps->smooth, &taps->smooth, precision))) return rc;
+    return build_rest(ctx, p, taps, precision, false, first, count);
 }
 
 int klt_pyr_build_u8(klt_ctx *ctx, klt_pyr *p, const uint8_t *frames, size_t pitch, size_t frame_stride,
@@ -344,16 +370,7 @@ int klt_pyr_build_u8(klt_ctx *ctx, klt_pyr *p, const uint8_t *frames, size_t pit
         KLT_CUDA(ctx, cudaMemcpyAsync(ctx->ws, frames, bytes, cudaMemcpyHostToDevice, ctx->stream));
         dframes = (const uint8_t *)ctx->ws;
     }
-    if (precision == KLT_PRECISION_FAST) {
-        // fused u8 -> smoothed image + gradient pair of level 0 (one read of the frame, three writes)
-        rc = klt_stream_level0(ctx, dframes, pitch, frame_stride, p, taps);
-        if (rc < 0) return rc;
-        if (rc == 1) return build_rest(ctx, p, taps, precision, true);
-    }
-    // img.convert("F") + KLTComputeSmoothedImage (trackFeatures.py:165-166): one kernel, u8 in, f32 out
-    if ((rc = klt_launch_conv_sep_u8(ctx, dframes, pitch, frame_stride, p->level(0, 0, 0), p->lv[0].pitch, p->plane_floats,
-                                     p->w, p->h, p->batch, &taps->smooth, &taps->smooth, precision))) return rc;
-    return build_rest(ctx, p, taps, precision);
+    return build_u8_device(ctx, p, dframes, pitch, frame_stride, taps, precision, 0, p->batch);
 }
 
 int klt_pyr_build_f32(klt_ctx *ctx, klt_pyr *p, const float *images, size_t pitch, size_t frame_stride,
@@ -528,10 +545,56 @@ int klt_extract_patch(klt_ctx *ctx, const float *img, int w, int h, float x, flo
 int klt_track_pairs_u8(klt_ctx *ctx, const klt_params *params, const klt_taps *taps, int precision, klt_pyr *pyr1,
                        klt_pyr *pyr2, const uint8_t *frames1, const uint8_t *frames2, size_t pitch, size_t frame_stride,
                        int n_per_image, double *x, double *y, int32_t *val) {
+    if (!ctx || !params || !taps || !pyr1 || !pyr2 || !frames1 || !frames2) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
     int rc;
-    // NOTE: both builds may stage host frames through the (single) workspace; stream order makes that safe.
-    if ((rc = klt_pyr_build_u8(ctx, pyr1, frames1, pitch, frame_stride, taps, precision))) return rc;
-    if ((rc = klt_pyr_build_u8(ctx, pyr2, frames2, pitch, frame_stride, taps, precision))) return rc;
+    const bool host1 = !klt_is_device_ptr(frames1), host2 = !klt_is_device_ptr(frames2);
+    if (!host1 && !host2) {
+        if ((rc = klt_pyr_build_u8(ctx, pyr1, frames1, pitch, frame_stride, taps, precision))) return rc;
+        if ((rc = klt_pyr_build_u8(ctx, pyr2, frames2, pitch, frame_stride, taps, precision))) return rc;
+        return klt_track_features(ctx, params, pyr1, pyr2, n_per_image, x, y, val, nullptr);
+    }
+    if (host1 != host2) return klt_fail(ctx, KLT_ERR_INVALID, "frames1 and frames2 must both be host or both be device");
+    if (pyr1->batch != pyr2->batch || pyr1->w != pyr2->w || pyr1->h != pyr2->h) return klt_fail(ctx, KLT_ERR_INVALID, "pyramids differ in geometry");
+    if (pitch < (size_t)pyr1->w) return klt_fail(ctx, KLT_ERR_INVALID, "pitch smaller than width");
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    // Host frames: the batch is cut into chunks; the H2D copy of chunk k+1 (copy stream) overlaps the pyramid builds of
+    // chunk k (compute stream).  PCIe, not the kernels, bounds this path.
+    const int B = pyr1->batch;
+    const size_t one = (size_t)(pyr1->h - 1) * pitch + pyr1->w;                 // bytes actually read of one frame
+    const size_t per_set = (size_t)(B - 1) * frame_stride + one;
+    const size_t set_stride = (per_set + 255) / 256 * 256;
+    if (2 * set_stride > ctx->frames_bytes) {
+        KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        KLT_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        if (ctx->frames_dev) { KLT_CUDA(ctx, cudaFree(ctx->frames_dev)); ctx->frames_dev = nullptr; ctx->frames_bytes = 0; }
+        cudaError_t e = cudaMalloc(&ctx->frames_dev, 2 * set_stride);
+        if (e != cudaSuccess) return klt_fail(ctx, KLT_ERR_NOMEM, "cudaMalloc(%zu) for frame staging failed: %s", 2 * set_stride, cudaGetErrorString(e));
+        ctx->frames_bytes = 2 * set_stride;
+    }
+    uint8_t *d1 = (uint8_t *)ctx->frames_dev, *d2 = d1 + set_stride;
+    int nchunks = B < 4 ? 1 : (B < 16 ? 2 : 4);
+    if (nchunks > 16) nchunks = 16;
+    const int per_chunk = (B + nchunks - 1) / nchunks;
+    // the staging buffers may still be read by kernels of the previous call
+    KLT_CUDA(ctx, cudaEventRecord(ctx->compute_done, ctx->stream));
+    KLT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_done, 0));
+    pyr1->precision = pyr2->precision = precision;
+    int k = 0;
+    for (int first = 0; first < B; first += per_chunk, k++) {
+        const int count = first + per_chunk <= B ? per_chunk : B - first;
+        const size_t off = (size_t)first * frame_stride, bytes = (size_t)(count - 1) * frame_stride + one;
+        KLT_CUDA(ctx, cudaMemcpyAsync(d1 + off, frames1 + off, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        KLT_CUDA(ctx, cudaMemcpyAsync(d2 + off, frames2 + off, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        KLT_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[k], ctx->copy_stream));
+    }
+    k = 0;
+    for (int first = 0; first < B; first += per_chunk, k++) {
+        const int count = first + per_chunk <= B ? per_chunk : B - first;
+        const size_t off = (size_t)first * frame_stride;
+        KLT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[k], 0));
+        if ((rc = build_u8_device(ctx, pyr1, d1 + off, pitch, frame_stride, taps, precision, first, count))) return rc;
+        if ((rc = build_u8_device(ctx, pyr2, d2 + off, pitch, frame_stride, taps, precision, first, count))) return rc;
+    }
     return klt_track_features(ctx, params, pyr1, pyr2, n_per_image, x, y, val, nullptr);
 }
 

@@ -58,6 +58,12 @@ struct klt_ctx {
     std::string err;
     int64_t launches;
     cudaEvent_t ev0, ev1;
+    // upload pipeline of klt_track_pairs_u8: copy stream, per-chunk events, device staging for the frames
+    cudaStream_t copy_stream;
+    cudaEvent_t chunk_ev[16];
+    cudaEvent_t compute_done;
+    void *frames_dev;
+    size_t frames_bytes;
     // grow-only device workspace
     void *ws;
     size_t ws_bytes;
@@ -115,9 +121,11 @@ int klt_launch_pyr_down(klt_ctx *ctx, const float *in, size_t in_pitch, size_t i
                         const klt_kernel1d *g, int precision);
 
 // ---- klt_stream.cu: warp-streaming FAST-path kernels; return 1 = launched, 0 = configuration not covered ----
-int klt_stream_level0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t frame_stride, klt_pyr *p, const klt_taps *taps);
-int klt_stream_grad(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps);
-int klt_stream_down2(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps);
+// (first, count): the sub-range of the pyramid batch to build; `frames` points at image `first`
+int klt_stream_level0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t frame_stride, klt_pyr *p, const klt_taps *taps,
+                      int first, int count);
+int klt_stream_grad(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps, int first, int count);
+int klt_stream_down2(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps, int first, int count);
 
 // ---- klt_select.cu -----------------------------------------------------------------------------------
 int klt_launch_scan(klt_ctx *ctx, const float *gx, const float *gy, size_t pitch, int w, int h, int bx, int by,

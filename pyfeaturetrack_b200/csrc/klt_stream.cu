@@ -365,7 +365,7 @@ static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // Returns 1 if the streaming kernel was launched, 0 if the configuration is not covered (caller falls back), <0 on error.
 int klt_stream_level0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t frame_stride, klt_pyr *p,
-                      const klt_taps *taps) {
+                      const klt_taps *taps, int first, int count) {
     StreamTaps T;
     const int ns = taps->smooth.n;
     if (ns != 3 && ns != 5 && ns != 7 && ns != 9) return 0;
@@ -381,14 +381,14 @@ int klt_stream_level0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t 
     const int strip_ctas = (n_strips + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     int rows = 0;
     switch (RS) {
-        case 1: rows = pick_rows_per_seg(ctx, stream_level0_kernel<1>, H, strip_ctas, p->batch, 32); break;
-        case 2: rows = pick_rows_per_seg(ctx, stream_level0_kernel<2>, H, strip_ctas, p->batch, 32); break;
-        case 3: rows = pick_rows_per_seg(ctx, stream_level0_kernel<3>, H, strip_ctas, p->batch, 32); break;
-        default: rows = pick_rows_per_seg(ctx, stream_level0_kernel<4>, H, strip_ctas, p->batch, 32); break;
+        case 1: rows = pick_rows_per_seg(ctx, stream_level0_kernel<1>, H, strip_ctas, count, 32); break;
+        case 2: rows = pick_rows_per_seg(ctx, stream_level0_kernel<2>, H, strip_ctas, count, 32); break;
+        case 3: rows = pick_rows_per_seg(ctx, stream_level0_kernel<3>, H, strip_ctas, count, 32); break;
+        default: rows = pick_rows_per_seg(ctx, stream_level0_kernel<4>, H, strip_ctas, count, 32); break;
     }
-    dim3 grid(strip_ctas, (H + rows - 1) / rows, p->batch), block(WARPS_PER_CTA * 32);
-    const double bytes = 13.0 * W * H * p->batch;        // 1 B read + 3 x 4 B written per pixel
-    float *img = p->level(0, 0, 0), *gx = p->level(1, 0, 0), *gy = p->level(2, 0, 0);
+    dim3 grid(strip_ctas, (H + rows - 1) / rows, count), block(WARPS_PER_CTA * 32);
+    const double bytes = 13.0 * W * H * count;        // 1 B read + 3 x 4 B written per pixel
+    float *img = p->level(0, first, 0), *gx = p->level(1, first, 0), *gy = p->level(2, first, 0);
 #define LAUNCH_L0(R)                                                                                                   \
     KLT_LAUNCH(ctx, "stream_level0", bytes,                                                                            \
                (stream_level0_kernel<R><<<grid, block, 0, ctx->stream>>>(frames, pitch, frame_stride, img, gx, gy,      \
@@ -405,26 +405,26 @@ int klt_stream_level0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t 
     return 1;
 }
 
-int klt_stream_grad(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps) {
+int klt_stream_grad(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps, int first, int count) {
     StreamTaps T;
     if (!fill_taps(&taps->grad_gauss, T.g, 7) || !fill_taps(&taps->grad_deriv, T.d, 7)) return 0;
     for (int j = 0; j < 9; j++) T.s[j] = 0.f;
     for (int j = 0; j < 11; j++) T.p[j] = 0.f;
     const LevelDesc &a = p->lv[level];
-    if (a.w < 16 || a.h < 8 || (a.w & 3) || !aligned16(p->level(0, 0, level)) || (p->plane_floats & 3)) return 0;
+    if (a.w < 16 || a.h < 8 || (a.w & 3) || !aligned16(p->level(0, first, level)) || (p->plane_floats & 3)) return 0;
     const int n_strips = (a.w + 119) / 120;
     const int strip_ctas = (n_strips + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    const int rows = pick_rows_per_seg(ctx, stream_grad_kernel, a.h, strip_ctas, p->batch, 24);
-    dim3 grid(strip_ctas, (a.h + rows - 1) / rows, p->batch), block(WARPS_PER_CTA * 32);
-    const double bytes = 12.0 * a.w * a.h * p->batch;
+    const int rows = pick_rows_per_seg(ctx, stream_grad_kernel, a.h, strip_ctas, count, 24);
+    dim3 grid(strip_ctas, (a.h + rows - 1) / rows, count), block(WARPS_PER_CTA * 32);
+    const double bytes = 12.0 * a.w * a.h * count;
     KLT_LAUNCH(ctx, "stream_grad", bytes,
-               (stream_grad_kernel<<<grid, block, 0, ctx->stream>>>(p->level(0, 0, level), a.pitch, p->plane_floats,
-                                                                    p->level(1, 0, level), p->level(2, 0, level), a.pitch,
+               (stream_grad_kernel<<<grid, block, 0, ctx->stream>>>(p->level(0, first, level), a.pitch, p->plane_floats,
+                                                                    p->level(1, first, level), p->level(2, first, level), a.pitch,
                                                                     p->plane_floats, a.w, a.h, rows, n_strips, T)));
     return 1;
 }
 
-int klt_stream_down2(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps) {
+int klt_stream_down2(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps, int first, int count) {
     if (p->ss != 2 || level < 1) return 0;
     StreamTaps T;
     if (taps->pyramid.n > 11 || !fill_taps(&taps->pyramid, T.p, 11)) return 0;
@@ -432,15 +432,15 @@ int klt_stream_down2(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps) 
     for (int j = 0; j < 7; j++) { T.g[j] = 0.f; T.d[j] = 0.f; }
     const LevelDesc &a = p->lv[level - 1], &b = p->lv[level];
     if (b.w < 8 || b.h < 8 || a.w < 32 || a.h < 16 || (a.w & 3) || (b.w & 3)) return 0;
-    if (!aligned16(p->level(0, 0, level - 1)) || !aligned16(p->level(0, 0, level)) || (p->plane_floats & 3)) return 0;
+    if (!aligned16(p->level(0, first, level - 1)) || !aligned16(p->level(0, first, level)) || (p->plane_floats & 3)) return 0;
     const int n_strips = (b.w + 119) / 120;
     const int strip_ctas = (n_strips + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    const int rows = pick_rows_per_seg(ctx, stream_down2_kernel, b.h, strip_ctas, p->batch, 24);
-    dim3 grid(strip_ctas, (b.h + rows - 1) / rows, p->batch), block(WARPS_PER_CTA * 32);
-    const double bytes = 4.0 * ((double)a.w * a.h + (double)b.w * b.h) * p->batch;
+    const int rows = pick_rows_per_seg(ctx, stream_down2_kernel, b.h, strip_ctas, count, 24);
+    dim3 grid(strip_ctas, (b.h + rows - 1) / rows, count), block(WARPS_PER_CTA * 32);
+    const double bytes = 4.0 * ((double)a.w * a.h + (double)b.w * b.h) * count;
     KLT_LAUNCH(ctx, "stream_down2", bytes,
-               (stream_down2_kernel<<<grid, block, 0, ctx->stream>>>(p->level(0, 0, level - 1), a.pitch, p->plane_floats, a.w,
-                                                                     a.h, p->level(0, 0, level), b.pitch, p->plane_floats, b.w,
+               (stream_down2_kernel<<<grid, block, 0, ctx->stream>>>(p->level(0, first, level - 1), a.pitch, p->plane_floats, a.w,
+                                                                     a.h, p->level(0, first, level), b.pitch, p->plane_floats, b.w,
                                                                      b.h, rows, n_strips, T)));
     return 1;
 }

@@ -209,20 +209,22 @@ lk_track_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ xs, do
 // ---------------------------------------------------------------------------------------------------------------------
 // FAST tracking kernel (used when the pyramids were built in KLT_PRECISION_FAST): same algorithm and status logic,
 // float32 bilinear weights and shuffle reductions instead of the reference's exact operation order.
-// Mapping: one LANE per window ROW, G = 8 (W <= 7) or 16 (W <= 15) lanes per feature, 32/G features per warp.
-// A lane loads the W+1 source pixels of its two source rows once per patch (horizontally adjacent samples share
-// corners: 2.3 loads per sample instead of 4), keeps its row of the three templates in registers, accumulates the five
-// window sums over its row with FMAs, and the G lanes of a feature combine them with log2(G) shuffle steps.
+// Mapping: one LANE per window COLUMN, G = 8 (W <= 7) or 16 (W <= 15) lanes per feature, 32/G features per warp.
+// A lane loads the W+1 source pixels of its column and of the column to its right once per patch (vertically adjacent
+// samples share corners: 2.3 loads per sample instead of 4; the lanes of a feature touch one or two 32-byte sectors
+// per source row), keeps its column of the three templates in registers, accumulates the five window sums over its
+// column with FMAs, and the G lanes of a feature combine them with log2(G) shuffle steps.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int W>
-__device__ __forceinline__ void patch_row(const float *__restrict__ img, int pitch, int ix, int iy, int j, float w00,
+__device__ __forceinline__ void patch_col(const float *__restrict__ img, int pitch, int ix, int iy, int i, float w00,
                                           float w01, float w10, float w11, float (&out)[W]) {
-    const float *p = img + (size_t)(iy + j - W / 2) * pitch + (ix - W / 2);
-    float a0[W + 1], a1[W + 1];
+    // lane i owns window COLUMN i: the lanes of a feature read consecutive addresses of each source row (coalesced)
+    const float *p = img + (size_t)(iy - W / 2) * pitch + (ix - W / 2 + i);
+    float a[W + 1], b[W + 1];
 #pragma unroll
-    for (int i = 0; i < W + 1; i++) { a0[i] = __ldg(p + i); a1[i] = __ldg(p + pitch + i); }
+    for (int j = 0; j < W + 1; j++) { a[j] = __ldg(p + (size_t)j * pitch); b[j] = __ldg(p + (size_t)j * pitch + 1); }
 #pragma unroll
-    for (int i = 0; i < W; i++) out[i] = fmaf(w11, a1[i + 1], fmaf(w10, a1[i], fmaf(w01, a0[i + 1], w00 * a0[i])));
+    for (int j = 0; j < W; j++) out[j] = fmaf(w11, b[j + 1], fmaf(w10, a[j + 1], fmaf(w01, b[j], w00 * a[j])));
 }
 
 template <int G>
@@ -240,7 +242,7 @@ lk_track_rows_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ x
     constexpr int FPW = 32 / G;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = (blockIdx.x * (blockDim.x >> 5) + warp) * FPW + lane / G;
-    const int j = lane % G;                       // window row handled by this lane
+    const int j = lane % G;                       // window column handled by this lane
     const bool row_ok = j < W;
     bool alive = f < A.total;
     if (alive) alive = vals[f] >= 0;              // trackFeatures.py:253
@@ -272,9 +274,9 @@ lk_track_rows_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ x
             if (alive && row_ok) {
                 const float ax = x1 - (float)ix, ay = y1 - (float)iy;
                 const float w11 = ax * ay, w01 = ax - w11, w10 = ay - w11, w00 = 1.f - ax - ay + w11;
-                patch_row<W>(I1, pitch, ix, iy, j, w00, w01, w10, w11, T);
-                patch_row<W>(GX1, pitch, ix, iy, j, w00, w01, w10, w11, Tgx);
-                patch_row<W>(GY1, pitch, ix, iy, j, w00, w01, w10, w11, Tgy);
+                patch_col<W>(I1, pitch, ix, iy, j, w00, w01, w10, w11, T);
+                patch_col<W>(GX1, pitch, ix, iy, j, w00, w01, w10, w11, Tgx);
+                patch_col<W>(GY1, pitch, ix, iy, j, w00, w01, w10, w11, Tgy);
             } else {
 #pragma unroll
                 for (int i = 0; i < W; i++) { T[i] = 0.f; Tgx[i] = 0.f; Tgy[i] = 0.f; }
@@ -295,9 +297,9 @@ lk_track_rows_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ x
                 const float ax = x2 - (float)ix, ay = y2 - (float)iy;
                 const float w11 = ax * ay, w01 = ax - w11, w10 = ay - w11, w00 = 1.f - ax - ay + w11;
                 float P[W], Px[W], Py[W];
-                patch_row<W>(I2, pitch, ix, iy, j, w00, w01, w10, w11, P);
-                patch_row<W>(GX2, pitch, ix, iy, j, w00, w01, w10, w11, Px);
-                patch_row<W>(GY2, pitch, ix, iy, j, w00, w01, w10, w11, Py);
+                patch_col<W>(I2, pitch, ix, iy, j, w00, w01, w10, w11, P);
+                patch_col<W>(GX2, pitch, ix, iy, j, w00, w01, w10, w11, Px);
+                patch_col<W>(GY2, pitch, ix, iy, j, w00, w01, w10, w11, Py);
 #pragma unroll
                 for (int i = 0; i < W; i++) {
                     const float diff = T[i] - P[i], gx = Tgx[i] + Px[i], gy = Tgy[i] + Py[i];
@@ -335,7 +337,7 @@ lk_track_rows_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ x
                 const float ax = x2 - (float)ix, ay = y2 - (float)iy;
                 const float w11 = ax * ay, w01 = ax - w11, w10 = ay - w11, w00 = 1.f - ax - ay + w11;
                 float P[W];
-                patch_row<W>(I2, pitch, ix, iy, j, w00, w01, w10, w11, P);
+                patch_col<W>(I2, pitch, ix, iy, j, w00, w01, w10, w11, P);
 #pragma unroll
                 for (int i = 0; i < W; i++) res += fabsf(T[i] - P[i]);
             }

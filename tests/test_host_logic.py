@@ -1,0 +1,160 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU): context defaults, border math, kernel taps,
+the kernel-cache replay, feature objects, sharding."""
+import pickle
+
+import numpy as np
+import pytest
+
+
+def test_status_codes_and_defaults(golden):
+    from pyfeaturetrack_b200 import klt
+    s = klt.kltState
+    assert (s.KLT_TRACKED, s.KLT_NOT_FOUND, s.KLT_SMALL_DET, s.KLT_MAX_ITERATIONS, s.KLT_OOB, s.KLT_LARGE_RESIDUE) == (0, -1, -2, -3, -4, -5)
+    tc = klt.KLT_TrackingContext()
+    assert [tc.nPyramidLevels, tc.subsampling, tc.borderx, tc.bordery] == list(golden["default_ctx"])
+    assert isinstance(tc.borderx, float)                      # quirk Q1: true division
+    assert (tc.mindist, tc.window_width, tc.window_height, tc.max_iterations) == (10, 7, 7, 10)
+    assert tc.max_residue is None and tc.min_determinant == 0.01 and tc.min_displacement == 0.1
+    assert tc.affineConsistencyCheck == -1 and tc.affine_window_width == 15
+    assert tc.pyramid_last is None and not tc.sequentialMode and not tc.retainTrackers
+
+
+def test_borders_and_pyramid_heuristic(golden):
+    from pyfeaturetrack_b200 import klt
+    for w, L, ss, border in golden["borders"]:
+        tc = klt.KLT_TrackingContext()
+        tc.window_width = tc.window_height = int(w)
+        tc.nPyramidLevels, tc.subsampling = int(L), int(ss)
+        tc.KLTUpdateTCBorder()
+        assert tc.borderx == border and tc.bordery == border
+    for sr, L, ss in golden["pyramid_choices"]:
+        tc = klt.KLT_TrackingContext()
+        tc.KLTChangeTCPyramid(int(sr))
+        assert (tc.nPyramidLevels, tc.subsampling) == (int(L), int(ss))
+
+
+def test_window_fixups_warn_and_mutate(capsys):
+    from pyfeaturetrack_b200 import klt
+    tc = klt.KLT_TrackingContext()
+    tc.window_width, tc.window_height = 6, 2
+    tc.KLTUpdateTCBorder()
+    assert (tc.window_width, tc.window_height) == (7, 3)
+    assert "must be odd" in capsys.readouterr().out
+
+
+@pytest.mark.parametrize("sigma", [0.7, 1.0, 1.5, 1.8, 3.6, 7.2])
+def test_kernel_taps_bit_exact(golden, sigma):
+    from pyfeaturetrack_b200 import convolve
+    g, d = convolve._computeKernels(sigma)
+    assert np.array_equal(np.array(g), golden["taps_g_%s" % sigma])
+    assert np.array_equal(np.array(d), golden["taps_d_%s" % sigma])
+    assert convolve.KLTGetKernelWidths(sigma) == (len(g), len(d))
+    assert convolve.cached_sigma_last == sigma
+
+
+def test_kernel_too_wide_raises_nameerror_like_reference():
+    from pyfeaturetrack_b200 import convolve
+    with pytest.raises(NameError):
+        convolve._computeKernels(14.4)
+
+
+def test_kernel_cache_quirk_replayed():
+    """convolve.py:236,258: a sigma within 0.05 of the cached one reuses the stale taps (quirk Q8)."""
+    from pyfeaturetrack_b200 import convolve
+    convolve._computeKernels(1.0)
+    g_stale, _ = convolve._kernels_for_smoothing(1.04)
+    assert convolve.cached_sigma_last == 1.0 and list(g_stale) == list(convolve._computeKernels(1.0)[0])
+    g_new, _ = convolve._kernels_for_smoothing(1.06)
+    assert convolve.cached_sigma_last == 1.06 and len(g_new) == 7
+
+
+def test_taps_replay_matches_reference_cache_sequence(reference):
+    """_taps_for_one_image must leave the kernel cache exactly where the reference's ComputeImagePyramids leaves it."""
+    from pyfeaturetrack_b200 import klt, trackFeatures, convolve
+    rklt, rconv = reference["klt"], reference["convolve"]
+    for kw in (dict(), dict(nPyramidLevels=3, subsampling=2), dict(window_width=15, window_height=15),
+               dict(grad_sigma=0.72), dict(nPyramidLevels=1), dict(smooth_sigma_fact=0.15, grad_sigma=1.02)):
+        tc, rtc = klt.KLT_TrackingContext(), rklt.KLT_TrackingContext()
+        for t in (tc, rtc):
+            for k, v in kw.items():
+                setattr(t, k, v)
+            t.KLTUpdateTCBorder()
+        taps = trackFeatures._taps_for_one_image(tc)
+        # replay the reference's call sequence for one image on its own cache (trackFeatures.py:165-172)
+        img = np.zeros((16, 16), np.float32)
+        rconv.KLTComputeSmoothedImage(img, rtc.smooth_sigma_fact * max(rtc.window_width, rtc.window_height))
+        smooth_ref = list(rconv.cachegauss)
+        for _ in range(1, rtc.nPyramidLevels):
+            rconv.KLTComputeSmoothedImage(img, rtc.subsampling * rtc.pyramid_sigma_fact)
+        pyr_ref = list(rconv.cachegauss)
+        for _ in range(rtc.nPyramidLevels):
+            rconv.KLTComputeGradients(img, rtc.grad_sigma)
+        assert list(taps.smooth.taps[:taps.smooth.n]) == smooth_ref
+        if rtc.nPyramidLevels > 1:
+            assert list(taps.pyramid.taps[:taps.pyramid.n]) == pyr_ref
+        assert list(taps.grad_gauss.taps[:taps.grad_gauss.n]) == list(rconv.cachegauss)
+        assert list(taps.grad_deriv.taps[:taps.grad_deriv.n]) == list(rconv.cachegaussderiv)
+        assert convolve.cached_sigma_last == rconv.cached_sigma_last
+
+
+def test_feature_objects():
+    from pyfeaturetrack_b200 import klt
+    f = klt.KLT_Feature()
+    assert not hasattr(f, "x") and not hasattr(f, "val")      # quirk Q5
+    f.x, f.y, f.val = 1.5, 2.5, 0
+    g = pickle.loads(pickle.dumps([f]))[0]
+    assert (g.x, g.y, g.val) == (1.5, 2.5, 0)
+    h = klt.KLT_Feature(); h.x = h.y = -1.0; h.val = -4
+    assert klt.KLTCountRemainingFeatures([f, h]) == 1
+
+
+def test_params_struct_from_context():
+    from pyfeaturetrack_b200 import klt, selectGoodFeatures as sgf
+    tc = klt.KLT_TrackingContext()
+    p = sgf.make_params(tc)
+    assert (p.window_width, p.n_levels, p.subsampling, p.has_max_residue) == (7, 2, 4, 0)
+    assert p.borderx == 30.0
+    tc.max_residue = 10.0
+    tc.retainTrackers = True
+    p = sgf.make_params(tc)
+    assert p.has_max_residue == 1 and p.max_residue == 10.0 and p.retain_trackers == 1
+
+
+def test_unported_paths_fail_like_the_reference(img01):
+    from pyfeaturetrack_b200 import klt, trackFeatures as tf
+    tf.KLT_verbose = 0
+    tc = klt.KLT_TrackingContext()
+    f = klt.KLT_Feature(); f.x, f.y, f.val = 100.0, 100.0, 0
+    tc.lighting_insensitive = True
+    with pytest.raises(Exception, match="Not implemented"):
+        tf.KLTTrackFeatures(tc, img01[0], img01[1], [f])
+    with pytest.raises(AssertionError):
+        tf.KLTTrackFeatures(klt.KLT_TrackingContext(), img01[0], img01[1][:100], [f])
+
+
+def test_install_dropin_aliases_reference_module_names():
+    import sys
+    import pyfeaturetrack_b200 as P
+    saved = {k: sys.modules.get(k) for k in P.DROPIN_MODULES}
+    try:
+        P.install_dropin()
+        import klt, selectGoodFeatures, trackFeatures, convolve, pyramid, goodFeaturesUtils, trackFeaturesUtils  # noqa
+        assert klt.KLT_TrackingContext is P.klt.KLT_TrackingContext
+        assert hasattr(selectGoodFeatures, "KLTSelectGoodFeatures") and hasattr(trackFeatures, "KLTTrackFeatures")
+        assert hasattr(goodFeaturesUtils, "ScanImageForGoodFeatures") and hasattr(trackFeaturesUtils, "extractImagePatchSlow")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_shard_range_partitions():
+    from pyfeaturetrack_b200.shard import shard_range
+    for n in (0, 1, 7, 8, 300, 2401):
+        for world in (1, 2, 3, 8):
+            got = [u for r in range(world) for u in shard_range(n, r, world)]
+            assert got == list(range(n))
+            sizes = [len(shard_range(n, r, world)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
