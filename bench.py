@@ -309,6 +309,7 @@ def run_b200(args):
         out["cpu_baseline"] = cpu_baseline(wl, distinct, sel, budget_s=args.cpu_budget)
     if world == 1 and args.api_pairs > 0:
         out["api_single_pair"] = api_single_pair(wl, distinct, klt, sgf, trackFeatures, args.api_pairs)
+        out["select"] = select_timing(wl, distinct, klt, sgf, ctx, args.api_pairs)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -333,6 +334,25 @@ def api_single_pair(wl, distinct, klt, sgf, tf, reps):
             tracked = sum(1 for f in fl if f.val == 0)
     return {"call": "KLTTrackFeatures(tc, img1, img2, fl) with PIL images", "ms_per_pair": round(1e3 * float(np.mean(ts)), 3),
             "frame_pairs_per_sec": round(1.0 / float(np.mean(ts)), 1), "tracked_features_per_sec": round(tracked / float(np.mean(ts)), 1)}
+
+
+def select_timing(wl, distinct, klt, sgf, ctx, reps):
+    """KLTSelectGoodFeatures (strict: bit-identical selection) through the drop-in call, one frame per call."""
+    tc = tc_for(wl, klt)
+    ts = []
+    ctx.profile_reset()
+    for r in range(reps + 2):
+        if r == 2:
+            ctx.profile(True)
+        t0 = time.perf_counter()
+        fl = sgf.KLTSelectGoodFeatures(tc, distinct[r % len(distinct)][0], wl["n"])
+        if r >= 2:
+            ts.append(time.perf_counter() - t0)
+    ctx.profile(False)
+    prof = ctx.profile_read()
+    return {"call": "KLTSelectGoodFeatures(tc, img, n) strict", "ms_per_frame": round(1e3 * float(np.mean(ts)), 3),
+            "found": sum(1 for f in fl if f.val > 0),
+            "kernel_ms_per_frame": {k: round(v["ms"] / reps, 4) for k, v in prof.items()}}
 
 
 # ------------------------------------------------------------------------------------------------------------------

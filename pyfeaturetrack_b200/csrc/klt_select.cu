@@ -5,55 +5,95 @@
 //
 // The reference's eigenvalues carry the rounding of three float32 summed-area tables built by strictly
 // sequential additions (np.cumsum along rows, then along columns); selection ORDER depends on that rounding
-// (SURVEY 7.3), so the tables are rebuilt here with the same chains: one thread per row, then one thread per
-// column.  A parallel prefix scan would be faster per element but produces different float32 sums.
+// (SURVEY 7.3), so the tables are rebuilt here with the same chains: one lane per row (tiles transposed through
+// shared memory so that global traffic stays coalesced), then one thread per column.  A parallel prefix scan would
+// be faster per element but produces different float32 sums.
+//
+// The reference sorts every candidate (1.87 M at 1080p) although greedy suppression consumes only the best ~8.5 N.
+// Here a histogram of the eigenvalues picks a threshold that keeps roughly the best M = 32 N + 8192 candidates, only
+// those are sorted (stable LSD radix sort on 64-bit keys) and walked; if the walk runs out of candidates before every
+// slot is filled, the selection is repeated without the threshold, so the result is always the exact greedy result.
+#include <cuda_pipeline.h>
+
 #include "klt_common.cuh"
 
 // ---- summed-area tables -------------------------------------------------------------------------------
-// rows: s[y][x] = s[y][x-1] + p[y][x], p = exact fp32 product (np.power(g,2.) / g*g, pyx:49-51)
+// rows: s[y][x] = s[y][x-1] + p[y][x], p = exact fp32 product (np.power(g,2.) / g*g, pyx:49-51).
+// One warp owns 32 rows.  32x32 tiles of gx, gy are brought in with cp.async (double buffered, coalesced), each lane
+// then walks ITS row of the tile sequentially (the float32 chain of np.cumsum), and the three result tiles go back
+// transposed so that the stores are coalesced too.
+#define SAT_T 32
+#define SAT_NBUF 4                      // cp.async ring: tiles are requested 3 chunks ahead of their use
+struct SatSmem {
+    float in[SAT_NBUF][2][SAT_T][SAT_T + 1];   // [buffer][gx|gy][row][col]
+    float out[3][SAT_T][SAT_T + 1];
+};
+
 __global__ void __launch_bounds__(32)
 sat_rows_kernel(const float *__restrict__ gx, const float *__restrict__ gy, size_t pitch, int W, int H,
                 float *__restrict__ sxx, float *__restrict__ sxy, float *__restrict__ syy) {
-    const int y = blockIdx.x * blockDim.x + threadIdx.x;
-    if (y >= H) return;
-    const float *a = gx + (size_t)y * pitch, *b = gy + (size_t)y * pitch;
-    float *oxx = sxx + (size_t)y * W, *oxy = sxy + (size_t)y * W, *oyy = syy + (size_t)y * W;
-    float axx = 0.f, axy = 0.f, ayy = 0.f;     // 0 + p == p exactly, so starting from 0 equals cumsum's first copy
-    int x = 0;
-    for (; x + 8 <= W; x += 8) {
-        float va[8], vb[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) { va[i] = a[x + i]; vb[i] = b[x + i]; }
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            axx = __fadd_rn(axx, __fmul_rn(va[i], va[i]));
-            axy = __fadd_rn(axy, __fmul_rn(va[i], vb[i]));
-            ayy = __fadd_rn(ayy, __fmul_rn(vb[i], vb[i]));
-            oxx[x + i] = axx; oxy[x + i] = axy; oyy[x + i] = ayy;
+    __shared__ SatSmem sm;
+    const int lane = threadIdx.x;
+    const int y0 = blockIdx.x * SAT_T;
+    const int nchunks = (W + SAT_T - 1) / SAT_T;
+    auto issue = [&](int chunk, int buf) {
+        const int x = chunk * SAT_T + lane;
+        if (x < W) {
+#pragma unroll 8
+            for (int i = 0; i < SAT_T; i++) {
+                const int y = min(y0 + i, H - 1);
+                __pipeline_memcpy_async(&sm.in[buf][0][i][lane], gx + (size_t)y * pitch + x, 4);
+                __pipeline_memcpy_async(&sm.in[buf][1][i][lane], gy + (size_t)y * pitch + x, 4);
+            }
         }
+        __pipeline_commit();
+    };
+    float axx = 0.f, axy = 0.f, ayy = 0.f;     // 0 + p == p exactly, so starting from 0 equals cumsum's first copy
+    for (int c = 0; c < SAT_NBUF - 1; c++) {
+        if (c < nchunks) issue(c, c); else __pipeline_commit();
     }
-    for (; x < W; x++) {
-        const float va = a[x], vb = b[x];
-        axx = __fadd_rn(axx, __fmul_rn(va, va));
-        axy = __fadd_rn(axy, __fmul_rn(va, vb));
-        ayy = __fadd_rn(ayy, __fmul_rn(vb, vb));
-        oxx[x] = axx; oxy[x] = axy; oyy[x] = ayy;
+    for (int c = 0; c < nchunks; c++) {
+        const int buf = c % SAT_NBUF;
+        if (c + SAT_NBUF - 1 < nchunks) issue(c + SAT_NBUF - 1, (c + SAT_NBUF - 1) % SAT_NBUF); else __pipeline_commit();
+        __pipeline_wait_prior(SAT_NBUF - 1);
+        __syncwarp();
+        const int ncol = min(SAT_T, W - c * SAT_T);
+        for (int k = 0; k < ncol; k++) {       // lane = row: sequential chain along x
+            const float a = sm.in[buf][0][lane][k], b = sm.in[buf][1][lane][k];
+            axx = __fadd_rn(axx, __fmul_rn(a, a));
+            axy = __fadd_rn(axy, __fmul_rn(a, b));
+            ayy = __fadd_rn(ayy, __fmul_rn(b, b));
+            sm.out[0][lane][k] = axx; sm.out[1][lane][k] = axy; sm.out[2][lane][k] = ayy;
+        }
+        __syncwarp();
+        const int x = c * SAT_T + lane;
+        if (x < W) {
+#pragma unroll 8
+            for (int i = 0; i < SAT_T; i++) {
+                const int y = y0 + i;
+                if (y < H) {
+                    const size_t o = (size_t)y * W + x;
+                    sxx[o] = sm.out[0][i][lane]; sxy[o] = sm.out[1][i][lane]; syy[o] = sm.out[2][i][lane];
+                }
+            }
+        }
+        __syncwarp();
     }
 }
 // columns: s[y][x] = s[y-1][x] + s[y][x]; blockIdx.y selects the table
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64)
 sat_cols_kernel(float *__restrict__ s0, float *__restrict__ s1, float *__restrict__ s2, int W, int H) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= W) return;
     float *s = (blockIdx.y == 0 ? s0 : blockIdx.y == 1 ? s1 : s2) + x;
     float acc = s[0];
     int y = 1;
-    for (; y + 8 <= H; y += 8) {
-        float v[8];
+    for (; y + 16 <= H; y += 16) {
+        float v[16];
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = s[(size_t)(y + i) * W];
+        for (int i = 0; i < 16; i++) v[i] = s[(size_t)(y + i) * W];
 #pragma unroll
-        for (int i = 0; i < 8; i++) { acc = __fadd_rn(acc, v[i]); s[(size_t)(y + i) * W] = acc; }
+        for (int i = 0; i < 16; i++) { acc = __fadd_rn(acc, v[i]); s[(size_t)(y + i) * W] = acc; }
     }
     for (; y < H; y++) { acc = __fadd_rn(acc, s[(size_t)y * W]); s[(size_t)y * W] = acc; }
 }
@@ -80,25 +120,85 @@ __device__ __forceinline__ unsigned long long make_key(float val, int x, int y) 
     return ~k;
 }
 
+// histogram bin of an eigenvalue >= 1: exponent and 5 mantissa bits (3 % resolution), 2048 bins
+#define EIG_BINS 2048
+__device__ __forceinline__ int eig_bin(float v) {
+    const int b = (int)(__float_as_uint(v) >> 18) - (0x3F800000 >> 18);
+    return min(max(b, 0), EIG_BINS - 1);
+}
+
+// eigenvalue map (+ optional histogram of the values >= min_val).  One block = 256 columns x EIG_ROWS candidate rows.
+#define EIG_ROWS 8
 __global__ void __launch_bounds__(256)
 eigen_kernel(const float *__restrict__ sxx, const float *__restrict__ sxy, const float *__restrict__ syy, int W,
              int bx, int by, int hw, int hh, int step, int nx, int ny, float *__restrict__ val_out,
-             unsigned long long *__restrict__ keys, unsigned int *__restrict__ nkeys, float min_val) {
+             unsigned int *__restrict__ hist, float min_val) {
+    __shared__ unsigned int h[EIG_BINS];
+    if (hist) {
+        for (int b = threadIdx.x; b < EIG_BINS; b += 256) h[b] = 0;
+        __syncthreads();
+    }
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    for (int jj = 0; jj < EIG_ROWS; jj++) {
+        const int j = blockIdx.y * EIG_ROWS + jj;
+        if (i < nx && j < ny) {
+            const int x = bx + i * step, y = by + j * step;
+            const float v = min_eigenvalue(window_sum(sxx, W, x, y, hw, hh), window_sum(sxy, W, x, y, hw, hh),
+                                           window_sum(syy, W, x, y, hw, hh));
+            val_out[(size_t)j * nx + i] = v;
+            if (hist && v >= min_val) atomicAdd(&h[eig_bin(v)], 1u);
+        }
+    }
+    if (hist) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < EIG_BINS; b += 256)
+            if (h[b]) atomicAdd(&hist[b], h[b]);
+    }
+}
+
+// picks the highest bin T such that at least `target` candidates lie in bins >= T (T = 0 if there are fewer)
+__global__ void __launch_bounds__(32)
+threshold_kernel(const unsigned int *__restrict__ hist, unsigned int target, int force_all, unsigned int *__restrict__ out /* [0]=T */) {
+    const int lane = threadIdx.x;
+    constexpr int PER = EIG_BINS / 32;
+    unsigned int mine = 0;
+    for (int b = 0; b < PER; b++) mine += hist[lane * PER + b];
+    unsigned int suffix = mine;                       // inclusive suffix sum over lanes (lane 31 = highest bins)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int v = __shfl_down_sync(0xffffffffu, suffix, o);
+        if (lane + o < 32) suffix += v;
+    }
+    const unsigned int above = suffix - mine;         // candidates in lanes above this one
+    const bool here = above < target && suffix >= target;
+    const unsigned int m = __ballot_sync(0xffffffffu, here);
+    if (force_all || m == 0u) { if (lane == 0) out[0] = 0; return; }
+    if (here) {
+        unsigned int acc = above;
+        int T = lane * PER;
+        for (int b = PER - 1; b >= 0; b--) {
+            acc += hist[lane * PER + b];
+            if (acc >= target) { T = lane * PER + b; break; }
+        }
+        out[0] = (unsigned int)T;
+    }
+}
+
+// compaction of the candidates with bin >= T into 64-bit keys (block-aggregated append; order is irrelevant, the
+// keys are unique and get sorted)
+__global__ void __launch_bounds__(256)
+compact_kernel(const float *__restrict__ val, int bx, int by, int step, int nx, int ny, float min_val,
+               const unsigned int *__restrict__ thr, unsigned long long *__restrict__ keys, unsigned int *__restrict__ nkeys) {
     __shared__ unsigned int warp_cnt[8];
     __shared__ unsigned int block_base;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    const bool inside = i < nx && j < ny;
-    const int x = bx + i * step, y = by + j * step;
+    const int i = blockIdx.x * 256 + threadIdx.x, j = blockIdx.y;
+    const int T = (int)thr[0];
     float v = 0.f;
-    if (inside) {
-        v = min_eigenvalue(window_sum(sxx, W, x, y, hw, hh), window_sum(sxy, W, x, y, hw, hh),
-                           window_sum(syy, W, x, y, hw, hh));
-        if (val_out) val_out[(size_t)j * nx + i] = v;
+    bool keep = false;
+    if (i < nx && j < ny) {
+        v = val[(size_t)j * nx + i];
+        keep = v >= min_val && eig_bin(v) >= T;     // candidates below min_eigenvalue can never be accepted (:116)
     }
-    if (!keys) return;
-    // block-aggregated compaction: candidates below min_eigenvalue can never be accepted (:116), drop them
-    const bool keep = inside && v >= min_val;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int m = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) warp_cnt[warp] = __popc(m);
@@ -109,7 +209,7 @@ eigen_kernel(const float *__restrict__ sxx, const float *__restrict__ sxy, const
         block_base = tot ? atomicAdd(nkeys, tot) : 0u;
     }
     __syncthreads();
-    if (keep) keys[block_base + warp_cnt[warp] + __popc(m & ((1u << lane) - 1u))] = make_key(v, x, y);
+    if (keep) keys[block_base + warp_cnt[warp] + __popc(m & ((1u << lane) - 1u))] = make_key(v, bx + i * step, by + j * step);
 }
 
 // ---- LSD radix sort of 64-bit keys (8-bit digits, stable) -----------------------------------------------
@@ -190,23 +290,32 @@ rs_scatter_kernel(const unsigned long long *__restrict__ in, unsigned long long 
 }
 
 // ---- greedy minimum-distance suppression (_enforceMinimumDistance) ----------------------------------------
-// One warp walks the sorted candidates 32 at a time.  A candidate is dead if the byte map says a better
-// feature already claimed its pixel, or if a feature accepted earlier IN THE SAME batch lies within
-// Chebyshev distance r = mindist-1 (which is exactly what the map would say after that feature was marked).
-// This reproduces the sequential greedy walk exactly, including the order in which slots are filled.
+// One warp walks the sorted candidates 32 at a time.  Accepted features are remembered in a grid of cells of side
+// cs = r + 1 (r = mindist - 1): two features in one cell would be closer than mindist, so a cell holds at most one and
+// a candidate only has to look at its 3x3 cell neighbourhood (shared memory, or global memory for very large images).
+// Features that survive from a previous frame (replacement mode, :64-69) are pre-marked in a byte map by a separate
+// kernel (they may be closer to each other than mindist); the map value travels with the prefetched key.
+// A candidate also dies if a feature accepted earlier IN THE SAME batch lies within Chebyshev distance r.  This
+// reproduces the sequential greedy walk exactly, including the order in which slots are filled.
 struct GreedyArgs {
     const unsigned long long *keys;
     const unsigned int *nkeys;
-    unsigned char *map;
+    const unsigned char *premap;     // NULL in SELECTING_ALL mode
+    unsigned short *grid_global;     // used when the cell grid does not fit in shared memory
     int W, H, r, n_features, overwrite;
+    int cs, gw, gh, grid_in_smem;
     double *fx, *fy;
     int *fval;
-    unsigned long long *consumed;
+    unsigned long long *consumed;    // [0] candidates consumed, [1] 1 if the keys ran out before all slots were filled
 };
 
-__device__ __forceinline__ void mark_region(unsigned char *map, int W, int H, int x, int y, int r, int lane) {
-    const int side = 2 * r + 1;
-    for (int idx = lane; idx < side * side; idx += 32) {
+__global__ void __launch_bounds__(256)
+premark_kernel(const double *__restrict__ fx, const double *__restrict__ fy, const int *__restrict__ fval, int n,
+               unsigned char *__restrict__ map, int W, int H, int r) {
+    const int f = blockIdx.x;
+    if (f >= n || fval[f] < 0) return;
+    const int x = (int)fx[f], y = (int)fy[f], side = 2 * r + 1;
+    for (int idx = threadIdx.x; idx < side * side; idx += blockDim.x) {
         const int iy = y - r + idx / side, ix = x - r + idx % side;
         if (ix >= 0 && ix < W && iy >= 0 && iy < H) map[(size_t)iy * W + ix] = 1;
     }
@@ -214,35 +323,63 @@ __device__ __forceinline__ void mark_region(unsigned char *map, int W, int H, in
 
 __global__ void __launch_bounds__(32)
 greedy_kernel(const __grid_constant__ GreedyArgs A) {
+    extern __shared__ unsigned short grid_smem[];
     const int lane = threadIdx.x;
     const unsigned int n = *A.nkeys;
-    volatile unsigned char *vmap = A.map;
-    int indx = 0;
-    if (!A.overwrite) {
-        for (int f = 0; f < A.n_features; f++)               // :64-69 pre-mark surviving features
-            if (A.fval[f] >= 0) mark_region(A.map, A.W, A.H, (int)A.fx[f], (int)A.fy[f], A.r, lane);
+    unsigned short *grid = A.grid_in_smem ? grid_smem : A.grid_global;
+    const int ncell = A.gw * A.gh;
+    if (A.r >= 0) {
+        for (int c = lane; c < ncell; c += 32) grid[c] = 0xFFFFu;
         __syncwarp();
-        __threadfence_block();
-        while (indx < A.n_features && A.fval[indx] >= 0) indx++;
     }
+    int indx = 0;
+    if (!A.overwrite) while (indx < A.n_features && A.fval[indx] >= 0) indx++;
     unsigned long long pi = 0;
     bool full = indx >= A.n_features;
+    // prefetch: key and pre-mark of the first batch
+    unsigned long long kn = lane < n ? ~A.keys[lane] : 0ull;
+    unsigned char pn = 0;
+    if (A.premap && lane < n) pn = A.premap[(size_t)(kn & 8191ull) * A.W + ((kn >> 13) & 8191ull)];
     // the reference reads one more candidate before noticing that every slot is taken (:96-112)
     while (pi < n && !full) {
-        const unsigned long long i = pi + lane;
-        const bool valid = i < n;
-        const unsigned long long k = valid ? ~A.keys[i] : 0ull;
+        const unsigned long long k = kn;
+        const bool valid = pi + lane < n;
+        const unsigned char pre = pn;
+        {   // prefetch the next batch (independent of what gets accepted in this one)
+            const unsigned long long i2 = pi + 32 + lane;
+            kn = i2 < n ? ~A.keys[i2] : 0ull;
+            pn = 0;
+            if (A.premap && i2 < n) pn = A.premap[(size_t)(kn & 8191ull) * A.W + ((kn >> 13) & 8191ull)];
+        }
         const int x = (int)((k >> 13) & 8191ull), y = (int)(k & 8191ull);
         const float val = __uint_as_float((unsigned int)(k >> 26));
-        bool live = valid && vmap[(size_t)y * A.W + x] == 0;
+        bool live = valid && pre == 0;
+        if (live && A.r >= 0) {
+            const int cx = x / A.cs, cy = y / A.cs;
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                for (int dx = -1; dx <= 1; dx++) {
+                    const int ncx = cx + dx, ncy = cy + dy;
+                    if (ncx >= 0 && ncx < A.gw && ncy >= 0 && ncy < A.gh) {
+                        const unsigned int g = grid[ncy * A.gw + ncx];
+                        if (g != 0xFFFFu) {
+                            const int fx = ncx * A.cs + (int)(g >> 8), fy = ncy * A.cs + (int)(g & 255u);
+                            if (abs(fx - x) <= A.r && abs(fy - y) <= A.r) live = false;
+                        }
+                    }
+                }
+        }
         unsigned int m;
         int last = -1;
         while ((m = __ballot_sync(0xffffffffu, live)) != 0u) {
             const int leader = __ffs(m) - 1;
             const int lx = __shfl_sync(0xffffffffu, x, leader), ly = __shfl_sync(0xffffffffu, y, leader);
             const float lval = __shfl_sync(0xffffffffu, val, leader);
-            if (lane == 0) { A.fx[indx] = (double)lx; A.fy[indx] = (double)ly; A.fval[indx] = (int)lval; }
-            mark_region(A.map, A.W, A.H, lx, ly, A.r, lane);
+            if (lane == 0) {
+                A.fx[indx] = (double)lx; A.fy[indx] = (double)ly; A.fval[indx] = (int)lval;
+                if (A.r >= 0) grid[(ly / A.cs) * A.gw + lx / A.cs] = (unsigned short)(((lx % A.cs) << 8) | (ly % A.cs));
+            }
             if (lane == leader || (abs(x - lx) <= A.r && abs(y - ly) <= A.r)) live = false;
             indx++;
             if (!A.overwrite) while (indx < A.n_features && A.fval[indx] >= 0) indx++;
@@ -250,35 +387,42 @@ greedy_kernel(const __grid_constant__ GreedyArgs A) {
             if (indx >= A.n_features) { full = true; break; }
         }
         __syncwarp();
-        __threadfence_block();
         if (full) { pi += (unsigned long long)last + 1; if (pi < n) pi += 1; }
         else pi += 32;
     }
     if (pi > n) pi = n;
-    if (!full && A.overwrite && lane == 0)
-        for (int f = indx; f < A.n_features; f++) { A.fx[f] = -1.0; A.fy[f] = -1.0; A.fval[f] = KLT_NOT_FOUND; }
-    if (lane == 0 && A.consumed) *A.consumed = pi;
+    if (lane == 0) {
+        A.consumed[0] = pi;
+        A.consumed[1] = full ? 0ull : 1ull;
+        A.consumed[2] = (unsigned long long)indx;
+    }
+}
+
+// fills the slots the walk could not fill (SELECTING_ALL only): x = y = -1, val = KLT_NOT_FOUND (C-KLT behaviour, quirk Q6)
+__global__ void fill_not_found_kernel(double *fx, double *fy, int *fval, int n, const unsigned long long *consumed) {
+    const int f = (int)consumed[2] + blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < n) { fx[f] = -1.0; fy[f] = -1.0; fval[f] = KLT_NOT_FOUND; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+static int launch_sat(klt_ctx *ctx, const float *gx, const float *gy, size_t pitch, int w, int h, float *sxx, float *sxy, float *syy) {
+    KLT_LAUNCH(ctx, "sat_rows", 20.0 * w * h, (sat_rows_kernel<<<(h + SAT_T - 1) / SAT_T, 32, 0, ctx->stream>>>(gx, gy, pitch, w, h, sxx, sxy, syy)));
+    KLT_LAUNCH(ctx, "sat_cols", 24.0 * w * h, (sat_cols_kernel<<<dim3((w + 63) / 64, 3), 64, 0, ctx->stream>>>(sxx, sxy, syy, w, h)));
+    return KLT_OK;
+}
+
 int klt_launch_scan(klt_ctx *ctx, const float *gx, const float *gy, size_t pitch, int w, int h, int bx, int by, int hw,
                     int hh, int skip, float *val_dev, int nx, int ny) {
-    // workspace: 3 SATs
     const size_t plane = align_up((size_t)w * h * sizeof(float), 256);
     int rc = klt_ws_reserve(ctx, 3 * plane);
     if (rc) return rc;
     float *sxx = (float *)ctx->ws, *sxy = (float *)((char *)ctx->ws + plane), *syy = (float *)((char *)ctx->ws + 2 * plane);
-    sat_rows_kernel<<<(h + 31) / 32, 32, 0, ctx->stream>>>(gx, gy, pitch, w, h, sxx, sxy, syy);
-    KLT_CHECK_LAUNCH(ctx);
-    sat_cols_kernel<<<dim3((w + 127) / 128, 3), 128, 0, ctx->stream>>>(sxx, sxy, syy, w, h);
-    KLT_CHECK_LAUNCH(ctx);
-    if (nx > 0 && ny > 0) {
-        eigen_kernel<<<dim3((nx + 255) / 256, ny), 256, 0, ctx->stream>>>(sxx, sxy, syy, w, bx, by, hw, hh, skip + 1, nx, ny,
-                                                                        val_dev, nullptr, nullptr, 0.f);
-        KLT_CHECK_LAUNCH(ctx);
-    }
+    if ((rc = launch_sat(ctx, gx, gy, pitch, w, h, sxx, sxy, syy))) return rc;
+    if (nx > 0 && ny > 0)
+        KLT_LAUNCH(ctx, "eigen", 52.0 * nx * ny, (eigen_kernel<<<dim3((nx + 255) / 256, (ny + EIG_ROWS - 1) / EIG_ROWS), 256, 0, ctx->stream>>>(
+                                                      sxx, sxy, syy, w, bx, by, hw, hh, skip + 1, nx, ny, val_dev, nullptr, 0.f)));
     return KLT_OK;
 }
 
@@ -298,75 +442,102 @@ int klt_select_device(klt_ctx *ctx, const klt_params *p, const float *gx, const 
     if (w - bx > bx) nx = (w - 2 * bx + step - 1) / step;
     if (h - by > by) ny = (h - 2 * by + step - 1) / step;
     const size_t ncand = (size_t)nx * ny;
-    int mindist = p->mindist < 0 ? 0 : p->mindist;            // :241-243
-    int min_eig = p->min_eigenvalue < 1 ? 1 : p->min_eigenvalue;   // :53
+    const int mindist = p->mindist < 0 ? 0 : p->mindist;                 // :241-243
+    const int min_eig = p->min_eigenvalue < 1 ? 1 : p->min_eigenvalue;   // :53
+    const int r = mindist - 1;                                           // :61
+    if (r > 254) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "mindist larger than 255");
 
     const size_t plane = align_up((size_t)w * h * sizeof(float), 256);
+    const size_t val_b = align_up((ncand + 1) * sizeof(float), 256);
     const size_t keys_b = align_up((ncand + 1) * sizeof(unsigned long long), 256);
-    const int nblocks = (int)((ncand + RS_CHUNK - 1) / RS_CHUNK) + 1;
-    const size_t hist_b = align_up((size_t)256 * nblocks * sizeof(unsigned int), 256);
+    const int max_blocks = (int)((ncand + RS_CHUNK - 1) / RS_CHUNK) + 1;
+    const size_t hist_b = align_up((size_t)256 * max_blocks * sizeof(unsigned int), 256);
     const size_t map_b = align_up((size_t)w * h, 256);
     const size_t feat_b = align_up((size_t)n_features * (2 * sizeof(double) + sizeof(int)) + 64, 256);
-    const size_t total = 3 * plane + 2 * keys_b + hist_b + map_b + feat_b + 256;
+    const int cs = r >= 0 ? r + 1 : 1, gw = (w + cs - 1) / cs, gh = (h + cs - 1) / cs;
+    const size_t grid_b = align_up((size_t)gw * gh * sizeof(unsigned short), 256);
+    const bool grid_in_smem = grid_b <= 200 * 1024;
+    const size_t total = 3 * plane + val_b + 2 * keys_b + hist_b + map_b + feat_b + grid_b + EIG_BINS * 4 + 512;
     int rc = klt_ws_reserve(ctx, total);
     if (rc) return rc;
     char *wsp = (char *)ctx->ws;
     float *sxx = (float *)wsp; wsp += plane;
     float *sxy = (float *)wsp; wsp += plane;
     float *syy = (float *)wsp; wsp += plane;
+    float *vmap = (float *)wsp; wsp += val_b;
     unsigned long long *keys0 = (unsigned long long *)wsp; wsp += keys_b;
     unsigned long long *keys1 = (unsigned long long *)wsp; wsp += keys_b;
     unsigned int *hist = (unsigned int *)wsp; wsp += hist_b;
     unsigned char *map = (unsigned char *)wsp; wsp += map_b;
     double *fx = (double *)wsp; double *fy = fx + n_features; int *fval = (int *)(fy + n_features); wsp += feat_b;
-    unsigned int *nkeys = (unsigned int *)wsp;
-    unsigned long long *consumed = (unsigned long long *)(wsp + 8);
+    unsigned short *grid_g = (unsigned short *)wsp; wsp += grid_b;
+    unsigned int *ehist = (unsigned int *)wsp; wsp += EIG_BINS * 4;
+    unsigned int *nkeys = (unsigned int *)wsp;                       // [0] key count, [1] threshold bin
+    unsigned long long *consumed = (unsigned long long *)(wsp + 64); // [0] consumed, [1] ran out, [2] next slot
 
-    KLT_CUDA(ctx, cudaMemsetAsync(nkeys, 0, 16, ctx->stream));
-    KLT_CUDA(ctx, cudaMemsetAsync(map, 0, (size_t)w * h, ctx->stream));
+    KLT_CUDA(ctx, cudaMemsetAsync(ehist, 0, EIG_BINS * 4 + 512, ctx->stream));
     if (replace) {
         KLT_CUDA(ctx, cudaMemcpyAsync(fx, x, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
         KLT_CUDA(ctx, cudaMemcpyAsync(fy, y, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
         KLT_CUDA(ctx, cudaMemcpyAsync(fval, val, n_features * sizeof(int), cudaMemcpyDefault, ctx->stream));
+        KLT_CUDA(ctx, cudaMemsetAsync(map, 0, (size_t)w * h, ctx->stream));
+        if (r >= 0 && n_features > 0)
+            KLT_LAUNCH(ctx, "premark", 0.0, (premark_kernel<<<n_features, 128, 0, ctx->stream>>>(fx, fy, fval, n_features, map, w, h, r)));
     }
-    sat_rows_kernel<<<(h + 31) / 32, 32, 0, ctx->stream>>>(gx, gy, pitch, w, h, sxx, sxy, syy);
-    KLT_CHECK_LAUNCH(ctx);
-    sat_cols_kernel<<<dim3((w + 127) / 128, 3), 128, 0, ctx->stream>>>(sxx, sxy, syy, w, h);
-    KLT_CHECK_LAUNCH(ctx);
-    if (ncand) {
-        eigen_kernel<<<dim3((nx + 255) / 256, ny), 256, 0, ctx->stream>>>(sxx, sxy, syy, w, bx, by, hw, hh, step, nx, ny, nullptr,
-                                                                        keys0, nkeys, (float)min_eig);
-        KLT_CHECK_LAUNCH(ctx);
-        // 58 significant key bits -> 8 passes of 8 bits (the launch geometry covers the worst case ncand;
-        // blocks beyond the actual key count see no valid items)
-        unsigned long long *src = keys0, *dst = keys1;
-        for (int pass = 0; pass < 8; pass++) {
-            rs_hist_kernel<<<nblocks, RS_THREADS, 0, ctx->stream>>>(src, nkeys, pass * 8, hist, nblocks);
-            KLT_CHECK_LAUNCH(ctx);
-            rs_scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, 256 * nblocks);
-            KLT_CHECK_LAUNCH(ctx);
-            rs_scatter_kernel<<<nblocks, RS_THREADS, 0, ctx->stream>>>(src, dst, nkeys, pass * 8, hist, nblocks);
-            KLT_CHECK_LAUNCH(ctx);
-            unsigned long long *t = src; src = dst; dst = t;
+    if ((rc = launch_sat(ctx, gx, gy, pitch, w, h, sxx, sxy, syy))) return rc;
+    if (ncand)
+        KLT_LAUNCH(ctx, "eigen", 52.0 * ncand, (eigen_kernel<<<dim3((nx + 255) / 256, (ny + EIG_ROWS - 1) / EIG_ROWS), 256, 0, ctx->stream>>>(
+                                                    sxx, sxy, syy, w, bx, by, hw, hh, step, nx, ny, vmap, ehist, (float)min_eig)));
+    GreedyArgs G;
+    G.nkeys = nkeys; G.premap = replace ? map : nullptr; G.grid_global = grid_g; G.W = w; G.H = h; G.r = r;
+    G.n_features = n_features; G.overwrite = replace ? 0 : 1; G.cs = cs; G.gw = gw; G.gh = gh; G.grid_in_smem = grid_in_smem ? 1 : 0;
+    G.fx = fx; G.fy = fy; G.fval = fval; G.consumed = consumed;
+    if (grid_in_smem) KLT_CUDA(ctx, cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    unsigned long long cons[3] = {0, 0, 0};
+    const unsigned int target = (unsigned int)(32u * (unsigned int)n_features + 8192u);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        // attempt 0: only the best ~target candidates; attempt 1 (rare): every candidate >= min_eigenvalue
+        unsigned int hk[2] = {0, 0};
+        if (ncand) {
+            KLT_CUDA(ctx, cudaMemsetAsync(nkeys, 0, 8, ctx->stream));
+            KLT_LAUNCH(ctx, "threshold", 0.0, (threshold_kernel<<<1, 32, 0, ctx->stream>>>(ehist, target, attempt, nkeys + 1)));
+            KLT_LAUNCH(ctx, "compact", 4.0 * ncand, (compact_kernel<<<dim3((nx + 255) / 256, ny), 256, 0, ctx->stream>>>(
+                                                        vmap, bx, by, step, nx, ny, (float)min_eig, nkeys + 1, keys0, nkeys)));
+            KLT_CUDA(ctx, cudaMemcpyAsync(hk, nkeys, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));        // the sort's launch geometry follows the key count
         }
-        GreedyArgs G;
-        G.keys = src; G.nkeys = nkeys; G.map = map; G.W = w; G.H = h; G.r = mindist - 1; G.n_features = n_features;
-        G.overwrite = replace ? 0 : 1; G.fx = fx; G.fy = fy; G.fval = fval; G.consumed = consumed;
-        greedy_kernel<<<1, 32, 0, ctx->stream>>>(G);
-        KLT_CHECK_LAUNCH(ctx);
-    } else {
-        GreedyArgs G;
-        G.keys = keys0; G.nkeys = nkeys; G.map = map; G.W = w; G.H = h; G.r = mindist - 1; G.n_features = n_features;
-        G.overwrite = replace ? 0 : 1; G.fx = fx; G.fy = fy; G.fval = fval; G.consumed = consumed;
-        greedy_kernel<<<1, 32, 0, ctx->stream>>>(G);
-        KLT_CHECK_LAUNCH(ctx);
+        const unsigned int nk = hk[0];
+        const int nblocks = (int)((nk + RS_CHUNK - 1) / RS_CHUNK);
+        unsigned long long *src = keys0, *dst = keys1;
+        if (nblocks > 0) {
+            // 58 significant key bits -> 8 passes of 8 bits
+            for (int pass = 0; pass < 8; pass++) {
+                KLT_LAUNCH(ctx, "rs_hist", 8.0 * nk, (rs_hist_kernel<<<nblocks, RS_THREADS, 0, ctx->stream>>>(src, nkeys, pass * 8, hist, nblocks)));
+                KLT_LAUNCH(ctx, "rs_scan", 0.0, (rs_scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, 256 * nblocks)));
+                KLT_LAUNCH(ctx, "rs_scatter", 16.0 * nk, (rs_scatter_kernel<<<nblocks, RS_THREADS, 0, ctx->stream>>>(src, dst, nkeys, pass * 8, hist, nblocks)));
+                unsigned long long *t = src; src = dst; dst = t;
+            }
+        }
+        if (replace && attempt == 1) {      // the first walk may have filled slots: start again from the caller's list
+            KLT_CUDA(ctx, cudaMemcpyAsync(fval, val, n_features * sizeof(int), cudaMemcpyDefault, ctx->stream));
+            KLT_CUDA(ctx, cudaMemcpyAsync(fx, x, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
+            KLT_CUDA(ctx, cudaMemcpyAsync(fy, y, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
+        }
+        G.keys = src;
+        KLT_LAUNCH(ctx, "greedy", 0.0, (greedy_kernel<<<1, 32, grid_in_smem ? grid_b : 0, ctx->stream>>>(G)));
+        KLT_CUDA(ctx, cudaMemcpyAsync(cons, consumed, sizeof(cons), cudaMemcpyDeviceToHost, ctx->stream));
+        KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const bool thresholded = hk[1] > 0;
+        if (!(cons[1] && thresholded)) break;   // all slots filled, or nothing was excluded: this IS the greedy result
+    }
+    if (!replace && cons[1] && (int)cons[2] < n_features) {
+        const int rest = n_features - (int)cons[2];
+        KLT_LAUNCH(ctx, "fill_not_found", 0.0, (fill_not_found_kernel<<<(rest + 127) / 128, 128, 0, ctx->stream>>>(fx, fy, fval, n_features, consumed)));
     }
     KLT_CUDA(ctx, cudaMemcpyAsync(x, fx, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
     KLT_CUDA(ctx, cudaMemcpyAsync(y, fy, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
     KLT_CUDA(ctx, cudaMemcpyAsync(val, fval, n_features * sizeof(int), cudaMemcpyDefault, ctx->stream));
-    unsigned long long cons = 0;
-    if (n_consumed) KLT_CUDA(ctx, cudaMemcpyAsync(&cons, consumed, sizeof(cons), cudaMemcpyDeviceToHost, ctx->stream));
     KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (n_consumed) *n_consumed = (int64_t)cons;
+    if (n_consumed) *n_consumed = (int64_t)cons[0];
     return KLT_OK;
 }
