@@ -103,6 +103,68 @@ __device__ __forceinline__ void grad_row(GradState &st, const StreamTaps &T, con
 // ---- level 0: u8 frame -> smoothed image, gradx, grady -----------------------------------------------------------
 // Lane l of a warp owns columns c = 120*strip + 4*(l-1) .. c+3; lanes 1..30 store outputs.
 template <int RS>
+struct L0State {
+    const unsigned char *b0, *bl, *br;     // frame base + (mirrored) column of the own / left / right quad
+    unsigned int sel0, sell, selr;          // byte-reversal selectors for mirrored quads
+    unsigned int w0, wl, wr;                // quads of the row loaded one iteration ahead
+    float sa[4][2 * RS];                    // pending smoothed rows
+    GradState gs;
+    float *p_img, *p_gx, *p_gy;             // next output rows
+    size_t opitch;                          // output pitch in floats
+    unsigned int pitch;
+    int H, ys, ye, t1, writer;
+};
+
+// One input row t: finish smoothed row r = t - RS, feed it to the gradient stage (finishing gradient row r - 3).
+// LEAN = steady state of a segment: every store happens, no warm-up tests.
+template <int RS, bool LEAN>
+__device__ __forceinline__ void l0_row(L0State<RS> &S, const StreamTaps &T, int t) {
+    // ---- consume the row loaded one iteration ago, then immediately issue the next row's loads ----
+    const unsigned int q0 = __byte_perm(S.w0, 0u, S.sel0), ql = __byte_perm(S.wl, 0u, S.sell), qr = __byte_perm(S.wr, 0u, S.selr);
+    float u[4 + 2 * RS];                             // columns c-RS .. c+3+RS
+#pragma unroll
+    for (int i = 0; i < 4; i++) u[RS + i] = u8_to_f32(q0, i);
+#pragma unroll
+    for (int k = 0; k < RS; k++) {
+        u[k] = u8_to_f32(ql, 4 - RS + k);
+        u[RS + 4 + k] = u8_to_f32(qr, k);
+    }
+    {
+        const unsigned int ro = (unsigned int)reflect1(min(t + 1, S.t1 - 1), S.H) * S.pitch;
+        S.w0 = __ldg(reinterpret_cast<const unsigned int *>(S.b0 + ro));
+        S.wl = __ldg(reinterpret_cast<const unsigned int *>(S.bl + ro));
+        S.wr = __ldg(reinterpret_cast<const unsigned int *>(S.br + ro));
+        const int tp = t + PREFETCH_ROWS;
+        if (tp < S.t1) prefetch_l2(S.b0 + (unsigned int)reflect1(tp, S.H) * S.pitch);
+    }
+    // ---- horizontal + vertical smooth ----
+    float s[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float h = T.s[0] * u[i];
+#pragma unroll
+        for (int j = 1; j < 2 * RS + 1; j++) h = fmaf(T.s[j], u[i + j], h);
+        s[i] = vacc<RS>(S.sa[i], T.s, h);
+    }
+    const int r = t - RS;
+    if (!LEAN && r < S.ys - 3) return;                   // vertical smooth still warming up (warp-uniform)
+    if (LEAN || (r >= S.ys && r < S.ye)) {
+        if (S.writer) *reinterpret_cast<float4 *>(S.p_img) = make_float4(s[0], s[1], s[2], s[3]);
+        S.p_img += S.opitch;
+    }
+    float4 gx, gy;
+    grad_row(S.gs, T, s, gx, gy);                        // completes gradient row q = r - 3
+    if (LEAN || r - 3 >= S.ys) {                         // q < ye by construction
+        if (S.writer) {
+            *reinterpret_cast<float4 *>(S.p_gx) = gx;
+            *reinterpret_cast<float4 *>(S.p_gy) = gy;
+        }
+        S.p_gx += S.opitch;
+        S.p_gy += S.opitch;
+    }
+}
+
+template <int RS>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 stream_level0_kernel(const unsigned char *__restrict__ frames, size_t pitch, size_t frame_stride, float *__restrict__ img,
                      float *__restrict__ gxo, float *__restrict__ gyo, int out_pitch, size_t out_stride, int W, int H,
@@ -113,75 +175,37 @@ stream_level0_kernel(const unsigned char *__restrict__ frames, size_t pitch, siz
     const int ys = blockIdx.y * rows_per_seg, ye = min(H, ys + rows_per_seg);
     const int c = strip * 120 + 4 * (lane - 1);
     const unsigned char *src = frames + (size_t)blockIdx.z * frame_stride;
+    L0State<RS> S;
     // own quad and the two neighbour quads (through L1: the neighbour lanes load them as their own)
     bool rv0, rvl, rvr;
     const int m0 = mirror_quad(c, W, rv0), ml = mirror_quad(c - 4, W, rvl), mr = mirror_quad(c + 4, W, rvr);
-    const unsigned int sel0 = rv0 ? 0x0123u : 0x3210u, sell = rvl ? 0x0123u : 0x3210u, selr = rvr ? 0x0123u : 0x3210u;
-    const bool writer = lane >= 1 && lane <= 30 && c < W;
-    const size_t ooff = (size_t)blockIdx.z * out_stride + (size_t)c;
-    float *p_img = img + ooff + (size_t)ys * out_pitch;   // next row to store
-    float *p_gx = gxo + ooff + (size_t)ys * out_pitch;
-    float *p_gy = gyo + ooff + (size_t)ys * out_pitch;
-
-    float sa[4][2 * RS];
+    S.b0 = src + m0; S.bl = src + ml; S.br = src + mr;
+    S.sel0 = rv0 ? 0x0123u : 0x3210u; S.sell = rvl ? 0x0123u : 0x3210u; S.selr = rvr ? 0x0123u : 0x3210u;
+    S.writer = (lane >= 1 && lane <= 30 && c < W) ? 1 : 0;
+    const size_t ooff = (size_t)blockIdx.z * out_stride + (size_t)c + (size_t)ys * out_pitch;
+    S.p_img = img + ooff; S.p_gx = gxo + ooff; S.p_gy = gyo + ooff;
+    S.opitch = (size_t)out_pitch; S.pitch = (unsigned int)pitch;
+    S.H = H; S.ys = ys; S.ye = ye;
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int m = 0; m < 2 * RS; m++) sa[i][m] = 0.f;
-    GradState gs;
-    grad_init(gs);
+        for (int m = 0; m < 2 * RS; m++) S.sa[i][m] = 0.f;
+    grad_init(S.gs);
 
     const int t0 = ys - 3 - RS, t1 = ye + 3 + RS;       // input rows [t0, t1) of the reflect-extended frame
-    const unsigned char *row = src + (size_t)reflect1(t0, H) * pitch;
-    unsigned int w0 = __ldg(reinterpret_cast<const unsigned int *>(row + m0));
-    unsigned int wl = __ldg(reinterpret_cast<const unsigned int *>(row + ml));
-    unsigned int wr = __ldg(reinterpret_cast<const unsigned int *>(row + mr));
-    for (int t = t0; t < t1; t++) {
-        // ---- consume the row loaded one iteration ago, then immediately issue the next row's loads ----
-        const unsigned int q0 = __byte_perm(w0, 0u, sel0), ql = __byte_perm(wl, 0u, sell), qr = __byte_perm(wr, 0u, selr);
-        float u[4 + 2 * RS];                             // columns c-RS .. c+3+RS
-#pragma unroll
-        for (int i = 0; i < 4; i++) u[RS + i] = u8_to_f32(q0, i);
-#pragma unroll
-        for (int k = 0; k < RS; k++) {
-            u[k] = u8_to_f32(ql, 4 - RS + k);
-            u[RS + 4 + k] = u8_to_f32(qr, k);
-        }
-        {
-            const int tn = min(t + 1, t1 - 1);
-            const unsigned char *nrow = src + (size_t)reflect1(tn, H) * pitch;
-            w0 = __ldg(reinterpret_cast<const unsigned int *>(nrow + m0));
-            wl = __ldg(reinterpret_cast<const unsigned int *>(nrow + ml));
-            wr = __ldg(reinterpret_cast<const unsigned int *>(nrow + mr));
-            const int tp = t + PREFETCH_ROWS;
-            if (tp < t1) prefetch_l2(src + (size_t)reflect1(tp, H) * pitch + m0);
-        }
-        // ---- horizontal + vertical smooth: completes smoothed row r = t - RS ----
-        float s[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            float h = T.s[0] * u[i];
-#pragma unroll
-            for (int j = 1; j < 2 * RS + 1; j++) h = fmaf(T.s[j], u[i + j], h);
-            s[i] = vacc<RS>(sa[i], T.s, h);
-        }
-        const int r = t - RS;
-        if (r < ys - 3) continue;                        // vertical smooth still warming up (warp-uniform)
-        if (r >= ys && r < ye) {
-            if (writer) *reinterpret_cast<float4 *>(p_img) = make_float4(s[0], s[1], s[2], s[3]);
-            p_img += out_pitch;
-        }
-        float4 gx, gy;
-        grad_row(gs, T, s, gx, gy);                      // completes gradient row q = r - 3
-        if (r - 3 >= ys) {                               // q < ye by construction
-            if (writer) {
-                *reinterpret_cast<float4 *>(p_gx) = gx;
-                *reinterpret_cast<float4 *>(p_gy) = gy;
-            }
-            p_gx += out_pitch;
-            p_gy += out_pitch;
-        }
+    S.t1 = t1;
+    {
+        const unsigned int ro = (unsigned int)reflect1(t0, H) * S.pitch;
+        S.w0 = __ldg(reinterpret_cast<const unsigned int *>(S.b0 + ro));
+        S.wl = __ldg(reinterpret_cast<const unsigned int *>(S.bl + ro));
+        S.wr = __ldg(reinterpret_cast<const unsigned int *>(S.br + ro));
     }
+    // warm-up rows and the first three stored rows (tests inside), the steady state (no tests), the last three rows
+    int t = t0;
+    const int lean0 = min(ys + 3 + RS, t1), lean1 = max(lean0, ye + RS);
+    for (; t < lean0; t++) l0_row<RS, false>(S, T, t);
+    for (; t < lean1; t++) l0_row<RS, true>(S, T, t);
+    for (; t < t1; t++) l0_row<RS, false>(S, T, t);
 }
 
 // ---- gradients only: float image -> gradx, grady (levels >= 1) ---------------------------------------------------
