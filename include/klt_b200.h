@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KLT_B200_ABI_VERSION 1
+#define KLT_B200_ABI_VERSION 2
 #define KLT_MAX_TAPS 71   /* convolve.py:28 maxKernelWidth */
 #define KLT_MAX_LEVELS 8
 
@@ -58,6 +58,7 @@ typedef enum klt_status {
 
 typedef struct klt_ctx klt_ctx; /* one per (device, stream) */
 typedef struct klt_pyr klt_pyr; /* a batch of image pyramids: intensity, gradx, grady for every level */
+typedef struct klt_affine klt_affine; /* per-feature affine-consistency state (templates, template centre, 2x2 map) */
 
 /* One 1-D kernel, as produced by _computeKernels (convolve.py:27-93).  Computed on the host. */
 typedef struct klt_kernel1d {
@@ -88,7 +89,12 @@ typedef struct klt_params {
     float max_residue;
     int32_t retain_trackers;
     int32_t lighting_insensitive; /* must be 0: the reference raises (trackFeaturesUtils.pyx:434-437) */
-    int32_t reserved[8];
+    /* affine consistency check (klt.py:67-73); only read by klt_track_features_affine */
+    int32_t affine_consistency_check;        /* -1 off, 0 translation, 1 similarity, 2 affine */
+    int32_t affine_window_width, affine_window_height;
+    int32_t affine_max_iterations;
+    float affine_max_residue, affine_min_displacement, affine_max_displacement_differ;
+    int32_t reserved[1];
 } klt_params;
 
 /* ---- library / context ------------------------------------------------------------------------- */
@@ -177,6 +183,26 @@ int klt_select_good_features(klt_ctx *ctx, const klt_params *params, const klt_p
  * n_iterations (optional, host): total Newton iterations executed. */
 int klt_track_features(klt_ctx *ctx, const klt_params *params, const klt_pyr *pyr1, const klt_pyr *pyr2,
                        int n_per_image, double *x, double *y, int32_t *val, int64_t *n_iterations);
+/* ---- affine consistency check: the block at trackFeatures.py:347-399.  The reference's callees there
+ * (_KLTCreateFloatImage, _am_getSubFloatImage, _am_trackFeatureAffine) are undefined (NameError); these entry points
+ * implement the C-KLT 1.3.4 routines of those names (parity against oracle/klt_oracle.c, unpinned by the reference).
+ * A klt_affine holds, for n_features_total feature slots, what the reference keeps on each KLT_Feature:
+ * aff_img / aff_img_gradx / aff_img_grady ((aw+2) x (ah+2) templates), aff_x, aff_y, aff_Axx, aff_Ayx, aff_Axy, aff_Ayy. */
+int klt_affine_create(klt_ctx *ctx, int n_features_total, int affine_window_width, int affine_window_height, klt_affine **out);
+int klt_affine_destroy(klt_ctx *ctx, klt_affine *a);
+/* mask (host, n_features_total ints, or NULL = all): slots to reset to "no template, aff_x = aff_y = -1, A = identity"
+ * (what selectGoodFeatures.py:120-128 does to a (re)selected feature) */
+int klt_affine_reset(klt_ctx *ctx, klt_affine *a, const int32_t *mask);
+/* host copies of the state: has_template[n], aff_x[n], aff_y[n], A[n][4] = (Axx, Ayx, Axy, Ayy); any pointer may be NULL */
+int klt_affine_download(klt_ctx *ctx, const klt_affine *a, int32_t *has_template, float *aff_x, float *aff_y, float *A);
+/* template of one slot: float32 [3][(ah+2)][(aw+2)] (img, gradx, grady), host */
+int klt_affine_download_template(klt_ctx *ctx, const klt_affine *a, int slot, float *out);
+/* klt_track_features followed by the affine block for every feature the translational tracker reports KLT_TRACKED:
+ * first successful track stores the template from pyr1 level 0; later tracks run the affine tracker against pyr2
+ * level 0 and turn the feature's val into its status (x = y = -1 when lost).  x, y, val: host or device. */
+int klt_track_features_affine(klt_ctx *ctx, const klt_params *params, const klt_pyr *pyr1, const klt_pyr *pyr2,
+                              int n_per_image, double *x, double *y, int32_t *val, klt_affine *a, int64_t *n_iterations);
+
 /* trackFeaturesUtils.extractImagePatchSlow(img, x, y, height, width) (trackFeaturesUtils.pyx:14-18):
  * img float32 [h][w] host or device, out float32 [height][width] host. */
 int klt_extract_patch(klt_ctx *ctx, const float *img, int w, int h, float x, float y, int height, int width,

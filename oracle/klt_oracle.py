@@ -37,6 +37,12 @@ class _TrackParams(C.Structure):
                 ("n_levels", C.c_int), ("subsampling", C.c_int), ("borderx", C.c_double), ("bordery", C.c_double)]
 
 
+class _AffineParams(C.Structure):
+    _fields_ = [("affine_map", C.c_int), ("width", C.c_int), ("height", C.c_int), ("max_iterations", C.c_int),
+                ("step_factor", C.c_float), ("small_det", C.c_float), ("th", C.c_float), ("th_aff", C.c_float),
+                ("max_residue", C.c_float), ("mdd", C.c_float)]
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -57,6 +63,8 @@ def lib():
         L.orc_extract_patch.argtypes = [fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, fp]
         L.orc_track_feature_level.argtypes = [C.c_float, C.c_float, dp, dp, fp, fp, fp, fp, fp, fp, C.c_int, C.c_int,
                                               C.POINTER(_TrackParams), ip]
+        L.orc_affine_step.argtypes = [C.POINTER(_AffineParams), fp, fp, fp, fp, fp, fp, C.c_int, C.c_int, C.c_double,
+                                      C.c_double, C.c_double, C.c_double, ip, fp, fp, fp, fp]
         _LIB = L
     return _LIB
 
@@ -205,6 +213,13 @@ class Params:
         self.pyramid_sigma_fact = 0.9
         self.step_factor = 1.0
         self.nSkippedPixels = 0
+        self.affineConsistencyCheck = -1
+        self.affine_window_width = 15
+        self.affine_window_height = 15
+        self.affine_max_iterations = 10
+        self.affine_max_residue = 10.0
+        self.affine_min_displacement = 0.02
+        self.affine_max_displacement_differ = 1.5
         self.nPyramidLevels = 2          # what KLTChangeTCPyramid(15) gives for 7x7 (klt.py:77,84-128)
         self.subsampling = 4
         self.cache = KernelCache()
@@ -349,3 +364,68 @@ def extract_patch(img, x, y, h, w):
     if not ok:
         raise AssertionError("patch out of bounds (trackFeaturesUtils.pyx:35)")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Affine consistency check (trackFeatures.py:347-399) -- PARITY UNPINNED BY THE REFERENCE (its callees are
+# undefined there); this drives the C-KLT 1.3.4 restatement in klt_oracle.c (orc_affine_step).
+# ---------------------------------------------------------------------------------------------------
+class AffineState:
+    """What the reference keeps on each KLT_Feature: aff_img*, aff_x, aff_y, aff_A** (selectGoodFeatures.py:120-128)."""
+
+    def __init__(self, n, aw=15, ah=15):
+        self.n, self.aw, self.ah = n, aw, ah
+        self.has = np.zeros(n, np.int32)
+        self.aff_x = np.full(n, -1.0, np.float32)
+        self.aff_y = np.full(n, -1.0, np.float32)
+        self.A = np.tile(np.array([1, 0, 0, 1], np.float32), (n, 1))
+        self.tmpl = np.zeros((n, 3, ah + 2, aw + 2), np.float32)
+
+    def reset(self, mask):
+        m = np.asarray(mask, bool)
+        self.has[m] = 0
+        self.aff_x[m] = -1.0
+        self.aff_y[m] = -1.0
+        self.A[m] = (1, 0, 0, 1)
+
+
+def track_features_affine(p, img1_u8, img2_u8, x, y, val, aff, state=None):
+    """KLTTrackFeatures with tc.affineConsistencyCheck >= 0: translational tracking, then the affine block per feature."""
+    x_in = np.array(x, np.float64)
+    y_in = np.array(y, np.float64)
+    val_in = np.array(val, np.int32)
+    if p.sequentialMode and state is not None and state.get("pyramid_last") is not None:
+        pyr1 = state["pyramid_last"]
+    else:
+        pyr1 = image_pyramids(p, img1_u8)
+    pyr2 = image_pyramids(p, img2_u8)
+    x2, y2, v2, it = track_on_pyramids(p, pyr1, pyr2, x_in, y_in, val_in)
+    if p.sequentialMode and state is not None:
+        state["pyramid_last"] = pyr2
+    ap = _AffineParams(int(p.affineConsistencyCheck), p.affine_window_width, p.affine_window_height,
+                       p.affine_max_iterations, p.step_factor, p.min_determinant, p.min_displacement,
+                       p.affine_min_displacement, p.affine_max_residue, p.affine_max_displacement_differ)
+    i1, g1x, g1y = (np.ascontiguousarray(a[0], np.float32) for a in pyr1)
+    i2, g2x, g2y = (np.ascontiguousarray(a[0], np.float32) for a in pyr2)
+    nr, nc = i1.shape
+    for f in range(len(x_in)):
+        if val_in[f] < 0:
+            continue
+        if v2[f] != KLT_TRACKED:
+            aff.has[f] = 0
+            continue
+        has = C.c_int(int(aff.has[f]))
+        ax, ay = C.c_float(float(aff.aff_x[f])), C.c_float(float(aff.aff_y[f]))
+        A = np.ascontiguousarray(aff.A[f])
+        t = np.ascontiguousarray(aff.tmpl[f])
+        st = lib().orc_affine_step(C.byref(ap), _f(i1), _f(g1x), _f(g1y), _f(i2), _f(g2x), _f(g2y), nc, nr,
+                                   float(x_in[f]), float(y_in[f]), float(x2[f]), float(y2[f]), C.byref(has),
+                                   C.byref(ax), C.byref(ay), _f(A), _f(t))
+        if st == ORC_ASSERT:
+            raise AssertionError("affine template leaves the image")
+        aff.has[f], aff.aff_x[f], aff.aff_y[f] = has.value, ax.value, ay.value
+        aff.A[f] = A
+        aff.tmpl[f] = t
+        if st != KLT_TRACKED:
+            v2[f], x2[f], y2[f] = st, -1.0, -1.0
+    return x2, y2, v2, it

@@ -44,7 +44,11 @@ class Params(C.Structure):
                 ("mindist", C.c_int32), ("min_eigenvalue", C.c_int32), ("n_skipped_pixels", C.c_int32),
                 ("max_iterations", C.c_int32), ("min_determinant", C.c_float), ("min_displacement", C.c_float),
                 ("step_factor", C.c_float), ("has_max_residue", C.c_int32), ("max_residue", C.c_float),
-                ("retain_trackers", C.c_int32), ("lighting_insensitive", C.c_int32), ("reserved", C.c_int32 * 8)]
+                ("retain_trackers", C.c_int32), ("lighting_insensitive", C.c_int32),
+                ("affine_consistency_check", C.c_int32), ("affine_window_width", C.c_int32),
+                ("affine_window_height", C.c_int32), ("affine_max_iterations", C.c_int32),
+                ("affine_max_residue", C.c_float), ("affine_min_displacement", C.c_float),
+                ("affine_max_displacement_differ", C.c_float), ("reserved", C.c_int32 * 1)]
 
 
 _lib = None
@@ -88,6 +92,12 @@ SIGNATURES = {
     "klt_select_good_features": (_i, [_vp, C.POINTER(Params), _vp, _i, _fp, _fp, _i, _i, _i, _i, _dp, _dp, _ip,
                                       C.POINTER(C.c_int64)]),
     "klt_track_features": (_i, [_vp, C.POINTER(Params), _vp, _vp, _i, _dp, _dp, _ip, C.POINTER(C.c_int64)]),
+    "klt_affine_create": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),
+    "klt_affine_destroy": (_i, [_vp, _vp]),
+    "klt_affine_reset": (_i, [_vp, _vp, _ip]),
+    "klt_affine_download": (_i, [_vp, _vp, _ip, _fp, _fp, _fp]),
+    "klt_affine_download_template": (_i, [_vp, _vp, _i, _fp]),
+    "klt_track_features_affine": (_i, [_vp, C.POINTER(Params), _vp, _vp, _i, _dp, _dp, _ip, _vp, C.POINTER(C.c_int64)]),
     "klt_extract_patch": (_i, [_vp, _fp, _i, _i, C.c_float, C.c_float, _i, _i, _fp]),
     "klt_track_pairs_u8": (_i, [_vp, C.POINTER(Params), C.POINTER(Taps), _i, _vp, _vp, _u8p, _u8p, _sz, _sz, _i,
                                 _dp, _dp, _ip]),
@@ -168,6 +178,50 @@ class Pyramid:
     def close(self):
         if self.handle:
             lib().klt_pyr_destroy(self.ctx.handle, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class AffineState:
+    """Owns one klt_affine: per-feature templates, template centres and 2x2 maps of the affine consistency check."""
+
+    def __init__(self, ctx, n, aw, ah):
+        self.ctx, self.n, self.aw, self.ah = ctx, n, aw, ah
+        hnd = C.c_void_p()
+        ctx.check(lib().klt_affine_create(ctx.handle, n, aw, ah, C.byref(hnd)))
+        self.handle = hnd
+
+    def reset(self, mask=None):
+        if mask is None:
+            self.ctx.check(lib().klt_affine_reset(self.ctx.handle, self.handle, None))
+        else:
+            m = np.ascontiguousarray(mask, np.int32)
+            assert m.shape == (self.n,)
+            self.ctx.check(lib().klt_affine_reset(self.ctx.handle, self.handle, m.ctypes.data))
+            self.ctx.sync()
+
+    def download(self):
+        has = np.empty(self.n, np.int32)
+        ax = np.empty(self.n, np.float32)
+        ay = np.empty(self.n, np.float32)
+        A = np.empty((self.n, 4), np.float32)
+        self.ctx.check(lib().klt_affine_download(self.ctx.handle, self.handle, has.ctypes.data, ax.ctypes.data,
+                                                 ay.ctypes.data, A.ctypes.data))
+        return has, ax, ay, A
+
+    def template(self, slot):
+        out = np.empty((3, self.ah + 2, self.aw + 2), np.float32)
+        self.ctx.check(lib().klt_affine_download_template(self.ctx.handle, self.handle, slot, out.ctypes.data))
+        return out
+
+    def close(self):
+        if self.handle:
+            lib().klt_affine_destroy(self.ctx.handle, self.handle)
             self.handle = None
 
     def __del__(self):

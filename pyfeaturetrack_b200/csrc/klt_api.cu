@@ -479,17 +479,22 @@ static int check_track_args(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1
     return KLT_OK;
 }
 
-int klt_track_features(klt_ctx *ctx, const klt_params *params, const klt_pyr *pyr1, const klt_pyr *pyr2, int n_per_image,
-                       double *x, double *y, int32_t *val, int64_t *n_iterations) {
+static int track_impl(klt_ctx *ctx, const klt_params *params, const klt_pyr *pyr1, const klt_pyr *pyr2, int n_per_image,
+                      double *x, double *y, int32_t *val, klt_affine *aff, int64_t *n_iterations) {
     if (!ctx || !params || !pyr1 || !pyr2 || !x || !y || !val || n_per_image < 0) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
     int rc;
     if ((rc = check_track_args(ctx, params, pyr1, pyr2))) return rc;
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t total = (size_t)n_per_image * pyr1->batch;
+    if (aff) {
+        if ((size_t)aff->n != total) return klt_fail(ctx, KLT_ERR_INVALID, "affine state has %d slots, %zu features given", aff->n, total);
+        if (params->affine_consistency_check < 0 || params->affine_consistency_check > 2) return klt_fail(ctx, KLT_ERR_INVALID, "affine_consistency_check must be 0, 1 or 2");
+        if (params->affine_window_width != aff->aw || params->affine_window_height != aff->ah) return klt_fail(ctx, KLT_ERR_INVALID, "affine window differs from the affine state's");
+    }
     const bool host = !klt_is_device_ptr(x);
     if (host != !klt_is_device_ptr(y) || host != !klt_is_device_ptr(val)) return klt_fail(ctx, KLT_ERR_INVALID, "x, y, val must all be host or all be device");
     const size_t fbytes = align_up(total * sizeof(double), 256);
-    if ((rc = klt_ws_reserve(ctx, 3 * fbytes + 256))) return rc;
+    if ((rc = klt_ws_reserve(ctx, 6 * fbytes + 256))) return rc;
     char *wsp = (char *)ctx->ws;
     unsigned long long *iters = (unsigned long long *)wsp;
     int *aflag = (int *)(wsp + 8);
@@ -502,7 +507,16 @@ int klt_track_features(klt_ctx *ctx, const klt_params *params, const klt_pyr *py
         KLT_CUDA(ctx, cudaMemcpyAsync(dy, y, total * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         KLT_CUDA(ctx, cudaMemcpyAsync(dval, val, total * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
+    double *x_in = nullptr, *y_in = nullptr;
+    int32_t *val_in = nullptr;
+    if (aff) {   // the affine block needs the pre-track positions (xloc, yloc) and which features were live
+        x_in = (double *)(wsp + 256 + 3 * fbytes); y_in = (double *)(wsp + 256 + 4 * fbytes); val_in = (int32_t *)(wsp + 256 + 5 * fbytes);
+        KLT_CUDA(ctx, cudaMemcpyAsync(x_in, dx, total * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        KLT_CUDA(ctx, cudaMemcpyAsync(y_in, dy, total * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        KLT_CUDA(ctx, cudaMemcpyAsync(val_in, dval, total * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     if ((rc = klt_launch_track(ctx, params, pyr1, pyr2, n_per_image, dx, dy, dval, iters, aflag))) return rc;
+    if (aff && (rc = klt_launch_affine(ctx, params, pyr1, pyr2, n_per_image, x_in, y_in, val_in, dx, dy, dval, aff, aflag))) return rc;
     if (host) {
         KLT_CUDA(ctx, cudaMemcpyAsync(x, dx, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         KLT_CUDA(ctx, cudaMemcpyAsync(y, dy, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -516,6 +530,76 @@ int klt_track_features(klt_ctx *ctx, const klt_params *params, const klt_pyr *py
         if ((int)(res[1] & 0xffffffffull))
             return klt_fail(ctx, KLT_ERR_ASSERT, "a feature window leaves the image at a pyramid level: the reference raises AssertionError (trackFeaturesUtils.pyx:35)");
     }
+    return KLT_OK;
+}
+
+int klt_track_features(klt_ctx *ctx, const klt_params *params, const klt_pyr *pyr1, const klt_pyr *pyr2, int n_per_image,
+                       double *x, double *y, int32_t *val, int64_t *n_iterations) {
+    return track_impl(ctx, params, pyr1, pyr2, n_per_image, x, y, val, nullptr, n_iterations);
+}
+
+int klt_track_features_affine(klt_ctx *ctx, const klt_params *params, const klt_pyr *pyr1, const klt_pyr *pyr2, int n_per_image,
+                              double *x, double *y, int32_t *val, klt_affine *a, int64_t *n_iterations) {
+    if (!a) return klt_fail(ctx, KLT_ERR_INVALID, "affine state is NULL");
+    return track_impl(ctx, params, pyr1, pyr2, n_per_image, x, y, val, a, n_iterations);
+}
+
+int klt_affine_create(klt_ctx *ctx, int n, int aw, int ah, klt_affine **out) {
+    if (!ctx || !out || n < 0 || aw < 3 || ah < 3 || !(aw & 1) || !(ah & 1)) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    klt_affine *a = new klt_affine();
+    a->n = n; a->aw = aw; a->ah = ah;
+    const size_t tn = (size_t)(aw + 2) * (ah + 2);
+    const size_t b_has = align_up((size_t)n * 4 + 4, 256), b_f = align_up((size_t)n * 4 + 4, 256), b_A = align_up((size_t)n * 16 + 16, 256);
+    const size_t bytes = b_has + 2 * b_f + b_A + (size_t)n * 3 * tn * 4 + 256;
+    cudaError_t e = cudaMalloc(&a->block, bytes);
+    if (e != cudaSuccess) { delete a; return klt_fail(ctx, KLT_ERR_NOMEM, "cudaMalloc(%zu) for affine state failed: %s", bytes, cudaGetErrorString(e)); }
+    char *b = (char *)a->block;
+    a->has = (int *)b; b += b_has;
+    a->aff_x = (float *)b; b += b_f;
+    a->aff_y = (float *)b; b += b_f;
+    a->A = (float *)b; b += b_A;
+    a->tmpl = (float *)b;
+    int rc = klt_launch_affine_reset(ctx, a, nullptr);
+    if (rc) { cudaFree(a->block); delete a; return rc; }
+    *out = a;
+    return KLT_OK;
+}
+
+int klt_affine_destroy(klt_ctx *ctx, klt_affine *a) {
+    if (!a) return KLT_OK;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    cudaFree(a->block);
+    delete a;
+    return KLT_OK;
+}
+
+int klt_affine_reset(klt_ctx *ctx, klt_affine *a, const int32_t *mask) {
+    if (!ctx || !a) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!mask) return klt_launch_affine_reset(ctx, a, nullptr);
+    int rc = klt_ws_reserve(ctx, (size_t)a->n * 4 + 256);
+    if (rc) return rc;
+    KLT_CUDA(ctx, cudaMemcpyAsync(ctx->ws, mask, (size_t)a->n * 4, cudaMemcpyDefault, ctx->stream));
+    return klt_launch_affine_reset(ctx, a, (const int *)ctx->ws);
+}
+
+int klt_affine_download(klt_ctx *ctx, const klt_affine *a, int32_t *has_template, float *aff_x, float *aff_y, float *A) {
+    if (!ctx || !a) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    const size_t n = (size_t)a->n;
+    if (has_template) KLT_CUDA(ctx, cudaMemcpyAsync(has_template, a->has, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (aff_x) KLT_CUDA(ctx, cudaMemcpyAsync(aff_x, a->aff_x, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (aff_y) KLT_CUDA(ctx, cudaMemcpyAsync(aff_y, a->aff_y, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (A) KLT_CUDA(ctx, cudaMemcpyAsync(A, a->A, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KLT_OK;
+}
+
+int klt_affine_download_template(klt_ctx *ctx, const klt_affine *a, int slot, float *out) {
+    if (!ctx || !a || !out || slot < 0 || slot >= a->n) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    const size_t tn = (size_t)(a->aw + 2) * (a->ah + 2);
+    KLT_CUDA(ctx, cudaMemcpyAsync(out, a->tmpl + (size_t)slot * 3 * tn, 3 * tn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KLT_OK;
 }
 

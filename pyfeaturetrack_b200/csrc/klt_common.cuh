@@ -37,6 +37,15 @@ struct klt_pyr {
     }
 };
 
+struct klt_affine {
+    int n, aw, ah;
+    int *has;                 // [n] template present
+    float *aff_x, *aff_y;     // [n] template centre
+    float *A;                 // [n][4] Axx, Ayx, Axy, Ayy
+    float *tmpl;              // [n][3][(ah+2)*(aw+2)]
+    void *block;              // the single allocation behind the arrays above
+};
+
 // Per-kernel device timing (klt_profile_* in klt_b200.h): CUDA events recorded on the context's stream around
 // every launch while profiling is enabled; resolved lazily.
 struct KltProfRec {
@@ -138,6 +147,12 @@ int klt_launch_track(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const
                      double *x_dev, double *y_dev, int32_t *val_dev, unsigned long long *iters_dev, int *assert_dev);
 int klt_launch_extract_patch(klt_ctx *ctx, const float *img, size_t pitch, int w, int h, float x, float y,
                              int height, int width, float *out_dev, int *ok_dev);
+
+// ---- klt_affine.cu -----------------------------------------------------------------------------------
+int klt_launch_affine(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const klt_pyr *p2, int n_per_image,
+                      const double *x_in, const double *y_in, const int32_t *val_in, double *x, double *y, int32_t *val,
+                      klt_affine *st, int *assert_dev);
+int klt_launch_affine_reset(klt_ctx *ctx, klt_affine *st, const int *mask_dev);
 
 __host__ __device__ static inline int klt_reflect(int i, int n) {
     // scipy 'reflect' (half-sample symmetric); loop handles kernels wider than the image

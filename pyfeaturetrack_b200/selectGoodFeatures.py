@@ -56,6 +56,12 @@ def make_params(tc):
     p.max_residue = 0.0 if tc.max_residue is None else tc.max_residue
     p.retain_trackers = 1 if tc.retainTrackers else 0
     p.lighting_insensitive = 1 if tc.lighting_insensitive else 0
+    p.affine_consistency_check = int(tc.affineConsistencyCheck)
+    p.affine_window_width, p.affine_window_height = int(tc.affine_window_width), int(tc.affine_window_height)
+    p.affine_max_iterations = int(tc.affine_max_iterations)
+    p.affine_max_residue = tc.affine_max_residue
+    p.affine_min_displacement = tc.affine_min_displacement
+    p.affine_max_displacement_differ = tc.affine_max_displacement_differ
     return p
 
 

@@ -105,6 +105,38 @@ def _features_to_arrays(featurelist):
     return x, y, val
 
 
+class AffineTemplate(object):
+    """feat.aff_img / aff_img_gradx / aff_img_grady: the (aw+2) x (ah+2) template kept on the device; converts to a
+    NumPy array on demand (np.asarray(feat.aff_img)) and pickles as that array."""
+
+    def __init__(self, state, slot, which):
+        self.state, self.slot, self.which = state, slot, which
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.state.template(self.slot)[self.which]
+        return a if dtype is None else a.astype(dtype)
+
+    def __reduce__(self):
+        return (np.array, (self.__array__(),))
+
+
+def _affine_state(tc, ctx, featurelist):
+    """The klt_affine of this tracking context, with the slots of features that carry no template reset
+    (freshly selected or replaced features have aff_img = None, selectGoodFeatures.py:120-128)."""
+    n = len(featurelist)
+    st = getattr(tc, "_klt_affine", None)
+    if st is None or st.n != n or st.aw != tc.affine_window_width or st.ah != tc.affine_window_height or st.ctx is not ctx:
+        st = tc._klt_affine = _capi.AffineState(ctx, n, int(tc.affine_window_width), int(tc.affine_window_height))
+    mask = np.zeros(n, np.int32)
+    for i, feat in enumerate(featurelist):
+        t = getattr(feat, "aff_img", None)
+        if not (isinstance(t, AffineTemplate) and t.state is st and t.slot == i):
+            mask[i] = 1
+    if mask.any():
+        st.reset(mask)
+    return st
+
+
 def _clear_affine(feat):
     feat.aff_img = None
     feat.aff_img_gradx = None
@@ -120,17 +152,26 @@ def KLTTrackFeatures(tc, img1, img2, featurelist):
     _fix_window(tc, "Tracking context")
     if tc.lighting_insensitive:
         raise Exception("Not implemented")                      # trackFeaturesUtils.pyx:435
-    if tc.affineConsistencyCheck >= 0:
-        # the reference dies here with NameError: _KLTCreateFloatImage is undefined (trackFeatures.py:356)
-        raise NameError("name '_KLTCreateFloatImage' is not defined (affine consistency check is not implemented in the reference)")
+    use_affine = tc.affineConsistencyCheck >= 0
+    if use_affine and tc.affineConsistencyCheck > 2:
+        raise ValueError("affineConsistencyCheck must be -1, 0, 1 or 2")
 
     pyramid1, pyramid1_gradx, pyramid1_grady, pyramid2, pyramid2_gradx, pyramid2_grady = ComputeImagePyramids(tc, img1, img2)
     ctx = pyramid1.pyr.ctx
     x, y, val = _features_to_arrays(featurelist)
     was_live = val >= 0
     params = make_params(tc)
-    ctx.check(_capi.lib().klt_track_features(ctx.handle, C.byref(params), pyramid1.pyr.handle, pyramid2.pyr.handle,
-                                            len(featurelist), x.ctypes.data, y.ctypes.data, val.ctypes.data, None))
+    aff = None
+    if use_affine:
+        # The reference's affine block (trackFeatures.py:347-399) calls three undefined functions; this runs the C-KLT
+        # routines of those names on the GPU.  Per-feature state lives in a klt_affine keyed by list position.
+        aff = _affine_state(tc, ctx, featurelist)
+        ctx.check(_capi.lib().klt_track_features_affine(ctx.handle, C.byref(params), pyramid1.pyr.handle,
+                                                       pyramid2.pyr.handle, len(featurelist), x.ctypes.data,
+                                                       y.ctypes.data, val.ctypes.data, aff.handle, None))
+    else:
+        ctx.check(_capi.lib().klt_track_features(ctx.handle, C.byref(params), pyramid1.pyr.handle, pyramid2.pyr.handle,
+                                                len(featurelist), x.ctypes.data, y.ctypes.data, val.ctypes.data, None))
     xs, ys, vals = x.tolist(), y.tolist(), val.tolist()
     for i, feat in enumerate(featurelist):
         if not was_live[i]:
@@ -141,6 +182,19 @@ def KLTTrackFeatures(tc, img1, img2, featurelist):
         else:
             feat.x, feat.y, feat.val = -1.0, -1.0, v
             if hasattr(feat, "aff_img"):
+                _clear_affine(feat)
+
+    if use_affine:
+        has, ax, ay, A = aff.download()
+        for i, feat in enumerate(featurelist):
+            if not was_live[i]:
+                continue
+            feat.aff_x, feat.aff_y = float(ax[i]), float(ay[i])
+            feat.aff_Axx, feat.aff_Ayx, feat.aff_Axy, feat.aff_Ayy = (float(v) for v in A[i])
+            if has[i]:
+                if not isinstance(getattr(feat, "aff_img", None), AffineTemplate):
+                    feat.aff_img, feat.aff_img_gradx, feat.aff_img_grady = (AffineTemplate(aff, i, w) for w in range(3))
+            else:
                 _clear_affine(feat)
 
     if tc.sequentialMode:

@@ -207,3 +207,46 @@ def test_live_reference_random_configs(oracle, reference):
         tf.KLTTrackFeatures(tc, Image.fromarray(imgs[0]), Image.fromarray(imgs[1]), ref_fl)
         trk = oracle.track_features(p, imgs[0], imgs[1], *sel)[:3]
         assert_features_equal(trk, ([float(f.x) for f in ref_fl], [float(f.y) for f in ref_fl], [f.val for f in ref_fl]))
+
+
+# ---- affine consistency check: unpinned by the reference (its callees are undefined there); property tests only -------
+def _affine_sequence(n_frames=5, H=360, W=480):
+    """Frames of one texture under a growing rotation + scale + shift (known ground truth)."""
+    import scipy.ndimage as ndi
+    from pyfeaturetrack_b200 import synth
+    base = synth._texture(H, W, 7)
+    c = np.array([64 + H / 2, 64 + W / 2])
+    raw = []
+    for k in range(n_frames):
+        a, s = 0.01 * k, 1 + 0.004 * k
+        M = s * np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        off = c - M @ c + np.array([0.6 * k, -0.9 * k])
+        raw.append(ndi.affine_transform(base, M, offset=off, order=3, mode="reflect")[64:-64, 64:-64])
+    lo, hi = raw[0].min(), raw[0].max()
+    return [np.clip((f - lo) * 255 / (hi - lo), 0, 255).astype(np.uint8) for f in raw]
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_affine_restatement_recovers_known_warp(oracle, mode):
+    frames = _affine_sequence()
+    p = P(oracle, nPyramidLevels=2, subsampling=2, max_residue=10.0, affineConsistencyCheck=mode)
+    p.borderx = p.bordery = max(p.borderx, 12.0)
+    x, y, v = oracle.select_good_features(p, frames[0], 120)
+    aff = oracle.AffineState(120)
+    for k in range(1, len(frames)):
+        x, y, v, _ = oracle.track_features_affine(p, frames[k - 1], frames[k], x, y, v, aff)
+        if k == 1:
+            assert aff.has.sum() == (v == 0).sum() and np.all(aff.A == (1, 0, 0, 1))     # first track only stores templates
+            live = v == 0
+            assert np.all((aff.aff_x[live] >= 8) & (aff.aff_x[live] < 9))                  # frac + (15+2)//2
+    live = v == 0
+    assert live.mean() > 0.9
+    a, s = 0.01 * 4, 1 + 0.004 * 4
+    want = np.array([np.cos(a) / s, np.sin(a) / s, -np.sin(a) / s, np.cos(a) / s])       # inverse of the resampling map
+    got = aff.A[live].mean(0)
+    if mode == 0:
+        assert np.all(aff.A[live] == (1, 0, 0, 1))
+    else:
+        assert np.abs(got - want).max() < 5e-3, (got, want)
+    # lost features have no template and aff_x = aff_y = -1 once the affine tracker rejected them
+    assert np.all(aff.has[~live] == 0)
