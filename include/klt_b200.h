@@ -208,6 +208,23 @@ int klt_track_features_affine(klt_ctx *ctx, const klt_params *params, const klt_
 int klt_extract_patch(klt_ctx *ctx, const float *img, int w, int h, float x, float y, int height, int width,
                       float *out);
 
+/* trackFeaturesUtils.trackFeatureIterateCKLT(x2, y2, gxPatch, gyPatch, imgPatch, img2, gradx2, grady2, tc)
+ * (trackFeaturesUtils.pyx:393-459): the Newton loop for ONE feature on caller-provided template patches.
+ * patches: float32 [window_height][window_width] host; img2/gradx2/grady2: float32 [h][w] host or device. */
+int klt_track_iterate(klt_ctx *ctx, const klt_params *params, float x2, float y2, const float *gx_patch,
+                      const float *gy_patch, const float *img_patch, const float *img2, const float *gradx2,
+                      const float *grady2, int w, int h, float *x2_out, float *y2_out, int32_t *status,
+                      int32_t *iterations);
+/* computeIntensityDifference (mode 0: out = patch1 - patch(img2 at x2,y2), pyx:61-97) and computeGradientSum
+ * (mode 1: out = -patch1 - patch(img2 at x2,y2), pyx:107-142); out: float32 [height][width] host */
+int klt_patch_combine(klt_ctx *ctx, const float *patch1, const float *img2, int w, int h, float x2, float y2, int height,
+                      int width, int mode, float *out);
+/* _enforceMinimumDistance(pointlist, featurelist, ncols, nrows, mindist, min_eigenvalue, overwriteAllFeatures)
+ * (selectGoodFeatures.py:45-135) on a caller-ordered candidate list (host arrays, walked front to back) */
+int klt_enforce_min_distance(klt_ctx *ctx, int n_points, const float *pval, const int32_t *px, const int32_t *py,
+                             int ncols, int nrows, int mindist, int min_eigenvalue, int overwrite_all, int n_features,
+                             double *x, double *y, int32_t *val);
+
 /* ---- whole-call convenience: KLTTrackFeatures(tc, img1, img2, fl) for `batch` independent frame pairs with
  * HOST (ideally pinned) or device uint8 frames: upload, two pyramid builds, tracking, download.
  * pyr1/pyr2 are caller-provided scratch pyramids of matching geometry (reused across calls). */

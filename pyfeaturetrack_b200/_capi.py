@@ -99,6 +99,10 @@ SIGNATURES = {
     "klt_affine_download_template": (_i, [_vp, _vp, _i, _fp]),
     "klt_track_features_affine": (_i, [_vp, C.POINTER(Params), _vp, _vp, _i, _dp, _dp, _ip, _vp, C.POINTER(C.c_int64)]),
     "klt_extract_patch": (_i, [_vp, _fp, _i, _i, C.c_float, C.c_float, _i, _i, _fp]),
+    "klt_track_iterate": (_i, [_vp, C.POINTER(Params), C.c_float, C.c_float, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i,
+                               C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "klt_patch_combine": (_i, [_vp, _fp, _fp, _i, _i, C.c_float, C.c_float, _i, _i, _i, _fp]),
+    "klt_enforce_min_distance": (_i, [_vp, _i, _fp, _ip, _ip, _i, _i, _i, _i, _i, _i, _dp, _dp, _ip]),
     "klt_track_pairs_u8": (_i, [_vp, C.POINTER(Params), C.POINTER(Taps), _i, _vp, _vp, _u8p, _u8p, _sz, _sz, _i,
                                 _dp, _dp, _ip]),
 }

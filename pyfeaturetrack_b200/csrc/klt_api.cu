@@ -626,6 +626,92 @@ int klt_extract_patch(klt_ctx *ctx, const float *img, int w, int h, float x, flo
     return KLT_OK;
 }
 
+// ---- operator-level entry points of the reference's Cython modules --------------------------------------------------
+static int stage_image(klt_ctx *ctx, const float *img, size_t n, char *slot, const float **dev) {
+    *dev = img;
+    if (!klt_is_device_ptr(img)) {
+        KLT_CUDA(ctx, cudaMemcpyAsync(slot, img, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        *dev = (const float *)slot;
+    }
+    return KLT_OK;
+}
+
+int klt_track_iterate(klt_ctx *ctx, const klt_params *params, float x2, float y2, const float *gx_patch, const float *gy_patch,
+                      const float *img_patch, const float *img2, const float *gradx2, const float *grady2, int w, int h,
+                      float *x2_out, float *y2_out, int32_t *status, int32_t *iterations) {
+    if (!ctx || !params || !gx_patch || !gy_patch || !img_patch || !img2 || !gradx2 || !grady2 || w <= 0 || h <= 0)
+        return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    if (params->lighting_insensitive) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "lighting_insensitive: Not implemented (trackFeaturesUtils.pyx:435)");
+    if (params->window_width != params->window_height) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "non-square windows are refused (quirk Q10)");
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)w * h, plane = align_up(n * sizeof(float), 256);
+    const size_t pn = (size_t)params->window_width * params->window_height, pbytes = align_up(3 * pn * sizeof(float), 256);
+    int rc = klt_ws_reserve(ctx, 3 * plane + pbytes + 256);
+    if (rc) return rc;
+    char *wsp = (char *)ctx->ws;
+    const float *d2, *dgx, *dgy;
+    if ((rc = stage_image(ctx, img2, n, wsp, &d2))) return rc;
+    if ((rc = stage_image(ctx, gradx2, n, wsp + plane, &dgx))) return rc;
+    if ((rc = stage_image(ctx, grady2, n, wsp + 2 * plane, &dgy))) return rc;
+    float *tp = (float *)(wsp + 3 * plane), *dout = (float *)(wsp + 3 * plane + pbytes);
+    KLT_CUDA(ctx, cudaMemcpyAsync(tp, img_patch, pn * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    KLT_CUDA(ctx, cudaMemcpyAsync(tp + pn, gx_patch, pn * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    KLT_CUDA(ctx, cudaMemcpyAsync(tp + 2 * pn, gy_patch, pn * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    if ((rc = klt_launch_iterate(ctx, params, tp, d2, dgx, dgy, w, h, x2, y2, dout))) return rc;
+    float res[4];
+    KLT_CUDA(ctx, cudaMemcpyAsync(res, dout, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
+    KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (x2_out) *x2_out = res[0];
+    if (y2_out) *y2_out = res[1];
+    if (status) *status = (int32_t)res[2];
+    if (iterations) *iterations = (int32_t)res[3];
+    return KLT_OK;
+}
+
+int klt_patch_combine(klt_ctx *ctx, const float *patch1, const float *img2, int w, int h, float x2, float y2, int height,
+                      int width, int mode, float *out) {
+    if (!ctx || !patch1 || !img2 || !out || w <= 0 || h <= 0 || width < 1 || height < 1 || mode < 0 || mode > 1)
+        return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)w * h, plane = align_up(n * sizeof(float), 256), pn = (size_t)width * height, pbytes = align_up(pn * sizeof(float), 256);
+    int rc = klt_ws_reserve(ctx, plane + 2 * pbytes + 256);
+    if (rc) return rc;
+    char *wsp = (char *)ctx->ws;
+    const float *dimg;
+    if ((rc = stage_image(ctx, img2, n, wsp, &dimg))) return rc;
+    float *dp1 = (float *)(wsp + plane), *dout = (float *)(wsp + plane + pbytes);
+    int *dok = (int *)(wsp + plane + 2 * pbytes);
+    KLT_CUDA(ctx, cudaMemcpyAsync(dp1, patch1, pn * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    if ((rc = klt_launch_patch_combine(ctx, dp1, dimg, w, h, x2, y2, height, width, mode, dout, dok))) return rc;
+    int ok = 0;
+    KLT_CUDA(ctx, cudaMemcpyAsync(out, dout, pn * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    KLT_CUDA(ctx, cudaMemcpyAsync(&ok, dok, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!ok) return klt_fail(ctx, KLT_ERR_ASSERT, "patch out of bounds (trackFeaturesUtils.pyx:35)");
+    return KLT_OK;
+}
+
+int klt_enforce_min_distance(klt_ctx *ctx, int n_points, const float *pval, const int32_t *px, const int32_t *py, int ncols,
+                             int nrows, int mindist, int min_eigenvalue, int overwrite_all, int n_features, double *x,
+                             double *y, int32_t *val) {
+    if (!ctx || n_points < 0 || (n_points && (!pval || !px || !py)) || !x || !y || !val || n_features < 0)
+        return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (min_eigenvalue < 1) min_eigenvalue = 1;                       // selectGoodFeatures.py:53
+    std::vector<unsigned long long> keys;
+    keys.reserve((size_t)n_points);
+    for (int i = 0; i < n_points; i++) {
+        if (px[i] < 0 || px[i] >= ncols || py[i] < 0 || py[i] >= nrows)
+            return klt_fail(ctx, KLT_ERR_ASSERT, "candidate %d out of bounds (selectGoodFeatures.py:104-107)", i);
+        if (!(pval[i] >= (float)min_eigenvalue)) continue;           // can never be accepted (:116); skipping keeps the walk order
+        unsigned int bits;
+        memcpy(&bits, &pval[i], 4);
+        keys.push_back(~(((unsigned long long)bits << 26) | ((unsigned long long)px[i] << 13) | (unsigned long long)py[i]));
+    }
+    return klt_greedy_presorted(ctx, keys.data(), (unsigned int)keys.size(), ncols, nrows, mindist, n_features, overwrite_all ? 1 : 0,
+                                x, y, val);
+}
+
 int klt_track_pairs_u8(klt_ctx *ctx, const klt_params *params, const klt_taps *taps, int precision, klt_pyr *pyr1,
                        klt_pyr *pyr2, const uint8_t *frames1, const uint8_t *frames2, size_t pitch, size_t frame_stride,
                        int n_per_image, double *x, double *y, int32_t *val) {

@@ -147,6 +147,12 @@ int klt_launch_track(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const
                      double *x_dev, double *y_dev, int32_t *val_dev, unsigned long long *iters_dev, int *assert_dev);
 int klt_launch_extract_patch(klt_ctx *ctx, const float *img, size_t pitch, int w, int h, float x, float y,
                              int height, int width, float *out_dev, int *ok_dev);
+int klt_launch_iterate(klt_ctx *ctx, const klt_params *p, const float *tpatch_dev, const float *img2, const float *gx2,
+                       const float *gy2, int w_img, int h_img, float x2, float y2, float *out_dev);
+int klt_launch_patch_combine(klt_ctx *ctx, const float *p1_dev, const float *img, int w, int h, float x, float y, int height,
+                             int width, int mode, float *out_dev, int *ok_dev);
+int klt_greedy_presorted(klt_ctx *ctx, const unsigned long long *keys_host, unsigned int nkeys, int w, int h, int mindist,
+                         int n_features, int overwrite, double *x, double *y, int32_t *val);
 
 // ---- klt_affine.cu -----------------------------------------------------------------------------------
 int klt_launch_affine(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const klt_pyr *p2, int n_per_image,

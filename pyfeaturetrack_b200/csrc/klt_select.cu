@@ -541,3 +541,57 @@ int klt_select_device(klt_ctx *ctx, const klt_params *p, const float *gx, const 
     if (n_consumed) *n_consumed = (int64_t)cons[0];
     return KLT_OK;
 }
+
+// _enforceMinimumDistance on a caller-provided, already ordered candidate list (selectGoodFeatures.py:45-135):
+// keys_host[i] = ~((val_bits << 26) | (x << 13) | y) in walk order.
+int klt_greedy_presorted(klt_ctx *ctx, const unsigned long long *keys_host, unsigned int nk, int w, int h, int mindist,
+                         int n_features, int overwrite, double *x, double *y, int32_t *val) {
+    if (w > 8191 || h > 8191) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "image larger than 8191 pixels per side");
+    if (mindist < 0) mindist = 0;
+    const int r = mindist - 1;
+    if (r > 254) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "mindist larger than 255");
+    const size_t keys_b = align_up(((size_t)nk + 1) * sizeof(unsigned long long), 256);
+    const size_t map_b = align_up((size_t)w * h, 256);
+    const size_t feat_b = align_up((size_t)n_features * (2 * sizeof(double) + sizeof(int)) + 64, 256);
+    const int cs = r >= 0 ? r + 1 : 1, gw = (w + cs - 1) / cs, gh = (h + cs - 1) / cs;
+    const size_t grid_b = align_up((size_t)gw * gh * sizeof(unsigned short), 256);
+    const bool grid_in_smem = grid_b <= 200 * 1024;
+    int rc = klt_ws_reserve(ctx, keys_b + map_b + feat_b + grid_b + 512);
+    if (rc) return rc;
+    char *wsp = (char *)ctx->ws;
+    unsigned long long *keys = (unsigned long long *)wsp; wsp += keys_b;
+    unsigned char *map = (unsigned char *)wsp; wsp += map_b;
+    double *fx = (double *)wsp; double *fy = fx + n_features; int *fval = (int *)(fy + n_features); wsp += feat_b;
+    unsigned short *grid_g = (unsigned short *)wsp; wsp += grid_b;
+    unsigned int *nkeys = (unsigned int *)wsp;
+    unsigned long long *consumed = (unsigned long long *)(wsp + 64);
+    KLT_CUDA(ctx, cudaMemsetAsync(nkeys, 0, 512, ctx->stream));
+    KLT_CUDA(ctx, cudaMemcpyAsync(nkeys, &nk, sizeof(nk), cudaMemcpyHostToDevice, ctx->stream));
+    if (nk) KLT_CUDA(ctx, cudaMemcpyAsync(keys, keys_host, (size_t)nk * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    if (!overwrite) {
+        KLT_CUDA(ctx, cudaMemcpyAsync(fx, x, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
+        KLT_CUDA(ctx, cudaMemcpyAsync(fy, y, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
+        KLT_CUDA(ctx, cudaMemcpyAsync(fval, val, n_features * sizeof(int), cudaMemcpyDefault, ctx->stream));
+        KLT_CUDA(ctx, cudaMemsetAsync(map, 0, (size_t)w * h, ctx->stream));
+        if (r >= 0 && n_features > 0)
+            KLT_LAUNCH(ctx, "premark", 0.0, (premark_kernel<<<n_features, 128, 0, ctx->stream>>>(fx, fy, fval, n_features, map, w, h, r)));
+    }
+    GreedyArgs G;
+    G.keys = keys; G.nkeys = nkeys; G.premap = overwrite ? nullptr : map; G.grid_global = grid_g; G.W = w; G.H = h; G.r = r;
+    G.n_features = n_features; G.overwrite = overwrite; G.cs = cs; G.gw = gw; G.gh = gh; G.grid_in_smem = grid_in_smem ? 1 : 0;
+    G.fx = fx; G.fy = fy; G.fval = fval; G.consumed = consumed;
+    if (grid_in_smem) KLT_CUDA(ctx, cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    KLT_LAUNCH(ctx, "greedy", 0.0, (greedy_kernel<<<1, 32, grid_in_smem ? grid_b : 0, ctx->stream>>>(G)));
+    unsigned long long cons[3] = {0, 0, 0};
+    KLT_CUDA(ctx, cudaMemcpyAsync(cons, consumed, sizeof(cons), cudaMemcpyDeviceToHost, ctx->stream));
+    KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (overwrite && cons[1] && (int)cons[2] < n_features) {
+        const int rest = n_features - (int)cons[2];
+        KLT_LAUNCH(ctx, "fill_not_found", 0.0, (fill_not_found_kernel<<<(rest + 127) / 128, 128, 0, ctx->stream>>>(fx, fy, fval, n_features, consumed)));
+    }
+    KLT_CUDA(ctx, cudaMemcpyAsync(x, fx, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    KLT_CUDA(ctx, cudaMemcpyAsync(y, fy, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    KLT_CUDA(ctx, cudaMemcpyAsync(val, fval, n_features * sizeof(int), cudaMemcpyDefault, ctx->stream));
+    KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KLT_OK;
+}

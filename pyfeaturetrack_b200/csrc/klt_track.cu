@@ -71,6 +71,57 @@ __device__ float np_pairwise_sum(const float *a, int n) {
     }
 }
 
+// trackFeatureIterateCKLT (trackFeaturesUtils.pyx:393-459) for one feature, executed by one warp with the reference's
+// exact float32 operation order.  T/Tgx/Tgy: the w*h template patches (shared memory), S: 5*w*h floats of scratch.
+__device__ __forceinline__ int iterate_exact(const float *T, const float *Tgx, const float *Tgy, float *S,
+                                             const float *__restrict__ I2, const float *__restrict__ GX2,
+                                             const float *__restrict__ GY2, int pitch, int nc, int nr, int w, int h,
+                                             float step_factor, float small_det, float th, int max_iterations, int lane,
+                                             float &x2, float &y2, int &iteration) {
+    const int n = w * h, hw = w / 2, hh = h / 2;
+    const float fhw = (float)hw, fhh = (float)hh, fnc = (float)nc, fnr = (float)nr;
+    int status = KLT_TRACKED;
+    while (true) {
+        if (__fsub_rn(x2, fhw) < 0.f || __fsub_rn(fnc, __fadd_rn(x2, fhw)) < 1.001f ||
+            __fsub_rn(y2, fhh) < 0.f || __fsub_rn(fnr, __fadd_rn(y2, fhh)) < 1.001f) { status = KLT_OOB; break; }
+        const int ix = (int)x2, iy = (int)y2;
+        const float ax = __double2float_rn(__dsub_rn((double)x2, (double)ix));
+        const float ay = __double2float_rn(__dsub_rn((double)y2, (double)iy));
+        for (int k = lane; k < n; k += 32) {
+            const int j = k / w, i = k - j * w;
+            const size_t o = (size_t)(iy + j - hh) * pitch + (ix + i - hw);
+            const float diff = __fsub_rn(T[k], bilerp_ref(I2 + o, pitch, ax, ay));       // pyx:61-88
+            const float gx = __fadd_rn(Tgx[k], bilerp_ref(GX2 + o, pitch, ax, ay));      // -jacobian[:,0], pyx:107-128
+            const float gy = __fadd_rn(Tgy[k], bilerp_ref(GY2 + o, pitch, ax, ay));
+            S[k] = __fmul_rn(gx, gx);
+            S[n + k] = __fmul_rn(gx, gy);
+            S[2 * n + k] = __fmul_rn(gy, gy);
+            S[3 * n + k] = __fmul_rn(diff, gx);
+            S[4 * n + k] = __fmul_rn(diff, gy);
+        }
+        __syncwarp();
+        float acc = 0.f;                      // lanes 0..4: one sequential float32 sum each (pyx:246-305)
+        if (lane < 5) {
+            const float *s = S + lane * n;
+#pragma unroll 7
+            for (int k = 0; k < n; k++) acc = __fadd_rn(acc, s[k]);
+        }
+        __syncwarp();
+        const float gxx = __shfl_sync(0xffffffffu, acc, 0), gxy = __shfl_sync(0xffffffffu, acc, 1),
+                    gyy = __shfl_sync(0xffffffffu, acc, 2);
+        const float ex = __fmul_rn(__shfl_sync(0xffffffffu, acc, 3), step_factor),
+                    ey = __fmul_rn(__shfl_sync(0xffffffffu, acc, 4), step_factor);
+        const float det = __fsub_rn(__fmul_rn(gxx, gyy), __fmul_rn(gxy, gxy));            // pyx:318-340
+        if (det < small_det) { status = KLT_SMALL_DET; break; }
+        const float dx = __fdiv_rn(__fsub_rn(__fmul_rn(gyy, ex), __fmul_rn(gxy, ey)), det);
+        const float dy = __fdiv_rn(__fsub_rn(__fmul_rn(gxx, ey), __fmul_rn(gxy, ex)), det);
+        x2 = __fadd_rn(x2, dx); y2 = __fadd_rn(y2, dy);
+        iteration++;
+        if (!((fabsf(dx) >= th || fabsf(dy) >= th) && iteration < max_iterations)) break;
+    }
+    return status;
+}
+
 // Shared memory per warp: T, Tgx, Tgy (templates) + 5 product arrays, each n = w*h floats.
 __global__ void __launch_bounds__(128)
 lk_track_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ xs, double *__restrict__ ys,
@@ -123,46 +174,10 @@ lk_track_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ xs, do
 
         // ---- trackFeatureIterateCKLT (pyx:393-459), float32 state ----
         float x2 = __double2float_rn(xout), y2 = __double2float_rn(yout);
-        int status = KLT_TRACKED, iteration = 0;
-        const float fhw = (float)hw, fhh = (float)hh, fnc = (float)nc, fnr = (float)nr;
-        while (true) {
-            if (__fsub_rn(x2, fhw) < 0.f || __fsub_rn(fnc, __fadd_rn(x2, fhw)) < 1.001f ||
-                __fsub_rn(y2, fhh) < 0.f || __fsub_rn(fnr, __fadd_rn(y2, fhh)) < 1.001f) { status = KLT_OOB; break; }
-            const int ix = (int)x2, iy = (int)y2;
-            const float ax = __double2float_rn(__dsub_rn((double)x2, (double)ix));
-            const float ay = __double2float_rn(__dsub_rn((double)y2, (double)iy));
-            for (int k = lane; k < n; k += 32) {
-                const int j = k / A.w, i = k - j * A.w;
-                const size_t o = (size_t)(iy + j - hh) * pitch + (ix + i - hw);
-                const float diff = __fsub_rn(T[k], bilerp_ref(I2 + o, pitch, ax, ay));       // pyx:61-88
-                const float gx = __fadd_rn(Tgx[k], bilerp_ref(GX2 + o, pitch, ax, ay));      // -jacobian[:,0], pyx:107-128
-                const float gy = __fadd_rn(Tgy[k], bilerp_ref(GY2 + o, pitch, ax, ay));
-                S[k] = __fmul_rn(gx, gx);
-                S[n + k] = __fmul_rn(gx, gy);
-                S[2 * n + k] = __fmul_rn(gy, gy);
-                S[3 * n + k] = __fmul_rn(diff, gx);
-                S[4 * n + k] = __fmul_rn(diff, gy);
-            }
-            __syncwarp();
-            float acc = 0.f;                      // lanes 0..4: one sequential float32 sum each (pyx:246-305)
-            if (lane < 5) {
-                const float *s = S + lane * n;
-#pragma unroll 7
-                for (int k = 0; k < n; k++) acc = __fadd_rn(acc, s[k]);
-            }
-            __syncwarp();
-            const float gxx = __shfl_sync(0xffffffffu, acc, 0), gxy = __shfl_sync(0xffffffffu, acc, 1),
-                        gyy = __shfl_sync(0xffffffffu, acc, 2);
-            const float ex = __fmul_rn(__shfl_sync(0xffffffffu, acc, 3), A.step_factor),
-                        ey = __fmul_rn(__shfl_sync(0xffffffffu, acc, 4), A.step_factor);
-            const float det = __fsub_rn(__fmul_rn(gxx, gyy), __fmul_rn(gxy, gxy));            // pyx:318-340
-            if (det < A.small_det) { status = KLT_SMALL_DET; break; }
-            const float dx = __fdiv_rn(__fsub_rn(__fmul_rn(gyy, ex), __fmul_rn(gxy, ey)), det);
-            const float dy = __fdiv_rn(__fsub_rn(__fmul_rn(gxx, ey), __fmul_rn(gxy, ex)), det);
-            x2 = __fadd_rn(x2, dx); y2 = __fadd_rn(y2, dy);
-            iteration++;
-            if (!((fabsf(dx) >= A.th || fabsf(dy) >= A.th) && iteration < A.max_iterations)) break;
-        }
+        int iteration = 0;
+        const int status0 = iterate_exact(T, Tgx, Tgy, S, I2, GX2, GY2, pitch, nc, nr, A.w, A.h, A.step_factor, A.small_det, A.th,
+                                          A.max_iterations, lane, x2, y2, iteration);
+        int status = status0;
         my_iters += iteration;
 
         // ---- back in _trackFeature (trackFeatures.py:108-136): doubles, hw = width/2 ----
@@ -427,6 +442,59 @@ __global__ void extract_patch_kernel(const float *__restrict__ img, int pitch, i
         const int j = k / width, i = k - j * width;
         out[k] = bilerp_ref(img + (size_t)(iy + j - hh) * pitch + (ix + i - hw), pitch, ax, ay);
     }
+}
+
+// Operator-level entry: trackFeaturesUtils.trackFeatureIterateCKLT on caller-provided template patches (one warp).
+__global__ void __launch_bounds__(32)
+lk_iterate_kernel(const float *__restrict__ tpatch /* [3][h*w]: img, gx, gy */, const float *__restrict__ img2,
+                  const float *__restrict__ gx2, const float *__restrict__ gy2, int pitch, int nc, int nr, int w, int h,
+                  float step_factor, float small_det, float th, int max_iterations, float x2, float y2, float *out /* x2,y2,status,iteration */) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x, n = w * h;
+    float *T = smem, *Tgx = T + n, *Tgy = T + 2 * n, *S = T + 3 * n;
+    for (int k = lane; k < 3 * n; k += 32) T[k] = tpatch[k];
+    __syncwarp();
+    int iteration = 0;
+    const int status = iterate_exact(T, Tgx, Tgy, S, img2, gx2, gy2, pitch, nc, nr, w, h, step_factor, small_det, th,
+                                     max_iterations, lane, x2, y2, iteration);
+    if (lane == 0) { out[0] = x2; out[1] = y2; out[2] = (float)status; out[3] = (float)iteration; }
+}
+
+int klt_launch_iterate(klt_ctx *ctx, const klt_params *p, const float *tpatch_dev, const float *img2, const float *gx2,
+                       const float *gy2, int w_img, int h_img, float x2, float y2, float *out_dev) {
+    const int n = p->window_width * p->window_height;
+    const size_t smem = (size_t)8 * n * sizeof(float);
+    if (smem > 200 * 1024) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "window too large");
+    KLT_CUDA(ctx, cudaFuncSetAttribute(lk_iterate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    KLT_LAUNCH(ctx, "lk_iterate", 0.0, (lk_iterate_kernel<<<1, 32, smem, ctx->stream>>>(tpatch_dev, img2, gx2, gy2, w_img, w_img, h_img,
+                                                                                      p->window_width, p->window_height, p->step_factor,
+                                                                                      p->min_determinant, p->min_displacement,
+                                                                                      p->max_iterations, x2, y2, out_dev)));
+    return KLT_OK;
+}
+
+// computeIntensityDifference (mode 0: p1 - patch(img2)) / computeGradientSum (mode 1: -p1 - patch(img2)), pyx:61-142
+__global__ void patch_combine_kernel(const float *__restrict__ p1, const float *__restrict__ img, int pitch, int nc, int nr,
+                                     float x, float y, int height, int width, int mode, float *__restrict__ out, int *__restrict__ ok) {
+    const int ix = (int)x, iy = (int)y, hw = width / 2, hh = height / 2;
+    if (!(ix - hw >= 0 && iy - hh >= 0 && ix + hw + 2 <= nc && iy + hh + 2 <= nr)) {
+        if (threadIdx.x == 0) *ok = 0;
+        return;
+    }
+    if (threadIdx.x == 0) *ok = 1;
+    const float ax = __double2float_rn(__dsub_rn((double)x, (double)ix));
+    const float ay = __double2float_rn(__dsub_rn((double)y, (double)iy));
+    for (int k = threadIdx.x; k < width * height; k += blockDim.x) {
+        const int j = k / width, i = k - j * width;
+        const float g2 = bilerp_ref(img + (size_t)(iy + j - hh) * pitch + (ix + i - hw), pitch, ax, ay);
+        out[k] = mode == 0 ? __fsub_rn(p1[k], g2) : __fsub_rn(-p1[k], g2);
+    }
+}
+
+int klt_launch_patch_combine(klt_ctx *ctx, const float *p1_dev, const float *img, int w, int h, float x, float y, int height,
+                             int width, int mode, float *out_dev, int *ok_dev) {
+    KLT_LAUNCH(ctx, "patch_combine", 0.0, (patch_combine_kernel<<<1, 128, 0, ctx->stream>>>(p1_dev, img, w, w, h, x, y, height, width, mode, out_dev, ok_dev)));
+    return KLT_OK;
 }
 
 int klt_launch_extract_patch(klt_ctx *ctx, const float *img, size_t pitch, int w, int h, float x, float y, int height,

@@ -107,6 +107,39 @@ def _select_on_device(tc, pyr, nFeatures, featurelist, overwriteAllFeatures):
     return featurelist
 
 
+def _enforceMinimumDistance(pointlist, featurelist, ncols, nrows, mindist, min_eigenvalue, overwriteAllFeatures):
+    """Greedy minimum-distance suppression over a caller-ordered list of (val, x, y) tuples (selectGoodFeatures.py:45-135),
+    on the GPU (klt_enforce_min_distance).  Mutates and returns featurelist."""
+    ctx = _capi.default_ctx()
+    n = len(featurelist)
+    x = np.full(n, -1.0)
+    y = np.full(n, -1.0)
+    val = np.full(n, kltState.KLT_NOT_FOUND, np.int32)
+    if not overwriteAllFeatures:
+        for i, feat in enumerate(featurelist):
+            x[i], y[i], val[i] = feat.x, feat.y, feat.val
+    old_val = val.copy()
+    pv = np.ascontiguousarray([p[0] for p in pointlist], np.float32)
+    px = np.ascontiguousarray([p[1] for p in pointlist], np.int32)
+    py = np.ascontiguousarray([p[2] for p in pointlist], np.int32)
+    ctx.check(_capi.lib().klt_enforce_min_distance(ctx.handle, len(pointlist), pv.ctypes.data, px.ctypes.data, py.ctypes.data,
+                                                  int(ncols), int(nrows), int(mindist), int(min_eigenvalue),
+                                                  1 if overwriteAllFeatures else 0, n, x.ctypes.data, y.ctypes.data,
+                                                  val.ctypes.data))
+    xi, yi = x.astype(np.int32), y.astype(np.int32)
+    for i, feat in enumerate(featurelist):
+        if overwriteAllFeatures:
+            if val[i] >= 0:
+                feat.x, feat.y, feat.val = xi[i], yi[i], int(val[i])
+            else:
+                feat.x, feat.y, feat.val = -1, -1, kltState.KLT_NOT_FOUND
+            _reset_affine(feat)
+        elif old_val[i] < 0 and val[i] >= 0:
+            feat.x, feat.y, feat.val = xi[i], yi[i], int(val[i])
+            _reset_affine(feat)
+    return featurelist
+
+
 def _selection_pyramid(tc, img):
     """float image -> (optional) smooth -> gradients, as a 1-level device pyramid (selectGoodFeatures.py:181-197)."""
     ctx = _capi.default_ctx()

@@ -420,3 +420,62 @@ def test_affine_large_config_E(gpu_ctx, oracle):
         both = (gv == 0) & (v == 0)
         assert both.mean() > 0.9
         assert np.array_equal(gx[both], x[both]) and np.array_equal(gy[both], y[both])
+
+
+# ---- operator-level shims of the reference's Cython modules ---------------------------------------------------------
+def test_operator_level_iterate_and_patch_ops(gpu_ctx, oracle, golden, img01):
+    import ctypes as C
+    from pyfeaturetrack_b200 import trackFeaturesUtils as tfu, klt
+    p = P(oracle, max_residue=10.0)
+    pyr1, pyr2 = oracle.image_pyramids(p, img01[0]), oracle.image_pyramids(p, img01[1])
+    tc = make_tc(max_residue=10.0)
+    x, y, v = oracle.select_good_features(p, img01[0], 30)
+    tp = oracle._track_params(p)
+    for f in range(30):
+        x1, y1 = float(x[f]), float(y[f])
+        T = tfu.extractImagePatchSlow(pyr1[0][0], x1, y1, 7, 7)
+        Tx = tfu.extractImagePatchSlow(pyr1[1][0], x1, y1, 7, 7)
+        Ty = tfu.extractImagePatchSlow(pyr1[2][0], x1, y1, 7, 7)
+        assert np.array_equal(T, oracle.extract_patch(pyr1[0][0], x1, y1, 7, 7))
+        got = tfu.trackFeatureIterateCKLT(x1, y1, Tx, Ty, T, pyr2[0][0], pyr2[1][0], pyr2[2][0], tc)
+        # oracle: one level, same start
+        x2, y2, it = C.c_double(x1), C.c_double(y1), C.c_int()
+        st = oracle.lib().orc_track_feature_level(x1, y1, C.byref(x2), C.byref(y2), oracle._f(pyr1[0][0]), oracle._f(pyr1[1][0]),
+                                                  oracle._f(pyr1[2][0]), oracle._f(pyr2[0][0]), oracle._f(pyr2[1][0]),
+                                                  oracle._f(pyr2[2][0]), 320, 240, C.byref(tp), C.byref(it))
+        assert got[3] == it.value
+        if got[2] == 0 and st in (0, -3, -5):      # the level wrapper adds the residue / max-iteration mapping on top
+            assert (got[0], got[1]) == (x2.value, y2.value)
+    # computeIntensityDifference / computeGradientSum
+    work = np.empty((7, 7), np.float32)
+    out = np.empty(49, np.float32)
+    tfu.computeIntensityDifference(T, pyr2[0][0], 100.25, 80.5, work, out)
+    want = (T - oracle.extract_patch(pyr2[0][0], 100.25, 80.5, 7, 7)).ravel()
+    assert np.array_equal(out, want)
+    jac = np.empty((49, 2), np.float32)
+    tfu.computeGradientSum(Tx, pyr2[1][0], 100.25, 80.5, work, jac, 0)
+    assert np.array_equal(jac[:, 0], (-Tx - oracle.extract_patch(pyr2[1][0], 100.25, 80.5, 7, 7)).ravel())
+
+
+def test_enforce_minimum_distance_shim(gpu_ctx, oracle, golden, reference):
+    """_enforceMinimumDistance on an explicit point list: the GPU shim against the reference's own Python function."""
+    from pyfeaturetrack_b200 import selectGoodFeatures as sgf, klt
+    rsgf, rklt = reference["selectGoodFeatures"], reference["klt"]
+    val = golden["A_scan_val"]
+    ys, xs = np.mgrid[30:210, 30:290]
+    pts = sorted(zip(val.ravel().tolist(), xs.ravel().astype(np.int32), ys.ravel().astype(np.int32)))
+    pts.reverse()
+    pts = pts[:20000]
+    for overwrite in (True, False):
+        a = [klt.KLT_Feature() for _ in range(60)]
+        b = [rklt.KLT_Feature() for _ in range(60)]
+        if not overwrite:
+            rng = np.random.default_rng(0)
+            for fa, fb in zip(a, b):
+                if rng.random() < 0.5:
+                    fa.x = fb.x = float(rng.uniform(40, 280)); fa.y = fb.y = float(rng.uniform(40, 200)); fa.val = fb.val = 0
+                else:
+                    fa.x = fb.x = -1.0; fa.y = fb.y = -1.0; fa.val = fb.val = -4
+        sgf._enforceMinimumDistance(pts, a, 320, 240, 10, 1, overwrite)
+        rsgf._enforceMinimumDistance(pts, b, 320, 240, 10, 1, overwrite)
+        assert [(float(f.x), float(f.y), int(f.val)) for f in a] == [(float(f.x), float(f.y), int(f.val)) for f in b]
