@@ -242,6 +242,30 @@ __device__ __forceinline__ void patch_col(const float *__restrict__ img, int pit
     for (int j = 0; j < W; j++) out[j] = fmaf(w11, b[j + 1], fmaf(w10, a[j + 1], fmaf(w01, b[j], w00 * a[j])));
 }
 
+// the three patches (image, gradx, grady) of one position: all 6*(W+1) loads are issued before the first use, so one
+// memory round trip covers the whole phase
+template <int W>
+__device__ __forceinline__ void patch_col3(const float *__restrict__ i0, const float *__restrict__ i1,
+                                           const float *__restrict__ i2, int pitch, int ix, int iy, int i, float w00,
+                                           float w01, float w10, float w11, float (&o0)[W], float (&o1)[W], float (&o2)[W]) {
+    const size_t off = (size_t)(iy - W / 2) * pitch + (ix - W / 2 + i);
+    const float *p0 = i0 + off, *p1 = i1 + off, *p2 = i2 + off;
+    float a0[W + 1], b0[W + 1], a1[W + 1], b1[W + 1], a2[W + 1], b2[W + 1];
+#pragma unroll
+    for (int j = 0; j < W + 1; j++) {
+        const size_t r = (size_t)j * pitch;
+        a0[j] = __ldg(p0 + r); b0[j] = __ldg(p0 + r + 1);
+        a1[j] = __ldg(p1 + r); b1[j] = __ldg(p1 + r + 1);
+        a2[j] = __ldg(p2 + r); b2[j] = __ldg(p2 + r + 1);
+    }
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+        o0[j] = fmaf(w11, b0[j + 1], fmaf(w10, a0[j + 1], fmaf(w01, b0[j], w00 * a0[j])));
+        o1[j] = fmaf(w11, b1[j + 1], fmaf(w10, a1[j + 1], fmaf(w01, b1[j], w00 * a1[j])));
+        o2[j] = fmaf(w11, b2[j + 1], fmaf(w10, a2[j + 1], fmaf(w01, b2[j], w00 * a2[j])));
+    }
+}
+
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
@@ -289,9 +313,7 @@ lk_track_rows_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ x
             if (alive && row_ok) {
                 const float ax = x1 - (float)ix, ay = y1 - (float)iy;
                 const float w11 = ax * ay, w01 = ax - w11, w10 = ay - w11, w00 = 1.f - ax - ay + w11;
-                patch_col<W>(I1, pitch, ix, iy, j, w00, w01, w10, w11, T);
-                patch_col<W>(GX1, pitch, ix, iy, j, w00, w01, w10, w11, Tgx);
-                patch_col<W>(GY1, pitch, ix, iy, j, w00, w01, w10, w11, Tgy);
+                patch_col3<W>(I1, GX1, GY1, pitch, ix, iy, j, w00, w01, w10, w11, T, Tgx, Tgy);
             } else {
 #pragma unroll
                 for (int i = 0; i < W; i++) { T[i] = 0.f; Tgx[i] = 0.f; Tgy[i] = 0.f; }
@@ -312,9 +334,7 @@ lk_track_rows_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ x
                 const float ax = x2 - (float)ix, ay = y2 - (float)iy;
                 const float w11 = ax * ay, w01 = ax - w11, w10 = ay - w11, w00 = 1.f - ax - ay + w11;
                 float P[W], Px[W], Py[W];
-                patch_col<W>(I2, pitch, ix, iy, j, w00, w01, w10, w11, P);
-                patch_col<W>(GX2, pitch, ix, iy, j, w00, w01, w10, w11, Px);
-                patch_col<W>(GY2, pitch, ix, iy, j, w00, w01, w10, w11, Py);
+                patch_col3<W>(I2, GX2, GY2, pitch, ix, iy, j, w00, w01, w10, w11, P, Px, Py);
 #pragma unroll
                 for (int i = 0; i < W; i++) {
                     const float diff = T[i] - P[i], gx = Tgx[i] + Px[i], gy = Tgy[i] + Py[i];
