@@ -296,6 +296,20 @@ class Context:
             p = self._pyr_cache[key] = Pyramid(self, w, h, n_levels, subsampling, batch)
         return p
 
+    def pinned_stage(self, shape, key):
+        """A reusable pinned uint8 staging buffer of the given shape (one per key, e.g. per scratch pyramid)."""
+        st = self.__dict__.setdefault("_stages", {})
+        buf = st.get(key)
+        if buf is None or buf.shape != tuple(shape):
+            if len(st) > 8:
+                st.clear()
+            buf = st[key] = self.pinned_array(tuple(shape), np.uint8)
+        return buf
+
+    def sync_stage(self, key):
+        """The previous upload from this staging buffer must have been consumed before it is overwritten."""
+        self.sync()
+
     def host_alloc(self, nbytes):
         p = C.c_void_p()
         rc = lib().klt_host_alloc(nbytes, C.byref(p))

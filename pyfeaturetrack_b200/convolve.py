@@ -26,8 +26,17 @@ cachegaussderiv = None
 cached_sigma_last = None
 
 
+_kernel_memo = {}
+
+
 def _computeKernels(sigma):
-    """Gaussian and derivative-of-Gaussian taps, tails cut at 1 % of the peak (convolve.py:27-93)."""
+    """Gaussian and derivative-of-Gaussian taps, tails cut at 1 % of the peak (convolve.py:27-93).
+    A pure function of sigma, so results are memoised; the reference's single-slot cache globals are still updated."""
+    global cachegauss, cachegaussderiv, cached_sigma_last
+    hit = _kernel_memo.get(sigma)
+    if hit is not None:
+        cachegauss, cachegaussderiv, cached_sigma_last = list(hit[0]), list(hit[1]), sigma
+        return cachegauss, cachegaussderiv
     maxKernelWidth = 71
     factor = 0.01
     assert sigma >= 0.0
@@ -64,7 +73,8 @@ def _computeKernels(sigma):
         den -= i * deriv[i + dhw]
     deriv = [v / den for v in deriv]
 
-    global cachegauss, cachegaussderiv, cached_sigma_last
+    if len(_kernel_memo) < 256:
+        _kernel_memo[sigma] = (tuple(gauss), tuple(deriv))
     cachegauss, cachegaussderiv, cached_sigma_last = gauss, deriv, sigma
     return gauss, deriv
 

@@ -53,7 +53,11 @@ def _build_pyramids(tc, img, pyr):
     taps = _taps_for_one_image(tc)
     prec = config.track_precision_code()
     if is_u8:
-        pyr.build_u8(a, taps, prec)
+        # stage through pinned memory: the upload becomes a true asynchronous DMA instead of a pageable copy
+        stage = pyr.ctx.pinned_stage(a.shape, id(pyr))
+        pyr.ctx.sync_stage(id(pyr))
+        np.copyto(stage, a)
+        pyr.build_u8(stage, taps, prec)
     else:
         pyr.build_f32(a, taps, prec, already_smoothed=False)
     return _PyramidSet(pyr)
@@ -91,17 +95,14 @@ def ComputeImagePyramids(tc, img1, img2):
 
 
 def _features_to_arrays(featurelist):
-    n = len(featurelist)
-    x = np.empty(n)
-    y = np.empty(n)
-    val = np.empty(n, np.int32)
-    for i, feat in enumerate(featurelist):
-        v = feat.val
-        val[i] = v
-        if v >= 0:
-            x[i], y[i] = feat.x, feat.y
-        else:
-            x[i] = y[i] = -1.0
+    val = np.array([f.val for f in featurelist], np.int32)
+    live = val >= 0
+    if live.all():
+        x = np.array([f.x for f in featurelist], np.float64)
+        y = np.array([f.y for f in featurelist], np.float64)
+    else:
+        x = np.array([f.x if f.val >= 0 else -1.0 for f in featurelist], np.float64)
+        y = np.array([f.y if f.val >= 0 else -1.0 for f in featurelist], np.float64)
     return x, y, val
 
 
