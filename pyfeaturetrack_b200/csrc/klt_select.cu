@@ -80,6 +80,79 @@ sat_rows_kernel(const float *__restrict__ gx, const float *__restrict__ gy, size
         __syncwarp();
     }
 }
+
+// Same algorithm for W % 32 == 0 and 16-byte aligned rows: 128-bit cp.async, 128-bit shared loads/stores (row stride 36
+// floats keeps every quarter-warp on distinct banks), fully unrolled so that only the 32-step float32 add chains are serial.
+#define SAT_S 36
+struct SatSmemV {
+    float in[SAT_NBUF][2][SAT_T][SAT_S];
+    float out[3][SAT_T][SAT_S];
+};
+__global__ void __launch_bounds__(32)
+sat_rows_vec_kernel(const float *__restrict__ gx, const float *__restrict__ gy, size_t pitch, int W, int H,
+                    float *__restrict__ sxx, float *__restrict__ sxy, float *__restrict__ syy) {
+    extern __shared__ __align__(16) unsigned char sat_raw[];
+    SatSmemV &sm = *reinterpret_cast<SatSmemV *>(sat_raw);
+    const int lane = threadIdx.x;
+    const int y0 = blockIdx.x * SAT_T;
+    const int nchunks = W / SAT_T;
+    const int q = lane & 7, r8 = lane >> 3;            // 16-byte chunk within a tile row, row within a group of 4
+    auto issue = [&](int chunk, int buf) {
+        const int x = chunk * SAT_T + 4 * q;
+#pragma unroll
+        for (int g = 0; g < SAT_T / 4; g++) {
+            const int i = 4 * g + r8;
+            const int y = min(y0 + i, H - 1);
+            __pipeline_memcpy_async(&sm.in[buf][0][i][4 * q], gx + (size_t)y * pitch + x, 16);
+            __pipeline_memcpy_async(&sm.in[buf][1][i][4 * q], gy + (size_t)y * pitch + x, 16);
+        }
+        __pipeline_commit();
+    };
+    float axx = 0.f, axy = 0.f, ayy = 0.f;
+    for (int c = 0; c < SAT_NBUF - 1; c++) {
+        if (c < nchunks) issue(c, c); else __pipeline_commit();
+    }
+    for (int c = 0; c < nchunks; c++) {
+        const int buf = c % SAT_NBUF;
+        if (c + SAT_NBUF - 1 < nchunks) issue(c + SAT_NBUF - 1, (c + SAT_NBUF - 1) % SAT_NBUF); else __pipeline_commit();
+        __pipeline_wait_prior(SAT_NBUF - 1);
+        __syncwarp();
+        float4 va[8], vb[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            va[k] = *reinterpret_cast<const float4 *>(&sm.in[buf][0][lane][4 * k]);
+            vb[k] = *reinterpret_cast<const float4 *>(&sm.in[buf][1][lane][4 * k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {          // lane = row: the sequential float32 chain of np.cumsum along x
+            float4 oxx, oxy, oyy;
+            axx = __fadd_rn(axx, __fmul_rn(va[k].x, va[k].x)); axy = __fadd_rn(axy, __fmul_rn(va[k].x, vb[k].x)); ayy = __fadd_rn(ayy, __fmul_rn(vb[k].x, vb[k].x));
+            oxx.x = axx; oxy.x = axy; oyy.x = ayy;
+            axx = __fadd_rn(axx, __fmul_rn(va[k].y, va[k].y)); axy = __fadd_rn(axy, __fmul_rn(va[k].y, vb[k].y)); ayy = __fadd_rn(ayy, __fmul_rn(vb[k].y, vb[k].y));
+            oxx.y = axx; oxy.y = axy; oyy.y = ayy;
+            axx = __fadd_rn(axx, __fmul_rn(va[k].z, va[k].z)); axy = __fadd_rn(axy, __fmul_rn(va[k].z, vb[k].z)); ayy = __fadd_rn(ayy, __fmul_rn(vb[k].z, vb[k].z));
+            oxx.z = axx; oxy.z = axy; oyy.z = ayy;
+            axx = __fadd_rn(axx, __fmul_rn(va[k].w, va[k].w)); axy = __fadd_rn(axy, __fmul_rn(va[k].w, vb[k].w)); ayy = __fadd_rn(ayy, __fmul_rn(vb[k].w, vb[k].w));
+            oxx.w = axx; oxy.w = axy; oyy.w = ayy;
+            *reinterpret_cast<float4 *>(&sm.out[0][lane][4 * k]) = oxx;
+            *reinterpret_cast<float4 *>(&sm.out[1][lane][4 * k]) = oxy;
+            *reinterpret_cast<float4 *>(&sm.out[2][lane][4 * k]) = oyy;
+        }
+        __syncwarp();
+        const int x = c * SAT_T + 4 * q;
+#pragma unroll
+        for (int g = 0; g < SAT_T / 4; g++) {
+            const int i = 4 * g + r8, y = y0 + i;
+            if (y < H) {
+                const size_t o = (size_t)y * W + x;
+                *reinterpret_cast<float4 *>(sxx + o) = *reinterpret_cast<const float4 *>(&sm.out[0][i][4 * q]);
+                *reinterpret_cast<float4 *>(sxy + o) = *reinterpret_cast<const float4 *>(&sm.out[1][i][4 * q]);
+                *reinterpret_cast<float4 *>(syy + o) = *reinterpret_cast<const float4 *>(&sm.out[2][i][4 * q]);
+            }
+        }
+        __syncwarp();
+    }
+}
 // columns: s[y][x] = s[y-1][x] + s[y][x]; blockIdx.y selects the table
 __global__ void __launch_bounds__(64)
 sat_cols_kernel(float *__restrict__ s0, float *__restrict__ s1, float *__restrict__ s2, int W, int H) {
@@ -321,80 +394,133 @@ premark_kernel(const double *__restrict__ fx, const double *__restrict__ fy, con
     }
 }
 
-__global__ void __launch_bounds__(32)
+#define GREEDY_THREADS 1024
+// is candidate (x, y) within Chebyshev distance r of a feature registered in the 3x3 cell neighbourhood?
+__device__ __forceinline__ bool grid_conflict(const unsigned short *grid, int gw, int gh, int cs, int r, int x, int y) {
+    const int cx = x / cs, cy = y / cs;
+    bool hit = false;
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) {
+            const int ncx = cx + dx, ncy = cy + dy;
+            if (ncx >= 0 && ncx < gw && ncy >= 0 && ncy < gh) {
+                const unsigned int g = grid[ncy * gw + ncx];
+                if (g != 0xFFFFu) {
+                    const int fx = ncx * cs + (int)(g >> 8), fy = ncy * cs + (int)(g & 255u);
+                    hit |= abs(fx - x) <= r && abs(fy - y) <= r;
+                }
+            }
+        }
+    return hit;
+}
+
+// One CTA.  Candidates are taken 1024 at a time: (1) all 32 warps test their candidate against the features accepted in
+// EARLIER super-batches (most candidates die here) and compact the survivors, in order, into shared memory; (2) warp 0
+// walks the survivors 32 at a time exactly like the sequential reference loop: re-test against the grid (features
+// accepted earlier in this super-batch), then accept live candidates one by one in rank order, each accept killing the
+// later candidates of the batch within distance r.
+__global__ void __launch_bounds__(GREEDY_THREADS)
 greedy_kernel(const __grid_constant__ GreedyArgs A) {
     extern __shared__ unsigned short grid_smem[];
-    const int lane = threadIdx.x;
+    __shared__ unsigned long long surv_key[GREEDY_THREADS];
+    __shared__ unsigned int surv_idx[GREEDY_THREADS];
+    __shared__ unsigned int warp_cnt[32];
+    __shared__ int s_indx, s_full, s_nsurv;
+    __shared__ unsigned long long s_consumed;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int n = *A.nkeys;
     unsigned short *grid = A.grid_in_smem ? grid_smem : A.grid_global;
-    const int ncell = A.gw * A.gh;
-    if (A.r >= 0) {
-        for (int c = lane; c < ncell; c += 32) grid[c] = 0xFFFFu;
-        __syncwarp();
+    if (A.r >= 0)
+        for (int c = tid; c < A.gw * A.gh; c += GREEDY_THREADS) grid[c] = 0xFFFFu;
+    if (tid == 0) {
+        int indx = 0;
+        if (!A.overwrite) while (indx < A.n_features && A.fval[indx] >= 0) indx++;
+        s_indx = indx; s_full = indx >= A.n_features; s_consumed = 0ull;
     }
-    int indx = 0;
-    if (!A.overwrite) while (indx < A.n_features && A.fval[indx] >= 0) indx++;
-    unsigned long long pi = 0;
-    bool full = indx >= A.n_features;
-    // prefetch: key and pre-mark of the first batch
-    unsigned long long kn = lane < n ? ~A.keys[lane] : 0ull;
-    unsigned char pn = 0;
-    if (A.premap && lane < n) pn = A.premap[(size_t)(kn & 8191ull) * A.W + ((kn >> 13) & 8191ull)];
-    // the reference reads one more candidate before noticing that every slot is taken (:96-112)
-    while (pi < n && !full) {
-        const unsigned long long k = kn;
-        const bool valid = pi + lane < n;
-        const unsigned char pre = pn;
-        {   // prefetch the next batch (independent of what gets accepted in this one)
-            const unsigned long long i2 = pi + 32 + lane;
-            kn = i2 < n ? ~A.keys[i2] : 0ull;
-            pn = 0;
-            if (A.premap && i2 < n) pn = A.premap[(size_t)(kn & 8191ull) * A.W + ((kn >> 13) & 8191ull)];
+    __syncthreads();
+    for (unsigned long long base = 0; base < n && !s_full; base += GREEDY_THREADS) {
+        // ---- phase 1: parallel test against earlier super-batches, ordered compaction of the survivors ----
+        const unsigned long long i = base + tid;
+        bool live = i < n;
+        unsigned long long k = 0ull;
+        if (live) {
+            k = ~A.keys[i];
+            const int x = (int)((k >> 13) & 8191ull), y = (int)(k & 8191ull);
+            if (A.premap && A.premap[(size_t)y * A.W + x]) live = false;
+            if (live && A.r >= 0 && grid_conflict(grid, A.gw, A.gh, A.cs, A.r, x, y)) live = false;
         }
-        const int x = (int)((k >> 13) & 8191ull), y = (int)(k & 8191ull);
-        const float val = __uint_as_float((unsigned int)(k >> 26));
-        bool live = valid && pre == 0;
-        if (live && A.r >= 0) {
-            const int cx = x / A.cs, cy = y / A.cs;
+        const unsigned int m = __ballot_sync(0xffffffffu, live);
+        if (lane == 0) warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        if (warp == 0) {
+            unsigned int c = warp_cnt[lane], incl = c;
 #pragma unroll
-            for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-                for (int dx = -1; dx <= 1; dx++) {
-                    const int ncx = cx + dx, ncy = cy + dy;
-                    if (ncx >= 0 && ncx < A.gw && ncy >= 0 && ncy < A.gh) {
-                        const unsigned int g = grid[ncy * A.gw + ncx];
-                        if (g != 0xFFFFu) {
-                            const int fx = ncx * A.cs + (int)(g >> 8), fy = ncy * A.cs + (int)(g & 255u);
-                            if (abs(fx - x) <= A.r && abs(fy - y) <= A.r) live = false;
-                        }
+            for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            warp_cnt[lane] = incl - c;
+            if (lane == 31) s_nsurv = (int)incl;
+        }
+        __syncthreads();
+        if (live) {
+            const unsigned int pos = warp_cnt[warp] + __popc(m & ((1u << lane) - 1u));
+            surv_key[pos] = k; surv_idx[pos] = (unsigned int)(i - base);
+        }
+        __syncthreads();
+        // ---- phase 2: warp 0 walks the survivors in rank order ----
+        if (warp == 0) {
+            int indx = s_indx;
+            bool full = false;
+            unsigned int last_off = 0;
+            const int ns = s_nsurv;
+            for (int b0 = 0; b0 < ns && !full; b0 += 32) {
+                const bool valid = b0 + lane < ns;
+                const unsigned long long kk = valid ? surv_key[b0 + lane] : 0ull;
+                const unsigned int off = valid ? surv_idx[b0 + lane] : 0u;
+                const int x = (int)((kk >> 13) & 8191ull), y = (int)(kk & 8191ull);
+                const float val = __uint_as_float((unsigned int)(kk >> 26));
+                bool lv = valid;
+                if (lv && A.r >= 0 && grid_conflict(grid, A.gw, A.gh, A.cs, A.r, x, y)) lv = false;
+                // cell index and in-cell offsets once per candidate (all lanes in parallel), not once per accept
+                const int cx = x / A.cs, cy = y / A.cs;
+                const int cell = cy * A.gw + cx;
+                const unsigned int ofs = (unsigned int)(((x - cx * A.cs) << 8) | (y - cy * A.cs));
+                unsigned int mm;
+                while ((mm = __ballot_sync(0xffffffffu, lv)) != 0u) {
+                    const int leader = __ffs(mm) - 1;
+                    const int lx = __shfl_sync(0xffffffffu, x, leader), ly = __shfl_sync(0xffffffffu, y, leader);
+                    const float lval = __shfl_sync(0xffffffffu, val, leader);
+                    const int lcell = __shfl_sync(0xffffffffu, cell, leader);
+                    const unsigned int lofs = __shfl_sync(0xffffffffu, ofs, leader);
+                    last_off = __shfl_sync(0xffffffffu, off, leader);
+                    if (lane == 0) {
+                        A.fx[indx] = (double)lx; A.fy[indx] = (double)ly; A.fval[indx] = (int)lval;
+                        if (A.r >= 0) grid[lcell] = (unsigned short)lofs;
                     }
+                    if (lane == leader || (abs(x - lx) <= A.r && abs(y - ly) <= A.r)) lv = false;
+                    indx++;
+                    if (!A.overwrite) while (indx < A.n_features && A.fval[indx] >= 0) indx++;
+                    if (indx >= A.n_features) { full = true; break; }
                 }
-        }
-        unsigned int m;
-        int last = -1;
-        while ((m = __ballot_sync(0xffffffffu, live)) != 0u) {
-            const int leader = __ffs(m) - 1;
-            const int lx = __shfl_sync(0xffffffffu, x, leader), ly = __shfl_sync(0xffffffffu, y, leader);
-            const float lval = __shfl_sync(0xffffffffu, val, leader);
-            if (lane == 0) {
-                A.fx[indx] = (double)lx; A.fy[indx] = (double)ly; A.fval[indx] = (int)lval;
-                if (A.r >= 0) grid[(ly / A.cs) * A.gw + lx / A.cs] = (unsigned short)(((lx % A.cs) << 8) | (ly % A.cs));
+                __syncwarp();
             }
-            if (lane == leader || (abs(x - lx) <= A.r && abs(y - ly) <= A.r)) live = false;
-            indx++;
-            if (!A.overwrite) while (indx < A.n_features && A.fval[indx] >= 0) indx++;
-            last = leader;
-            if (indx >= A.n_features) { full = true; break; }
+            if (lane == 0) {
+                s_indx = indx;
+                if (full) {
+                    // the reference reads one more candidate before noticing that every slot is taken (:96-112)
+                    unsigned long long c = base + last_off + 1;
+                    if (c < n) c += 1;
+                    s_consumed = c; s_full = 1;
+                } else {
+                    s_consumed = base + GREEDY_THREADS < n ? base + GREEDY_THREADS : (unsigned long long)n;
+                }
+            }
         }
-        __syncwarp();
-        if (full) { pi += (unsigned long long)last + 1; if (pi < n) pi += 1; }
-        else pi += 32;
+        __syncthreads();
     }
-    if (pi > n) pi = n;
-    if (lane == 0) {
-        A.consumed[0] = pi;
-        A.consumed[1] = full ? 0ull : 1ull;
-        A.consumed[2] = (unsigned long long)indx;
+    if (tid == 0) {
+        A.consumed[0] = s_consumed;
+        A.consumed[1] = s_full ? 0ull : 1ull;
+        A.consumed[2] = (unsigned long long)s_indx;
     }
 }
 
@@ -408,6 +534,11 @@ __global__ void fill_not_found_kernel(double *fx, double *fy, int *fval, int n, 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static int launch_sat(klt_ctx *ctx, const float *gx, const float *gy, size_t pitch, int w, int h, float *sxx, float *sxy, float *syy) {
+    const bool vec = (w % SAT_T) == 0 && (pitch % 4) == 0 && ((reinterpret_cast<uintptr_t>(gx) | reinterpret_cast<uintptr_t>(gy)) & 15) == 0;
+    if (vec) {
+        KLT_CUDA(ctx, cudaFuncSetAttribute(sat_rows_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SatSmemV)));
+        KLT_LAUNCH(ctx, "sat_rows", 20.0 * w * h, (sat_rows_vec_kernel<<<(h + SAT_T - 1) / SAT_T, 32, sizeof(SatSmemV), ctx->stream>>>(gx, gy, pitch, w, h, sxx, sxy, syy)));
+    } else
     KLT_LAUNCH(ctx, "sat_rows", 20.0 * w * h, (sat_rows_kernel<<<(h + SAT_T - 1) / SAT_T, 32, 0, ctx->stream>>>(gx, gy, pitch, w, h, sxx, sxy, syy)));
     KLT_LAUNCH(ctx, "sat_cols", 24.0 * w * h, (sat_cols_kernel<<<dim3((w + 63) / 64, 3), 64, 0, ctx->stream>>>(sxx, sxy, syy, w, h)));
     return KLT_OK;
@@ -456,7 +587,7 @@ int klt_select_device(klt_ctx *ctx, const klt_params *p, const float *gx, const 
     const size_t feat_b = align_up((size_t)n_features * (2 * sizeof(double) + sizeof(int)) + 64, 256);
     const int cs = r >= 0 ? r + 1 : 1, gw = (w + cs - 1) / cs, gh = (h + cs - 1) / cs;
     const size_t grid_b = align_up((size_t)gw * gh * sizeof(unsigned short), 256);
-    const bool grid_in_smem = grid_b <= 200 * 1024;
+    const bool grid_in_smem = grid_b <= 180 * 1024;
     const size_t total = 3 * plane + val_b + 2 * keys_b + hist_b + map_b + feat_b + grid_b + EIG_BINS * 4 + 512;
     int rc = klt_ws_reserve(ctx, total);
     if (rc) return rc;
@@ -492,7 +623,7 @@ int klt_select_device(klt_ctx *ctx, const klt_params *p, const float *gx, const 
     G.nkeys = nkeys; G.premap = replace ? map : nullptr; G.grid_global = grid_g; G.W = w; G.H = h; G.r = r;
     G.n_features = n_features; G.overwrite = replace ? 0 : 1; G.cs = cs; G.gw = gw; G.gh = gh; G.grid_in_smem = grid_in_smem ? 1 : 0;
     G.fx = fx; G.fy = fy; G.fval = fval; G.consumed = consumed;
-    if (grid_in_smem) KLT_CUDA(ctx, cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (grid_in_smem) KLT_CUDA(ctx, cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_b));
     unsigned long long cons[3] = {0, 0, 0};
     const unsigned int target = (unsigned int)(32u * (unsigned int)n_features + 8192u);
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -524,7 +655,7 @@ int klt_select_device(klt_ctx *ctx, const klt_params *p, const float *gx, const 
             KLT_CUDA(ctx, cudaMemcpyAsync(fy, y, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
         }
         G.keys = src;
-        KLT_LAUNCH(ctx, "greedy", 0.0, (greedy_kernel<<<1, 32, grid_in_smem ? grid_b : 0, ctx->stream>>>(G)));
+        KLT_LAUNCH(ctx, "greedy", 0.0, (greedy_kernel<<<1, GREEDY_THREADS, grid_in_smem ? grid_b : 0, ctx->stream>>>(G)));
         KLT_CUDA(ctx, cudaMemcpyAsync(cons, consumed, sizeof(cons), cudaMemcpyDeviceToHost, ctx->stream));
         KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         const bool thresholded = hk[1] > 0;
@@ -555,7 +686,7 @@ int klt_greedy_presorted(klt_ctx *ctx, const unsigned long long *keys_host, unsi
     const size_t feat_b = align_up((size_t)n_features * (2 * sizeof(double) + sizeof(int)) + 64, 256);
     const int cs = r >= 0 ? r + 1 : 1, gw = (w + cs - 1) / cs, gh = (h + cs - 1) / cs;
     const size_t grid_b = align_up((size_t)gw * gh * sizeof(unsigned short), 256);
-    const bool grid_in_smem = grid_b <= 200 * 1024;
+    const bool grid_in_smem = grid_b <= 180 * 1024;
     int rc = klt_ws_reserve(ctx, keys_b + map_b + feat_b + grid_b + 512);
     if (rc) return rc;
     char *wsp = (char *)ctx->ws;
@@ -580,8 +711,8 @@ int klt_greedy_presorted(klt_ctx *ctx, const unsigned long long *keys_host, unsi
     G.keys = keys; G.nkeys = nkeys; G.premap = overwrite ? nullptr : map; G.grid_global = grid_g; G.W = w; G.H = h; G.r = r;
     G.n_features = n_features; G.overwrite = overwrite; G.cs = cs; G.gw = gw; G.gh = gh; G.grid_in_smem = grid_in_smem ? 1 : 0;
     G.fx = fx; G.fy = fy; G.fval = fval; G.consumed = consumed;
-    if (grid_in_smem) KLT_CUDA(ctx, cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    KLT_LAUNCH(ctx, "greedy", 0.0, (greedy_kernel<<<1, 32, grid_in_smem ? grid_b : 0, ctx->stream>>>(G)));
+    if (grid_in_smem) KLT_CUDA(ctx, cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_b));
+    KLT_LAUNCH(ctx, "greedy", 0.0, (greedy_kernel<<<1, GREEDY_THREADS, grid_in_smem ? grid_b : 0, ctx->stream>>>(G)));
     unsigned long long cons[3] = {0, 0, 0};
     KLT_CUDA(ctx, cudaMemcpyAsync(cons, consumed, sizeof(cons), cudaMemcpyDeviceToHost, ctx->stream));
     KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

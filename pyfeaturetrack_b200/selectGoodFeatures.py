@@ -65,16 +65,13 @@ def make_params(tc):
     return p
 
 
+_AFFINE_RESET = dict(aff_img=None, aff_img_gradx=None, aff_img_grady=None, aff_x=-1.0, aff_y=-1.0, aff_Axx=1.0,
+                     aff_Ayx=0.0, aff_Axy=0.0, aff_Ayy=1.0)
+
+
 def _reset_affine(feat):
-    feat.aff_img = None
-    feat.aff_img_gradx = None
-    feat.aff_img_grady = None
-    feat.aff_x = -1.0
-    feat.aff_y = -1.0
-    feat.aff_Axx = 1.0
-    feat.aff_Ayx = 0.0
-    feat.aff_Axy = 0.0
-    feat.aff_Ayy = 1.0
+    """selectGoodFeatures.py:120-128"""
+    feat.__dict__.update(_AFFINE_RESET)
 
 
 def _select_on_device(tc, pyr, nFeatures, featurelist, overwriteAllFeatures):

@@ -479,3 +479,33 @@ def test_enforce_minimum_distance_shim(gpu_ctx, oracle, golden, reference):
         sgf._enforceMinimumDistance(pts, a, 320, 240, 10, 1, overwrite)
         rsgf._enforceMinimumDistance(pts, b, 320, 240, 10, 1, overwrite)
         assert [(float(f.x), float(f.y), int(f.val)) for f in a] == [(float(f.x), float(f.y), int(f.val)) for f in b]
+
+
+def test_config_D_sequence_with_replacement(gpu_ctx, oracle):
+    """Config D shape (shortened): one 1080p sequence in sequentialMode, per frame KLTTrackFeatures(prev, cur) then
+    KLTReplaceLostFeatures; STRICT pyramids => bit-identical to the oracle frame after frame."""
+    from pyfeaturetrack_b200 import synth, selectGoodFeatures as sgf, trackFeatures as tf, config
+    config.set_precision(track="strict")
+    nfr = 5
+    shifts = [(s[0] * 6, s[1] * 6) for s in synth.sequence_shifts(nfr)]      # ~7 px/frame so that features get lost
+    frames = synth.frames(1080, 1920, shifts, seed=101)
+    kw = dict(nPyramidLevels=3, subsampling=2, max_residue=10.0, sequentialMode=True)
+    p = P(oracle, **kw)
+    tc = make_tc(**kw)
+    n = 1000
+    x, y, v = oracle.select_good_features(p, frames[0], n)
+    f = sgf.KLTSelectGoodFeatures(tc, frames[0], n)
+    assert_features_equal(fl_arrays(f), (x, y, v))
+    state = {}
+    lost_total = 0
+    for k in range(1, nfr):
+        x, y, v, _ = oracle.track_features(p, frames[k - 1], frames[k], x, y, v, state)
+        tf.KLTTrackFeatures(tc, frames[k - 1], frames[k], f)
+        assert_features_equal(fl_arrays(f), (x, y, v))
+        lost_total += int((v < 0).sum())
+        _, gxs, gys = state["pyramid_last"]
+        x, y, v, _ = oracle.select_from_gradients(p, gxs[0], gys[0], n, existing=(x, y, v))
+        sgf.KLTReplaceLostFeatures(tc, frames[k], f)
+        assert_features_equal(fl_arrays(f), (x, y, v))
+        assert (v >= 0).all()
+    assert lost_total > 0
