@@ -352,6 +352,7 @@ def run_b200(args):
     if world == 1 and args.api_pairs > 0:
         out["api_single_pair"] = api_single_pair(wl, distinct, klt, sgf, trackFeatures, args.api_pairs)
         out["select"] = select_timing(wl, distinct, klt, sgf, ctx, args.api_pairs)
+        out["sequence_api"] = sequence_timing(wl, klt, sgf, trackFeatures, max(6, args.api_pairs))
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -376,6 +377,31 @@ def api_single_pair(wl, distinct, klt, sgf, tf, reps):
             tracked = sum(1 for f in fl if f.val == 0)
     return {"call": "KLTTrackFeatures(tc, img1, img2, fl) with PIL images", "ms_per_pair": round(1e3 * float(np.mean(ts)), 3),
             "frame_pairs_per_sec": round(1.0 / float(np.mean(ts)), 1), "tracked_features_per_sec": round(tracked / float(np.mean(ts)), 1)}
+
+
+def sequence_timing(wl, klt, sgf, tf, nframes):
+    """Config D shape, one sequence through the drop-in API: sequentialMode, per frame KLTTrackFeatures(prev, cur) then
+    KLTReplaceLostFeatures (one pyramid build per frame, selection on the device-resident gradients)."""
+    from pyfeaturetrack_b200 import synth
+    frames = synth.fast_frames(wl["H"], wl["W"], nframes + 1, seed=7)
+    tc = tc_for(wl, klt)
+    tc.sequentialMode = True
+    fl = sgf.KLTSelectGoodFeatures(tc, frames[0], wl["n"])
+    tf.KLTTrackFeatures(tc, frames[0], frames[1], fl)          # warm-up: allocates the two ping-pong pyramids
+    sgf.KLTReplaceLostFeatures(tc, frames[1], fl)
+    t_track = t_repl = 0.0
+    for k in range(2, nframes + 1):
+        t0 = time.perf_counter()
+        tf.KLTTrackFeatures(tc, frames[k - 1], frames[k], fl)
+        t1 = time.perf_counter()
+        sgf.KLTReplaceLostFeatures(tc, frames[k], fl)
+        t2 = time.perf_counter()
+        t_track += t1 - t0
+        t_repl += t2 - t1
+    m = nframes - 1
+    return {"call": "sequentialMode: KLTTrackFeatures + KLTReplaceLostFeatures per frame (drop-in API, one sequence)",
+            "ms_track_per_frame": round(1e3 * t_track / m, 3), "ms_replace_per_frame": round(1e3 * t_repl / m, 3),
+            "frames_per_sec": round(m / (t_track + t_repl), 1)}
 
 
 def select_timing(wl, distinct, klt, sgf, ctx, reps):
