@@ -156,8 +156,8 @@ __device__ __forceinline__ void l0_row(L0State<RS> &S, const StreamTaps &T, int 
     grad_row(S.gs, T, s, gx, gy);                        // completes gradient row q = r - 3
     if (LEAN || r - 3 >= S.ys) {                         // q < ye by construction
         if (S.writer) {
-            *reinterpret_cast<float4 *>(S.p_gx) = gx;
-            *reinterpret_cast<float4 *>(S.p_gy) = gy;
+            __stcs(reinterpret_cast<float4 *>(S.p_gx), gx);      // gradients are not re-read by the build: stream them
+            __stcs(reinterpret_cast<float4 *>(S.p_gy), gy);      // past L2 so that the smoothed image stays resident
         }
         S.p_gx += S.opitch;
         S.p_gy += S.opitch;
@@ -242,8 +242,8 @@ stream_grad_kernel(const float *__restrict__ in, int in_pitch, size_t in_stride,
         grad_row(gs, T, s, gx, gy);
         if (t - 3 >= ys) {
             if (writer) {
-                *reinterpret_cast<float4 *>(p_gx) = gx;
-                *reinterpret_cast<float4 *>(p_gy) = gy;
+                __stcs(reinterpret_cast<float4 *>(p_gx), gx);
+                __stcs(reinterpret_cast<float4 *>(p_gy), gy);
             }
             p_gx += out_pitch;
             p_gy += out_pitch;
@@ -438,7 +438,7 @@ int klt_stream_grad(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps, i
     if (a.w < 16 || a.h < 8 || (a.w & 3) || !aligned16(p->level(0, first, level)) || (p->plane_floats & 3)) return 0;
     const int n_strips = (a.w + 119) / 120;
     const int strip_ctas = (n_strips + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    const int rows = pick_rows_per_seg(ctx, stream_grad_kernel, a.h, strip_ctas, count, 24);
+    const int rows = pick_rows_per_seg(ctx, stream_grad_kernel, a.h, strip_ctas, count, 8);
     dim3 grid(strip_ctas, (a.h + rows - 1) / rows, count), block(WARPS_PER_CTA * 32);
     const double bytes = 12.0 * a.w * a.h * count;
     KLT_LAUNCH(ctx, "stream_grad", bytes,
@@ -459,7 +459,7 @@ int klt_stream_down2(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps, 
     if (!aligned16(p->level(0, first, level - 1)) || !aligned16(p->level(0, first, level)) || (p->plane_floats & 3)) return 0;
     const int n_strips = (b.w + 119) / 120;
     const int strip_ctas = (n_strips + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    const int rows = pick_rows_per_seg(ctx, stream_down2_kernel, b.h, strip_ctas, count, 24);
+    const int rows = pick_rows_per_seg(ctx, stream_down2_kernel, b.h, strip_ctas, count, 8);
     dim3 grid(strip_ctas, (b.h + rows - 1) / rows, count), block(WARPS_PER_CTA * 32);
     const double bytes = 4.0 * ((double)a.w * a.h + (double)b.w * b.h) * count;
     KLT_LAUNCH(ctx, "stream_down2", bytes,
