@@ -158,3 +158,21 @@ def test_shard_range_partitions():
             assert got == list(range(n))
             sizes = [len(shard_range(n, r, world)) for r in range(world)]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_write_feature_list_roundtrip(tmp_path, img01):
+    from pyfeaturetrack_b200 import klt, writeFeatures as wf, selectGoodFeatures as sgf
+    sgf.KLT_verbose = 0
+    fl = []
+    for i in range(5):
+        f = klt.KLT_Feature(); f.x, f.y, f.val = 10.5 + i, 20.25 + 2 * i, (0 if i % 2 == 0 else -4)
+        fl.append(f)
+    wf.KLTWriteFeatureList(fl, str(tmp_path / "fl.bin"), None)
+    back = wf.KLTReadFeatureList(str(tmp_path / "fl.bin"))
+    assert [(f.x, f.y, f.val) for f in back] == [(f.x, f.y, f.val) for f in fl]
+    wf.KLTWriteFeatureList(fl, str(tmp_path / "fl.txt"), "%5.1f")
+    assert "( 10.5, 20.2)=0" in open(str(tmp_path / "fl.txt")).read() or "( 10.5, 20.3)=0" in open(str(tmp_path / "fl.txt")).read()
+    wf.KLTWriteFeatureListToPPM(fl, img01[0], str(tmp_path / "f.ppm"))
+    from PIL import Image
+    rgb = np.array(Image.open(str(tmp_path / "f.ppm")))
+    assert tuple(rgb[20, 11]) == (255, 0, 0) and tuple(rgb[22, 12]) != (255, 0, 0)     # feature 0 drawn, feature 1 (lost) not
