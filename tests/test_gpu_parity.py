@@ -509,3 +509,85 @@ def test_config_D_sequence_with_replacement(gpu_ctx, oracle):
         assert_features_equal(fl_arrays(f), (x, y, v))
         assert (v >= 0).all()
     assert lost_total > 0
+
+
+# ---- more shapes: every window size the FAST kernel is instantiated for, several pyramid geometries, odd image sizes ----
+@pytest.mark.parametrize("win,L,ss,shape", [(3, 2, 2, (200, 264)), (5, 3, 2, (240, 320)), (9, 2, 4, (241, 323)), (11, 1, 2, (180, 256)),
+                                            (13, 2, 2, (256, 384)), (7, 2, 8, (360, 488)), (17, 2, 2, (300, 400)), (7, 4, 2, (480, 640))])
+def test_tracking_window_and_pyramid_variants(gpu_ctx, oracle, win, L, ss, shape):
+    from pyfeaturetrack_b200 import selectGoodFeatures as sgf, trackFeatures as tf, config
+    imgs = _synth(30 + win + L, shape, shift=(1.2, -1.9))
+    kw = dict(window_width=win, window_height=win, nPyramidLevels=L, subsampling=ss, max_residue=12.0)
+    p = P(oracle, **kw)
+    tc = make_tc(**kw)
+    assert p.borderx == tc.borderx
+    n = 80
+    want_sel = oracle.select_good_features(p, imgs[0], n)
+    want_trk = oracle.track_features(p, imgs[0], imgs[1], *want_sel)[:3]
+    for mode in ("strict", "fast"):
+        config.set_precision(track=mode)
+        f = sgf.KLTSelectGoodFeatures(tc, imgs[0], n)
+        assert_features_equal(fl_arrays(f), want_sel)
+        tf.KLTTrackFeatures(tc, imgs[0], imgs[1], f)
+        if mode == "strict":
+            assert_features_equal(fl_arrays(f), want_trk)
+        else:
+            got = fl_arrays(f)
+            assert np.mean(got[2] == want_trk[2]) >= 0.97          # 80 features: allow two threshold flips
+            both = (got[2] == 0) & (want_trk[2] == 0)
+            assert np.abs(got[0][both] - want_trk[0][both]).max() <= POS_TOL
+            assert np.abs(got[1][both] - want_trk[1][both]).max() <= POS_TOL
+
+
+def test_random_feature_positions_and_dead_features(gpu_ctx, oracle):
+    """Features the caller made up (fractional positions, some dead, some near the border): statuses follow the oracle."""
+    from pyfeaturetrack_b200 import klt, trackFeatures as tf, config
+    imgs = _synth(41, (300, 400), shift=(2.5, 3.5))
+    kw = dict(nPyramidLevels=2, subsampling=2, max_residue=8.0)
+    p = P(oracle, **kw)
+    tc = make_tc(**kw)
+    rng = np.random.default_rng(9)
+    n = 400
+    x = rng.uniform(16, 400 - 17, n).astype(np.float32).astype(np.float64)
+    y = rng.uniform(16, 300 - 17, n).astype(np.float32).astype(np.float64)
+    v = np.where(rng.random(n) < 0.2, rng.integers(-5, 0, n), rng.integers(0, 500, n)).astype(np.int32)
+    want = oracle.track_features(p, imgs[0], imgs[1], x, y, v)[:3]
+    for mode in ("strict", "fast"):
+        config.set_precision(track=mode)
+        fl_ = []
+        for i in range(n):
+            f = klt.KLT_Feature(); f.x, f.y, f.val = float(x[i]), float(y[i]), int(v[i])
+            fl_.append(f)
+        tf.KLTTrackFeatures(tc, imgs[0], imgs[1], fl_)
+        got = fl_arrays(fl_)
+        dead = v < 0
+        assert np.array_equal(got[2][dead], v[dead]) and np.array_equal(got[0][dead], x[dead])     # untouched
+        if mode == "strict":
+            assert_features_equal(got, want)
+        else:
+            assert_features_close(got, want)
+    assert len(set(want[2].tolist())) >= 3
+    # empty list and an all-dead list are no-ops
+    tf.KLTTrackFeatures(tc, imgs[0], imgs[1], [])
+    f = klt.KLT_Feature(); f.x, f.y, f.val = -1.0, -1.0, -4
+    tf.KLTTrackFeatures(tc, imgs[0], imgs[1], [f])
+    assert (f.x, f.y, f.val) == (-1.0, -1.0, -4)
+
+
+def test_selection_edge_cases(gpu_ctx, oracle):
+    from pyfeaturetrack_b200 import selectGoodFeatures as sgf
+    imgs = _synth(42, (160, 200))
+    # more features requested than can exist at this mindist: the rest is KLT_NOT_FOUND (-1)
+    kw = dict(mindist=25)
+    p = P(oracle, **kw)
+    tc = make_tc(**kw)
+    want = oracle.select_good_features(p, imgs[0], 200)
+    f = sgf.KLTSelectGoodFeatures(tc, imgs[0], 200)
+    assert_features_equal(fl_arrays(f), want)
+    assert (want[2] == -1).any() and (want[2] > 0).any()
+    # mindist 0 / 1: no suppression; min_eigenvalue high: few features
+    for kw in (dict(mindist=0), dict(mindist=1), dict(min_eigenvalue=4000), dict(nSkippedPixels=3, mindist=4)):
+        p = P(oracle, **kw)
+        tc = make_tc(**kw)
+        assert_features_equal(fl_arrays(sgf.KLTSelectGoodFeatures(tc, imgs[0], 60)), oracle.select_good_features(p, imgs[0], 60))
+    assert sgf.KLTSelectGoodFeatures(make_tc(), imgs[0], 0) == []
