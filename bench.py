@@ -310,17 +310,30 @@ def run_b200(args):
                              "bytes_per_launch": r["bytes"] / r["launches"]}
     total_kernel_ms = sum(r["ms"] for r in prof.values())
     dom = max(prof.items(), key=lambda kv: kv[1]["ms"])[0] if prof else None
+    # LK: algorithmic bytes follow from the measured iteration count (3 patches per template / iteration)
+    lk_name = [k for k in kernels if k.startswith("lk_track")]
+    bytes_pair, bytes_frame, bytes_lk = algorithmic_bytes_per_pair(wl, it.value / B)
+    for k in lk_name:
+        kernels[k]["bytes_per_launch"] = bytes_lk * B
+        kernels[k]["gbps"] = bytes_lk * B / (kernels[k]["ms_per_launch"] * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:   # DRAM traffic of the dominant kernel from the committed ncu capture (per frame, scaled to this launch)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+        if dom in tj["per_frame_bytes"]:
+            traffic = tj["per_frame_bytes"][dom] * B
+            traffic_src = tj["source"]
+    except Exception:
+        pass
     roof = None
     if dom and prof[dom]["bytes"]:
         r = prof[dom]
         ach = (r["bytes"] / r["launches"]) / (r["ms"] / r["launches"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(ach / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "share_of_step": round(r["ms"] / total_kernel_ms, 3),
                 "bytes_per_launch": r["bytes"] / r["launches"], "ms_per_launch": r["ms"] / r["launches"]}
     step_s = dev_ms * 1e-3 / args.steps
     e2e_s = e2e_ms * 1e-3 / e2e_steps
-    bytes_pair, bytes_frame, bytes_lk = algorithmic_bytes_per_pair(wl, it.value / B)
     out = {
         "metric": "tracked_features_per_sec", "value": round(tracked_all / step_s, 1), "unit": "tracked features/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 4),

@@ -95,14 +95,14 @@ def ComputeImagePyramids(tc, img1, img2):
 
 
 def _features_to_arrays(featurelist):
-    val = np.array([f.val for f in featurelist], np.int32)
-    live = val >= 0
-    if live.all():
-        x = np.array([f.x for f in featurelist], np.float64)
-        y = np.array([f.y for f in featurelist], np.float64)
+    n = len(featurelist)
+    val = np.fromiter((f.val for f in featurelist), np.int32, n)
+    if n and val.min() >= 0:
+        x = np.fromiter((f.x for f in featurelist), np.float64, n)
+        y = np.fromiter((f.y for f in featurelist), np.float64, n)
     else:
-        x = np.array([f.x if f.val >= 0 else -1.0 for f in featurelist], np.float64)
-        y = np.array([f.y if f.val >= 0 else -1.0 for f in featurelist], np.float64)
+        x = np.fromiter((f.x if f.val >= 0 else -1.0 for f in featurelist), np.float64, n)
+        y = np.fromiter((f.y if f.val >= 0 else -1.0 for f in featurelist), np.float64, n)
     return x, y, val
 
 
@@ -174,15 +174,15 @@ def KLTTrackFeatures(tc, img1, img2, featurelist):
         ctx.check(_capi.lib().klt_track_features(ctx.handle, C.byref(params), pyramid1.pyr.handle, pyramid2.pyr.handle,
                                                 len(featurelist), x.ctypes.data, y.ctypes.data, val.ctypes.data, None))
     xs, ys, vals = x.tolist(), y.tolist(), val.tolist()
-    for i, feat in enumerate(featurelist):
-        if not was_live[i]:
+    for feat, live, fx, fy, v in zip(featurelist, was_live.tolist(), xs, ys, vals):
+        if not live:
             continue                                             # trackFeatures.py:253
-        v = vals[i]
-        if v == kltState.KLT_TRACKED:
-            feat.x, feat.y, feat.val = xs[i], ys[i], kltState.KLT_TRACKED
+        d = feat.__dict__
+        if v == 0:                                               # KLT_TRACKED
+            d["x"] = fx; d["y"] = fy; d["val"] = 0
         else:
-            feat.x, feat.y, feat.val = -1.0, -1.0, v
-            if hasattr(feat, "aff_img"):
+            d["x"] = -1.0; d["y"] = -1.0; d["val"] = v
+            if "aff_img" in d:
                 _clear_affine(feat)
 
     if use_affine:
