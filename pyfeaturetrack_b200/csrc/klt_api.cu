@@ -35,15 +35,6 @@ int klt_ws_reserve(klt_ctx *ctx, size_t bytes) {
     return KLT_OK;
 }
 
-int klt_pinned_reserve(klt_ctx *ctx, size_t bytes) {
-    if (bytes <= ctx->pinned_bytes) return KLT_OK;
-    if (ctx->pinned) { KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); KLT_CUDA(ctx, cudaFreeHost(ctx->pinned)); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
-    cudaError_t e = cudaMallocHost(&ctx->pinned, bytes);
-    if (e != cudaSuccess) return klt_fail(ctx, KLT_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
-    ctx->pinned_bytes = bytes;
-    return KLT_OK;
-}
-
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int klt_prof_begin(klt_ctx *ctx, const char *name, double bytes) {
@@ -125,7 +116,7 @@ int klt_ctx_create(int device, void *stream, klt_ctx **out) {
     ctx->device = device;
     ctx->profiling = false;
     ctx->launches = 0;
-    ctx->ws = nullptr; ctx->ws_bytes = 0; ctx->pinned = nullptr; ctx->pinned_bytes = 0;
+    ctx->ws = nullptr; ctx->ws_bytes = 0;
     ctx->own_stream = stream == nullptr;
     if (stream) ctx->stream = (cudaStream_t)stream;
     else if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -162,7 +153,6 @@ int klt_ctx_destroy(klt_ctx *ctx) {
     cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->chunk_ev[i]);
     cudaEventDestroy(ctx->compute_done);
-    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -443,7 +433,7 @@ int klt_scan_good_features(klt_ctx *ctx, const float *gradx, const float *grady,
         dgy = d;
     }
     if ((rc = klt_launch_scan(ctx, dgx, dgy, w, w, h, borderx, bordery, window_hw, window_hh, n_skipped_pixels, dval, nx, ny))) return rc;
-    if ((size_t)nx * ny)
+    if (nx > 0 && ny > 0)
         KLT_CUDA(ctx, cudaMemcpyAsync(val, dval, (size_t)nx * ny * sizeof(float), cudaMemcpyDefault, ctx->stream));
     KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KLT_OK;

@@ -7,8 +7,6 @@
 
 #include "../../include/klt_b200.h"
 
-#define KLT_NUM_SMS_B200 148
-
 // Kernel taps passed BY VALUE as a kernel parameter (constant bank): no global state, no symbol copies.
 // c[j] is the tap that multiplies in[x + j - r]  (convolution: c[j] = taps[n-1-j]).
 struct TapsF {
@@ -76,9 +74,6 @@ struct klt_ctx {
     // grow-only device workspace
     void *ws;
     size_t ws_bytes;
-    // small pinned staging area
-    void *pinned;
-    size_t pinned_bytes;
     int num_sms;
 };
 
@@ -107,7 +102,6 @@ void klt_prof_end(klt_ctx *ctx, int token);
     } while (0)
 
 int klt_ws_reserve(klt_ctx *ctx, size_t bytes);          // grow-only workspace
-int klt_pinned_reserve(klt_ctx *ctx, size_t bytes);
 bool klt_is_device_ptr(const void *p);
 
 int klt_make_taps(klt_ctx *ctx, const klt_kernel1d *k, TapsF *f, TapsD *d);
