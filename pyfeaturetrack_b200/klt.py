@@ -33,61 +33,46 @@ def _fix_window(tc, who):
         KLTWarning("({0}) Window height must be at least three.  \nChanging to {1}.\n".format(who, tc.window_height))
 
 
+# field -> default (klt.py:45-73 of the reference; documented there at :200-246)
+_TC_DEFAULTS = (
+    ("mindist", 10), ("window_width", 7), ("window_height", 7),
+    ("sequentialMode", False), ("retainTrackers", False), ("smoothBeforeSelecting", True),
+    ("writeInternalImages", False), ("lighting_insensitive", False),
+    ("min_eigenvalue", 1), ("min_determinant", 0.01), ("max_iterations", 10), ("min_displacement", 0.1),
+    ("max_residue", None),                       # None switches the residue check off (quirk Q4)
+    ("grad_sigma", 1.0), ("smooth_sigma_fact", 0.1), ("pyramid_sigma_fact", 0.9), ("step_factor", 1.0),
+    ("nSkippedPixels", 0),
+    ("pyramid_last", None), ("pyramid_last_gradx", None), ("pyramid_last_grady", None),
+    # affine consistency check
+    ("affineConsistencyCheck", -1), ("affine_window_width", 15), ("affine_window_height", 15),
+    ("affine_max_iterations", 10), ("affine_max_residue", 10.), ("affine_min_displacement", 0.02),
+    ("affine_max_displacement_differ", 1.5),
+)
+# search_range / window_halfwidth <= bound  ->  (nPyramidLevels, subsampling)   (klt.py:105-117)
+_PYRAMID_STEPS = ((3.0, 2, 2), (5.0, 2, 4), (9.0, 2, 8))
+
+
 class KLT_TrackingContext:
     def __init__(self):
-        self.mindist = 10
-        self.window_width = 7
-        self.window_height = 7
-        self.sequentialMode = False
-        self.retainTrackers = False
-        self.smoothBeforeSelecting = True
-        self.writeInternalImages = False
-        self.lighting_insensitive = False
-        self.min_eigenvalue = 1
-        self.min_determinant = 0.01
-        self.max_iterations = 10
-        self.min_displacement = 0.1
-        self.max_residue = None
-        self.grad_sigma = 1.0
-        self.smooth_sigma_fact = 0.1
-        self.pyramid_sigma_fact = 0.9
-        self.step_factor = 1.0
-        self.nSkippedPixels = 0
-        self.pyramid_last = None
-        self.pyramid_last_gradx = None
-        self.pyramid_last_grady = None
-        # affine consistency check
-        self.affineConsistencyCheck = -1
-        self.affine_window_width = 15
-        self.affine_window_height = 15
-        self.affine_max_iterations = 10
-        self.affine_max_residue = 10.
-        self.affine_min_displacement = 0.02
-        self.affine_max_displacement_differ = 1.5
-
-        self.KLTChangeTCPyramid(15)
+        for name, value in _TC_DEFAULTS:
+            setattr(self, name, value)
+        self.KLTChangeTCPyramid(15)          # klt.py:76-77: search range 15 -> 2 levels, subsampling 4 for 7x7
         self.KLTUpdateTCBorder()
 
     def KLTChangeTCPyramid(self, search_range):
         """Pyramid depth / subsampling heuristic (klt.py:84-128)."""
         _fix_window(self, "KLTChangeTCPyramid")
-        window_halfwidth = min(self.window_width, self.window_height) / 2.0
-        subsampling = float(search_range) / window_halfwidth
-        if subsampling < 1.0:
+        ratio = float(search_range) / (min(self.window_width, self.window_height) / 2.0)
+        if ratio < 1.0:
             self.nPyramidLevels = 1          # subsampling keeps its previous value (quirk Q12)
-        elif subsampling <= 3.0:
-            self.nPyramidLevels = 2
-            self.subsampling = 2
-        elif subsampling <= 5.0:
-            self.nPyramidLevels = 2
-            self.subsampling = 4
-        elif subsampling <= 9.0:
-            self.nPyramidLevels = 2
-            self.subsampling = 8
-        else:
-            val = float(math.log(7.0 * subsampling + 1.0) / math.log(8.0))
-            self.nPyramidLevels = int(val + 0.99)
-            self.subsampling = 8
+            return
+        for bound, levels, ss in _PYRAMID_STEPS:
+            if ratio <= bound:
+                self.nPyramidLevels, self.subsampling = levels, ss
+                return
+        # search_range = halfwidth * (8^levels - 1) / 7, rounded up
+        self.nPyramidLevels = int(float(math.log(7.0 * ratio + 1.0) / math.log(8.0)) + 0.99)
+        self.subsampling = 8
 
     def KLTUpdateTCBorder(self):
         """Border lost to convolution and windows (klt.py:137-189)."""
