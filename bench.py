@@ -132,6 +132,9 @@ def run_b200(args):
     import torch.distributed as dist
     rank, world, local = dist_env()
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from pyfeaturetrack_b200 import _capi, klt, trackFeatures, selectGoodFeatures as sgf, config
