@@ -36,6 +36,8 @@ WORKLOADS = {
               ss=2, win=7, max_residue=10.0),
     "E": dict(name="E (translational part): synthetic 1080p frame pairs, 1000 features, 3 levels, ss=2, 15x15 windows", H=1080,
               W=1920, n=1000, L=3, ss=2, win=15, max_residue=10.0),
+    "B4": dict(name="B4: as B but with the reference's DEFAULT pyramid (2 levels, subsampling 4)", H=1080, W=1920, n=1000, L=2,
+               ss=4, win=7, max_residue=10.0),
     "A": dict(name="A: 320x240 synthetic stand-in for example1.py, 100 features, default context", H=240, W=320, n=100,
               L=2, ss=4, win=7, max_residue=10.0),
 }

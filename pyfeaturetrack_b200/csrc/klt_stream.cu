@@ -353,6 +353,107 @@ stream_down2_kernel(const float *__restrict__ in, int in_pitch, size_t in_stride
     }
 }
 
+// ---- pyramid step for subsampling SS with a (2R+1)-tap gauss, generic form of the kernel above ------------------------
+// (used for SS = 4, R = 10: the reference's DEFAULT pyramid, sigma = 0.9 * 4 -> 21 taps).
+// Lane owns 4 output columns = 4*SS input columns [ci, ci + 4*SS); it needs NL = R - SS/2 more on the left and
+// NR = NL + 1 on the right, all of which the adjacent lanes own.  Input rows r = SS*j + ph update the pending outputs
+// Y = j + m with tap index ph - SS*m - SS/2 + R; output Y = j + m_min completes at phase 0 of period j.
+template <int R> struct DownTaps { float c[2 * R + 1]; };
+
+template <int SS, int R>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
+stream_down_kernel(const float *__restrict__ in, int in_pitch, size_t in_stride, int W, int H, float *__restrict__ out,
+                   int out_pitch, size_t out_stride, int OW, int OH, int rows_per_seg, int n_strips,
+                   const __grid_constant__ DownTaps<R> T) {
+    static_assert(SS % 2 == 0 && (R + SS / 2) % SS == 0, "the completing tap must fall on phase 0");
+    constexpr int NQ = SS;                       // own quads per input row
+    constexpr int NL = R - SS / 2, NR = NL + 1;
+    static_assert(NL >= 0 && NR <= 4 * SS, "neighbour columns must come from the adjacent lanes");
+    constexpr int M_MAX = (R - SS / 2) / SS, M_MIN = -((R + SS / 2) / SS);
+    constexpr int NP = M_MAX - M_MIN;            // outputs pending between periods
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x * WARPS_PER_CTA + warp;
+    if (strip >= n_strips) return;
+    const int ys = blockIdx.y * rows_per_seg, ye = min(OH, ys + rows_per_seg);
+    const int X = strip * 120 + 4 * (lane - 1);
+    const int ci = SS * X;
+    const float *src = in + (size_t)blockIdx.z * in_stride;
+    int mq[NQ];
+    bool rvq[NQ], any_rev = false;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) { mq[q] = mirror_quad(ci + 4 * q, W, rvq[q]); any_rev |= rvq[q]; }
+    const bool warp_rev = __any_sync(FULLMASK, any_rev);
+    const bool writer = lane >= 1 && lane <= 30 && X < OW;
+    float *p_out = out + (size_t)blockIdx.z * out_stride + (size_t)ys * out_pitch + X;
+    float Q[4][NP];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int m = 0; m < NP; m++) Q[i][m] = 0.f;
+
+    const int j0 = ys - M_MAX, j1 = ye - M_MIN;          // periods; period j completes output Y = j + M_MIN
+    const int r_last = SS * j1 - 1;
+    float4 bufA[NQ], bufB[NQ];
+    auto load_row = [&](int r, float4 (&b)[NQ]) {
+        const float *row = src + (size_t)reflect1(min(r, r_last), H) * in_pitch;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) b[q] = __ldg(reinterpret_cast<const float4 *>(row + mq[q]));
+    };
+    // horizontal (2R+1)-tap filter at the 4 sampled columns of one buffered row
+    auto hrow = [&](const float4 (&b)[NQ], float (&h)[4]) {
+        float e[NL + 4 * SS + NR];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            float4 v = b[q];
+            if (warp_rev && rvq[q]) v = make_float4(v.w, v.z, v.y, v.x);
+            e[NL + 4 * q] = v.x; e[NL + 4 * q + 1] = v.y; e[NL + 4 * q + 2] = v.z; e[NL + 4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int k = 0; k < NL; k++) e[k] = __shfl_up_sync(FULLMASK, e[NL + 4 * SS - NL + k], 1);
+#pragma unroll
+        for (int k = 0; k < NR; k++) e[NL + 4 * SS + k] = __shfl_down_sync(FULLMASK, e[NL + k], 1);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float acc = T.c[0] * e[SS * i];
+#pragma unroll
+            for (int t = 1; t < 2 * R + 1; t++) acc = fmaf(T.c[t], e[SS * i + t], acc);
+            h[i] = acc;
+        }
+    };
+    load_row(SS * j0, bufA);
+    load_row(SS * j0 + 1, bufB);
+    for (int j = j0; j < j1; j++) {
+#pragma unroll
+        for (int ph = 0; ph < SS; ph++) {
+            const int r = SS * j + ph;
+            float h[4];
+            if (ph & 1) { hrow(bufB, h); load_row(r + 2, bufB); }
+            else { hrow(bufA, h); load_row(r + 2, bufA); }
+            if (ph == 0) {
+                if (j + 2 < j1) prefetch_l2(src + (size_t)reflect1(min(r + 2 * SS, r_last), H) * in_pitch + mq[0]);
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    o[i] = fmaf(T.c[-SS * M_MIN - SS / 2 + R], h[i], Q[i][0]);
+#pragma unroll
+                    for (int k = 0; k < NP - 1; k++) Q[i][k] = fmaf(T.c[-SS * (M_MIN + 1 + k) - SS / 2 + R], h[i], Q[i][k + 1]);
+                    Q[i][NP - 1] = T.c[-SS * M_MAX - SS / 2 + R] * h[i];
+                }
+                const int Y = j + M_MIN;
+                if (Y >= ys) {                           // Y < ye by construction
+                    if (writer) *reinterpret_cast<float4 *>(p_out) = make_float4(o[0], o[1], o[2], o[3]);
+                    p_out += out_pitch;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int k = 0; k < NP; k++) Q[i][k] = fmaf(T.c[ph - SS * (M_MIN + 1 + k) - SS / 2 + R], h[i], Q[i][k]);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Segment height: fill the GPU with (at most) ONE wave of resident CTAs, so that equal-sized segments finish together
 // and the warm-up rows (2*(radius) per segment) stay a small fraction of the work.
@@ -448,8 +549,33 @@ int klt_stream_grad(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps, i
     return 1;
 }
 
+static int stream_down4(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps, int first, int count) {
+    constexpr int R = 10;
+    DownTaps<R> T;
+    const klt_kernel1d *k = &taps->pyramid;
+    if (k->n > 2 * R + 1 || !(k->n & 1)) return 0;
+    const int pad = (2 * R + 1 - k->n) / 2;
+    for (int j = 0; j < 2 * R + 1; j++) T.c[j] = 0.f;
+    for (int j = 0; j < k->n; j++) T.c[pad + j] = (float)k->taps[k->n - 1 - j];
+    const LevelDesc &a = p->lv[level - 1], &b = p->lv[level];
+    if (b.w < 8 || b.h < 8 || a.w < 64 || a.h < 32 || (a.w & 3) || (b.w & 3)) return 0;
+    if (!aligned16(p->level(0, first, level - 1)) || !aligned16(p->level(0, first, level)) || (p->plane_floats & 3)) return 0;
+    const int n_strips = (b.w + 119) / 120;
+    const int strip_ctas = (n_strips + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int rows = pick_rows_per_seg(ctx, stream_down_kernel<4, R>, b.h, strip_ctas, count, 8);
+    dim3 grid(strip_ctas, (b.h + rows - 1) / rows, count), block(WARPS_PER_CTA * 32);
+    const double bytes = 4.0 * ((double)a.w * a.h + (double)b.w * b.h) * count;
+    KLT_LAUNCH(ctx, "stream_down4", bytes,
+               (stream_down_kernel<4, R><<<grid, block, 0, ctx->stream>>>(p->level(0, first, level - 1), a.pitch, p->plane_floats,
+                                                                          a.w, a.h, p->level(0, first, level), b.pitch,
+                                                                          p->plane_floats, b.w, b.h, rows, n_strips, T)));
+    return 1;
+}
+
 int klt_stream_down2(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps, int first, int count) {
-    if (p->ss != 2 || level < 1) return 0;
+    if (level < 1) return 0;
+    if (p->ss == 4) return stream_down4(ctx, p, level, taps, first, count);
+    if (p->ss != 2) return 0;
     StreamTaps T;
     if (taps->pyramid.n > 11 || !fill_taps(&taps->pyramid, T.p, 11)) return 0;
     for (int j = 0; j < 9; j++) T.s[j] = 0.f;
