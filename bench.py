@@ -371,6 +371,7 @@ def run_b200(args):
         out["api_single_pair"] = api_single_pair(wl, distinct, klt, sgf, trackFeatures, args.api_pairs)
         out["select"] = select_timing(wl, distinct, klt, sgf, ctx, args.api_pairs)
         out["sequence_api"] = sequence_timing(wl, klt, sgf, trackFeatures, max(6, args.api_pairs))
+        out["sequence_api_affine"] = sequence_timing(wl, klt, sgf, trackFeatures, max(6, args.api_pairs), affine=2)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -397,13 +398,14 @@ def api_single_pair(wl, distinct, klt, sgf, tf, reps):
             "frame_pairs_per_sec": round(1.0 / float(np.mean(ts)), 1), "tracked_features_per_sec": round(tracked / float(np.mean(ts)), 1)}
 
 
-def sequence_timing(wl, klt, sgf, tf, nframes):
+def sequence_timing(wl, klt, sgf, tf, nframes, affine=-1):
     """Config D shape, one sequence through the drop-in API: sequentialMode, per frame KLTTrackFeatures(prev, cur) then
     KLTReplaceLostFeatures (one pyramid build per frame, selection on the device-resident gradients)."""
     from pyfeaturetrack_b200 import synth
     frames = synth.fast_frames(wl["H"], wl["W"], nframes + 1, seed=7)
     tc = tc_for(wl, klt)
     tc.sequentialMode = True
+    tc.affineConsistencyCheck = affine                        # config E: 15x15 affine windows, 6x6 solve per feature
     fl = sgf.KLTSelectGoodFeatures(tc, frames[0], wl["n"])
     tf.KLTTrackFeatures(tc, frames[0], frames[1], fl)          # warm-up: allocates the two ping-pong pyramids
     sgf.KLTReplaceLostFeatures(tc, frames[1], fl)
@@ -417,7 +419,9 @@ def sequence_timing(wl, klt, sgf, tf, nframes):
         t_track += t1 - t0
         t_repl += t2 - t1
     m = nframes - 1
-    return {"call": "sequentialMode: KLTTrackFeatures + KLTReplaceLostFeatures per frame (drop-in API, one sequence)",
+    return {"call": "sequentialMode%s: KLTTrackFeatures + KLTReplaceLostFeatures per frame (drop-in API, one sequence)" %
+                    ("" if affine < 0 else ", affineConsistencyCheck=%d" % affine),
+            "tracked_at_end": sum(1 for f in fl if f.val >= 0),
             "ms_track_per_frame": round(1e3 * t_track / m, 3), "ms_replace_per_frame": round(1e3 * t_repl / m, 3),
             "frames_per_sec": round(m / (t_track + t_repl), 1)}
 
