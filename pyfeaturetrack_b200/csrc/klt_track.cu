@@ -230,33 +230,45 @@ lk_track_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ xs, do
 // per source row), keeps its column of the three templates in registers, accumulates the five window sums over its
 // column with FMAs, and the G lanes of a feature combine them with log2(G) shuffle steps.
 // ---------------------------------------------------------------------------------------------------------------------
+// Lane i of a feature's lane group owns window COLUMN i and lane W the extra right-hand column: each lane loads ONE value
+// per source row (the group reads W+1 consecutive addresses: coalesced) and takes the right-hand neighbour of the
+// bilinear footprint from the next lane by shuffle, which halves the L1 wavefronts of the naive 4-tap gather.  Every
+// lane of the warp must call these (the shuffles are warp-wide); `ld` says whether this lane really loads.
 template <int W>
-__device__ __forceinline__ void patch_col(const float *__restrict__ img, int pitch, int ix, int iy, int i, float w00,
-                                          float w01, float w10, float w11, float (&out)[W]) {
-    // lane i owns window COLUMN i: the lanes of a feature read consecutive addresses of each source row (coalesced)
-    const float *p = img + (size_t)(iy - W / 2) * pitch + (ix - W / 2 + i);
+__device__ __forceinline__ void patch_col(const float *__restrict__ img, int pitch, int ix, int iy, int i, bool ld,
+                                          float w00, float w01, float w10, float w11, float (&out)[W]) {
+    const float *p = img + (ld ? (size_t)(iy - W / 2) * pitch + (ix - W / 2 + i) : 0);
     float a[W + 1], b[W + 1];
 #pragma unroll
-    for (int j = 0; j < W + 1; j++) { a[j] = __ldg(p + (size_t)j * pitch); b[j] = __ldg(p + (size_t)j * pitch + 1); }
+    for (int j = 0; j < W + 1; j++) a[j] = ld ? __ldg(p + (size_t)j * pitch) : 0.f;
+#pragma unroll
+    for (int j = 0; j < W + 1; j++) b[j] = __shfl_down_sync(0xffffffffu, a[j], 1);
 #pragma unroll
     for (int j = 0; j < W; j++) out[j] = fmaf(w11, b[j + 1], fmaf(w10, a[j + 1], fmaf(w01, b[j], w00 * a[j])));
 }
 
-// the three patches (image, gradx, grady) of one position: all 6*(W+1) loads are issued before the first use, so one
+// the three patches (image, gradx, grady) of one position: all 3*(W+1) loads are issued before the first use, so one
 // memory round trip covers the whole phase
 template <int W>
 __device__ __forceinline__ void patch_col3(const float *__restrict__ i0, const float *__restrict__ i1,
-                                           const float *__restrict__ i2, int pitch, int ix, int iy, int i, float w00,
-                                           float w01, float w10, float w11, float (&o0)[W], float (&o1)[W], float (&o2)[W]) {
-    const size_t off = (size_t)(iy - W / 2) * pitch + (ix - W / 2 + i);
+                                           const float *__restrict__ i2, int pitch, int ix, int iy, int i, bool ld,
+                                           float w00, float w01, float w10, float w11, float (&o0)[W], float (&o1)[W],
+                                           float (&o2)[W]) {
+    const size_t off = ld ? (size_t)(iy - W / 2) * pitch + (ix - W / 2 + i) : 0;
     const float *p0 = i0 + off, *p1 = i1 + off, *p2 = i2 + off;
     float a0[W + 1], b0[W + 1], a1[W + 1], b1[W + 1], a2[W + 1], b2[W + 1];
 #pragma unroll
     for (int j = 0; j < W + 1; j++) {
         const size_t r = (size_t)j * pitch;
-        a0[j] = __ldg(p0 + r); b0[j] = __ldg(p0 + r + 1);
-        a1[j] = __ldg(p1 + r); b1[j] = __ldg(p1 + r + 1);
-        a2[j] = __ldg(p2 + r); b2[j] = __ldg(p2 + r + 1);
+        a0[j] = ld ? __ldg(p0 + r) : 0.f;
+        a1[j] = ld ? __ldg(p1 + r) : 0.f;
+        a2[j] = ld ? __ldg(p2 + r) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < W + 1; j++) {
+        b0[j] = __shfl_down_sync(0xffffffffu, a0[j], 1);
+        b1[j] = __shfl_down_sync(0xffffffffu, a1[j], 1);
+        b2[j] = __shfl_down_sync(0xffffffffu, a2[j], 1);
     }
 #pragma unroll
     for (int j = 0; j < W; j++) {
@@ -282,7 +294,8 @@ lk_track_rows_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ x
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = (blockIdx.x * (blockDim.x >> 5) + warp) * FPW + lane / G;
     const int j = lane % G;                       // window column handled by this lane
-    const bool row_ok = j < W;
+    const bool row_ok = j < W;                    // lane owns a window column
+    const bool col_ld = j <= W;                   // lane loads a source column (lane W: the right-hand extra one)
     bool alive = f < A.total;
     if (alive) alive = vals[f] >= 0;              // trackFeatures.py:253
     if (!__any_sync(0xffffffffu, alive)) return;
@@ -310,11 +323,12 @@ lk_track_rows_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ x
                 st = KLT_INTERNAL_ASSERT;
                 alive = false;
             }
-            if (alive && row_ok) {
+            {
                 const float ax = x1 - (float)ix, ay = y1 - (float)iy;
                 const float w11 = ax * ay, w01 = ax - w11, w10 = ay - w11, w00 = 1.f - ax - ay + w11;
-                patch_col3<W>(I1, GX1, GY1, pitch, ix, iy, j, w00, w01, w10, w11, T, Tgx, Tgy);
-            } else {
+                patch_col3<W>(I1, GX1, GY1, pitch, ix, iy, j, alive && col_ld, w00, w01, w10, w11, T, Tgx, Tgy);
+            }
+            if (!(alive && row_ok)) {
 #pragma unroll
                 for (int i = 0; i < W; i++) { T[i] = 0.f; Tgx[i] = 0.f; Tgy[i] = 0.f; }
             }
@@ -329,17 +343,19 @@ lk_track_rows_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ x
                 iterating = false;
             }
             float gxx = 0.f, gxy = 0.f, gyy = 0.f, ex = 0.f, ey = 0.f;
-            if (iterating && row_ok) {
+            {
                 const int ix = (int)x2, iy = (int)y2;
                 const float ax = x2 - (float)ix, ay = y2 - (float)iy;
                 const float w11 = ax * ay, w01 = ax - w11, w10 = ay - w11, w00 = 1.f - ax - ay + w11;
                 float P[W], Px[W], Py[W];
-                patch_col3<W>(I2, GX2, GY2, pitch, ix, iy, j, w00, w01, w10, w11, P, Px, Py);
+                patch_col3<W>(I2, GX2, GY2, pitch, ix, iy, j, iterating && col_ld, w00, w01, w10, w11, P, Px, Py);
+                if (iterating && row_ok) {
 #pragma unroll
-                for (int i = 0; i < W; i++) {
-                    const float diff = T[i] - P[i], gx = Tgx[i] + Px[i], gy = Tgy[i] + Py[i];
-                    gxx = fmaf(gx, gx, gxx); gxy = fmaf(gx, gy, gxy); gyy = fmaf(gy, gy, gyy);
-                    ex = fmaf(diff, gx, ex); ey = fmaf(diff, gy, ey);
+                    for (int i = 0; i < W; i++) {
+                        const float diff = T[i] - P[i], gx = Tgx[i] + Px[i], gy = Tgy[i] + Py[i];
+                        gxx = fmaf(gx, gx, gxx); gxy = fmaf(gx, gy, gxy); gyy = fmaf(gy, gy, gyy);
+                        ex = fmaf(diff, gx, ex); ey = fmaf(diff, gy, ey);
+                    }
                 }
             }
             gxx = group_sum<G>(gxx); gxy = group_sum<G>(gxy); gyy = group_sum<G>(gyy);
@@ -367,14 +383,16 @@ lk_track_rows_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ x
         const bool need_res = alive && status == KLT_TRACKED && A.has_max_residue;
         if (__any_sync(0xffffffffu, need_res)) {
             float res = 0.f;
-            if (need_res && row_ok) {
+            {
                 const int ix = (int)x2, iy = (int)y2;
                 const float ax = x2 - (float)ix, ay = y2 - (float)iy;
                 const float w11 = ax * ay, w01 = ax - w11, w10 = ay - w11, w00 = 1.f - ax - ay + w11;
                 float P[W];
-                patch_col<W>(I2, pitch, ix, iy, j, w00, w01, w10, w11, P);
+                patch_col<W>(I2, pitch, ix, iy, j, need_res && col_ld, w00, w01, w10, w11, P);
+                if (need_res && row_ok) {
 #pragma unroll
-                for (int i = 0; i < W; i++) res += fabsf(T[i] - P[i]);
+                    for (int i = 0; i < W; i++) res += fabsf(T[i] - P[i]);
+                }
             }
             res = group_sum<G>(res) / (float)(W * W);
             if (need_res && res > A.max_residue) status = KLT_LARGE_RESIDUE;
