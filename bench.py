@@ -148,7 +148,7 @@ def run_b200(args):
     wl = WORKLOADS[args.workload]
     H, W, n, L, ss = wl["H"], wl["W"], wl["n"], wl["L"], wl["ss"]
     B = args.pairs
-    prec = _capi.PRECISION_STRICT if args.precision == "strict" else _capi.PRECISION_FAST
+    prec = {"strict": _capi.PRECISION_STRICT, "fast": _capi.PRECISION_FAST, "windowed": _capi.PRECISION_FAST_WINDOWED}[args.precision]
     config.set_precision(track=args.precision)
 
     # ---- inputs: a few distinct seeded pairs (different per rank), tiled to the batch; features selected on the GPU
@@ -342,7 +342,7 @@ def run_b200(args):
     out = {
         "metric": "tracked_features_per_sec", "value": round(tracked_all / step_s, 1), "unit": "tracked features/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 4),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fast" else "f64-accumulate/f32",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision != "strict" else "f64-accumulate/f32",
         "data": "synthetic",
         "frame_pairs_per_sec": round(pairs_all / step_s, 2),
         "config": {"workload": wl["name"], "pairs_per_step_per_gpu": B, "features_per_pair": n, "distinct_pairs": args.distinct,
@@ -596,7 +596,7 @@ def main():
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=32, help="independent frame pairs per step per GPU")
     ap.add_argument("--distinct", type=int, default=4, help="distinct seeded pairs generated per rank (tiled to --pairs)")
-    ap.add_argument("--precision", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--precision", default="fast", choices=["fast", "strict", "windowed"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--api-pairs", type=int, default=10)

@@ -55,6 +55,11 @@ typedef enum klt_status {
 /* arithmetic mode of the convolution / pyramid kernels */
 #define KLT_PRECISION_FAST 0   /* fp32 FMA accumulation (<= 1e-6 relative-to-max of the reference images) */
 #define KLT_PRECISION_STRICT 1 /* fp64 accumulation in SciPy's exact operation order: bit-identical images */
+/* FAST arithmetic, pyramid builds only: write the intensity planes and skip the gradient planes.  klt_track_features
+ * then evaluates the gradient pair (convolve.py:245-246) inside the windows the features visit, in shared memory;
+ * anything that asks for a gradient plane (klt_pyr_download, klt_pyr_level_ptr, the affine tracker, window sizes or
+ * gradient kernels the windowed tracker does not cover) builds the planes on demand, so results never depend on it. */
+#define KLT_PRECISION_FAST_WINDOWED 2
 
 typedef struct klt_ctx klt_ctx; /* one per (device, stream) */
 typedef struct klt_pyr klt_pyr; /* a batch of image pyramids: intensity, gradx, grady for every level */

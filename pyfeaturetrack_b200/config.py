@@ -5,12 +5,16 @@ strict : convolutions accumulate in float64 in SciPy's exact operation order -> 
 fast   : float32 FMA convolutions (images within ~5e-7 relative-to-max of the reference's); tracking then
          agrees to ~1e-4 px.  Selection order is sensitive to the last bit of the gradients,
          so selection and the operator-level functions default to strict; tracking defaults to fast.
+windowed : (tracking only) fast arithmetic on image-only pyramids: the gradient planes are not written; the tracker
+         evaluates the gradient pair inside the windows the features visit.  Same results as fast to ~1e-5 px;
+         anything that asks for a gradient plane builds it on demand.
 """
 import os
 
 from . import _capi
 
 _MODES = {"fast": _capi.PRECISION_FAST, "strict": _capi.PRECISION_STRICT}
+_TRACK_MODES = dict(_MODES, windowed=_capi.PRECISION_FAST_WINDOWED)
 
 operator_precision = os.environ.get("KLT_B200_OPERATOR_PRECISION", "strict")
 select_precision = os.environ.get("KLT_B200_SELECT_PRECISION", "strict")
@@ -19,9 +23,11 @@ track_precision = os.environ.get("KLT_B200_TRACK_PRECISION", "fast")
 
 def set_precision(track=None, select=None, operator=None):
     global track_precision, select_precision, operator_precision
-    for v in (track, select, operator):
+    for v in (select, operator):
         if v is not None and v not in _MODES:
             raise ValueError("precision must be 'fast' or 'strict'")
+    if track is not None and track not in _TRACK_MODES:
+        raise ValueError("track precision must be 'fast', 'strict' or 'windowed'")
     if track is not None:
         track_precision = track
     if select is not None:
@@ -39,4 +45,4 @@ def select_precision_code():
 
 
 def track_precision_code():
-    return _MODES[track_precision]
+    return _TRACK_MODES[track_precision]

@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "klt_common.cuh"
+#include "klt_track_args.cuh"
 
 static thread_local std::string g_create_error;
 
@@ -262,12 +263,14 @@ int klt_pyr_create(klt_ctx *ctx, int w, int h, int n_levels, int subsampling, in
         return klt_fail(ctx, KLT_ERR_INVALID, "Pyramid's subsampling must be either 2, 4, 8, 16, or 32");   // pyramid.py:17-20
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
     klt_pyr *p = new klt_pyr();
+    p->hx = new KltPyrHost();
+    p->hx->taps_valid = false; p->hx->grad_valid = false;
     p->w = w; p->h = h; p->n_levels = n_levels; p->ss = subsampling; p->batch = batch;
     p->precision = KLT_PRECISION_STRICT;
     size_t off = 0;
     int lw = w, lh = h;
     for (int l = 0; l < n_levels; l++) {
-        if (lw < 1 || lh < 1) { delete p; return klt_fail(ctx, KLT_ERR_INVALID, "pyramid level %d is empty", l); }
+        if (lw < 1 || lh < 1) { delete p->hx; delete p; return klt_fail(ctx, KLT_ERR_INVALID, "pyramid level %d is empty", l); }
         p->lv[l].w = lw; p->lv[l].h = lh; p->lv[l].pitch = (lw + 3) & ~3; p->lv[l].off = off;
         off += align_up((size_t)p->lv[l].pitch * lh, 64);    // 256-byte aligned levels
         lw /= subsampling; lh /= subsampling;               // int(n / ss), pyramid.py:63-64
@@ -275,7 +278,7 @@ int klt_pyr_create(klt_ctx *ctx, int w, int h, int n_levels, int subsampling, in
     p->plane_floats = off;
     const size_t bytes = 3 * (size_t)batch * off * sizeof(float);
     cudaError_t e = cudaMalloc(&p->base, bytes);
-    if (e != cudaSuccess) { delete p; return klt_fail(ctx, KLT_ERR_NOMEM, "cudaMalloc(%zu) for pyramid failed: %s", bytes, cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { delete p->hx; delete p; return klt_fail(ctx, KLT_ERR_NOMEM, "cudaMalloc(%zu) for pyramid failed: %s", bytes, cudaGetErrorString(e)); }
     *out = p;
     return KLT_OK;
 }
@@ -284,6 +287,7 @@ int klt_pyr_destroy(klt_ctx *ctx, klt_pyr *pyr) {
     if (!pyr) return KLT_OK;
     if (ctx) cudaStreamSynchronize(ctx->stream);
     cudaFree(pyr->base);
+    delete pyr->hx;
     delete pyr;
     return KLT_OK;
 }
@@ -305,8 +309,24 @@ static int check_taps(klt_ctx *ctx, const klt_taps *t) {
 // levels 1..L-1 and all gradients, given level 0 intensity already in place (level0_grad_done: the fused level-0
 // kernel has already written gradx/grady of level 0).  FAST precision takes the warp-streaming kernels where they
 // cover the configuration; everything else runs the generic tiled kernels.
+static int build_gradients(klt_ctx *ctx, klt_pyr *p, const klt_taps *taps, int precision, int first_level, int first, int count) {
+    int rc;
+    const size_t stride = p->plane_floats;
+    const bool fast = precision == KLT_PRECISION_FAST;
+    for (int l = first_level; l < p->n_levels; l++) {
+        const LevelDesc &a = p->lv[l];
+        rc = fast ? klt_stream_grad(ctx, p, l, taps, first, count) : 0;
+        if (rc < 0) return rc;
+        if (rc == 0 && (rc = klt_launch_grad_pair(ctx, p->level(0, first, l), a.pitch, stride, p->level(1, first, l),
+                                                  p->level(2, first, l), a.pitch, stride, a.w, a.h, count, &taps->grad_gauss,
+                                                  &taps->grad_deriv, precision))) return rc;
+    }
+    return KLT_OK;
+}
+
+// `windowed`: leave the gradient planes unwritten (KLT_PRECISION_FAST_WINDOWED)
 static int build_rest(klt_ctx *ctx, klt_pyr *p, const klt_taps *taps, int precision, bool level0_grad_done = false,
-                      int first = 0, int count = -1) {
+                      int first = 0, int count = -1, bool windowed = false) {
     if (count < 0) count = p->batch;
     int rc;
     const size_t stride = p->plane_floats;
@@ -318,22 +338,40 @@ static int build_rest(klt_ctx *ctx, klt_pyr *p, const klt_taps *taps, int precis
         if (rc == 0 && (rc = klt_launch_pyr_down(ctx, p->level(0, first, l - 1), a.pitch, stride, a.w, a.h, p->level(0, first, l),
                                                  b.pitch, stride, b.w, b.h, p->ss, count, &taps->pyramid, precision))) return rc;
     }
-    for (int l = level0_grad_done ? 1 : 0; l < p->n_levels; l++) {
-        const LevelDesc &a = p->lv[l];
-        rc = fast ? klt_stream_grad(ctx, p, l, taps, first, count) : 0;
-        if (rc < 0) return rc;
-        if (rc == 0 && (rc = klt_launch_grad_pair(ctx, p->level(0, first, l), a.pitch, stride, p->level(1, first, l),
-                                                  p->level(2, first, l), a.pitch, stride, a.w, a.h, count, &taps->grad_gauss,
-                                                  &taps->grad_deriv, precision))) return rc;
-    }
+    if (windowed) return KLT_OK;
+    return build_gradients(ctx, p, taps, precision, level0_grad_done ? 1 : 0, first, count);
+}
+
+// bookkeeping of a build: `precision` as given by the caller; returns the arithmetic precision to run with
+static int begin_build(klt_pyr *p, const klt_taps *taps, int precision, bool *windowed) {
+    *windowed = precision == KLT_PRECISION_FAST_WINDOWED;
+    const int arith = *windowed ? KLT_PRECISION_FAST : precision;
+    p->precision = arith;
+    p->hx->taps = *taps; p->hx->taps_valid = true;
+    p->hx->grad_valid = !*windowed;
+    return arith;
+}
+
+int klt_pyr_ensure_gradients(klt_ctx *ctx, klt_pyr *p) {
+    if (!p->hx || p->hx->grad_valid) return KLT_OK;
+    if (!p->hx->taps_valid) return klt_fail(ctx, KLT_ERR_INVALID, "pyramid has not been built");
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = build_gradients(ctx, p, &p->hx->taps, p->precision, 0, 0, p->batch);
+    if (rc) return rc;
+    p->hx->grad_valid = true;
     return KLT_OK;
 }
 
 // device frames -> pyramids for images [first, first+count); dframes points at image `first`
 static int build_u8_device(klt_ctx *ctx, klt_pyr *p, const uint8_t *dframes, size_t pitch, size_t frame_stride,
-                           const klt_taps *taps, int precision, int first, int count) {
+                           const klt_taps *taps, int precision, int first, int count, bool windowed = false) {
     int rc;
-    if (precision == KLT_PRECISION_FAST) {
+    if (windowed) {
+        // u8 -> smoothed image only
+        rc = klt_stream_smooth0(ctx, dframes, pitch, frame_stride, p, taps, first, count);
+        if (rc < 0) return rc;
+        if (rc == 1) return build_rest(ctx, p, taps, precision, false, first, count, true);
+    } else if (precision == KLT_PRECISION_FAST) {
         // fused u8 -> smoothed image + gradient pair of level 0 (one read of the frame, three writes)
         rc = klt_stream_level0(ctx, dframes, pitch, frame_stride, p, taps, first, count);
         if (rc < 0) return rc;
@@ -342,7 +380,7 @@ static int build_u8_device(klt_ctx *ctx, klt_pyr *p, const uint8_t *dframes, siz
     // img.convert("F") + KLTComputeSmoothedImage (trackFeatures.py:165-166): one kernel, u8 in, f32 out
     if ((rc = klt_launch_conv_sep_u8(ctx, dframes, pitch, frame_stride, p->level(0, first, 0), p->lv[0].pitch, p->plane_floats,
                                      p->w, p->h, count, &taps->smooth, &taps->smooth, precision))) return rc;
-    return build_rest(ctx, p, taps, precision, false, first, count);
+    return build_rest(ctx, p, taps, precision, false, first, count, windowed);
 }
 
 int klt_pyr_build_u8(klt_ctx *ctx, klt_pyr *p, const uint8_t *frames, size_t pitch, size_t frame_stride,
@@ -352,7 +390,8 @@ int klt_pyr_build_u8(klt_ctx *ctx, klt_pyr *p, const uint8_t *frames, size_t pit
     if ((rc = check_taps(ctx, taps))) return rc;
     if (pitch < (size_t)p->w) return klt_fail(ctx, KLT_ERR_INVALID, "pitch %zu smaller than width %d", pitch, p->w);
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
-    p->precision = precision;
+    bool windowed;
+    precision = begin_build(p, taps, precision, &windowed);
     const uint8_t *dframes = frames;
     if (!klt_is_device_ptr(frames)) {
         const size_t bytes = (size_t)(p->batch - 1) * frame_stride + (size_t)(p->h - 1) * pitch + p->w;
@@ -360,7 +399,7 @@ int klt_pyr_build_u8(klt_ctx *ctx, klt_pyr *p, const uint8_t *frames, size_t pit
         KLT_CUDA(ctx, cudaMemcpyAsync(ctx->ws, frames, bytes, cudaMemcpyHostToDevice, ctx->stream));
         dframes = (const uint8_t *)ctx->ws;
     }
-    return build_u8_device(ctx, p, dframes, pitch, frame_stride, taps, precision, 0, p->batch);
+    return build_u8_device(ctx, p, dframes, pitch, frame_stride, taps, precision, 0, p->batch, windowed);
 }
 
 int klt_pyr_build_f32(klt_ctx *ctx, klt_pyr *p, const float *images, size_t pitch, size_t frame_stride,
@@ -370,12 +409,13 @@ int klt_pyr_build_f32(klt_ctx *ctx, klt_pyr *p, const float *images, size_t pitc
     if ((rc = check_taps(ctx, taps))) return rc;
     if (pitch < (size_t)p->w) return klt_fail(ctx, KLT_ERR_INVALID, "pitch %zu smaller than width %d", pitch, p->w);
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
-    p->precision = precision;
+    bool windowed;
+    precision = begin_build(p, taps, precision, &windowed);
     if (already_smoothed) {
         for (int b = 0; b < p->batch; b++)
             KLT_CUDA(ctx, cudaMemcpy2DAsync(p->level(0, b, 0), p->lv[0].pitch * sizeof(float), images + (size_t)b * frame_stride,
                                             pitch * sizeof(float), p->w * sizeof(float), p->h, cudaMemcpyDefault, ctx->stream));
-        return build_rest(ctx, p, taps, precision);
+        return build_rest(ctx, p, taps, precision, false, 0, -1, windowed);
     }
     const float *dimg = images;
     if (!klt_is_device_ptr(images)) {
@@ -386,12 +426,16 @@ int klt_pyr_build_f32(klt_ctx *ctx, klt_pyr *p, const float *images, size_t pitc
     }
     if ((rc = klt_launch_conv_sep_f32(ctx, dimg, pitch, frame_stride, p->level(0, 0, 0), p->lv[0].pitch, p->plane_floats, p->w,
                                       p->h, p->batch, &taps->smooth, &taps->smooth, precision))) return rc;
-    return build_rest(ctx, p, taps, precision);
+    return build_rest(ctx, p, taps, precision, false, 0, -1, windowed);
 }
 
 int klt_pyr_download(klt_ctx *ctx, const klt_pyr *p, int image, int which, int level, float *out) {
     if (!ctx || !p || !out || image < 0 || image >= p->batch || which < 0 || which > 2 || level < 0 || level >= p->n_levels)
         return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    if (which > 0) {
+        int rc = klt_pyr_ensure_gradients(ctx, const_cast<klt_pyr *>(p));
+        if (rc) return rc;
+    }
     const LevelDesc &a = p->lv[level];
     KLT_CUDA(ctx, cudaMemcpy2DAsync(out, a.w * sizeof(float), p->level(which, image, level), a.pitch * sizeof(float),
                                     a.w * sizeof(float), a.h, cudaMemcpyDefault, ctx->stream));
@@ -401,6 +445,7 @@ int klt_pyr_download(klt_ctx *ctx, const klt_pyr *p, int image, int which, int l
 
 int klt_pyr_level_ptr(const klt_pyr *p, int image, int which, int level, const float **ptr) {
     if (!p || !ptr || image < 0 || image >= p->batch || which < 0 || which > 2 || level < 0 || level >= p->n_levels) return KLT_ERR_INVALID;
+    if (which > 0 && !klt_pyr_has_gradients(p)) return KLT_ERR_UNSUPPORTED;   // image-only pyramid: download builds them
     *ptr = p->level(which, image, level);
     return KLT_OK;
 }
@@ -475,6 +520,11 @@ static int track_impl(klt_ctx *ctx, const klt_params *params, const klt_pyr *pyr
     int rc;
     if ((rc = check_track_args(ctx, params, pyr1, pyr2))) return rc;
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (aff || !klt_windowed_supported(params, pyr1, pyr2)) {
+        // the affine tracker and the configurations the windowed tracker does not cover read gradient planes
+        if ((rc = klt_pyr_ensure_gradients(ctx, const_cast<klt_pyr *>(pyr1)))) return rc;
+        if ((rc = klt_pyr_ensure_gradients(ctx, const_cast<klt_pyr *>(pyr2)))) return rc;
+    }
     const size_t total = (size_t)n_per_image * pyr1->batch;
     if (aff) {
         if ((size_t)aff->n != total) return klt_fail(ctx, KLT_ERR_INVALID, "affine state has %d slots, %zu features given", aff->n, total);
@@ -738,7 +788,9 @@ int klt_track_pairs_u8(klt_ctx *ctx, const klt_params *params, const klt_taps *t
     // the staging buffers may still be read by kernels of the previous call
     KLT_CUDA(ctx, cudaEventRecord(ctx->compute_done, ctx->stream));
     KLT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_done, 0));
-    pyr1->precision = pyr2->precision = precision;
+    bool windowed;
+    begin_build(pyr1, taps, precision, &windowed);
+    precision = begin_build(pyr2, taps, precision, &windowed);
     int k = 0;
     for (int first = 0; first < B; first += per_chunk, k++) {
         const int count = first + per_chunk <= B ? per_chunk : B - first;
@@ -752,8 +804,8 @@ int klt_track_pairs_u8(klt_ctx *ctx, const klt_params *params, const klt_taps *t
         const int count = first + per_chunk <= B ? per_chunk : B - first;
         const size_t off = (size_t)first * frame_stride;
         KLT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[k], 0));
-        if ((rc = build_u8_device(ctx, pyr1, d1 + off, pitch, frame_stride, taps, precision, first, count))) return rc;
-        if ((rc = build_u8_device(ctx, pyr2, d2 + off, pitch, frame_stride, taps, precision, first, count))) return rc;
+        if ((rc = build_u8_device(ctx, pyr1, d1 + off, pitch, frame_stride, taps, precision, first, count, windowed))) return rc;
+        if ((rc = build_u8_device(ctx, pyr2, d2 + off, pitch, frame_stride, taps, precision, first, count, windowed))) return rc;
     }
     return klt_track_features(ctx, params, pyr1, pyr2, n_per_image, x, y, val, nullptr);
 }

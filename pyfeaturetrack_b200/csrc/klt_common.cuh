@@ -24,7 +24,15 @@ struct LevelDesc {
     size_t off;               // offset in floats of image 0 inside the component plane
 };
 
+// host-only part of a pyramid (kept behind a pointer so that klt_pyr stays a small by-value kernel argument)
+struct KltPyrHost {
+    klt_taps taps;            // kernels of the last build (the windowed tracker and lazy gradient builds need them)
+    bool taps_valid;
+    bool grad_valid;          // gradient planes hold the gradients of the current images
+};
+
 struct klt_pyr {
+    KltPyrHost *hx;
     int w, h, n_levels, ss, batch;
     int precision;            // KLT_PRECISION_* of the last build (selects the tracking kernel's arithmetic)
     LevelDesc lv[KLT_MAX_LEVELS];
@@ -104,6 +112,10 @@ void klt_prof_end(klt_ctx *ctx, int token);
 int klt_ws_reserve(klt_ctx *ctx, size_t bytes);          // grow-only workspace
 bool klt_is_device_ptr(const void *p);
 
+static inline bool klt_pyr_has_gradients(const klt_pyr *p) { return !p->hx || p->hx->grad_valid; }
+// build the gradient planes of an image-only pyramid (no-op when they are valid)
+extern "C" int klt_pyr_ensure_gradients(klt_ctx *ctx, klt_pyr *p);
+
 int klt_make_taps(klt_ctx *ctx, const klt_kernel1d *k, TapsF *f, TapsD *d);
 
 // ---- launchers (klt_conv.cu) -- all pointers are DEVICE pointers, pitches in elements ----------------
@@ -127,6 +139,9 @@ int klt_launch_pyr_down(klt_ctx *ctx, const float *in, size_t in_pitch, size_t i
 // (first, count): the sub-range of the pyramid batch to build; `frames` points at image `first`
 int klt_stream_level0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t frame_stride, klt_pyr *p, const klt_taps *taps,
                       int first, int count);
+// u8 frame -> smoothed level-0 image only (image-only pyramids)
+int klt_stream_smooth0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t frame_stride, klt_pyr *p, const klt_taps *taps,
+                       int first, int count);
 int klt_stream_grad(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps, int first, int count);
 int klt_stream_down2(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps, int first, int count);
 

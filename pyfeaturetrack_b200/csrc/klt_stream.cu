@@ -208,6 +208,73 @@ stream_level0_kernel(const unsigned char *__restrict__ frames, size_t pitch, siz
     for (; t < t1; t++) l0_row<RS, false>(S, T, t);
 }
 
+// ---- level 0 of an image-only pyramid: u8 frame -> smoothed image (KLT_PRECISION_FAST_WINDOWED) -----------------------
+// Same strip/lane geometry and load pipeline as stream_level0_kernel without the gradient stage: 1 B read + 4 B written
+// per pixel, 2*(2*RS+1) FMAs.
+template <int RS>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8)
+stream_smooth0_kernel(const unsigned char *__restrict__ frames, size_t pitch, size_t frame_stride, float *__restrict__ img,
+                      int out_pitch, size_t out_stride, int W, int H, int rows_per_seg, int n_strips,
+                      const __grid_constant__ StreamTaps T) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x * WARPS_PER_CTA + warp;
+    if (strip >= n_strips) return;
+    const int ys = blockIdx.y * rows_per_seg, ye = min(H, ys + rows_per_seg);
+    const int c = strip * 120 + 4 * (lane - 1);
+    const unsigned char *src = frames + (size_t)blockIdx.z * frame_stride;
+    bool rv0, rvl, rvr;
+    const int m0 = mirror_quad(c, W, rv0), ml = mirror_quad(c - 4, W, rvl), mr = mirror_quad(c + 4, W, rvr);
+    const unsigned char *b0 = src + m0, *bl = src + ml, *br = src + mr;
+    const unsigned int sel0 = rv0 ? 0x0123u : 0x3210u, sell = rvl ? 0x0123u : 0x3210u, selr = rvr ? 0x0123u : 0x3210u;
+    const bool writer = lane >= 1 && lane <= 30 && c < W;
+    float *p_img = img + (size_t)blockIdx.z * out_stride + (size_t)c + (size_t)ys * out_pitch;
+    const unsigned int upitch = (unsigned int)pitch;
+    float sa[4][2 * RS];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int m = 0; m < 2 * RS; m++) sa[i][m] = 0.f;
+    const int t0 = ys - RS, t1 = ye + RS;
+    unsigned int w0, wl, wr;
+    {
+        const unsigned int ro = (unsigned int)reflect1(t0, H) * upitch;
+        w0 = __ldg(reinterpret_cast<const unsigned int *>(b0 + ro));
+        wl = __ldg(reinterpret_cast<const unsigned int *>(bl + ro));
+        wr = __ldg(reinterpret_cast<const unsigned int *>(br + ro));
+    }
+    for (int t = t0; t < t1; t++) {
+        const unsigned int q0 = __byte_perm(w0, 0u, sel0), ql = __byte_perm(wl, 0u, sell), qr = __byte_perm(wr, 0u, selr);
+        float u[4 + 2 * RS];
+#pragma unroll
+        for (int i = 0; i < 4; i++) u[RS + i] = u8_to_f32(q0, i);
+#pragma unroll
+        for (int k = 0; k < RS; k++) {
+            u[k] = u8_to_f32(ql, 4 - RS + k);
+            u[RS + 4 + k] = u8_to_f32(qr, k);
+        }
+        {
+            const unsigned int ro = (unsigned int)reflect1(min(t + 1, t1 - 1), H) * upitch;
+            w0 = __ldg(reinterpret_cast<const unsigned int *>(b0 + ro));
+            wl = __ldg(reinterpret_cast<const unsigned int *>(bl + ro));
+            wr = __ldg(reinterpret_cast<const unsigned int *>(br + ro));
+            const int tp = t + PREFETCH_ROWS;
+            if (tp < t1) prefetch_l2(b0 + (unsigned int)reflect1(tp, H) * upitch);
+        }
+        float s[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float h = T.s[0] * u[i];
+#pragma unroll
+            for (int j = 1; j < 2 * RS + 1; j++) h = fmaf(T.s[j], u[i + j], h);
+            s[i] = vacc<RS>(sa[i], T.s, h);
+        }
+        if (t - RS >= ys) {
+            if (writer) *reinterpret_cast<float4 *>(p_img) = make_float4(s[0], s[1], s[2], s[3]);
+            p_img += out_pitch;
+        }
+    }
+}
+
 // ---- gradients only: float image -> gradx, grady (levels >= 1) ---------------------------------------------------
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 stream_grad_kernel(const float *__restrict__ in, int in_pitch, size_t in_stride, float *__restrict__ gxo,
@@ -527,6 +594,46 @@ int klt_stream_level0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t 
         default: return 0;
     }
 #undef LAUNCH_L0
+    return 1;
+}
+
+int klt_stream_smooth0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t frame_stride, klt_pyr *p,
+                       const klt_taps *taps, int first, int count) {
+    StreamTaps T;
+    const int ns = taps->smooth.n;
+    if (ns != 3 && ns != 5 && ns != 7 && ns != 9) return 0;
+    if (!is_symmetric(&taps->smooth)) return 0;
+    const int RS = ns / 2;
+    if (!fill_taps(&taps->smooth, T.s, ns)) return 0;
+    for (int j = 0; j < 11; j++) T.p[j] = 0.f;
+    for (int j = 0; j < 7; j++) T.g[j] = T.d[j] = 0.f;
+    const int W = p->w, H = p->h;
+    if (W < 16 || H < 16 || (W & 3)) return 0;
+    if ((reinterpret_cast<uintptr_t>(frames) & 3) || (pitch & 3) || (frame_stride & 3)) return 0;
+    const int n_strips = (W + 119) / 120;
+    const int strip_ctas = (n_strips + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    int rows = 0;
+    switch (RS) {
+        case 1: rows = pick_rows_per_seg(ctx, stream_smooth0_kernel<1>, H, strip_ctas, count, 32); break;
+        case 2: rows = pick_rows_per_seg(ctx, stream_smooth0_kernel<2>, H, strip_ctas, count, 32); break;
+        case 3: rows = pick_rows_per_seg(ctx, stream_smooth0_kernel<3>, H, strip_ctas, count, 32); break;
+        default: rows = pick_rows_per_seg(ctx, stream_smooth0_kernel<4>, H, strip_ctas, count, 32); break;
+    }
+    dim3 grid(strip_ctas, (H + rows - 1) / rows, count), block(WARPS_PER_CTA * 32);
+    const double bytes = 5.0 * W * H * count;         // 1 B read + 4 B written per pixel
+    float *img = p->level(0, first, 0);
+#define LAUNCH_S0(R)                                                                                                   \
+    KLT_LAUNCH(ctx, "stream_smooth0", bytes,                                                                           \
+               (stream_smooth0_kernel<R><<<grid, block, 0, ctx->stream>>>(frames, pitch, frame_stride, img, p->lv[0].pitch, \
+                                                                          p->plane_floats, W, H, rows, n_strips, T)))
+    switch (RS) {
+        case 1: LAUNCH_S0(1); break;
+        case 2: LAUNCH_S0(2); break;
+        case 3: LAUNCH_S0(3); break;
+        case 4: LAUNCH_S0(4); break;
+        default: return 0;
+    }
+#undef LAUNCH_S0
     return 1;
 }
 

@@ -17,21 +17,7 @@
 // Given bit-identical pyramids (STRICT mode) the positions and status codes are bit-identical to the
 // reference's; with FAST pyramids they agree to ~1e-4 px.
 #include "klt_common.cuh"
-
-#define KLT_INTERNAL_ASSERT (-100)
-
-struct TrackArgs {
-    klt_pyr p1, p2;
-    int w, h;               // window
-    int n_levels, ss;
-    int max_iterations;
-    float small_det, th, step_factor;
-    int has_max_residue;
-    float max_residue;
-    int retain;
-    double borderx, bordery;
-    int n_per_image, total;
-};
+#include "klt_track_args.cuh"
 
 // bilinear sample with the reference's mixed precision (trackFeaturesUtils.pyx:44-47)
 __device__ __forceinline__ float bilerp_ref(const float *__restrict__ p, int pitch, float ax, float ay) {
@@ -442,6 +428,12 @@ int klt_launch_track(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const
     A.borderx = p->borderx; A.bordery = p->bordery;
     A.n_per_image = n_per_image; A.total = n_per_image * p1->batch;
     if (A.total <= 0) return KLT_OK;
+    // image-only pyramids (FAST_WINDOWED builds): gradients are evaluated inside the tracking windows
+    if (!klt_pyr_has_gradients(p1) || !klt_pyr_has_gradients(p2)) {
+        if (!klt_windowed_supported(p, p1, p2))
+            return klt_fail(ctx, KLT_ERR_INVALID, "image-only pyramid reached the plane-based tracker (internal error)");
+        return klt_launch_track_windowed(ctx, A, p1, p2, x_dev, y_dev, val_dev, iters_dev, assert_dev);
+    }
     if (!exact && A.w == A.h) {          // FAST pyramids: float32 row-per-lane kernel for the common window sizes
         switch (A.w) {
             case 3: return launch_rows<3>(ctx, A, x_dev, y_dev, val_dev, iters_dev, assert_dev);

@@ -1,0 +1,26 @@
+// Kernel-argument structs shared by the tracking translation units (klt_track.cu, klt_track_windowed.cu).
+#pragma once
+#include "klt_common.cuh"
+
+#define KLT_INTERNAL_ASSERT (-100)
+
+struct TrackArgs {
+    klt_pyr p1, p2;
+    int w, h;               // window
+    int n_levels, ss;
+    int max_iterations;
+    float small_det, th, step_factor;
+    int has_max_residue;
+    float max_residue;
+    int retain;
+    double borderx, bordery;
+    int n_per_image, total;
+};
+
+// gradient kernels of the two pyramids (the reference's kernel cache can hand different ones to the two images,
+// convolve.py:236,258); c[j] multiplies in[x + j - 3]
+struct WindowedTaps { float g1[7], d1[7], g2[7], d2[7]; };
+
+bool klt_windowed_supported(const klt_params *p, const klt_pyr *p1, const klt_pyr *p2);
+int klt_launch_track_windowed(klt_ctx *ctx, const TrackArgs &A, const klt_pyr *p1, const klt_pyr *p2, double *x_dev,
+                              double *y_dev, int32_t *val_dev, unsigned long long *iters_dev, int *assert_dev);

@@ -1,0 +1,384 @@
+// Pyramidal Lucas-Kanade on IMAGE-ONLY pyramids (KLT_PRECISION_FAST_WINDOWED): the gradient planes of the reference
+// (trackFeatures.py:171-176, `_KLTComputeGradients` per level) are never written to HBM.  A tracked feature only ever
+// reads gradients inside its (W+1)^2 window -- ~3 % of a 1080p frame for 1000 features -- so each warp evaluates the
+// 7-tap separable gradient pair (convolve.py:245-246) just for the pixels its feature visits:
+//
+//   * one WARP per feature; per pyramid level the warp stages a square region of the smoothed image with cp.async
+//     (window + margin + filter radius, SciPy 'reflect' indices at the image border) into shared memory,
+//   * runs the horizontal pass one region ROW per lane (sliding 7-value register window, both kernels at once) and the
+//     vertical pass one region COLUMN per lane, leaving gradx/grady of the region in shared memory,
+//   * and then iterates exactly like the dense FAST kernel (lk_track_rows_kernel), except that every bilinear sample
+//     comes from shared memory: one global round trip per level instead of one per Newton step.
+//   * The second image's region carries a margin of M pixels around the start window; if the window walks out of it the
+//     region is re-staged around the current position (warp-uniform branch; the values do not depend on the region).
+//
+// Arithmetic: float32 FMA, the same tap order as the dense FAST kernels (c[0..6] left to right / top to bottom), so the
+// window gradients agree with the planes `stream_grad_kernel` would have written to ~1 ulp; the tracked positions agree
+// with the dense FAST path to ~1e-5 px.  STRICT pyramids never come here.
+#include "klt_common.cuh"
+#include "klt_track_args.cuh"
+
+namespace {
+
+constexpr int RG = 3;      // gradient kernel radius served here (grad_sigma = 1.0: 7 taps); other radii use the planes
+constexpr int MARGIN = 2;  // pixels of slack around the start window of the second image
+constexpr int LAZY_WARPS = 4;
+#ifndef LAZY_MIN_CTAS
+#define LAZY_MIN_CTAS 5
+#endif
+
+template <int W>
+struct Cfg {
+    // first image: the exact window (S1 output pixels a side); second image: window + margin
+    static constexpr int S1 = W + 1, N1 = S1 + 2 * RG, NP1 = N1 | 1, SP1 = S1 | 1;      // odd pitches: conflict-free
+    static constexpr int S2 = W + 1 + 2 * MARGIN, N2 = S2 + 2 * RG, NP2 = N2 | 1, SP2 = S2 | 1;
+    // per-warp shared memory (floats): staged input, horizontal results (deriv, gauss), gradx, grady of both regions
+    static constexpr int IN1 = 0, TD1 = IN1 + N1 * NP1, TG1 = TD1 + N1 * SP1, GX1 = TG1 + N1 * SP1, GY1 = GX1 + S1 * SP1;
+    static constexpr int IN2 = GY1 + S1 * SP1, TD2 = IN2 + N2 * NP2, TG2 = TD2 + N2 * SP2, GX2 = TG2 + N2 * SP2, GY2 = GX2 + S2 * SP2;
+    static constexpr int FLOATS = GY2 + S2 * SP2;
+    static constexpr int PX = (W * W + 31) / 32;                         // window pixels per lane
+    static constexpr bool MERGED = N1 + N2 <= 32;                        // one lane per row of BOTH regions
+};
+
+__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// issue the copies of the N x N input region whose top-left pixel is (sx0, sy0) (SciPy 'reflect' outside the image)
+template <int N, int NP>
+__device__ __forceinline__ void stage_region(float *__restrict__ dst, const float *__restrict__ img, int pitch, int nc, int nr,
+                                             int sx0, int sy0, int lane) {
+    const bool interior = sx0 >= 0 && sy0 >= 0 && sx0 + N <= nc && sy0 + N <= nr;       // warp-uniform
+    if (interior) {
+        const float *src = img + (size_t)sy0 * pitch + sx0;
+#pragma unroll
+        for (int idx = lane; idx < N * N; idx += 32) {
+            const int ry = idx / N, rx = idx - ry * N;
+            cp_async4(dst + ry * NP + rx, src + ry * pitch + rx);
+        }
+    } else {
+#pragma unroll 1
+        for (int idx = lane; idx < N * N; idx += 32) {
+            const int ry = idx / N, rx = idx - ry * N;
+            cp_async4(dst + ry * NP + rx, img + (size_t)klt_reflect(sy0 + ry, nr) * pitch + klt_reflect(sx0 + rx, nc));
+        }
+    }
+}
+
+// horizontal pass of one region row: S outputs of both kernels from the N = S + 6 staged values
+template <int S>
+__device__ __forceinline__ void hrow(const float *__restrict__ row, float *__restrict__ td, float *__restrict__ tg,
+                                     const float (&g)[7], const float (&d)[7], int nout) {
+    constexpr int N = S + 2 * RG;
+    float v[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] = row[i];
+#pragma unroll
+    for (int c = 0; c < S; c++) {
+        float hd = d[0] * v[c], hg = g[0] * v[c];
+#pragma unroll
+        for (int j = 1; j < 7; j++) { hd = fmaf(d[j], v[c + j], hd); hg = fmaf(g[j], v[c + j], hg); }
+        if (c < nout) { td[c] = hd; tg[c] = hg; }
+    }
+}
+
+// vertical pass: lane = (plane, column); gx = gauss_v(deriv_h), gy = deriv_v(gauss_h)
+template <int S, int SP>
+__device__ __forceinline__ void vpass(const float *__restrict__ td, const float *__restrict__ tg, float *__restrict__ gx,
+                                      float *__restrict__ gy, const float (&g)[7], const float (&d)[7], int lane) {
+    constexpr int N = S + 2 * RG;
+#pragma unroll
+    for (int item = lane; item < 2 * S; item += 32) {
+        const bool second = item >= S;
+        const int col = second ? item - S : item;
+        const float *src = (second ? tg : td) + col;
+        float *dst = (second ? gy : gx) + col;
+        float t[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) t[j] = second ? d[j] : g[j];
+        float v[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) v[i] = src[i * SP];
+#pragma unroll
+        for (int r = 0; r < S; r++) {
+            float o = t[0] * v[r];
+#pragma unroll
+            for (int j = 1; j < 7; j++) o = fmaf(t[j], v[r + j], o);
+            dst[r * SP] = o;
+        }
+    }
+}
+
+// gradients of the staged second-image region (also the re-staging path)
+template <int W>
+__device__ __forceinline__ void gradients2(float *__restrict__ s, const WindowedTaps &K, int lane) {
+    using C = Cfg<W>;
+    if (lane < C::N2) hrow<C::S2>(s + C::IN2 + lane * C::NP2, s + C::TD2 + lane * C::SP2, s + C::TG2 + lane * C::SP2, K.g2, K.d2, C::S2);
+    __syncwarp();
+    vpass<C::S2, C::SP2>(s + C::TD2, s + C::TG2, s + C::GX2, s + C::GY2, K.g2, K.d2, lane);
+    __syncwarp();
+}
+
+// gradients of both staged regions of a level
+template <int W>
+__device__ __forceinline__ void gradients_both(float *__restrict__ s, const WindowedTaps &K, int lane) {
+    using C = Cfg<W>;
+    if (C::MERGED) {
+        // lanes [0, N2): rows of the second image's region; lanes [N2, N2+N1): rows of the first image's.  One code path:
+        // the first-image lanes run the S2-wide loop and keep their first S1 outputs (their reads past the row end stay
+        // inside the warp's buffer).
+        const bool second = lane < C::N2;
+        const int row = second ? lane : lane - C::N2;
+        if (second || row < C::N1) {
+            const float *src = s + (second ? C::IN2 + row * C::NP2 : C::IN1 + row * C::NP1);
+            float *td = s + (second ? C::TD2 + row * C::SP2 : C::TD1 + row * C::SP1);
+            float *tg = s + (second ? C::TG2 + row * C::SP2 : C::TG1 + row * C::SP1);
+            float g[7], d[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) { g[j] = second ? K.g2[j] : K.g1[j]; d[j] = second ? K.d2[j] : K.d1[j]; }
+            hrow<C::S2>(src, td, tg, g, d, second ? C::S2 : C::S1);
+        }
+    } else {
+        if (lane < C::N2) hrow<C::S2>(s + C::IN2 + lane * C::NP2, s + C::TD2 + lane * C::SP2, s + C::TG2 + lane * C::SP2, K.g2, K.d2, C::S2);
+        if (lane < C::N1) hrow<C::S1>(s + C::IN1 + lane * C::NP1, s + C::TD1 + lane * C::SP1, s + C::TG1 + lane * C::SP1, K.g1, K.d1, C::S1);
+    }
+    __syncwarp();
+    vpass<C::S2, C::SP2>(s + C::TD2, s + C::TG2, s + C::GX2, s + C::GY2, K.g2, K.d2, lane);
+    vpass<C::S1, C::SP1>(s + C::TD1, s + C::TG1, s + C::GX1, s + C::GY1, K.g1, K.d1, lane);
+    __syncwarp();
+}
+
+__device__ __forceinline__ float bil(const float *p, int P, float w00, float w01, float w10, float w11) {
+    return fmaf(w11, p[P + 1], fmaf(w10, p[P], fmaf(w01, p[1], w00 * p[0])));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// L2 prefetch of the rows of an N-wide region (top-left input pixel (sx0, sy0)), one row per lane starting at lane0
+template <int N>
+__device__ __forceinline__ void prefetch_region(const float *__restrict__ img, int pitch, int nc, int nr, int sx0, int sy0, int row) {
+    const int y = min(max(sy0 + row, 0), nr - 1);
+    const int xa = min(max(sx0, 0), nc - 1), xb = min(max(sx0 + N - 1, 0), nc - 1);
+    const float *p = img + (size_t)y * pitch;
+#pragma unroll
+    for (int k = 0; k * 8 < N; k++) prefetch_l2(p + min(xa + 8 * k, xb));
+    prefetch_l2(p + xb);
+}
+
+template <int W>
+__global__ void __launch_bounds__(LAZY_WARPS * 32, (W <= 11 ? LAZY_MIN_CTAS : 3))
+lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ WindowedTaps K, double *__restrict__ xs,
+                   double *__restrict__ ys, int *__restrict__ vals, unsigned long long *__restrict__ iters_total,
+                   int *__restrict__ assert_flag) {
+    using C = Cfg<W>;
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.x * LAZY_WARPS + warp;
+    if (f >= A.total) return;                     // one feature per warp: all control flow below is warp-uniform
+    if (vals[f] < 0) return;                      // trackFeatures.py:253
+    float *s = smem + warp * C::FLOATS;
+    const int image = f / A.n_per_image;
+    constexpr int hw = W / 2;
+    const double ss = (double)A.ss;
+    double xloc = xs[f], yloc = ys[f];
+    for (int r = A.n_levels - 1; r >= 0; r--) { xloc /= ss; yloc /= ss; }
+    double xout = xloc, yout = yloc;
+    int st = KLT_TRACKED;
+    unsigned int my_iters = 0;
+    bool alive = true;
+
+    for (int r = A.n_levels - 1; r >= 0; r--) {
+        xloc *= ss; yloc *= ss; xout *= ss; yout *= ss;
+        if (!alive) continue;
+        const int nc = A.p1.lv[r].w, nr = A.p1.lv[r].h, pitch = A.p1.lv[r].pitch;
+        const float *I1 = A.p1.level(0, image, r), *I2 = A.p2.level(0, image, r);
+        const float x1 = (float)xloc, y1 = (float)yloc;
+        const int ix1 = (int)x1, iy1 = (int)y1;
+        if (!(ix1 - hw >= 0 && iy1 - hw >= 0 && ix1 + hw + 2 <= nc && iy1 + hw + 2 <= nr)) {   // pyx:35
+            if (lane == 0) atomicExch(assert_flag, 1);
+            st = KLT_INTERNAL_ASSERT;
+            alive = false;
+            continue;
+        }
+        float x2 = (float)xout, y2 = (float)yout;
+        int status = KLT_TRACKED, iteration = 0;
+        const float fnc = (float)nc, fnr = (float)nr, fhw = (float)hw;
+        // top-left OUTPUT pixel of the second image's region; the start window sits MARGIN pixels inside it
+        int rx0 = (int)x2 - hw - MARGIN, ry0 = (int)y2 - hw - MARGIN;
+        const bool start_inside = !(x2 - fhw < 0.f || fnc - (x2 + fhw) < 1.001f || y2 - fhw < 0.f || fnr - (y2 + fhw) < 1.001f);
+        // one memory round trip: both regions of this level
+        stage_region<C::N1, C::NP1>(s + C::IN1, I1, pitch, nc, nr, ix1 - hw - RG, iy1 - hw - RG, lane);
+        if (start_inside) stage_region<C::N2, C::NP2>(s + C::IN2, I2, pitch, nc, nr, rx0 - RG, ry0 - RG, lane);
+        if (r > 0) {
+            // pull the next (finer) level's regions towards L2 while this level computes
+            const int ncn = A.p1.lv[r - 1].w, nrn = A.p1.lv[r - 1].h, pn = A.p1.lv[r - 1].pitch;
+            const float xn1 = (float)(xloc * ss), yn1 = (float)(yloc * ss);
+            const float xn2 = (float)((double)x2 * ss), yn2 = (float)((double)y2 * ss);
+            if (lane < C::N2 && lane + 0 < 32)
+                prefetch_region<C::N2>(A.p2.level(0, image, r - 1), pn, ncn, nrn, (int)xn2 - hw - MARGIN - RG, (int)yn2 - hw - MARGIN - RG, lane);
+            if (lane < C::N1)
+                prefetch_region<C::N1>(A.p1.level(0, image, r - 1), pn, ncn, nrn, (int)xn1 - hw - RG, (int)yn1 - hw - RG, lane);
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        if (start_inside) gradients_both<W>(s, K, lane);
+        else {
+            if (lane < C::N1) hrow<C::S1>(s + C::IN1 + lane * C::NP1, s + C::TD1 + lane * C::SP1, s + C::TG1 + lane * C::SP1, K.g1, K.d1, C::S1);
+            __syncwarp();
+            vpass<C::S1, C::SP1>(s + C::TD1, s + C::TG1, s + C::GX1, s + C::GY1, K.g1, K.d1, lane);
+            __syncwarp();
+            rx0 = -0x40000000;                     // nothing staged for the second image (the loop exits with OOB at once)
+        }
+        // template: the first image's window, gradients interpolated like the image (trackFeatures.py:87-92)
+        float T[C::PX], Tgx[C::PX], Tgy[C::PX];
+        int po[C::PX], pi[C::PX];                  // this lane's window pixels inside the second image's region (ox = oy = 0)
+        {
+            const float ax = x1 - (float)ix1, ay = y1 - (float)iy1;
+            const float w11 = ax * ay, w01 = ax - w11, w10 = ay - w11, w00 = 1.f - ax - ay + w11;
+#pragma unroll
+            for (int i = 0; i < C::PX; i++) {
+                const int k = lane + 32 * i;
+                const bool on = k < W * W;
+                const int pr = on ? k / W : 0, pc = on ? k - pr * W : 0;
+                po[i] = pr * C::SP2 + pc;
+                pi[i] = (pr + RG) * C::NP2 + pc + RG;
+                T[i] = on ? bil(s + C::IN1 + (pr + RG) * C::NP1 + pc + RG, C::NP1, w00, w01, w10, w11) : 0.f;
+                Tgx[i] = on ? bil(s + C::GX1 + pr * C::SP1 + pc, C::SP1, w00, w01, w10, w11) : 0.f;
+                Tgy[i] = on ? bil(s + C::GY1 + pr * C::SP1 + pc, C::SP1, w00, w01, w10, w11) : 0.f;
+            }
+        }
+        for (;;) {
+            if (x2 - fhw < 0.f || fnc - (x2 + fhw) < 1.001f || y2 - fhw < 0.f || fnr - (y2 + fhw) < 1.001f) {
+                status = KLT_OOB;
+                break;
+            }
+            const int ix = (int)x2, iy = (int)y2;
+            int ox = ix - hw - rx0, oy = iy - hw - ry0;
+            if (ox < 0 || oy < 0 || ox > 2 * MARGIN || oy > 2 * MARGIN) {      // the window left the region: stage a new one
+                rx0 = ix - hw - MARGIN; ry0 = iy - hw - MARGIN;
+                __syncwarp();
+                stage_region<C::N2, C::NP2>(s + C::IN2, I2, pitch, nc, nr, rx0 - RG, ry0 - RG, lane);
+                cp_async_wait_all();
+                __syncwarp();
+                gradients2<W>(s, K, lane);
+                ox = MARGIN; oy = MARGIN;
+            }
+            const float ax = x2 - (float)ix, ay = y2 - (float)iy;
+            const float w11 = ax * ay, w01 = ax - w11, w10 = ay - w11, w00 = 1.f - ax - ay + w11;
+            const float *bi = s + C::IN2 + oy * C::NP2 + ox, *bx = s + C::GX2 + oy * C::SP2 + ox, *by = s + C::GY2 + oy * C::SP2 + ox;
+            float gxx = 0.f, gxy = 0.f, gyy = 0.f, ex = 0.f, ey = 0.f;
+#pragma unroll
+            for (int i = 0; i < C::PX; i++) {
+                if (lane + 32 * i < W * W) {
+                    const float P = bil(bi + pi[i], C::NP2, w00, w01, w10, w11);
+                    const float Px = bil(bx + po[i], C::SP2, w00, w01, w10, w11);
+                    const float Py = bil(by + po[i], C::SP2, w00, w01, w10, w11);
+                    const float diff = T[i] - P, gx = Tgx[i] + Px, gy = Tgy[i] + Py;
+                    gxx = fmaf(gx, gx, gxx); gxy = fmaf(gx, gy, gxy); gyy = fmaf(gy, gy, gyy);
+                    ex = fmaf(diff, gx, ex); ey = fmaf(diff, gy, ey);
+                }
+            }
+            gxx = warp_sum(gxx); gxy = warp_sum(gxy); gyy = warp_sum(gyy);
+            ex = warp_sum(ex) * A.step_factor; ey = warp_sum(ey) * A.step_factor;
+            const float det = __fsub_rn(__fmul_rn(gxx, gyy), __fmul_rn(gxy, gxy));
+            if (det < A.small_det) { status = KLT_SMALL_DET; break; }
+            const float dx = __fdiv_rn(__fsub_rn(__fmul_rn(gyy, ex), __fmul_rn(gxy, ey)), det);
+            const float dy = __fdiv_rn(__fsub_rn(__fmul_rn(gxx, ey), __fmul_rn(gxy, ex)), det);
+            x2 += dx; y2 += dy;
+            iteration++;
+            if (!((fabsf(dx) >= A.th || fabsf(dy) >= A.th) && iteration < A.max_iterations)) break;
+        }
+        my_iters += iteration;
+        {
+            const double x2d = (double)x2, y2d = (double)y2, hwd = W / 2.0;
+            if (x2d - hwd < 0.0 || (double)nc - (x2d + hwd) < 1.001 || y2d - hwd < 0.0 || (double)nr - (y2d + hwd) < 1.001)
+                status = KLT_OOB;
+        }
+        if (status == KLT_TRACKED && A.has_max_residue) {
+            const int ix = (int)x2, iy = (int)y2;
+            int ox = ix - hw - rx0, oy = iy - hw - ry0;
+            if (ox < 0 || oy < 0 || ox > 2 * MARGIN || oy > 2 * MARGIN) {
+                rx0 = ix - hw - MARGIN; ry0 = iy - hw - MARGIN;
+                __syncwarp();
+                stage_region<C::N2, C::NP2>(s + C::IN2, I2, pitch, nc, nr, rx0 - RG, ry0 - RG, lane);
+                cp_async_wait_all();
+                __syncwarp();
+                ox = MARGIN; oy = MARGIN;
+            }
+            const float ax = x2 - (float)ix, ay = y2 - (float)iy;
+            const float w11 = ax * ay, w01 = ax - w11, w10 = ay - w11, w00 = 1.f - ax - ay + w11;
+            const float *bi = s + C::IN2 + oy * C::NP2 + ox;
+            float res = 0.f;
+#pragma unroll
+            for (int i = 0; i < C::PX; i++)
+                if (lane + 32 * i < W * W) res += fabsf(T[i] - bil(bi + pi[i], C::NP2, w00, w01, w10, w11));
+            res = warp_sum(res) / (float)(W * W);
+            if (res > A.max_residue) status = KLT_LARGE_RESIDUE;
+        }
+        __syncwarp();                              // all lanes are done with the regions before the next level overwrites them
+        xout = (double)x2; yout = (double)y2;
+        if (A.retain) st = KLT_TRACKED;
+        else if (status == KLT_SMALL_DET || status == KLT_OOB || status == KLT_LARGE_RESIDUE) st = status;
+        else if (iteration >= A.max_iterations) st = KLT_MAX_ITERATIONS;
+        else st = KLT_TRACKED;
+        if (st == KLT_SMALL_DET || st == KLT_OOB) alive = false;                               // :284-285
+    }
+    if (lane == 0) {
+        if (my_iters) atomicAdd(iters_total, (unsigned long long)my_iters);
+        if (st == KLT_INTERNAL_ASSERT) return;
+        const int W0 = A.p1.lv[0].w, H0 = A.p1.lv[0].h;
+        const bool oob = xout < A.borderx || xout > (double)(W0 - 1) - A.borderx || yout < A.bordery ||
+                         yout > (double)(H0 - 1) - A.bordery;
+        if (st == KLT_OOB || oob) { xs[f] = -1.0; ys[f] = -1.0; vals[f] = KLT_OOB; }
+        else if (st == KLT_SMALL_DET || st == KLT_LARGE_RESIDUE || st == KLT_MAX_ITERATIONS) { xs[f] = -1.0; ys[f] = -1.0; vals[f] = st; }
+        else { xs[f] = xout; ys[f] = yout; vals[f] = KLT_TRACKED; }
+    }
+}
+
+template <int W>
+int launch_windowed(klt_ctx *ctx, const TrackArgs &A, const WindowedTaps &K, double *x, double *y, int32_t *v,
+                    unsigned long long *it, int *af) {
+    const int blocks = (A.total + LAZY_WARPS - 1) / LAZY_WARPS;
+    // algorithmic bytes: the staged regions of both images on every level (restaging not counted) + the feature records
+    const double bytes = (double)A.total * (A.n_levels * 4.0 * (Cfg<W>::N1 * Cfg<W>::N1 + Cfg<W>::N2 * Cfg<W>::N2) + 40.0);
+    const size_t smem = (size_t)LAZY_WARPS * Cfg<W>::FLOATS * sizeof(float);
+    if (smem > 48 * 1024) KLT_CUDA(ctx, cudaFuncSetAttribute(lk_windowed_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KLT_LAUNCH(ctx, "lk_windowed", bytes, (lk_windowed_kernel<W><<<blocks, LAZY_WARPS * 32, smem, ctx->stream>>>(A, K, x, y, v, it, af)));
+    return KLT_OK;
+}
+
+bool radius3(const klt_kernel1d &k) { return k.n == 2 * RG + 1; }
+void flip7(const klt_kernel1d &k, float *dst) { for (int j = 0; j < 7; j++) dst[j] = (float)k.taps[6 - j]; }
+
+}  // namespace
+
+bool klt_windowed_supported(const klt_params *p, const klt_pyr *p1, const klt_pyr *p2) {
+    if (p1->precision == KLT_PRECISION_STRICT || p2->precision == KLT_PRECISION_STRICT) return false;
+    if (p->window_width != p->window_height || (p->window_width & 1) == 0 || p->window_width < 3 || p->window_width > 15) return false;
+    if (!p1->hx || !p2->hx || !p1->hx->taps_valid || !p2->hx->taps_valid) return false;
+    return radius3(p1->hx->taps.grad_gauss) && radius3(p1->hx->taps.grad_deriv) && radius3(p2->hx->taps.grad_gauss) &&
+           radius3(p2->hx->taps.grad_deriv);
+}
+
+int klt_launch_track_windowed(klt_ctx *ctx, const TrackArgs &A, const klt_pyr *p1, const klt_pyr *p2, double *x_dev,
+                              double *y_dev, int32_t *val_dev, unsigned long long *iters_dev, int *assert_dev) {
+    WindowedTaps K;
+    flip7(p1->hx->taps.grad_gauss, K.g1); flip7(p1->hx->taps.grad_deriv, K.d1);
+    flip7(p2->hx->taps.grad_gauss, K.g2); flip7(p2->hx->taps.grad_deriv, K.d2);
+    switch (A.w) {
+        case 3: return launch_windowed<3>(ctx, A, K, x_dev, y_dev, val_dev, iters_dev, assert_dev);
+        case 5: return launch_windowed<5>(ctx, A, K, x_dev, y_dev, val_dev, iters_dev, assert_dev);
+        case 7: return launch_windowed<7>(ctx, A, K, x_dev, y_dev, val_dev, iters_dev, assert_dev);
+        case 9: return launch_windowed<9>(ctx, A, K, x_dev, y_dev, val_dev, iters_dev, assert_dev);
+        case 11: return launch_windowed<11>(ctx, A, K, x_dev, y_dev, val_dev, iters_dev, assert_dev);
+        case 13: return launch_windowed<13>(ctx, A, K, x_dev, y_dev, val_dev, iters_dev, assert_dev);
+        case 15: return launch_windowed<15>(ctx, A, K, x_dev, y_dev, val_dev, iters_dev, assert_dev);
+    }
+    return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "windowed tracking: window %d not covered", A.w);
+}

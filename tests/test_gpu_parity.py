@@ -299,10 +299,11 @@ def test_full_size_configs(gpu_ctx, oracle, cfg):
     tf.KLTTrackFeatures(tc, imgs[0], imgs[1], f)
     assert_features_equal(fl_arrays(f), want_trk)
     assert (want_trk[2] == 0).mean() > 0.95
-    config.set_precision(track="fast")
-    f = sgf.KLTSelectGoodFeatures(tc, imgs[0], cfg["n"])
-    tf.KLTTrackFeatures(tc, imgs[0], imgs[1], f)
-    assert_features_close(fl_arrays(f), want_trk)
+    for mode in ("fast", "windowed"):
+        config.set_precision(track=mode)
+        f = sgf.KLTSelectGoodFeatures(tc, imgs[0], cfg["n"])
+        tf.KLTTrackFeatures(tc, imgs[0], imgs[1], f)
+        assert_features_close(fl_arrays(f), want_trk)
 
 
 def test_batched_pairs_match_single(gpu_ctx, oracle):
@@ -524,7 +525,7 @@ def test_tracking_window_and_pyramid_variants(gpu_ctx, oracle, win, L, ss, shape
     n = 80
     want_sel = oracle.select_good_features(p, imgs[0], n)
     want_trk = oracle.track_features(p, imgs[0], imgs[1], *want_sel)[:3]
-    for mode in ("strict", "fast"):
+    for mode in ("strict", "fast", "windowed"):
         config.set_precision(track=mode)
         f = sgf.KLTSelectGoodFeatures(tc, imgs[0], n)
         assert_features_equal(fl_arrays(f), want_sel)
@@ -552,7 +553,7 @@ def test_random_feature_positions_and_dead_features(gpu_ctx, oracle):
     y = rng.uniform(16, 300 - 17, n).astype(np.float32).astype(np.float64)
     v = np.where(rng.random(n) < 0.2, rng.integers(-5, 0, n), rng.integers(0, 500, n)).astype(np.int32)
     want = oracle.track_features(p, imgs[0], imgs[1], x, y, v)[:3]
-    for mode in ("strict", "fast"):
+    for mode in ("strict", "fast", "windowed"):
         config.set_precision(track=mode)
         fl_ = []
         for i in range(n):
@@ -591,3 +592,68 @@ def test_selection_edge_cases(gpu_ctx, oracle):
         tc = make_tc(**kw)
         assert_features_equal(fl_arrays(sgf.KLTSelectGoodFeatures(tc, imgs[0], 60)), oracle.select_good_features(p, imgs[0], 60))
     assert sgf.KLTSelectGoodFeatures(make_tc(), imgs[0], 0) == []
+
+
+def test_windowed_pyramids_build_gradients_on_demand(gpu_ctx, oracle):
+    """KLT_PRECISION_FAST_WINDOWED: image-only pyramids; a gradient plane asked for later equals the FAST build's, the
+    windowed tracker agrees with the plane-based FAST tracker, and the affine tracker still works on such pyramids."""
+    from pyfeaturetrack_b200 import _capi, trackFeatures, selectGoodFeatures as sgf
+    H, W, L, ss, n = 360, 488, 3, 2, 300
+    a, c = _synth(77, (H, W), shift=(2.2, -1.4))
+    kw = dict(nPyramidLevels=L, subsampling=ss, max_residue=10.0)
+    tc = make_tc(**kw)
+    p = P(oracle, **kw)
+    taps = trackFeatures._taps_for_one_image(tc)
+    params = sgf.make_params(tc)
+    sel = oracle.select_good_features(p, a, n)
+    res = {}
+    for name, prec in (("fast", _capi.PRECISION_FAST), ("windowed", _capi.PRECISION_FAST_WINDOWED)):
+        p1 = _capi.Pyramid(gpu_ctx, W, H, L, ss, 1)
+        p2 = _capi.Pyramid(gpu_ctx, W, H, L, ss, 1)
+        p1.build_u8(a, taps, prec)
+        p2.build_u8(c, taps, prec)
+        x, y, v = (np.array(z) for z in sel)
+        gpu_ctx.check(_capi.lib().klt_track_features(gpu_ctx.handle, C.byref(params), p1.handle, p2.handle, n,
+                                                     x.ctypes.data, y.ctypes.data, v.ctypes.data, None))
+        res[name] = (x, y, v, [p2.download(0, l) for l in range(L)], [p2.download(1, l) for l in range(L)],
+                     [p2.download(2, l) for l in range(L)])
+        p1.close(); p2.close()
+    f, w = res["fast"], res["windowed"]
+    for l in range(L):
+        assert np.array_equal(f[3][l], w[3][l]) or np.abs(f[3][l] - w[3][l]).max() <= 1e-4      # same smoothing arithmetic
+        for k in (4, 5):                                                                        # planes built on demand
+            assert np.abs(f[k][l] - w[k][l]).max() <= 1e-5 * np.abs(f[k][l]).max()
+    assert np.mean(f[2] == w[2]) >= 0.995
+    both = (f[2] == 0) & (w[2] == 0)
+    assert both.sum() > 0.8 * n
+    assert np.abs(f[0][both] - w[0][both]).max() <= 1e-3 and np.abs(f[1][both] - w[1][both]).max() <= 1e-3
+    want = oracle.track_features(p, a, c, *sel)[:3]
+    assert_features_close((w[0], w[1], w[2]), want)
+
+
+def test_windowed_sequence_and_affine(gpu_ctx, oracle):
+    """sequentialMode (pyramid reuse) and the affine consistency check on image-only pyramids follow the FAST path."""
+    from pyfeaturetrack_b200 import selectGoodFeatures as sgf, trackFeatures as tf, config
+    frames = [synth_frame(k) for k in range(4)]
+    out = {}
+    for mode in ("fast", "windowed"):
+        for affine in (-1, 2):
+            config.set_precision(track=mode)
+            tc = make_tc(nPyramidLevels=2, subsampling=2, max_residue=10.0)
+            tc.sequentialMode = True
+            tc.affineConsistencyCheck = affine
+            f = sgf.KLTSelectGoodFeatures(tc, frames[0], 120)
+            for k in range(1, 4):                 # no replacement: one status flip would reshuffle every later slot
+                tf.KLTTrackFeatures(tc, frames[k - 1], frames[k], f)
+            out[(mode, affine)] = fl_arrays(f)
+    for affine in (-1, 2):
+        a, b = out[("fast", affine)], out[("windowed", affine)]
+        assert np.mean(a[2] == b[2]) >= 0.97
+        same = (a[2] == b[2])
+        assert np.abs(a[0][same] - b[0][same]).max() <= 2e-3 and np.abs(a[1][same] - b[1][same]).max() <= 2e-3
+
+
+def synth_frame(k, shape=(300, 400)):
+    from pyfeaturetrack_b200 import synth
+    base = _synth(5, (shape[0] + 16, shape[1] + 16))[0]
+    return np.ascontiguousarray(base[k:k + shape[0], 2 * k:2 * k + shape[1]])
