@@ -47,17 +47,32 @@ __device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// issue the copies of the N x N input region whose top-left pixel is (sx0, sy0) (SciPy 'reflect' outside the image)
+// issue the copies of the N x N input region whose top-left pixel is (sx0, sy0) (SciPy 'reflect' outside the image).
+// Interior regions (the common case): half-warp h copies rows h, h+2, ... -- lane column fixed, one pointer bump per
+// row, no index arithmetic; columns beyond 16 go through a short flat loop.
 template <int N, int NP>
 __device__ __forceinline__ void stage_region(float *__restrict__ dst, const float *__restrict__ img, int pitch, int nc, int nr,
                                              int sx0, int sy0, int lane) {
     const bool interior = sx0 >= 0 && sy0 >= 0 && sx0 + N <= nc && sy0 + N <= nr;       // warp-uniform
     if (interior) {
         const float *src = img + (size_t)sy0 * pitch + sx0;
+        constexpr int C0 = N < 16 ? N : 16;
+        const int half = lane >> 4, col = lane & 15;
+        if (col < C0) {
+            const float *p = src + half * pitch + col;
+            float *q = dst + half * NP + col;
 #pragma unroll
-        for (int idx = lane; idx < N * N; idx += 32) {
-            const int ry = idx / N, rx = idx - ry * N;
-            cp_async4(dst + ry * NP + rx, src + ry * pitch + rx);
+            for (int ry = 0; ry < N; ry += 2) {
+                if (ry + 1 < N || half == 0) cp_async4(q + ry * NP, p + ry * pitch);
+            }
+        }
+        if (N > 16) {
+            constexpr int REM = N - 16;
+#pragma unroll
+            for (int idx = lane; idx < REM * N; idx += 32) {
+                const int ry = idx / REM, rx = 16 + idx - ry * REM;
+                cp_async4(dst + ry * NP + rx, src + ry * pitch + rx);
+            }
         }
     } else {
 #pragma unroll 1
@@ -85,10 +100,34 @@ __device__ __forceinline__ void hrow(const float *__restrict__ row, float *__res
     }
 }
 
-// vertical pass: lane = (plane, column); gx = gauss_v(deriv_h), gy = deriv_v(gauss_h)
+// vertical pass: gx = gauss_v(deriv_h) on the lower half-warp, gy = deriv_v(gauss_h) on the upper one, lane = column
+// (tv = this lane's vertical taps: gauss for the lower half-warp, deriv for the upper one)
 template <int S, int SP>
 __device__ __forceinline__ void vpass(const float *__restrict__ td, const float *__restrict__ tg, float *__restrict__ gx,
-                                      float *__restrict__ gy, const float (&g)[7], const float (&d)[7], int lane) {
+                                      float *__restrict__ gy, const float (&tv)[7], int lane) {
+    constexpr int N = S + 2 * RG;
+    static_assert(S <= 16, "one column per lane of a half-warp");
+    const bool second = lane >= 16;
+    const int col = lane & 15;
+    if (col < S) {
+        const float *src = (second ? tg : td) + col;
+        float *dst = (second ? gy : gx) + col;
+        float v[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) v[i] = src[i * SP];
+#pragma unroll
+        for (int r = 0; r < S; r++) {
+            float o = tv[0] * v[r];
+#pragma unroll
+            for (int j = 1; j < 7; j++) o = fmaf(tv[j], v[r + j], o);
+            dst[r * SP] = o;
+        }
+    }
+}
+// windows too wide for a half-warp: lane = (plane, column), several rounds
+template <int S, int SP>
+__device__ __forceinline__ void vpass_wide(const float *__restrict__ td, const float *__restrict__ tg, float *__restrict__ gx,
+                                           float *__restrict__ gy, const float (&g)[7], const float (&d)[7], int lane) {
     constexpr int N = S + 2 * RG;
 #pragma unroll
     for (int item = lane; item < 2 * S; item += 32) {
@@ -111,43 +150,56 @@ __device__ __forceinline__ void vpass(const float *__restrict__ td, const float 
         }
     }
 }
+template <int S, int SP>
+__device__ __forceinline__ void vpass_any(const float *td, const float *tg, float *gx, float *gy, const float (&g)[7],
+                                          const float (&d)[7], const float (&tv)[7], int lane) {
+    if constexpr (S <= 16) vpass<S, SP>(td, tg, gx, gy, tv, lane);
+    else vpass_wide<S, SP>(td, tg, gx, gy, g, d, lane);
+}
 
 // gradients of the staged second-image region (also the re-staging path)
 template <int W>
-__device__ __forceinline__ void gradients2(float *__restrict__ s, const WindowedTaps &K, int lane) {
+__device__ __forceinline__ void gradients2(float *__restrict__ s, const WindowedTaps &K, const float (&tv2)[7], int lane) {
     using C = Cfg<W>;
     if (lane < C::N2) hrow<C::S2>(s + C::IN2 + lane * C::NP2, s + C::TD2 + lane * C::SP2, s + C::TG2 + lane * C::SP2, K.g2, K.d2, C::S2);
     __syncwarp();
-    vpass<C::S2, C::SP2>(s + C::TD2, s + C::TG2, s + C::GX2, s + C::GY2, K.g2, K.d2, lane);
+    vpass_any<C::S2, C::SP2>(s + C::TD2, s + C::TG2, s + C::GX2, s + C::GY2, K.g2, K.d2, tv2, lane);
+    __syncwarp();
+}
+template <int W>
+__device__ __forceinline__ void gradients1(float *__restrict__ s, const WindowedTaps &K, const float (&tv1)[7], int lane) {
+    using C = Cfg<W>;
+    if (lane < C::N1) hrow<C::S1>(s + C::IN1 + lane * C::NP1, s + C::TD1 + lane * C::SP1, s + C::TG1 + lane * C::SP1, K.g1, K.d1, C::S1);
+    __syncwarp();
+    vpass_any<C::S1, C::SP1>(s + C::TD1, s + C::TG1, s + C::GX1, s + C::GY1, K.g1, K.d1, tv1, lane);
     __syncwarp();
 }
 
-// gradients of both staged regions of a level
+// gradients of both staged regions of a level.  same_taps: both images were built with the same gradient kernels (always,
+// unless the reference's kernel cache handed them different ones) -- then one lane per row of BOTH regions runs one
+// code path with the taps as constant-bank operands.
 template <int W>
-__device__ __forceinline__ void gradients_both(float *__restrict__ s, const WindowedTaps &K, int lane) {
+__device__ __forceinline__ void gradients_both(float *__restrict__ s, const WindowedTaps &K, const float (&tv1)[7],
+                                               const float (&tv2)[7], bool same_taps, int lane) {
     using C = Cfg<W>;
-    if (C::MERGED) {
-        // lanes [0, N2): rows of the second image's region; lanes [N2, N2+N1): rows of the first image's.  One code path:
-        // the first-image lanes run the S2-wide loop and keep their first S1 outputs (their reads past the row end stay
-        // inside the warp's buffer).
+    if (C::MERGED && same_taps) {
+        // lanes [0, N2): rows of the second image's region; lanes [N2, N2+N1): rows of the first image's.  The first-image
+        // lanes run the S2-wide loop and keep their first S1 outputs (their reads past the row end stay inside the buffer).
         const bool second = lane < C::N2;
         const int row = second ? lane : lane - C::N2;
         if (second || row < C::N1) {
             const float *src = s + (second ? C::IN2 + row * C::NP2 : C::IN1 + row * C::NP1);
             float *td = s + (second ? C::TD2 + row * C::SP2 : C::TD1 + row * C::SP1);
             float *tg = s + (second ? C::TG2 + row * C::SP2 : C::TG1 + row * C::SP1);
-            float g[7], d[7];
-#pragma unroll
-            for (int j = 0; j < 7; j++) { g[j] = second ? K.g2[j] : K.g1[j]; d[j] = second ? K.d2[j] : K.d1[j]; }
-            hrow<C::S2>(src, td, tg, g, d, second ? C::S2 : C::S1);
+            hrow<C::S2>(src, td, tg, K.g2, K.d2, second ? C::S2 : C::S1);
         }
     } else {
         if (lane < C::N2) hrow<C::S2>(s + C::IN2 + lane * C::NP2, s + C::TD2 + lane * C::SP2, s + C::TG2 + lane * C::SP2, K.g2, K.d2, C::S2);
         if (lane < C::N1) hrow<C::S1>(s + C::IN1 + lane * C::NP1, s + C::TD1 + lane * C::SP1, s + C::TG1 + lane * C::SP1, K.g1, K.d1, C::S1);
     }
     __syncwarp();
-    vpass<C::S2, C::SP2>(s + C::TD2, s + C::TG2, s + C::GX2, s + C::GY2, K.g2, K.d2, lane);
-    vpass<C::S1, C::SP1>(s + C::TD1, s + C::TG1, s + C::GX1, s + C::GY1, K.g1, K.d1, lane);
+    vpass_any<C::S2, C::SP2>(s + C::TD2, s + C::TG2, s + C::GX2, s + C::GY2, K.g2, K.d2, tv2, lane);
+    vpass_any<C::S1, C::SP1>(s + C::TD1, s + C::TG1, s + C::GX1, s + C::GY1, K.g1, K.d1, tv1, lane);
     __syncwarp();
 }
 
@@ -192,6 +244,15 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
     int st = KLT_TRACKED;
     unsigned int my_iters = 0;
     bool alive = true;
+    // this lane's vertical taps (lower half-warp: gauss -> gradx, upper: deriv -> grady) and whether both images share them
+    float tv1[7], tv2[7];
+    bool same_taps = true;
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+        tv1[j] = lane >= 16 ? K.d1[j] : K.g1[j];
+        tv2[j] = lane >= 16 ? K.d2[j] : K.g2[j];
+        same_taps = same_taps && K.g1[j] == K.g2[j] && K.d1[j] == K.d2[j];
+    }
 
     for (int r = A.n_levels - 1; r >= 0; r--) {
         xloc *= ss; yloc *= ss; xout *= ss; yout *= ss;
@@ -227,12 +288,9 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
         }
         cp_async_wait_all();
         __syncwarp();
-        if (start_inside) gradients_both<W>(s, K, lane);
+        if (start_inside) gradients_both<W>(s, K, tv1, tv2, same_taps, lane);
         else {
-            if (lane < C::N1) hrow<C::S1>(s + C::IN1 + lane * C::NP1, s + C::TD1 + lane * C::SP1, s + C::TG1 + lane * C::SP1, K.g1, K.d1, C::S1);
-            __syncwarp();
-            vpass<C::S1, C::SP1>(s + C::TD1, s + C::TG1, s + C::GX1, s + C::GY1, K.g1, K.d1, lane);
-            __syncwarp();
+            gradients1<W>(s, K, tv1, lane);
             rx0 = -0x40000000;                     // nothing staged for the second image (the loop exits with OOB at once)
         }
         // template: the first image's window, gradients interpolated like the image (trackFeatures.py:87-92)
@@ -266,7 +324,7 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
                 stage_region<C::N2, C::NP2>(s + C::IN2, I2, pitch, nc, nr, rx0 - RG, ry0 - RG, lane);
                 cp_async_wait_all();
                 __syncwarp();
-                gradients2<W>(s, K, lane);
+                gradients2<W>(s, K, tv2, lane);
                 ox = MARGIN; oy = MARGIN;
             }
             const float ax = x2 - (float)ix, ay = y2 - (float)iy;
