@@ -209,56 +209,39 @@ stream_level0_kernel(const unsigned char *__restrict__ frames, size_t pitch, siz
 }
 
 // ---- level 0 of an image-only pyramid: u8 frame -> smoothed image (KLT_PRECISION_FAST_WINDOWED) -----------------------
-// Same strip/lane geometry and load pipeline as stream_level0_kernel without the gradient stage: 1 B read + 4 B written
-// per pixel, 2*(2*RS+1) FMAs.
-template <int RS>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8)
-stream_smooth0_kernel(const unsigned char *__restrict__ frames, size_t pitch, size_t frame_stride, float *__restrict__ img,
-                      int out_pitch, size_t out_stride, int W, int H, int rows_per_seg, int n_strips,
-                      const __grid_constant__ StreamTaps T) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int strip = blockIdx.x * WARPS_PER_CTA + warp;
-    if (strip >= n_strips) return;
-    const int ys = blockIdx.y * rows_per_seg, ye = min(H, ys + rows_per_seg);
-    const int c = strip * 120 + 4 * (lane - 1);
-    const unsigned char *src = frames + (size_t)blockIdx.z * frame_stride;
-    bool rv0, rvl, rvr;
-    const int m0 = mirror_quad(c, W, rv0), ml = mirror_quad(c - 4, W, rvl), mr = mirror_quad(c + 4, W, rvr);
-    const unsigned char *b0 = src + m0, *bl = src + ml, *br = src + mr;
-    const unsigned int sel0 = rv0 ? 0x0123u : 0x3210u, sell = rvl ? 0x0123u : 0x3210u, selr = rvr ? 0x0123u : 0x3210u;
-    const bool writer = lane >= 1 && lane <= 30 && c < W;
-    float *p_img = img + (size_t)blockIdx.z * out_stride + (size_t)c + (size_t)ys * out_pitch;
-    const unsigned int upitch = (unsigned int)pitch;
+// Same strip/lane geometry as stream_level0_kernel without the gradient stage: 1 B read + 4 B written per pixel,
+// 2*(2*RS+1) FMAs.  With so little arithmetic per byte the kernel is bound by instruction issue, so the row loop is kept
+// minimal: each lane loads and converts only its own quad (the RS neighbour columns come from the adjacent lanes by
+// shuffle), and segments that do not touch the top/bottom border walk a running row pointer (no reflection arithmetic).
+template <int RS, bool INTERIOR>
+__device__ __forceinline__ void smooth0_rows(const unsigned char *__restrict__ b0, unsigned int sel0, unsigned int upitch, int H,
+                                             int ys, int t0, int t1, bool writer, float *__restrict__ p_img, int out_pitch,
+                                             const StreamTaps &T) {
     float sa[4][2 * RS];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int m = 0; m < 2 * RS; m++) sa[i][m] = 0.f;
-    const int t0 = ys - RS, t1 = ye + RS;
-    unsigned int w0, wl, wr;
-    {
-        const unsigned int ro = (unsigned int)reflect1(t0, H) * upitch;
-        w0 = __ldg(reinterpret_cast<const unsigned int *>(b0 + ro));
-        wl = __ldg(reinterpret_cast<const unsigned int *>(bl + ro));
-        wr = __ldg(reinterpret_cast<const unsigned int *>(br + ro));
-    }
+    const unsigned char *pr = b0 + (INTERIOR ? (size_t)t0 * upitch : (size_t)reflect1(t0, H) * upitch);
+    unsigned int w0 = __ldg(reinterpret_cast<const unsigned int *>(pr));
     for (int t = t0; t < t1; t++) {
-        const unsigned int q0 = __byte_perm(w0, 0u, sel0), ql = __byte_perm(wl, 0u, sell), qr = __byte_perm(wr, 0u, selr);
+        const unsigned int q0 = __byte_perm(w0, 0u, sel0);
         float u[4 + 2 * RS];
 #pragma unroll
         for (int i = 0; i < 4; i++) u[RS + i] = u8_to_f32(q0, i);
-#pragma unroll
-        for (int k = 0; k < RS; k++) {
-            u[k] = u8_to_f32(ql, 4 - RS + k);
-            u[RS + 4 + k] = u8_to_f32(qr, k);
-        }
-        {
-            const unsigned int ro = (unsigned int)reflect1(min(t + 1, t1 - 1), H) * upitch;
-            w0 = __ldg(reinterpret_cast<const unsigned int *>(b0 + ro));
-            wl = __ldg(reinterpret_cast<const unsigned int *>(bl + ro));
-            wr = __ldg(reinterpret_cast<const unsigned int *>(br + ro));
+        if (INTERIOR) {
+            pr += upitch;                                              // one row past the segment is still inside the image
+            w0 = __ldg(reinterpret_cast<const unsigned int *>(pr));
+            prefetch_l2(pr + (PREFETCH_ROWS - 1) * upitch);
+        } else {
+            w0 = __ldg(reinterpret_cast<const unsigned int *>(b0 + (unsigned int)reflect1(min(t + 1, t1 - 1), H) * upitch));
             const int tp = t + PREFETCH_ROWS;
             if (tp < t1) prefetch_l2(b0 + (unsigned int)reflect1(tp, H) * upitch);
+        }
+#pragma unroll
+        for (int k = 0; k < RS; k++) {
+            u[k] = __shfl_up_sync(FULLMASK, u[4 + k], 1);               // columns c-RS .. c-1: the left lane's last RS
+            u[RS + 4 + k] = __shfl_down_sync(FULLMASK, u[RS + k], 1);   // columns c+4 .. c+3+RS: the right lane's first RS
         }
         float s[4];
 #pragma unroll
@@ -273,6 +256,29 @@ stream_smooth0_kernel(const unsigned char *__restrict__ frames, size_t pitch, si
             p_img += out_pitch;
         }
     }
+}
+
+template <int RS>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8)
+stream_smooth0_kernel(const unsigned char *__restrict__ frames, size_t pitch, size_t frame_stride, float *__restrict__ img,
+                      int out_pitch, size_t out_stride, int W, int H, int rows_per_seg, int n_strips,
+                      const __grid_constant__ StreamTaps T) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x * WARPS_PER_CTA + warp;
+    if (strip >= n_strips) return;
+    const int ys = blockIdx.y * rows_per_seg, ye = min(H, ys + rows_per_seg);
+    const int c = strip * 120 + 4 * (lane - 1);
+    const unsigned char *src = frames + (size_t)blockIdx.z * frame_stride;
+    bool rv0;
+    const int m0 = mirror_quad(c, W, rv0);
+    const unsigned char *b0 = src + m0;
+    const unsigned int sel0 = rv0 ? 0x0123u : 0x3210u;
+    const bool writer = lane >= 1 && lane <= 30 && c < W;
+    float *p_img = img + (size_t)blockIdx.z * out_stride + (size_t)c + (size_t)ys * out_pitch;
+    const int t0 = ys - RS, t1 = ye + RS;
+    // interior: every row the loop loads or prefetches, [t0, t1 + PREFETCH_ROWS), lies inside the frame
+    if (t0 >= 0 && t1 + PREFETCH_ROWS <= H) smooth0_rows<RS, true>(b0, sel0, (unsigned int)pitch, H, ys, t0, t1, writer, p_img, out_pitch, T);
+    else smooth0_rows<RS, false>(b0, sel0, (unsigned int)pitch, H, ys, t0, t1, writer, p_img, out_pitch, T);
 }
 
 // ---- gradients only: float image -> gradx, grady (levels >= 1) ---------------------------------------------------
