@@ -4,7 +4,7 @@ strict : convolutions accumulate in float64 in SciPy's exact operation order -> 
          tracked positions and status codes are bit-identical to the reference's.
 fast   : float32 FMA convolutions (images within ~5e-7 relative-to-max of the reference's); tracking then
          agrees to ~1e-4 px.  Selection order is sensitive to the last bit of the gradients,
-         so selection and the operator-level functions default to strict; tracking defaults to fast.
+         so selection and the operator-level functions default to strict; tracking defaults to windowed.
 windowed : (tracking only) fast arithmetic on image-only pyramids: the gradient planes are not written; the tracker
          evaluates the gradient pair inside the windows the features visit.  Same results as fast to ~1e-5 px;
          anything that asks for a gradient plane builds it on demand.
@@ -18,7 +18,7 @@ _TRACK_MODES = dict(_MODES, windowed=_capi.PRECISION_FAST_WINDOWED)
 
 operator_precision = os.environ.get("KLT_B200_OPERATOR_PRECISION", "strict")
 select_precision = os.environ.get("KLT_B200_SELECT_PRECISION", "strict")
-track_precision = os.environ.get("KLT_B200_TRACK_PRECISION", "fast")
+track_precision = os.environ.get("KLT_B200_TRACK_PRECISION", "windowed")
 
 
 def set_precision(track=None, select=None, operator=None):

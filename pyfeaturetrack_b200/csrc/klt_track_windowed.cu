@@ -33,7 +33,8 @@ struct Cfg {
     static constexpr int S1 = W + 1, N1 = S1 + 2 * RG, NP1 = N1 | 1, SP1 = S1 | 1;      // odd pitches: conflict-free
     static constexpr int S2 = W + 1 + 2 * MARGIN, N2 = S2 + 2 * RG, NP2 = N2 | 1, SP2 = S2 | 1;
     // per-warp shared memory (floats): staged input, horizontal results (deriv, gauss), gradx, grady of both regions
-    static constexpr int IN1 = 0, TD1 = IN1 + N1 * NP1, TG1 = TD1 + N1 * SP1, GX1 = TG1 + N1 * SP1, GY1 = GX1 + S1 * SP1;
+    // (IN1 is padded: in the merged horizontal pass the first image's lanes read N2 values of their N1-wide rows)
+    static constexpr int IN1 = 0, TD1 = IN1 + N1 * NP1 + (N2 - N1), TG1 = TD1 + N1 * SP1, GX1 = TG1 + N1 * SP1, GY1 = GX1 + S1 * SP1;
     static constexpr int IN2 = GY1 + S1 * SP1, TD2 = IN2 + N2 * NP2, TG2 = TD2 + N2 * SP2, GX2 = TG2 + N2 * SP2, GY2 = GX2 + S2 * SP2;
     static constexpr int FLOATS = GY2 + S2 * SP2;
     static constexpr int PX = (W * W + 31) / 32;                         // window pixels per lane
