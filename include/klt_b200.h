@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KLT_B200_ABI_VERSION 2
+#define KLT_B200_ABI_VERSION 3
 #define KLT_MAX_TAPS 71   /* convolve.py:28 maxKernelWidth */
 #define KLT_MAX_LEVELS 8
 
@@ -57,8 +57,8 @@ typedef enum klt_status {
 #define KLT_PRECISION_STRICT 1 /* fp64 accumulation in SciPy's exact operation order: bit-identical images */
 /* FAST arithmetic, pyramid builds only: write the intensity planes and skip the gradient planes.  klt_track_features
  * then evaluates the gradient pair (convolve.py:245-246) inside the windows the features visit, in shared memory;
- * anything that asks for a gradient plane (klt_pyr_download, klt_pyr_level_ptr, the affine tracker, window sizes or
- * gradient kernels the windowed tracker does not cover) builds the planes on demand, so results never depend on it. */
+ * anything that asks for a gradient plane (klt_pyr_download, klt_pyr_ensure_gradients, the affine tracker, window sizes
+ * or gradient kernels the windowed tracker does not cover) builds the planes on demand, so results never depend on it. */
 #define KLT_PRECISION_FAST_WINDOWED 2
 
 typedef struct klt_ctx klt_ctx; /* one per (device, stream) */
@@ -161,8 +161,13 @@ int klt_pyr_build_f32(klt_ctx *ctx, klt_pyr *pyr, const float *images, size_t pi
                       const klt_taps *taps, int precision, int already_smoothed);
 /* which: 0 = intensity, 1 = gradx, 2 = grady.  out: float32 [h_level][w_level] contiguous, host or device. */
 int klt_pyr_download(klt_ctx *ctx, const klt_pyr *pyr, int image, int which, int level, float *out);
-/* device pointer of a level (for callers that keep working on the device) */
+/* device pointer of a level (for callers that keep working on the device).  A gradient plane of an image-only
+ * (KLT_PRECISION_FAST_WINDOWED) pyramid does not exist until klt_pyr_ensure_gradients or klt_pyr_download has built
+ * it: KLT_ERR_UNSUPPORTED until then. */
 int klt_pyr_level_ptr(const klt_pyr *pyr, int image, int which, int level, const float **ptr);
+/* Build the gradient planes of an image-only pyramid with the kernels of its last build (_KLTComputeGradients per
+ * level, trackFeatures.py:171-176); no-op when they are valid. */
+int klt_pyr_ensure_gradients(klt_ctx *ctx, klt_pyr *pyr);
 
 /* ---- selection: replaces goodFeaturesUtils.ScanImageForGoodFeatures (goodFeaturesUtils.pyx:35-73),
  * the sort (selectGoodFeatures.py:234-236) and _enforceMinimumDistance (selectGoodFeatures.py:45-135).

@@ -88,6 +88,7 @@ SIGNATURES = {
     "klt_pyr_build_f32": (_i, [_vp, _vp, _fp, _sz, _sz, C.POINTER(Taps), _i, _i]),
     "klt_pyr_download": (_i, [_vp, _vp, _i, _i, _i, _fp]),
     "klt_pyr_level_ptr": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),
+    "klt_pyr_ensure_gradients": (_i, [_vp, _vp]),
     "klt_scan_good_features": (_i, [_vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _fp]),
     "klt_select_good_features": (_i, [_vp, C.POINTER(Params), _vp, _i, _fp, _fp, _i, _i, _i, _i, _dp, _dp, _ip,
                                       C.POINTER(C.c_int64)]),

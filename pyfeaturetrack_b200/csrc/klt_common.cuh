@@ -113,8 +113,6 @@ int klt_ws_reserve(klt_ctx *ctx, size_t bytes);          // grow-only workspace
 bool klt_is_device_ptr(const void *p);
 
 static inline bool klt_pyr_has_gradients(const klt_pyr *p) { return !p->hx || p->hx->grad_valid; }
-// build the gradient planes of an image-only pyramid (no-op when they are valid)
-extern "C" int klt_pyr_ensure_gradients(klt_ctx *ctx, klt_pyr *p);
 
 int klt_make_taps(klt_ctx *ctx, const klt_kernel1d *k, TapsF *f, TapsD *d);
 
