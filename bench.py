@@ -146,15 +146,18 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     rank, world, local = dist_env()
+    # stdout carries exactly one JSON line: anything a library prints meanwhile (NCCL's "NCCL version ..." banner is
+    # written to fd 1 at NCCL_DEBUG=VERSION and WARN) goes to stderr; the JSON line is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from pyfeaturetrack_b200 import _capi, klt, trackFeatures, selectGoodFeatures as sgf, config
+    from pyfeaturetrack_b200 import _capi, klt, trackFeatures, selectGoodFeatures as sgf, config, shard
     sgf.KLT_verbose = 0
     trackFeatures.KLT_verbose = 0
+    host_cpus = shard.bind_host_to_gpu(local) if not args.no_bind else 0      # before any pinned allocation
     _capi.set_device(local)
     ctx = _capi.default_ctx()
     lib = _capi.lib()
@@ -366,7 +369,7 @@ def run_b200(args):
         "data": "synthetic",
         "frame_pairs_per_sec": round(pairs_all / step_s, 2),
         "config": {"workload": wl["name"], "pairs_per_step_per_gpu": B, "features_per_pair": n, "distinct_pairs": args.distinct,
-                   "precision": args.precision, "parallelism": "independent frame pairs sharded %d-way, no collective" % world,
+                   "precision": args.precision, "host_cpus_bound_per_rank": host_cpus, "parallelism": "independent frame pairs sharded %d-way, no collective" % world,
                    "l2": "no flush needed: each step streams %.0f MB of pyramids per GPU (> 126 MB L2); inputs %.0f MB" %
                          ((p1.nbytes() + p2.nbytes()) / 1e6, 2 * frame_bytes / 1e6)},
         "e2e": {"value": round(e2e_tracked_all / e2e_s, 1), "unit": "tracked features/s",
@@ -397,7 +400,10 @@ def run_b200(args):
         out["select"] = select_timing(wl, distinct, klt, sgf, ctx, args.api_pairs)
         out["sequence_api"] = sequence_timing(wl, klt, sgf, trackFeatures, max(6, args.api_pairs))
         out["sequence_api_affine"] = sequence_timing(wl, klt, sgf, trackFeatures, max(6, args.api_pairs), affine=2)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     print(json.dumps(out))
+    sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
@@ -621,6 +627,7 @@ def main():
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=32, help="independent frame pairs per step per GPU")
     ap.add_argument("--distinct", type=int, default=4, help="distinct seeded pairs generated per rank (tiled to --pairs)")
+    ap.add_argument("--no-bind", action="store_true", help="do not pin the process to the CPUs local to its GPU")
     ap.add_argument("--precision", default="windowed", choices=["fast", "strict", "windowed"],
                     help="windowed (default): fast arithmetic on image-only pyramids; fast: dense gradient planes; strict: bit-exact")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -33,3 +33,28 @@ def gather_features(local, n_units, n_features, dist=None, device=None):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         out.append(t.cpu().numpy())
     return out[0], out[1], out[2].astype(np.int32)
+
+
+def bind_host_to_gpu(device_index):
+    """Pin this process to the CPUs that are local to its GPU (NVML's ideal CPU affinity = the GPU's NUMA node), so that
+    the pinned staging buffers it allocates afterwards and the threads that fill them sit on the memory controller next
+    to the GPU's PCIe root.  With one process per GPU this keeps N uploads from crowding one socket's memory.
+    Returns the number of CPUs bound to, or 0 when NVML / the affinity call is unavailable (nothing changes then)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        bus = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0

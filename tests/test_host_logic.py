@@ -176,3 +176,23 @@ def test_write_feature_list_roundtrip(tmp_path, img01):
     from PIL import Image
     rgb = np.array(Image.open(str(tmp_path / "f.ppm")))
     assert tuple(rgb[20, 11]) == (255, 0, 0) and tuple(rgb[22, 12]) != (255, 0, 0)     # feature 0 drawn, feature 1 (lost) not
+
+
+def test_precision_modes_and_host_binding():
+    """config: 'windowed' is a tracking-only mode; the NUMA binding helper is a no-op without NVML/GPU."""
+    import pytest
+    from pyfeaturetrack_b200 import config, _capi, shard
+    saved = (config.track_precision, config.select_precision, config.operator_precision)
+    try:
+        config.set_precision(track="windowed")
+        assert config.track_precision_code() == _capi.PRECISION_FAST_WINDOWED == 2
+        config.set_precision(track="fast", select="strict", operator="fast")
+        assert (config.track_precision_code(), config.select_precision_code(), config.operator_precision_code()) == (0, 1, 0)
+        for bad in (dict(select="windowed"), dict(operator="windowed"), dict(track="exact")):
+            with pytest.raises(ValueError):
+                config.set_precision(**bad)
+    finally:
+        config.set_precision(track=saved[0], select=saved[1], operator=saved[2])
+    import torch
+    if not torch.cuda.is_available():
+        assert shard.bind_host_to_gpu(0) == 0
