@@ -188,7 +188,11 @@ def test_precision_modes_and_host_binding():
         assert config.track_precision_code() == _capi.PRECISION_FAST_WINDOWED == 2
         config.set_precision(track="fast", select="strict", operator="fast")
         assert (config.track_precision_code(), config.select_precision_code(), config.operator_precision_code()) == (0, 1, 0)
-        for bad in (dict(select="windowed"), dict(operator="windowed"), dict(track="exact")):
+        config.set_precision(track="auto")
+        px = 1920 * 1080
+        assert config.track_precision_code() == 2 and config.track_precision_code(1000, px) == 2      # sparse: windowed
+        assert config.track_precision_code(px // config.AUTO_PIXELS_PER_FEATURE + 1, px) == 0          # dense: planes
+        for bad in (dict(select="windowed"), dict(operator="auto"), dict(track="exact")):
             with pytest.raises(ValueError):
                 config.set_precision(**bad)
     finally:
