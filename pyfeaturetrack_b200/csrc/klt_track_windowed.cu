@@ -29,16 +29,19 @@ constexpr int LAZY_WARPS = 4;
 
 template <int W>
 struct Cfg {
-    // first image: the exact window (S1 output pixels a side); second image: window + margin
-    static constexpr int S1 = W + 1, N1 = S1 + 2 * RG, NP1 = N1 | 1, SP1 = S1 | 1;      // odd pitches: conflict-free
-    static constexpr int S2 = W + 1 + 2 * MARGIN, N2 = S2 + 2 * RG, NP2 = N2 | 1, SP2 = S2 | 1;
-    // per-warp shared memory (floats): staged input, horizontal results (deriv, gauss), gradx, grady of both regions
-    // (IN1 is padded: in the merged horizontal pass the first image's lanes read N2 values of their N1-wide rows)
-    static constexpr int IN1 = 0, TD1 = IN1 + N1 * NP1 + (N2 - N1), TG1 = TD1 + N1 * SP1, GX1 = TG1 + N1 * SP1, GY1 = GX1 + S1 * SP1;
-    static constexpr int IN2 = GY1 + S1 * SP1, TD2 = IN2 + N2 * NP2, TG2 = TD2 + N2 * SP2, GX2 = TG2 + N2 * SP2, GY2 = GX2 + S2 * SP2;
-    static constexpr int FLOATS = GY2 + S2 * SP2;
-    static constexpr int PX = (W * W + 31) / 32;                         // window pixels per lane
-    static constexpr bool MERGED = N1 + N2 <= 32;                        // one lane per row of BOTH regions
+    static constexpr int S = W + 1;                         // gradient region of either image: the bilinear footprint of the window
+    static constexpr int NG = S + 2 * RG;                   // smoothed-image rows/columns that region needs
+    static constexpr int N1 = NG, NP1 = N1 | 1;             // staged region of the first image (odd pitches: conflict-free walks)
+    static constexpr int N2 = NG + 2 * MARGIN, NP2 = N2 | 1;   // staged region of the second image: MARGIN pixels of slack all round
+    static constexpr int SP = S | 1;
+    // per-warp shared memory (floats): staged inputs, horizontal results (deriv, gauss) and gradx / grady of both images
+    static constexpr int IN1 = 0, IN2 = IN1 + N1 * NP1;
+    static constexpr int TD2 = IN2 + N2 * NP2, TG2 = TD2 + NG * SP, TD1 = TG2 + NG * SP, TG1 = TD1 + NG * SP;
+    static constexpr int GX2 = TG1 + NG * SP, GY2 = GX2 + S * SP, GX1 = GY2 + S * SP, GY1 = GX1 + S * SP;
+    static constexpr int FLOATS = GY1 + S * SP;
+    static constexpr int PX = (W * W + 31) / 32;            // window pixels per lane
+    static constexpr bool MERGED_H = 2 * NG <= 32;          // one lane per row of BOTH regions in the horizontal pass
+    static constexpr bool QUAD_V = S <= 8;                  // vertical pass: 4 groups of 8 lanes (gx2, gy2, gx1, gy1)
 };
 
 __device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc) {
@@ -84,10 +87,10 @@ __device__ __forceinline__ void stage_region(float *__restrict__ dst, const floa
     }
 }
 
-// horizontal pass of one region row: S outputs of both kernels from the N = S + 6 staged values
+// horizontal pass of one region row: S outputs of both kernels from S + 6 consecutive staged values
 template <int S>
 __device__ __forceinline__ void hrow(const float *__restrict__ row, float *__restrict__ td, float *__restrict__ tg,
-                                     const float (&g)[7], const float (&d)[7], int nout) {
+                                     const float (&g)[7], const float (&d)[7]) {
     constexpr int N = S + 2 * RG;
     float v[N];
 #pragma unroll
@@ -97,110 +100,64 @@ __device__ __forceinline__ void hrow(const float *__restrict__ row, float *__res
         float hd = d[0] * v[c], hg = g[0] * v[c];
 #pragma unroll
         for (int j = 1; j < 7; j++) { hd = fmaf(d[j], v[c + j], hd); hg = fmaf(g[j], v[c + j], hg); }
-        if (c < nout) { td[c] = hd; tg[c] = hg; }
+        td[c] = hd; tg[c] = hg;
     }
 }
 
-// vertical pass: gx = gauss_v(deriv_h) on the lower half-warp, gy = deriv_v(gauss_h) on the upper one, lane = column
-// (tv = this lane's vertical taps: gauss for the lower half-warp, deriv for the upper one)
+// vertical pass of one output column: S outputs from S + 6 rows of the horizontal result
 template <int S, int SP>
-__device__ __forceinline__ void vpass(const float *__restrict__ td, const float *__restrict__ tg, float *__restrict__ gx,
-                                      float *__restrict__ gy, const float (&tv)[7], int lane) {
+__device__ __forceinline__ void vcol(const float *__restrict__ src, float *__restrict__ dst, const float (&t)[7]) {
     constexpr int N = S + 2 * RG;
-    static_assert(S <= 16, "one column per lane of a half-warp");
-    const bool second = lane >= 16;
-    const int col = lane & 15;
-    if (col < S) {
-        const float *src = (second ? tg : td) + col;
-        float *dst = (second ? gy : gx) + col;
-        float v[N];
+    float v[N];
 #pragma unroll
-        for (int i = 0; i < N; i++) v[i] = src[i * SP];
+    for (int i = 0; i < N; i++) v[i] = src[i * SP];
 #pragma unroll
-        for (int r = 0; r < S; r++) {
-            float o = tv[0] * v[r];
+    for (int r = 0; r < S; r++) {
+        float o = t[0] * v[r];
 #pragma unroll
-            for (int j = 1; j < 7; j++) o = fmaf(tv[j], v[r + j], o);
-            dst[r * SP] = o;
-        }
+        for (int j = 1; j < 7; j++) o = fmaf(t[j], v[r + j], o);
+        dst[r * SP] = o;
     }
 }
-// windows too wide for a half-warp: lane = (plane, column), several rounds
-template <int S, int SP>
-__device__ __forceinline__ void vpass_wide(const float *__restrict__ td, const float *__restrict__ tg, float *__restrict__ gx,
-                                           float *__restrict__ gy, const float (&g)[7], const float (&d)[7], int lane) {
-    constexpr int N = S + 2 * RG;
-#pragma unroll
-    for (int item = lane; item < 2 * S; item += 32) {
-        const bool second = item >= S;
-        const int col = second ? item - S : item;
-        const float *src = (second ? tg : td) + col;
-        float *dst = (second ? gy : gx) + col;
-        float t[7];
-#pragma unroll
-        for (int j = 0; j < 7; j++) t[j] = second ? d[j] : g[j];
-        float v[N];
-#pragma unroll
-        for (int i = 0; i < N; i++) v[i] = src[i * SP];
-#pragma unroll
-        for (int r = 0; r < S; r++) {
-            float o = t[0] * v[r];
-#pragma unroll
-            for (int j = 1; j < 7; j++) o = fmaf(t[j], v[r + j], o);
-            dst[r * SP] = o;
-        }
-    }
-}
-template <int S, int SP>
-__device__ __forceinline__ void vpass_any(const float *td, const float *tg, float *gx, float *gy, const float (&g)[7],
-                                          const float (&d)[7], const float (&tv)[7], int lane) {
-    if constexpr (S <= 16) vpass<S, SP>(td, tg, gx, gy, tv, lane);
-    else vpass_wide<S, SP>(td, tg, gx, gy, g, d, lane);
-}
 
-// gradients of the staged second-image region (also the re-staging path)
+// Gradients of the window of the second image at offset (ox, oy) inside its staged region and, unless only2, of the
+// first image's region.  gx = gauss_v(deriv_h(img)), gy = deriv_v(gauss_h(img))  (convolve.py:245-246).
+// tq: this lane's vertical taps for the 4 x 8 mapping (QUAD_V) -- group 0: gx2, 1: gy2, 2: gx1, 3: gy1;
+// th1 / th2: for the half-warp mapping (lower half: gauss -> gx, upper half: deriv -> gy).
 template <int W>
-__device__ __forceinline__ void gradients2(float *__restrict__ s, const WindowedTaps &K, const float (&tv2)[7], int lane) {
+__device__ __forceinline__ void window_gradients(float *__restrict__ s, const WindowedTaps &K, const float (&tq)[7],
+                                                 const float (&th1)[7], const float (&th2)[7], bool same_taps, bool only2,
+                                                 int ox, int oy, int lane) {
     using C = Cfg<W>;
-    if (lane < C::N2) hrow<C::S2>(s + C::IN2 + lane * C::NP2, s + C::TD2 + lane * C::SP2, s + C::TG2 + lane * C::SP2, K.g2, K.d2, C::S2);
-    __syncwarp();
-    vpass_any<C::S2, C::SP2>(s + C::TD2, s + C::TG2, s + C::GX2, s + C::GY2, K.g2, K.d2, tv2, lane);
-    __syncwarp();
-}
-template <int W>
-__device__ __forceinline__ void gradients1(float *__restrict__ s, const WindowedTaps &K, const float (&tv1)[7], int lane) {
-    using C = Cfg<W>;
-    if (lane < C::N1) hrow<C::S1>(s + C::IN1 + lane * C::NP1, s + C::TD1 + lane * C::SP1, s + C::TG1 + lane * C::SP1, K.g1, K.d1, C::S1);
-    __syncwarp();
-    vpass_any<C::S1, C::SP1>(s + C::TD1, s + C::TG1, s + C::GX1, s + C::GY1, K.g1, K.d1, tv1, lane);
-    __syncwarp();
-}
-
-// gradients of both staged regions of a level.  same_taps: both images were built with the same gradient kernels (always,
-// unless the reference's kernel cache handed them different ones) -- then one lane per row of BOTH regions runs one
-// code path with the taps as constant-bank operands.
-template <int W>
-__device__ __forceinline__ void gradients_both(float *__restrict__ s, const WindowedTaps &K, const float (&tv1)[7],
-                                               const float (&tv2)[7], bool same_taps, int lane) {
-    using C = Cfg<W>;
-    if (C::MERGED && same_taps) {
-        // lanes [0, N2): rows of the second image's region; lanes [N2, N2+N1): rows of the first image's.  The first-image
-        // lanes run the S2-wide loop and keep their first S1 outputs (their reads past the row end stay inside the buffer).
-        const bool second = lane < C::N2;
-        const int row = second ? lane : lane - C::N2;
-        if (second || row < C::N1) {
-            const float *src = s + (second ? C::IN2 + row * C::NP2 : C::IN1 + row * C::NP1);
-            float *td = s + (second ? C::TD2 + row * C::SP2 : C::TD1 + row * C::SP1);
-            float *tg = s + (second ? C::TG2 + row * C::SP2 : C::TG1 + row * C::SP1);
-            hrow<C::S2>(src, td, tg, K.g2, K.d2, second ? C::S2 : C::S1);
+    const float *in2 = s + C::IN2 + oy * C::NP2 + ox;
+    if (C::MERGED_H && same_taps) {
+        const bool second = lane < C::NG;                   // lanes [0, NG): second image, [NG, 2 NG): first image
+        const int row = second ? lane : lane - C::NG;
+        if (second || (!only2 && row < C::NG)) {
+            const float *src = second ? in2 + row * C::NP2 : s + C::IN1 + row * C::NP1;
+            float *td = s + (second ? C::TD2 : C::TD1) + row * C::SP, *tg = s + (second ? C::TG2 : C::TG1) + row * C::SP;
+            hrow<C::S>(src, td, tg, K.g2, K.d2);
         }
     } else {
-        if (lane < C::N2) hrow<C::S2>(s + C::IN2 + lane * C::NP2, s + C::TD2 + lane * C::SP2, s + C::TG2 + lane * C::SP2, K.g2, K.d2, C::S2);
-        if (lane < C::N1) hrow<C::S1>(s + C::IN1 + lane * C::NP1, s + C::TD1 + lane * C::SP1, s + C::TG1 + lane * C::SP1, K.g1, K.d1, C::S1);
+        if (lane < C::NG) hrow<C::S>(in2 + lane * C::NP2, s + C::TD2 + lane * C::SP, s + C::TG2 + lane * C::SP, K.g2, K.d2);
+        if (!only2 && lane < C::NG) hrow<C::S>(s + C::IN1 + lane * C::NP1, s + C::TD1 + lane * C::SP, s + C::TG1 + lane * C::SP, K.g1, K.d1);
     }
     __syncwarp();
-    vpass_any<C::S2, C::SP2>(s + C::TD2, s + C::TG2, s + C::GX2, s + C::GY2, K.g2, K.d2, tv2, lane);
-    vpass_any<C::S1, C::SP1>(s + C::TD1, s + C::TG1, s + C::GX1, s + C::GY1, K.g1, K.d1, tv1, lane);
+    if (C::QUAD_V) {
+        const int grp = lane >> 3, col = lane & 7;
+        if (col < C::S && (!only2 || grp < 2)) {
+            const int src = grp == 0 ? C::TD2 : (grp == 1 ? C::TG2 : (grp == 2 ? C::TD1 : C::TG1));
+            const int dst = grp == 0 ? C::GX2 : (grp == 1 ? C::GY2 : (grp == 2 ? C::GX1 : C::GY1));
+            vcol<C::S, C::SP>(s + src + col, s + dst + col, tq);
+        }
+    } else {
+        const bool upper = lane >= 16;
+        const int col = lane & 15;
+        if (col < C::S) {
+            vcol<C::S, C::SP>(s + (upper ? C::TG2 : C::TD2) + col, s + (upper ? C::GY2 : C::GX2) + col, th2);
+            if (!only2) vcol<C::S, C::SP>(s + (upper ? C::TG1 : C::TD1) + col, s + (upper ? C::GY1 : C::GX1) + col, th1);
+        }
+    }
     __syncwarp();
 }
 
@@ -213,7 +170,7 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// L2 prefetch of the rows of an N-wide region (top-left input pixel (sx0, sy0)), one row per lane starting at lane0
+// L2 prefetch of one row of an N-wide region (top-left input pixel (sx0, sy0))
 template <int N>
 __device__ __forceinline__ void prefetch_region(const float *__restrict__ img, int pitch, int nc, int nr, int sx0, int sy0, int row) {
     const int y = min(max(sy0 + row, 0), nr - 1);
@@ -238,20 +195,22 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
     float *s = smem + warp * C::FLOATS;
     const int image = f / A.n_per_image;
     constexpr int hw = W / 2;
-    const double ss = (double)A.ss;
+    const double ss = (double)A.ss, inv_ss = 1.0 / ss;        // subsampling is a power of two: x * inv_ss == x / ss exactly
     double xloc = xs[f], yloc = ys[f];
-    for (int r = A.n_levels - 1; r >= 0; r--) { xloc /= ss; yloc /= ss; }
+    for (int r = A.n_levels - 1; r >= 0; r--) { xloc *= inv_ss; yloc *= inv_ss; }
     double xout = xloc, yout = yloc;
     int st = KLT_TRACKED;
     unsigned int my_iters = 0;
     bool alive = true;
-    // this lane's vertical taps (lower half-warp: gauss -> gradx, upper: deriv -> grady) and whether both images share them
-    float tv1[7], tv2[7];
+    // this lane's vertical taps for the two lane mappings of the vertical pass, and whether both images share their kernels
+    float tq[7], th1[7], th2[7];
     bool same_taps = true;
 #pragma unroll
     for (int j = 0; j < 7; j++) {
-        tv1[j] = lane >= 16 ? K.d1[j] : K.g1[j];
-        tv2[j] = lane >= 16 ? K.d2[j] : K.g2[j];
+        const int grp = lane >> 3;
+        tq[j] = grp == 0 ? K.g2[j] : (grp == 1 ? K.d2[j] : (grp == 2 ? K.g1[j] : K.d1[j]));
+        th1[j] = lane >= 16 ? K.d1[j] : K.g1[j];
+        th2[j] = lane >= 16 ? K.d2[j] : K.g2[j];
         same_taps = same_taps && K.g1[j] == K.g2[j] && K.d1[j] == K.d2[j];
     }
 
@@ -271,8 +230,10 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
         float x2 = (float)xout, y2 = (float)yout;
         int status = KLT_TRACKED, iteration = 0;
         const float fnc = (float)nc, fnr = (float)nr, fhw = (float)hw;
-        // top-left OUTPUT pixel of the second image's region; the start window sits MARGIN pixels inside it
+        // (rx0, ry0): window position at offset (0, 0) of the staged region of the second image; the start window sits
+        // MARGIN pixels inside.  (gix, giy): window position the gradients in shared memory belong to.
         int rx0 = (int)x2 - hw - MARGIN, ry0 = (int)y2 - hw - MARGIN;
+        int gix = -0x40000000, giy = -0x40000000;
         const bool start_inside = !(x2 - fhw < 0.f || fnc - (x2 + fhw) < 1.001f || y2 - fhw < 0.f || fnr - (y2 + fhw) < 1.001f);
         // one memory round trip: both regions of this level
         stage_region<C::N1, C::NP1>(s + C::IN1, I1, pitch, nc, nr, ix1 - hw - RG, iy1 - hw - RG, lane);
@@ -282,21 +243,24 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
             const int ncn = A.p1.lv[r - 1].w, nrn = A.p1.lv[r - 1].h, pn = A.p1.lv[r - 1].pitch;
             const float xn1 = (float)(xloc * ss), yn1 = (float)(yloc * ss);
             const float xn2 = (float)((double)x2 * ss), yn2 = (float)((double)y2 * ss);
-            if (lane < C::N2 && lane + 0 < 32)
+            if (lane < C::N2)
                 prefetch_region<C::N2>(A.p2.level(0, image, r - 1), pn, ncn, nrn, (int)xn2 - hw - MARGIN - RG, (int)yn2 - hw - MARGIN - RG, lane);
             if (lane < C::N1)
                 prefetch_region<C::N1>(A.p1.level(0, image, r - 1), pn, ncn, nrn, (int)xn1 - hw - RG, (int)yn1 - hw - RG, lane);
         }
         cp_async_wait_all();
         __syncwarp();
-        if (start_inside) gradients_both<W>(s, K, tv1, tv2, same_taps, lane);
-        else {
-            gradients1<W>(s, K, tv1, lane);
-            rx0 = -0x40000000;                     // nothing staged for the second image (the loop exits with OOB at once)
+        if (start_inside) {
+            window_gradients<W>(s, K, tq, th1, th2, same_taps, false, MARGIN, MARGIN, lane);
+            gix = (int)x2; giy = (int)y2;
+        } else {
+            // the loop below leaves with OOB at once; only the template is needed.  (The second image's buffer holds
+            // stale but finite data; its results are never used.)
+            window_gradients<W>(s, K, tq, th1, th2, same_taps, false, MARGIN, MARGIN, lane);
         }
         // template: the first image's window, gradients interpolated like the image (trackFeatures.py:87-92)
         float T[C::PX], Tgx[C::PX], Tgy[C::PX];
-        int po[C::PX], pi[C::PX];                  // this lane's window pixels inside the second image's region (ox = oy = 0)
+        int po[C::PX], pi[C::PX];                  // this lane's window pixels: offsets in a gradient array / in the staged region
         {
             const float ax = x1 - (float)ix1, ay = y1 - (float)iy1;
             const float w11 = ax * ay, w01 = ax - w11, w10 = ay - w11, w00 = 1.f - ax - ay + w11;
@@ -305,39 +269,43 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
                 const int k = lane + 32 * i;
                 const bool on = k < W * W;
                 const int pr = on ? k / W : 0, pc = on ? k - pr * W : 0;
-                po[i] = pr * C::SP2 + pc;
+                po[i] = pr * C::SP + pc;
                 pi[i] = (pr + RG) * C::NP2 + pc + RG;
                 T[i] = on ? bil(s + C::IN1 + (pr + RG) * C::NP1 + pc + RG, C::NP1, w00, w01, w10, w11) : 0.f;
-                Tgx[i] = on ? bil(s + C::GX1 + pr * C::SP1 + pc, C::SP1, w00, w01, w10, w11) : 0.f;
-                Tgy[i] = on ? bil(s + C::GY1 + pr * C::SP1 + pc, C::SP1, w00, w01, w10, w11) : 0.f;
+                Tgx[i] = on ? bil(s + C::GX1 + po[i], C::SP, w00, w01, w10, w11) : 0.f;
+                Tgy[i] = on ? bil(s + C::GY1 + po[i], C::SP, w00, w01, w10, w11) : 0.f;
             }
         }
+        int ox = MARGIN, oy = MARGIN;
         for (;;) {
             if (x2 - fhw < 0.f || fnc - (x2 + fhw) < 1.001f || y2 - fhw < 0.f || fnr - (y2 + fhw) < 1.001f) {
                 status = KLT_OOB;
                 break;
             }
             const int ix = (int)x2, iy = (int)y2;
-            int ox = ix - hw - rx0, oy = iy - hw - ry0;
-            if (ox < 0 || oy < 0 || ox > 2 * MARGIN || oy > 2 * MARGIN) {      // the window left the region: stage a new one
-                rx0 = ix - hw - MARGIN; ry0 = iy - hw - MARGIN;
+            if (ix != gix || iy != giy) {                   // the window moved to another pixel: new gradients
+                ox = ix - hw - rx0; oy = iy - hw - ry0;
                 __syncwarp();
-                stage_region<C::N2, C::NP2>(s + C::IN2, I2, pitch, nc, nr, rx0 - RG, ry0 - RG, lane);
-                cp_async_wait_all();
-                __syncwarp();
-                gradients2<W>(s, K, tv2, lane);
-                ox = MARGIN; oy = MARGIN;
+                if (ox < 0 || oy < 0 || ox > 2 * MARGIN || oy > 2 * MARGIN) {      // it even left the staged region
+                    rx0 = ix - hw - MARGIN; ry0 = iy - hw - MARGIN;
+                    stage_region<C::N2, C::NP2>(s + C::IN2, I2, pitch, nc, nr, rx0 - RG, ry0 - RG, lane);
+                    cp_async_wait_all();
+                    __syncwarp();
+                    ox = MARGIN; oy = MARGIN;
+                }
+                window_gradients<W>(s, K, tq, th1, th2, same_taps, true, ox, oy, lane);
+                gix = ix; giy = iy;
             }
             const float ax = x2 - (float)ix, ay = y2 - (float)iy;
             const float w11 = ax * ay, w01 = ax - w11, w10 = ay - w11, w00 = 1.f - ax - ay + w11;
-            const float *bi = s + C::IN2 + oy * C::NP2 + ox, *bx = s + C::GX2 + oy * C::SP2 + ox, *by = s + C::GY2 + oy * C::SP2 + ox;
+            const float *bi = s + C::IN2 + oy * C::NP2 + ox;
             float gxx = 0.f, gxy = 0.f, gyy = 0.f, ex = 0.f, ey = 0.f;
 #pragma unroll
             for (int i = 0; i < C::PX; i++) {
                 if (lane + 32 * i < W * W) {
                     const float P = bil(bi + pi[i], C::NP2, w00, w01, w10, w11);
-                    const float Px = bil(bx + po[i], C::SP2, w00, w01, w10, w11);
-                    const float Py = bil(by + po[i], C::SP2, w00, w01, w10, w11);
+                    const float Px = bil(s + C::GX2 + po[i], C::SP, w00, w01, w10, w11);
+                    const float Py = bil(s + C::GY2 + po[i], C::SP, w00, w01, w10, w11);
                     const float diff = T[i] - P, gx = Tgx[i] + Px, gy = Tgy[i] + Py;
                     gxx = fmaf(gx, gx, gxx); gxy = fmaf(gx, gy, gxy); gyy = fmaf(gy, gy, gyy);
                     ex = fmaf(diff, gx, ex); ey = fmaf(diff, gy, ey);
@@ -361,7 +329,7 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
         }
         if (status == KLT_TRACKED && A.has_max_residue) {
             const int ix = (int)x2, iy = (int)y2;
-            int ox = ix - hw - rx0, oy = iy - hw - ry0;
+            ox = ix - hw - rx0; oy = iy - hw - ry0;
             if (ox < 0 || oy < 0 || ox > 2 * MARGIN || oy > 2 * MARGIN) {
                 rx0 = ix - hw - MARGIN; ry0 = iy - hw - MARGIN;
                 __syncwarp();
