@@ -22,7 +22,7 @@ namespace {
 
 constexpr int RG = 3;      // gradient kernel radius served here (grad_sigma = 1.0: 7 taps); other radii use the planes
 constexpr int MARGIN = 2;  // pixels of slack around the start window of the second image
-constexpr int LAZY_WARPS = 4;
+constexpr int LAZY_WARPS = 4;   // (4 or 5 CTAs/SM measured equal, 6..8 are 4-6 % slower: more warps only add shared-memory contention)
 #ifndef LAZY_MIN_CTAS
 #define LAZY_MIN_CTAS 5
 #endif
@@ -181,8 +181,8 @@ __device__ __forceinline__ void prefetch_region(const float *__restrict__ img, i
     prefetch_l2(p + xb);
 }
 
-template <int W>
-__global__ void __launch_bounds__(LAZY_WARPS * 32, (W <= 11 ? LAZY_MIN_CTAS : 3))
+template <int W, int MINB>
+__global__ void __launch_bounds__(LAZY_WARPS * 32, MINB)
 lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ WindowedTaps K, double *__restrict__ xs,
                    double *__restrict__ ys, int *__restrict__ vals, unsigned long long *__restrict__ iters_total,
                    int *__restrict__ assert_flag) {
@@ -375,8 +375,9 @@ int launch_windowed(klt_ctx *ctx, const TrackArgs &A, const WindowedTaps &K, dou
     // algorithmic bytes: the staged regions of both images on every level (restaging not counted) + the feature records
     const double bytes = (double)A.total * (A.n_levels * 4.0 * (Cfg<W>::N1 * Cfg<W>::N1 + Cfg<W>::N2 * Cfg<W>::N2) + 40.0);
     const size_t smem = (size_t)LAZY_WARPS * Cfg<W>::FLOATS * sizeof(float);
-    if (smem > 48 * 1024) KLT_CUDA(ctx, cudaFuncSetAttribute(lk_windowed_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KLT_LAUNCH(ctx, "lk_windowed", bytes, (lk_windowed_kernel<W><<<blocks, LAZY_WARPS * 32, smem, ctx->stream>>>(A, K, x, y, v, it, af)));
+    constexpr int MINB = W <= 11 ? LAZY_MIN_CTAS : 3;
+    if (smem > 48 * 1024) KLT_CUDA(ctx, cudaFuncSetAttribute(lk_windowed_kernel<W, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KLT_LAUNCH(ctx, "lk_windowed", bytes, (lk_windowed_kernel<W, MINB><<<blocks, LAZY_WARPS * 32, smem, ctx->stream>>>(A, K, x, y, v, it, af)));
     return KLT_OK;
 }
 
