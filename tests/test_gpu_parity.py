@@ -657,3 +657,30 @@ def synth_frame(k, shape=(300, 400)):
     from pyfeaturetrack_b200 import synth
     base = _synth(5, (shape[0] + 16, shape[1] + 16))[0]
     return np.ascontiguousarray(base[k:k + shape[0], 2 * k:2 * k + shape[1]])
+
+
+def test_windowed_large_motion_restages_its_region(gpu_ctx, oracle):
+    """One pyramid level and a 3-4 px shift: the window walks out of the 2-pixel margin of the staged region during the
+    Newton iterations, so the windowed tracker has to re-stage (and re-evaluate the gradients) mid-loop."""
+    from pyfeaturetrack_b200 import selectGoodFeatures as sgf, trackFeatures as tf, config
+    imgs = _synth(91, (300, 400), shift=(3.6, -2.7))
+    kw = dict(nPyramidLevels=1, subsampling=2, max_residue=15.0, max_iterations=20)
+    p = P(oracle, **kw)
+    tc = make_tc(**kw)
+    n = 150
+    want_sel = oracle.select_good_features(p, imgs[0], n)
+    want = oracle.track_features(p, imgs[0], imgs[1], *want_sel)[:3]
+    assert (want[2] == 0).mean() > 0.5                       # most features do converge across the 3-4 px
+    moved = np.hypot(want[0] - want_sel[0], want[1] - want_sel[1])[want[2] == 0]
+    assert np.median(moved) > 3.0
+    out = {}
+    for mode in ("fast", "windowed"):
+        config.set_precision(track=mode)
+        f = sgf.KLTSelectGoodFeatures(tc, imgs[0], n)
+        tf.KLTTrackFeatures(tc, imgs[0], imgs[1], f)
+        out[mode] = fl_arrays(f)
+        got = out[mode]
+        assert np.mean(got[2] == want[2]) >= 0.97
+        both = (got[2] == 0) & (want[2] == 0)
+        assert np.abs(got[0][both] - want[0][both]).max() <= POS_TOL and np.abs(got[1][both] - want[1][both]).max() <= POS_TOL
+    assert np.mean(out["fast"][2] == out["windowed"][2]) >= 0.99
