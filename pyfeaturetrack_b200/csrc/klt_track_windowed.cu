@@ -31,15 +31,29 @@ template <int W>
 struct Cfg {
     static constexpr int S = W + 1;                         // gradient region of either image: the bilinear footprint of the window
     static constexpr int NG = S + 2 * RG;                   // smoothed-image rows/columns that region needs
-    static constexpr int N1 = NG, NP1 = N1 | 1;             // staged region of the first image (odd pitches: conflict-free walks)
-    static constexpr int N2 = NG + 2 * MARGIN, NP2 = N2 | 1;   // staged region of the second image: MARGIN pixels of slack all round
-    static constexpr int SP = S | 1;
+    // Window pixels -> lanes.  Linear (k = lane + 32 i) in general; where it costs no extra round, LPR lanes per window row
+    // (7x7: 8 lanes per row, 4 rows per round), which lets the pitches below make every bilinear tap a conflict-free access.
+    static constexpr int LPR = W <= 4 ? 4 : (W <= 8 ? 8 : 16), RPR = 32 / LPR;
+    static constexpr bool ROWMAP = LPR <= 8 && ((W + RPR - 1) / RPR) * 32 <= ((W * W + 31) / 32) * 32;   // 3x3 and 7x7
+    // (15x15 qualifies arithmetically, but its linear mapping is already nearly conflict-free and measured 6 % faster)
+    static constexpr int PX = ROWMAP ? (W + RPR - 1) / RPR : (W * W + 31) / 32;           // rounds = window pixels per lane
+    // staged regions: odd pitches keep the one-row-per-lane walks of the horizontal pass conflict-free; for 7x7, 25 also
+    // puts the 4 window rows of a round on disjoint banks (0, 25, 18, 11 + 7 columns)
+    static constexpr int N1 = NG, NP1 = W == 7 ? 25 : (N1 | 1);             // first image
+    static constexpr int N2 = NG + 2 * MARGIN, NP2 = W == 7 ? 25 : (N2 | 1);   // second image: MARGIN pixels of slack all round
+    static constexpr int SP = S | 1;                        // horizontal results (row-per-lane stores, column-per-lane loads)
+    static constexpr int GP = (ROWMAP && LPR == S) ? S : SP;   // gradient planes: pitch = lanes per window row where possible
     // per-warp shared memory (floats): staged inputs, horizontal results (deriv, gauss) and gradx / grady of both images
+    // The four horizontal-result planes (and the four gradient planes) start 8 banks apart (QUAD_V) or 16 (half-warp
+    // mapping): the lane groups of the vertical pass, which walk one plane each, then never share a bank, and neither do
+    // the two row groups of the merged horizontal pass when they store.
+    static constexpr int GROUP_BANKS = S <= 8 ? 8 : 16;
+    static constexpr int pad_to(int n, int banks) { return n + ((banks - n % 32) % 32 + 32) % 32; }
+    static constexpr int TSZ = pad_to(NG * SP, GROUP_BANKS), GSZ = pad_to(S * GP, GROUP_BANKS);
     static constexpr int IN1 = 0, IN2 = IN1 + N1 * NP1;
-    static constexpr int TD2 = IN2 + N2 * NP2, TG2 = TD2 + NG * SP, TD1 = TG2 + NG * SP, TG1 = TD1 + NG * SP;
-    static constexpr int GX2 = TG1 + NG * SP, GY2 = GX2 + S * SP, GX1 = GY2 + S * SP, GY1 = GX1 + S * SP;
-    static constexpr int FLOATS = GY1 + S * SP;
-    static constexpr int PX = (W * W + 31) / 32;            // window pixels per lane
+    static constexpr int TD2 = pad_to(IN2 + N2 * NP2, 0), TG2 = TD2 + TSZ, TD1 = TG2 + TSZ, TG1 = TD1 + TSZ;
+    static constexpr int GX2 = pad_to(TG1 + TSZ, 0), GY2 = GX2 + GSZ, GX1 = GY2 + GSZ, GY1 = GX1 + GSZ;
+    static constexpr int FLOATS = GY1 + GSZ;
     static constexpr bool MERGED_H = 2 * NG <= 32;          // one lane per row of BOTH regions in the horizontal pass
     static constexpr bool QUAD_V = S <= 8;                  // vertical pass: 4 groups of 8 lanes (gx2, gy2, gx1, gy1)
 };
@@ -105,7 +119,7 @@ __device__ __forceinline__ void hrow(const float *__restrict__ row, float *__res
 }
 
 // vertical pass of one output column: S outputs from S + 6 rows of the horizontal result
-template <int S, int SP>
+template <int S, int SP, int GP>
 __device__ __forceinline__ void vcol(const float *__restrict__ src, float *__restrict__ dst, const float (&t)[7]) {
     constexpr int N = S + 2 * RG;
     float v[N];
@@ -116,7 +130,7 @@ __device__ __forceinline__ void vcol(const float *__restrict__ src, float *__res
         float o = t[0] * v[r];
 #pragma unroll
         for (int j = 1; j < 7; j++) o = fmaf(t[j], v[r + j], o);
-        dst[r * SP] = o;
+        dst[r * GP] = o;
     }
 }
 
@@ -148,14 +162,14 @@ __device__ __forceinline__ void window_gradients(float *__restrict__ s, const Wi
         if (col < C::S && (!only2 || grp < 2)) {
             const int src = grp == 0 ? C::TD2 : (grp == 1 ? C::TG2 : (grp == 2 ? C::TD1 : C::TG1));
             const int dst = grp == 0 ? C::GX2 : (grp == 1 ? C::GY2 : (grp == 2 ? C::GX1 : C::GY1));
-            vcol<C::S, C::SP>(s + src + col, s + dst + col, tq);
+            vcol<C::S, C::SP, C::GP>(s + src + col, s + dst + col, tq);
         }
     } else {
         const bool upper = lane >= 16;
         const int col = lane & 15;
         if (col < C::S) {
-            vcol<C::S, C::SP>(s + (upper ? C::TG2 : C::TD2) + col, s + (upper ? C::GY2 : C::GX2) + col, th2);
-            if (!only2) vcol<C::S, C::SP>(s + (upper ? C::TG1 : C::TD1) + col, s + (upper ? C::GY1 : C::GX1) + col, th1);
+            vcol<C::S, C::SP, C::GP>(s + (upper ? C::TG2 : C::TD2) + col, s + (upper ? C::GY2 : C::GX2) + col, th2);
+            if (!only2) vcol<C::S, C::SP, C::GP>(s + (upper ? C::TG1 : C::TD1) + col, s + (upper ? C::GY1 : C::GX1) + col, th1);
         }
     }
     __syncwarp();
@@ -261,19 +275,23 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
         // template: the first image's window, gradients interpolated like the image (trackFeatures.py:87-92)
         float T[C::PX], Tgx[C::PX], Tgy[C::PX];
         int po[C::PX], pi[C::PX];                  // this lane's window pixels: offsets in a gradient array / in the staged region
+        bool pon[C::PX];
         {
             const float ax = x1 - (float)ix1, ay = y1 - (float)iy1;
             const float w11 = ax * ay, w01 = ax - w11, w10 = ay - w11, w00 = 1.f - ax - ay + w11;
 #pragma unroll
             for (int i = 0; i < C::PX; i++) {
-                const int k = lane + 32 * i;
-                const bool on = k < W * W;
-                const int pr = on ? k / W : 0, pc = on ? k - pr * W : 0;
-                po[i] = pr * C::SP + pc;
+                int pr, pc;
+                if (C::ROWMAP) { pr = C::RPR * i + lane / C::LPR; pc = lane % C::LPR; }
+                else { const int k = lane + 32 * i; pr = k / W; pc = k - pr * W; }
+                const bool on = pr < W && pc < W;
+                if (!on) { pr = 0; pc = 0; }
+                pon[i] = on;
+                po[i] = pr * C::GP + pc;
                 pi[i] = (pr + RG) * C::NP2 + pc + RG;
                 T[i] = on ? bil(s + C::IN1 + (pr + RG) * C::NP1 + pc + RG, C::NP1, w00, w01, w10, w11) : 0.f;
-                Tgx[i] = on ? bil(s + C::GX1 + po[i], C::SP, w00, w01, w10, w11) : 0.f;
-                Tgy[i] = on ? bil(s + C::GY1 + po[i], C::SP, w00, w01, w10, w11) : 0.f;
+                Tgx[i] = on ? bil(s + C::GX1 + po[i], C::GP, w00, w01, w10, w11) : 0.f;
+                Tgy[i] = on ? bil(s + C::GY1 + po[i], C::GP, w00, w01, w10, w11) : 0.f;
             }
         }
         int ox = MARGIN, oy = MARGIN;
@@ -302,10 +320,10 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
             float gxx = 0.f, gxy = 0.f, gyy = 0.f, ex = 0.f, ey = 0.f;
 #pragma unroll
             for (int i = 0; i < C::PX; i++) {
-                if (lane + 32 * i < W * W) {
+                if (pon[i]) {
                     const float P = bil(bi + pi[i], C::NP2, w00, w01, w10, w11);
-                    const float Px = bil(s + C::GX2 + po[i], C::SP, w00, w01, w10, w11);
-                    const float Py = bil(s + C::GY2 + po[i], C::SP, w00, w01, w10, w11);
+                    const float Px = bil(s + C::GX2 + po[i], C::GP, w00, w01, w10, w11);
+                    const float Py = bil(s + C::GY2 + po[i], C::GP, w00, w01, w10, w11);
                     const float diff = T[i] - P, gx = Tgx[i] + Px, gy = Tgy[i] + Py;
                     gxx = fmaf(gx, gx, gxx); gxy = fmaf(gx, gy, gxy); gyy = fmaf(gy, gy, gyy);
                     ex = fmaf(diff, gx, ex); ey = fmaf(diff, gy, ey);
@@ -344,7 +362,7 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
             float res = 0.f;
 #pragma unroll
             for (int i = 0; i < C::PX; i++)
-                if (lane + 32 * i < W * W) res += fabsf(T[i] - bil(bi + pi[i], C::NP2, w00, w01, w10, w11));
+                if (pon[i]) res += fabsf(T[i] - bil(bi + pi[i], C::NP2, w00, w01, w10, w11));
             res = warp_sum(res) / (float)(W * W);
             if (res > A.max_residue) status = KLT_LARGE_RESIDUE;
         }
