@@ -282,9 +282,9 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < C::PX; i++) {
                 int pr, pc;
-                if (C::ROWMAP) { pr = C::RPR * i + lane / C::LPR; pc = lane % C::LPR; }
-                else { const int k = lane + 32 * i; pr = k / W; pc = k - pr * W; }
-                const bool on = pr < W && pc < W;
+                bool on;
+                if (C::ROWMAP) { pr = C::RPR * i + lane / C::LPR; pc = lane % C::LPR; on = pr < W && pc < W; }
+                else { const int k = lane + 32 * i; on = k < W * W; pr = k / W; pc = k - pr * W; }   // (true at compile time for most i)
                 if (!on) { pr = 0; pc = 0; }
                 pon[i] = on;
                 po[i] = pr * C::GP + pc;
