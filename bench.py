@@ -439,10 +439,11 @@ def sequence_timing(wl, klt, sgf, tf, nframes, affine=-1):
     tc.sequentialMode = True
     tc.affineConsistencyCheck = affine                        # config E: 15x15 affine windows, 6x6 solve per feature
     fl = sgf.KLTSelectGoodFeatures(tc, frames[0], wl["n"])
-    tf.KLTTrackFeatures(tc, frames[0], frames[1], fl)          # warm-up: allocates the two ping-pong pyramids
-    sgf.KLTReplaceLostFeatures(tc, frames[1], fl)
+    for k in (1, 2):                                            # warm-up: the first two calls allocate the three pyramids
+        tf.KLTTrackFeatures(tc, frames[k - 1], frames[k], fl)   # a sequence rotates through (cudaMalloc: 3-50 ms each)
+        sgf.KLTReplaceLostFeatures(tc, frames[k], fl)
     t_track = t_repl = 0.0
-    for k in range(2, nframes + 1):
+    for k in range(3, nframes + 1):
         t0 = time.perf_counter()
         tf.KLTTrackFeatures(tc, frames[k - 1], frames[k], fl)
         t1 = time.perf_counter()
@@ -450,7 +451,7 @@ def sequence_timing(wl, klt, sgf, tf, nframes, affine=-1):
         t2 = time.perf_counter()
         t_track += t1 - t0
         t_repl += t2 - t1
-    m = nframes - 1
+    m = nframes - 2
     return {"call": "sequentialMode%s: KLTTrackFeatures + KLTReplaceLostFeatures per frame (drop-in API, one sequence)" %
                     ("" if affine < 0 else ", affineConsistencyCheck=%d" % affine),
             "tracked_at_end": sum(1 for f in fl if f.val >= 0),

@@ -264,7 +264,7 @@ int klt_pyr_create(klt_ctx *ctx, int w, int h, int n_levels, int subsampling, in
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
     klt_pyr *p = new klt_pyr();
     p->hx = new KltPyrHost();
-    p->hx->taps_valid = false; p->hx->grad_valid = false;
+    p->hx->taps_valid = false; p->hx->grad_valid = false; p->hx->grad0_valid = false;
     p->w = w; p->h = h; p->n_levels = n_levels; p->ss = subsampling; p->batch = batch;
     p->precision = KLT_PRECISION_STRICT;
     size_t off = 0;
@@ -309,11 +309,13 @@ static int check_taps(klt_ctx *ctx, const klt_taps *t) {
 // levels 1..L-1 and all gradients, given level 0 intensity already in place (level0_grad_done: the fused level-0
 // kernel has already written gradx/grady of level 0).  FAST precision takes the warp-streaming kernels where they
 // cover the configuration; everything else runs the generic tiled kernels.
-static int build_gradients(klt_ctx *ctx, klt_pyr *p, const klt_taps *taps, int precision, int first_level, int first, int count) {
+static int build_gradients(klt_ctx *ctx, klt_pyr *p, const klt_taps *taps, int precision, int first_level, int first, int count,
+                           int end_level = -1) {
     int rc;
     const size_t stride = p->plane_floats;
     const bool fast = precision == KLT_PRECISION_FAST;
-    for (int l = first_level; l < p->n_levels; l++) {
+    if (end_level < 0) end_level = p->n_levels;
+    for (int l = first_level; l < end_level; l++) {
         const LevelDesc &a = p->lv[l];
         rc = fast ? klt_stream_grad(ctx, p, l, taps, first, count) : 0;
         if (rc < 0) return rc;
@@ -348,17 +350,28 @@ static int begin_build(klt_pyr *p, const klt_taps *taps, int precision, bool *wi
     const int arith = *windowed ? KLT_PRECISION_FAST : precision;
     p->precision = arith;
     p->hx->taps = *taps; p->hx->taps_valid = true;
-    p->hx->grad_valid = !*windowed;
+    p->hx->grad_valid = p->hx->grad0_valid = !*windowed;
     return arith;
 }
 
 int klt_pyr_ensure_gradients(klt_ctx *ctx, klt_pyr *p) {
+    if (!ctx || !p) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
     if (!p->hx || p->hx->grad_valid) return KLT_OK;
     if (!p->hx->taps_valid) return klt_fail(ctx, KLT_ERR_INVALID, "pyramid has not been built");
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
-    int rc = build_gradients(ctx, p, &p->hx->taps, p->precision, 0, 0, p->batch);
+    int rc = build_gradients(ctx, p, &p->hx->taps, p->precision, p->hx->grad0_valid ? 1 : 0, 0, p->batch);
     if (rc) return rc;
-    p->hx->grad_valid = true;
+    p->hx->grad_valid = p->hx->grad0_valid = true;
+    return KLT_OK;
+}
+
+// level 0 only: what selection on a tracking pyramid reads (KLTReplaceLostFeatures in sequentialMode)
+static int ensure_gradients_level0(klt_ctx *ctx, klt_pyr *p) {
+    if (!p->hx || p->hx->grad_valid || p->hx->grad0_valid) return KLT_OK;
+    if (!p->hx->taps_valid) return klt_fail(ctx, KLT_ERR_INVALID, "pyramid has not been built");
+    int rc = build_gradients(ctx, p, &p->hx->taps, p->precision, 0, 0, p->batch, 1);
+    if (rc) return rc;
+    p->hx->grad0_valid = true;
     return KLT_OK;
 }
 
@@ -491,6 +504,8 @@ int klt_select_good_features(klt_ctx *ctx, const klt_params *params, const klt_p
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
     if (pyr) {
         if (image < 0 || image >= pyr->batch) return klt_fail(ctx, KLT_ERR_INVALID, "image index out of range");
+        int rc = ensure_gradients_level0(ctx, const_cast<klt_pyr *>(pyr));      // image-only pyramids: build level 0's planes now
+        if (rc) return rc;
         return klt_select_device(ctx, params, pyr->level(1, image, 0), pyr->level(2, image, 0), pyr->lv[0].pitch, pyr->w, pyr->h,
                                  n_features, replace, x, y, val, n_consumed);
     }

@@ -28,7 +28,8 @@ struct LevelDesc {
 struct KltPyrHost {
     klt_taps taps;            // kernels of the last build (the windowed tracker and lazy gradient builds need them)
     bool taps_valid;
-    bool grad_valid;          // gradient planes hold the gradients of the current images
+    bool grad_valid;          // gradient planes of ALL levels hold the gradients of the current images
+    bool grad0_valid;         // at least level 0 does (selection on a tracking pyramid needs only that one)
 };
 
 struct klt_pyr {

@@ -65,43 +65,50 @@ def make_params(tc):
     return p
 
 
+# attributes a (re)selected feature starts with (selectGoodFeatures.py:120-128)
 _AFFINE_RESET = dict(aff_img=None, aff_img_gradx=None, aff_img_grady=None, aff_x=-1.0, aff_y=-1.0, aff_Axx=1.0,
                      aff_Ayx=0.0, aff_Axy=0.0, aff_Ayy=1.0)
-
-
-def _reset_affine(feat):
-    """selectGoodFeatures.py:120-128"""
-    feat.__dict__.update(_AFFINE_RESET)
 
 
 def _select_on_device(tc, pyr, nFeatures, featurelist, overwriteAllFeatures):
     """Scan + sort + _enforceMinimumDistance on level-0 gradients of `pyr` (selectGoodFeatures.py:215-246)."""
     ctx = pyr.ctx
-    x = np.full(nFeatures, -1.0)
-    y = np.full(nFeatures, -1.0)
-    val = np.full(nFeatures, kltState.KLT_NOT_FOUND, np.int32)
-    if not overwriteAllFeatures:
-        for i, feat in enumerate(featurelist):
-            x[i], y[i], val[i] = feat.x, feat.y, feat.val
+    x, y, val = _gather(featurelist, nFeatures, overwriteAllFeatures)
     old_val = val.copy()
     params = make_params(tc)
     consumed = C.c_int64()
     ctx.check(_capi.lib().klt_select_good_features(ctx.handle, C.byref(params), pyr.handle, 0, None, None, 0, 0,
                                                   nFeatures, 0 if overwriteAllFeatures else 1, x.ctypes.data,
                                                   y.ctypes.data, val.ctypes.data, C.byref(consumed)))
-    xi = x.astype(np.int32)
-    yi = y.astype(np.int32)
-    for i, feat in enumerate(featurelist):
-        if overwriteAllFeatures:
-            if val[i] >= 0:
-                feat.x, feat.y, feat.val = xi[i], yi[i], int(val[i])       # np.int32 / int, quirk Q13
-            else:
-                feat.x, feat.y, feat.val = -1, -1, kltState.KLT_NOT_FOUND   # C-KLT's fill (quirk Q6)
-            _reset_affine(feat)
-        elif old_val[i] < 0 and val[i] >= 0:
-            feat.x, feat.y, feat.val = xi[i], yi[i], int(val[i])
-            _reset_affine(feat)
+    _scatter(featurelist, x, y, val, old_val, overwriteAllFeatures)
     return featurelist
+
+
+def _gather(featurelist, n, overwriteAllFeatures):
+    """x, y, val arrays of the list for the C ABI (all -1 / KLT_NOT_FOUND when every slot is overwritten)."""
+    if overwriteAllFeatures:
+        return np.full(n, -1.0), np.full(n, -1.0), np.full(n, kltState.KLT_NOT_FOUND, np.int32)
+    return (np.fromiter((f.x for f in featurelist), np.float64, n), np.fromiter((f.y for f in featurelist), np.float64, n),
+            np.fromiter((f.val for f in featurelist), np.int32, n))
+
+
+def _scatter(featurelist, x, y, val, old_val, overwriteAllFeatures):
+    """Write the selection back into the KLT_Feature objects (selectGoodFeatures.py:110-128): x, y become np.int32 and
+    val a Python int (quirk Q13); lists instead of per-element ndarray indexing keep this loop off the profile."""
+    xi, yi, vi = list(x.astype(np.int32)), list(y.astype(np.int32)), val.tolist()
+    if overwriteAllFeatures:
+        for feat, xv, yv, v in zip(featurelist, xi, yi, vi):
+            d = feat.__dict__
+            if v >= 0:
+                d["x"], d["y"], d["val"] = xv, yv, v
+            else:
+                d["x"], d["y"], d["val"] = -1, -1, kltState.KLT_NOT_FOUND    # C-KLT's fill (quirk Q6)
+            d.update(_AFFINE_RESET)
+    else:
+        for i in np.flatnonzero((old_val < 0) & (val >= 0)).tolist():
+            d = featurelist[i].__dict__
+            d["x"], d["y"], d["val"] = xi[i], yi[i], vi[i]
+            d.update(_AFFINE_RESET)
 
 
 def _enforceMinimumDistance(pointlist, featurelist, ncols, nrows, mindist, min_eigenvalue, overwriteAllFeatures):
@@ -109,12 +116,7 @@ def _enforceMinimumDistance(pointlist, featurelist, ncols, nrows, mindist, min_e
     on the GPU (klt_enforce_min_distance).  Mutates and returns featurelist."""
     ctx = _capi.default_ctx()
     n = len(featurelist)
-    x = np.full(n, -1.0)
-    y = np.full(n, -1.0)
-    val = np.full(n, kltState.KLT_NOT_FOUND, np.int32)
-    if not overwriteAllFeatures:
-        for i, feat in enumerate(featurelist):
-            x[i], y[i], val[i] = feat.x, feat.y, feat.val
+    x, y, val = _gather(featurelist, n, overwriteAllFeatures)
     old_val = val.copy()
     pv = np.ascontiguousarray([p[0] for p in pointlist], np.float32)
     px = np.ascontiguousarray([p[1] for p in pointlist], np.int32)
@@ -123,17 +125,7 @@ def _enforceMinimumDistance(pointlist, featurelist, ncols, nrows, mindist, min_e
                                                   int(ncols), int(nrows), int(mindist), int(min_eigenvalue),
                                                   1 if overwriteAllFeatures else 0, n, x.ctypes.data, y.ctypes.data,
                                                   val.ctypes.data))
-    xi, yi = x.astype(np.int32), y.astype(np.int32)
-    for i, feat in enumerate(featurelist):
-        if overwriteAllFeatures:
-            if val[i] >= 0:
-                feat.x, feat.y, feat.val = xi[i], yi[i], int(val[i])
-            else:
-                feat.x, feat.y, feat.val = -1, -1, kltState.KLT_NOT_FOUND
-            _reset_affine(feat)
-        elif old_val[i] < 0 and val[i] >= 0:
-            feat.x, feat.y, feat.val = xi[i], yi[i], int(val[i])
-            _reset_affine(feat)
+    _scatter(featurelist, x, y, val, old_val, overwriteAllFeatures)
     return featurelist
 
 

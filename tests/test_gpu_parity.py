@@ -684,3 +684,31 @@ def test_windowed_large_motion_restages_its_region(gpu_ctx, oracle):
         both = (got[2] == 0) & (want[2] == 0)
         assert np.abs(got[0][both] - want[0][both]).max() <= POS_TOL and np.abs(got[1][both] - want[1][both]).max() <= POS_TOL
     assert np.mean(out["fast"][2] == out["windowed"][2]) >= 0.99
+
+
+def test_windowed_sequence_replacement_reads_real_gradients(gpu_ctx, oracle):
+    """KLTReplaceLostFeatures in sequentialMode selects on the tracking pyramid's level-0 gradients; on an image-only
+    pyramid those planes must be built first (they were once left unwritten: replacement then filled too few slots)."""
+    from pyfeaturetrack_b200 import selectGoodFeatures as sgf, trackFeatures as tf, config
+    frames = [synth_frame(k, (360, 480)) for k in range(3)]
+    res = {}
+    for mode in ("fast", "windowed"):
+        config.set_precision(track=mode)
+        tc = make_tc(nPyramidLevels=2, subsampling=2, max_residue=10.0)
+        tc.sequentialMode = True
+        f = sgf.KLTSelectGoodFeatures(tc, frames[0], 200)
+        tf.KLTTrackFeatures(tc, frames[0], frames[1], f)
+        for feat in f[::4]:                       # lose a quarter of the features on purpose
+            feat.x, feat.y, feat.val = -1.0, -1.0, -3
+        sgf.KLTReplaceLostFeatures(tc, frames[1], f)
+        res[mode] = fl_arrays(f)
+    for mode in res:
+        assert (res[mode][2] >= 0).all()          # every lost slot was refilled
+    a, b = res["fast"], res["windowed"]
+    new_a = {(int(x), int(y)) for x, y, v in zip(*a) if v > 0}
+    new_b = {(int(x), int(y)) for x, y, v in zip(*b) if v > 0}
+    assert len(new_a) == len(new_b) >= 50         # the 50 slots lost on purpose + whatever tracking lost
+    assert len(new_a & new_b) >= 0.9 * len(new_a)  # same gradients up to ~1e-6: the same corners win
+    d = np.maximum(np.abs(b[0][:, None] - b[0][None, :]), np.abs(b[1][:, None] - b[1][None, :]))
+    np.fill_diagonal(d, 1e9)
+    assert d.min() >= tc.mindist - 1              # tracked positions are fractional: the integer grid test allows -1
