@@ -3,14 +3,21 @@
 // reads gradients inside its (W+1)^2 window -- ~3 % of a 1080p frame for 1000 features -- so each warp evaluates the
 // 7-tap separable gradient pair (convolve.py:245-246) just for the pixels its feature visits:
 //
-//   * one WARP per feature; per pyramid level the warp stages a square region of the smoothed image with cp.async
-//     (window + margin + filter radius, SciPy 'reflect' indices at the image border) into shared memory,
-//   * runs the horizontal pass one region ROW per lane (sliding 7-value register window, both kernels at once) and the
-//     vertical pass one region COLUMN per lane, leaving gradx/grady of the region in shared memory,
-//   * and then iterates exactly like the dense FAST kernel (lk_track_rows_kernel), except that every bilinear sample
-//     comes from shared memory: one global round trip per level instead of one per Newton step.
-//   * The second image's region carries a margin of M pixels around the start window; if the window walks out of it the
-//     region is re-staged around the current position (warp-uniform branch; the values do not depend on the region).
+//   * one WARP per feature; per pyramid level the warp stages, with cp.async, a square region of the smoothed image of
+//     each frame into shared memory (first image: bilinear footprint of the window + filter radius; second image: the
+//     same + MARGIN pixels of slack; SciPy 'reflect' indices at the image border) and meanwhile prefetches the next
+//     level's regions into L2;
+//   * evaluates the gradient pair on the (W+1)^2 footprint of each window: horizontal pass = one region ROW per lane
+//     (sliding 7-value register window, both kernels at once, the rows of both images in one pass where 32 lanes
+//     suffice), vertical pass = one COLUMN per lane, the planes gx2, gy2, gx1, gy1 on separate lane groups;
+//   * iterates exactly like the dense FAST kernel (lk_track_rows_kernel), except that every bilinear sample comes from
+//     shared memory: one global round trip per level instead of one per Newton step;
+//   * when the window moves to another integer position the second image's gradients are re-evaluated there (0.2 times
+//     per level on the benchmark), and when it walks out of the staged region that is re-staged around the current
+//     position (warp-uniform branches; the values do not depend on where the region sits).
+//   * The shared-memory layout is bank-aware: the four horizontal-result planes and the four gradient planes start 8
+//     banks apart, and for 7x7 windows 8 lanes serve a window row and the staged regions use pitch 25, which puts the
+//     four window rows of a round on disjoint banks (ncu: conflict replays 40 % -> 16 % of the wavefronts).
 //
 // Arithmetic: float32 FMA, the same tap order as the dense FAST kernels (c[0..6] left to right / top to bottom), so the
 // window gradients agree with the planes `stream_grad_kernel` would have written to ~1 ulp; the tracked positions agree
@@ -22,10 +29,8 @@ namespace {
 
 constexpr int RG = 3;      // gradient kernel radius served here (grad_sigma = 1.0: 7 taps); other radii use the planes
 constexpr int MARGIN = 2;  // pixels of slack around the start window of the second image
-constexpr int LAZY_WARPS = 4;   // (4 or 5 CTAs/SM measured equal, 6..8 are 4-6 % slower: more warps only add shared-memory contention)
-#ifndef LAZY_MIN_CTAS
-#define LAZY_MIN_CTAS 5
-#endif
+constexpr int WIN_WARPS = 4;     // features (warps) per CTA
+constexpr int WIN_MIN_CTAS = 5;  // 4 or 5 CTAs/SM measured equal, 6..8 are 4-6 % slower: more warps only add shared-memory contention
 
 template <int W>
 struct Cfg {
@@ -196,14 +201,14 @@ __device__ __forceinline__ void prefetch_region(const float *__restrict__ img, i
 }
 
 template <int W, int MINB>
-__global__ void __launch_bounds__(LAZY_WARPS * 32, MINB)
+__global__ void __launch_bounds__(WIN_WARPS * 32, MINB)
 lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ WindowedTaps K, double *__restrict__ xs,
                    double *__restrict__ ys, int *__restrict__ vals, unsigned long long *__restrict__ iters_total,
                    int *__restrict__ assert_flag) {
     using C = Cfg<W>;
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int f = blockIdx.x * LAZY_WARPS + warp;
+    const int f = blockIdx.x * WIN_WARPS + warp;
     if (f >= A.total) return;                     // one feature per warp: all control flow below is warp-uniform
     if (vals[f] < 0) return;                      // trackFeatures.py:253
     float *s = smem + warp * C::FLOATS;
@@ -389,13 +394,13 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
 template <int W>
 int launch_windowed(klt_ctx *ctx, const TrackArgs &A, const WindowedTaps &K, double *x, double *y, int32_t *v,
                     unsigned long long *it, int *af) {
-    const int blocks = (A.total + LAZY_WARPS - 1) / LAZY_WARPS;
+    const int blocks = (A.total + WIN_WARPS - 1) / WIN_WARPS;
     // algorithmic bytes: the staged regions of both images on every level (restaging not counted) + the feature records
     const double bytes = (double)A.total * (A.n_levels * 4.0 * (Cfg<W>::N1 * Cfg<W>::N1 + Cfg<W>::N2 * Cfg<W>::N2) + 40.0);
-    const size_t smem = (size_t)LAZY_WARPS * Cfg<W>::FLOATS * sizeof(float);
-    constexpr int MINB = W <= 11 ? LAZY_MIN_CTAS : 3;
+    const size_t smem = (size_t)WIN_WARPS * Cfg<W>::FLOATS * sizeof(float);
+    constexpr int MINB = W <= 11 ? WIN_MIN_CTAS : 3;
     if (smem > 48 * 1024) KLT_CUDA(ctx, cudaFuncSetAttribute(lk_windowed_kernel<W, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KLT_LAUNCH(ctx, "lk_windowed", bytes, (lk_windowed_kernel<W, MINB><<<blocks, LAZY_WARPS * 32, smem, ctx->stream>>>(A, K, x, y, v, it, af)));
+    KLT_LAUNCH(ctx, "lk_windowed", bytes, (lk_windowed_kernel<W, MINB><<<blocks, WIN_WARPS * 32, smem, ctx->stream>>>(A, K, x, y, v, it, af)));
     return KLT_OK;
 }
 
