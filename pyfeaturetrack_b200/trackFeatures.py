@@ -4,6 +4,8 @@ signature, mutates the feature list in place and returns None; pyramids and the 
 from __future__ import print_function
 import ctypes as C
 
+import threading
+
 import numpy as np
 
 from . import _capi
@@ -48,13 +50,14 @@ class _PyramidSet(object):
         self.grady = DevicePyramid(pyr, 2)
 
 
-_density_hint = None     # (live features, pixels) of the KLTTrackFeatures call in progress: input of config's `auto` mode
+_hint = threading.local()     # .density = (features, pixels) of the KLTTrackFeatures call in progress on this thread:
+                              # the input of config's `auto` mode
 
 
 def _build_pyramids(tc, img, pyr):
     a, is_u8 = _image_u8_or_f32(img)
     taps = _taps_for_one_image(tc)
-    prec = config.track_precision_code(*(_density_hint or (None, None)))
+    prec = config.track_precision_code(*(getattr(_hint, "density", None) or (None, None)))
     if is_u8:
         # stage through pinned memory: the upload becomes a true asynchronous DMA instead of a pageable copy
         stage = pyr.ctx.pinned_stage(a.shape, id(pyr))
@@ -160,13 +163,12 @@ def KLTTrackFeatures(tc, img1, img2, featurelist):
     if use_affine and tc.affineConsistencyCheck > 2:
         raise ValueError("affineConsistencyCheck must be -1, 0, 1 or 2")
 
-    global _density_hint
     # the affine block reads gradient planes, so `auto` should build them in the fused dense pass right away
-    _density_hint = (len(featurelist) if not use_affine else 1 << 60, ncols * nrows)
+    _hint.density = (len(featurelist) if not use_affine else 1 << 60, ncols * nrows)
     try:
         pyramid1, pyramid1_gradx, pyramid1_grady, pyramid2, pyramid2_gradx, pyramid2_grady = ComputeImagePyramids(tc, img1, img2)
     finally:
-        _density_hint = None
+        _hint.density = None
     ctx = pyramid1.pyr.ctx
     x, y, val = _features_to_arrays(featurelist)
     was_live = val >= 0
