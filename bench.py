@@ -627,7 +627,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
-    ap.add_argument("--pairs", type=int, default=32, help="independent frame pairs per step per GPU")
+    ap.add_argument("--pairs", type=int, default=64, help="independent frame pairs per step per GPU")
     ap.add_argument("--distinct", type=int, default=4, help="distinct seeded pairs generated per rank (tiled to --pairs)")
     ap.add_argument("--no-bind", action="store_true", help="do not pin the process to the CPUs local to its GPU")
     ap.add_argument("--precision", default="windowed", choices=["fast", "strict", "windowed"],

@@ -213,9 +213,48 @@ stream_level0_kernel(const unsigned char *__restrict__ frames, size_t pitch, siz
 // 2*(2*RS+1) FMAs.  With so little arithmetic per byte the kernel is bound by instruction issue, so the row loop is kept
 // minimal: each lane loads and converts only its own quad (the RS neighbour columns come from the adjacent lanes by
 // shuffle), and segments that do not touch the top/bottom border walk a running row pointer (no reflection arithmetic).
+// one input row of the smooth-only kernel; STORE = the vertical filter has seen 2*RS rows (output row t - RS is complete)
+template <int RS, bool INTERIOR, bool STORE>
+__device__ __forceinline__ void smooth0_row(const unsigned char *__restrict__ b0, const unsigned char *&pr, unsigned int &w0,
+                                            unsigned int sel0, unsigned int upitch, int H, int t, int t1, bool writer,
+                                            float *&p_img, int out_pitch, float (&sa)[4][2 * RS], const StreamTaps &T) {
+    const unsigned int q0 = __byte_perm(w0, 0u, sel0);
+    float u[4 + 2 * RS];
+    // I2F.U8 with a byte selector: one instruction per pixel on the conversion pipe, which this kernel leaves idle
+    // (the level-0 kernel with its 38 FMA/px keeps the two-instruction ALU form of u8_to_f32)
+#pragma unroll
+    for (int i = 0; i < 4; i++) u[RS + i] = (float)((q0 >> (8 * i)) & 0xffu);
+    if (INTERIOR) {
+        pr += upitch;                                              // one row past the segment is still inside the image
+        w0 = __ldg(reinterpret_cast<const unsigned int *>(pr));
+        prefetch_l2(pr + (PREFETCH_ROWS - 1) * upitch);
+    } else {
+        w0 = __ldg(reinterpret_cast<const unsigned int *>(b0 + (unsigned int)reflect1(min(t + 1, t1 - 1), H) * upitch));
+        const int tp = t + PREFETCH_ROWS;
+        if (tp < t1) prefetch_l2(b0 + (unsigned int)reflect1(tp, H) * upitch);
+    }
+#pragma unroll
+    for (int k = 0; k < RS; k++) {
+        u[k] = __shfl_up_sync(FULLMASK, u[4 + k], 1);               // columns c-RS .. c-1: the left lane's last RS
+        u[RS + 4 + k] = __shfl_down_sync(FULLMASK, u[RS + k], 1);   // columns c+4 .. c+3+RS: the right lane's first RS
+    }
+    float s[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float h = T.s[0] * u[i];
+#pragma unroll
+        for (int j = 1; j < 2 * RS + 1; j++) h = fmaf(T.s[j], u[i + j], h);
+        s[i] = vacc<RS>(sa[i], T.s, h);
+    }
+    if (STORE) {
+        if (writer) *reinterpret_cast<float4 *>(p_img) = make_float4(s[0], s[1], s[2], s[3]);
+        p_img += out_pitch;
+    }
+}
+
 template <int RS, bool INTERIOR>
 __device__ __forceinline__ void smooth0_rows(const unsigned char *__restrict__ b0, unsigned int sel0, unsigned int upitch, int H,
-                                             int ys, int t0, int t1, bool writer, float *__restrict__ p_img, int out_pitch,
+                                             int ys, int t0, int t1, bool writer, float *p_img, int out_pitch,
                                              const StreamTaps &T) {
     float sa[4][2 * RS];
 #pragma unroll
@@ -224,38 +263,12 @@ __device__ __forceinline__ void smooth0_rows(const unsigned char *__restrict__ b
         for (int m = 0; m < 2 * RS; m++) sa[i][m] = 0.f;
     const unsigned char *pr = b0 + (INTERIOR ? (size_t)t0 * upitch : (size_t)reflect1(t0, H) * upitch);
     unsigned int w0 = __ldg(reinterpret_cast<const unsigned int *>(pr));
-    for (int t = t0; t < t1; t++) {
-        const unsigned int q0 = __byte_perm(w0, 0u, sel0);
-        float u[4 + 2 * RS];
-#pragma unroll
-        for (int i = 0; i < 4; i++) u[RS + i] = u8_to_f32(q0, i);
-        if (INTERIOR) {
-            pr += upitch;                                              // one row past the segment is still inside the image
-            w0 = __ldg(reinterpret_cast<const unsigned int *>(pr));
-            prefetch_l2(pr + (PREFETCH_ROWS - 1) * upitch);
-        } else {
-            w0 = __ldg(reinterpret_cast<const unsigned int *>(b0 + (unsigned int)reflect1(min(t + 1, t1 - 1), H) * upitch));
-            const int tp = t + PREFETCH_ROWS;
-            if (tp < t1) prefetch_l2(b0 + (unsigned int)reflect1(tp, H) * upitch);
-        }
-#pragma unroll
-        for (int k = 0; k < RS; k++) {
-            u[k] = __shfl_up_sync(FULLMASK, u[4 + k], 1);               // columns c-RS .. c-1: the left lane's last RS
-            u[RS + 4 + k] = __shfl_down_sync(FULLMASK, u[RS + k], 1);   // columns c+4 .. c+3+RS: the right lane's first RS
-        }
-        float s[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            float h = T.s[0] * u[i];
-#pragma unroll
-            for (int j = 1; j < 2 * RS + 1; j++) h = fmaf(T.s[j], u[i + j], h);
-            s[i] = vacc<RS>(sa[i], T.s, h);
-        }
-        if (t - RS >= ys) {
-            if (writer) *reinterpret_cast<float4 *>(p_img) = make_float4(s[0], s[1], s[2], s[3]);
-            p_img += out_pitch;
-        }
-    }
+    int t = t0;
+    for (; t < t0 + 2 * RS; t++)                       // warm-up rows: nothing to store yet (t - RS < ys)
+        smooth0_row<RS, INTERIOR, false>(b0, pr, w0, sel0, upitch, H, t, t1, writer, p_img, out_pitch, sa, T);
+#pragma unroll 2
+    for (; t < t1; t++)
+        smooth0_row<RS, INTERIOR, true>(b0, pr, w0, sel0, upitch, H, t, t1, writer, p_img, out_pitch, sa, T);
 }
 
 template <int RS>
