@@ -52,6 +52,8 @@ __device__ __forceinline__ int mirror_quad(int c, int W, bool &rev) {
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// one I2F.U8 with a byte selector (conversion pipe, a quarter of the FMA rate -- plenty for 4..8 pixels per lane-row)
+__device__ __forceinline__ float u8_byte_to_f32(unsigned int word, int byte) { return (float)((word >> (8 * byte)) & 0xffu); }
 __device__ __forceinline__ float u8_to_f32(unsigned int word, int byte) {
     // 0x4B000000 | b is the float 8388608 + b; exact for b in 0..255, and runs on the ALU/FMA pipes (no I2F)
     return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u | (unsigned int)byte)) - 8388608.0f;
@@ -120,14 +122,16 @@ struct L0State {
 template <int RS, bool LEAN>
 __device__ __forceinline__ void l0_row(L0State<RS> &S, const StreamTaps &T, int t) {
     // ---- consume the row loaded one iteration ago, then immediately issue the next row's loads ----
+    // (the halo lanes 0 and 31 need their OUTER neighbour columns too -- their smoothed values feed the gradient stage of
+    // lanes 1 and 30 -- so every lane reads its neighbour quads through L1 instead of shuffling them)
     const unsigned int q0 = __byte_perm(S.w0, 0u, S.sel0), ql = __byte_perm(S.wl, 0u, S.sell), qr = __byte_perm(S.wr, 0u, S.selr);
     float u[4 + 2 * RS];                             // columns c-RS .. c+3+RS
 #pragma unroll
-    for (int i = 0; i < 4; i++) u[RS + i] = u8_to_f32(q0, i);
+    for (int i = 0; i < 4; i++) u[RS + i] = u8_byte_to_f32(q0, i);
 #pragma unroll
     for (int k = 0; k < RS; k++) {
-        u[k] = u8_to_f32(ql, 4 - RS + k);
-        u[RS + 4 + k] = u8_to_f32(qr, k);
+        u[k] = u8_byte_to_f32(ql, 4 - RS + k);
+        u[RS + 4 + k] = u8_byte_to_f32(qr, k);
     }
     {
         const unsigned int ro = (unsigned int)reflect1(min(t + 1, S.t1 - 1), S.H) * S.pitch;
@@ -223,7 +227,7 @@ __device__ __forceinline__ void smooth0_row(const unsigned char *__restrict__ b0
     // I2F.U8 with a byte selector: one instruction per pixel on the conversion pipe, which this kernel leaves idle
     // (the level-0 kernel with its 38 FMA/px keeps the two-instruction ALU form of u8_to_f32)
 #pragma unroll
-    for (int i = 0; i < 4; i++) u[RS + i] = (float)((q0 >> (8 * i)) & 0xffu);
+    for (int i = 0; i < 4; i++) u[RS + i] = u8_byte_to_f32(q0, i);
     if (INTERIOR) {
         pr += upitch;                                              // one row past the segment is still inside the image
         w0 = __ldg(reinterpret_cast<const unsigned int *>(pr));
