@@ -430,6 +430,11 @@ def api_single_pair(wl, distinct, klt, sgf, tf, reps):
             "frame_pairs_per_sec": round(1.0 / float(np.mean(ts)), 1), "tracked_features_per_sec": round(tracked / float(np.mean(ts)), 1)}
 
 
+def _capi_sync():
+    from pyfeaturetrack_b200 import _capi
+    _capi.default_ctx().sync()
+
+
 def sequence_timing(wl, klt, sgf, tf, nframes, affine=-1):
     """Config D shape, one sequence through the drop-in API: sequentialMode, per frame KLTTrackFeatures(prev, cur) then
     KLTReplaceLostFeatures (one pyramid build per frame, selection on the device-resident gradients)."""
@@ -442,7 +447,11 @@ def sequence_timing(wl, klt, sgf, tf, nframes, affine=-1):
     for k in (1, 2):                                            # warm-up: the first two calls allocate the three pyramids
         tf.KLTTrackFeatures(tc, frames[k - 1], frames[k], fl)   # a sequence rotates through (cudaMalloc: 3-50 ms each)
         sgf.KLTReplaceLostFeatures(tc, frames[k], fl)
+    import gc
+    gc.collect()                                                # free what earlier phases left behind (multi-GB pyramids: a
+    _capi_sync()                                                # cudaFree of those inside the timed loop costs ~300 ms)
     t_track = t_repl = 0.0
+    per_frame = []
     for k in range(3, nframes + 1):
         t0 = time.perf_counter()
         tf.KLTTrackFeatures(tc, frames[k - 1], frames[k], fl)
@@ -451,12 +460,14 @@ def sequence_timing(wl, klt, sgf, tf, nframes, affine=-1):
         t2 = time.perf_counter()
         t_track += t1 - t0
         t_repl += t2 - t1
+        per_frame.append(round(1e3 * (t2 - t0), 2))
     m = nframes - 2
     return {"call": "sequentialMode%s: KLTTrackFeatures + KLTReplaceLostFeatures per frame (drop-in API, one sequence)" %
                     ("" if affine < 0 else ", affineConsistencyCheck=%d" % affine),
             "tracked_at_end": sum(1 for f in fl if f.val >= 0),
             "ms_track_per_frame": round(1e3 * t_track / m, 3), "ms_replace_per_frame": round(1e3 * t_repl / m, 3),
-            "frames_per_sec": round(m / (t_track + t_repl), 1)}
+            "frames_per_sec": round(m / (t_track + t_repl), 1),
+            "ms_per_frame_median": float(np.median(per_frame)), "ms_per_frame_max": max(per_frame)}
 
 
 def select_timing(wl, distinct, klt, sgf, ctx, reps):

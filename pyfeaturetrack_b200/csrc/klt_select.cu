@@ -287,8 +287,9 @@ compact_kernel(const float *__restrict__ val, int bx, int by, int step, int nx, 
 
 // ---- LSD radix sort of 64-bit keys (8-bit digits, stable) -----------------------------------------------
 #define RS_THREADS 256
-#define RS_ITEMS 16
+#define RS_ITEMS 4
 #define RS_CHUNK (RS_THREADS * RS_ITEMS)
+#define RS_FUSED_SCAN_BLOCKS 96   // up to this many blocks each scatter block scans the raw counts itself
 
 __global__ void __launch_bounds__(RS_THREADS)
 rs_hist_kernel(const unsigned long long *__restrict__ keys, const unsigned int *__restrict__ n_ptr, int shift,
@@ -327,14 +328,35 @@ rs_scan_kernel(unsigned int *__restrict__ hist, int total) {
     for (int i = lo; i < hi; i++) { const unsigned int v = hist[i]; hist[i] = run; run += v; }
 }
 
+template <bool SCANNED>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out,
                   const unsigned int *__restrict__ n_ptr, int shift, const unsigned int *__restrict__ hist, int nblocks) {
     __shared__ unsigned int running[256];
     __shared__ unsigned int wh[RS_THREADS / 32][256];
+    __shared__ unsigned int wtot[RS_THREADS / 32];
     const unsigned int n = *n_ptr;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    running[t] = hist[(size_t)t * nblocks + blockIdx.x];
+    if (SCANNED) {
+        running[t] = hist[(size_t)t * nblocks + blockIdx.x];
+    } else {
+        // few blocks: every block derives its own offsets from the raw per-block counts (saves the scan launch).
+        // offset(digit t, this block) = keys with a smaller digit + keys with digit t in earlier blocks
+        unsigned int total = 0, before = 0;
+        for (int b = 0; b < nblocks; b++) {
+            const unsigned int c = hist[(size_t)t * nblocks + b];
+            total += c;
+            if (b < (int)blockIdx.x) before += c;
+        }
+        unsigned int incl = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        unsigned int wbase = 0;
+        for (int w = 0; w < warp; w++) wbase += wtot[w];
+        running[t] = wbase + incl - total + before;
+    }
 #pragma unroll
     for (int w = 0; w < RS_THREADS / 32; w++) wh[w][t] = 0;
     __syncthreads();
@@ -644,8 +666,12 @@ int klt_select_device(klt_ctx *ctx, const klt_params *p, const float *gx, const 
             // 58 significant key bits -> 8 passes of 8 bits
             for (int pass = 0; pass < 8; pass++) {
                 KLT_LAUNCH(ctx, "rs_hist", 8.0 * nk, (rs_hist_kernel<<<nblocks, RS_THREADS, 0, ctx->stream>>>(src, nkeys, pass * 8, hist, nblocks)));
-                KLT_LAUNCH(ctx, "rs_scan", 0.0, (rs_scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, 256 * nblocks)));
-                KLT_LAUNCH(ctx, "rs_scatter", 16.0 * nk, (rs_scatter_kernel<<<nblocks, RS_THREADS, 0, ctx->stream>>>(src, dst, nkeys, pass * 8, hist, nblocks)));
+                if (nblocks <= RS_FUSED_SCAN_BLOCKS) {
+                    KLT_LAUNCH(ctx, "rs_scatter", 16.0 * nk, (rs_scatter_kernel<false><<<nblocks, RS_THREADS, 0, ctx->stream>>>(src, dst, nkeys, pass * 8, hist, nblocks)));
+                } else {
+                    KLT_LAUNCH(ctx, "rs_scan", 0.0, (rs_scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, 256 * nblocks)));
+                    KLT_LAUNCH(ctx, "rs_scatter", 16.0 * nk, (rs_scatter_kernel<true><<<nblocks, RS_THREADS, 0, ctx->stream>>>(src, dst, nkeys, pass * 8, hist, nblocks)));
+                }
                 unsigned long long *t = src; src = dst; dst = t;
             }
         }
