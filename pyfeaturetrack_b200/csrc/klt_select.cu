@@ -401,6 +401,7 @@ struct GreedyArgs {
     int cs, gw, gh, grid_in_smem;
     double *fx, *fy;
     int *fval;
+    int *free_slots;                 // [n_features] scratch: the fillable slots in list order (replacement mode)
     unsigned long long *consumed;    // [0] candidates consumed, [1] 1 if the keys ran out before all slots were filled
 };
 
@@ -439,27 +440,50 @@ __device__ __forceinline__ bool grid_conflict(const unsigned short *grid, int gw
 
 // One CTA.  Candidates are taken 1024 at a time: (1) all 32 warps test their candidate against the features accepted in
 // EARLIER super-batches (most candidates die here) and compact the survivors, in order, into shared memory; (2) warp 0
-// walks the survivors 32 at a time exactly like the sequential reference loop: re-test against the grid (features
-// accepted earlier in this super-batch), then accept live candidates one by one in rank order, each accept killing the
-// later candidates of the batch within distance r.
+// walks the survivors 32 at a time with exactly the result of the sequential reference loop: re-test against the grid
+// (features accepted earlier in this super-batch), then resolve the batch in parallel -- lane i is accepted iff no EARLIER
+// accepted lane lies within distance r.  That recurrence is solved by iteration: an undecided lane is rejected as soon as
+// an accepted earlier lane conflicts with it and accepted as soon as all its earlier conflicting lanes are rejected; the
+// lowest undecided lane is decided in every round, typical batches need 2-4 rounds.  Accepted lanes then fill their slots
+// (the k-th accepted candidate takes the k-th fillable slot) and register in the grid all at once.
 __global__ void __launch_bounds__(GREEDY_THREADS)
 greedy_kernel(const __grid_constant__ GreedyArgs A) {
     extern __shared__ unsigned short grid_smem[];
     __shared__ unsigned long long surv_key[GREEDY_THREADS];
     __shared__ unsigned int surv_idx[GREEDY_THREADS];
     __shared__ unsigned int warp_cnt[32];
-    __shared__ int s_indx, s_full, s_nsurv;
+    __shared__ int s_filled, s_slots, s_full, s_nsurv;
     __shared__ unsigned long long s_consumed;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int n = *A.nkeys;
     unsigned short *grid = A.grid_in_smem ? grid_smem : A.grid_global;
     if (A.r >= 0)
         for (int c = tid; c < A.gw * A.gh; c += GREEDY_THREADS) grid[c] = 0xFFFFu;
-    if (tid == 0) {
-        int indx = 0;
-        if (!A.overwrite) while (indx < A.n_features && A.fval[indx] >= 0) indx++;
-        s_indx = indx; s_full = indx >= A.n_features; s_consumed = 0ull;
+    // fillable slots: every slot (SELECTING_ALL) or, in list order, the slots of lost features (:64-69, :110-112)
+    if (tid == 0) { s_slots = A.overwrite ? A.n_features : 0; s_filled = 0; s_consumed = 0ull; }
+    __syncthreads();
+    if (!A.overwrite) {
+        for (int f0 = 0; f0 < A.n_features; f0 += GREEDY_THREADS) {
+            const int f = f0 + tid;
+            const bool lost = f < A.n_features && A.fval[f] < 0;
+            const unsigned int m = __ballot_sync(0xffffffffu, lost);
+            if (lane == 0) warp_cnt[warp] = __popc(m);
+            __syncthreads();
+            if (warp == 0) {
+                unsigned int c = warp_cnt[lane], incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                warp_cnt[lane] = incl - c;
+                if (lane == 31) s_nsurv = (int)incl;
+            }
+            __syncthreads();
+            if (lost) A.free_slots[s_slots + warp_cnt[warp] + __popc(m & ((1u << lane) - 1u))] = f;
+            __syncthreads();
+            if (tid == 0) s_slots += s_nsurv;
+            __syncthreads();
+        }
     }
+    if (tid == 0) s_full = s_slots == 0;
     __syncthreads();
     for (unsigned long long base = 0; base < n && !s_full; base += GREEDY_THREADS) {
         // ---- phase 1: parallel test against earlier super-batches, ordered compaction of the survivors ----
@@ -490,10 +514,12 @@ greedy_kernel(const __grid_constant__ GreedyArgs A) {
         __syncthreads();
         // ---- phase 2: warp 0 walks the survivors in rank order ----
         if (warp == 0) {
-            int indx = s_indx;
+            int filled = s_filled;
+            const int slots = s_slots;
             bool full = false;
             unsigned int last_off = 0;
             const int ns = s_nsurv;
+            const unsigned int lt = (1u << lane) - 1u;
             for (int b0 = 0; b0 < ns && !full; b0 += 32) {
                 const bool valid = b0 + lane < ns;
                 const unsigned long long kk = valid ? surv_key[b0 + lane] : 0ull;
@@ -502,31 +528,46 @@ greedy_kernel(const __grid_constant__ GreedyArgs A) {
                 const float val = __uint_as_float((unsigned int)(kk >> 26));
                 bool lv = valid;
                 if (lv && A.r >= 0 && grid_conflict(grid, A.gw, A.gh, A.cs, A.r, x, y)) lv = false;
-                // cell index and in-cell offsets once per candidate (all lanes in parallel), not once per accept
-                const int cx = x / A.cs, cy = y / A.cs;
-                const int cell = cy * A.gw + cx;
-                const unsigned int ofs = (unsigned int)(((x - cx * A.cs) << 8) | (y - cy * A.cs));
-                unsigned int mm;
-                while ((mm = __ballot_sync(0xffffffffu, lv)) != 0u) {
-                    const int leader = __ffs(mm) - 1;
-                    const int lx = __shfl_sync(0xffffffffu, x, leader), ly = __shfl_sync(0xffffffffu, y, leader);
-                    const float lval = __shfl_sync(0xffffffffu, val, leader);
-                    const int lcell = __shfl_sync(0xffffffffu, cell, leader);
-                    const unsigned int lofs = __shfl_sync(0xffffffffu, ofs, leader);
-                    last_off = __shfl_sync(0xffffffffu, off, leader);
-                    if (lane == 0) {
-                        A.fx[indx] = (double)lx; A.fy[indx] = (double)ly; A.fval[indx] = (int)lval;
-                        if (A.r >= 0) grid[lcell] = (unsigned short)lofs;
+                const unsigned int live_mask = __ballot_sync(0xffffffffu, lv);
+                if (live_mask == 0u) continue;
+                // earlier live lanes of the batch within distance r of this one
+                unsigned int confl = 0u;
+                if (A.r >= 0) {
+                    for (unsigned int mm = live_mask; mm; mm &= mm - 1u) {
+                        const int j = __ffs(mm) - 1;
+                        const int xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j);
+                        if (j < lane && abs(x - xj) <= A.r && abs(y - yj) <= A.r) confl |= 1u << j;
                     }
-                    if (lane == leader || (abs(x - lx) <= A.r && abs(y - ly) <= A.r)) lv = false;
-                    indx++;
-                    if (!A.overwrite) while (indx < A.n_features && A.fval[indx] >= 0) indx++;
-                    if (indx >= A.n_features) { full = true; break; }
                 }
+                unsigned int acc = 0u, rej = 0u, undecided = live_mask;
+                while (undecided) {
+                    const bool mine = (undecided >> lane) & 1u;
+                    const bool r_now = mine && (confl & acc) != 0u;
+                    const bool a_now = mine && !r_now && (confl & ~rej) == 0u;      // (confl & ~rej) has no accepted bit here
+                    const unsigned int na = __ballot_sync(0xffffffffu, a_now), nr = __ballot_sync(0xffffffffu, r_now);
+                    acc |= na; rej |= nr; undecided &= ~(na | nr);
+                }
+                // the k-th accepted candidate takes the k-th fillable slot; stop where the slots run out
+                const int nacc = __popc(acc), room = slots - filled;
+                const int take = nacc < room ? nacc : room;
+                const int rank = __popc(acc & lt);
+                const bool store = ((acc >> lane) & 1u) && rank < take;
+                if (store) {
+                    const int slot = A.overwrite ? filled + rank : A.free_slots[filled + rank];
+                    A.fx[slot] = (double)x; A.fy[slot] = (double)y; A.fval[slot] = (int)val;
+                    if (A.r >= 0) {
+                        const int cx = x / A.cs, cy = y / A.cs;
+                        grid[cy * A.gw + cx] = (unsigned short)(((x - cx * A.cs) << 8) | (y - cy * A.cs));
+                    }
+                }
+                const unsigned int stored = __ballot_sync(0xffffffffu, store);
+                last_off = __shfl_sync(0xffffffffu, off, 31 - __clz(stored));     // the last candidate that was accepted
+                filled += take;
+                if (filled >= slots) full = true;
                 __syncwarp();
             }
             if (lane == 0) {
-                s_indx = indx;
+                s_filled = filled;
                 if (full) {
                     // the reference reads one more candidate before noticing that every slot is taken (:96-112)
                     unsigned long long c = base + last_off + 1;
@@ -542,7 +583,7 @@ greedy_kernel(const __grid_constant__ GreedyArgs A) {
     if (tid == 0) {
         A.consumed[0] = s_consumed;
         A.consumed[1] = s_full ? 0ull : 1ull;
-        A.consumed[2] = (unsigned long long)s_indx;
+        A.consumed[2] = (unsigned long long)s_filled;      // SELECTING_ALL: also the first unfilled slot
     }
 }
 
@@ -606,7 +647,7 @@ int klt_select_device(klt_ctx *ctx, const klt_params *p, const float *gx, const 
     const int max_blocks = (int)((ncand + RS_CHUNK - 1) / RS_CHUNK) + 1;
     const size_t hist_b = align_up((size_t)256 * max_blocks * sizeof(unsigned int), 256);
     const size_t map_b = align_up((size_t)w * h, 256);
-    const size_t feat_b = align_up((size_t)n_features * (2 * sizeof(double) + sizeof(int)) + 64, 256);
+    const size_t feat_b = align_up((size_t)n_features * (2 * sizeof(double) + 2 * sizeof(int)) + 64, 256);
     const int cs = r >= 0 ? r + 1 : 1, gw = (w + cs - 1) / cs, gh = (h + cs - 1) / cs;
     const size_t grid_b = align_up((size_t)gw * gh * sizeof(unsigned short), 256);
     const bool grid_in_smem = grid_b <= 180 * 1024;
@@ -644,7 +685,7 @@ int klt_select_device(klt_ctx *ctx, const klt_params *p, const float *gx, const 
     GreedyArgs G;
     G.nkeys = nkeys; G.premap = replace ? map : nullptr; G.grid_global = grid_g; G.W = w; G.H = h; G.r = r;
     G.n_features = n_features; G.overwrite = replace ? 0 : 1; G.cs = cs; G.gw = gw; G.gh = gh; G.grid_in_smem = grid_in_smem ? 1 : 0;
-    G.fx = fx; G.fy = fy; G.fval = fval; G.consumed = consumed;
+    G.fx = fx; G.fy = fy; G.fval = fval; G.free_slots = fval + n_features; G.consumed = consumed;
     if (grid_in_smem) KLT_CUDA(ctx, cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_b));
     unsigned long long cons[3] = {0, 0, 0};
     const unsigned int target = (unsigned int)(32u * (unsigned int)n_features + 8192u);
@@ -709,7 +750,7 @@ int klt_greedy_presorted(klt_ctx *ctx, const unsigned long long *keys_host, unsi
     if (r > 254) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "mindist larger than 255");
     const size_t keys_b = align_up(((size_t)nk + 1) * sizeof(unsigned long long), 256);
     const size_t map_b = align_up((size_t)w * h, 256);
-    const size_t feat_b = align_up((size_t)n_features * (2 * sizeof(double) + sizeof(int)) + 64, 256);
+    const size_t feat_b = align_up((size_t)n_features * (2 * sizeof(double) + 2 * sizeof(int)) + 64, 256);
     const int cs = r >= 0 ? r + 1 : 1, gw = (w + cs - 1) / cs, gh = (h + cs - 1) / cs;
     const size_t grid_b = align_up((size_t)gw * gh * sizeof(unsigned short), 256);
     const bool grid_in_smem = grid_b <= 180 * 1024;
@@ -736,7 +777,7 @@ int klt_greedy_presorted(klt_ctx *ctx, const unsigned long long *keys_host, unsi
     GreedyArgs G;
     G.keys = keys; G.nkeys = nkeys; G.premap = overwrite ? nullptr : map; G.grid_global = grid_g; G.W = w; G.H = h; G.r = r;
     G.n_features = n_features; G.overwrite = overwrite; G.cs = cs; G.gw = gw; G.gh = gh; G.grid_in_smem = grid_in_smem ? 1 : 0;
-    G.fx = fx; G.fy = fy; G.fval = fval; G.consumed = consumed;
+    G.fx = fx; G.fy = fy; G.fval = fval; G.free_slots = fval + n_features; G.consumed = consumed;
     if (grid_in_smem) KLT_CUDA(ctx, cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_b));
     KLT_LAUNCH(ctx, "greedy", 0.0, (greedy_kernel<<<1, GREEDY_THREADS, grid_in_smem ? grid_b : 0, ctx->stream>>>(G)));
     unsigned long long cons[3] = {0, 0, 0};
