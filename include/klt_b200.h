@@ -152,7 +152,9 @@ int klt_pyr_destroy(klt_ctx *ctx, klt_pyr *pyr);
 int klt_pyr_dims(const klt_pyr *pyr, int level, int *w, int *h, int *pitch);
 size_t klt_pyr_bytes(const klt_pyr *pyr);
 /* frames: uint8 [batch][h][pitch] (host or device), frame_stride in elements between images.
- * = img.convert("F") -> smooth -> KLTPyramid.Compute -> KLTComputeGradients per level, for every image. */
+ * = img.convert("F") -> smooth -> KLTPyramid.Compute -> KLTComputeGradients per level, for every image.
+ * precision KLT_PRECISION_FAST_WINDOWED defers the last step (see above); klt_select_good_features on such a pyramid
+ * builds level 0's gradient planes first, klt_track_features_affine all of them. */
 int klt_pyr_build_u8(klt_ctx *ctx, klt_pyr *pyr, const uint8_t *frames, size_t pitch, size_t frame_stride,
                      const klt_taps *taps, int precision);
 /* same from float32 images (host or device).  already_smoothed != 0: the images ARE level 0 (pyramid.py:56 takes
