@@ -93,7 +93,10 @@ typedef struct klt_params {
     int32_t has_max_residue;      /* 0 == tc.max_residue is None (klt.py:57) */
     float max_residue;
     int32_t retain_trackers;
-    int32_t lighting_insensitive; /* must be 0: the reference raises (trackFeaturesUtils.pyx:434-437) */
+    int32_t lighting_insensitive; /* gain/bias-normalised windows as in the C the reference carries as comments
+                                   * (trackFeaturesUtils.pyx:152-239; the reference itself raises, :434-437): honoured by
+                                   * klt_track_features (exact-order kernel), refused by klt_track_iterate and together
+                                   * with the affine check.  Parity: against the oracle's restatement only. */
     /* affine consistency check (klt.py:67-73); only read by klt_track_features_affine */
     int32_t affine_consistency_check;        /* -1 off, 0 translation, 1 similarity, 2 affine */
     int32_t affine_window_width, affine_window_height;

@@ -34,7 +34,8 @@ class _TrackParams(C.Structure):
     _fields_ = [("window_width", C.c_int), ("window_height", C.c_int), ("max_iterations", C.c_int),
                 ("min_determinant", C.c_float), ("min_displacement", C.c_float), ("step_factor", C.c_float),
                 ("has_max_residue", C.c_int), ("max_residue", C.c_float), ("retain_trackers", C.c_int),
-                ("n_levels", C.c_int), ("subsampling", C.c_int), ("borderx", C.c_double), ("bordery", C.c_double)]
+                ("n_levels", C.c_int), ("subsampling", C.c_int), ("borderx", C.c_double), ("bordery", C.c_double),
+                ("lighting_insensitive", C.c_int)]
 
 
 class _AffineParams(C.Structure):
@@ -213,6 +214,7 @@ class Params:
         self.pyramid_sigma_fact = 0.9
         self.step_factor = 1.0
         self.nSkippedPixels = 0
+        self.lighting_insensitive = False   # the reference raises when set; restated from its commented C (UNPINNED)
         self.affineConsistencyCheck = -1
         self.affine_window_width = 15
         self.affine_window_height = 15
@@ -317,7 +319,8 @@ def _track_params(p):
     return _TrackParams(p.window_width, p.window_height, p.max_iterations, p.min_determinant, p.min_displacement,
                         p.step_factor, 0 if p.max_residue is None else 1,
                         0.0 if p.max_residue is None else p.max_residue, 1 if p.retainTrackers else 0,
-                        p.nPyramidLevels, int(p.subsampling), float(p.borderx), float(p.bordery))
+                        p.nPyramidLevels, int(p.subsampling), float(p.borderx), float(p.bordery),
+                        1 if getattr(p, "lighting_insensitive", False) else 0)
 
 
 def track_on_pyramids(p, pyr1, pyr2, x, y, val):

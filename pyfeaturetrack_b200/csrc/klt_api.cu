@@ -517,7 +517,6 @@ int klt_select_good_features(klt_ctx *ctx, const klt_params *params, const klt_p
 
 // ---- tracking -----------------------------------------------------------------------------------------------
 static int check_track_args(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const klt_pyr *p2) {
-    if (p->lighting_insensitive) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "lighting_insensitive: Not implemented (trackFeaturesUtils.pyx:435)");
     if (p1->w != p2->w || p1->h != p2->h || p1->n_levels != p2->n_levels || p1->ss != p2->ss || p1->batch != p2->batch)
         return klt_fail(ctx, KLT_ERR_INVALID, "pyramids differ in geometry");
     if (p->n_levels != p1->n_levels || p->subsampling != p1->ss)
@@ -535,7 +534,9 @@ static int track_impl(klt_ctx *ctx, const klt_params *params, const klt_pyr *pyr
     int rc;
     if ((rc = check_track_args(ctx, params, pyr1, pyr2))) return rc;
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (aff || !klt_windowed_supported(params, pyr1, pyr2)) {
+    if (aff && params->lighting_insensitive)
+        return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "lighting_insensitive together with the affine consistency check is not supported");
+    if (aff || params->lighting_insensitive || !klt_windowed_supported(params, pyr1, pyr2)) {
         // the affine tracker and the configurations the windowed tracker does not cover read gradient planes
         if ((rc = klt_pyr_ensure_gradients(ctx, const_cast<klt_pyr *>(pyr1)))) return rc;
         if ((rc = klt_pyr_ensure_gradients(ctx, const_cast<klt_pyr *>(pyr2)))) return rc;

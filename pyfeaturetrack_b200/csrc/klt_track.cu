@@ -57,13 +57,37 @@ __device__ float np_pairwise_sum(const float *a, int n) {
     }
 }
 
+// Gain / bias normalisation of the lighting-insensitive mode (the C carried as comments in trackFeaturesUtils.pyx:152-239;
+// the reference itself raises "Not implemented", so parity is against the oracle's restatement only).  T, P: the two
+// windows in shared memory.  Lanes 0..3 run one sequential float32 sum each, in the C's row-major order:
+//   alpha = sqrt((sum T^2/n)/(sum P^2/n)), belta = sum T/n - alpha * sum P/n; alphag = sqrt((sum T/n)/(sum P/n)) is what
+//   the gradient routine computes (it accumulates the plain values into its sum*_squared variables, pyx:222-224).
+struct LiCoeffs { float alpha, belta, alphag; };
+__device__ __forceinline__ LiCoeffs li_coefficients(const float *T, const float *P, int n, int lane) {
+    float acc = 0.f;
+    if (lane < 4) {
+        const float *s = (lane & 1) ? P : T;
+        if (lane < 2) for (int k = 0; k < n; k++) acc = __fadd_rn(acc, s[k]);
+        else for (int k = 0; k < n; k++) acc = __fadd_rn(acc, __fmul_rn(s[k], s[k]));
+    }
+    const float sum1 = __shfl_sync(0xffffffffu, acc, 0), sum2 = __shfl_sync(0xffffffffu, acc, 1);
+    const float sq1 = __shfl_sync(0xffffffffu, acc, 2), sq2 = __shfl_sync(0xffffffffu, acc, 3);
+    const float fn = (float)n;
+    LiCoeffs c;
+    c.alpha = __double2float_rn(__dsqrt_rn((double)__fdiv_rn(__fdiv_rn(sq1, fn), __fdiv_rn(sq2, fn))));
+    const float m1 = __fdiv_rn(sum1, fn), m2 = __fdiv_rn(sum2, fn);
+    c.belta = __fsub_rn(m1, __fmul_rn(c.alpha, m2));
+    c.alphag = __double2float_rn(__dsqrt_rn((double)__fdiv_rn(m1, m2)));
+    return c;
+}
+
 // trackFeatureIterateCKLT (trackFeaturesUtils.pyx:393-459) for one feature, executed by one warp with the reference's
 // exact float32 operation order.  T/Tgx/Tgy: the w*h template patches (shared memory), S: 5*w*h floats of scratch.
 __device__ __forceinline__ int iterate_exact(const float *T, const float *Tgx, const float *Tgy, float *S,
                                              const float *__restrict__ I2, const float *__restrict__ GX2,
                                              const float *__restrict__ GY2, int pitch, int nc, int nr, int w, int h,
                                              float step_factor, float small_det, float th, int max_iterations, int lane,
-                                             float &x2, float &y2, int &iteration) {
+                                             float &x2, float &y2, int &iteration, bool lighting_insensitive = false) {
     const int n = w * h, hw = w / 2, hh = h / 2;
     const float fhw = (float)hw, fhh = (float)hh, fnc = (float)nc, fnr = (float)nr;
     int status = KLT_TRACKED;
@@ -73,17 +97,41 @@ __device__ __forceinline__ int iterate_exact(const float *T, const float *Tgx, c
         const int ix = (int)x2, iy = (int)y2;
         const float ax = __double2float_rn(__dsub_rn((double)x2, (double)ix));
         const float ay = __double2float_rn(__dsub_rn((double)y2, (double)iy));
-        for (int k = lane; k < n; k += 32) {
-            const int j = k / w, i = k - j * w;
-            const size_t o = (size_t)(iy + j - hh) * pitch + (ix + i - hw);
-            const float diff = __fsub_rn(T[k], bilerp_ref(I2 + o, pitch, ax, ay));       // pyx:61-88
-            const float gx = __fadd_rn(Tgx[k], bilerp_ref(GX2 + o, pitch, ax, ay));      // -jacobian[:,0], pyx:107-128
-            const float gy = __fadd_rn(Tgy[k], bilerp_ref(GY2 + o, pitch, ax, ay));
-            S[k] = __fmul_rn(gx, gx);
-            S[n + k] = __fmul_rn(gx, gy);
-            S[2 * n + k] = __fmul_rn(gy, gy);
-            S[3 * n + k] = __fmul_rn(diff, gx);
-            S[4 * n + k] = __fmul_rn(diff, gy);
+        if (lighting_insensitive) {
+            // second image's patches first (the normalisation needs whole-window sums), then the products in place:
+            // element k is read and overwritten by the same lane
+            for (int k = lane; k < n; k += 32) {
+                const int j = k / w, i = k - j * w;
+                const size_t o = (size_t)(iy + j - hh) * pitch + (ix + i - hw);
+                S[k] = bilerp_ref(I2 + o, pitch, ax, ay);
+                S[n + k] = bilerp_ref(GX2 + o, pitch, ax, ay);
+                S[2 * n + k] = bilerp_ref(GY2 + o, pitch, ax, ay);
+            }
+            __syncwarp();
+            const LiCoeffs c = li_coefficients(T, S, n, lane);
+            for (int k = lane; k < n; k += 32) {
+                const float diff = __fsub_rn(__fsub_rn(T[k], __fmul_rn(S[k], c.alpha)), c.belta);
+                const float gx = __fadd_rn(Tgx[k], __fmul_rn(S[n + k], c.alphag));
+                const float gy = __fadd_rn(Tgy[k], __fmul_rn(S[2 * n + k], c.alphag));
+                S[k] = __fmul_rn(gx, gx);
+                S[n + k] = __fmul_rn(gx, gy);
+                S[2 * n + k] = __fmul_rn(gy, gy);
+                S[3 * n + k] = __fmul_rn(diff, gx);
+                S[4 * n + k] = __fmul_rn(diff, gy);
+            }
+        } else {
+            for (int k = lane; k < n; k += 32) {
+                const int j = k / w, i = k - j * w;
+                const size_t o = (size_t)(iy + j - hh) * pitch + (ix + i - hw);
+                const float diff = __fsub_rn(T[k], bilerp_ref(I2 + o, pitch, ax, ay));       // pyx:61-88
+                const float gx = __fadd_rn(Tgx[k], bilerp_ref(GX2 + o, pitch, ax, ay));      // -jacobian[:,0], pyx:107-128
+                const float gy = __fadd_rn(Tgy[k], bilerp_ref(GY2 + o, pitch, ax, ay));
+                S[k] = __fmul_rn(gx, gx);
+                S[n + k] = __fmul_rn(gx, gy);
+                S[2 * n + k] = __fmul_rn(gy, gy);
+                S[3 * n + k] = __fmul_rn(diff, gx);
+                S[4 * n + k] = __fmul_rn(diff, gy);
+            }
         }
         __syncwarp();
         float acc = 0.f;                      // lanes 0..4: one sequential float32 sum each (pyx:246-305)
@@ -162,7 +210,7 @@ lk_track_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ xs, do
         float x2 = __double2float_rn(xout), y2 = __double2float_rn(yout);
         int iteration = 0;
         const int status0 = iterate_exact(T, Tgx, Tgy, S, I2, GX2, GY2, pitch, nc, nr, A.w, A.h, A.step_factor, A.small_det, A.th,
-                                          A.max_iterations, lane, x2, y2, iteration);
+                                          A.max_iterations, lane, x2, y2, iteration, A.lighting_insensitive != 0);
         int status = status0;
         my_iters += iteration;
 
@@ -174,10 +222,20 @@ lk_track_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ xs, do
             const int ix = (int)x2, iy = (int)y2;
             const float ax = __double2float_rn(__dsub_rn((double)x2, (double)ix));
             const float ay = __double2float_rn(__dsub_rn((double)y2, (double)iy));
-            for (int k = lane; k < n; k += 32) {
-                const int j = k / A.w, i = k - j * A.w;
-                const size_t o = (size_t)(iy + j - hh) * pitch + (ix + i - hw);
-                S[k] = fabsf(__fsub_rn(T[k], bilerp_ref(I2 + o, pitch, ax, ay)));
+            if (A.lighting_insensitive) {         // trackFeatures.py:120-121 (the callee is undefined in the reference)
+                for (int k = lane; k < n; k += 32) {
+                    const int j = k / A.w, i = k - j * A.w;
+                    S[k] = bilerp_ref(I2 + (size_t)(iy + j - hh) * pitch + (ix + i - hw), pitch, ax, ay);
+                }
+                __syncwarp();
+                const LiCoeffs c = li_coefficients(T, S, n, lane);
+                for (int k = lane; k < n; k += 32) S[k] = fabsf(__fsub_rn(__fsub_rn(T[k], __fmul_rn(S[k], c.alpha)), c.belta));
+            } else {
+                for (int k = lane; k < n; k += 32) {
+                    const int j = k / A.w, i = k - j * A.w;
+                    const size_t o = (size_t)(iy + j - hh) * pitch + (ix + i - hw);
+                    S[k] = fabsf(__fsub_rn(T[k], bilerp_ref(I2 + o, pitch, ax, ay)));
+                }
             }
             __syncwarp();
             float res = 0.f;
@@ -427,14 +485,15 @@ int klt_launch_track(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const
     A.retain = p->retain_trackers;
     A.borderx = p->borderx; A.bordery = p->bordery;
     A.n_per_image = n_per_image; A.total = n_per_image * p1->batch;
+    A.lighting_insensitive = p->lighting_insensitive ? 1 : 0;
     if (A.total <= 0) return KLT_OK;
     // image-only pyramids (FAST_WINDOWED builds): gradients are evaluated inside the tracking windows
-    if (!klt_pyr_has_gradients(p1) || !klt_pyr_has_gradients(p2)) {
+    if (!A.lighting_insensitive && (!klt_pyr_has_gradients(p1) || !klt_pyr_has_gradients(p2))) {
         if (!klt_windowed_supported(p, p1, p2))
             return klt_fail(ctx, KLT_ERR_INVALID, "image-only pyramid reached the plane-based tracker (internal error)");
         return klt_launch_track_windowed(ctx, A, p1, p2, x_dev, y_dev, val_dev, iters_dev, assert_dev);
     }
-    if (!exact && A.w == A.h) {          // FAST pyramids: float32 row-per-lane kernel for the common window sizes
+    if (!exact && A.w == A.h && !A.lighting_insensitive) {   // FAST pyramids: float32 row-per-lane kernel for the common window sizes
         switch (A.w) {
             case 3: return launch_rows<3>(ctx, A, x_dev, y_dev, val_dev, iters_dev, assert_dev);
             case 5: return launch_rows<5>(ctx, A, x_dev, y_dev, val_dev, iters_dev, assert_dev);

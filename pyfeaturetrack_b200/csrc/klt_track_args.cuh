@@ -15,6 +15,7 @@ struct TrackArgs {
     int retain;
     double borderx, bordery;
     int n_per_image, total;
+    int lighting_insensitive;   // gain / bias normalisation of trackFeaturesUtils.pyx:152-239 (exact-order kernel only)
 };
 
 // gradient kernels of the two pyramids (the reference's kernel cache can hand different ones to the two images,

@@ -157,9 +157,11 @@ def KLTTrackFeatures(tc, img1, img2, featurelist):
         print("(KLT) Tracking {0} features in a {1} by {2} image...  ".format(
             KLTCountRemainingFeatures(featurelist), ncols, nrows))
     _fix_window(tc, "Tracking context")
-    if tc.lighting_insensitive:
-        raise Exception("Not implemented")                      # trackFeaturesUtils.pyx:435
     use_affine = tc.affineConsistencyCheck >= 0
+    if tc.lighting_insensitive and use_affine:
+        # the reference raises for lighting_insensitive alone (trackFeaturesUtils.pyx:435); this build implements the
+        # mode from the C the reference carries as comments (:152-239) -- but not together with the affine check
+        raise Exception("Not implemented")
     if use_affine and tc.affineConsistencyCheck > 2:
         raise ValueError("affineConsistencyCheck must be -1, 0, 1 or 2")
 

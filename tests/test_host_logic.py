@@ -126,6 +126,7 @@ def test_unported_paths_fail_like_the_reference(img01):
     tc = klt.KLT_TrackingContext()
     f = klt.KLT_Feature(); f.x, f.y, f.val = 100.0, 100.0, 0
     tc.lighting_insensitive = True
+    tc.affineConsistencyCheck = 2      # lighting_insensitive alone is implemented here (the reference raises); with affine it is not
     with pytest.raises(Exception, match="Not implemented"):
         tf.KLTTrackFeatures(tc, img01[0], img01[1], [f])
     with pytest.raises(AssertionError):
@@ -200,3 +201,26 @@ def test_precision_modes_and_host_binding():
     import torch
     if not torch.cuda.is_available():
         assert shard.bind_host_to_gpu(0) == 0
+
+
+def test_oracle_lighting_insensitive_restatement():
+    """Lighting-insensitive tracking, restated from the C the reference carries as comments (trackFeaturesUtils.pyx:152-239;
+    the reference raises instead): under a gain + bias change of the second frame the plain tracker rejects most features
+    with KLT_LARGE_RESIDUE, the normalised one keeps tracking them to the same displacement."""
+    from oracle import klt_oracle as O
+    from pyfeaturetrack_b200 import synth
+    a, b = synth.frame_pair(240, 320, seed=5, shift=(1.6, -2.2))
+    dim = np.clip(0.6 * b.astype(np.float32) + 40, 0, 255).astype(np.uint8)
+    res = {}
+    for li in (False, True):
+        p = O.Params(nPyramidLevels=2, subsampling=2, max_residue=10.0, lighting_insensitive=li)
+        sel = O.select_good_features(p, a, 100)
+        for name, img2 in (("same", b), ("dim", dim)):
+            x, y, v, _ = O.track_features(p, a, img2, *sel)
+            ok = v == 0
+            res[(li, name)] = (int(ok.sum()), float(np.median((x - sel[0])[ok])), float(np.median((y - sel[1])[ok])), v)
+    assert res[(False, "same")][0] >= 90 and res[(True, "same")][0] >= 90
+    assert res[(False, "dim")][0] < 40 and (res[(False, "dim")][3] == -5).sum() > 50     # large residue without normalisation
+    assert res[(True, "dim")][0] >= 80                                                  # recovered with it
+    for k in ((True, "same"), (True, "dim")):
+        assert abs(res[k][1] - res[(False, "same")][1]) < 0.1 and abs(res[k][2] - res[(False, "same")][2]) < 0.1
