@@ -14,7 +14,7 @@ import sys
 __version__ = "0.1.0"
 
 DROPIN_MODULES = ["error", "klt_util", "convolve", "klt", "pyramid", "goodFeaturesUtils", "trackFeaturesUtils",
-                  "selectGoodFeatures", "trackFeatures", "writeFeatures"]
+                  "selectGoodFeatures", "trackFeatures", "writeFeatures", "storeFeatures"]
 
 
 def install_dropin():

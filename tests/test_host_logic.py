@@ -224,3 +224,30 @@ def test_oracle_lighting_insensitive_restatement():
     assert res[(True, "dim")][0] >= 80                                                  # recovered with it
     for k in ((True, "same"), (True, "dim")):
         assert abs(res[k][1] - res[(False, "same")][1]) < 0.1 and abs(res[k][2] - res[(False, "same")][2]) < 0.1
+
+
+def test_feature_table_and_history_round_trip():
+    """storeFeatures: the table/history routines the reference only declares (klt.py:272-283)."""
+    from pyfeaturetrack_b200 import storeFeatures as sf, klt
+    nframes, nfeat = 4, 5
+    ft = sf.KLTCreateFeatureTable(nframes, nfeat)
+    fl = sf.KLTCreateFeatureList(nfeat)
+    for frame in range(nframes):
+        for i, f in enumerate(fl):
+            f.x, f.y, f.val = 10.0 * i + frame, 2.0 * i - frame, (0 if frame else 100 + i) if i != 3 or frame < 2 else -4
+        sf.KLTStoreFeatureList(fl, ft, frame)
+    out = sf.KLTCreateFeatureList(nfeat)
+    sf.KLTExtractFeatureList(out, ft, 2)
+    assert [(f.x, f.y, f.val) for f in out] == [(10.0 * i + 2, 2.0 * i - 2, 0 if i != 3 else -4) for i in range(nfeat)]
+    fh = sf.KLTCreateFeatureHistory(nframes)
+    sf.KLTExtractFeatureHistory(fh, ft, 3)
+    assert [r.val for r in fh.feature] == [103, 0, -4, -4]
+    fh.feature[1].x = 999.0
+    sf.KLTStoreFeatureHistory(fh, ft, 3)
+    x, y, v = sf.table_arrays(ft)
+    assert x.shape == (nfeat, nframes) and x[3, 1] == 999.0 and v[3, 3] == -4 and v[0, 0] == 100
+    with pytest.raises(SystemExit):
+        sf.KLTStoreFeatureList(fl, ft, nframes)                   # frame out of range: KLTError exits like the C library
+    with pytest.raises(SystemExit):
+        sf.KLTStoreFeatureList(fl[:-1], ft, 0)
+    assert isinstance(ft, klt.KLT_FeatureTable) and isinstance(fh, klt.KLT_FeatureHistory)
