@@ -752,3 +752,75 @@ def test_lighting_insensitive_vs_restatement(gpu_ctx, oracle):
     tc.affineConsistencyCheck = 2
     with pytest.raises(Exception, match="Not implemented"):
         tf.KLTTrackFeatures(tc, a, dim, f)
+
+
+def test_windowed_corner_configurations(gpu_ctx, oracle):
+    """Image-only pyramids off the beaten path: float32 input images, a small image whose staged regions hang over the
+    border (reflect path), a gradient kernel the windowed tracker does not serve (planes built on demand), and a batch
+    of pairs through klt_track_pairs_u8."""
+    from pyfeaturetrack_b200 import _capi, selectGoodFeatures as sgf, trackFeatures as tf, config
+    config.set_precision(track="windowed")
+    # (1) float32 images (values off the uint8 grid)
+    a, b = _synth(61, (240, 320), shift=(1.3, -0.8))
+    af, bf = a.astype(np.float32) * 0.5 + 3.25, b.astype(np.float32) * 0.5 + 3.25
+    kw = dict(nPyramidLevels=2, subsampling=2, max_residue=10.0)
+    p, tc = P(oracle, **kw), make_tc(**kw)
+    sel = oracle.select_good_features(p, af, 80)
+    want = oracle.track_features(p, af, bf, *sel)[:3]
+    f = sgf.KLTSelectGoodFeatures(tc, af, 80)
+    tf.KLTTrackFeatures(tc, af, bf, f)
+    got = fl_arrays(f)
+    assert np.mean(got[2] == want[2]) >= 0.97
+    both = (got[2] == 0) & (want[2] == 0)
+    assert both.sum() > 60 and np.abs(got[0][both] - want[0][both]).max() <= POS_TOL
+    # (2) small image, 3 levels: at the coarsest level (30 x 40) the staged 16 x 16 regions of the outer features hang over
+    # the image border (reflected staging path)
+    a, b = _synth(62, (120, 160), shift=(0.6, -0.4))
+    kw = dict(nPyramidLevels=3, subsampling=2, max_residue=12.0, window_width=5, window_height=5)
+    p, tc = P(oracle, **kw), make_tc(**kw)
+    sel = oracle.select_good_features(p, a, 50)
+    want = oracle.track_features(p, a, b, *sel)[:3]
+    f = sgf.KLTSelectGoodFeatures(tc, a, 50)
+    tf.KLTTrackFeatures(tc, a, b, f)
+    got = fl_arrays(f)
+    assert np.mean(got[2] == want[2]) >= 0.95
+    both = (got[2] == 0) & (want[2] == 0)
+    assert both.sum() >= 30 and np.abs(got[0][both] - want[0][both]).max() <= POS_TOL and np.abs(got[1][both] - want[1][both]).max() <= POS_TOL
+    # (3) grad_sigma 1.5: 9- or 11-tap gradient kernels -> the windowed tracker declines, the planes are built on demand
+    a, b = _synth(63, (240, 320), shift=(1.1, 1.4))
+    kw = dict(nPyramidLevels=2, subsampling=2, max_residue=10.0, grad_sigma=1.5)
+    p, tc = P(oracle, **kw), make_tc(**kw)
+    sel = oracle.select_good_features(p, a, 80)
+    want = oracle.track_features(p, a, b, *sel)[:3]
+    f = sgf.KLTSelectGoodFeatures(tc, a, 80)
+    tf.KLTTrackFeatures(tc, a, b, f)
+    got = fl_arrays(f)
+    assert np.mean(got[2] == want[2]) >= 0.97
+    both = (got[2] == 0) & (want[2] == 0)
+    assert np.abs(got[0][both] - want[0][both]).max() <= POS_TOL
+    # (4) a batch of pairs in one call == the same pairs one at a time (bit for bit: same kernels, same data)
+    H, W, B, n = 240, 320, 3, 64
+    kw = dict(nPyramidLevels=2, subsampling=2, max_residue=10.0)
+    p, tc = P(oracle, **kw), make_tc(**kw)
+    taps, params = tf._taps_for_one_image(tc), sgf.make_params(tc)
+    f1 = np.empty((B, H, W), np.uint8); f2 = np.empty((B, H, W), np.uint8)
+    xs = np.empty((B, n)); ys = np.empty((B, n)); vs = np.empty((B, n), np.int32)
+    for k in range(B):
+        f1[k], f2[k] = _synth(70 + k, (H, W))
+        xs[k], ys[k], vs[k] = oracle.select_good_features(p, f1[k], n)
+    single = []
+    for k in range(B):
+        q1, q2 = _capi.Pyramid(gpu_ctx, W, H, 2, 2, 1), _capi.Pyramid(gpu_ctx, W, H, 2, 2, 1)
+        x, y, v = xs[k].copy(), ys[k].copy(), vs[k].copy()
+        gpu_ctx.check(_capi.lib().klt_track_pairs_u8(gpu_ctx.handle, C.byref(params), C.byref(taps), _capi.PRECISION_FAST_WINDOWED,
+                                                     q1.handle, q2.handle, f1[k].ctypes.data, f2[k].ctypes.data, W, W * H, n,
+                                                     x.ctypes.data, y.ctypes.data, v.ctypes.data))
+        single.append((x, y, v)); q1.close(); q2.close()
+    q1, q2 = _capi.Pyramid(gpu_ctx, W, H, 2, 2, B), _capi.Pyramid(gpu_ctx, W, H, 2, 2, B)
+    gpu_ctx.check(_capi.lib().klt_track_pairs_u8(gpu_ctx.handle, C.byref(params), C.byref(taps), _capi.PRECISION_FAST_WINDOWED,
+                                                 q1.handle, q2.handle, f1.ctypes.data, f2.ctypes.data, W, W * H, n,
+                                                 xs.ctypes.data, ys.ctypes.data, vs.ctypes.data))
+    for k in range(B):
+        assert_features_equal((xs[k], ys[k], vs[k]), single[k])
+        assert_features_close((xs[k], ys[k], vs[k]), oracle.track_features(p, f1[k], f2[k], *oracle.select_good_features(p, f1[k], n))[:3])
+    q1.close(); q2.close()
