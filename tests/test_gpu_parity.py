@@ -702,6 +702,14 @@ def test_windowed_sequence_replacement_reads_real_gradients(gpu_ctx, oracle):
             feat.x, feat.y, feat.val = -1.0, -1.0, -3
         sgf.KLTReplaceLostFeatures(tc, frames[1], f)
         res[mode] = fl_arrays(f)
+        if mode == "windowed":                    # the reference's tc.pyramid_last_gradx / _grady views keep working
+            p = P(oracle, nPyramidLevels=2, subsampling=2)
+            simg = oracle.smooth(frames[1].astype(np.float32), p.smooth_sigma(), p.cache)
+            want_gx, want_gy = oracle.gradients(simg, p.grad_sigma, p.cache)
+            got_gx, got_gy = tc.pyramid_last_gradx.img[0], tc.pyramid_last_grady.img[0]
+            assert np.abs(got_gx - want_gx).max() <= 1e-5 * np.abs(want_gx).max()
+            assert np.abs(got_gy - want_gy).max() <= 1e-5 * np.abs(want_gy).max()
+            assert tc.pyramid_last_gradx.img[1].shape == (180, 240)      # coarser planes are built on demand as well
     for mode in res:
         assert (res[mode][2] >= 0).all()          # every lost slot was refilled
     a, b = res["fast"], res["windowed"]
