@@ -290,6 +290,27 @@ def run_b200(args):
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t[0])
+    # the same end-to-end step from ONE host thread on ONE context: asynchronous calls, two sets of pinned result
+    # buffers, the upload of step k+1 overlapping the kernels of step k through the context's two staging halves
+    def run_e2e_async(steps):
+        sets = [(hx, hy, hv), (hxb, hyb, hvb)]
+        for k in range(steps):
+            s_ = k & 1
+            if k >= 2:
+                ctx.check(lib.klt_async_wait(ctx.handle, s_))           # step k-2 is complete: its buffers are free again
+            ax, ay, av = sets[s_]
+            ax[:] = x0; ay[:] = y0; av[:] = v0
+            ctx.check(lib.klt_track_pairs_u8_async(ctx.handle, C.byref(params), C.byref(taps), prec, p1.handle, p2.handle,
+                                                   f1.ctypes.data, f2.ctypes.data, W, W * H, n, ax.ctypes.data, ay.ctypes.data,
+                                                   av.ctypes.data))
+            ctx.check(lib.klt_async_mark(ctx.handle, s_))
+        ctx.check(lib.klt_async_result(ctx.handle))
+    run_e2e_async(4)
+    barrier()
+    t0 = time.perf_counter()
+    run_e2e_async(e2e_steps)
+    async_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
     single_ms, _, _ = timed(step_e2e, max(3, args.steps // 2), 3)     # one context, one call at a time (latency view)
     single_ms /= max(3, args.steps // 2)
     e2e_tracked = int((hv == 0).sum())
@@ -378,7 +399,10 @@ def run_b200(args):
                 "h2d_bytes_per_step": 2 * frame_bytes + feat_bytes, "d2h_bytes_per_step": feat_bytes,
                 "api": "klt_track_pairs_u8 (C ABI) with pinned host frames and host feature arrays; two host threads with one "
                        "context each alternate steps (upload of one overlaps kernels of the other); wall clock",
-                "ms_per_step_single_context": round(single_ms, 4)},
+                "ms_per_step_single_context": round(single_ms, 4),
+                "async_one_thread": {"api": "klt_track_pairs_u8_async + klt_async_mark/wait on one context from one host thread",
+                                     "ms_per_step": round(async_ms / e2e_steps, 4),
+                                     "frame_pairs_per_sec_per_gpu": round(B / (async_ms / e2e_steps) * 1e3, 2)}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,

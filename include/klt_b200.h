@@ -246,6 +246,20 @@ int klt_enforce_min_distance(klt_ctx *ctx, int n_points, const float *pval, cons
 int klt_track_pairs_u8(klt_ctx *ctx, const klt_params *params, const klt_taps *taps, int precision, klt_pyr *pyr1,
                        klt_pyr *pyr2, const uint8_t *frames1, const uint8_t *frames2, size_t pitch,
                        size_t frame_stride, int n_per_image, double *x, double *y, int32_t *val);
+/* The same without waiting: everything, including the download of x / y / val, is only enqueued (pass pinned host
+ * memory from klt_host_alloc, or device pointers; the frames must stay untouched until the stream has consumed them).
+ * Two staging halves alternate between calls, so the upload of call k+1 overlaps the kernels of call k on ONE context
+ * and one host thread -- SURVEY 8(f) rank 2.  klt_async_result waits for the stream and reports whether any of the calls
+ * since the last klt_async_result hit the reference's AssertionError case (KLT_ERR_ASSERT), else KLT_OK. */
+int klt_track_pairs_u8_async(klt_ctx *ctx, const klt_params *params, const klt_taps *taps, int precision,
+                             klt_pyr *pyr1, klt_pyr *pyr2, const uint8_t *frames1, const uint8_t *frames2,
+                             size_t pitch, size_t frame_stride, int n_per_image, double *x, double *y, int32_t *val);
+int klt_async_result(klt_ctx *ctx);
+/* Host-side completion marks for pipelining asynchronous calls: klt_async_mark(slot) records "everything enqueued so far"
+ * (slot 0..15), klt_async_wait(slot) blocks the host until that point has been reached -- e.g. before reusing the pinned
+ * buffers of the call before last. */
+int klt_async_mark(klt_ctx *ctx, int slot);
+int klt_async_wait(klt_ctx *ctx, int slot);
 
 #ifdef __cplusplus
 }

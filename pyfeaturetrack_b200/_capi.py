@@ -106,6 +106,11 @@ SIGNATURES = {
     "klt_enforce_min_distance": (_i, [_vp, _i, _fp, _ip, _ip, _i, _i, _i, _i, _i, _i, _dp, _dp, _ip]),
     "klt_track_pairs_u8": (_i, [_vp, C.POINTER(Params), C.POINTER(Taps), _i, _vp, _vp, _u8p, _u8p, _sz, _sz, _i,
                                 _dp, _dp, _ip]),
+    "klt_track_pairs_u8_async": (_i, [_vp, C.POINTER(Params), C.POINTER(Taps), _i, _vp, _vp, _u8p, _u8p, _sz, _sz, _i,
+                                      _dp, _dp, _ip]),
+    "klt_async_result": (_i, [_vp]),
+    "klt_async_mark": (_i, [_vp, _i]),
+    "klt_async_wait": (_i, [_vp, _i]),
 }
 
 

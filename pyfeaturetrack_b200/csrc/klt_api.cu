@@ -128,8 +128,12 @@ int klt_ctx_create(int device, void *stream, klt_ctx **out) {
     cudaEventCreate(&ctx->ev1);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 16; i++) cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->compute_done, cudaEventDisableTiming);
+    for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&ctx->half_free[i], cudaEventDisableTiming);
+    ctx->half_next = 0;
     ctx->frames_dev = nullptr; ctx->frames_bytes = 0;
+    ctx->async_flag_dev = nullptr;
+    for (int i = 0; i < 16; i++) cudaEventCreateWithFlags(&ctx->marks[i], cudaEventDisableTiming);
+    if (cudaMalloc(&ctx->async_flag_dev, 256) == cudaSuccess) cudaMemset(ctx->async_flag_dev, 0, 256);
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->num_sms = prop.multiProcessorCount;
@@ -153,7 +157,9 @@ int klt_ctx_destroy(klt_ctx *ctx) {
     if (ctx->frames_dev) cudaFree(ctx->frames_dev);
     cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->chunk_ev[i]);
-    cudaEventDestroy(ctx->compute_done);
+    for (int i = 0; i < 2; i++) cudaEventDestroy(ctx->half_free[i]);
+    if (ctx->async_flag_dev) cudaFree(ctx->async_flag_dev);
+    for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->marks[i]);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -529,7 +535,7 @@ static int check_track_args(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1
 }
 
 static int track_impl(klt_ctx *ctx, const klt_params *params, const klt_pyr *pyr1, const klt_pyr *pyr2, int n_per_image,
-                      double *x, double *y, int32_t *val, klt_affine *aff, int64_t *n_iterations) {
+                      double *x, double *y, int32_t *val, klt_affine *aff, int64_t *n_iterations, bool async = false) {
     if (!ctx || !params || !pyr1 || !pyr2 || !x || !y || !val || n_per_image < 0) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
     int rc;
     if ((rc = check_track_args(ctx, params, pyr1, pyr2))) return rc;
@@ -553,7 +559,7 @@ static int track_impl(klt_ctx *ctx, const klt_params *params, const klt_pyr *pyr
     if ((rc = klt_ws_reserve(ctx, 6 * fbytes + 256))) return rc;
     char *wsp = (char *)ctx->ws;
     unsigned long long *iters = (unsigned long long *)wsp;
-    int *aflag = (int *)(wsp + 8);
+    int *aflag = async ? ctx->async_flag_dev : (int *)(wsp + 8);     // asynchronous calls share one sticky flag
     double *dx = x, *dy = y;
     int32_t *dval = val;
     KLT_CUDA(ctx, cudaMemsetAsync(wsp, 0, 16, ctx->stream));
@@ -578,6 +584,7 @@ static int track_impl(klt_ctx *ctx, const klt_params *params, const klt_pyr *pyr
         KLT_CUDA(ctx, cudaMemcpyAsync(y, dy, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         KLT_CUDA(ctx, cudaMemcpyAsync(val, dval, total * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     }
+    if (async) return KLT_OK;                    // results land when the stream gets there: klt_sync / klt_async_result
     if (host || n_iterations) {
         unsigned long long res[2] = {0, 0};
         KLT_CUDA(ctx, cudaMemcpyAsync(res, wsp, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -768,23 +775,25 @@ int klt_enforce_min_distance(klt_ctx *ctx, int n_points, const float *pval, cons
                                 x, y, val);
 }
 
-int klt_track_pairs_u8(klt_ctx *ctx, const klt_params *params, const klt_taps *taps, int precision, klt_pyr *pyr1,
-                       klt_pyr *pyr2, const uint8_t *frames1, const uint8_t *frames2, size_t pitch, size_t frame_stride,
-                       int n_per_image, double *x, double *y, int32_t *val) {
+static int track_pairs_impl(klt_ctx *ctx, const klt_params *params, const klt_taps *taps, int precision, klt_pyr *pyr1,
+                            klt_pyr *pyr2, const uint8_t *frames1, const uint8_t *frames2, size_t pitch, size_t frame_stride,
+                            int n_per_image, double *x, double *y, int32_t *val, bool async) {
     if (!ctx || !params || !taps || !pyr1 || !pyr2 || !frames1 || !frames2) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
     int rc;
     const bool host1 = !klt_is_device_ptr(frames1), host2 = !klt_is_device_ptr(frames2);
     if (!host1 && !host2) {
         if ((rc = klt_pyr_build_u8(ctx, pyr1, frames1, pitch, frame_stride, taps, precision))) return rc;
         if ((rc = klt_pyr_build_u8(ctx, pyr2, frames2, pitch, frame_stride, taps, precision))) return rc;
-        return klt_track_features(ctx, params, pyr1, pyr2, n_per_image, x, y, val, nullptr);
+        return track_impl(ctx, params, pyr1, pyr2, n_per_image, x, y, val, nullptr, nullptr, async);
     }
     if (host1 != host2) return klt_fail(ctx, KLT_ERR_INVALID, "frames1 and frames2 must both be host or both be device");
     if (pyr1->batch != pyr2->batch || pyr1->w != pyr2->w || pyr1->h != pyr2->h) return klt_fail(ctx, KLT_ERR_INVALID, "pyramids differ in geometry");
     if (pitch < (size_t)pyr1->w) return klt_fail(ctx, KLT_ERR_INVALID, "pitch smaller than width");
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
     // Host frames: the batch is cut into chunks; the H2D copy of chunk k+1 (copy stream) overlaps the pyramid builds of
-    // chunk k (compute stream).  PCIe, not the kernels, bounds this path.
+    // chunk k (compute stream), and the two staging halves alternate between calls, so the upload of the NEXT call overlaps
+    // the tracking kernels of this one when the caller does not wait in between (klt_track_pairs_u8_async, or a second
+    // context on another thread).  PCIe, not the kernels, bounds this path.
     const int B = pyr1->batch;
     const size_t one = (size_t)(pyr1->h - 1) * pitch + pyr1->w;                 // bytes actually read of one frame
     const size_t per_set = (size_t)(B - 1) * frame_stride + one;
@@ -793,17 +802,18 @@ int klt_track_pairs_u8(klt_ctx *ctx, const klt_params *params, const klt_taps *t
         KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         KLT_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
         if (ctx->frames_dev) { KLT_CUDA(ctx, cudaFree(ctx->frames_dev)); ctx->frames_dev = nullptr; ctx->frames_bytes = 0; }
-        cudaError_t e = cudaMalloc(&ctx->frames_dev, 2 * set_stride);
-        if (e != cudaSuccess) return klt_fail(ctx, KLT_ERR_NOMEM, "cudaMalloc(%zu) for frame staging failed: %s", 2 * set_stride, cudaGetErrorString(e));
+        cudaError_t e = cudaMalloc(&ctx->frames_dev, 4 * set_stride);
+        if (e != cudaSuccess) return klt_fail(ctx, KLT_ERR_NOMEM, "cudaMalloc(%zu) for frame staging failed: %s", 4 * set_stride, cudaGetErrorString(e));
         ctx->frames_bytes = 2 * set_stride;
     }
-    uint8_t *d1 = (uint8_t *)ctx->frames_dev, *d2 = d1 + set_stride;
+    const int half = ctx->half_next;
+    ctx->half_next ^= 1;
+    uint8_t *d1 = (uint8_t *)ctx->frames_dev + (size_t)half * ctx->frames_bytes, *d2 = d1 + set_stride;
     int nchunks = B < 4 ? 1 : (B < 16 ? 2 : 4);
     if (nchunks > 16) nchunks = 16;
     const int per_chunk = (B + nchunks - 1) / nchunks;
-    // the staging buffers may still be read by kernels of the previous call
-    KLT_CUDA(ctx, cudaEventRecord(ctx->compute_done, ctx->stream));
-    KLT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_done, 0));
+    // this half may still be read by the builds of the call before last
+    KLT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->half_free[half], 0));
     bool windowed;
     begin_build(pyr1, taps, precision, &windowed);
     precision = begin_build(pyr2, taps, precision, &windowed);
@@ -823,7 +833,45 @@ int klt_track_pairs_u8(klt_ctx *ctx, const klt_params *params, const klt_taps *t
         if ((rc = build_u8_device(ctx, pyr1, d1 + off, pitch, frame_stride, taps, precision, first, count, windowed))) return rc;
         if ((rc = build_u8_device(ctx, pyr2, d2 + off, pitch, frame_stride, taps, precision, first, count, windowed))) return rc;
     }
-    return klt_track_features(ctx, params, pyr1, pyr2, n_per_image, x, y, val, nullptr);
+    KLT_CUDA(ctx, cudaEventRecord(ctx->half_free[half], ctx->stream));
+    return track_impl(ctx, params, pyr1, pyr2, n_per_image, x, y, val, nullptr, nullptr, async);
+}
+
+int klt_track_pairs_u8(klt_ctx *ctx, const klt_params *params, const klt_taps *taps, int precision, klt_pyr *pyr1,
+                       klt_pyr *pyr2, const uint8_t *frames1, const uint8_t *frames2, size_t pitch, size_t frame_stride,
+                       int n_per_image, double *x, double *y, int32_t *val) {
+    return track_pairs_impl(ctx, params, taps, precision, pyr1, pyr2, frames1, frames2, pitch, frame_stride, n_per_image, x, y, val, false);
+}
+
+int klt_track_pairs_u8_async(klt_ctx *ctx, const klt_params *params, const klt_taps *taps, int precision, klt_pyr *pyr1,
+                             klt_pyr *pyr2, const uint8_t *frames1, const uint8_t *frames2, size_t pitch,
+                             size_t frame_stride, int n_per_image, double *x, double *y, int32_t *val) {
+    if (!ctx || !ctx->async_flag_dev) return klt_fail(ctx, KLT_ERR_NOMEM, "asynchronous calls need the context's status word");
+    return track_pairs_impl(ctx, params, taps, precision, pyr1, pyr2, frames1, frames2, pitch, frame_stride, n_per_image, x, y, val, true);
+}
+
+int klt_async_mark(klt_ctx *ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 16) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    KLT_CUDA(ctx, cudaEventRecord(ctx->marks[slot], ctx->stream));
+    return KLT_OK;
+}
+
+int klt_async_wait(klt_ctx *ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 16) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    KLT_CUDA(ctx, cudaEventSynchronize(ctx->marks[slot]));
+    return KLT_OK;
+}
+
+int klt_async_result(klt_ctx *ctx) {
+    if (!ctx || !ctx->async_flag_dev) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    int flag = 0;
+    KLT_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->async_flag_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    KLT_CUDA(ctx, cudaMemsetAsync(ctx->async_flag_dev, 0, sizeof(int), ctx->stream));
+    KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flag)
+        return klt_fail(ctx, KLT_ERR_ASSERT, "a feature window left the image at a pyramid level in one of the asynchronous calls: the reference raises AssertionError (trackFeaturesUtils.pyx:35)");
+    return KLT_OK;
 }
 
 }  // extern "C"

@@ -77,9 +77,12 @@ struct klt_ctx {
     // upload pipeline of klt_track_pairs_u8: copy stream, per-chunk events, device staging for the frames
     cudaStream_t copy_stream;
     cudaEvent_t chunk_ev[16];
-    cudaEvent_t compute_done;
-    void *frames_dev;
-    size_t frames_bytes;
+    cudaEvent_t half_free[2];   // recorded on the compute stream once the builds have consumed that staging half
+    int half_next;
+    void *frames_dev;           // two staging halves, so that the upload of call k+1 overlaps the kernels of call k
+    size_t frames_bytes;        // bytes of ONE half
+    cudaEvent_t marks[16];      // klt_async_mark / klt_async_wait
+    int *async_flag_dev;        // sticky "a window left the image" flag of the asynchronous calls (klt_async_result)
     // grow-only device workspace
     void *ws;
     size_t ws_bytes;

@@ -832,3 +832,55 @@ def test_windowed_corner_configurations(gpu_ctx, oracle):
         assert_features_equal((xs[k], ys[k], vs[k]), single[k])
         assert_features_close((xs[k], ys[k], vs[k]), oracle.track_features(p, f1[k], f2[k], *oracle.select_good_features(p, f1[k], n))[:3])
     q1.close(); q2.close()
+
+
+def test_async_pairs_pipeline_matches_sync(gpu_ctx, oracle):
+    """klt_track_pairs_u8_async: three different batches issued back to back on one context without waiting (the staging
+    halves alternate, uploads overlap the previous call's kernels) give exactly the synchronous call's results; the
+    sticky status word reports the reference's AssertionError case."""
+    from pyfeaturetrack_b200 import _capi, trackFeatures as tf, selectGoodFeatures as sgf
+    lib = _capi.lib()
+    H, W, B, n, K = 240, 320, 2, 48, 3
+    kw = dict(nPyramidLevels=2, subsampling=2, max_residue=10.0)
+    p, tc = P(oracle, **kw), make_tc(**kw)
+    taps, params = tf._taps_for_one_image(tc), sgf.make_params(tc)
+    f1 = [gpu_ctx.pinned_array((B, H, W), np.uint8) for _ in range(K)]
+    f2 = [gpu_ctx.pinned_array((B, H, W), np.uint8) for _ in range(K)]
+    xs = [gpu_ctx.pinned_array((B, n), np.float64) for _ in range(K)]
+    ys = [gpu_ctx.pinned_array((B, n), np.float64) for _ in range(K)]
+    vs = [gpu_ctx.pinned_array((B, n), np.int32) for _ in range(K)]
+    start = []
+    for k in range(K):
+        for b in range(B):
+            f1[k][b], f2[k][b] = _synth(200 + 10 * k + b, (H, W), shift=(0.7 * (k + 1), -0.9 * (b + 1)))
+            xs[k][b], ys[k][b], vs[k][b] = oracle.select_good_features(p, f1[k][b], n)
+        start.append((xs[k].copy(), ys[k].copy(), vs[k].copy()))
+    p1, p2 = _capi.Pyramid(gpu_ctx, W, H, 2, 2, B), _capi.Pyramid(gpu_ctx, W, H, 2, 2, B)
+    for prec in (_capi.PRECISION_FAST_WINDOWED, _capi.PRECISION_STRICT):
+        want = []
+        for k in range(K):
+            x, y, v = (a.copy() for a in start[k])
+            gpu_ctx.check(lib.klt_track_pairs_u8(gpu_ctx.handle, C.byref(params), C.byref(taps), prec, p1.handle, p2.handle,
+                                                 f1[k].ctypes.data, f2[k].ctypes.data, W, W * H, n, x.ctypes.data, y.ctypes.data, v.ctypes.data))
+            want.append((x, y, v))
+        for k in range(K):
+            xs[k][:], ys[k][:], vs[k][:] = start[k]
+        for k in range(K):
+            gpu_ctx.check(lib.klt_track_pairs_u8_async(gpu_ctx.handle, C.byref(params), C.byref(taps), prec, p1.handle, p2.handle,
+                                                       f1[k].ctypes.data, f2[k].ctypes.data, W, W * H, n, xs[k].ctypes.data,
+                                                       ys[k].ctypes.data, vs[k].ctypes.data))
+            gpu_ctx.check(lib.klt_async_mark(gpu_ctx.handle, k))
+        gpu_ctx.check(lib.klt_async_wait(gpu_ctx.handle, 0))
+        assert_features_equal((xs[0], ys[0], vs[0]), want[0])          # the first call is complete once its mark is reached
+        gpu_ctx.check(lib.klt_async_result(gpu_ctx.handle))
+        for k in range(K):
+            assert_features_equal((xs[k], ys[k], vs[k]), want[k])
+    # a feature whose window leaves a pyramid level: the synchronous call fails, the asynchronous one reports it later
+    xs[0][:], ys[0][:], vs[0][:] = start[0]
+    xs[0][0, 0], ys[0][0, 0], vs[0][0, 0] = 1.0, 1.0, 0
+    assert lib.klt_track_pairs_u8_async(gpu_ctx.handle, C.byref(params), C.byref(taps), _capi.PRECISION_FAST_WINDOWED, p1.handle,
+                                        p2.handle, f1[0].ctypes.data, f2[0].ctypes.data, W, W * H, n, xs[0].ctypes.data,
+                                        ys[0].ctypes.data, vs[0].ctypes.data) == 0
+    assert lib.klt_async_result(gpu_ctx.handle) == _capi.KLT_ERR_ASSERT
+    assert lib.klt_async_result(gpu_ctx.handle) == 0                   # the status word is cleared by reading it
+    p1.close(); p2.close()
