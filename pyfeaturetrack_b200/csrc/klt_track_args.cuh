@@ -20,7 +20,7 @@ struct TrackArgs {
 
 // gradient kernels of the two pyramids (the reference's kernel cache can hand different ones to the two images,
 // convolve.py:236,258); c[j] multiplies in[x + j - 3]
-struct WindowedTaps { float g1[7], d1[7], g2[7], d2[7]; };
+struct WindowedTaps { float g1[7], d1[7], g2[7], d2[7]; int same; /* both images share their kernels (the normal case) */ };
 
 bool klt_windowed_supported(const klt_params *p, const klt_pyr *p1, const klt_pyr *p2);
 int klt_launch_track_windowed(klt_ctx *ctx, const TrackArgs &A, const klt_pyr *p1, const klt_pyr *p2, double *x_dev,

@@ -188,6 +188,24 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// Five warp-wide sums at once, 16 shuffles instead of 25: after the first exchange the lower half-warp owns a, b, c and
+// the upper one d, e; after the second each quarter owns one of a, b, d, e (c rides along on the lower half); three
+// plain butterfly rounds finish them and five broadcasts hand the totals to every lane.
+__device__ __forceinline__ void warp_sum5(float &a, float &b, float &c, float &d, float &e, int lane) {
+    const unsigned int full = 0xffffffffu;
+    const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+    const float t0 = __shfl_xor_sync(full, up16 ? a : d, 16);
+    const float t1 = __shfl_xor_sync(full, up16 ? b : e, 16);
+    const float t2 = __shfl_xor_sync(full, up16 ? c : 0.f, 16);
+    const float A = (up16 ? d : a) + t0, B = (up16 ? e : b) + t1;
+    float Cc = up16 ? 0.f : c + t2;
+    float X = (up8 ? B : A) + __shfl_xor_sync(full, up8 ? A : B, 8);
+    Cc += __shfl_xor_sync(full, Cc, 8);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { X += __shfl_xor_sync(full, X, o); Cc += __shfl_xor_sync(full, Cc, o); }
+    a = __shfl_sync(full, X, 0); b = __shfl_sync(full, X, 8); d = __shfl_sync(full, X, 16); e = __shfl_sync(full, X, 24);
+    c = __shfl_sync(full, Cc, 0);
+}
 
 // L2 prefetch of one row of an N-wide region (top-left input pixel (sx0, sy0))
 template <int N>
@@ -196,7 +214,7 @@ __device__ __forceinline__ void prefetch_region(const float *__restrict__ img, i
     const int xa = min(max(sx0, 0), nc - 1), xb = min(max(sx0 + N - 1, 0), nc - 1);
     const float *p = img + (size_t)y * pitch;
 #pragma unroll
-    for (int k = 0; k * 8 < N; k++) prefetch_l2(p + min(xa + 8 * k, xb));
+    for (int k = 0; k * 16 < N; k++) prefetch_l2(p + min(xa + 16 * k, xb));      // one touch per 64 bytes
     prefetch_l2(p + xb);
 }
 
@@ -213,6 +231,8 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
     if (vals[f] < 0) return;                      // trackFeatures.py:253
     float *s = smem + warp * C::FLOATS;
     const int image = f / A.n_per_image;
+    const float *const plane1 = A.p1.base + (size_t)image * A.p1.plane_floats;      // intensity planes of this feature's pair
+    const float *const plane2 = A.p2.base + (size_t)image * A.p2.plane_floats;
     constexpr int hw = W / 2;
     const double ss = (double)A.ss, inv_ss = 1.0 / ss;        // subsampling is a power of two: x * inv_ss == x / ss exactly
     double xloc = xs[f], yloc = ys[f];
@@ -223,21 +243,20 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
     bool alive = true;
     // this lane's vertical taps for the two lane mappings of the vertical pass, and whether both images share their kernels
     float tq[7], th1[7], th2[7];
-    bool same_taps = true;
+    const bool same_taps = K.same != 0;
 #pragma unroll
     for (int j = 0; j < 7; j++) {
         const int grp = lane >> 3;
         tq[j] = grp == 0 ? K.g2[j] : (grp == 1 ? K.d2[j] : (grp == 2 ? K.g1[j] : K.d1[j]));
         th1[j] = lane >= 16 ? K.d1[j] : K.g1[j];
         th2[j] = lane >= 16 ? K.d2[j] : K.g2[j];
-        same_taps = same_taps && K.g1[j] == K.g2[j] && K.d1[j] == K.d2[j];
     }
 
     for (int r = A.n_levels - 1; r >= 0; r--) {
         xloc *= ss; yloc *= ss; xout *= ss; yout *= ss;
         if (!alive) continue;
         const int nc = A.p1.lv[r].w, nr = A.p1.lv[r].h, pitch = A.p1.lv[r].pitch;
-        const float *I1 = A.p1.level(0, image, r), *I2 = A.p2.level(0, image, r);
+        const float *I1 = plane1 + A.p1.lv[r].off, *I2 = plane2 + A.p2.lv[r].off;
         const float x1 = (float)xloc, y1 = (float)yloc;
         const int ix1 = (int)x1, iy1 = (int)y1;
         if (!(ix1 - hw >= 0 && iy1 - hw >= 0 && ix1 + hw + 2 <= nc && iy1 + hw + 2 <= nr)) {   // pyx:35
@@ -263,9 +282,9 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
             const float xn1 = (float)(xloc * ss), yn1 = (float)(yloc * ss);
             const float xn2 = (float)((double)x2 * ss), yn2 = (float)((double)y2 * ss);
             if (lane < C::N2)
-                prefetch_region<C::N2>(A.p2.level(0, image, r - 1), pn, ncn, nrn, (int)xn2 - hw - MARGIN - RG, (int)yn2 - hw - MARGIN - RG, lane);
+                prefetch_region<C::N2>(plane2 + A.p2.lv[r - 1].off, pn, ncn, nrn, (int)xn2 - hw - MARGIN - RG, (int)yn2 - hw - MARGIN - RG, lane);
             if (lane < C::N1)
-                prefetch_region<C::N1>(A.p1.level(0, image, r - 1), pn, ncn, nrn, (int)xn1 - hw - RG, (int)yn1 - hw - RG, lane);
+                prefetch_region<C::N1>(plane1 + A.p1.lv[r - 1].off, pn, ncn, nrn, (int)xn1 - hw - RG, (int)yn1 - hw - RG, lane);
         }
         cp_async_wait_all();
         __syncwarp();
@@ -334,8 +353,8 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
                     ex = fmaf(diff, gx, ex); ey = fmaf(diff, gy, ey);
                 }
             }
-            gxx = warp_sum(gxx); gxy = warp_sum(gxy); gyy = warp_sum(gyy);
-            ex = warp_sum(ex) * A.step_factor; ey = warp_sum(ey) * A.step_factor;
+            warp_sum5(gxx, gxy, gyy, ex, ey, lane);
+            ex *= A.step_factor; ey *= A.step_factor;
             const float det = __fsub_rn(__fmul_rn(gxx, gyy), __fmul_rn(gxy, gxy));
             if (det < A.small_det) { status = KLT_SMALL_DET; break; }
             const float dx = __fdiv_rn(__fsub_rn(__fmul_rn(gyy, ex), __fmul_rn(gxy, ey)), det);
@@ -422,6 +441,8 @@ int klt_launch_track_windowed(klt_ctx *ctx, const TrackArgs &A, const klt_pyr *p
     WindowedTaps K;
     flip7(p1->hx->taps.grad_gauss, K.g1); flip7(p1->hx->taps.grad_deriv, K.d1);
     flip7(p2->hx->taps.grad_gauss, K.g2); flip7(p2->hx->taps.grad_deriv, K.d2);
+    K.same = 1;
+    for (int j = 0; j < 7; j++) K.same = K.same && K.g1[j] == K.g2[j] && K.d1[j] == K.d2[j];
     switch (A.w) {
         case 3: return launch_windowed<3>(ctx, A, K, x_dev, y_dev, val_dev, iters_dev, assert_dev);
         case 5: return launch_windowed<5>(ctx, A, K, x_dev, y_dev, val_dev, iters_dev, assert_dev);
