@@ -357,8 +357,9 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
             ex *= A.step_factor; ey *= A.step_factor;
             const float det = __fsub_rn(__fmul_rn(gxx, gyy), __fmul_rn(gxy, gxy));
             if (det < A.small_det) { status = KLT_SMALL_DET; break; }
-            const float dx = __fdiv_rn(__fsub_rn(__fmul_rn(gyy, ex), __fmul_rn(gxy, ey)), det);
-            const float dy = __fdiv_rn(__fsub_rn(__fmul_rn(gxx, ey), __fmul_rn(gxy, ex)), det);
+            const float inv = __frcp_rn(det);             // one reciprocal instead of two divisions (within 1 ulp of them)
+            const float dx = __fsub_rn(__fmul_rn(gyy, ex), __fmul_rn(gxy, ey)) * inv;
+            const float dy = __fsub_rn(__fmul_rn(gxx, ey), __fmul_rn(gxy, ex)) * inv;
             x2 += dx; y2 += dy;
             iteration++;
             if (!((fabsf(dx) >= A.th || fabsf(dy) >= A.th) && iteration < A.max_iterations)) break;
