@@ -54,11 +54,12 @@ struct Cfg {
     // the two row groups of the merged horizontal pass when they store.
     static constexpr int GROUP_BANKS = S <= 8 ? 8 : 16;
     static constexpr int pad_to(int n, int banks) { return n + ((banks - n % 32) % 32 + 32) % 32; }
-    static constexpr int TSZ = pad_to(NG * SP, GROUP_BANKS), GSZ = pad_to(S * GP, GROUP_BANKS);
+    static constexpr int TSZ = pad_to(NG * SP, GROUP_BANKS);
+    static constexpr int GSZ = pad_to(2 * S * GP, 16);      // gradients: ONE plane of (gx, gy) pairs per image -> 64-bit loads
     static constexpr int IN1 = 0, IN2 = IN1 + N1 * NP1;
     static constexpr int TD2 = pad_to(IN2 + N2 * NP2, 0), TG2 = TD2 + TSZ, TD1 = TG2 + TSZ, TG1 = TD1 + TSZ;
-    static constexpr int GX2 = pad_to(TG1 + TSZ, 0), GY2 = GX2 + GSZ, GX1 = GY2 + GSZ, GY1 = GX1 + GSZ;
-    static constexpr int FLOATS = GY1 + GSZ;
+    static constexpr int G2 = pad_to(TG1 + TSZ, 0), G1 = G2 + GSZ;
+    static constexpr int FLOATS = G1 + GSZ;
     static constexpr bool MERGED_H = 2 * NG <= 32;          // one lane per row of BOTH regions in the horizontal pass
     static constexpr bool QUAD_V = S <= 8;                  // vertical pass: 4 groups of 8 lanes (gx2, gy2, gx1, gy1)
 };
@@ -135,7 +136,7 @@ __device__ __forceinline__ void vcol(const float *__restrict__ src, float *__res
         float o = t[0] * v[r];
 #pragma unroll
         for (int j = 1; j < 7; j++) o = fmaf(t[j], v[r + j], o);
-        dst[r * GP] = o;
+        dst[2 * r * GP] = o;                               // interleaved (gx, gy) plane
     }
 }
 
@@ -166,15 +167,15 @@ __device__ __forceinline__ void window_gradients(float *__restrict__ s, const Wi
         const int grp = lane >> 3, col = lane & 7;
         if (col < C::S && (!only2 || grp < 2)) {
             const int src = grp == 0 ? C::TD2 : (grp == 1 ? C::TG2 : (grp == 2 ? C::TD1 : C::TG1));
-            const int dst = grp == 0 ? C::GX2 : (grp == 1 ? C::GY2 : (grp == 2 ? C::GX1 : C::GY1));
-            vcol<C::S, C::SP, C::GP>(s + src + col, s + dst + col, tq);
+            const int dst = (grp < 2 ? C::G2 : C::G1) + (grp & 1);            // gx at even, gy at odd floats
+            vcol<C::S, C::SP, C::GP>(s + src + col, s + dst + 2 * col, tq);
         }
     } else {
         const bool upper = lane >= 16;
         const int col = lane & 15;
         if (col < C::S) {
-            vcol<C::S, C::SP, C::GP>(s + (upper ? C::TG2 : C::TD2) + col, s + (upper ? C::GY2 : C::GX2) + col, th2);
-            if (!only2) vcol<C::S, C::SP, C::GP>(s + (upper ? C::TG1 : C::TD1) + col, s + (upper ? C::GY1 : C::GX1) + col, th1);
+            vcol<C::S, C::SP, C::GP>(s + (upper ? C::TG2 : C::TD2) + col, s + C::G2 + (upper ? 1 : 0) + 2 * col, th2);
+            if (!only2) vcol<C::S, C::SP, C::GP>(s + (upper ? C::TG1 : C::TD1) + col, s + C::G1 + (upper ? 1 : 0) + 2 * col, th1);
         }
     }
     __syncwarp();
@@ -182,6 +183,13 @@ __device__ __forceinline__ void window_gradients(float *__restrict__ s, const Wi
 
 __device__ __forceinline__ float bil(const float *p, int P, float w00, float w01, float w10, float w11) {
     return fmaf(w11, p[P + 1], fmaf(w10, p[P], fmaf(w01, p[1], w00 * p[0])));
+}
+// bilinear sample of an interleaved (gx, gy) plane: four 64-bit loads for both gradients; P = pitch in pairs
+__device__ __forceinline__ float2 bil2(const float *p, int P, float w00, float w01, float w10, float w11) {
+    const float2 a = *reinterpret_cast<const float2 *>(p), b = *reinterpret_cast<const float2 *>(p + 2);
+    const float2 c = *reinterpret_cast<const float2 *>(p + 2 * P), d = *reinterpret_cast<const float2 *>(p + 2 * P + 2);
+    return make_float2(fmaf(w11, d.x, fmaf(w10, c.x, fmaf(w01, b.x, w00 * a.x))),
+                       fmaf(w11, d.y, fmaf(w10, c.y, fmaf(w01, b.y, w00 * a.y))));
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -314,8 +322,8 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
                 po[i] = pr * C::GP + pc;
                 pi[i] = (pr + RG) * C::NP2 + pc + RG;
                 T[i] = on ? bil(s + C::IN1 + (pr + RG) * C::NP1 + pc + RG, C::NP1, w00, w01, w10, w11) : 0.f;
-                Tgx[i] = on ? bil(s + C::GX1 + po[i], C::GP, w00, w01, w10, w11) : 0.f;
-                Tgy[i] = on ? bil(s + C::GY1 + po[i], C::GP, w00, w01, w10, w11) : 0.f;
+                const float2 tg = on ? bil2(s + C::G1 + 2 * po[i], C::GP, w00, w01, w10, w11) : make_float2(0.f, 0.f);
+                Tgx[i] = tg.x; Tgy[i] = tg.y;
             }
         }
         int ox = MARGIN, oy = MARGIN;
@@ -346,9 +354,8 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
             for (int i = 0; i < C::PX; i++) {
                 if (pon[i]) {
                     const float P = bil(bi + pi[i], C::NP2, w00, w01, w10, w11);
-                    const float Px = bil(s + C::GX2 + po[i], C::GP, w00, w01, w10, w11);
-                    const float Py = bil(s + C::GY2 + po[i], C::GP, w00, w01, w10, w11);
-                    const float diff = T[i] - P, gx = Tgx[i] + Px, gy = Tgy[i] + Py;
+                    const float2 Pg = bil2(s + C::G2 + 2 * po[i], C::GP, w00, w01, w10, w11);
+                    const float diff = T[i] - P, gx = Tgx[i] + Pg.x, gy = Tgy[i] + Pg.y;
                     gxx = fmaf(gx, gx, gxx); gxy = fmaf(gx, gy, gxy); gyy = fmaf(gy, gy, gyy);
                     ex = fmaf(diff, gx, ex); ey = fmaf(diff, gy, ey);
                 }
