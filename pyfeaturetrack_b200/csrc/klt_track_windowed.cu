@@ -15,8 +15,8 @@
 //   * when the window moves to another integer position the second image's gradients are re-evaluated there (0.2 times
 //     per level on the benchmark), and when it walks out of the staged region that is re-staged around the current
 //     position (warp-uniform branches; the values do not depend on where the region sits).
-//   * The shared-memory layout is bank-aware: the four horizontal-result planes and the four gradient planes start 8
-//     banks apart, and for 7x7 windows 8 lanes serve a window row and the staged regions use pitch 25, which puts the
+//   * The shared-memory layout is bank-aware: the four horizontal-result planes start 8 banks apart, the gradients of an
+//     image are one plane of (gx, gy) pairs (64-bit bilinear taps, the two images 16 banks apart), and for 7x7 windows 8 lanes serve a window row and the staged regions use pitch 25, which puts the
 //     four window rows of a round on disjoint banks (ncu: conflict replays 40 % -> 16 % of the wavefronts).
 //
 // Arithmetic: float32 FMA, the same tap order as the dense FAST kernels (c[0..6] left to right / top to bottom), so the
