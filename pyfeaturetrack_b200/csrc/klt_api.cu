@@ -113,6 +113,10 @@ int klt_ctx_create(int device, void *stream, klt_ctx **out) {
                         e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
     if (device < 0 || device >= count) return klt_fail(nullptr, KLT_ERR_INVALID, "device %d out of range (%d devices)", device, count);
     if ((e = cudaSetDevice(device)) != cudaSuccess) return klt_fail(nullptr, KLT_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return klt_fail(nullptr, KLT_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10)       // the library carries sm_100a code only; fail loudly here instead of at the first launch
+        return klt_fail(nullptr, KLT_ERR_UNSUPPORTED, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU", device, prop.name, prop.major, prop.minor);
     klt_ctx *ctx = new klt_ctx();
     ctx->device = device;
     ctx->profiling = false;
@@ -134,16 +138,7 @@ int klt_ctx_create(int device, void *stream, klt_ctx **out) {
     ctx->async_flag_dev = nullptr;
     for (int i = 0; i < 16; i++) cudaEventCreateWithFlags(&ctx->marks[i], cudaEventDisableTiming);
     if (cudaMalloc(&ctx->async_flag_dev, 256) == cudaSuccess) cudaMemset(ctx->async_flag_dev, 0, 256);
-    cudaDeviceProp prop;
-    cudaGetDeviceProperties(&prop, device);
     ctx->num_sms = prop.multiProcessorCount;
-    if (prop.major < 10) {
-        // the library carries sm_100a code only; fail loudly instead of at the first launch
-        std::string name = prop.name;
-        if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
-        delete ctx;
-        return klt_fail(nullptr, KLT_ERR_UNSUPPORTED, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU", device, name.c_str(), prop.major, prop.minor);
-    }
     *out = ctx;
     return KLT_OK;
 }
