@@ -165,11 +165,12 @@ int klt_ctx_destroy(klt_ctx *ctx) {
 const char *klt_last_error(const klt_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int klt_sync(klt_ctx *ctx) {
+    if (!ctx) return KLT_ERR_INVALID;
     KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KLT_OK;
 }
-void *klt_ctx_stream(klt_ctx *ctx) { return (void *)ctx->stream; }
-int64_t klt_launch_count(const klt_ctx *ctx) { return ctx->launches; }
+void *klt_ctx_stream(klt_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int64_t klt_launch_count(const klt_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int klt_host_alloc(size_t bytes, void **out) {
     if (!out) return KLT_ERR_INVALID;
@@ -177,22 +178,26 @@ int klt_host_alloc(size_t bytes, void **out) {
 }
 int klt_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? KLT_OK : KLT_ERR_CUDA; }
 int klt_device_alloc(klt_ctx *ctx, size_t bytes, void **out) {
+    if (!ctx || !out) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaError_t e = cudaMalloc(out, bytes);
     if (e != cudaSuccess) return klt_fail(ctx, KLT_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
     return KLT_OK;
 }
 int klt_device_free(klt_ctx *ctx, void *p) {
+    if (!ctx) return KLT_ERR_INVALID;
     KLT_CUDA(ctx, cudaFree(p));
     return KLT_OK;
 }
 int klt_memcpy(klt_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (!ctx || (bytes && (!dst || !src))) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
     KLT_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
     return KLT_OK;
 }
-int klt_timer_start(klt_ctx *ctx) { KLT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream)); return KLT_OK; }
-int klt_timer_stop(klt_ctx *ctx) { KLT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream)); return KLT_OK; }
+int klt_timer_start(klt_ctx *ctx) { if (!ctx) return KLT_ERR_INVALID; KLT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream)); return KLT_OK; }
+int klt_timer_stop(klt_ctx *ctx) { if (!ctx) return KLT_ERR_INVALID; KLT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream)); return KLT_OK; }
 int klt_timer_elapsed_ms(klt_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
     KLT_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
     KLT_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
     return KLT_OK;
