@@ -54,3 +54,26 @@ def test_no_cpu_fallback():
         if fn.endswith(".py"):
             text = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in text.replace("oracle/", "").lower() or fn in ("synth.py",), fn + " mentions the oracle"
+
+
+def _build_c_demo(tmpdir):
+    import subprocess
+    pkg = os.path.join(ROOT, "pyfeaturetrack_b200")
+    exe = os.path.join(str(tmpdir), "c_abi_demo")
+    subprocess.check_call(["gcc", "-std=c11", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_abi_demo.c"),
+                           "-L" + pkg, "-lkltb200", "-Wl,-rpath," + pkg, "-lm", "-o", exe])
+    return exe
+
+
+def test_plain_c_program_links_against_the_abi(tmp_path):
+    """examples/c_abi_demo.c compiles as C11 against include/klt_b200.h and links to libkltb200.so; without a GPU it
+    stops with the library's own message (exit 3) -- the C-ABI boundary has no CPU fallback either."""
+    import subprocess
+    from pyfeaturetrack_b200 import _capi
+    _capi.lib()                                   # builds the library if needed
+    exe = _build_c_demo(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if r.returncode == 3:
+        assert "no CPU fallback" in r.stderr or "Blackwell" in r.stderr or "CUDA" in r.stderr
+    else:
+        assert r.returncode == 0 and "tracked" in r.stdout, r.stderr

@@ -4,6 +4,7 @@ pyfeaturetrack_b200), against the CPU oracle on the same seeded inputs and again
 Bars (BASELINE.json north_star): STRICT mode is bit-exact everywhere (images, eigen map, selection, positions, status
 codes).  FAST mode: images within 1e-5 relative-to-max, positions within 1e-3 px, status codes >= 99.9 %."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -884,3 +885,16 @@ def test_async_pairs_pipeline_matches_sync(gpu_ctx, oracle):
     assert lib.klt_async_result(gpu_ctx.handle) == _capi.KLT_ERR_ASSERT
     assert lib.klt_async_result(gpu_ctx.handle) == 0                   # the status word is cleared by reading it
     p1.close(); p2.close()
+
+
+def test_plain_c_demo_tracks_the_known_shift(gpu_ctx, tmp_path):
+    """The C program of examples/ (select + klt_track_pairs_u8 through the bare ABI) recovers the (3, 2) pixel shift."""
+    import re, subprocess, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_capi_symbols import _build_c_demo
+    r = subprocess.run([_build_c_demo(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    m = re.match(r"tracked (\d+) of (\d+) features, median shift \(([-\d.]+), ([-\d.]+)\)", r.stdout)
+    assert m, r.stdout
+    assert int(m.group(1)) >= 0.8 * int(m.group(2))
+    assert abs(float(m.group(3)) - 3.0) < 0.1 and abs(float(m.group(4)) - 2.0) < 0.1
