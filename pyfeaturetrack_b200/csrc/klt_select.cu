@@ -552,6 +552,7 @@ greedy_kernel(const __grid_constant__ GreedyArgs A) {
                 const int take = nacc < room ? nacc : room;
                 const int rank = __popc(acc & lt);
                 const bool store = ((acc >> lane) & 1u) && rank < take;
+                __syncwarp();                     // every lane has finished reading the grid before anyone registers in it
                 if (store) {
                     const int slot = A.overwrite ? filled + rank : A.free_slots[filled + rank];
                     A.fx[slot] = (double)x; A.fy[slot] = (double)y; A.fval[slot] = (int)val;
