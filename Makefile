@@ -23,4 +23,4 @@ bench-reference:  ## the unmodified reference on the host cores, same metric and
 
 clean:
 	rm -f pyfeaturetrack_b200/csrc/*.o pyfeaturetrack_b200/libkltb200.so oracle/libkltoracle.so
-	rm -rf oracle/_ref
+	@echo "(oracle/_ref is kept: it can only be rebuilt where the reference sources are mounted)"
