@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KLT_B200_ABI_VERSION 3
+#define KLT_B200_ABI_VERSION 4
 #define KLT_MAX_TAPS 71   /* convolve.py:28 maxKernelWidth */
 #define KLT_MAX_LEVELS 8
 
@@ -64,6 +64,13 @@ typedef enum klt_status {
 typedef struct klt_ctx klt_ctx; /* one per (device, stream) */
 typedef struct klt_pyr klt_pyr; /* a batch of image pyramids: intensity, gradx, grady for every level */
 typedef struct klt_affine klt_affine; /* per-feature affine-consistency state (templates, template centre, 2x2 map) */
+typedef struct klt_sequence klt_sequence; /* B lock-stepped sequences: two pyramid batches, device-resident feature lists */
+
+/* how the minimum-eigenvalue map of a selection is computed */
+#define KLT_SELECT_STRICT 0 /* float32 summed-area tables built by the reference's sequential chains (goodFeaturesUtils.pyx:49-51):
+                             * on STRICT gradients the selection is bit-identical to the reference's */
+#define KLT_SELECT_FAST 1   /* gradients + direct window sums + eigenvalue fused in one pass over the level-0 image; same
+                             * feature SET as the reference for ~99.8 % of the features, not the same slots */
 
 /* One 1-D kernel, as produced by _computeKernels (convolve.py:27-93).  Computed on the host. */
 typedef struct klt_kernel1d {
@@ -189,6 +196,17 @@ int klt_select_good_features(klt_ctx *ctx, const klt_params *params, const klt_p
                              const float *gradx, const float *grady, int w, int h, int n_features, int replace,
                              double *x, double *y, int32_t *val, int64_t *n_consumed);
 
+/* The same for EVERY image of a pyramid batch in one chain of launches without host synchronisation (the candidate count,
+ * the sort and the greedy walk are sized and driven on the device): KLTSelectGoodFeatures (replace == 0) or
+ * KLTReplaceLostFeatures (replace == 1) for pyr->batch images.  x, y, val: [batch][n_features], host or device (device
+ * arrays are updated in place and the call returns without waiting).  select_mode: KLT_SELECT_STRICT / KLT_SELECT_FAST. */
+int klt_select_good_features_batch(klt_ctx *ctx, const klt_params *params, klt_pyr *pyr, int n_features, int replace,
+                                   int select_mode, double *x, double *y, int32_t *val);
+
+/* The minimum-eigenvalue maps alone, for every image of a pyramid batch, by either method: what ScanImageForGoodFeatures
+ * returns as pointlistval (goodFeaturesUtils.pyx:53-71), val [batch][ny][nx] (host or device; NULL: only report nx, ny). */
+int klt_eigen_map_batch(klt_ctx *ctx, const klt_params *params, klt_pyr *pyr, int select_mode, float *val, int *nx, int *ny);
+
 /* ---- tracking: replaces KLTTrackFeatures' per-feature loop (trackFeatures.py:250-346), _trackFeature
  * (:67-136) and trackFeaturesUtils.trackFeatureIterateCKLT / extractImagePatch* / _compute* / _solveEquation
  * (trackFeaturesUtils.pyx:14-51,61-128,246-340,393-459).
@@ -260,6 +278,43 @@ int klt_async_result(klt_ctx *ctx);
  * buffers of the call before last. */
 int klt_async_mark(klt_ctx *ctx, int slot);
 int klt_async_wait(klt_ctx *ctx, int slot);
+
+/* ---- sequences: KLTTrackFeatures in tc.sequentialMode (pyramid reuse, trackFeatures.py:152-161,401-404) followed by
+ * KLTReplaceLostFeatures (_KLTSelectGoodFeatures(REPLACING_SOME) on tc.pyramid_last's gradients,
+ * selectGoodFeatures.py:176-179,45-135) for n_sequences independent, lock-stepped sequences -- BASELINE config D.
+ * A klt_sequence owns two pyramid batches (previous / current frame), the device-resident feature lists
+ * [n_sequences][n_features] and the selection workspace.  One step = one pyramid build + one tracking launch + one
+ * selection chain for all sequences, enqueued without any host synchronisation and, from the third step on, replayed from
+ * a CUDA graph.  precision: KLT_PRECISION_* of the pyramid builds (and with it the tracker's arithmetic); select_mode:
+ * KLT_SELECT_*.  With KLT_PRECISION_STRICT + KLT_SELECT_STRICT every list equals the reference's bit for bit. */
+int klt_sequence_create(klt_ctx *ctx, const klt_params *params, const klt_taps *taps, int w, int h, int n_sequences,
+                        int n_features, int precision, int select_mode, klt_sequence **out);
+int klt_sequence_destroy(klt_ctx *ctx, klt_sequence *seq);
+/* first frames: uint8 [n_sequences][h][pitch], host (ideally pinned) or device.  Builds the pyramids; select != 0 also
+ * runs KLTSelectGoodFeatures(tc, frame, n_features) for every sequence (else call klt_sequence_set_features). */
+int klt_sequence_start_u8(klt_ctx *ctx, klt_sequence *seq, const uint8_t *frames, size_t pitch, size_t frame_stride,
+                          int select);
+/* x, y, val: [n_sequences][n_features], host or device */
+int klt_sequence_set_features(klt_ctx *ctx, klt_sequence *seq, const double *x, const double *y, const int32_t *val);
+/* next frames: KLTTrackFeatures(prev, cur) and, if replace != 0, KLTReplaceLostFeatures(cur) for every sequence.
+ * Everything is only enqueued.  Optional outputs ([n_sequences][n_features]; pinned host memory or device; they are
+ * written when the stream gets there -- klt_sequence_sync / klt_sync / klt_async_wait): x, y, val = the lists after the
+ * step (tracked features val 0, new features val > 0, lost and not replaced val < 0); val_tracked = val after tracking,
+ * before replacement (the kltState codes).  The frames must stay untouched until the stream has consumed them. */
+int klt_sequence_step_u8(klt_ctx *ctx, klt_sequence *seq, const uint8_t *frames, size_t pitch, size_t frame_stride,
+                         int replace, double *x, double *y, int32_t *val, int32_t *val_tracked);
+/* synchronous download of the current lists (any pointer may be NULL) */
+int klt_sequence_get_features(klt_ctx *ctx, klt_sequence *seq, double *x, double *y, int32_t *val, int32_t *val_tracked);
+/* waits for the stream; KLT_ERR_ASSERT if a window left the image in one of the steps since the last call (the
+ * reference's AssertionError, trackFeaturesUtils.pyx:35); n_iterations (optional): Newton iterations since then */
+int klt_sequence_sync(klt_ctx *ctx, klt_sequence *seq, int64_t *n_iterations);
+/* diagnostics of the last selection of every sequence: out [n_sequences][4] = candidates the greedy walk consumed, 1 if
+ * the candidates ran out before every slot was filled, slots filled, number of times the walk had to widen its range */
+int klt_sequence_select_stats(klt_ctx *ctx, klt_sequence *seq, int64_t *out);
+/* the pyramid batch of the latest frame (owned by the sequence; valid until the next step) */
+int klt_sequence_pyramid(klt_sequence *seq, klt_pyr **out);
+/* 1 once steps are replayed from CUDA graphs (0: plain launches, e.g. while profiling or with $KLT_B200_NO_GRAPH) */
+int klt_sequence_uses_graph(const klt_sequence *seq);
 
 #ifdef __cplusplus
 }

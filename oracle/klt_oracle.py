@@ -305,6 +305,23 @@ def select_from_gradients(p, gx, gy, n_features, existing=None):
     return fx, fy, fv, used
 
 
+def select_from_map(p, val, W, H, n_features):
+    """Sort + _enforceMinimumDistance (selectGoodFeatures.py:234-246) on a caller-provided eigenvalue map val[ny, nx] laid out
+    like ScanImageForGoodFeatures' output for this geometry -- used by tests to separate the effect of the map's rounding
+    from the rest of the selection."""
+    window_hw, window_hh = p.window_width / 2, p.window_height / 2
+    bx, by = max(p.borderx, window_hw), max(p.bordery, window_hh)
+    bx, by = int(bx), int(by)
+    val = np.ascontiguousarray(val, np.float32)
+    fx = np.full(n_features, -1.0)
+    fy = np.full(n_features, -1.0)
+    fv = np.full(n_features, KLT_NOT_FOUND, np.int32)
+    used = lib().orc_select_from_scan(_f(val), val.shape[1], val.shape[0], bx, by, p.nSkippedPixels, W, H, max(p.mindist, 0),
+                                      int(p.min_eigenvalue), 1, n_features, _d(fx), _d(fy), _i(fv))
+    assert used >= 0
+    return fx, fy, fv
+
+
 def select_good_features(p, img_u8, n_features):
     """KLTSelectGoodFeatures (selectGoodFeatures.py:141-261, 279-294) -> (x, y, val) arrays."""
     f = np.asarray(img_u8).astype(np.float32)

@@ -10,6 +10,7 @@ _LIBPATH = os.path.join(_HERE, "libkltb200.so")
 
 KLT_MAX_TAPS = 71
 PRECISION_FAST, PRECISION_STRICT, PRECISION_FAST_WINDOWED = 0, 1, 2
+SELECT_STRICT, SELECT_FAST = 0, 1
 KLT_ERR_INVALID, KLT_ERR_CUDA, KLT_ERR_NOMEM, KLT_ERR_UNSUPPORTED, KLT_ERR_ASSERT = -1, -2, -3, -4, -5
 
 
@@ -92,6 +93,8 @@ SIGNATURES = {
     "klt_scan_good_features": (_i, [_vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _fp]),
     "klt_select_good_features": (_i, [_vp, C.POINTER(Params), _vp, _i, _fp, _fp, _i, _i, _i, _i, _dp, _dp, _ip,
                                       C.POINTER(C.c_int64)]),
+    "klt_select_good_features_batch": (_i, [_vp, C.POINTER(Params), _vp, _i, _i, _i, _dp, _dp, _ip]),
+    "klt_eigen_map_batch": (_i, [_vp, C.POINTER(Params), _vp, _i, _fp, C.POINTER(_i), C.POINTER(_i)]),
     "klt_track_features": (_i, [_vp, C.POINTER(Params), _vp, _vp, _i, _dp, _dp, _ip, C.POINTER(C.c_int64)]),
     "klt_affine_create": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),
     "klt_affine_destroy": (_i, [_vp, _vp]),
@@ -111,6 +114,16 @@ SIGNATURES = {
     "klt_async_result": (_i, [_vp]),
     "klt_async_mark": (_i, [_vp, _i]),
     "klt_async_wait": (_i, [_vp, _i]),
+    "klt_sequence_create": (_i, [_vp, C.POINTER(Params), C.POINTER(Taps), _i, _i, _i, _i, _i, _i, C.POINTER(_vp)]),
+    "klt_sequence_destroy": (_i, [_vp, _vp]),
+    "klt_sequence_start_u8": (_i, [_vp, _vp, _u8p, _sz, _sz, _i]),
+    "klt_sequence_set_features": (_i, [_vp, _vp, _dp, _dp, _ip]),
+    "klt_sequence_step_u8": (_i, [_vp, _vp, _u8p, _sz, _sz, _i, _dp, _dp, _ip, _ip]),
+    "klt_sequence_get_features": (_i, [_vp, _vp, _dp, _dp, _ip, _ip]),
+    "klt_sequence_sync": (_i, [_vp, _vp, C.POINTER(C.c_int64)]),
+    "klt_sequence_select_stats": (_i, [_vp, _vp, _vp]),
+    "klt_sequence_pyramid": (_i, [_vp, C.POINTER(_vp)]),
+    "klt_sequence_uses_graph": (_i, [_vp]),
 }
 
 
@@ -232,6 +245,74 @@ class AffineState:
     def close(self):
         if self.handle:
             lib().klt_affine_destroy(self.ctx.handle, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Sequence:
+    """Owns one klt_sequence: n_sequences lock-stepped sequences (sequentialMode tracking + per-frame replacement)."""
+
+    def __init__(self, ctx, params, taps, w, h, n_sequences, n_features, precision, select_mode):
+        self.ctx, self.w, self.h, self.B, self.n = ctx, w, h, n_sequences, n_features
+        hnd = C.c_void_p()
+        ctx.check(lib().klt_sequence_create(ctx.handle, C.byref(params), C.byref(taps), w, h, n_sequences, n_features,
+                                            precision, select_mode, C.byref(hnd)))
+        self.handle = hnd
+        self._keep = []
+
+    def _frames(self, frames):
+        if isinstance(frames, np.ndarray):
+            assert frames.dtype == np.uint8 and frames.flags.c_contiguous and frames.shape == (self.B, self.h, self.w)
+            self._keep = [frames] + self._keep[:2]       # host memory must outlive the asynchronous upload
+            return frames.ctypes.data
+        return int(frames)
+
+    def start(self, frames, select=True):
+        self.ctx.check(lib().klt_sequence_start_u8(self.ctx.handle, self.handle, self._frames(frames), self.w,
+                                                   self.w * self.h, 1 if select else 0))
+
+    def set_features(self, x, y, val):
+        x, y = np.ascontiguousarray(x, np.float64), np.ascontiguousarray(y, np.float64)
+        val = np.ascontiguousarray(val, np.int32)
+        assert x.shape == y.shape == val.shape == (self.B, self.n)
+        self.ctx.check(lib().klt_sequence_set_features(self.ctx.handle, self.handle, x.ctypes.data, y.ctypes.data,
+                                                       val.ctypes.data))
+        self.ctx.sync()
+
+    def step(self, frames, replace=True, out=None):
+        """out: None (results stay on the device) or (x, y, val, val_tracked) pinned arrays / device pointers."""
+        o = [0, 0, 0, 0] if out is None else [ptr(a) if a is not None else 0 for a in out]
+        self.ctx.check(lib().klt_sequence_step_u8(self.ctx.handle, self.handle, self._frames(frames), self.w,
+                                                  self.w * self.h, 1 if replace else 0, o[0], o[1], o[2], o[3]))
+
+    def features(self):
+        x, y = np.empty((self.B, self.n)), np.empty((self.B, self.n))
+        v, vt = np.empty((self.B, self.n), np.int32), np.empty((self.B, self.n), np.int32)
+        self.ctx.check(lib().klt_sequence_get_features(self.ctx.handle, self.handle, x.ctypes.data, y.ctypes.data,
+                                                       v.ctypes.data, vt.ctypes.data))
+        return x, y, v, vt
+
+    def sync(self):
+        it = C.c_int64()
+        self.ctx.check(lib().klt_sequence_sync(self.ctx.handle, self.handle, C.byref(it)))
+        return it.value
+
+    def select_stats(self):
+        out = np.zeros((self.B, 4), np.int64)
+        self.ctx.check(lib().klt_sequence_select_stats(self.ctx.handle, self.handle, out.ctypes.data))
+        return out
+
+    def uses_graph(self):
+        return bool(lib().klt_sequence_uses_graph(self.handle))
+
+    def close(self):
+        if self.handle:
+            lib().klt_sequence_destroy(self.ctx.handle, self.handle)
             self.handle = None
 
     def __del__(self):

@@ -3,6 +3,7 @@
 // klt_conv.cu, klt_select.cu and klt_track.cu.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "klt_common.cuh"
@@ -139,6 +140,11 @@ int klt_ctx_create(int device, void *stream, klt_ctx **out) {
     for (int i = 0; i < 16; i++) cudaEventCreateWithFlags(&ctx->marks[i], cudaEventDisableTiming);
     if (cudaMalloc(&ctx->async_flag_dev, 256) == cudaSuccess) cudaMemset(ctx->async_flag_dev, 0, 256);
     ctx->num_sms = prop.multiProcessorCount;
+    ctx->select_chunk = 4096;
+    if (const char *e2 = getenv("KLT_B200_SELECT_CHUNK")) {
+        const int v = atoi(e2);
+        if (v >= 32 && v <= 4096 && (v & (v - 1)) == 0) ctx->select_chunk = v;
+    }
     *out = ctx;
     return KLT_OK;
 }
@@ -351,7 +357,7 @@ static int build_rest(klt_ctx *ctx, klt_pyr *p, const klt_taps *taps, int precis
 }
 
 // bookkeeping of a build: `precision` as given by the caller; returns the arithmetic precision to run with
-static int begin_build(klt_pyr *p, const klt_taps *taps, int precision, bool *windowed) {
+int klt_begin_build(klt_pyr *p, const klt_taps *taps, int precision, bool *windowed) {
     *windowed = precision == KLT_PRECISION_FAST_WINDOWED;
     const int arith = *windowed ? KLT_PRECISION_FAST : precision;
     p->precision = arith;
@@ -372,7 +378,7 @@ int klt_pyr_ensure_gradients(klt_ctx *ctx, klt_pyr *p) {
 }
 
 // level 0 only: what selection on a tracking pyramid reads (KLTReplaceLostFeatures in sequentialMode)
-static int ensure_gradients_level0(klt_ctx *ctx, klt_pyr *p) {
+int klt_ensure_gradients_level0(klt_ctx *ctx, klt_pyr *p) {
     if (!p->hx || p->hx->grad_valid || p->hx->grad0_valid) return KLT_OK;
     if (!p->hx->taps_valid) return klt_fail(ctx, KLT_ERR_INVALID, "pyramid has not been built");
     int rc = build_gradients(ctx, p, &p->hx->taps, p->precision, 0, 0, p->batch, 1);
@@ -382,8 +388,8 @@ static int ensure_gradients_level0(klt_ctx *ctx, klt_pyr *p) {
 }
 
 // device frames -> pyramids for images [first, first+count); dframes points at image `first`
-static int build_u8_device(klt_ctx *ctx, klt_pyr *p, const uint8_t *dframes, size_t pitch, size_t frame_stride,
-                           const klt_taps *taps, int precision, int first, int count, bool windowed = false) {
+int klt_build_u8_device(klt_ctx *ctx, klt_pyr *p, const uint8_t *dframes, size_t pitch, size_t frame_stride,
+                        const klt_taps *taps, int precision, int first, int count, bool windowed) {
     int rc;
     if (windowed) {
         // u8 -> smoothed image only
@@ -410,7 +416,7 @@ int klt_pyr_build_u8(klt_ctx *ctx, klt_pyr *p, const uint8_t *frames, size_t pit
     if (pitch < (size_t)p->w) return klt_fail(ctx, KLT_ERR_INVALID, "pitch %zu smaller than width %d", pitch, p->w);
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
     bool windowed;
-    precision = begin_build(p, taps, precision, &windowed);
+    precision = klt_begin_build(p, taps, precision, &windowed);
     const uint8_t *dframes = frames;
     if (!klt_is_device_ptr(frames)) {
         const size_t bytes = (size_t)(p->batch - 1) * frame_stride + (size_t)(p->h - 1) * pitch + p->w;
@@ -418,7 +424,7 @@ int klt_pyr_build_u8(klt_ctx *ctx, klt_pyr *p, const uint8_t *frames, size_t pit
         KLT_CUDA(ctx, cudaMemcpyAsync(ctx->ws, frames, bytes, cudaMemcpyHostToDevice, ctx->stream));
         dframes = (const uint8_t *)ctx->ws;
     }
-    return build_u8_device(ctx, p, dframes, pitch, frame_stride, taps, precision, 0, p->batch, windowed);
+    return klt_build_u8_device(ctx, p, dframes, pitch, frame_stride, taps, precision, 0, p->batch, windowed);
 }
 
 int klt_pyr_build_f32(klt_ctx *ctx, klt_pyr *p, const float *images, size_t pitch, size_t frame_stride,
@@ -429,7 +435,7 @@ int klt_pyr_build_f32(klt_ctx *ctx, klt_pyr *p, const float *images, size_t pitc
     if (pitch < (size_t)p->w) return klt_fail(ctx, KLT_ERR_INVALID, "pitch %zu smaller than width %d", pitch, p->w);
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
     bool windowed;
-    precision = begin_build(p, taps, precision, &windowed);
+    precision = klt_begin_build(p, taps, precision, &windowed);
     if (already_smoothed) {
         for (int b = 0; b < p->batch; b++)
             KLT_CUDA(ctx, cudaMemcpy2DAsync(p->level(0, b, 0), p->lv[0].pitch * sizeof(float), images + (size_t)b * frame_stride,
@@ -510,15 +516,30 @@ int klt_select_good_features(klt_ctx *ctx, const klt_params *params, const klt_p
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
     if (pyr) {
         if (image < 0 || image >= pyr->batch) return klt_fail(ctx, KLT_ERR_INVALID, "image index out of range");
-        int rc = ensure_gradients_level0(ctx, const_cast<klt_pyr *>(pyr));      // image-only pyramids: build level 0's planes now
+        if (pyr->batch == 1) return klt_select_batch(ctx, params, KLT_SELECT_STRICT, const_cast<klt_pyr *>(pyr), nullptr, nullptr, 0, 0, pyr->w, pyr->h, 1, n_features, replace, x, y, val, n_consumed);
+        int rc = klt_ensure_gradients_level0(ctx, const_cast<klt_pyr *>(pyr));      // image-only pyramids: build level 0's planes now
         if (rc) return rc;
-        return klt_select_device(ctx, params, pyr->level(1, image, 0), pyr->level(2, image, 0), pyr->lv[0].pitch, pyr->w, pyr->h,
-                                 n_features, replace, x, y, val, n_consumed);
+        return klt_select_batch(ctx, params, KLT_SELECT_STRICT, nullptr, pyr->level(1, image, 0), pyr->level(2, image, 0), 0, pyr->lv[0].pitch, pyr->w, pyr->h,
+                                1, n_features, replace, x, y, val, n_consumed);
     }
     if (!gradx || !grady || w <= 0 || h <= 0) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
     if (!klt_is_device_ptr(gradx) || !klt_is_device_ptr(grady))
         return klt_fail(ctx, KLT_ERR_INVALID, "explicit gradient images must be device pointers (use a pyramid or klt_device_alloc)");
-    return klt_select_device(ctx, params, gradx, grady, w, w, h, n_features, replace, x, y, val, n_consumed);
+    return klt_select_batch(ctx, params, KLT_SELECT_STRICT, nullptr, gradx, grady, 0, w, w, h, 1, n_features, replace, x, y, val, n_consumed);
+}
+
+int klt_select_good_features_batch(klt_ctx *ctx, const klt_params *params, klt_pyr *pyr, int n_features, int replace,
+                                   int select_mode, double *x, double *y, int32_t *val) {
+    if (!ctx || !params || !pyr || !x || !y || !val || n_features < 0) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    if (select_mode != KLT_SELECT_STRICT && select_mode != KLT_SELECT_FAST) return klt_fail(ctx, KLT_ERR_INVALID, "select_mode must be KLT_SELECT_STRICT or KLT_SELECT_FAST");
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    return klt_select_batch(ctx, params, select_mode, pyr, nullptr, nullptr, 0, 0, pyr->w, pyr->h, pyr->batch, n_features, replace, x, y, val, nullptr);
+}
+
+int klt_eigen_map_batch(klt_ctx *ctx, const klt_params *params, klt_pyr *pyr, int select_mode, float *val, int *nx, int *ny) {
+    if (!ctx || !params || !pyr) return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
+    KLT_CUDA(ctx, cudaSetDevice(ctx->device));
+    return klt_eigen_maps(ctx, params, select_mode, pyr, val, nx, ny);
 }
 
 // ---- tracking -----------------------------------------------------------------------------------------------
@@ -815,8 +836,8 @@ static int track_pairs_impl(klt_ctx *ctx, const klt_params *params, const klt_ta
     // this half may still be read by the builds of the call before last
     KLT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->half_free[half], 0));
     bool windowed;
-    begin_build(pyr1, taps, precision, &windowed);
-    precision = begin_build(pyr2, taps, precision, &windowed);
+    klt_begin_build(pyr1, taps, precision, &windowed);
+    precision = klt_begin_build(pyr2, taps, precision, &windowed);
     int k = 0;
     for (int first = 0; first < B; first += per_chunk, k++) {
         const int count = first + per_chunk <= B ? per_chunk : B - first;
@@ -830,8 +851,8 @@ static int track_pairs_impl(klt_ctx *ctx, const klt_params *params, const klt_ta
         const int count = first + per_chunk <= B ? per_chunk : B - first;
         const size_t off = (size_t)first * frame_stride;
         KLT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[k], 0));
-        if ((rc = build_u8_device(ctx, pyr1, d1 + off, pitch, frame_stride, taps, precision, first, count, windowed))) return rc;
-        if ((rc = build_u8_device(ctx, pyr2, d2 + off, pitch, frame_stride, taps, precision, first, count, windowed))) return rc;
+        if ((rc = klt_build_u8_device(ctx, pyr1, d1 + off, pitch, frame_stride, taps, precision, first, count, windowed))) return rc;
+        if ((rc = klt_build_u8_device(ctx, pyr2, d2 + off, pitch, frame_stride, taps, precision, first, count, windowed))) return rc;
     }
     KLT_CUDA(ctx, cudaEventRecord(ctx->half_free[half], ctx->stream));
     return track_impl(ctx, params, pyr1, pyr2, n_per_image, x, y, val, nullptr, nullptr, async);

@@ -87,6 +87,7 @@ struct klt_ctx {
     void *ws;
     size_t ws_bytes;
     int num_sms;
+    int select_chunk;           // chunk capacity of select_walk_kernel (4096; $KLT_B200_SELECT_CHUNK shrinks it for tests)
 };
 
 int klt_fail(klt_ctx *ctx, int code, const char *fmt, ...);
@@ -120,6 +121,16 @@ static inline bool klt_pyr_has_gradients(const klt_pyr *p) { return !p->hx || p-
 
 int klt_make_taps(klt_ctx *ctx, const klt_kernel1d *k, TapsF *f, TapsD *d);
 
+// ---- klt_api.cu: pieces of the pyramid build that klt_sequence.cu reuses --------------------------------
+extern "C" {   // (defined inside klt_api.cu's extern "C" block; not part of the public ABI)
+// bookkeeping of a build: `precision` as given by the caller; returns the arithmetic precision to run with
+int klt_begin_build(klt_pyr *p, const klt_taps *taps, int precision, bool *windowed);
+// device frames -> pyramids for images [first, first+count); dframes points at image `first`
+int klt_build_u8_device(klt_ctx *ctx, klt_pyr *p, const uint8_t *dframes, size_t pitch, size_t frame_stride,
+                        const klt_taps *taps, int precision, int first, int count, bool windowed);
+int klt_ensure_gradients_level0(klt_ctx *ctx, klt_pyr *p);
+}
+
 // ---- launchers (klt_conv.cu) -- all pointers are DEVICE pointers, pitches in elements ----------------
 // separable convolution out = vk_v( hk_h(in) ), batched over `batch` images
 int klt_launch_conv_sep_f32(klt_ctx *ctx, const float *in, size_t in_pitch, size_t in_stride, float *out,
@@ -150,8 +161,13 @@ int klt_stream_down2(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps, 
 // ---- klt_select.cu -----------------------------------------------------------------------------------
 int klt_launch_scan(klt_ctx *ctx, const float *gx, const float *gy, size_t pitch, int w, int h, int bx, int by,
                     int hw, int hh, int skip, float *val_dev /* [ny][nx] */, int nx, int ny);
-int klt_select_device(klt_ctx *ctx, const klt_params *p, const float *gx, const float *gy, size_t pitch, int w,
-                      int h, int n_features, int replace, double *x, double *y, int32_t *val, int64_t *n_consumed);
+// full selection for every image of `pyr` (or, pyr == NULL, for B explicit device gradient images img_stride apart);
+// x, y, val: [B][n_features] host or device
+int klt_select_batch(klt_ctx *ctx, const klt_params *p, int select_mode, klt_pyr *pyr, const float *gx0, const float *gy0,
+                     size_t img_stride, size_t pitch, int w, int h, int B, int n_features, int replace, double *x, double *y,
+                     int32_t *val, int64_t *n_consumed);
+
+int klt_eigen_maps(klt_ctx *ctx, const klt_params *p, int select_mode, klt_pyr *pyr, float *val, int *nx_out, int *ny_out);
 
 // ---- klt_track.cu ------------------------------------------------------------------------------------
 int klt_launch_track(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const klt_pyr *p2, int n_per_image,

@@ -1,26 +1,36 @@
-// Good-feature selection on the GPU (sm_100a).
+// Good-feature selection on the GPU (sm_100a), batched over the images of a pyramid batch and free of host
+// synchronisation: every decision (how many candidates to sort, when to stop, when to widen the candidate set) is taken
+// on the device, so a whole selection -- or a whole sequence step (klt_sequence.cu) -- is one chain of launches that can
+// be captured in a CUDA graph.
 //
 // Replaces goodFeaturesUtils.ScanImageForGoodFeatures (goodFeaturesUtils.pyx:35-73), the candidate sort
 // (selectGoodFeatures.py:234-236) and _enforceMinimumDistance (selectGoodFeatures.py:45-135).
 //
-// The reference's eigenvalues carry the rounding of three float32 summed-area tables built by strictly
-// sequential additions (np.cumsum along rows, then along columns); selection ORDER depends on that rounding
-// (SURVEY 7.3), so the tables are rebuilt here with the same chains: one lane per row (tiles transposed through
-// shared memory so that global traffic stays coalesced), then one thread per column.  A parallel prefix scan would
+// STRICT eigenvalues: the reference's values carry the rounding of three float32 summed-area tables built by strictly
+// sequential additions (np.cumsum along rows, then along columns); selection ORDER depends on that rounding,
+// so the tables are rebuilt with the same chains: one lane per row (tiles transposed through shared memory so that
+// global traffic stays coalesced), then one thread per column, then the four-corner combine.  A parallel prefix scan would
 // be faster per element but produces different float32 sums.
+// FAST eigenvalues (klt_select_fast.cu): gradients, window sums and the eigenvalue from one shared-memory tile.
 //
-// The reference sorts every candidate (1.87 M at 1080p) although greedy suppression consumes only the best ~8.5 N.
-// Here a histogram of the eigenvalues picks a threshold that keeps roughly the best M = 32 N + 8192 candidates, only
-// those are sorted (stable LSD radix sort on 64-bit keys) and walked; if the walk runs out of candidates before every
-// slot is filled, the selection is repeated without the threshold, so the result is always the exact greedy result.
+// Sort + greedy: the reference sorts every candidate (1.87 M at 1080p) although the greedy walk consumes only the best
+// ~8.5 N.  Here the eigen kernels also build a 4096-bin histogram of the values (exponent + 7 mantissa bits, 0.8 %
+// resolution); select_plan_kernel picks the bin range that holds about 32 N + 8192 candidates; select_scatter_kernel
+// writes those candidates grouped by bin (descending) -- a one-pass MSD radix step; select_walk_kernel (one CTA per
+// image) then takes bin groups of up to 4096 candidates at a time: drops the ones a feature accepted earlier already
+// suppresses, sorts the rest in shared memory (bitonic) and runs the exact sequential greedy recurrence on them.  If the
+// range runs out before every slot is filled the CTA widens it by itself (gathers the next bins from the eigenvalue map)
+// until the map is exhausted, so the result is always the exact greedy result.  Replacement mode (KLTReplaceLostFeatures)
+// leaves the candidates that surviving features suppress out of the histogram and the keys.
 #include <cuda_pipeline.h>
 
 #include "klt_common.cuh"
+#include "klt_select.cuh"
 
-// ---- summed-area tables -------------------------------------------------------------------------------
+// ---- summed-area tables: row pass -----------------------------------------------------------------------
 // rows: s[y][x] = s[y][x-1] + p[y][x], p = exact fp32 product (np.power(g,2.) / g*g, pyx:49-51).
-// One warp owns 32 rows.  32x32 tiles of gx, gy are brought in with cp.async (double buffered, coalesced), each lane
-// then walks ITS row of the tile sequentially (the float32 chain of np.cumsum), and the three result tiles go back
+// One warp owns 32 rows of one image.  32x32 tiles of gx, gy are brought in with cp.async (ring of 4, coalesced), each
+// lane then walks ITS row of the tile sequentially (the float32 chain of np.cumsum), and the three result tiles go back
 // transposed so that the stores are coalesced too.
 #define SAT_T 32
 #define SAT_NBUF 4                      // cp.async ring: tiles are requested 3 chunks ahead of their use
@@ -30,11 +40,13 @@ struct SatSmem {
 };
 
 __global__ void __launch_bounds__(32)
-sat_rows_kernel(const float *__restrict__ gx, const float *__restrict__ gy, size_t pitch, int W, int H,
-                float *__restrict__ sxx, float *__restrict__ sxy, float *__restrict__ syy) {
+sat_rows_kernel(const float *__restrict__ gx0, const float *__restrict__ gy0, size_t img_stride, size_t pitch, int W, int H,
+                float *__restrict__ sat, size_t plane) {
     __shared__ SatSmem sm;
     const int lane = threadIdx.x;
     const int y0 = blockIdx.x * SAT_T;
+    const float *gx = gx0 + (size_t)blockIdx.y * img_stride, *gy = gy0 + (size_t)blockIdx.y * img_stride;
+    float *sxx = sat + (size_t)blockIdx.y * 3 * plane, *sxy = sxx + plane, *syy = sxy + plane;
     const int nchunks = (W + SAT_T - 1) / SAT_T;
     auto issue = [&](int chunk, int buf) {
         const int x = chunk * SAT_T + lane;
@@ -89,12 +101,14 @@ struct SatSmemV {
     float out[3][SAT_T][SAT_S];
 };
 __global__ void __launch_bounds__(32)
-sat_rows_vec_kernel(const float *__restrict__ gx, const float *__restrict__ gy, size_t pitch, int W, int H,
-                    float *__restrict__ sxx, float *__restrict__ sxy, float *__restrict__ syy) {
+sat_rows_vec_kernel(const float *__restrict__ gx0, const float *__restrict__ gy0, size_t img_stride, size_t pitch, int W, int H,
+                    float *__restrict__ sat, size_t plane) {
     extern __shared__ __align__(16) unsigned char sat_raw[];
     SatSmemV &sm = *reinterpret_cast<SatSmemV *>(sat_raw);
     const int lane = threadIdx.x;
     const int y0 = blockIdx.x * SAT_T;
+    const float *gx = gx0 + (size_t)blockIdx.y * img_stride, *gy = gy0 + (size_t)blockIdx.y * img_stride;
+    float *sxx = sat + (size_t)blockIdx.y * 3 * plane, *sxy = sxx + plane, *syy = sxy + plane;
     const int nchunks = W / SAT_T;
     const int q = lane & 7, r8 = lane >> 3;            // 16-byte chunk within a tile row, row within a group of 4
     auto issue = [&](int chunk, int buf) {
@@ -153,12 +167,28 @@ sat_rows_vec_kernel(const float *__restrict__ gx, const float *__restrict__ gy, 
         __syncwarp();
     }
 }
-// columns: s[y][x] = s[y-1][x] + s[y][x]; blockIdx.y selects the table
+
+// min eigenvalue (pyx:17-19), operand types as in the Cython-generated C
+__device__ __forceinline__ float min_eigenvalue(float gxx, float gxy, float gyy) {
+    const float d = __fsub_rn(gxx, gyy);
+    const float dd = __fmul_rn(d, d);
+    const double t = __dadd_rn((double)dd, __dmul_rn(__dmul_rn(4.0, (double)gxy), (double)gxy));
+    const float sqrtTerm = __double2float_rn(sqrt(t));   // reference: pow(t, 0.5); IEEE sqrt is the correctly rounded value
+    const float s = __fsub_rn(__fadd_rn(gxx, gyy), sqrtTerm);
+    return __double2float_rn(__dmul_rn((double)s, 0.5));   // s / 2. exactly (a power of two)
+}
+
+// ---- column pass -----------------------------------------------------------------------------------------------------
+// columns: s[y][x] = s[y-1][x] + s[y][x] (np.cumsum(axis 0), sequential), in place.  One thread owns one column of one
+// table of one image; 16 independent loads are in flight per thread while the add chain runs.  (A variant that kept the
+// running sums in a shared-memory ring and evaluated the eigenvalues from it -- no write-back of the tables -- was
+// measured at 914 us per 8 images against 130 + 40 us for this pass plus the eigen kernel: with one chain per thread the
+// fused kernel cannot hide the latency of the eigenvalue's float64 sqrt behind anything.)
 __global__ void __launch_bounds__(64)
-sat_cols_kernel(float *__restrict__ s0, float *__restrict__ s1, float *__restrict__ s2, int W, int H) {
+sat_cols_kernel(float *__restrict__ sat, size_t plane, int W, int H) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= W) return;
-    float *s = (blockIdx.y == 0 ? s0 : blockIdx.y == 1 ? s1 : s2) + x;
+    float *s = sat + ((size_t)blockIdx.z * 3 + blockIdx.y) * plane + x;
     float acc = s[0];
     int y = 1;
     for (; y + 16 <= H; y += 16) {
@@ -171,21 +201,121 @@ sat_cols_kernel(float *__restrict__ s0, float *__restrict__ s1, float *__restric
     for (; y < H; y++) { acc = __fadd_rn(acc, s[(size_t)y * W]); s[(size_t)y * W] = acc; }
 }
 
-// four-corner combine + min eigenvalue (pyx:17-31), operand types as in the Cython-generated C
+// four-corner combine (pyx:23-31): (c + a - b - d) in float32, in that order
 __device__ __forceinline__ float window_sum(const float *__restrict__ s, int W, int x, int y, int hw, int hh) {
     const float a = s[(size_t)(y - hh - 1) * W + (x - hw - 1)], b = s[(size_t)(y - hh - 1) * W + (x + hw)];
     const float c = s[(size_t)(y + hh) * W + (x + hw)], d = s[(size_t)(y + hh) * W + (x - hw - 1)];
     return __fsub_rn(__fsub_rn(__fadd_rn(c, a), b), d);
 }
-__device__ __forceinline__ float min_eigenvalue(float gxx, float gxy, float gyy) {
-    const float d = __fsub_rn(gxx, gyy);
-    const float dd = __fmul_rn(d, d);
-    const double t = __dadd_rn((double)dd, __dmul_rn(__dmul_rn(4.0, (double)gxy), (double)gxy));
-    const float sqrtTerm = __double2float_rn(sqrt(t));   // reference: pow(t, 0.5); IEEE sqrt is the correctly rounded value
-    const float s = __fsub_rn(__fadd_rn(gxx, gyy), sqrtTerm);
-    return __double2float_rn(__ddiv_rn((double)s, 2.0));
+
+// eigenvalue map (+ histogram of the values >= min_val that no surviving feature suppresses).  One block = 256 candidate
+// columns x EIG_ROWS candidate rows of one image.
+#define EIG_ROWS 8
+template <bool HIST>
+__global__ void __launch_bounds__(256)
+eigen_kernel(const float *__restrict__ sat, size_t plane, const __grid_constant__ SelDev S) {
+    __shared__ unsigned int h[HIST ? SEL_BINS : 1];
+    const int b = blockIdx.z;
+    if (HIST) {
+        for (int k = threadIdx.x; k < SEL_BINS; k += 256) h[k] = 0;
+        __syncthreads();
+    }
+    const float *sxx = sat + (size_t)b * 3 * plane, *sxy = sxx + plane, *syy = sxy + plane;
+    float *vmap = S.vmap + (size_t)b * S.ncand;
+    const unsigned char *pm = S.premap ? S.premap + (size_t)b * S.map_stride : nullptr;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    for (int jj = 0; jj < EIG_ROWS; jj++) {
+        const int j = blockIdx.y * EIG_ROWS + jj;
+        if (i < S.nx && j < S.ny) {
+            const int x = S.bx + i * S.step, y = S.by + j * S.step;
+            const float v = min_eigenvalue(window_sum(sxx, S.W, x, y, S.hw, S.hh), window_sum(sxy, S.W, x, y, S.hw, S.hh),
+                                           window_sum(syy, S.W, x, y, S.hw, S.hh));
+            vmap[(size_t)j * S.nx + i] = v;
+            if (HIST && v >= S.min_val && !(pm && pm[(size_t)y * S.W + x])) atomicAdd(&h[eig_rbin(v)], 1u);
+        }
+    }
+    if (HIST) {
+        __syncthreads();
+        unsigned int *hist = S.hist + (size_t)b * SEL_BINS;
+        for (int k = threadIdx.x; k < SEL_BINS; k += 256)
+            if (h[k]) atomicAdd(&hist[k], h[k]);
+    }
 }
 
+// ---- plan: which bins to sort first ---------------------------------------------------------------------------------
+// block-wide inclusive scan of one value per thread (WALK_THREADS threads)
+__device__ __forceinline__ unsigned int block_scan_incl(unsigned int v, unsigned int *warp_tot /* [32] shared */, unsigned int *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    __syncthreads();                                    // warp_tot may still be read by a previous call
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned int base = 0, tot = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) { const unsigned int c = warp_tot[w]; if (w < warp) base += c; tot += c; }
+    if (total) *total = tot;
+    return incl + base;
+}
+
+// Range of reversed bins [rb_lo, rb_hi] holding at least `target` candidates (or everything that is left).  Fills
+// pre[rb] = candidates in bins [rb_lo, rb) for every rb (pre[SEL_BINS] = all of them; bins below rb_lo count as empty) and,
+// if given, cur[rb] = the same (the gather's append cursors).  WALK_THREADS threads, 4 bins each; results through shared scalars.
+__device__ void plan_range(const unsigned int *__restrict__ hist, unsigned int rb_lo, unsigned int target, unsigned int *pre,
+                           unsigned int *cur, unsigned int *warp_tot, unsigned int *s_rb_hi, unsigned int *s_nkeys) {
+    const int t = threadIdx.x;
+    unsigned int c[4], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const unsigned int rb = 4 * t + j;
+        c[j] = rb >= rb_lo ? hist[rb] : 0u;
+        sum += c[j];
+    }
+    if (t == 0) *s_rb_hi = SEL_BINS - 1;
+    const unsigned int incl = block_scan_incl(sum, warp_tot, nullptr);     // contains two __syncthreads
+    unsigned int run = incl - sum;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const unsigned int rb = 4 * t + j;
+        pre[rb] = run;
+        if (cur) cur[rb] = run;
+        if (run < target && run + c[j] >= target) atomicMin(s_rb_hi, rb);  // the bin in which the running count reaches the target
+        run += c[j];
+    }
+    if (t == WALK_THREADS - 1) pre[SEL_BINS] = run;
+    __syncthreads();
+    if (t == 0) *s_nkeys = pre[*s_rb_hi + 1];
+    __syncthreads();
+}
+
+__device__ __forceinline__ unsigned int count_lost(const int *__restrict__ fval, int n, unsigned int *warp_tot) {
+    unsigned int mine = 0;
+    for (int f = threadIdx.x; f < n; f += blockDim.x) mine += fval[f] < 0 ? 1u : 0u;
+    unsigned int tot;
+    block_scan_incl(mine, warp_tot, &tot);
+    return tot;
+}
+
+__global__ void __launch_bounds__(WALK_THREADS)
+select_plan_kernel(const __grid_constant__ SelDev S) {
+    __shared__ unsigned int pre[SEL_BINS + 1];
+    __shared__ unsigned int warp_tot[32];
+    __shared__ unsigned int s_rb_hi, s_nkeys;
+    const int b = blockIdx.x, t = threadIdx.x;
+    const unsigned int slots = S.replace ? count_lost(S.fval + (size_t)b * S.n_features, S.n_features, warp_tot) : (unsigned int)S.n_features;
+    const unsigned int target = slots ? S.target_mul * slots + S.target_add : 0u;
+    unsigned int *plan = S.plan + (size_t)b * SEL_PLAN_WORDS;
+    unsigned int *offs = S.offs + (size_t)b * (SEL_BINS + 1), *cursor = S.cursor + (size_t)b * SEL_BINS;
+    if (target == 0) {          // nothing to fill: no keys at all
+        if (t == 0) { plan[SEL_PLAN_RB_HI] = 0xFFFFFFFFu; plan[SEL_PLAN_NKEYS] = 0; plan[SEL_PLAN_SLOTS] = 0; }
+        return;
+    }
+    plan_range(S.hist + (size_t)b * SEL_BINS, 0u, target, pre, nullptr, warp_tot, &s_rb_hi, &s_nkeys);
+    for (int k = t; k < SEL_BINS; k += WALK_THREADS) { offs[k] = pre[k]; cursor[k] = 0; }
+    if (t == 0) { offs[SEL_BINS] = pre[SEL_BINS]; plan[SEL_PLAN_RB_HI] = s_rb_hi; plan[SEL_PLAN_NKEYS] = s_nkeys; plan[SEL_PLAN_SLOTS] = slots; }
+}
+
+// ---- scatter: candidates of the planned bin range -> keys grouped by bin (descending value) -----------------------------
 // key layout (ascending sort of ~key == descending (val, x, y)): [val bits 32][x 13][y 13]
 __device__ __forceinline__ unsigned long long make_key(float val, int x, int y) {
     const unsigned long long k = ((unsigned long long)__float_as_uint(val) << 26) | ((unsigned long long)x << 13) |
@@ -193,232 +323,65 @@ __device__ __forceinline__ unsigned long long make_key(float val, int x, int y) 
     return ~k;
 }
 
-// histogram bin of an eigenvalue >= 1: exponent and 5 mantissa bits (3 % resolution), 2048 bins
-#define EIG_BINS 2048
-__device__ __forceinline__ int eig_bin(float v) {
-    const int b = (int)(__float_as_uint(v) >> 18) - (0x3F800000 >> 18);
-    return min(max(b, 0), EIG_BINS - 1);
-}
-
-// eigenvalue map (+ optional histogram of the values >= min_val).  One block = 256 columns x EIG_ROWS candidate rows.
-#define EIG_ROWS 8
+#define SCAT_ROWS 4
 __global__ void __launch_bounds__(256)
-eigen_kernel(const float *__restrict__ sxx, const float *__restrict__ sxy, const float *__restrict__ syy, int W,
-             int bx, int by, int hw, int hh, int step, int nx, int ny, float *__restrict__ val_out,
-             unsigned int *__restrict__ hist, float min_val) {
-    __shared__ unsigned int h[EIG_BINS];
-    if (hist) {
-        for (int b = threadIdx.x; b < EIG_BINS; b += 256) h[b] = 0;
-        __syncthreads();
-    }
+select_scatter_kernel(const __grid_constant__ SelDev S) {
+    const int b = blockIdx.z;
+    const unsigned int rb_hi = S.plan[(size_t)b * SEL_PLAN_WORDS + SEL_PLAN_RB_HI];
+    if (rb_hi == 0xFFFFFFFFu) return;
     const int i = blockIdx.x * 256 + threadIdx.x;
-    for (int jj = 0; jj < EIG_ROWS; jj++) {
-        const int j = blockIdx.y * EIG_ROWS + jj;
-        if (i < nx && j < ny) {
-            const int x = bx + i * step, y = by + j * step;
-            const float v = min_eigenvalue(window_sum(sxx, W, x, y, hw, hh), window_sum(sxy, W, x, y, hw, hh),
-                                           window_sum(syy, W, x, y, hw, hh));
-            val_out[(size_t)j * nx + i] = v;
-            if (hist && v >= min_val) atomicAdd(&h[eig_bin(v)], 1u);
+    const float *vmap = S.vmap + (size_t)b * S.ncand;
+    const unsigned char *pm = S.premap ? S.premap + (size_t)b * S.map_stride : nullptr;
+    const unsigned int *offs = S.offs + (size_t)b * (SEL_BINS + 1);
+    unsigned int *cursor = S.cursor + (size_t)b * SEL_BINS;
+    unsigned long long *keys = S.keys + (size_t)b * S.key_stride;
+    const int lane = threadIdx.x & 31;
+    for (int jj = 0; jj < SCAT_ROWS; jj++) {
+        const int j = blockIdx.y * SCAT_ROWS + jj;
+        bool keep = false;
+        float v = 0.f;
+        int x = 0, y = 0, rb = SEL_BINS;
+        if (i < S.nx && j < S.ny) {
+            v = vmap[(size_t)j * S.nx + i];
+            x = S.bx + i * S.step; y = S.by + j * S.step;
+            if (v >= S.min_val) {                         // candidates below min_eigenvalue can never be accepted (:116)
+                rb = eig_rbin(v);
+                keep = (unsigned int)rb <= rb_hi && !(pm && pm[(size_t)y * S.W + x]);
+            }
+        }
+        if (!__any_sync(0xffffffffu, keep)) continue;     // the usual case: the planned range holds ~0.1-2 % of the candidates
+        // warp-aggregated append: one atomic per distinct bin in the warp
+        const unsigned int peers = __match_any_sync(0xffffffffu, keep ? rb : SEL_BINS + lane);
+        if (keep) {
+            const int leader = __ffs(peers) - 1;
+            unsigned int base = 0;
+            if (lane == leader) base = atomicAdd(&cursor[rb], (unsigned int)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            keys[offs[rb] + base + __popc(peers & ((1u << lane) - 1u))] = make_key(v, x, y);
         }
     }
-    if (hist) {
-        __syncthreads();
-        for (int b = threadIdx.x; b < EIG_BINS; b += 256)
-            if (h[b]) atomicAdd(&hist[b], h[b]);
-    }
 }
 
-// picks the highest bin T such that at least `target` candidates lie in bins >= T (T = 0 if there are fewer)
-__global__ void __launch_bounds__(32)
-threshold_kernel(const unsigned int *__restrict__ hist, unsigned int target, int force_all, unsigned int *__restrict__ out /* [0]=T */) {
-    const int lane = threadIdx.x;
-    constexpr int PER = EIG_BINS / 32;
-    unsigned int mine = 0;
-    for (int b = 0; b < PER; b++) mine += hist[lane * PER + b];
-    unsigned int suffix = mine;                       // inclusive suffix sum over lanes (lane 31 = highest bins)
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned int v = __shfl_down_sync(0xffffffffu, suffix, o);
-        if (lane + o < 32) suffix += v;
-    }
-    const unsigned int above = suffix - mine;         // candidates in lanes above this one
-    const bool here = above < target && suffix >= target;
-    const unsigned int m = __ballot_sync(0xffffffffu, here);
-    if (force_all || m == 0u) { if (lane == 0) out[0] = 0; return; }
-    if (here) {
-        unsigned int acc = above;
-        int T = lane * PER;
-        for (int b = PER - 1; b >= 0; b--) {
-            acc += hist[lane * PER + b];
-            if (acc >= target) { T = lane * PER + b; break; }
-        }
-        out[0] = (unsigned int)T;
-    }
-}
-
-// compaction of the candidates with bin >= T into 64-bit keys (block-aggregated append; order is irrelevant, the
-// keys are unique and get sorted)
-__global__ void __launch_bounds__(256)
-compact_kernel(const float *__restrict__ val, int bx, int by, int step, int nx, int ny, float min_val,
-               const unsigned int *__restrict__ thr, unsigned long long *__restrict__ keys, unsigned int *__restrict__ nkeys) {
-    __shared__ unsigned int warp_cnt[8];
-    __shared__ unsigned int block_base;
-    const int i = blockIdx.x * 256 + threadIdx.x, j = blockIdx.y;
-    const int T = (int)thr[0];
-    float v = 0.f;
-    bool keep = false;
-    if (i < nx && j < ny) {
-        v = val[(size_t)j * nx + i];
-        keep = v >= min_val && eig_bin(v) >= T;     // candidates below min_eigenvalue can never be accepted (:116)
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned int m = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) warp_cnt[warp] = __popc(m);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int tot = 0;
-        for (int w = 0; w < 8; w++) { const unsigned int c = warp_cnt[w]; warp_cnt[w] = tot; tot += c; }
-        block_base = tot ? atomicAdd(nkeys, tot) : 0u;
-    }
-    __syncthreads();
-    if (keep) keys[block_base + warp_cnt[warp] + __popc(m & ((1u << lane) - 1u))] = make_key(v, bx + i * step, by + j * step);
-}
-
-// ---- LSD radix sort of 64-bit keys (8-bit digits, stable) -----------------------------------------------
-#define RS_THREADS 256
-#define RS_ITEMS 4
-#define RS_CHUNK (RS_THREADS * RS_ITEMS)
-#define RS_FUSED_SCAN_BLOCKS 96   // up to this many blocks each scatter block scans the raw counts itself
-
-__global__ void __launch_bounds__(RS_THREADS)
-rs_hist_kernel(const unsigned long long *__restrict__ keys, const unsigned int *__restrict__ n_ptr, int shift,
-               unsigned int *__restrict__ hist, int nblocks) {
-    __shared__ unsigned int h[256];
-    const unsigned int n = *n_ptr;
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    const size_t base = (size_t)blockIdx.x * RS_CHUNK;
-    for (int r = 0; r < RS_ITEMS; r++) {
-        const size_t i = base + (size_t)r * RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&h[(unsigned int)(keys[i] >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
-}
-
-// exclusive scan of hist[0..total) in place, one CTA
-__global__ void __launch_bounds__(1024)
-rs_scan_kernel(unsigned int *__restrict__ hist, int total) {
-    __shared__ unsigned int part[1024];
-    const int t = threadIdx.x;
-    const int per = (total + 1023) / 1024;
-    const int lo = min(t * per, total), hi = min(lo + per, total);
-    unsigned int s = 0;
-    for (int i = lo; i < hi; i++) s += hist[i];
-    part[t] = s;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {       // Hillis-Steele inclusive scan
-        unsigned int v = t >= off ? part[t - off] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    unsigned int run = part[t] - s;
-    for (int i = lo; i < hi; i++) { const unsigned int v = hist[i]; hist[i] = run; run += v; }
-}
-
-template <bool SCANNED>
-__global__ void __launch_bounds__(RS_THREADS)
-rs_scatter_kernel(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out,
-                  const unsigned int *__restrict__ n_ptr, int shift, const unsigned int *__restrict__ hist, int nblocks) {
-    __shared__ unsigned int running[256];
-    __shared__ unsigned int wh[RS_THREADS / 32][256];
-    __shared__ unsigned int wtot[RS_THREADS / 32];
-    const unsigned int n = *n_ptr;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (SCANNED) {
-        running[t] = hist[(size_t)t * nblocks + blockIdx.x];
-    } else {
-        // few blocks: every block derives its own offsets from the raw per-block counts (saves the scan launch).
-        // offset(digit t, this block) = keys with a smaller digit + keys with digit t in earlier blocks
-        unsigned int total = 0, before = 0;
-        for (int b = 0; b < nblocks; b++) {
-            const unsigned int c = hist[(size_t)t * nblocks + b];
-            total += c;
-            if (b < (int)blockIdx.x) before += c;
-        }
-        unsigned int incl = total;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        if (lane == 31) wtot[warp] = incl;
-        __syncthreads();
-        unsigned int wbase = 0;
-        for (int w = 0; w < warp; w++) wbase += wtot[w];
-        running[t] = wbase + incl - total + before;
-    }
-#pragma unroll
-    for (int w = 0; w < RS_THREADS / 32; w++) wh[w][t] = 0;
-    __syncthreads();
-    const size_t base = (size_t)blockIdx.x * RS_CHUNK;
-    for (int r = 0; r < RS_ITEMS; r++) {
-        const size_t i = base + (size_t)r * RS_THREADS + t;
-        const bool valid = i < n;
-        const unsigned long long key = valid ? in[i] : 0ull;
-        const unsigned int d = valid ? ((unsigned int)(key >> shift) & 255u) : (0x1000u + lane);
-        const unsigned int peers = __match_any_sync(0xffffffffu, d);
-        const unsigned int rank = __popc(peers & ((1u << lane) - 1u));
-        if (valid && rank == 0) wh[warp][d] = __popc(peers);
-        __syncthreads();
-        if (valid) {
-            unsigned int off = running[d] + rank;
-            for (int w = 0; w < warp; w++) off += wh[w][d];
-            out[off] = key;
-        }
-        __syncthreads();
-        unsigned int tot = 0;
-#pragma unroll
-        for (int w = 0; w < RS_THREADS / 32; w++) { tot += wh[w][t]; wh[w][t] = 0; }
-        running[t] += tot;
-        __syncthreads();
-    }
-}
-
-// ---- greedy minimum-distance suppression (_enforceMinimumDistance) ----------------------------------------
-// One warp walks the sorted candidates 32 at a time.  Accepted features are remembered in a grid of cells of side
-// cs = r + 1 (r = mindist - 1): two features in one cell would be closer than mindist, so a cell holds at most one and
-// a candidate only has to look at its 3x3 cell neighbourhood (shared memory, or global memory for very large images).
-// Features that survive from a previous frame (replacement mode, :64-69) are pre-marked in a byte map by a separate
-// kernel (they may be closer to each other than mindist); the map value travels with the prefetched key.
-// A candidate also dies if a feature accepted earlier IN THE SAME batch lies within Chebyshev distance r.  This
-// reproduces the sequential greedy walk exactly, including the order in which slots are filled.
-struct GreedyArgs {
-    const unsigned long long *keys;
-    const unsigned int *nkeys;
-    const unsigned char *premap;     // NULL in SELECTING_ALL mode
-    unsigned short *grid_global;     // used when the cell grid does not fit in shared memory
-    int W, H, r, n_features, overwrite;
-    int cs, gw, gh, grid_in_smem;
-    double *fx, *fy;
-    int *fval;
-    int *free_slots;                 // [n_features] scratch: the fillable slots in list order (replacement mode)
-    unsigned long long *consumed;    // [0] candidates consumed, [1] 1 if the keys ran out before all slots were filled
-};
-
-__global__ void __launch_bounds__(256)
-premark_kernel(const double *__restrict__ fx, const double *__restrict__ fy, const int *__restrict__ fval, int n,
-               unsigned char *__restrict__ map, int W, int H, int r) {
-    const int f = blockIdx.x;
-    if (f >= n || fval[f] < 0) return;
-    const int x = (int)fx[f], y = (int)fy[f], side = 2 * r + 1;
+// ---- pre-marking of the surviving features (replacement mode, selectGoodFeatures.py:64-69) ---------------------------
+__global__ void __launch_bounds__(128)
+premark_kernel(const __grid_constant__ SelDev S) {
+    const int f = blockIdx.x, b = blockIdx.y;
+    const size_t fo = (size_t)b * S.n_features + f;
+    if (S.fval[fo] < 0) return;
+    unsigned char *map = S.premap + (size_t)b * S.map_stride;
+    const int x = (int)S.fx[fo], y = (int)S.fy[fo], r = S.r, side = 2 * r + 1;
     for (int idx = threadIdx.x; idx < side * side; idx += blockDim.x) {
         const int iy = y - r + idx / side, ix = x - r + idx % side;
-        if (ix >= 0 && ix < W && iy >= 0 && iy < H) map[(size_t)iy * W + ix] = 1;
+        if (ix >= 0 && ix < S.W && iy >= 0 && iy < S.H) map[(size_t)iy * S.W + ix] = 1;
     }
 }
 
-#define GREEDY_THREADS 1024
-// is candidate (x, y) within Chebyshev distance r of a feature registered in the 3x3 cell neighbourhood?
+// ---- the walk: sort + greedy minimum-distance suppression (_enforceMinimumDistance) -----------------------------------
+// Accepted features are remembered in a grid of cells of side cs = r + 1 (r = mindist - 1): two features in one cell would
+// be closer than mindist, so a cell holds at most one and a candidate only has to look at its 3x3 cell neighbourhood
+// (shared memory, or global memory for very large images).  Features that survive from a previous frame (replacement
+// mode) are not in the grid -- they may be closer to each other than mindist -- the candidates they suppress never become
+// keys.
 __device__ __forceinline__ bool grid_conflict(const unsigned short *grid, int gw, int gh, int cs, int r, int x, int y) {
     const int cx = x / cs, cy = y / cs;
     bool hit = false;
@@ -438,34 +401,106 @@ __device__ __forceinline__ bool grid_conflict(const unsigned short *grid, int gw
     return hit;
 }
 
-// One CTA.  Candidates are taken 1024 at a time: (1) all 32 warps test their candidate against the features accepted in
-// EARLIER super-batches (most candidates die here) and compact the survivors, in order, into shared memory; (2) warp 0
-// walks the survivors 32 at a time with exactly the result of the sequential reference loop: re-test against the grid
-// (features accepted earlier in this super-batch), then resolve the batch in parallel -- lane i is accepted iff no EARLIER
-// accepted lane lies within distance r.  That recurrence is solved by iteration: an undecided lane is rejected as soon as
-// an accepted earlier lane conflicts with it and accepted as soon as all its earlier conflicting lanes are rejected; the
-// lowest undecided lane is decided in every round, typical batches need 2-4 rounds.  Accepted lanes then fill their slots
-// (the k-th accepted candidate takes the k-th fillable slot) and register in the grid all at once.
-__global__ void __launch_bounds__(GREEDY_THREADS)
-greedy_kernel(const __grid_constant__ GreedyArgs A) {
-    extern __shared__ unsigned short grid_smem[];
-    __shared__ unsigned long long surv_key[GREEDY_THREADS];
-    __shared__ unsigned int surv_idx[GREEDY_THREADS];
-    __shared__ unsigned int warp_cnt[32];
-    __shared__ int s_filled, s_slots, s_full, s_nsurv;
-    __shared__ unsigned long long s_consumed;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned int n = *A.nkeys;
-    unsigned short *grid = A.grid_in_smem ? grid_smem : A.grid_global;
-    if (A.r >= 0)
-        for (int c = tid; c < A.gw * A.gh; c += GREEDY_THREADS) grid[c] = 0xFFFFu;
-    // fillable slots: every slot (SELECTING_ALL) or, in list order, the slots of lost features (:64-69, :110-112)
-    if (tid == 0) { s_slots = A.overwrite ? A.n_features : 0; s_filled = 0; s_consumed = 0ull; }
+// in-place ascending bitonic sort of s[0..P), P a power of two, whole block
+__device__ void bitonic_sort(unsigned long long *s, int P) {
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = s[i], b = s[ixj];
+                    if ((a > b) == ((i & k) == 0)) { s[i] = b; s[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// Slow path for a bin that holds more keys than a chunk (massive ties, e.g. periodic patterns): stable LSD radix sort of
+// keys[0..m) in global memory by ONE CTA, 4-bit digits, ping-pong with tmp; the sorted keys end in `keys`.
+__device__ void block_radix_sort(unsigned long long *keys, unsigned long long *tmp, unsigned int m, unsigned int *warp_tot) {
+    __shared__ unsigned int dh[16], dbase[16];
+    __shared__ unsigned int wh[WALK_THREADS / 32][16];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    unsigned long long *src = keys, *dst = tmp;
+    for (int shift = 0; shift < 60; shift += 4) {
+        if (t < 16) dh[t] = 0;
+        __syncthreads();
+        for (unsigned int i = t; i < m; i += WALK_THREADS) atomicAdd(&dh[(unsigned int)(src[i] >> shift) & 15u], 1u);
+        __syncthreads();
+        bool skip = false;
+        if (t < 16) {
+            unsigned int base = 0;
+            for (int d = 0; d < t; d++) base += dh[d];
+            dbase[t] = base;
+        }
+        for (int d = 0; d < 16; d++) skip |= dh[d] == m;              // every key has the same digit: nothing moves
+        __syncthreads();
+        if (skip) continue;
+        for (unsigned int tile = 0; tile < m; tile += WALK_THREADS) {
+            const unsigned int i = tile + t;
+            const bool valid = i < m;
+            const unsigned long long key = valid ? src[i] : 0ull;
+            const unsigned int d = valid ? ((unsigned int)(key >> shift) & 15u) : (16u + lane);
+            const unsigned int peers = __match_any_sync(0xffffffffu, d);
+            const unsigned int rank = __popc(peers & ((1u << lane) - 1u));
+            if (lane < 16) wh[warp][lane] = 0;
+            __syncwarp();
+            if (valid && rank == 0) wh[warp][d] = __popc(peers);
+            __syncthreads();
+            if (valid) {
+                unsigned int o = dbase[d] + rank;
+                for (int w = 0; w < warp; w++) o += wh[w][d];
+                dst[o] = key;
+            }
+            __syncthreads();
+            if (t < 16) {
+                unsigned int tot = 0;
+                for (int w = 0; w < WALK_THREADS / 32; w++) tot += wh[w][t];
+                dbase[t] += tot;
+            }
+            __syncthreads();
+        }
+        unsigned long long *x = src; src = dst; dst = x;
+        __threadfence_block();
+    }
+    if (src != keys) {
+        for (unsigned int i = t; i < m; i += WALK_THREADS) keys[i] = src[i];
+    }
     __syncthreads();
-    if (!A.overwrite) {
-        for (int f0 = 0; f0 < A.n_features; f0 += GREEDY_THREADS) {
+    (void)warp_tot;
+}
+
+__global__ void __launch_bounds__(WALK_THREADS, 1)
+select_walk_kernel(const __grid_constant__ SelDev S, int presorted) {
+    extern __shared__ __align__(16) unsigned char wsm[];
+    unsigned long long *sk = reinterpret_cast<unsigned long long *>(wsm);      // survivors of phase 1 of the current chunk, sorted
+    unsigned int *pre = reinterpret_cast<unsigned int *>(sk + S.ch);            // [SEL_BINS + 1] keys of the current range above each reversed bin
+    unsigned int *off = pre + SEL_BINS + 4;                                     // [SEL_BINS] append cursors of the fallback gather
+    __shared__ unsigned int warp_cnt[32];
+    __shared__ int s_filled, s_slots, s_full, s_ns;
+    __shared__ unsigned int s_m, s_e, s_big, s_rb_hi, s_nkeys;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_features = S.n_features;
+    double *fx = S.fx + (size_t)b * n_features, *fy = S.fy + (size_t)b * n_features;
+    int *fval = S.fval + (size_t)b * n_features;
+    int *free_slots = S.free_slots + (size_t)b * n_features;
+    unsigned long long *keys = S.keys + (size_t)b * S.key_stride, *keys2 = S.keys2 + (size_t)b * S.key_stride;
+    const unsigned int *hist = S.hist + (size_t)b * SEL_BINS;
+    const unsigned int *offs_planned = S.offs + (size_t)b * (SEL_BINS + 1);
+    unsigned long long *status = S.status + (size_t)b * SEL_STATUS_WORDS;
+    unsigned short *grid = S.grid_in_smem ? reinterpret_cast<unsigned short *>(off + SEL_BINS) : S.grid_global + (size_t)b * S.grid_stride;
+    const int overwrite = S.replace ? 0 : 1;
+    const unsigned char *pm_walk = (presorted && S.premap) ? S.premap + (size_t)b * S.map_stride : nullptr;
+    if (S.r >= 0)
+        for (int c = tid; c < S.gw * S.gh; c += WALK_THREADS) grid[c] = 0xFFFFu;
+    // fillable slots: every slot (SELECTING_ALL) or, in list order, the slots of lost features (:64-69, :110-112)
+    if (tid == 0) { s_slots = overwrite ? n_features : 0; s_filled = 0; }
+    __syncthreads();
+    if (!overwrite) {
+        for (int f0 = 0; f0 < n_features; f0 += WALK_THREADS) {
             const int f = f0 + tid;
-            const bool lost = f < A.n_features && A.fval[f] < 0;
+            const bool lost = f < n_features && fval[f] < 0;
             const unsigned int m = __ballot_sync(0xffffffffu, lost);
             if (lane == 0) warp_cnt[warp] = __popc(m);
             __syncthreads();
@@ -474,155 +509,186 @@ greedy_kernel(const __grid_constant__ GreedyArgs A) {
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
                 warp_cnt[lane] = incl - c;
-                if (lane == 31) s_nsurv = (int)incl;
+                if (lane == 31) s_ns = (int)incl;
             }
             __syncthreads();
-            if (lost) A.free_slots[s_slots + warp_cnt[warp] + __popc(m & ((1u << lane) - 1u))] = f;
+            if (lost) free_slots[s_slots + warp_cnt[warp] + __popc(m & ((1u << lane) - 1u))] = f;
             __syncthreads();
-            if (tid == 0) s_slots += s_nsurv;
+            if (tid == 0) s_slots += s_ns;
             __syncthreads();
         }
     }
     if (tid == 0) s_full = s_slots == 0;
     __syncthreads();
-    for (unsigned long long base = 0; base < n && !s_full; base += GREEDY_THREADS) {
-        // ---- phase 1: parallel test against earlier super-batches, ordered compaction of the survivors ----
-        const unsigned long long i = base + tid;
-        bool live = i < n;
-        unsigned long long k = 0ull;
-        if (live) {
-            k = ~A.keys[i];
-            const int x = (int)((k >> 13) & 8191ull), y = (int)(k & 8191ull);
-            if (A.premap && A.premap[(size_t)y * A.W + x]) live = false;
-            if (live && A.r >= 0 && grid_conflict(grid, A.gw, A.gh, A.cs, A.r, x, y)) live = false;
-        }
-        const unsigned int m = __ballot_sync(0xffffffffu, live);
-        if (lane == 0) warp_cnt[warp] = __popc(m);
-        __syncthreads();
-        if (warp == 0) {
-            unsigned int c = warp_cnt[lane], incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            warp_cnt[lane] = incl - c;
-            if (lane == 31) s_nsurv = (int)incl;
-        }
-        __syncthreads();
-        if (live) {
-            const unsigned int pos = warp_cnt[warp] + __popc(m & ((1u << lane) - 1u));
-            surv_key[pos] = k; surv_idx[pos] = (unsigned int)(i - base);
-        }
-        __syncthreads();
-        // ---- phase 2: warp 0 walks the survivors in rank order ----
-        if (warp == 0) {
-            int filled = s_filled;
-            const int slots = s_slots;
-            bool full = false;
-            unsigned int last_off = 0;
-            const int ns = s_nsurv;
-            const unsigned int lt = (1u << lane) - 1u;
-            for (int b0 = 0; b0 < ns && !full; b0 += 32) {
-                const bool valid = b0 + lane < ns;
-                const unsigned long long kk = valid ? surv_key[b0 + lane] : 0ull;
-                const unsigned int off = valid ? surv_idx[b0 + lane] : 0u;
-                const int x = (int)((kk >> 13) & 8191ull), y = (int)(kk & 8191ull);
-                const float val = __uint_as_float((unsigned int)(kk >> 26));
-                bool lv = valid;
-                if (lv && A.r >= 0 && grid_conflict(grid, A.gw, A.gh, A.cs, A.r, x, y)) lv = false;
-                const unsigned int live_mask = __ballot_sync(0xffffffffu, lv);
-                if (live_mask == 0u) continue;
-                // earlier live lanes of the batch within distance r of this one
-                unsigned int confl = 0u;
-                if (A.r >= 0) {
-                    for (unsigned int mm = live_mask; mm; mm &= mm - 1u) {
-                        const int j = __ffs(mm) - 1;
-                        const int xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j);
-                        if (j < lane && abs(x - xj) <= A.r && abs(y - yj) <= A.r) confl |= 1u << j;
+    const int slots = s_slots;
+    const unsigned int target = slots ? S.target_mul * (unsigned int)slots + S.target_add : 0u;
+    unsigned long long consumed = 0ull;
+    unsigned int fallbacks = 0;
+    unsigned int rb_lo = 0, rb_hi, nkeys;
+    if (presorted) { rb_hi = 0; nkeys = S.plan[(size_t)b * SEL_PLAN_WORDS + SEL_PLAN_NKEYS]; }
+    else { rb_hi = S.plan[(size_t)b * SEL_PLAN_WORDS + SEL_PLAN_RB_HI]; nkeys = S.plan[(size_t)b * SEL_PLAN_WORDS + SEL_PLAN_NKEYS]; }
+    if (!s_full && rb_hi != 0xFFFFFFFFu) {
+        if (!presorted)
+            for (int k = tid; k <= SEL_BINS; k += WALK_THREADS) pre[k] = offs_planned[k];
+        for (;;) {                                       // candidate ranges: the planned one, then fallbacks
+            __syncthreads();
+            unsigned int rb = rb_lo;
+            while (rb <= rb_hi && !s_full) {
+                if (tid == 0) {
+                    unsigned int m, e, big = 0;
+                    if (presorted) { m = nkeys; e = rb_hi + 1; big = 1; }
+                    else {
+                        // the longest run of bins [rb, e) that fits a chunk: binary search in the prefix counts
+                        const unsigned int p0 = pre[rb];
+                        unsigned int lo = rb, hi = rb_hi + 1;             // pre[lo] - p0 <= ch always holds
+                        while (lo < hi) {
+                            const unsigned int mid = (lo + hi + 1) >> 1;
+                            if (pre[mid] - p0 <= (unsigned int)S.ch) lo = mid; else hi = mid - 1;
+                        }
+                        e = lo; m = pre[e] - p0;
+                        if (e == rb) { e = rb + 1; m = pre[e] - p0; big = 1; }      // one bin larger than a chunk
+                    }
+                    s_m = m; s_e = e; s_big = big;
+                }
+                __syncthreads();
+                const unsigned int pos = presorted ? 0u : pre[rb];
+                const unsigned int m = s_m, e = s_e, big = s_big;
+                if (big && !presorted && m > 1) block_radix_sort(keys + pos, keys2 + pos, m, warp_cnt);
+                for (unsigned int piece = 0; piece < m && !s_full; piece += S.ch) {
+                    const int mm = (int)min((unsigned int)S.ch, m - piece);
+                    // ---- phase 1: drop what the features accepted so far suppress; ordered compaction of the rest ----
+                    if (tid == 0) s_ns = 0;
+                    __syncthreads();
+                    for (int i0 = 0; i0 < mm; i0 += WALK_THREADS) {
+                        const int i = i0 + tid;
+                        bool live = i < mm;
+                        unsigned long long kk = 0ull;
+                        if (live) {
+                            kk = keys[pos + piece + i];
+                            const unsigned long long k = ~kk;
+                            const int x = (int)((k >> 13) & 8191ull), y = (int)(k & 8191ull);
+                            if (pm_walk && pm_walk[(size_t)y * S.W + x]) live = false;      // only a caller-ordered list can still hold these (:109-116)
+                            if (live && S.r >= 0 && grid_conflict(grid, S.gw, S.gh, S.cs, S.r, x, y)) live = false;
+                        }
+                        const unsigned int bm = __ballot_sync(0xffffffffu, live);
+                        if (lane == 0) warp_cnt[warp] = __popc(bm);
+                        __syncthreads();
+                        const int base = s_ns;
+                        unsigned int before = 0, tot = 0;
+                        for (int w = 0; w < WALK_THREADS / 32; w++) { const unsigned int c = warp_cnt[w]; if (w < warp) before += c; tot += c; }
+                        if (live) sk[base + before + __popc(bm & ((1u << lane) - 1u))] = kk;
+                        __syncthreads();
+                        if (tid == 0) s_ns = base + (int)tot;
+                        __syncthreads();
+                    }
+                    const int ns = s_ns;
+                    if (!big && ns > 1) {
+                        int P = 2;
+                        while (P < ns) P <<= 1;
+                        for (int i = ns + tid; i < P; i += WALK_THREADS) sk[i] = ~0ull;
+                        __syncthreads();
+                        bitonic_sort(sk, P);
+                    }
+                    // ---- phase 2: warp 0 walks the survivors in rank order with exactly the result of the sequential loop:
+                    // re-test against the grid (features accepted earlier in this chunk), then resolve 32 candidates at once --
+                    // lane i is accepted iff no EARLIER accepted lane lies within distance r.  That recurrence is solved by
+                    // iteration: an undecided lane is rejected as soon as an accepted earlier lane conflicts with it and accepted
+                    // as soon as all its earlier conflicting lanes are rejected; the lowest undecided lane is decided in every
+                    // round.  Accepted lanes then fill their slots (the k-th accepted candidate takes the k-th fillable slot)
+                    // and register in the grid together.
+                    if (warp == 0) {
+                        int filled = s_filled;
+                        bool full = false;
+                        const unsigned int lt = (1u << lane) - 1u;
+                        for (int b0 = 0; b0 < ns && !full; b0 += 32) {
+                            const bool valid = b0 + lane < ns;
+                            const unsigned long long k = valid ? ~sk[b0 + lane] : 0ull;
+                            const int x = (int)((k >> 13) & 8191ull), y = (int)(k & 8191ull);
+                            const float val = __uint_as_float((unsigned int)(k >> 26));
+                            bool lv = valid;
+                            if (lv && S.r >= 0 && grid_conflict(grid, S.gw, S.gh, S.cs, S.r, x, y)) lv = false;
+                            const unsigned int live_mask = __ballot_sync(0xffffffffu, lv);
+                            if (live_mask == 0u) continue;
+                            unsigned int confl = 0u;       // earlier live lanes of the batch within distance r of this one
+                            if (S.r >= 0) {
+                                for (unsigned int mmk = live_mask; mmk; mmk &= mmk - 1u) {
+                                    const int j = __ffs(mmk) - 1;
+                                    const int xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j);
+                                    if (j < lane && abs(x - xj) <= S.r && abs(y - yj) <= S.r) confl |= 1u << j;
+                                }
+                            }
+                            unsigned int acc = 0u, rej = 0u, undecided = live_mask;
+                            while (undecided) {
+                                const bool mine = (undecided >> lane) & 1u;
+                                const bool r_now = mine && (confl & acc) != 0u;
+                                const bool a_now = mine && !r_now && (confl & ~rej) == 0u;
+                                const unsigned int na = __ballot_sync(0xffffffffu, a_now), nr = __ballot_sync(0xffffffffu, r_now);
+                                acc |= na; rej |= nr; undecided &= ~(na | nr);
+                            }
+                            const int nacc = __popc(acc), room = slots - filled;
+                            const int take = nacc < room ? nacc : room;
+                            const int rank = __popc(acc & lt);
+                            const bool store = ((acc >> lane) & 1u) && rank < take;
+                            __syncwarp();                 // every lane has finished reading the grid before anyone registers in it
+                            if (store) {
+                                const int slot = overwrite ? filled + rank : free_slots[filled + rank];
+                                fx[slot] = (double)x; fy[slot] = (double)y; fval[slot] = (int)val;
+                                if (S.r >= 0) {
+                                    const int cx = x / S.cs, cy = y / S.cs;
+                                    grid[cy * S.gw + cx] = (unsigned short)(((x - cx * S.cs) << 8) | (y - cy * S.cs));
+                                }
+                            }
+                            filled += take;
+                            if (filled >= slots) full = true;
+                            __syncwarp();
+                        }
+                        if (lane == 0) { s_filled = filled; if (full) s_full = 1; }
+                    }
+                    __syncthreads();
+                    consumed += (unsigned long long)mm;
+                }
+                rb = e;
+                __syncthreads();                          // pre[] / s_m are read above; thread 0 rewrites s_m next
+            }
+            if (s_full || presorted || rb_hi >= SEL_BINS - 1) break;
+            // ---- fallback: the range ran out before every slot was filled: gather the next bins from the eigenvalue map ----
+            fallbacks++;
+            rb_lo = rb_hi + 1;
+            plan_range(hist, rb_lo, target, pre, off, warp_cnt, &s_rb_hi, &s_nkeys);
+            rb_hi = s_rb_hi; nkeys = s_nkeys;
+            if (nkeys == 0) break;                       // nothing left above min_eigenvalue
+            const float *vmap = S.vmap + (size_t)b * S.ncand;
+            const unsigned char *pm = S.premap ? S.premap + (size_t)b * S.map_stride : nullptr;
+            for (size_t c = tid; c < S.ncand; c += WALK_THREADS) {
+                const float v = vmap[c];
+                if (v >= S.min_val) {
+                    const unsigned int rbk = (unsigned int)eig_rbin(v);
+                    if (rbk >= rb_lo && rbk <= rb_hi) {
+                        const int j = (int)(c / S.nx), i = (int)(c - (size_t)j * S.nx);
+                        const int x = S.bx + i * S.step, y = S.by + j * S.step;
+                        if (!(pm && pm[(size_t)y * S.W + x])) keys[atomicAdd(&off[rbk], 1u)] = make_key(v, x, y);
                     }
                 }
-                unsigned int acc = 0u, rej = 0u, undecided = live_mask;
-                while (undecided) {
-                    const bool mine = (undecided >> lane) & 1u;
-                    const bool r_now = mine && (confl & acc) != 0u;
-                    const bool a_now = mine && !r_now && (confl & ~rej) == 0u;      // (confl & ~rej) has no accepted bit here
-                    const unsigned int na = __ballot_sync(0xffffffffu, a_now), nr = __ballot_sync(0xffffffffu, r_now);
-                    acc |= na; rej |= nr; undecided &= ~(na | nr);
-                }
-                // the k-th accepted candidate takes the k-th fillable slot; stop where the slots run out
-                const int nacc = __popc(acc), room = slots - filled;
-                const int take = nacc < room ? nacc : room;
-                const int rank = __popc(acc & lt);
-                const bool store = ((acc >> lane) & 1u) && rank < take;
-                __syncwarp();                     // every lane has finished reading the grid before anyone registers in it
-                if (store) {
-                    const int slot = A.overwrite ? filled + rank : A.free_slots[filled + rank];
-                    A.fx[slot] = (double)x; A.fy[slot] = (double)y; A.fval[slot] = (int)val;
-                    if (A.r >= 0) {
-                        const int cx = x / A.cs, cy = y / A.cs;
-                        grid[cy * A.gw + cx] = (unsigned short)(((x - cx * A.cs) << 8) | (y - cy * A.cs));
-                    }
-                }
-                const unsigned int stored = __ballot_sync(0xffffffffu, store);
-                last_off = __shfl_sync(0xffffffffu, off, 31 - __clz(stored));     // the last candidate that was accepted
-                filled += take;
-                if (filled >= slots) full = true;
-                __syncwarp();
             }
-            if (lane == 0) {
-                s_filled = filled;
-                if (full) {
-                    // the reference reads one more candidate before noticing that every slot is taken (:96-112)
-                    unsigned long long c = base + last_off + 1;
-                    if (c < n) c += 1;
-                    s_consumed = c; s_full = 1;
-                } else {
-                    s_consumed = base + GREEDY_THREADS < n ? base + GREEDY_THREADS : (unsigned long long)n;
-                }
-            }
+            __syncthreads();
         }
-        __syncthreads();
     }
+    __syncthreads();
+    // SELECTING_ALL: slots the walk could not fill get x = y = -1, val = KLT_NOT_FOUND (C-KLT behaviour, quirk Q6)
+    if (overwrite)
+        for (int f = s_filled + tid; f < n_features; f += WALK_THREADS) { fx[f] = -1.0; fy[f] = -1.0; fval[f] = KLT_NOT_FOUND; }
     if (tid == 0) {
-        A.consumed[0] = s_consumed;
-        A.consumed[1] = s_full ? 0ull : 1ull;
-        A.consumed[2] = (unsigned long long)s_filled;      // SELECTING_ALL: also the first unfilled slot
+        status[0] = consumed;
+        status[1] = s_full ? 0ull : 1ull;
+        status[2] = (unsigned long long)s_filled;
+        status[3] = (unsigned long long)fallbacks;
     }
-}
-
-// fills the slots the walk could not fill (SELECTING_ALL only): x = y = -1, val = KLT_NOT_FOUND (C-KLT behaviour, quirk Q6)
-__global__ void fill_not_found_kernel(double *fx, double *fy, int *fval, int n, const unsigned long long *consumed) {
-    const int f = (int)consumed[2] + blockIdx.x * blockDim.x + threadIdx.x;
-    if (f < n) { fx[f] = -1.0; fy[f] = -1.0; fval[f] = KLT_NOT_FOUND; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static int launch_sat(klt_ctx *ctx, const float *gx, const float *gy, size_t pitch, int w, int h, float *sxx, float *sxy, float *syy) {
-    const bool vec = (w % SAT_T) == 0 && (pitch % 4) == 0 && ((reinterpret_cast<uintptr_t>(gx) | reinterpret_cast<uintptr_t>(gy)) & 15) == 0;
-    if (vec) {
-        KLT_CUDA(ctx, cudaFuncSetAttribute(sat_rows_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SatSmemV)));
-        KLT_LAUNCH(ctx, "sat_rows", 20.0 * w * h, (sat_rows_vec_kernel<<<(h + SAT_T - 1) / SAT_T, 32, sizeof(SatSmemV), ctx->stream>>>(gx, gy, pitch, w, h, sxx, sxy, syy)));
-    } else
-    KLT_LAUNCH(ctx, "sat_rows", 20.0 * w * h, (sat_rows_kernel<<<(h + SAT_T - 1) / SAT_T, 32, 0, ctx->stream>>>(gx, gy, pitch, w, h, sxx, sxy, syy)));
-    KLT_LAUNCH(ctx, "sat_cols", 24.0 * w * h, (sat_cols_kernel<<<dim3((w + 63) / 64, 3), 64, 0, ctx->stream>>>(sxx, sxy, syy, w, h)));
-    return KLT_OK;
-}
-
-int klt_launch_scan(klt_ctx *ctx, const float *gx, const float *gy, size_t pitch, int w, int h, int bx, int by, int hw,
-                    int hh, int skip, float *val_dev, int nx, int ny) {
-    const size_t plane = align_up((size_t)w * h * sizeof(float), 256);
-    int rc = klt_ws_reserve(ctx, 3 * plane);
-    if (rc) return rc;
-    float *sxx = (float *)ctx->ws, *sxy = (float *)((char *)ctx->ws + plane), *syy = (float *)((char *)ctx->ws + 2 * plane);
-    if ((rc = launch_sat(ctx, gx, gy, pitch, w, h, sxx, sxy, syy))) return rc;
-    if (nx > 0 && ny > 0)
-        KLT_LAUNCH(ctx, "eigen", 52.0 * nx * ny, (eigen_kernel<<<dim3((nx + 255) / 256, (ny + EIG_ROWS - 1) / EIG_ROWS), 256, 0, ctx->stream>>>(
-                                                      sxx, sxy, syy, w, bx, by, hw, hh, skip + 1, nx, ny, val_dev, nullptr, 0.f)));
-    return KLT_OK;
-}
-
-int klt_select_device(klt_ctx *ctx, const klt_params *p, const float *gx, const float *gy, size_t pitch, int w, int h,
-                      int n_features, int replace, double *x, double *y, int32_t *val, int64_t *n_consumed) {
+int klt_sel_geometry(klt_ctx *ctx, const klt_params *p, int w, int h, int n_features, int replace, SelDev *S) {
     if (w > 8191 || h > 8191) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "image larger than 8191 pixels per side");
     // border and window exactly as selectGoodFeatures.py:168-169,215-221,230 (true division, then int truncation)
     double window_hw = p->window_width / 2.0, window_hh = p->window_height / 2.0;
@@ -636,108 +702,217 @@ int klt_select_device(klt_ctx *ctx, const klt_params *p, const float *gx, const 
     int nx = 0, ny = 0;
     if (w - bx > bx) nx = (w - 2 * bx + step - 1) / step;
     if (h - by > by) ny = (h - 2 * by + step - 1) / step;
-    const size_t ncand = (size_t)nx * ny;
     const int mindist = p->mindist < 0 ? 0 : p->mindist;                 // :241-243
-    const int min_eig = p->min_eigenvalue < 1 ? 1 : p->min_eigenvalue;   // :53
     const int r = mindist - 1;                                           // :61
     if (r > 254) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "mindist larger than 255");
+    memset(S, 0, sizeof *S);
+    S->W = w; S->H = h; S->bx = bx; S->by = by; S->hw = hw; S->hh = hh; S->step = step; S->nx = nx; S->ny = ny;
+    S->r = r; S->cs = r >= 0 ? r + 1 : 1; S->gw = (w + S->cs - 1) / S->cs; S->gh = (h + S->cs - 1) / S->cs;
+    S->n_features = n_features; S->replace = replace ? 1 : 0;
+    // :53 (min_eigenvalue < 1 -> 1) and :116 (val >= min_eigenvalue, a float/int comparison in the reference)
+    S->min_val = p->min_eigenvalue < 1 ? 1.0f : (float)p->min_eigenvalue;
+    S->ncand = (size_t)nx * ny;
+    S->key_stride = align_up(S->ncand + 1, 32);
+    S->map_stride = align_up((size_t)w * h, 256);
+    S->grid_stride = align_up((size_t)S->gw * S->gh, 128);
+    S->ch = ctx->select_chunk;
+    // replacement mode only sees the candidates no surviving feature suppresses: a smaller first range suffices
+    S->target_mul = replace ? 128u : 32u;
+    S->target_add = replace ? 1024u : 8192u;
+    const size_t grid_b = (size_t)S->gw * S->gh * sizeof(unsigned short);
+    const size_t fixed = (size_t)S->ch * sizeof(unsigned long long) + (2 * SEL_BINS + 4) * sizeof(unsigned int);
+    S->grid_in_smem = fixed + grid_b + 2048 <= 200 * 1024 ? 1 : 0;
+    return KLT_OK;
+}
 
+size_t klt_sel_workspace_bytes(const SelDev *S, int B, bool strict_sat, bool own_features) {
+    size_t t = 0;
+    if (strict_sat) t += align_up((size_t)B * 3 * S->W * S->H * sizeof(float), 256);
+    t += align_up((size_t)B * (S->ncand + 1) * sizeof(float), 256);              // vmap
+    t += align_up((size_t)B * (SEL_BINS * 3 + 1) * sizeof(unsigned int), 256);   // hist, cursor, offs
+    t += align_up((size_t)B * (SEL_PLAN_WORDS * sizeof(unsigned int) + SEL_STATUS_WORDS * sizeof(unsigned long long)), 256);
+    t += 2 * align_up((size_t)B * S->key_stride * sizeof(unsigned long long), 256);
+    if (S->replace) t += align_up((size_t)B * S->map_stride, 256);
+    if (!S->grid_in_smem) t += align_up((size_t)B * S->grid_stride * sizeof(unsigned short), 256);
+    t += align_up((size_t)B * S->n_features * sizeof(int) + 64, 256);            // free slots
+    if (own_features) t += align_up((size_t)B * S->n_features * (2 * sizeof(double) + sizeof(int)) + 64, 256);
+    return t + 1024;
+}
+
+void klt_sel_carve(SelDev *S, int B, bool strict_sat, bool own_features, char *base, float **sat) {
+    char *p = base;
+    auto take = [&](size_t bytes) { char *q = p; p += align_up(bytes, 256); return q; };
+    if (sat) *sat = nullptr;
+    if (strict_sat) { float *s = (float *)take((size_t)B * 3 * S->W * S->H * sizeof(float)); if (sat) *sat = s; }
+    S->vmap = (float *)take((size_t)B * (S->ncand + 1) * sizeof(float));
+    unsigned int *h3 = (unsigned int *)take((size_t)B * (SEL_BINS * 3 + 1) * sizeof(unsigned int));
+    S->hist = h3; S->cursor = h3 + (size_t)B * SEL_BINS; S->offs = h3 + (size_t)2 * B * SEL_BINS;      // offs: [B][SEL_BINS + 1]
+    char *ps = take((size_t)B * (SEL_PLAN_WORDS * sizeof(unsigned int) + SEL_STATUS_WORDS * sizeof(unsigned long long)));
+    S->status = (unsigned long long *)ps; S->plan = (unsigned int *)(ps + (size_t)B * SEL_STATUS_WORDS * sizeof(unsigned long long));
+    S->keys = (unsigned long long *)take((size_t)B * S->key_stride * sizeof(unsigned long long));
+    S->keys2 = (unsigned long long *)take((size_t)B * S->key_stride * sizeof(unsigned long long));
+    S->premap = S->replace ? (unsigned char *)take((size_t)B * S->map_stride) : nullptr;
+    S->grid_global = S->grid_in_smem ? nullptr : (unsigned short *)take((size_t)B * S->grid_stride * sizeof(unsigned short));
+    S->free_slots = (int *)take((size_t)B * S->n_features * sizeof(int) + 64);
+    if (own_features) {
+        char *f = take((size_t)B * S->n_features * (2 * sizeof(double) + sizeof(int)) + 64);
+        S->fx = (double *)f; S->fy = S->fx + (size_t)B * S->n_features; S->fval = (int *)(S->fy + (size_t)B * S->n_features);
+    }
+}
+
+static size_t walk_smem(const SelDev *S) {
+    size_t s = (size_t)S->ch * sizeof(unsigned long long) + (2 * SEL_BINS + 4) * sizeof(unsigned int);
+    if (S->grid_in_smem) s += (size_t)S->gw * S->gh * sizeof(unsigned short);
+    return s;
+}
+
+int klt_sel_prepare_kernels(klt_ctx *ctx, const SelDev *S) {
+    // function attributes are set outside any stream capture
+    KLT_CUDA(ctx, cudaFuncSetAttribute(sat_rows_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SatSmemV)));
+    KLT_CUDA(ctx, cudaFuncSetAttribute(select_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem(S)));
+    return KLT_OK;
+}
+
+// histogram reset + (replacement mode) pre-marking of the surviving features; must precede the eigen pass
+int klt_sel_launch_begin(klt_ctx *ctx, const SelDev *S, int B) {
+    KLT_CUDA(ctx, cudaMemsetAsync(S->hist, 0, (size_t)B * SEL_BINS * sizeof(unsigned int), ctx->stream));
+    if (S->replace) {
+        KLT_CUDA(ctx, cudaMemsetAsync(S->premap, 0, (size_t)B * S->map_stride, ctx->stream));
+        if (S->r >= 0 && S->n_features > 0)
+            KLT_LAUNCH(ctx, "premark", (double)B * S->map_stride, (premark_kernel<<<dim3(S->n_features, B), 128, 0, ctx->stream>>>(*S)));
+    }
+    return KLT_OK;
+}
+
+// STRICT eigenvalue map (+ histogram) of B images from their level-0 gradient planes
+int klt_sel_launch_eigen_strict(klt_ctx *ctx, const SelDev *S, int B, const float *gx0, const float *gy0, size_t img_stride,
+                                size_t pitch, float *sat, bool with_hist) {
+    const int w = S->W, h = S->H;
+    const size_t plane = (size_t)w * h;
+    const bool vec = (w % SAT_T) == 0 && (pitch % 4) == 0 && (img_stride % 4) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(gx0) | reinterpret_cast<uintptr_t>(gy0)) & 15) == 0;
+    const dim3 grid((h + SAT_T - 1) / SAT_T, B);
+    if (vec)
+        KLT_LAUNCH(ctx, "sat_rows", 20.0 * plane * B, (sat_rows_vec_kernel<<<grid, 32, sizeof(SatSmemV), ctx->stream>>>(gx0, gy0, img_stride, pitch, w, h, sat, plane)));
+    else
+        KLT_LAUNCH(ctx, "sat_rows", 20.0 * plane * B, (sat_rows_kernel<<<grid, 32, 0, ctx->stream>>>(gx0, gy0, img_stride, pitch, w, h, sat, plane)));
+    KLT_LAUNCH(ctx, "sat_cols", 24.0 * plane * B, (sat_cols_kernel<<<dim3((w + 63) / 64, 3, B), 64, 0, ctx->stream>>>(sat, plane, w, h)));
+    if (S->ncand) {
+        const dim3 g2((S->nx + 255) / 256, (S->ny + EIG_ROWS - 1) / EIG_ROWS, B);
+        const double bytes = (12.0 * plane + 4.0 * S->ncand) * B;
+        if (with_hist) KLT_LAUNCH(ctx, "eigen", bytes, (eigen_kernel<true><<<g2, 256, 0, ctx->stream>>>(sat, plane, *S)));
+        else KLT_LAUNCH(ctx, "eigen", bytes, (eigen_kernel<false><<<g2, 256, 0, ctx->stream>>>(sat, plane, *S)));
+    }
+    return KLT_OK;
+}
+
+// plan + scatter + walk on the eigenvalue maps and histograms of B images
+int klt_sel_launch_pick(klt_ctx *ctx, const SelDev *S, int B) {
+    KLT_LAUNCH(ctx, "select_plan", 0.0, (select_plan_kernel<<<B, WALK_THREADS, 0, ctx->stream>>>(*S)));
+    if (S->ncand)
+        KLT_LAUNCH(ctx, "select_scatter", 4.0 * S->ncand * B, (select_scatter_kernel<<<dim3((S->nx + 255) / 256, (S->ny + SCAT_ROWS - 1) / SCAT_ROWS, B), 256, 0, ctx->stream>>>(*S)));
+    KLT_LAUNCH(ctx, "select_walk", 0.0, (select_walk_kernel<<<B, WALK_THREADS, walk_smem(S), ctx->stream>>>(*S, 0)));
+    return KLT_OK;
+}
+
+int klt_launch_scan(klt_ctx *ctx, const float *gx, const float *gy, size_t pitch, int w, int h, int bx, int by, int hw,
+                    int hh, int skip, float *val_dev, int nx, int ny) {
+    SelDev S;
+    memset(&S, 0, sizeof S);
+    S.W = w; S.H = h; S.bx = bx; S.by = by; S.hw = hw; S.hh = hh; S.step = skip + 1; S.nx = nx; S.ny = ny;
+    S.ncand = (size_t)nx * ny; S.vmap = val_dev; S.min_val = 1.f;
     const size_t plane = align_up((size_t)w * h * sizeof(float), 256);
-    const size_t val_b = align_up((ncand + 1) * sizeof(float), 256);
-    const size_t keys_b = align_up((ncand + 1) * sizeof(unsigned long long), 256);
-    const int max_blocks = (int)((ncand + RS_CHUNK - 1) / RS_CHUNK) + 1;
-    const size_t hist_b = align_up((size_t)256 * max_blocks * sizeof(unsigned int), 256);
-    const size_t map_b = align_up((size_t)w * h, 256);
-    const size_t feat_b = align_up((size_t)n_features * (2 * sizeof(double) + 2 * sizeof(int)) + 64, 256);
-    const int cs = r >= 0 ? r + 1 : 1, gw = (w + cs - 1) / cs, gh = (h + cs - 1) / cs;
-    const size_t grid_b = align_up((size_t)gw * gh * sizeof(unsigned short), 256);
-    const bool grid_in_smem = grid_b <= 180 * 1024;
-    const size_t total = 3 * plane + val_b + 2 * keys_b + hist_b + map_b + feat_b + grid_b + EIG_BINS * 4 + 512;
-    int rc = klt_ws_reserve(ctx, total);
+    int rc = klt_ws_reserve(ctx, 3 * plane);
     if (rc) return rc;
-    char *wsp = (char *)ctx->ws;
-    float *sxx = (float *)wsp; wsp += plane;
-    float *sxy = (float *)wsp; wsp += plane;
-    float *syy = (float *)wsp; wsp += plane;
-    float *vmap = (float *)wsp; wsp += val_b;
-    unsigned long long *keys0 = (unsigned long long *)wsp; wsp += keys_b;
-    unsigned long long *keys1 = (unsigned long long *)wsp; wsp += keys_b;
-    unsigned int *hist = (unsigned int *)wsp; wsp += hist_b;
-    unsigned char *map = (unsigned char *)wsp; wsp += map_b;
-    double *fx = (double *)wsp; double *fy = fx + n_features; int *fval = (int *)(fy + n_features); wsp += feat_b;
-    unsigned short *grid_g = (unsigned short *)wsp; wsp += grid_b;
-    unsigned int *ehist = (unsigned int *)wsp; wsp += EIG_BINS * 4;
-    unsigned int *nkeys = (unsigned int *)wsp;                       // [0] key count, [1] threshold bin
-    unsigned long long *consumed = (unsigned long long *)(wsp + 64); // [0] consumed, [1] ran out, [2] next slot
+    if ((rc = klt_sel_prepare_kernels_scan(ctx, &S))) return rc;
+    return klt_sel_launch_eigen_strict(ctx, &S, 1, gx, gy, 0, pitch, (float *)ctx->ws, false);
+}
 
-    KLT_CUDA(ctx, cudaMemsetAsync(ehist, 0, EIG_BINS * 4 + 512, ctx->stream));
-    if (replace) {
-        KLT_CUDA(ctx, cudaMemcpyAsync(fx, x, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
-        KLT_CUDA(ctx, cudaMemcpyAsync(fy, y, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
-        KLT_CUDA(ctx, cudaMemcpyAsync(fval, val, n_features * sizeof(int), cudaMemcpyDefault, ctx->stream));
-        KLT_CUDA(ctx, cudaMemsetAsync(map, 0, (size_t)w * h, ctx->stream));
-        if (r >= 0 && n_features > 0)
-            KLT_LAUNCH(ctx, "premark", 0.0, (premark_kernel<<<n_features, 128, 0, ctx->stream>>>(fx, fy, fval, n_features, map, w, h, r)));
+int klt_sel_prepare_kernels_scan(klt_ctx *ctx, const SelDev *S) {
+    (void)S;
+    KLT_CUDA(ctx, cudaFuncSetAttribute(sat_rows_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SatSmemV)));
+    return KLT_OK;
+}
+
+// Full selection for B images with host or device feature arrays [B][n_features]; synchronises only to hand host arrays back.
+// Source: the level-0 planes of `pyr` (all its images), or explicit device gradient images (pyr == NULL, B images img_stride apart).
+int klt_select_batch(klt_ctx *ctx, const klt_params *p, int select_mode, klt_pyr *pyr, const float *gx0, const float *gy0,
+                     size_t img_stride, size_t pitch, int w, int h, int B, int n_features, int replace, double *x, double *y,
+                     int32_t *val, int64_t *n_consumed) {
+    SelDev S;
+    int rc = klt_sel_geometry(ctx, p, w, h, n_features, replace, &S);
+    if (rc) return rc;
+    const bool host = !klt_is_device_ptr(x);
+    if (host != !klt_is_device_ptr(y) || host != !klt_is_device_ptr(val)) return klt_fail(ctx, KLT_ERR_INVALID, "x, y, val must all be host or all be device");
+    const bool try_fast = select_mode == KLT_SELECT_FAST && pyr && pyr->hx && pyr->hx->taps_valid;
+    if ((rc = klt_ws_reserve(ctx, klt_sel_workspace_bytes(&S, B, true, host)))) return rc;
+    float *sat;
+    klt_sel_carve(&S, B, true, host, (char *)ctx->ws, &sat);
+    const size_t total = (size_t)B * n_features;
+    if (host) {
+        if (replace) {
+            KLT_CUDA(ctx, cudaMemcpyAsync(S.fx, x, total * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            KLT_CUDA(ctx, cudaMemcpyAsync(S.fy, y, total * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            KLT_CUDA(ctx, cudaMemcpyAsync(S.fval, val, total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        }
+    } else { S.fx = x; S.fy = y; S.fval = val; }
+    if ((rc = klt_sel_prepare_kernels(ctx, &S))) return rc;
+    if ((rc = klt_sel_launch_begin(ctx, &S, B))) return rc;
+    int done = 0;
+    if (try_fast) {
+        done = klt_sel_launch_eigen_fast(ctx, &S, B, pyr->level(0, 0, 0), pyr->plane_floats, pyr->lv[0].pitch, &pyr->hx->taps.grad_gauss,
+                                         &pyr->hx->taps.grad_deriv);
+        if (done < 0) return done;
     }
-    if ((rc = launch_sat(ctx, gx, gy, pitch, w, h, sxx, sxy, syy))) return rc;
-    if (ncand)
-        KLT_LAUNCH(ctx, "eigen", 52.0 * ncand, (eigen_kernel<<<dim3((nx + 255) / 256, (ny + EIG_ROWS - 1) / EIG_ROWS), 256, 0, ctx->stream>>>(
-                                                    sxx, sxy, syy, w, bx, by, hw, hh, step, nx, ny, vmap, ehist, (float)min_eig)));
-    GreedyArgs G;
-    G.nkeys = nkeys; G.premap = replace ? map : nullptr; G.grid_global = grid_g; G.W = w; G.H = h; G.r = r;
-    G.n_features = n_features; G.overwrite = replace ? 0 : 1; G.cs = cs; G.gw = gw; G.gh = gh; G.grid_in_smem = grid_in_smem ? 1 : 0;
-    G.fx = fx; G.fy = fy; G.fval = fval; G.free_slots = fval + n_features; G.consumed = consumed;
-    if (grid_in_smem) KLT_CUDA(ctx, cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_b));
-    unsigned long long cons[3] = {0, 0, 0};
-    const unsigned int target = (unsigned int)(32u * (unsigned int)n_features + 8192u);
-    for (int attempt = 0; attempt < 2; attempt++) {
-        // attempt 0: only the best ~target candidates; attempt 1 (rare): every candidate >= min_eigenvalue
-        unsigned int hk[2] = {0, 0};
-        if (ncand) {
-            KLT_CUDA(ctx, cudaMemsetAsync(nkeys, 0, 8, ctx->stream));
-            KLT_LAUNCH(ctx, "threshold", 0.0, (threshold_kernel<<<1, 32, 0, ctx->stream>>>(ehist, target, attempt, nkeys + 1)));
-            KLT_LAUNCH(ctx, "compact", 4.0 * ncand, (compact_kernel<<<dim3((nx + 255) / 256, ny), 256, 0, ctx->stream>>>(
-                                                        vmap, bx, by, step, nx, ny, (float)min_eig, nkeys + 1, keys0, nkeys)));
-            KLT_CUDA(ctx, cudaMemcpyAsync(hk, nkeys, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));        // the sort's launch geometry follows the key count
+    if (!done) {
+        if (pyr) {
+            if ((rc = klt_ensure_gradients_level0(ctx, pyr))) return rc;      // image-only pyramids: build level 0's planes now
+            gx0 = pyr->level(1, 0, 0); gy0 = pyr->level(2, 0, 0); img_stride = pyr->plane_floats; pitch = pyr->lv[0].pitch;
         }
-        const unsigned int nk = hk[0];
-        const int nblocks = (int)((nk + RS_CHUNK - 1) / RS_CHUNK);
-        unsigned long long *src = keys0, *dst = keys1;
-        if (nblocks > 0) {
-            // 58 significant key bits -> 8 passes of 8 bits
-            for (int pass = 0; pass < 8; pass++) {
-                KLT_LAUNCH(ctx, "rs_hist", 8.0 * nk, (rs_hist_kernel<<<nblocks, RS_THREADS, 0, ctx->stream>>>(src, nkeys, pass * 8, hist, nblocks)));
-                if (nblocks <= RS_FUSED_SCAN_BLOCKS) {
-                    KLT_LAUNCH(ctx, "rs_scatter", 16.0 * nk, (rs_scatter_kernel<false><<<nblocks, RS_THREADS, 0, ctx->stream>>>(src, dst, nkeys, pass * 8, hist, nblocks)));
-                } else {
-                    KLT_LAUNCH(ctx, "rs_scan", 0.0, (rs_scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, 256 * nblocks)));
-                    KLT_LAUNCH(ctx, "rs_scatter", 16.0 * nk, (rs_scatter_kernel<true><<<nblocks, RS_THREADS, 0, ctx->stream>>>(src, dst, nkeys, pass * 8, hist, nblocks)));
-                }
-                unsigned long long *t = src; src = dst; dst = t;
-            }
-        }
-        if (replace && attempt == 1) {      // the first walk may have filled slots: start again from the caller's list
-            KLT_CUDA(ctx, cudaMemcpyAsync(fval, val, n_features * sizeof(int), cudaMemcpyDefault, ctx->stream));
-            KLT_CUDA(ctx, cudaMemcpyAsync(fx, x, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
-            KLT_CUDA(ctx, cudaMemcpyAsync(fy, y, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
-        }
-        G.keys = src;
-        KLT_LAUNCH(ctx, "greedy", 0.0, (greedy_kernel<<<1, GREEDY_THREADS, grid_in_smem ? grid_b : 0, ctx->stream>>>(G)));
-        KLT_CUDA(ctx, cudaMemcpyAsync(cons, consumed, sizeof(cons), cudaMemcpyDeviceToHost, ctx->stream));
+        if ((rc = klt_sel_launch_eigen_strict(ctx, &S, B, gx0, gy0, img_stride, pitch, sat, true))) return rc;
+    }
+    if ((rc = klt_sel_launch_pick(ctx, &S, B))) return rc;
+    if (host) {
+        KLT_CUDA(ctx, cudaMemcpyAsync(x, S.fx, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        KLT_CUDA(ctx, cudaMemcpyAsync(y, S.fy, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        KLT_CUDA(ctx, cudaMemcpyAsync(val, S.fval, total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (host || n_consumed) {
+        unsigned long long st[SEL_STATUS_WORDS] = {0, 0, 0, 0};
+        KLT_CUDA(ctx, cudaMemcpyAsync(st, S.status, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
         KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        const bool thresholded = hk[1] > 0;
-        if (!(cons[1] && thresholded)) break;   // all slots filled, or nothing was excluded: this IS the greedy result
+        if (n_consumed) *n_consumed = (int64_t)st[0];
     }
-    if (!replace && cons[1] && (int)cons[2] < n_features) {
-        const int rest = n_features - (int)cons[2];
-        KLT_LAUNCH(ctx, "fill_not_found", 0.0, (fill_not_found_kernel<<<(rest + 127) / 128, 128, 0, ctx->stream>>>(fx, fy, fval, n_features, consumed)));
+    return KLT_OK;
+}
+
+// eigenvalue maps of every image of a pyramid batch by either method (diagnostics and tests): val [B][ny][nx], host or device
+int klt_eigen_maps(klt_ctx *ctx, const klt_params *p, int select_mode, klt_pyr *pyr, float *val, int *nx_out, int *ny_out) {
+    SelDev S;
+    int rc = klt_sel_geometry(ctx, p, pyr->w, pyr->h, 1, 0, &S);
+    if (rc) return rc;
+    const int B = pyr->batch;
+    if (nx_out) *nx_out = S.nx;
+    if (ny_out) *ny_out = S.ny;
+    if (!val || !S.ncand) return KLT_OK;
+    if ((rc = klt_ws_reserve(ctx, klt_sel_workspace_bytes(&S, B, true, false)))) return rc;
+    float *sat;
+    klt_sel_carve(&S, B, true, false, (char *)ctx->ws, &sat);
+    if ((rc = klt_sel_prepare_kernels(ctx, &S))) return rc;
+    if ((rc = klt_sel_launch_begin(ctx, &S, B))) return rc;
+    int done = 0;
+    if (select_mode == KLT_SELECT_FAST && pyr->hx && pyr->hx->taps_valid) {
+        done = klt_sel_launch_eigen_fast(ctx, &S, B, pyr->level(0, 0, 0), pyr->plane_floats, pyr->lv[0].pitch, &pyr->hx->taps.grad_gauss,
+                                         &pyr->hx->taps.grad_deriv);
+        if (done < 0) return done;
+        if (!done) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "the fused eigenvalue pass does not cover this window / gradient kernel");
     }
-    KLT_CUDA(ctx, cudaMemcpyAsync(x, fx, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
-    KLT_CUDA(ctx, cudaMemcpyAsync(y, fy, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
-    KLT_CUDA(ctx, cudaMemcpyAsync(val, fval, n_features * sizeof(int), cudaMemcpyDefault, ctx->stream));
+    if (!done) {
+        if ((rc = klt_ensure_gradients_level0(ctx, pyr))) return rc;
+        if ((rc = klt_sel_launch_eigen_strict(ctx, &S, B, pyr->level(1, 0, 0), pyr->level(2, 0, 0), pyr->plane_floats, pyr->lv[0].pitch, sat, true))) return rc;
+    }
+    KLT_CUDA(ctx, cudaMemcpyAsync(val, S.vmap, (size_t)B * S.ncand * sizeof(float), cudaMemcpyDefault, ctx->stream));
     KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (n_consumed) *n_consumed = (int64_t)cons[0];
     return KLT_OK;
 }
 
@@ -745,52 +920,30 @@ int klt_select_device(klt_ctx *ctx, const klt_params *p, const float *gx, const 
 // keys_host[i] = ~((val_bits << 26) | (x << 13) | y) in walk order.
 int klt_greedy_presorted(klt_ctx *ctx, const unsigned long long *keys_host, unsigned int nk, int w, int h, int mindist,
                          int n_features, int overwrite, double *x, double *y, int32_t *val) {
-    if (w > 8191 || h > 8191) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "image larger than 8191 pixels per side");
-    if (mindist < 0) mindist = 0;
-    const int r = mindist - 1;
-    if (r > 254) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "mindist larger than 255");
-    const size_t keys_b = align_up(((size_t)nk + 1) * sizeof(unsigned long long), 256);
-    const size_t map_b = align_up((size_t)w * h, 256);
-    const size_t feat_b = align_up((size_t)n_features * (2 * sizeof(double) + 2 * sizeof(int)) + 64, 256);
-    const int cs = r >= 0 ? r + 1 : 1, gw = (w + cs - 1) / cs, gh = (h + cs - 1) / cs;
-    const size_t grid_b = align_up((size_t)gw * gh * sizeof(unsigned short), 256);
-    const bool grid_in_smem = grid_b <= 180 * 1024;
-    int rc = klt_ws_reserve(ctx, keys_b + map_b + feat_b + grid_b + 512);
+    klt_params p;
+    memset(&p, 0, sizeof p);
+    p.window_width = p.window_height = 3; p.borderx = p.bordery = 2; p.mindist = mindist; p.min_eigenvalue = 1;
+    SelDev S;
+    int rc = klt_sel_geometry(ctx, &p, w, h, n_features, overwrite ? 0 : 1, &S);
     if (rc) return rc;
-    char *wsp = (char *)ctx->ws;
-    unsigned long long *keys = (unsigned long long *)wsp; wsp += keys_b;
-    unsigned char *map = (unsigned char *)wsp; wsp += map_b;
-    double *fx = (double *)wsp; double *fy = fx + n_features; int *fval = (int *)(fy + n_features); wsp += feat_b;
-    unsigned short *grid_g = (unsigned short *)wsp; wsp += grid_b;
-    unsigned int *nkeys = (unsigned int *)wsp;
-    unsigned long long *consumed = (unsigned long long *)(wsp + 64);
-    KLT_CUDA(ctx, cudaMemsetAsync(nkeys, 0, 512, ctx->stream));
-    KLT_CUDA(ctx, cudaMemcpyAsync(nkeys, &nk, sizeof(nk), cudaMemcpyHostToDevice, ctx->stream));
-    if (nk) KLT_CUDA(ctx, cudaMemcpyAsync(keys, keys_host, (size_t)nk * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    S.ncand = nk; S.key_stride = align_up((size_t)nk + 1, 32);        // the key buffer holds the caller's list
+    if ((rc = klt_ws_reserve(ctx, klt_sel_workspace_bytes(&S, 1, false, true)))) return rc;
+    klt_sel_carve(&S, 1, false, true, (char *)ctx->ws, nullptr);
+    unsigned int plan[SEL_PLAN_WORDS] = {0};
+    plan[SEL_PLAN_RB_HI] = 0; plan[SEL_PLAN_NKEYS] = nk;
+    KLT_CUDA(ctx, cudaMemcpyAsync(S.plan, plan, sizeof plan, cudaMemcpyHostToDevice, ctx->stream));
+    if (nk) KLT_CUDA(ctx, cudaMemcpyAsync(S.keys, keys_host, (size_t)nk * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
     if (!overwrite) {
-        KLT_CUDA(ctx, cudaMemcpyAsync(fx, x, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
-        KLT_CUDA(ctx, cudaMemcpyAsync(fy, y, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
-        KLT_CUDA(ctx, cudaMemcpyAsync(fval, val, n_features * sizeof(int), cudaMemcpyDefault, ctx->stream));
-        KLT_CUDA(ctx, cudaMemsetAsync(map, 0, (size_t)w * h, ctx->stream));
-        if (r >= 0 && n_features > 0)
-            KLT_LAUNCH(ctx, "premark", 0.0, (premark_kernel<<<n_features, 128, 0, ctx->stream>>>(fx, fy, fval, n_features, map, w, h, r)));
+        KLT_CUDA(ctx, cudaMemcpyAsync(S.fx, x, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
+        KLT_CUDA(ctx, cudaMemcpyAsync(S.fy, y, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
+        KLT_CUDA(ctx, cudaMemcpyAsync(S.fval, val, n_features * sizeof(int), cudaMemcpyDefault, ctx->stream));
     }
-    GreedyArgs G;
-    G.keys = keys; G.nkeys = nkeys; G.premap = overwrite ? nullptr : map; G.grid_global = grid_g; G.W = w; G.H = h; G.r = r;
-    G.n_features = n_features; G.overwrite = overwrite; G.cs = cs; G.gw = gw; G.gh = gh; G.grid_in_smem = grid_in_smem ? 1 : 0;
-    G.fx = fx; G.fy = fy; G.fval = fval; G.free_slots = fval + n_features; G.consumed = consumed;
-    if (grid_in_smem) KLT_CUDA(ctx, cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_b));
-    KLT_LAUNCH(ctx, "greedy", 0.0, (greedy_kernel<<<1, GREEDY_THREADS, grid_in_smem ? grid_b : 0, ctx->stream>>>(G)));
-    unsigned long long cons[3] = {0, 0, 0};
-    KLT_CUDA(ctx, cudaMemcpyAsync(cons, consumed, sizeof(cons), cudaMemcpyDeviceToHost, ctx->stream));
-    KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (overwrite && cons[1] && (int)cons[2] < n_features) {
-        const int rest = n_features - (int)cons[2];
-        KLT_LAUNCH(ctx, "fill_not_found", 0.0, (fill_not_found_kernel<<<(rest + 127) / 128, 128, 0, ctx->stream>>>(fx, fy, fval, n_features, consumed)));
-    }
-    KLT_CUDA(ctx, cudaMemcpyAsync(x, fx, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
-    KLT_CUDA(ctx, cudaMemcpyAsync(y, fy, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
-    KLT_CUDA(ctx, cudaMemcpyAsync(val, fval, n_features * sizeof(int), cudaMemcpyDefault, ctx->stream));
+    if ((rc = klt_sel_prepare_kernels(ctx, &S))) return rc;
+    if ((rc = klt_sel_launch_begin(ctx, &S, 1))) return rc;
+    KLT_LAUNCH(ctx, "select_walk", 0.0, (select_walk_kernel<<<1, WALK_THREADS, walk_smem(&S), ctx->stream>>>(S, 1)));
+    KLT_CUDA(ctx, cudaMemcpyAsync(x, S.fx, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    KLT_CUDA(ctx, cudaMemcpyAsync(y, S.fy, n_features * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    KLT_CUDA(ctx, cudaMemcpyAsync(val, S.fval, n_features * sizeof(int), cudaMemcpyDefault, ctx->stream));
     KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KLT_OK;
 }

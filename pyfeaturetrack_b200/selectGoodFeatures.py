@@ -76,10 +76,9 @@ def _select_on_device(tc, pyr, nFeatures, featurelist, overwriteAllFeatures):
     x, y, val = _gather(featurelist, nFeatures, overwriteAllFeatures)
     old_val = val.copy()
     params = make_params(tc)
-    consumed = C.c_int64()
-    ctx.check(_capi.lib().klt_select_good_features(ctx.handle, C.byref(params), pyr.handle, 0, None, None, 0, 0,
-                                                  nFeatures, 0 if overwriteAllFeatures else 1, x.ctypes.data,
-                                                  y.ctypes.data, val.ctypes.data, C.byref(consumed)))
+    ctx.check(_capi.lib().klt_select_good_features_batch(ctx.handle, C.byref(params), pyr.handle, nFeatures,
+                                                        0 if overwriteAllFeatures else 1, config.select_mode_code(),
+                                                        x.ctypes.data, y.ctypes.data, val.ctypes.data))
     _scatter(featurelist, x, y, val, old_val, overwriteAllFeatures)
     return featurelist
 

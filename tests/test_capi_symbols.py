@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), "libkltb200.so does not export " + name
         assert name in _capi.SIGNATURES, "ctypes binding lacks " + name
     assert sorted(_capi.SIGNATURES) == declared_functions()
-    assert lib.klt_abi_version() == 3
+    assert lib.klt_abi_version() == 4
 
 
 def test_struct_layouts_match_header():
