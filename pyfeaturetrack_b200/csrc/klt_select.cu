@@ -208,38 +208,52 @@ __device__ __forceinline__ float window_sum(const float *__restrict__ s, int W, 
     return __fsub_rn(__fsub_rn(__fadd_rn(c, a), b), d);
 }
 
-// eigenvalue map (+ histogram of the values >= min_val that no surviving feature suppresses).  One block = 256 candidate
-// columns x EIG_ROWS candidate rows of one image.
+// eigenvalue map.  One block = 256 candidate columns x EIG_ROWS candidate rows of one image.
 #define EIG_ROWS 8
-template <bool HIST>
 __global__ void __launch_bounds__(256)
 eigen_kernel(const float *__restrict__ sat, size_t plane, const __grid_constant__ SelDev S) {
-    __shared__ unsigned int h[HIST ? SEL_BINS : 1];
     const int b = blockIdx.z;
-    if (HIST) {
-        for (int k = threadIdx.x; k < SEL_BINS; k += 256) h[k] = 0;
-        __syncthreads();
-    }
     const float *sxx = sat + (size_t)b * 3 * plane, *sxy = sxx + plane, *syy = sxy + plane;
     float *vmap = S.vmap + (size_t)b * S.ncand;
-    const unsigned char *pm = S.premap ? S.premap + (size_t)b * S.map_stride : nullptr;
     const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= S.nx) return;
     for (int jj = 0; jj < EIG_ROWS; jj++) {
         const int j = blockIdx.y * EIG_ROWS + jj;
-        if (i < S.nx && j < S.ny) {
+        if (j < S.ny) {
             const int x = S.bx + i * S.step, y = S.by + j * S.step;
-            const float v = min_eigenvalue(window_sum(sxx, S.W, x, y, S.hw, S.hh), window_sum(sxy, S.W, x, y, S.hw, S.hh),
-                                           window_sum(syy, S.W, x, y, S.hw, S.hh));
-            vmap[(size_t)j * S.nx + i] = v;
-            if (HIST && v >= S.min_val && !(pm && pm[(size_t)y * S.W + x])) atomicAdd(&h[eig_rbin(v)], 1u);
+            vmap[(size_t)j * S.nx + i] = min_eigenvalue(window_sum(sxx, S.W, x, y, S.hw, S.hh), window_sum(sxy, S.W, x, y, S.hw, S.hh),
+                                                        window_sum(syy, S.W, x, y, S.hw, S.hh));
         }
     }
-    if (HIST) {
-        __syncthreads();
-        unsigned int *hist = S.hist + (size_t)b * SEL_BINS;
-        for (int k = threadIdx.x; k < SEL_BINS; k += 256)
-            if (h[k]) atomicAdd(&hist[k], h[k]);
+}
+
+// ---- histogram of the eigenvalue map (candidates >= min_val that no surviving feature suppresses) -----------------------
+// Separate from the eigen kernels on purpose: those are register- and latency-critical; this pass re-reads 4 B per candidate
+// at full occupancy (~2 us per 1080p image).
+#define HIST_ROWS 8
+__global__ void __launch_bounds__(256)
+select_hist_kernel(const __grid_constant__ SelDev S) {
+    __shared__ unsigned int h[SEL_BINS];
+    const int b = blockIdx.y;
+    for (int k = threadIdx.x; k < SEL_BINS; k += 256) h[k] = 0;
+    __syncthreads();
+    const float *vmap = S.vmap + (size_t)b * S.ncand;
+    const unsigned char *pm = S.premap ? S.premap + (size_t)b * S.map_stride : nullptr;
+    // few, long-lived blocks: the flush below costs up to SEL_BINS global atomics per block
+    const int tiles_x = (S.nx + 255) / 256, tiles = tiles_x * ((S.ny + HIST_ROWS - 1) / HIST_ROWS);
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int i = (tile % tiles_x) * 256 + threadIdx.x, j0 = (tile / tiles_x) * HIST_ROWS;
+        float v[HIST_ROWS];
+#pragma unroll
+        for (int jj = 0; jj < HIST_ROWS; jj++) v[jj] = (i < S.nx && j0 + jj < S.ny) ? vmap[(size_t)(j0 + jj) * S.nx + i] : 0.f;
+#pragma unroll
+        for (int jj = 0; jj < HIST_ROWS; jj++)
+            if (v[jj] >= S.min_val && !(pm && pm[(size_t)(S.by + (j0 + jj) * S.step) * S.W + S.bx + i * S.step])) atomicAdd(&h[eig_rbin(v[jj])], 1u);
     }
+    __syncthreads();
+    unsigned int *hist = S.hist + (size_t)b * SEL_BINS;
+    for (int k = threadIdx.x; k < SEL_BINS; k += 256)
+        if (h[k]) atomicAdd(&hist[k], h[k]);
 }
 
 // ---- plan: which bins to sort first ---------------------------------------------------------------------------------
@@ -323,7 +337,7 @@ __device__ __forceinline__ unsigned long long make_key(float val, int x, int y) 
     return ~k;
 }
 
-#define SCAT_ROWS 4
+#define SCAT_ROWS 8
 __global__ void __launch_bounds__(256)
 select_scatter_kernel(const __grid_constant__ SelDev S) {
     const int b = blockIdx.z;
@@ -336,20 +350,23 @@ select_scatter_kernel(const __grid_constant__ SelDev S) {
     unsigned int *cursor = S.cursor + (size_t)b * SEL_BINS;
     unsigned long long *keys = S.keys + (size_t)b * S.key_stride;
     const int lane = threadIdx.x & 31;
+    // the planned range holds ~0.1-2 % of the candidates: the smallest value that can be in it, as a float threshold
+    // (reversed bin <= rb_hi  <=>  (bits >> 16) >= 0x4F7F - rb_hi); values above the histogram's top land in bin 0
+    const float vmin = fmaxf(S.min_val, __uint_as_float((0x4F7Fu - min(rb_hi, (unsigned int)(SEL_BINS - 1))) << 16));
+    float v[SCAT_ROWS];
+#pragma unroll
     for (int jj = 0; jj < SCAT_ROWS; jj++) {
         const int j = blockIdx.y * SCAT_ROWS + jj;
-        bool keep = false;
-        float v = 0.f;
-        int x = 0, y = 0, rb = SEL_BINS;
-        if (i < S.nx && j < S.ny) {
-            v = vmap[(size_t)j * S.nx + i];
-            x = S.bx + i * S.step; y = S.by + j * S.step;
-            if (v >= S.min_val) {                         // candidates below min_eigenvalue can never be accepted (:116)
-                rb = eig_rbin(v);
-                keep = (unsigned int)rb <= rb_hi && !(pm && pm[(size_t)y * S.W + x]);
-            }
-        }
-        if (!__any_sync(0xffffffffu, keep)) continue;     // the usual case: the planned range holds ~0.1-2 % of the candidates
+        v[jj] = (i < S.nx && j < S.ny) ? vmap[(size_t)j * S.nx + i] : 0.f;
+    }
+#pragma unroll
+    for (int jj = 0; jj < SCAT_ROWS; jj++) {
+        const int j = blockIdx.y * SCAT_ROWS + jj;
+        bool keep = v[jj] >= vmin;                    // candidates below min_eigenvalue can never be accepted (:116)
+        if (!__any_sync(0xffffffffu, keep)) continue;
+        const int x = S.bx + i * S.step, y = S.by + j * S.step;
+        const int rb = eig_rbin(v[jj]);
+        keep = keep && (unsigned int)rb <= rb_hi && !(pm && pm[(size_t)y * S.W + x]);
         // warp-aggregated append: one atomic per distinct bin in the warp
         const unsigned int peers = __match_any_sync(0xffffffffu, keep ? rb : SEL_BINS + lane);
         if (keep) {
@@ -357,7 +374,7 @@ select_scatter_kernel(const __grid_constant__ SelDev S) {
             unsigned int base = 0;
             if (lane == leader) base = atomicAdd(&cursor[rb], (unsigned int)__popc(peers));
             base = __shfl_sync(peers, base, leader);
-            keys[offs[rb] + base + __popc(peers & ((1u << lane) - 1u))] = make_key(v, x, y);
+            keys[offs[rb] + base + __popc(peers & ((1u << lane) - 1u))] = make_key(v[jj], x, y);
         }
     }
 }
@@ -642,6 +659,7 @@ select_walk_kernel(const __grid_constant__ SelDev S, int presorted) {
                             if (filled >= slots) full = true;
                             __syncwarp();
                         }
+                        __syncwarp();                         // every lane has read s_filled (the loop may not have run)
                         if (lane == 0) { s_filled = filled; if (full) s_full = 1; }
                     }
                     __syncthreads();
@@ -786,7 +804,7 @@ int klt_sel_launch_begin(klt_ctx *ctx, const SelDev *S, int B) {
 
 // STRICT eigenvalue map (+ histogram) of B images from their level-0 gradient planes
 int klt_sel_launch_eigen_strict(klt_ctx *ctx, const SelDev *S, int B, const float *gx0, const float *gy0, size_t img_stride,
-                                size_t pitch, float *sat, bool with_hist) {
+                                size_t pitch, float *sat) {
     const int w = S->W, h = S->H;
     const size_t plane = (size_t)w * h;
     const bool vec = (w % SAT_T) == 0 && (pitch % 4) == 0 && (img_stride % 4) == 0 &&
@@ -800,14 +818,20 @@ int klt_sel_launch_eigen_strict(klt_ctx *ctx, const SelDev *S, int B, const floa
     if (S->ncand) {
         const dim3 g2((S->nx + 255) / 256, (S->ny + EIG_ROWS - 1) / EIG_ROWS, B);
         const double bytes = (12.0 * plane + 4.0 * S->ncand) * B;
-        if (with_hist) KLT_LAUNCH(ctx, "eigen", bytes, (eigen_kernel<true><<<g2, 256, 0, ctx->stream>>>(sat, plane, *S)));
-        else KLT_LAUNCH(ctx, "eigen", bytes, (eigen_kernel<false><<<g2, 256, 0, ctx->stream>>>(sat, plane, *S)));
+        KLT_LAUNCH(ctx, "eigen", bytes, (eigen_kernel<<<g2, 256, 0, ctx->stream>>>(sat, plane, *S)));
     }
     return KLT_OK;
 }
 
 // plan + scatter + walk on the eigenvalue maps and histograms of B images
 int klt_sel_launch_pick(klt_ctx *ctx, const SelDev *S, int B) {
+    if (S->ncand) {
+        const int tiles = ((S->nx + 255) / 256) * ((S->ny + HIST_ROWS - 1) / HIST_ROWS);
+        int nblk = (ctx->num_sms * 4 + B - 1) / B;           // about four blocks per SM over all images
+        if (nblk > tiles) nblk = tiles;
+        if (nblk < 1) nblk = 1;
+        KLT_LAUNCH(ctx, "select_hist", 4.0 * S->ncand * B, (select_hist_kernel<<<dim3(nblk, B), 256, 0, ctx->stream>>>(*S)));
+    }
     KLT_LAUNCH(ctx, "select_plan", 0.0, (select_plan_kernel<<<B, WALK_THREADS, 0, ctx->stream>>>(*S)));
     if (S->ncand)
         KLT_LAUNCH(ctx, "select_scatter", 4.0 * S->ncand * B, (select_scatter_kernel<<<dim3((S->nx + 255) / 256, (S->ny + SCAT_ROWS - 1) / SCAT_ROWS, B), 256, 0, ctx->stream>>>(*S)));
@@ -825,7 +849,7 @@ int klt_launch_scan(klt_ctx *ctx, const float *gx, const float *gy, size_t pitch
     int rc = klt_ws_reserve(ctx, 3 * plane);
     if (rc) return rc;
     if ((rc = klt_sel_prepare_kernels_scan(ctx, &S))) return rc;
-    return klt_sel_launch_eigen_strict(ctx, &S, 1, gx, gy, 0, pitch, (float *)ctx->ws, false);
+    return klt_sel_launch_eigen_strict(ctx, &S, 1, gx, gy, 0, pitch, (float *)ctx->ws);
 }
 
 int klt_sel_prepare_kernels_scan(klt_ctx *ctx, const SelDev *S) {
@@ -869,7 +893,7 @@ int klt_select_batch(klt_ctx *ctx, const klt_params *p, int select_mode, klt_pyr
             if ((rc = klt_ensure_gradients_level0(ctx, pyr))) return rc;      // image-only pyramids: build level 0's planes now
             gx0 = pyr->level(1, 0, 0); gy0 = pyr->level(2, 0, 0); img_stride = pyr->plane_floats; pitch = pyr->lv[0].pitch;
         }
-        if ((rc = klt_sel_launch_eigen_strict(ctx, &S, B, gx0, gy0, img_stride, pitch, sat, true))) return rc;
+        if ((rc = klt_sel_launch_eigen_strict(ctx, &S, B, gx0, gy0, img_stride, pitch, sat))) return rc;
     }
     if ((rc = klt_sel_launch_pick(ctx, &S, B))) return rc;
     if (host) {
@@ -909,7 +933,7 @@ int klt_eigen_maps(klt_ctx *ctx, const klt_params *p, int select_mode, klt_pyr *
     }
     if (!done) {
         if ((rc = klt_ensure_gradients_level0(ctx, pyr))) return rc;
-        if ((rc = klt_sel_launch_eigen_strict(ctx, &S, B, pyr->level(1, 0, 0), pyr->level(2, 0, 0), pyr->plane_floats, pyr->lv[0].pitch, sat, true))) return rc;
+        if ((rc = klt_sel_launch_eigen_strict(ctx, &S, B, pyr->level(1, 0, 0), pyr->level(2, 0, 0), pyr->plane_floats, pyr->lv[0].pitch, sat))) return rc;
     }
     KLT_CUDA(ctx, cudaMemcpyAsync(val, S.vmap, (size_t)B * S.ncand * sizeof(float), cudaMemcpyDefault, ctx->stream));
     KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

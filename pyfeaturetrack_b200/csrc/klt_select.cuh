@@ -46,8 +46,8 @@ int klt_sel_prepare_kernels(klt_ctx *ctx, const SelDev *S);          // cudaFunc
 int klt_sel_prepare_kernels_scan(klt_ctx *ctx, const SelDev *S);
 int klt_sel_launch_begin(klt_ctx *ctx, const SelDev *S, int B);
 int klt_sel_launch_eigen_strict(klt_ctx *ctx, const SelDev *S, int B, const float *gx0, const float *gy0, size_t img_stride,
-                                size_t pitch, float *sat, bool with_hist);
-// FAST eigenvalue map + histogram straight from the level-0 intensity planes (klt_select_fast.cu)
+                                size_t pitch, float *sat);
+// FAST eigenvalue map straight from the level-0 intensity planes (klt_select_fast.cu)
 int klt_sel_launch_eigen_fast(klt_ctx *ctx, const SelDev *S, int B, const float *img0, size_t img_stride, size_t pitch,
                               const klt_kernel1d *gauss, const klt_kernel1d *deriv);
 int klt_sel_launch_pick(klt_ctx *ctx, const SelDev *S, int B);

@@ -27,14 +27,12 @@ eigen_fast_kernel(const float *__restrict__ img0, size_t img_stride, size_t pitc
                   const __grid_constant__ FastTaps T, int rows_per_seg) {
     __shared__ float rowI[2][FS_THREADS];
     __shared__ float rowV[2][3][FS_THREADS];
-    __shared__ unsigned int h[SEL_BINS];
     const int t = threadIdx.x, b = blockIdx.z;
     const int W = S.W, H = S.H, hw = S.hw;
     const int halo = FS_R + hw, span = FS_THREADS - 2 * halo;
     const int x = S.bx - halo + (int)blockIdx.x * span + t;            // this thread's column
     const int xr = klt_reflect(x, W);
     const float *img = img0 + (size_t)b * img_stride + xr;
-    for (int k = t; k < SEL_BINS; k += FS_THREADS) h[k] = 0;
     // candidate rows of this segment
     const int ys = S.by + (int)blockIdx.y * rows_per_seg, ye = min(ys + rows_per_seg, H - S.by);
     if (ys >= ye) return;
@@ -42,7 +40,6 @@ eigen_fast_kernel(const float *__restrict__ img0, size_t img_stride, size_t pitc
     const bool cand_col = t >= halo && t < FS_THREADS - halo && x < W - S.bx && (ci % S.step) == 0;
     const int i_c = ci / S.step;
     float *vmap = S.vmap + (size_t)b * S.ncand;
-    const unsigned char *pm = S.premap ? S.premap + (size_t)b * S.map_stride : nullptr;
     float Px[6], Py[6];                   // pending gx / gy rows (vertical 7-tap filters)
     float Qxx[2 * HH], Qxy[2 * HH], Qyy[2 * HH];   // pending vertical window sums
 #pragma unroll
@@ -92,141 +89,150 @@ eigen_fast_kernel(const float *__restrict__ img0, size_t img_stride, size_t pitc
                 float gxx = 0.f, gxy = 0.f, gyy = 0.f;
                 for (int k = -hw; k <= hw; k++) { gxx += rowV[par][0][t + k]; gxy += rowV[par][1][t + k]; gyy += rowV[par][2][t + k]; }
                 const float dd = gxx - gyy;
-                const float v = 0.5f * ((gxx + gyy) - sqrtf(fmaf(dd, dd, 4.f * gxy * gxy)));
-                vmap[(size_t)(cj / S.step) * S.nx + i_c] = v;
-                if (v >= S.min_val && !(pm && pm[(size_t)yc * W + x])) atomicAdd(&h[eig_rbin(v)], 1u);
+                vmap[(size_t)(cj / S.step) * S.nx + i_c] = 0.5f * ((gxx + gyy) - sqrtf(fmaf(dd, dd, 4.f * gxy * gxy)));
             }
         }
     }
-    __syncthreads();
-    unsigned int *hist = S.hist + (size_t)b * SEL_BINS;
-    for (int k = t; k < SEL_BINS; k += FS_THREADS)
-        if (h[k]) atomicAdd(&hist[k], h[k]);
 }
 
 // ---- windows up to 7x7: the same pass with no shared memory and no barriers -------------------------------------------
-// A WARP owns 128 adjacent columns and marches down its row segment; a lane owns 4 adjacent columns (one 128-bit load per
-// row).  Horizontal neighbours -- three image columns for the 7-tap gradient filters, HH columns of window sums -- come from
-// the adjacent lanes by shuffle; lanes 0, 1, 30, 31 are halo lanes (112 of 128 columns produce output).  Everything else is
-// register arithmetic on four independent columns, so the kernel needs neither occupancy nor barriers to stay busy.
+// A WARP owns 32 * NC adjacent columns and marches down its row segment; a lane owns NC adjacent columns (one 64/128-bit load
+// per row).  Horizontal neighbours -- three image columns for the 7-tap gradient filters, HH columns of window sums -- come
+// from the adjacent lanes by shuffle; the outermost HL = ceil(6 / NC) lanes on either side are halo lanes.  Everything else is
+// register arithmetic on NC independent columns.  NC = 4 needs ~200 registers (8 warps per SM), NC = 2 ~110 (16 warps).
 #define FQ_PF 3
-template <int HH>
+template <int NC> struct QuadVec;
+template <> struct QuadVec<4> { typedef float4 type; };
+template <> struct QuadVec<2> { typedef float2 type; };
+
+template <int HH, int NC, bool STEP1>
 __global__ void __launch_bounds__(FS_THREADS)
 eigen_fast_quad_kernel(const float *__restrict__ img0, size_t img_stride, size_t pitch, const __grid_constant__ SelDev S,
                        const __grid_constant__ FastTaps T, int rows_per_seg, int n_strips, int vec_ok) {
-    __shared__ unsigned int h[SEL_BINS];
+    constexpr int HL = (FS_R + HH + NC - 1) / NC;                   // halo lanes per side
+    constexpr int USE = (32 - 2 * HL) * NC;                         // output columns per warp
+    constexpr int NB = (FS_R + NC - 1) / NC, NBH = (HH + NC - 1) / NC;   // neighbour lanes that hold the 3 / HH adjacent columns
+    typedef typename QuadVec<NC>::type vec_t;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, b = blockIdx.z;
     const int W = S.W, H = S.H;
-    for (int k = t; k < SEL_BINS; k += FS_THREADS) h[k] = 0;
-    __syncthreads();
     const int strip = blockIdx.x * (FS_THREADS / 32) + warp;
     const int ys = S.by + (int)blockIdx.y * rows_per_seg, ye = min(ys + rows_per_seg, H - S.by);
-    if (strip < n_strips && ys < ye) {
-        const int xa = S.bx & ~3;
-        const int xl = xa - 8 + strip * 112 + 4 * lane;             // first of this lane's 4 columns (multiple of 4)
-        const bool inside = xl >= 0 && xl + 3 < W;
-        const bool vec = inside && vec_ok;
-        const int c0 = klt_reflect(xl, W), c1 = klt_reflect(xl + 1, W), c2 = klt_reflect(xl + 2, W), c3 = klt_reflect(xl + 3, W);
-        const float *img = img0 + (size_t)b * img_stride;
-        auto load_row = [&](int y) -> float4 {
-            const float *r = img + (size_t)klt_reflect(y, H) * pitch;
-            if (vec) return *reinterpret_cast<const float4 *>(r + xl);
-            return make_float4(r[c0], r[c1], r[c2], r[c3]);
-        };
-        const bool out_lane = lane >= 2 && lane < 30;
-        float *vmap = S.vmap + (size_t)b * S.ncand;
-        const unsigned char *pm = S.premap ? S.premap + (size_t)b * S.map_stride : nullptr;
-        float Px[4][6], Py[4][6], Qxx[4][2 * HH], Qxy[4][2 * HH], Qyy[4][2 * HH];
+    if (strip >= n_strips || ys >= ye) return;
+    const int xa = S.bx & ~(NC - 1);
+    const int xl = xa - HL * NC + strip * USE + NC * lane;          // first of this lane's NC columns (multiple of NC)
+    const bool vec = xl >= 0 && xl + NC - 1 < W && vec_ok;
+    int cr[NC];
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
+    for (int c = 0; c < NC; c++) cr[c] = klt_reflect(xl + c, W);
+    const float *img = img0 + (size_t)b * img_stride;
+    float cur[NC], q[FQ_PF][NC];
+    auto load_row = [&](int y, float (&o)[NC]) {
+        const float *r = img + (size_t)klt_reflect(y, H) * pitch;
+        if (vec) {
+            const vec_t v = *reinterpret_cast<const vec_t *>(r + xl);
+            const float *pv = reinterpret_cast<const float *>(&v);
 #pragma unroll
-            for (int m = 0; m < 6; m++) { Px[c][m] = 0.f; Py[c][m] = 0.f; }
+            for (int c = 0; c < NC; c++) o[c] = pv[c];
+        } else {
 #pragma unroll
-            for (int m = 0; m < 2 * HH; m++) { Qxx[c][m] = 0.f; Qxy[c][m] = 0.f; Qyy[c][m] = 0.f; }
+            for (int c = 0; c < NC; c++) o[c] = r[cr[c]];
         }
-        const int y0 = ys - HH - FS_R, y_end = ye - 1 + HH + FS_R;
-        float4 q[FQ_PF];
+    };
+    const bool out_lane = lane >= HL && lane < 32 - HL;
+    float *vmap = S.vmap + (size_t)b * S.ncand;
+    float Px[NC][6], Py[NC][6], Qxx[NC][2 * HH], Qxy[NC][2 * HH], Qyy[NC][2 * HH];
 #pragma unroll
-        for (int i = 0; i < FQ_PF; i++) q[i] = load_row(min(y0 + i, y_end));
-        for (int y = y0; y <= y_end; y++) {
-            const float4 cur = q[0];
+    for (int c = 0; c < NC; c++) {
 #pragma unroll
-            for (int i = 0; i < FQ_PF - 1; i++) q[i] = q[i + 1];
-            q[FQ_PF - 1] = load_row(min(y + FQ_PF, y_end));
-            float I[10];                                            // columns xl-3 .. xl+6
-            I[0] = __shfl_up_sync(0xffffffffu, cur.y, 1); I[1] = __shfl_up_sync(0xffffffffu, cur.z, 1); I[2] = __shfl_up_sync(0xffffffffu, cur.w, 1);
-            I[3] = cur.x; I[4] = cur.y; I[5] = cur.z; I[6] = cur.w;
-            I[7] = __shfl_down_sync(0xffffffffu, cur.x, 1); I[8] = __shfl_down_sync(0xffffffffu, cur.y, 1); I[9] = __shfl_down_sync(0xffffffffu, cur.z, 1);
-            float vxx[4], vxy[4], vyy[4];
+        for (int m = 0; m < 6; m++) { Px[c][m] = 0.f; Py[c][m] = 0.f; }
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const float *r = &I[3 + c];
-                const float a1 = r[1] + r[-1], a2 = r[2] + r[-2], a3 = r[3] + r[-3];
-                const float b1 = r[1] - r[-1], b2 = r[2] - r[-2], b3 = r[3] - r[-3];
-                const float gh = fmaf(T.g[6], a3, fmaf(T.g[5], a2, fmaf(T.g[4], a1, T.g[3] * r[0])));
-                const float dh = fmaf(T.d[6], b3, fmaf(T.d[5], b2, T.d[4] * b1));
-                const float gx = fmaf(T.g[6], dh, Px[c][0]), gy = fmaf(T.d[6], gh, Py[c][0]);
+        for (int m = 0; m < 2 * HH; m++) { Qxx[c][m] = 0.f; Qxy[c][m] = 0.f; Qyy[c][m] = 0.f; }
+    }
+    // V[k] = value of column xl - R + k gathered from this lane (cols R .. R+NC-1) and its neighbours
+    auto gather = [&](const float (&v)[NC], float *V, int R, int nb) {
 #pragma unroll
-                for (int m = 0; m < 5; m++) { Px[c][m] = fmaf(T.g[5 - m], dh, Px[c][m + 1]); Py[c][m] = fmaf(T.d[5 - m], gh, Py[c][m + 1]); }
-                Px[c][5] = T.g[0] * dh; Py[c][5] = T.d[0] * gh;
-                const float pxx = gx * gx, pxy = gx * gy, pyy = gy * gy;
-                vxx[c] = Qxx[c][0] + pxx; vxy[c] = Qxy[c][0] + pxy; vyy[c] = Qyy[c][0] + pyy;
+        for (int k = 0; k < R; k++) {
+            // column xl - R + k lives in lane - ceil((R-k)/NC), element NC*that - (R-k)
+            const int d = (R - k + NC - 1) / NC, e = d * NC - (R - k);
+            V[k] = __shfl_up_sync(0xffffffffu, v[e], d);
+            const int kk = R + NC + k;                                // column xl + NC + k lives in lane + 1 + k/NC, element k % NC
+            V[kk] = __shfl_down_sync(0xffffffffu, v[k % NC], 1 + k / NC);
+        }
 #pragma unroll
-                for (int m = 0; m < 2 * HH - 1; m++) { Qxx[c][m] = Qxx[c][m + 1] + pxx; Qxy[c][m] = Qxy[c][m + 1] + pxy; Qyy[c][m] = Qyy[c][m + 1] + pyy; }
-                Qxx[c][2 * HH - 1] = pxx; Qxy[c][2 * HH - 1] = pxy; Qyy[c][2 * HH - 1] = pyy;
-            }
-            const int yc = y - FS_R - HH;
-            if (yc >= ys) {                                          // warp-uniform
-                // horizontal window sums: columns xl-HH .. xl+3+HH of the three planes
-                float sx[4], sxy_[4], sy[4];
-                auto hbox = [&](const float (&v)[4], float (&o)[4]) {
-                    float V[4 + 2 * HH];
+        for (int c = 0; c < NC; c++) V[R + c] = v[c];
+        (void)nb;
+    };
+    const int y0 = ys - HH - FS_R, y_end = ye - 1 + HH + FS_R;
 #pragma unroll
-                    for (int k = 0; k < HH; k++) {
-                        V[k] = __shfl_up_sync(0xffffffffu, v[4 - HH + k], 1);
-                        V[4 + HH + k] = __shfl_down_sync(0xffffffffu, v[k], 1);
-                    }
+    for (int i = 0; i < FQ_PF; i++) load_row(min(y0 + i, y_end), q[i]);
+    for (int y = y0; y <= y_end; y++) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++) V[HH + k] = v[k];
-                    float s0 = V[0];
+        for (int c = 0; c < NC; c++) cur[c] = q[0][c];
 #pragma unroll
-                    for (int k = 1; k <= 2 * HH; k++) s0 += V[k];
-                    o[0] = s0;
+        for (int i = 0; i < FQ_PF - 1; i++)
 #pragma unroll
-                    for (int c = 1; c < 4; c++) o[c] = o[c - 1] + V[c + 2 * HH] - V[c - 1];
-                };
-                hbox(vxx, sx); hbox(vxy, sxy_); hbox(vyy, sy);
-                const int cj = yc - S.by;
-                if (out_lane && (cj % S.step) == 0) {
-                    float *vrow = vmap + (size_t)(cj / S.step) * S.nx;
+            for (int c = 0; c < NC; c++) q[i][c] = q[i + 1][c];
+        load_row(min(y + FQ_PF, y_end), q[FQ_PF - 1]);
+        float I[NC + 2 * FS_R];                                       // columns xl-3 .. xl+NC+2
+        gather(cur, I, FS_R, NB);
+        float vxx[NC], vxy[NC], vyy[NC];
 #pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const int x = xl + c, ci = x - S.bx;
-                        if (ci >= 0 && x < W - S.bx && (ci % S.step) == 0) {
-                            const float dd = sx[c] - sy[c];
-                            const float v = 0.5f * ((sx[c] + sy[c]) - sqrtf(fmaf(dd, dd, 4.f * sxy_[c] * sxy_[c])));
-                            vrow[ci / S.step] = v;
-                            if (v >= S.min_val && !(pm && pm[(size_t)yc * W + x])) atomicAdd(&h[eig_rbin(v)], 1u);
-                        }
+        for (int c = 0; c < NC; c++) {
+            const float *r = &I[FS_R + c];
+            const float a1 = r[1] + r[-1], a2 = r[2] + r[-2], a3 = r[3] + r[-3];
+            const float b1 = r[1] - r[-1], b2 = r[2] - r[-2], b3 = r[3] - r[-3];
+            const float gh = fmaf(T.g[6], a3, fmaf(T.g[5], a2, fmaf(T.g[4], a1, T.g[3] * r[0])));
+            const float dh = fmaf(T.d[6], b3, fmaf(T.d[5], b2, T.d[4] * b1));
+            const float gx = fmaf(T.g[6], dh, Px[c][0]), gy = fmaf(T.d[6], gh, Py[c][0]);
+#pragma unroll
+            for (int m = 0; m < 5; m++) { Px[c][m] = fmaf(T.g[5 - m], dh, Px[c][m + 1]); Py[c][m] = fmaf(T.d[5 - m], gh, Py[c][m + 1]); }
+            Px[c][5] = T.g[0] * dh; Py[c][5] = T.d[0] * gh;
+            const float pxx = gx * gx, pxy = gx * gy, pyy = gy * gy;
+            vxx[c] = Qxx[c][0] + pxx; vxy[c] = Qxy[c][0] + pxy; vyy[c] = Qyy[c][0] + pyy;
+#pragma unroll
+            for (int m = 0; m < 2 * HH - 1; m++) { Qxx[c][m] = Qxx[c][m + 1] + pxx; Qxy[c][m] = Qxy[c][m + 1] + pxy; Qyy[c][m] = Qyy[c][m + 1] + pyy; }
+            Qxx[c][2 * HH - 1] = pxx; Qxy[c][2 * HH - 1] = pxy; Qyy[c][2 * HH - 1] = pyy;
+        }
+        const int yc = y - FS_R - HH;
+        if (yc >= ys) {                                          // warp-uniform
+            // horizontal window sums over columns xl-HH .. xl+NC-1+HH of the three planes
+            float sx[NC], sxy_[NC], sy[NC];
+            auto hbox = [&](const float (&v)[NC], float (&o)[NC]) {
+                float V[NC + 2 * HH];
+                gather(v, V, HH, NBH);
+                float s0 = V[0];
+#pragma unroll
+                for (int k = 1; k <= 2 * HH; k++) s0 += V[k];
+                o[0] = s0;
+#pragma unroll
+                for (int c = 1; c < NC; c++) o[c] = o[c - 1] + V[c + 2 * HH] - V[c - 1];
+            };
+            hbox(vxx, sx); hbox(vxy, sxy_); hbox(vyy, sy);
+            const int cj = yc - S.by;
+            if (out_lane && (STEP1 || (cj % S.step) == 0)) {
+                float *vrow = vmap + (size_t)(STEP1 ? cj : cj / S.step) * S.nx;
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    const int x = xl + c, ci = x - S.bx;
+                    if (ci >= 0 && x < W - S.bx && (STEP1 || (ci % S.step) == 0)) {
+                        const float dd = sx[c] - sy[c];
+                        vrow[STEP1 ? ci : ci / S.step] = 0.5f * ((sx[c] + sy[c]) - sqrtf(fmaf(dd, dd, 4.f * sxy_[c] * sxy_[c])));
                     }
                 }
             }
         }
     }
-    __syncthreads();
-    unsigned int *hist = S.hist + (size_t)b * SEL_BINS;
-    for (int k = t; k < SEL_BINS; k += FS_THREADS)
-        if (h[k]) atomicAdd(&hist[k], h[k]);
 }
 
-template <int HH>
+template <int HH, int NC>
 static int launch_fast_quad(klt_ctx *ctx, const SelDev *S, int B, const float *img0, size_t img_stride, size_t pitch, const FastTaps &T) {
-    const int ncols = S->W - S->bx - (S->bx & ~3), nrows = S->H - 2 * S->by;
+    constexpr int HL = (FS_R + HH + NC - 1) / NC, USE = (32 - 2 * HL) * NC;
+    const int ncols = S->W - S->bx - (S->bx & ~(NC - 1)), nrows = S->H - 2 * S->by;
     if (S->W - 2 * S->bx <= 0 || nrows <= 0) return 1;
-    const int n_strips = (ncols + 111) / 112;
+    const int n_strips = (ncols + USE - 1) / USE;
     const int strip_blocks = (n_strips + FS_THREADS / 32 - 1) / (FS_THREADS / 32);
-    // about two blocks per SM; a segment re-reads 2*(HH+3) warm-up rows, so keep segments >= 64 rows
-    long nseg = ((long)ctx->num_sms * 2) / ((long)strip_blocks * B);
+    // one wave of resident blocks (2 per SM at NC = 4, 4 at NC = 2); a segment re-reads 2*(HH+3) warm-up rows: keep it >= 64 rows
+    long nseg = ((long)ctx->num_sms * (NC == 4 ? 2 : 4)) / ((long)strip_blocks * B);
     if (nseg < 1) nseg = 1;
     int rows = (int)((nrows + nseg - 1) / nseg);
     if (rows < 64) rows = 64;
@@ -234,7 +240,10 @@ static int launch_fast_quad(klt_ctx *ctx, const SelDev *S, int B, const float *i
     const dim3 grid(strip_blocks, (nrows + rows - 1) / rows, B);
     const double bytes = (4.0 * S->W * S->H + 4.0 * S->ncand) * B;
     const int vec_ok = (pitch % 4) == 0 && (img_stride % 4) == 0 && (reinterpret_cast<uintptr_t>(img0) & 15) == 0;
-    KLT_LAUNCH(ctx, "eigen_fast", bytes, (eigen_fast_quad_kernel<HH><<<grid, FS_THREADS, 0, ctx->stream>>>(img0, img_stride, pitch, *S, T, rows, n_strips, vec_ok)));
+    if (S->step == 1)
+        KLT_LAUNCH(ctx, "eigen_fast", bytes, (eigen_fast_quad_kernel<HH, NC, true><<<grid, FS_THREADS, 0, ctx->stream>>>(img0, img_stride, pitch, *S, T, rows, n_strips, vec_ok)));
+    else
+        KLT_LAUNCH(ctx, "eigen_fast", bytes, (eigen_fast_quad_kernel<HH, NC, false><<<grid, FS_THREADS, 0, ctx->stream>>>(img0, img_stride, pitch, *S, T, rows, n_strips, vec_ok)));
     return 1;
 }
 
@@ -267,9 +276,9 @@ int klt_sel_launch_eigen_fast(klt_ctx *ctx, const SelDev *S, int B, const float 
         if (fabs(gauss->taps[3 + k] - gauss->taps[3 - k]) > 1e-12 || fabs(deriv->taps[3 + k] + deriv->taps[3 - k]) > 1e-12) return 0;
     if (fabs(deriv->taps[3]) > 1e-12) return 0;
     switch (S->hh) {
-        case 1: return launch_fast_quad<1>(ctx, S, B, img0, img_stride, pitch, T);
-        case 2: return launch_fast_quad<2>(ctx, S, B, img0, img_stride, pitch, T);
-        case 3: return launch_fast_quad<3>(ctx, S, B, img0, img_stride, pitch, T);
+        case 1: return ctx->fast_quad_nc == 2 ? launch_fast_quad<1, 2>(ctx, S, B, img0, img_stride, pitch, T) : launch_fast_quad<1, 4>(ctx, S, B, img0, img_stride, pitch, T);
+        case 2: return ctx->fast_quad_nc == 2 ? launch_fast_quad<2, 2>(ctx, S, B, img0, img_stride, pitch, T) : launch_fast_quad<2, 4>(ctx, S, B, img0, img_stride, pitch, T);
+        case 3: return ctx->fast_quad_nc == 2 ? launch_fast_quad<3, 2>(ctx, S, B, img0, img_stride, pitch, T) : launch_fast_quad<3, 4>(ctx, S, B, img0, img_stride, pitch, T);
         case 4: return launch_fast<4>(ctx, S, B, img0, img_stride, pitch, T);
         case 5: return launch_fast<5>(ctx, S, B, img0, img_stride, pitch, T);
         case 6: return launch_fast<6>(ctx, S, B, img0, img_stride, pitch, T);

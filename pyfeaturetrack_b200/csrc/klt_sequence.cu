@@ -53,7 +53,7 @@ static int select_on(klt_ctx *ctx, klt_sequence *q, klt_pyr *p, const SelDev *S)
     if (!done) {
         if ((rc = klt_ensure_gradients_level0(ctx, p))) return rc;
         if ((rc = klt_sel_launch_eigen_strict(ctx, S, q->B, p->level(1, 0, 0), p->level(2, 0, 0), p->plane_floats, p->lv[0].pitch,
-                                              q->sat, true))) return rc;
+                                              q->sat))) return rc;
     }
     return klt_sel_launch_pick(ctx, S, q->B);
 }
