@@ -14,6 +14,12 @@ One "step" = one pass of the hot path over one batch of `--pairs` independent fr
               host->device copies of the frames and features and the device->host copy of the results are inside
               the timed region.
 Multi-GPU: independent pairs are sharded over ranks, no data-path collective (weak scaling: `--pairs` per GPU).
+
+Beside the headline the line carries (all measured in the same run): `sustained` (the same step for >= 2 s with its own
+clock record), `dense_planes` (the reference's data flow: gradient planes written for every level), `sequence` (BASELINE
+config D: --seqs lock-stepped 1080p sequences per GPU x --seq-frames frames, sequentialMode tracking + per-frame feature
+replacement through klt_sequence, device-resident and host-fed), and at N = 1 `config_C`, `config_E`, the drop-in API
+timings and the CPU baseline; at N > 1 the final feature-list gather over NCCL (`gather`).
 """
 import argparse
 import ctypes as C
@@ -104,6 +110,13 @@ def make_inputs(wl, n_distinct, seed0=0):
     """n_distinct seeded synthetic pairs (SURVEY 8(d) generator) -> list of (frame1, frame2) uint8 arrays."""
     from pyfeaturetrack_b200 import synth
     return [synth.frame_pair(wl["H"], wl["W"], seed=seed0 + s) for s in range(n_distinct)]
+
+
+def bench_config(wl):
+    """The `config` object: what is computed -- identical in both arms (how much of it a step holds is under `run`)."""
+    return {"workload": wl["name"], "image": "%dx%d" % (wl["W"], wl["H"]), "features_per_pair": wl["n"], "pyramid_levels": wl["L"],
+            "subsampling": wl["ss"], "window": wl["win"], "max_residue": wl["max_residue"],
+            "call": "KLTTrackFeatures(tc, img1, img2, fl), non-sequential: two pyramid builds + tracking per pair"}
 
 
 def tc_for(wl, klt_mod):
@@ -205,15 +218,33 @@ def run_b200(args):
         ctx.check(lib.klt_pyr_build_u8(ctx.handle, p2.handle, d_f2, W, W * H, C.byref(taps), prec))
         ctx.check(lib.klt_track_features(ctx.handle, C.byref(params), p1.handle, p2.handle, n, d_x, d_y, d_v, None))
 
-    hx = ctx.pinned_array((B, n), np.float64)
-    hy = ctx.pinned_array((B, n), np.float64)
-    hv = ctx.pinned_array((B, n), np.int32)
+    # The feature arrays of the C-ABI call are in/out (the reference mutates its list): every e2e step gets its own
+    # pre-filled set from a ring, so the timed loops contain no host-side array copies.
+    e2e_steps = max(4, args.steps)
+    ring_len = e2e_steps + max(4, args.warmup) + 2
+
+    def make_ring(c, count):
+        ring = []
+        for _ in range(count):
+            ax, ay, av = c.pinned_array((B, n), np.float64), c.pinned_array((B, n), np.float64), c.pinned_array((B, n), np.int32)
+            ax[:] = x0; ay[:] = y0; av[:] = v0
+            ring.append((ax, ay, av))
+        return ring
+
+    def refill(ring):
+        for ax, ay, av in ring:
+            ax[:] = x0; ay[:] = y0; av[:] = v0
+
+    ring_a = make_ring(ctx, ring_len)
+    hx, hy, hv = ring_a[0]
+    single_pos = [0]
 
     def step_e2e():
-        hx[:] = x0; hy[:] = y0; hv[:] = v0
+        ax, ay, av = ring_a[single_pos[0] % ring_len]
+        single_pos[0] += 1
         ctx.check(lib.klt_track_pairs_u8(ctx.handle, C.byref(params), C.byref(taps), prec, p1.handle, p2.handle,
-                                         f1.ctypes.data, f2.ctypes.data, W, W * H, n, hx.ctypes.data, hy.ctypes.data,
-                                         hv.ctypes.data))
+                                         f1.ctypes.data, f2.ctypes.data, W, W * H, n, ax.ctypes.data, ay.ctypes.data,
+                                         av.ctypes.data))
 
     # e2e throughput: two host threads, each with its OWN context (own streams, pyramids, result buffers), issue the same
     # synchronous C-ABI call on alternating steps, so the upload of one step overlaps the kernels of the other
@@ -222,15 +253,13 @@ def run_b200(args):
     ctx_b = _capi.Context(local)
     p1b = _capi.Pyramid(ctx_b, W, H, L, ss, B)
     p2b = _capi.Pyramid(ctx_b, W, H, L, ss, B)
-    hxb = ctx_b.pinned_array((B, n), np.float64)
-    hyb = ctx_b.pinned_array((B, n), np.float64)
-    hvb = ctx_b.pinned_array((B, n), np.int32)
-    lanes = [(ctx, p1, p2, hx, hy, hv), (ctx_b, p1b, p2b, hxb, hyb, hvb)]
+    ring_b = make_ring(ctx_b, ring_len)
+    lanes = [(ctx, p1, p2, ring_a), (ctx_b, p1b, p2b, ring_b)]
 
     def e2e_worker(lane, count):
-        c, q1, q2, ax, ay, av = lanes[lane]
-        for _ in range(count):
-            ax[:] = x0; ay[:] = y0; av[:] = v0
+        c, q1, q2, ring = lanes[lane]
+        for k in range(count):
+            ax, ay, av = ring[k]
             c.check(lib.klt_track_pairs_u8(c.handle, C.byref(params), C.byref(taps), prec, q1.handle, q2.handle,
                                            f1.ctypes.data, f2.ctypes.data, W, W * H, n, ax.ctypes.data, ay.ctypes.data,
                                            av.ctypes.data))
@@ -279,13 +308,17 @@ def run_b200(args):
     ctx.memcpy(hv, d_v, B * n * 4)
     ctx.sync()
     tracked = int((hv == 0).sum())
-    e2e_steps = max(4, args.steps)
+    refill(ring_a)
     run_e2e(max(4, args.warmup))                         # warm-up (both contexts)
     barrier(); ctx_b.sync()
+    refill(ring_a); refill(ring_b)
+    barrier()
     t0 = time.perf_counter()
     run_e2e(e2e_steps)
     barrier(); ctx_b.sync()
     e2e_ms = (time.perf_counter() - t0) * 1e3            # wall clock: the region contains host work by design
+    e2e_tracked = int(sum((ring_a[k][2] == 0).sum() for k in range((e2e_steps + 1) // 2)) +
+                      sum((ring_b[k][2] == 0).sum() for k in range(e2e_steps // 2)))
     if world > 1:
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -293,28 +326,61 @@ def run_b200(args):
     # the same end-to-end step from ONE host thread on ONE context: asynchronous calls, two sets of pinned result
     # buffers, the upload of step k+1 overlapping the kernels of step k through the context's two staging halves
     def run_e2e_async(steps):
-        sets = [(hx, hy, hv), (hxb, hyb, hvb)]
         for k in range(steps):
             s_ = k & 1
             if k >= 2:
-                ctx.check(lib.klt_async_wait(ctx.handle, s_))           # step k-2 is complete: its buffers are free again
-            ax, ay, av = sets[s_]
-            ax[:] = x0; ay[:] = y0; av[:] = v0
+                ctx.check(lib.klt_async_wait(ctx.handle, s_))           # step k-2 is complete: its results can be consumed
+            ax, ay, av = ring_a[k % ring_len]
             ctx.check(lib.klt_track_pairs_u8_async(ctx.handle, C.byref(params), C.byref(taps), prec, p1.handle, p2.handle,
                                                    f1.ctypes.data, f2.ctypes.data, W, W * H, n, ax.ctypes.data, ay.ctypes.data,
                                                    av.ctypes.data))
             ctx.check(lib.klt_async_mark(ctx.handle, s_))
         ctx.check(lib.klt_async_result(ctx.handle))
+    refill(ring_a)
     run_e2e_async(4)
     barrier()
+    refill(ring_a)
     t0 = time.perf_counter()
     run_e2e_async(e2e_steps)
     async_ms = (time.perf_counter() - t0) * 1e3
     barrier()
+    refill(ring_a)
+    single_pos[0] = 0
     single_ms, _, _ = timed(step_e2e, max(3, args.steps // 2), 3)     # one context, one call at a time (latency view)
     single_ms /= max(3, args.steps // 2)
-    e2e_tracked = int((hv == 0).sum())
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- sustained leg: the same device-resident step back to back for >= 2 s, with its own clock record ----
+    sus_sampler = ClockSampler(local)
+    if rank == 0:
+        sus_sampler.start()
+    sus_steps = int(max(args.steps, min(20000, args.sustain_s / max(dev_ms * 1e-3 / args.steps, 1e-5))))
+    sus_ms, _, _ = timed(step_device, sus_steps, 1)
+    sus_clocks = sus_sampler.stop() if rank == 0 else None
+
+    # ---- the reference's data flow (dense gradient planes for every level), same step ----
+    dense = None
+    if args.precision == "windowed":
+        def step_dense():
+            ctx.memcpy(d_x, d_x0, B * n * 8); ctx.memcpy(d_y, d_y0, B * n * 8); ctx.memcpy(d_v, d_v0, B * n * 4)
+            ctx.check(lib.klt_pyr_build_u8(ctx.handle, p1.handle, d_f1, W, W * H, C.byref(taps), _capi.PRECISION_FAST))
+            ctx.check(lib.klt_pyr_build_u8(ctx.handle, p2.handle, d_f2, W, W * H, C.byref(taps), _capi.PRECISION_FAST))
+            ctx.check(lib.klt_track_features(ctx.handle, C.byref(params), p1.handle, p2.handle, n, d_x, d_y, d_v, None))
+        dense_ms, _, _ = timed(step_dense, args.steps, 3)
+        ctx.memcpy(hv, d_v, B * n * 4)
+        ctx.sync()
+        dense_tracked = int((hv == 0).sum())
+        ctx.profile_reset(); ctx.profile(True)
+        for _ in range(3):
+            step_dense()
+        ctx.profile(False)
+        dprof = ctx.profile_read()
+        dense = (dense_ms, dense_tracked, dprof)
+
+    # ---- BASELINE config D: lock-stepped sequences with per-frame replacement ----
+    seq = sequence_bench(ctx, lib, _capi, klt, sgf, trackFeatures, args, rank, world, local, barrier,
+                         (lambda t: dist.all_reduce(t, op=dist.ReduceOp.MAX)) if world > 1 else None,
+                         (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)) if world > 1 else None, torch)
 
     # ---- per-kernel durations, measured live with CUDA events on the launching stream (separate pass) ----
     ctx.profile_reset()
@@ -333,6 +399,22 @@ def run_b200(args):
     else:
         tracked_all, e2e_tracked_all = float(tracked), float(e2e_tracked)
     pairs_all = B * world
+    # ---- the one cross-device step of the path: the final feature-list gather (north_star), over NCCL at N > 1 ----
+    gather = None
+    if world > 1:
+        ctx.memcpy(hx, d_x, B * n * 8); ctx.memcpy(hy, d_y, B * n * 8); ctx.memcpy(hv, d_v, B * n * 4)
+        ctx.sync()
+        local_units = {rank * B + i: (hx[i], hy[i], hv[i]) for i in range(B)}
+        shard.gather_features(local_units, B * world, n, dist, torch.device("cuda", local))       # warm-up (NCCL channels)
+        barrier()
+        t0 = time.perf_counter()
+        gx, gy, gv = shard.gather_features(local_units, B * world, n, dist, torch.device("cuda", local))
+        barrier()
+        g_ms = (time.perf_counter() - t0) * 1e3
+        ok = bool(np.array_equal(gv[rank * B:(rank + 1) * B], np.asarray(hv)) and np.array_equal(gx[rank * B:(rank + 1) * B], np.asarray(hx)))
+        gather = {"call": "shard.gather_features: three all_reduce(SUM) over NCCL on fixed-size [units, n] tensors", "ms": round(g_ms, 3),
+                  "bytes_per_rank": B * n * 20, "units": B * world, "own_shard_intact": ok,
+                  "tracked_in_gathered_lists": int((gv == 0).sum())}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -384,17 +466,29 @@ def run_b200(args):
         roof["roofline_streaming"] = {k: round(v["gbps"] / peak, 4) for k, v in kernels.items() if k.startswith("stream_") and v["gbps"]}
     step_s = dev_ms * 1e-3 / args.steps
     e2e_s = e2e_ms * 1e-3 / e2e_steps
+    if args.precision == "windowed":
+        wb = windowed_bytes_per_pair(wl)[0]
+        pipeline = {"algorithmic_bytes_per_pair": wb, "accounting": "image-only pyramids: 5 B/px level 0 + decimations + the regions the tracker stages "
+                                                                      "(the dense-plane accounting of SURVEY 8(d) is under dense_planes)",
+                    "achieved_gbps": round(wb * B / step_s / 1e9, 1), "frac_of_hbm_peak": round(wb * B / step_s / 1e9 / peak, 4)}
+    else:
+        pipeline = {"algorithmic_bytes_per_pair": bytes_pair, "algorithmic_bytes_per_frame_build": bytes_frame, "lk_bytes_per_pair": bytes_lk,
+                    "accounting": "SURVEY 8(d): dense gradient planes", "achieved_gbps": round(bytes_pair * B / step_s / 1e9, 1),
+                    "frac_of_hbm_peak": round(bytes_pair * B / step_s / 1e9 / peak, 4)}
+    pipeline.update({"newton_iterations_per_pair": it.value / B, "tracked_fraction": tracked / float(B * n),
+                     "wall_ms_per_step": round(dev_wall / args.steps, 4)})
     out = {
         "metric": "tracked_features_per_sec", "value": round(tracked_all / step_s, 1), "unit": "tracked features/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision != "strict" else "f64-accumulate/f32",
         "data": "synthetic",
         "frame_pairs_per_sec": round(pairs_all / step_s, 2),
-        "config": {"workload": wl["name"], "pairs_per_step_per_gpu": B, "features_per_pair": n, "distinct_pairs": args.distinct,
-                   "precision": args.precision, "host_cpus_bound_per_rank": host_cpus, "parallelism": "independent frame pairs sharded %d-way, no collective" % world,
-                   "l2": "no flush needed: each step streams %.0f MB of pyramids per GPU (> 126 MB L2); inputs %.0f MB" %
-                         ((p1.nbytes() + p2.nbytes()) / 1e6, 2 * frame_bytes / 1e6)},
-        "e2e": {"value": round(e2e_tracked_all / e2e_s, 1), "unit": "tracked features/s",
+        "config": bench_config(wl),
+        "run": {"pairs_per_step_per_gpu": B, "distinct_pairs": args.distinct, "precision": args.precision,
+                "host_cpus_bound_per_rank": host_cpus, "parallelism": "independent frame pairs sharded %d-way, no collective" % world,
+                "l2": "no flush needed: each step streams %.0f MB of pyramids per GPU (> 126 MB L2); inputs %.0f MB" %
+                      ((p1.nbytes() + p2.nbytes()) / 1e6, 2 * frame_bytes / 1e6)},
+        "e2e": {"value": round(e2e_tracked_all / (e2e_ms * 1e-3), 1), "unit": "tracked features/s",
                 "frame_pairs_per_sec": round(pairs_all / e2e_s, 2), "ms_per_step": round(e2e_ms / e2e_steps, 4),
                 "h2d_bytes_per_step": 2 * frame_bytes + feat_bytes, "d2h_bytes_per_step": feat_bytes,
                 "api": "klt_track_pairs_u8 (C ABI) with pinned host frames and host feature arrays; two host threads with one "
@@ -407,30 +501,179 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": roof,
         "kernels": kernels,
-        "pipeline": {"algorithmic_bytes_per_pair": bytes_pair, "algorithmic_bytes_per_frame_build": bytes_frame,
-                     "lk_bytes_per_pair": bytes_lk, "achieved_gbps": round(bytes_pair * B / step_s / 1e9, 1),
-                     "frac_of_hbm_peak": round(bytes_pair * B / step_s / 1e9 / peak, 4),
-                     "accounting": "SURVEY 8(d): the reference's data flow with dense gradient planes"
-                                   + (" -- the windowed path never writes those planes, so this figure can exceed the HBM peak; "
-                                      "windowed_* is the traffic this path really needs" if args.precision == "windowed" else ""),
-                     "windowed_bytes_per_pair": windowed_bytes_per_pair(wl)[0] if args.precision == "windowed" else None,
-                     "windowed_achieved_gbps": round(windowed_bytes_per_pair(wl)[0] * B / step_s / 1e9, 1) if args.precision == "windowed" else None,
-                     "newton_iterations_per_pair": it.value / B, "tracked_fraction": tracked / float(B * n),
-                     "wall_ms_per_step": round(dev_wall / args.steps, 4)},
+        "pipeline": pipeline,
+        "sustained": {"value": round(tracked_all / (sus_ms * 1e-3 / sus_steps), 1), "unit": "tracked features/s", "steps": sus_steps,
+                      "seconds": round(sus_ms * 1e-3, 3), "ms_per_step": round(sus_ms / sus_steps, 4),
+                      "vs_burst": round((dev_ms / args.steps) / (sus_ms / sus_steps), 4), "clocks": sus_clocks},
     }
+    if dense is not None:
+        dense_ms, dense_tracked, dprof = dense
+        dtr = float(dense_tracked) * world        # rank 0's count stands for every rank (same workload shape)
+        out["dense_planes"] = {
+            "what": "the same step with KLT_PRECISION_FAST builds: gradient planes of every level written (the reference's data flow)",
+            "value": round(dtr / (dense_ms * 1e-3 / args.steps), 1), "unit": "tracked features/s",
+            "ms_per_step": round(dense_ms / args.steps, 4),
+            "algorithmic_bytes_per_pair": bytes_pair, "achieved_gbps": round(bytes_pair * B / (dense_ms * 1e-3 / args.steps) / 1e9, 1),
+            "frac_of_hbm_peak": round(bytes_pair * B / (dense_ms * 1e-3 / args.steps) / 1e9 / peak, 4),
+            "kernels": {k: {"ms_per_launch": round(v["ms"] / v["launches"], 5), "frac_of_hbm_peak": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak, 4) if v["bytes"] else None}
+                        for k, v in dprof.items() if v["launches"]}}
+    if seq is not None:
+        out["sequence"] = seq
+    if gather is not None:
+        out["gather"] = gather
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(wl, distinct, sel, budget_s=args.cpu_budget)
     if world == 1 and args.api_pairs > 0:
         out["api_single_pair"] = api_single_pair(wl, distinct, klt, sgf, trackFeatures, args.api_pairs)
         out["select"] = select_timing(wl, distinct, klt, sgf, ctx, args.api_pairs)
         out["sequence_api"] = sequence_timing(wl, klt, sgf, trackFeatures, max(6, args.api_pairs))
-        out["sequence_api_affine"] = sequence_timing(wl, klt, sgf, trackFeatures, max(6, args.api_pairs), affine=2)
+        out["config_E"] = sequence_timing(WORKLOADS["E"], klt, sgf, trackFeatures, max(6, args.api_pairs), affine=2)
+        out["config_E"]["workload"] = "E: 1080p sequence, 15x15 windows, affineConsistencyCheck=2 (6x6 solve per feature); parity of the affine block is against the in-repo restatement, the reference cannot run it"
+        out["config_C"] = config_c_timing(ctx, lib, _capi, klt, sgf, trackFeatures, peak)
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(out))
     sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
+
+
+def motion_cycle(H, W, seed, period=100):
+    """`period` uint8 frames of one textured scene following SURVEY 8(d)'s sequence trajectory (dy = 20 sin(2 pi k / 100),
+    dx = 20 cos(2 pi k / 100) - 20, sub-pixel, <= 1.26 px per frame); frame `period` would equal frame 0, so a sequence can
+    run around the cycle for any number of frames.  Bilinear sampling of one padded texture (cheap; the cubic generator of
+    the parity tests takes 0.15 s per 1080p frame)."""
+    import scipy.ndimage as ndi
+    rng = np.random.default_rng(seed)
+    pad = 48
+    t = rng.standard_normal((H + 2 * pad, W + 2 * pad)).astype(np.float32)
+    tex = ndi.gaussian_filter(t, 2.0) + 1.5 * ndi.gaussian_filter(t, 6.0)
+    lo, hi = float(tex.min()), float(tex.max())
+    tex = (tex - lo) * (255.0 / (hi - lo))
+    out = np.empty((period, H, W), np.uint8)
+    k = np.arange(period)
+    dy, dx = 20.0 * np.sin(2 * np.pi * k / period), 20.0 * np.cos(2 * np.pi * k / period) - 20.0
+    for i in range(period):
+        y0, x0 = pad - dy[i], pad - dx[i]
+        iy, ix = int(np.floor(y0)), int(np.floor(x0))
+        ay, ax = np.float32(y0 - iy), np.float32(x0 - ix)
+        a = tex[iy:iy + H + 1, ix:ix + W + 1]
+        f = (1 - ay) * ((1 - ax) * a[:-1, :-1] + ax * a[:-1, 1:]) + ay * ((1 - ax) * a[1:, :-1] + ax * a[1:, 1:])
+        np.clip(f + 0.5, 0, 255, out=f)
+        out[i] = f.astype(np.uint8)
+    return out
+
+
+def sequence_bench(ctx, lib, _capi, klt, sgf, tf, args, rank, world, local, barrier, reduce_max, reduce_sum, torch):
+    """BASELINE config D: per GPU `--seqs` independent 1080p sequences x `--seq-frames` frames in lock step, sequentialMode
+    tracking (one pyramid build per frame) + KLTReplaceLostFeatures every frame, through klt_sequence (one chain of launches
+    per step for all sequences, CUDA-graph replay, no host synchronisation).  Device-resident frames (`frames_per_sec`) and
+    host-fed (`e2e`: every step uploads its frames from pinned memory and downloads all feature lists)."""
+    if args.seqs <= 0 or args.seq_frames <= 0:
+        return None
+    wl = WORKLOADS["B"]
+    H, W, n = wl["H"], wl["W"], wl["n"]
+    S, F, period = args.seqs, args.seq_frames, 100
+    tc = tc_for(wl, klt)
+    tc.sequentialMode = True
+    params, taps = sgf.make_params(tc), tf._taps_for_one_image(tc)
+    ntex = min(2, S)
+    cycles = [motion_cycle(H, W, seed=5000 + 97 * rank + i, period=period) for i in range(ntex)]
+    host = ctx.pinned_array((period, S, H, W), np.uint8)       # step k of the batch: sequence s shows frame (k + phase_s) of its scene
+    for s_ in range(S):
+        phase = (s_ // ntex) * (period // max(1, (S + ntex - 1) // ntex))
+        host[:, s_] = np.roll(cycles[s_ % ntex], -phase, axis=0)
+    del cycles
+    step_bytes = S * H * W
+    dev = ctx.device_alloc(period * step_bytes)
+    ctx.memcpy(dev, host, period * step_bytes)
+    ctx.sync()
+    W_UP = 8                                                   # warm-up frames (graph capture happens on the 3rd and 4th)
+    res = {}
+
+    def run(prec, smode, seqs, frames, host_fed):
+        q = _capi.Sequence(ctx, params, taps, W, H, seqs, n, prec, smode)
+        stride = S * H * W                                     # a batch of `seqs` <= S sequences = the first `seqs` frames of a step
+        src = (lambda k: host[k % period][:seqs]) if host_fed else (lambda k: dev + (k % period) * stride)
+        outs = None
+        if host_fed:
+            outs = [tuple(ctx.pinned_array((seqs, n), dt) for dt in (np.float64, np.float64, np.int32, np.int32)) for _ in range(2)]
+        q.start(src(0))
+        for k in range(1, W_UP + 1):
+            q.step(src(k), out=outs[k & 1] if outs else None)
+        q.sync()
+        barrier()
+        l0 = ctx.launch_count()
+        tracked = 0
+        t0 = time.perf_counter()
+        ctx.timer_start()
+        for k in range(W_UP + 1, W_UP + 1 + frames):
+            if host_fed and k >= W_UP + 3:
+                ctx.check(lib.klt_async_wait(ctx.handle, k & 1))        # step k-2 has landed in outs[k & 1]: consume it
+                tracked += int((outs[k & 1][3] == 0).sum())
+            q.step(src(k), out=outs[k & 1] if outs else None)
+            if host_fed:
+                ctx.check(lib.klt_async_mark(ctx.handle, k & 1))
+        ctx.timer_stop()
+        ms = ctx.timer_elapsed_ms()
+        its = q.sync()
+        wall = (time.perf_counter() - t0) * 1e3
+        launches = ctx.launch_count() - l0
+        if host_fed:
+            for j in (0, 1):
+                tracked += int((outs[j][3] == 0).sum())
+        x, y, v, vt = q.features()
+        st = q.select_stats()
+        graph = q.uses_graph()
+        q.close()
+        barrier()
+        t = ms if not host_fed else wall                       # host-fed: wall clock (the region contains host work by design)
+        if reduce_max is not None:
+            tt = torch.tensor([t], device="cuda", dtype=torch.float64)
+            reduce_max(tt)
+            t = float(tt[0])
+        return dict(ms=t, frames=frames, seqs=seqs, launches=launches, graph=graph, iterations=its, tracked=tracked,
+                    tracked_frac_last=float((vt == 0).mean()), filled_frac_last=float((v >= 0).mean()),
+                    walk_consumed=float(st[:, 0].mean()), walk_fallbacks=int(st[:, 3].sum()))
+
+    fast = run(_capi.PRECISION_FAST_WINDOWED, _capi.SELECT_FAST, S, F, False)
+    e2e = run(_capi.PRECISION_FAST_WINDOWED, _capi.SELECT_FAST, S, F, True)
+    one = run(_capi.PRECISION_FAST_WINDOWED, _capi.SELECT_FAST, 1, F, False)
+    strict = run(_capi.PRECISION_STRICT, _capi.SELECT_STRICT, S, max(20, F // 5), False)
+    mixed = run(_capi.PRECISION_FAST_WINDOWED, _capi.SELECT_STRICT, S, max(20, F // 5), False)
+    ctx.device_free(dev)
+    tracked_e2e = float(e2e["tracked"])
+    if reduce_sum is not None:
+        tt = torch.tensor([tracked_e2e], device="cuda", dtype=torch.float64)
+        reduce_sum(tt)
+        tracked_e2e = float(tt[0])
+
+    def fps(r):
+        return round(world * r["seqs"] * r["frames"] / (r["ms"] * 1e-3), 1)
+    feat_per_frame = tracked_e2e / float(world * S * F)
+    return {
+        "workload": "D: %d independent 1080p sequences per GPU x %d frames, %d features, 3 levels, ss=2, 7x7, sequentialMode tracking + "
+                    "KLTReplaceLostFeatures every frame (synthetic scenes on the SURVEY 8(d) trajectory)" % (S, F, n),
+        "sequences_per_gpu": S, "frames": F, "n_gpus": world,
+        "mode": "windowed tracking (fast arithmetic) + fused fast selection",
+        "frames_per_sec": fps(fast), "ms_per_step": round(fast["ms"] / fast["frames"], 4),
+        "tracked_features_per_sec": round(fps(fast) * feat_per_frame, 1), "tracked_features_per_frame": round(feat_per_frame, 2),
+        "graph_replay": fast["graph"], "launches_per_step": fast["launches"] / float(fast["frames"]),
+        "newton_iterations_per_frame": fast["iterations"] / float(S * F),
+        "replacement_walk": {"candidates_consumed_per_frame": fast["walk_consumed"], "range_fallbacks_last_step": fast["walk_fallbacks"],
+                             "slots_filled_fraction": fast["filled_frac_last"]},
+        "e2e": {"frames_per_sec": fps(e2e), "ms_per_step": round(e2e["ms"] / e2e["frames"], 4),
+                "tracked_features_per_sec": round(tracked_e2e / (e2e["ms"] * 1e-3), 1),
+                "h2d_bytes_per_step": step_bytes, "d2h_bytes_per_step": S * n * (8 + 8 + 4 + 4),
+                "api": "klt_sequence_step_u8 with pinned host frames; lists (x, y, val, val_tracked) downloaded every step into two "
+                       "alternating pinned sets and consumed by the host two steps later (klt_async_mark / klt_async_wait); wall clock"},
+        "one_sequence_per_gpu": {"frames_per_sec": fps(one), "ms_per_frame": round(one["ms"] / one["frames"], 4),
+                                 "note": "BASELINE's literal sharding (one sequence per GPU): latency-bound, ~10 launches per frame from one graph"},
+        "strict": {"mode": "STRICT pyramids + exact-order tracker + STRICT selection: every list bit-identical to the reference's",
+                   "frames_per_sec": fps(strict), "ms_per_step": round(strict["ms"] / strict["frames"], 4), "frames": strict["frames"]},
+        "windowed_tracking_strict_selection": {"frames_per_sec": fps(mixed), "ms_per_step": round(mixed["ms"] / mixed["frames"], 4),
+                                               "frames": mixed["frames"]},
+    }
 
 
 def api_single_pair(wl, distinct, klt, sgf, tf, reps):
@@ -452,6 +695,52 @@ def api_single_pair(wl, distinct, klt, sgf, tf, reps):
             tracked = sum(1 for f in fl if f.val == 0)
     return {"call": "KLTTrackFeatures(tc, img1, img2, fl) with PIL images", "ms_per_pair": round(1e3 * float(np.mean(ts)), 3),
             "frame_pairs_per_sec": round(1.0 / float(np.mean(ts)), 1), "tracked_features_per_sec": round(tracked / float(np.mean(ts)), 1)}
+
+
+def config_c_timing(ctx, lib, _capi, klt, sgf, tf, peak, pairs=8, steps=6):
+    """BASELINE config C: synthetic 4K pairs, 10 000 features, 4 levels; device-resident, windowed tracking."""
+    wl = WORKLOADS["C"]
+    H, W, n, L, ss = wl["H"], wl["W"], wl["n"], wl["L"], wl["ss"]
+    tc = tc_for(wl, klt)
+    a, b = make_inputs(wl, 1, seed0=0)[0]
+    fl = sgf.KLTSelectGoodFeatures(tc, a, n)
+    x0 = np.tile(np.array([float(f.x) for f in fl]), (pairs, 1)); y0 = np.tile(np.array([float(f.y) for f in fl]), (pairs, 1))
+    v0 = np.tile(np.array([f.val for f in fl], np.int32), (pairs, 1))
+    taps, params = tf._taps_for_one_image(tc), sgf.make_params(tc)
+    fb = pairs * H * W
+    f1, f2 = np.ascontiguousarray(np.tile(a, (pairs, 1, 1))), np.ascontiguousarray(np.tile(b, (pairs, 1, 1)))
+    d1, d2 = ctx.device_alloc(fb), ctx.device_alloc(fb)
+    dx0, dy0, dv0 = ctx.device_alloc(pairs * n * 8), ctx.device_alloc(pairs * n * 8), ctx.device_alloc(pairs * n * 4)
+    dx, dy, dv = ctx.device_alloc(pairs * n * 8), ctx.device_alloc(pairs * n * 8), ctx.device_alloc(pairs * n * 4)
+    ctx.memcpy(d1, f1, fb); ctx.memcpy(d2, f2, fb)
+    ctx.memcpy(dx0, x0, pairs * n * 8); ctx.memcpy(dy0, y0, pairs * n * 8); ctx.memcpy(dv0, v0, pairs * n * 4)
+    p1, p2 = _capi.Pyramid(ctx, W, H, L, ss, pairs), _capi.Pyramid(ctx, W, H, L, ss, pairs)
+    ctx.sync()
+
+    def step():
+        ctx.memcpy(dx, dx0, pairs * n * 8); ctx.memcpy(dy, dy0, pairs * n * 8); ctx.memcpy(dv, dv0, pairs * n * 4)
+        ctx.check(lib.klt_pyr_build_u8(ctx.handle, p1.handle, d1, W, W * H, C.byref(taps), _capi.PRECISION_FAST_WINDOWED))
+        ctx.check(lib.klt_pyr_build_u8(ctx.handle, p2.handle, d2, W, W * H, C.byref(taps), _capi.PRECISION_FAST_WINDOWED))
+        ctx.check(lib.klt_track_features(ctx.handle, C.byref(params), p1.handle, p2.handle, n, dx, dy, dv, None))
+    for _ in range(3):
+        step()
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(steps):
+        step()
+    ctx.timer_stop()
+    ms = ctx.timer_elapsed_ms() / steps
+    hv = np.empty((pairs, n), np.int32)
+    ctx.memcpy(hv, dv, pairs * n * 4)
+    ctx.sync()
+    tracked = int((hv == 0).sum())
+    for d in (d1, d2, dx0, dy0, dv0, dx, dy, dv):
+        ctx.device_free(d)
+    p1.close(); p2.close()
+    wb = windowed_bytes_per_pair(wl)[0]
+    return {"workload": wl["name"], "pairs_per_step": pairs, "ms_per_step": round(ms, 4), "frame_pairs_per_sec": round(pairs / ms * 1e3, 1),
+            "tracked_features_per_sec": round(tracked / ms * 1e3, 1), "tracked_fraction": tracked / float(pairs * n),
+            "frac_of_hbm_peak": round(wb * pairs / (ms * 1e-3) / 1e9 / peak, 4), "precision": "windowed"}
 
 
 def _capi_sync():
@@ -648,7 +937,8 @@ def run_reference(args):
            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(1e3 * wall / steps, 2),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 accumulate in SciPy)",
            "data": "synthetic", "frame_pairs_per_sec": round(per_step * steps / wall, 3),
-           "config": {"workload": wl["name"], "pairs_per_step": per_step, "features_per_pair": wl["n"]},
+           "config": bench_config(wl),
+           "run": {"pairs_per_step": per_step, "processes": procs},
            "cpu_baseline": {"value": round(value, 1), "unit": "tracked features/s", "cores": procs, "kind": kind, "sample": sample},
            "e2e": {"value": round(value, 1), "unit": "tracked features/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -671,6 +961,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--api-pairs", type=int, default=10)
     ap.add_argument("--ref-procs", type=int, default=0)
+    ap.add_argument("--seqs", type=int, default=8, help="config D: lock-stepped sequences per GPU (0 disables the sequence object)")
+    ap.add_argument("--seq-frames", type=int, default=300)
+    ap.add_argument("--sustain-s", type=float, default=2.5, help="length of the sustained leg in seconds")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
