@@ -109,7 +109,9 @@ typedef struct klt_params {
     int32_t affine_window_width, affine_window_height;
     int32_t affine_max_iterations;
     float affine_max_residue, affine_min_displacement, affine_max_displacement_differ;
-    int32_t reserved[1];
+    float min_eigenvalue_f;       /* tc.min_eigenvalue when it is not an integer (the reference compares val >= min_eigenvalue in
+                                   * floating point, selectGoodFeatures.py:116): if > 0 it replaces min_eigenvalue; pass the smallest
+                                   * float32 >= the Python value */
 } klt_params;
 
 /* ---- library / context ------------------------------------------------------------------------- */
@@ -119,7 +121,10 @@ int klt_abi_version(void);
 int klt_ctx_create(int device, void *stream, klt_ctx **out);
 int klt_ctx_destroy(klt_ctx *ctx);
 const char *klt_last_error(const klt_ctx *ctx); /* ctx may be NULL: message of the last failed klt_ctx_create */
-int klt_sync(klt_ctx *ctx);                     /* cudaStreamSynchronize on the context's stream */
+/* cudaStreamSynchronize on the context's stream.  Returns KLT_ERR_ASSERT (once) if a call that returned without waiting --
+ * klt_track_features* on DEVICE arrays without n_iterations, klt_track_pairs_u8_async -- hit the reference's AssertionError
+ * case since the last klt_sync / klt_async_result. */
+int klt_sync(klt_ctx *ctx);
 void *klt_ctx_stream(klt_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t klt_launch_count(const klt_ctx *ctx);
@@ -213,7 +218,10 @@ int klt_eigen_map_batch(klt_ctx *ctx, const klt_params *params, klt_pyr *pyr, in
  * pyr1/pyr2: pyramids of the first/second images (same geometry and batch).  x, y, val: [batch][n_per_image]
  * host or device arrays, updated in place exactly like the reference mutates the feature list
  * (lost features: x=y=-1, val=status; tracked: val=0).  Features with val < 0 are skipped.
- * n_iterations (optional, host): total Newton iterations executed. */
+ * n_iterations (optional, host): total Newton iterations executed.
+ * Host arrays (or n_iterations != NULL): the call waits and returns KLT_ERR_ASSERT where the reference raises AssertionError
+ * (a window leaves the image at some level, trackFeaturesUtils.pyx:35).  Device arrays with n_iterations == NULL: the call only
+ * enqueues; that condition is then reported by the next klt_sync / klt_async_result on the context. */
 int klt_track_features(klt_ctx *ctx, const klt_params *params, const klt_pyr *pyr1, const klt_pyr *pyr2,
                        int n_per_image, double *x, double *y, int32_t *val, int64_t *n_iterations);
 /* ---- affine consistency check: the block at trackFeatures.py:347-399.  The reference's callees there
@@ -255,7 +263,7 @@ int klt_patch_combine(klt_ctx *ctx, const float *patch1, const float *img2, int 
 /* _enforceMinimumDistance(pointlist, featurelist, ncols, nrows, mindist, min_eigenvalue, overwriteAllFeatures)
  * (selectGoodFeatures.py:45-135) on a caller-ordered candidate list (host arrays, walked front to back) */
 int klt_enforce_min_distance(klt_ctx *ctx, int n_points, const float *pval, const int32_t *px, const int32_t *py,
-                             int ncols, int nrows, int mindist, int min_eigenvalue, int overwrite_all, int n_features,
+                             int ncols, int nrows, int mindist, double min_eigenvalue, int overwrite_all, int n_features,
                              double *x, double *y, int32_t *val);
 
 /* ---- whole-call convenience: KLTTrackFeatures(tc, img1, img2, fl) for `batch` independent frame pairs with

@@ -56,7 +56,7 @@ def lib():
         L.orc_scan_good_features.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                              fp, ip, ip]
         L.orc_select_from_scan.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                           C.c_int, C.c_int, C.c_int, dp, dp, ip]
+                                           C.c_double, C.c_int, C.c_int, dp, dp, ip]
         L.orc_select_from_scan.restype = C.c_long
         pp = C.POINTER(fp)
         L.orc_track_features.argtypes = [C.POINTER(_TrackParams), pp, pp, pp, pp, pp, pp, ip, ip, C.c_int, dp, dp, ip]
@@ -300,7 +300,7 @@ def select_from_gradients(p, gx, gy, n_features, existing=None):
         fv = np.array(existing[2], np.int32)
         overwrite = 0
     used = lib().orc_select_from_scan(_f(val), len(xs), len(ys), bx, by, p.nSkippedPixels, W, H, mindist,
-                                      int(p.min_eigenvalue), overwrite, n_features, _d(fx), _d(fy), _i(fv))
+                                      float(p.min_eigenvalue), overwrite, n_features, _d(fx), _d(fy), _i(fv))
     assert used >= 0
     return fx, fy, fv, used
 
@@ -317,7 +317,7 @@ def select_from_map(p, val, W, H, n_features):
     fy = np.full(n_features, -1.0)
     fv = np.full(n_features, KLT_NOT_FOUND, np.int32)
     used = lib().orc_select_from_scan(_f(val), val.shape[1], val.shape[0], bx, by, p.nSkippedPixels, W, H, max(p.mindist, 0),
-                                      int(p.min_eigenvalue), 1, n_features, _d(fx), _d(fy), _i(fv))
+                                      float(p.min_eigenvalue), 1, n_features, _d(fx), _d(fy), _i(fv))
     assert used >= 0
     return fx, fy, fv
 

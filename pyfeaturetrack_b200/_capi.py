@@ -1,7 +1,9 @@
 """ctypes binding of libkltb200.so (include/klt_b200.h).  There is no CPU fallback: if the CUDA library is
 missing or no B200 is present, every entry point raises."""
 import ctypes as C
+import functools
 import os
+import threading
 
 import numpy as np
 
@@ -49,10 +51,24 @@ class Params(C.Structure):
                 ("affine_consistency_check", C.c_int32), ("affine_window_width", C.c_int32),
                 ("affine_window_height", C.c_int32), ("affine_max_iterations", C.c_int32),
                 ("affine_max_residue", C.c_float), ("affine_min_displacement", C.c_float),
-                ("affine_max_displacement_differ", C.c_float), ("reserved", C.c_int32 * 1)]
+                ("affine_max_displacement_differ", C.c_float), ("min_eigenvalue_f", C.c_float)]
 
 
 _lib = None
+
+# The drop-in modules share ONE process-wide context (stream, workspace, scratch pyramids): like the reference under the GIL,
+# their entry points run one at a time.  ctypes releases the GIL during the C calls, so the serialisation is explicit.
+# Explicit Context objects are not covered: a klt_ctx is single-threaded, distinct contexts may run concurrently.
+api_lock = threading.RLock()
+
+
+def serialized(fn):
+    @functools.wraps(fn)
+    def wrapper(*a, **kw):
+        with api_lock:
+            return fn(*a, **kw)
+    return wrapper
+
 
 # name -> (restype, argtypes); every symbol include/klt_b200.h declares
 _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
@@ -106,7 +122,7 @@ SIGNATURES = {
     "klt_track_iterate": (_i, [_vp, C.POINTER(Params), C.c_float, C.c_float, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i,
                                C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "klt_patch_combine": (_i, [_vp, _fp, _fp, _i, _i, C.c_float, C.c_float, _i, _i, _i, _fp]),
-    "klt_enforce_min_distance": (_i, [_vp, _i, _fp, _ip, _ip, _i, _i, _i, _i, _i, _i, _dp, _dp, _ip]),
+    "klt_enforce_min_distance": (_i, [_vp, _i, _fp, _ip, _ip, _i, _i, _i, C.c_double, _i, _i, _dp, _dp, _ip]),
     "klt_track_pairs_u8": (_i, [_vp, C.POINTER(Params), C.POINTER(Taps), _i, _vp, _vp, _u8p, _u8p, _sz, _sz, _i,
                                 _dp, _dp, _ip]),
     "klt_track_pairs_u8_async": (_i, [_vp, C.POINTER(Params), C.POINTER(Taps), _i, _vp, _vp, _u8p, _u8p, _sz, _sz, _i,
@@ -384,12 +400,19 @@ class Context:
         return p
 
     def pinned_stage(self, shape, key):
-        """A reusable pinned uint8 staging buffer of the given shape (one per key, e.g. per scratch pyramid)."""
+        """A reusable pinned uint8 staging buffer of the given shape (one per key, e.g. per scratch pyramid).  Buffers that
+        are replaced or evicted are handed back to the driver (after a sync: an upload may still be reading them)."""
         st = self.__dict__.setdefault("_stages", {})
         buf = st.get(key)
         if buf is None or buf.shape != tuple(shape):
+            stale = [buf] if buf is not None else []
             if len(st) > 8:
+                stale += [b for b in st.values() if b is not buf]
                 st.clear()
+            if stale:
+                self.sync()
+                for b in stale:
+                    self.free_pinned(b)
             buf = st[key] = self.pinned_array(tuple(shape), np.uint8)
         return buf
 
@@ -405,12 +428,20 @@ class Context:
         return p.value
 
     def pinned_array(self, shape, dtype):
-        """numpy array over pinned host memory (freed with the process)."""
+        """numpy array over pinned host memory; free_pinned(array) or close() returns it to the driver."""
         dtype = np.dtype(dtype)
         n = int(np.prod(shape)) * dtype.itemsize
         addr = self.host_alloc(max(n, 1))
         buf = (C.c_char * max(n, 1)).from_address(addr)
-        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self.__dict__.setdefault("_pinned", {})[arr.ctypes.data] = addr
+        return arr
+
+    def free_pinned(self, arr):
+        """Hands a pinned_array's memory back (the caller must not touch the array afterwards)."""
+        addr = self.__dict__.get("_pinned", {}).pop(arr.ctypes.data, None)
+        if addr is not None:
+            lib().klt_host_free(addr)
 
     def device_alloc(self, nbytes):
         p = C.c_void_p()
@@ -428,6 +459,11 @@ class Context:
             for p in self._pyr_cache.values():
                 p.close()
             self._pyr_cache.clear()
+            lib().klt_sync(self.handle)
+            self.__dict__.get("_stages", {}).clear()
+            for addr in self.__dict__.get("_pinned", {}).values():
+                lib().klt_host_free(addr)
+            self.__dict__.get("_pinned", {}).clear()
             lib().klt_ctx_destroy(self.handle)
             self.handle = None
 

@@ -105,6 +105,7 @@ def _as_f32_image(img):
     return np.ascontiguousarray(a, np.float32)
 
 
+@_capi.serialized
 def _convolveSeparate(imgin, horiz_kernel, vert_kernel, precision=None):
     """imgout = vert(horiz(imgin)), reflect borders, float32 between the passes (convolve.py:208-214)."""
     ctx = _capi.default_ctx()
@@ -117,6 +118,7 @@ def _convolveSeparate(imgin, horiz_kernel, vert_kernel, precision=None):
     return out
 
 
+@_capi.serialized
 def KLTComputeGradients(img, sigma):
     """(gradx, grady) = (deriv_h o gauss_v, gauss_h o deriv_v) (convolve.py:226-248)."""
     gauss_kernel, gaussderiv_kernel = _kernels_for_gradients(sigma)
@@ -129,6 +131,7 @@ def KLTComputeGradients(img, sigma):
     return gradx, grady
 
 
+@_capi.serialized
 def KLTComputeSmoothedImage(img, sigma):
     """gauss_h o gauss_v (convolve.py:254-264)."""
     gauss, _ = _kernels_for_smoothing(sigma)

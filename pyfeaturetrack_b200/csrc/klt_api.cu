@@ -175,6 +175,15 @@ const char *klt_last_error(const klt_ctx *ctx) { return ctx ? ctx->err.c_str() :
 int klt_sync(klt_ctx *ctx) {
     if (!ctx) return KLT_ERR_INVALID;
     KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->async_flag_dev) {      // the sticky flag of calls that returned without waiting (see klt_track_features)
+        int flag = 0;
+        KLT_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->async_flag_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        KLT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (flag) {
+            KLT_CUDA(ctx, cudaMemsetAsync(ctx->async_flag_dev, 0, sizeof(int), ctx->stream));
+            return klt_fail(ctx, KLT_ERR_ASSERT, "a feature window left the image at a pyramid level in a call that did not wait for its result: the reference raises AssertionError (trackFeaturesUtils.pyx:35)");
+        }
+    }
     return KLT_OK;
 }
 void *klt_ctx_stream(klt_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
@@ -582,7 +591,11 @@ static int track_impl(klt_ctx *ctx, const klt_params *params, const klt_pyr *pyr
     if ((rc = klt_ws_reserve(ctx, 6 * fbytes + 256))) return rc;
     char *wsp = (char *)ctx->ws;
     unsigned long long *iters = (unsigned long long *)wsp;
-    int *aflag = async ? ctx->async_flag_dev : (int *)(wsp + 8);     // asynchronous calls share one sticky flag
+    // calls that return without reading the flag back (asynchronous, or device arrays without n_iterations) raise the context's
+    // sticky flag instead: klt_sync / klt_async_result report it
+    const bool deferred = async || (!host && !n_iterations);
+    if (deferred && !ctx->async_flag_dev) return klt_fail(ctx, KLT_ERR_NOMEM, "the context has no status word");
+    int *aflag = deferred ? ctx->async_flag_dev : (int *)(wsp + 8);
     double *dx = x, *dy = y;
     int32_t *dval = val;
     KLT_CUDA(ctx, cudaMemsetAsync(wsp, 0, 16, ctx->stream));
@@ -778,18 +791,18 @@ int klt_patch_combine(klt_ctx *ctx, const float *patch1, const float *img2, int 
 }
 
 int klt_enforce_min_distance(klt_ctx *ctx, int n_points, const float *pval, const int32_t *px, const int32_t *py, int ncols,
-                             int nrows, int mindist, int min_eigenvalue, int overwrite_all, int n_features, double *x,
+                             int nrows, int mindist, double min_eigenvalue, int overwrite_all, int n_features, double *x,
                              double *y, int32_t *val) {
     if (!ctx || n_points < 0 || (n_points && (!pval || !px || !py)) || !x || !y || !val || n_features < 0)
         return klt_fail(ctx, KLT_ERR_INVALID, "bad argument");
     KLT_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (min_eigenvalue < 1) min_eigenvalue = 1;                       // selectGoodFeatures.py:53
+    if (!(min_eigenvalue >= 1.0)) min_eigenvalue = 1.0;               // selectGoodFeatures.py:53
     std::vector<unsigned long long> keys;
     keys.reserve((size_t)n_points);
     for (int i = 0; i < n_points; i++) {
         if (px[i] < 0 || px[i] >= ncols || py[i] < 0 || py[i] >= nrows)
             return klt_fail(ctx, KLT_ERR_ASSERT, "candidate %d out of bounds (selectGoodFeatures.py:104-107)", i);
-        if (!(pval[i] >= (float)min_eigenvalue)) continue;           // can never be accepted (:116); skipping keeps the walk order
+        if (!((double)pval[i] >= min_eigenvalue)) continue;          // can never be accepted (:116, compared as numbers); skipping keeps the walk order
         unsigned int bits;
         memcpy(&bits, &pval[i], 4);
         keys.push_back(~(((unsigned long long)bits << 26) | ((unsigned long long)px[i] << 13) | (unsigned long long)py[i]));

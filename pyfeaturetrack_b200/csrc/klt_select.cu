@@ -728,7 +728,8 @@ int klt_sel_geometry(klt_ctx *ctx, const klt_params *p, int w, int h, int n_feat
     S->r = r; S->cs = r >= 0 ? r + 1 : 1; S->gw = (w + S->cs - 1) / S->cs; S->gh = (h + S->cs - 1) / S->cs;
     S->n_features = n_features; S->replace = replace ? 1 : 0;
     // :53 (min_eigenvalue < 1 -> 1) and :116 (val >= min_eigenvalue, a float/int comparison in the reference)
-    S->min_val = p->min_eigenvalue < 1 ? 1.0f : (float)p->min_eigenvalue;
+    S->min_val = p->min_eigenvalue_f > 0.f ? p->min_eigenvalue_f : (float)p->min_eigenvalue;
+    if (!(S->min_val >= 1.0f)) S->min_val = 1.0f;
     S->ncand = (size_t)nx * ny;
     S->key_stride = align_up(S->ncand + 1, 32);
     S->map_stride = align_up((size_t)w * h, 256);

@@ -14,6 +14,7 @@ def _check_f32_2d(a, name):
         raise ValueError("Buffer dtype mismatch, expected 'float32_t' but got '%s'" % a.dtype.name)
 
 
+@_capi.serialized
 def scan_values(gradxArr, gradyArr, borderx, bordery, window_hw, window_hh, nSkippedPixels):
     """The min-eigenvalue map as arrays: (xs int32[nx], ys int32[ny], val float32[ny, nx])."""
     _check_f32_2d(gradxArr, "gradxArr")

@@ -26,6 +26,7 @@ class KLTPyramid:
             ncols /= subsampling      # true division: floats from level 1 on, as in the reference under Python 3
             nrows /= subsampling
 
+    @_capi.serialized
     def Compute(self, img, sigma_fact):
         """Level 0 is `img` itself (no copy, quirk Q9); level i = smooth(level i-1, ss*sigma_fact) sampled at
         (ss*y + ss/2, ss*x + ss/2) (pyramid.py:37-77)."""

@@ -49,6 +49,13 @@ def make_params(tc):
     p.n_levels, p.subsampling = int(tc.nPyramidLevels), int(tc.subsampling)
     p.borderx, p.bordery = float(tc.borderx), float(tc.bordery)
     p.mindist, p.min_eigenvalue = int(tc.mindist), int(tc.min_eigenvalue)
+    if tc.min_eigenvalue != int(tc.min_eigenvalue):
+        # val >= tc.min_eigenvalue is a float32-vs-Python-float comparison in the reference (selectGoodFeatures.py:116): for a
+        # float32 val it equals val >= (the smallest float32 that is >= the Python value)
+        m = np.float32(tc.min_eigenvalue)
+        if float(m) < float(tc.min_eigenvalue):
+            m = np.nextafter(m, np.float32(np.inf))
+        p.min_eigenvalue_f = float(m)
     p.n_skipped_pixels = int(tc.nSkippedPixels)
     p.max_iterations = int(tc.max_iterations)
     p.min_determinant, p.min_displacement, p.step_factor = tc.min_determinant, tc.min_displacement, tc.step_factor
@@ -110,6 +117,7 @@ def _scatter(featurelist, x, y, val, old_val, overwriteAllFeatures):
             d.update(_AFFINE_RESET)
 
 
+@_capi.serialized
 def _enforceMinimumDistance(pointlist, featurelist, ncols, nrows, mindist, min_eigenvalue, overwriteAllFeatures):
     """Greedy minimum-distance suppression over a caller-ordered list of (val, x, y) tuples (selectGoodFeatures.py:45-135),
     on the GPU (klt_enforce_min_distance).  Mutates and returns featurelist."""
@@ -121,7 +129,7 @@ def _enforceMinimumDistance(pointlist, featurelist, ncols, nrows, mindist, min_e
     px = np.ascontiguousarray([p[1] for p in pointlist], np.int32)
     py = np.ascontiguousarray([p[2] for p in pointlist], np.int32)
     ctx.check(_capi.lib().klt_enforce_min_distance(ctx.handle, len(pointlist), pv.ctypes.data, px.ctypes.data, py.ctypes.data,
-                                                  int(ncols), int(nrows), int(mindist), int(min_eigenvalue),
+                                                  int(ncols), int(nrows), int(mindist), float(min_eigenvalue),
                                                   1 if overwriteAllFeatures else 0, n, x.ctypes.data, y.ctypes.data,
                                                   val.ctypes.data))
     _scatter(featurelist, x, y, val, old_val, overwriteAllFeatures)
@@ -155,6 +163,7 @@ def _selection_pyramid(tc, img):
     return pyr
 
 
+@_capi.serialized
 def _KLTSelectGoodFeatures(tc, img, nFeatures, mode, featurelist=None):
     overwriteAllFeatures = (mode == selectionMode.SELECTING_ALL)
     if featurelist is None:

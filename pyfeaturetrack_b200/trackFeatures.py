@@ -69,9 +69,13 @@ def _build_pyramids(tc, img, pyr):
     return _PyramidSet(pyr)
 
 
+@_capi.serialized
 def ComputeImagePyramids(tc, img1, img2):
     """-> pyramid1, pyramid1_gradx, pyramid1_grady, pyramid2, pyramid2_gradx, pyramid2_grady (trackFeatures.py:146-196).
-    The pyramids live on the device; `.img[i]` downloads a level on demand."""
+    The pyramids live on the device; `.img[i]` downloads a level on demand.  They are VIEWS of device memory this module
+    recycles: outside sequentialMode the context's two scratch pyramids are rebuilt by the next call, in sequentialMode the
+    pyramid of frame k-1 becomes the build target of frame k+1.  Copy the levels you want to keep (np.array(p.img[i]))
+    before the next KLTTrackFeatures call; the reference returns independent arrays."""
     ctx = _capi.default_ctx()
     ncols, nrows = _image_size(img1)
     L, ss = int(tc.nPyramidLevels), int(float(tc.subsampling))
@@ -150,6 +154,7 @@ def _clear_affine(feat):
     feat.aff_img_grady = None
 
 
+@_capi.serialized
 def KLTTrackFeatures(tc, img1, img2, featurelist):
     assert _image_size(img1) == _image_size(img2)
     ncols, nrows = _image_size(img1)
@@ -220,5 +225,5 @@ def KLTTrackFeatures(tc, img1, img2, featurelist):
 
     if KLT_verbose >= 1:
         print("\n\t{0} features successfully tracked.".format(KLTCountRemainingFeatures(featurelist)))
-        if tc.writeInternalImages:
-            print("\tWrote images to 'kltimg_tf*.pgm'.")
+        # (tc.writeInternalImages: the reference's dumps crash here -- it calls PIL's .save on ndarrays, trackFeatures.py:186-196 --
+        # and this build keeps the pyramids on the device; tc.pyramid_last.img[i] downloads a level for whoever wants a dump)

@@ -7,6 +7,7 @@ from . import _capi
 from .goodFeaturesUtils import _check_f32_2d
 
 
+@_capi.serialized
 def extractImagePatchSlow(img, x, y, height, width):
     """Bilinear (height x width) patch centred at fractional (x, y) (trackFeaturesUtils.pyx:14-51).
     Raises AssertionError when the window leaves the image, like the reference (:35)."""
@@ -25,6 +26,7 @@ def _params_from_tc(tc):
     return make_params(tc)
 
 
+@_capi.serialized
 def trackFeatureIterateCKLT(x2, y2, img1GradxPatch, img1GradyPatch, img1Patch, img2, gradx2, grady2, tc):
     """The Newton loop of one feature on caller-provided template patches (trackFeaturesUtils.pyx:393-459).
     -> (x2, y2, status, iteration) with x2, y2 Python floats holding float32 values."""
@@ -46,6 +48,7 @@ def trackFeatureIterateCKLT(x2, y2, img1GradxPatch, img1GradyPatch, img1Patch, i
     return ox.value, oy.value, st.value, it.value
 
 
+@_capi.serialized
 def _patch_combine(patch1, img2, x2, y2, workingPatch, mode):
     _check_f32_2d(patch1, "img1Patch")
     _check_f32_2d(img2, "img2")

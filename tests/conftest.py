@@ -21,6 +21,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_fullsize():
+    """Reference outputs at BASELINE's own sizes (tests/golden/make_golden_fullsize.py)."""
+    return np.load(os.path.join(GOLDEN_DIR, "reference_golden_fullsize.npz"))
+
+
+@pytest.fixture(scope="session")
 def img01():
     from PIL import Image
     return (np.array(Image.open(os.path.join(GOLDEN_DIR, "img0.pgm"))),

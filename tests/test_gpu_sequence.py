@@ -168,6 +168,37 @@ def test_dropin_select_and_replace_use_the_batch_chain(gpu_ctx, oracle):
         eq(got, want)
 
 
+def test_fractional_min_eigenvalue_and_sticky_assert_flag(gpu_ctx, oracle):
+    """(1) tc.min_eigenvalue = k + 0.5 cuts where the reference's float comparison cuts (not at int(k + 0.5));
+    (2) klt_track_features on DEVICE arrays without n_iterations does not wait: a window that leaves the image (the reference's
+    AssertionError, trackFeaturesUtils.pyx:35) is reported by the next klt_sync."""
+    from pyfeaturetrack_b200 import _capi, synth, selectGoodFeatures as sgf, trackFeatures as tf
+    img = synth.frames(240, 320, [(0.0, 0.0)], seed=17)[0]
+    x, y, v = oracle.select_good_features(oracle.Params(), img, 400)
+    found = np.sort(v[v > 0])
+    cut = float(found[len(found) // 2]) + 0.5
+    tc = make_tc(min_eigenvalue=cut)
+    fl = sgf.KLTSelectGoodFeatures(tc, img, 400)
+    got = (np.array([float(a.x) for a in fl]), np.array([float(a.y) for a in fl]), np.array([int(a.val) for a in fl]))
+    eq(got, oracle.select_good_features(oracle.Params(min_eigenvalue=cut), img, 400))
+    assert (got[2] == -1).any()
+    # sticky flag
+    tc = make_tc()
+    pyr = build_batch(gpu_ctx, tc, [img], _capi.PRECISION_FAST)
+    n = 4
+    hx, hy, hv = np.array([160.0, 2.0, 100.0, 50.0]), np.array([120.0, 2.0, 80.0, 60.0]), np.zeros(n, np.int32)    # feature 1 sits in the border
+    dx, dy, dv = gpu_ctx.device_alloc(n * 8), gpu_ctx.device_alloc(n * 8), gpu_ctx.device_alloc(n * 4)
+    gpu_ctx.memcpy(dx, hx, n * 8); gpu_ctx.memcpy(dy, hy, n * 8); gpu_ctx.memcpy(dv, hv, n * 4)
+    params = sgf.make_params(tc)
+    gpu_ctx.check(_capi.lib().klt_track_features(gpu_ctx.handle, C.byref(params), pyr.handle, pyr.handle, n, dx, dy, dv, None))
+    with pytest.raises(AssertionError):
+        gpu_ctx.sync()
+    gpu_ctx.sync()                       # reported once
+    for d in (dx, dy, dv):
+        gpu_ctx.device_free(d)
+    pyr.close()
+
+
 # ---- fused fast eigenvalue pass ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape,kw", [((480, 640), dict(nPyramidLevels=2, subsampling=2)),
                                       ((243, 325), dict(nSkippedPixels=2)),
@@ -382,3 +413,37 @@ def test_sequence_fast_modes_track_the_strict_sequence(gpu_ctx, oracle):
         alive_ref = np.mean([(want[s][k][3] == 0).sum() for k in range(1, nfr)])
         assert abs(alive_fast - alive_ref) <= 0.01 * n, (alive_fast, alive_ref)
         assert (got[-1][2][s] >= 0).all()
+
+
+# ---- the reference's own outputs at BASELINE's sizes (tests/golden/reference_golden_fullsize.npz) ------------------------------
+def test_fullsize_goldens_config_B_and_C(gpu_ctx, golden_fullsize):
+    """Drop-in API, STRICT: selection and tracking at 1080p / 1000 features and 4K / 10 000 features == the arrays the unmodified
+    reference produced (positions, values and status codes compared with ==)."""
+    from pyfeaturetrack_b200 import synth, selectGoodFeatures as sgf, trackFeatures as tf, config
+    config.set_precision(track="strict", select="strict")
+    for (H, W, n, L, key) in ((1080, 1920, 1000, 3, "B"), (2160, 3840, 10000, 4, "C")):
+        imgs = synth.frame_pair(H, W, seed=0)
+        tc = make_tc(nPyramidLevels=L, subsampling=2, max_residue=10.0)
+        fl = sgf.KLTSelectGoodFeatures(tc, imgs[0], n)
+        got = (np.array([float(a.x) for a in fl]), np.array([float(a.y) for a in fl]), np.array([int(a.val) for a in fl]))
+        eq(got, golden_fullsize["%s_sel%d" % (key, n)])
+        tf.KLTTrackFeatures(tc, imgs[0], imgs[1], fl)
+        got = (np.array([float(a.x) for a in fl]), np.array([float(a.y) for a in fl]), np.array([int(a.val) for a in fl]))
+        eq(got, golden_fullsize["%s_trk%d" % (key, n)])
+
+
+def test_fullsize_golden_config_D_sequence(gpu_ctx, golden_fullsize):
+    """klt_sequence, STRICT + STRICT, on the 1080p sequence of the golden file: after every frame the lists equal the
+    reference's (tracking result = val_tracked + positions of the tracked features; after replacement = x, y, val)."""
+    from pyfeaturetrack_b200 import _capi, synth
+    g = golden_fullsize["D_seq1000"]
+    nfr = 5
+    shifts = [(s[0] * 6, s[1] * 6) for s in synth.sequence_shifts(nfr)]
+    frames = synth.frames(1080, 1920, shifts, seed=101)
+    tc = make_tc(nPyramidLevels=3, subsampling=2, max_residue=10.0, sequentialMode=True)
+    got, _ = _run_sequence(gpu_ctx, tc, [frames, frames], 1000, _capi.PRECISION_STRICT, _capi.SELECT_STRICT)
+    for s in range(2):
+        eq((got[0][0][s], got[0][1][s], got[0][2][s]), g[0])
+        for k in range(1, nfr):
+            assert np.array_equal(got[k][3][s], g[2 * k - 1][2].astype(np.int32))          # status codes after tracking
+            eq((got[k][0][s], got[k][1][s], got[k][2][s]), g[2 * k])                        # lists after replacement

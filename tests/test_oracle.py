@@ -209,6 +209,125 @@ def test_live_reference_random_configs(oracle, reference):
         assert_features_equal(trk, ([float(f.x) for f in ref_fl], [float(f.y) for f in ref_fl], [f.val for f in ref_fl]))
 
 
+def test_oracle_equals_fullsize_goldens(oracle, golden_fullsize):
+    """Config B (1080p) selection + tracking and config D's sequence with replacement against the reference's committed outputs
+    (the 4K arrays are checked by the GPU suite and by test_live_reference_full_size; the scalar oracle needs ~1 min at 4K)."""
+    from pyfeaturetrack_b200 import synth
+    g = golden_fullsize
+    imgs = synth.frame_pair(1080, 1920, seed=0)
+    p = P(oracle, nPyramidLevels=3, subsampling=2, max_residue=10.0)
+    sel = oracle.select_good_features(p, imgs[0], 1000)
+    assert_features_equal(sel, g["B_sel1000"])
+    assert_features_equal(oracle.track_features(p, imgs[0], imgs[1], *sel)[:3], g["B_trk1000"])
+    nfr = 3
+    shifts = [(s[0] * 6, s[1] * 6) for s in synth.sequence_shifts(5)][:nfr]
+    frames = synth.frames(1080, 1920, shifts, seed=101)
+    p = P(oracle, nPyramidLevels=3, subsampling=2, max_residue=10.0, sequentialMode=True)
+    x, y, v = oracle.select_good_features(p, frames[0], 1000)
+    assert_features_equal((x, y, v), g["D_seq1000"][0])
+    state = {}
+    for k in range(1, nfr):
+        x, y, v, _ = oracle.track_features(p, frames[k - 1], frames[k], x, y, v, state)
+        assert_features_equal((x, y, v), g["D_seq1000"][2 * k - 1])
+        _, gxs, gys = state["pyramid_last"]
+        x, y, v, _ = oracle.select_from_gradients(p, gxs[0], gys[0], 1000, existing=(x, y, v))
+        assert_features_equal((x, y, v), g["D_seq1000"][2 * k])
+
+
+def test_live_reference_fractional_min_eigenvalue(oracle, reference):
+    """tc.min_eigenvalue is compared as a number, not truncated (selectGoodFeatures.py:53,116): the reference's own
+    _enforceMinimumDistance with a threshold of k + 0.5 rejects the candidates whose value is exactly k."""
+    from pyfeaturetrack_b200 import synth
+    klt, sgf = reference["klt"], reference["selectGoodFeatures"]
+    img = synth.frames(240, 320, [(0.0, 0.0)], seed=17)[0]
+    p0 = P(oracle)
+    f = oracle.smooth(img.astype(np.float32), p0.smooth_sigma(), p0.cache)
+    gx, gy = oracle.gradients(f, p0.grad_sigma, p0.cache)
+    bx = int(p0.borderx)
+    val, xs, ys = oracle.scan_good_features(gx, gy, bx, bx, 3, 3, 0)
+    # integer-valued eigenvalues make the point: with cut = k + 0.5 a value of exactly k must be rejected, int(cut) = k would accept it
+    val = np.floor(val).astype(np.float32)
+    x, y, v, _ = oracle.select_from_gradients(p0, gx, gy, 300)
+    cut = float(np.sort(v[v > 0])[150]) + 0.5
+    pts = [(float(val[j, i]), int(xs[i]), int(ys[j])) for j in range(len(ys)) for i in range(len(xs))]
+    pts.sort()
+    pts.reverse()
+    fl = []
+    for _ in range(300):
+        ft = klt.KLT_Feature()
+        ft.x, ft.y, ft.val = -1.0, -1.0, -1
+        fl.append(ft)
+    sgf._enforceMinimumDistance(pts, fl, 320, 240, 10, cut, True)
+    p = P(oracle, min_eigenvalue=cut)
+    got = oracle.select_from_map(p, val, 320, 240, 300)
+    assert_features_equal(got, ([float(t.x) for t in fl], [float(t.y) for t in fl], [t.val for t in fl]))
+    assert (got[2] == -1).any() and got[2][got[2] > 0].min() > cut
+
+
+@pytest.mark.parametrize("cfg", ["B", "C"])
+def test_live_reference_full_size(oracle, reference, cfg):
+    """The oracle against the unmodified reference at BASELINE's own sizes -- config B (1080p, 1000 features, 3 levels) selection
+    + tracking and config C (4K, 10 000 features, 4 levels) selection: the float32 summed-area-table rounding grows with the
+    image size, so this is the case that pins the selection ORDER.  Bit-identical (==)."""
+    from PIL import Image
+    from pyfeaturetrack_b200 import synth
+    klt, sgf, tf = reference["klt"], reference["selectGoodFeatures"], reference["trackFeatures"]
+    H, W, n, L = (1080, 1920, 1000, 3) if cfg == "B" else (2160, 3840, 10000, 4)
+    imgs = synth.frame_pair(H, W, seed=0)
+    kw = dict(nPyramidLevels=L, subsampling=2, max_residue=10.0)
+    tc = klt.KLT_TrackingContext()
+    for k, v in kw.items():
+        setattr(tc, k, v)
+    tc.KLTUpdateTCBorder()
+    p = P(oracle, **kw)
+    assert p.borderx == tc.borderx
+    ref_fl = sgf.KLTSelectGoodFeatures(tc, Image.fromarray(imgs[0]), n)
+    sel = oracle.select_good_features(p, imgs[0], n)
+    assert_features_equal(sel, ([float(f.x) for f in ref_fl], [float(f.y) for f in ref_fl], [f.val for f in ref_fl]))
+    if cfg == "B":        # (tracking at 4K is covered by the GPU suite against the oracle; the reference needs 7 s per 4K pair)
+        tf.KLTTrackFeatures(tc, Image.fromarray(imgs[0]), Image.fromarray(imgs[1]), ref_fl)
+        trk = oracle.track_features(p, imgs[0], imgs[1], *sel)[:3]
+        assert_features_equal(trk, ([float(f.x) for f in ref_fl], [float(f.y) for f in ref_fl], [f.val for f in ref_fl]))
+        assert (trk[2] == 0).sum() > 900
+
+
+def test_live_reference_sequence_with_replacement(oracle, reference):
+    """Config D's flow against the reference itself: sequentialMode tracking + replacement through the reference's own
+    _enforceMinimumDistance(..., overwriteAllFeatures=False) on tc.pyramid_last's gradients, 6 frames at 480x640."""
+    from PIL import Image
+    from pyfeaturetrack_b200 import synth
+    klt, sgf, tf = reference["klt"], reference["selectGoodFeatures"], reference["trackFeatures"]
+    nfr, n = 6, 200
+    shifts = [(a * 5, b * 5) for a, b in synth.sequence_shifts(nfr)]
+    frames = synth.frames(480, 640, shifts, seed=103)
+    kw = dict(nPyramidLevels=3, subsampling=2, max_residue=10.0, sequentialMode=True)
+    tc = klt.KLT_TrackingContext()
+    for k, v in kw.items():
+        setattr(tc, k, v)
+    tc.KLTUpdateTCBorder()
+    p = P(oracle, **kw)
+    fl = sgf.KLTSelectGoodFeatures(tc, Image.fromarray(frames[0]), n)
+    x, y, v = oracle.select_good_features(p, frames[0], n)
+    state = {}
+    replaced = 0
+    for k in range(1, nfr):
+        tf.KLTTrackFeatures(tc, Image.fromarray(frames[k - 1]), Image.fromarray(frames[k]), fl)
+        x, y, v, _ = oracle.track_features(p, frames[k - 1], frames[k], x, y, v, state)
+        assert_features_equal((x, y, v), ([float(f.x) for f in fl], [float(f.y) for f in fl], [f.val for f in fl]))
+        replaced += int((v < 0).sum())
+        # the reference has no public replacement entry point: drive its own pieces the way KLTReplaceLostFeatures would
+        gx, gy = tc.pyramid_last_gradx.img[0], tc.pyramid_last_grady.img[0]
+        bx = int(max(tc.borderx, tc.window_width / 2)); hw = int(tc.window_width / 2)
+        import goodFeaturesUtils as rgfu
+        px, py, pv = rgfu.ScanImageForGoodFeatures(gx, gy, bx, bx, hw, hw, tc.nSkippedPixels)
+        pts = list(zip(pv, px, py)); pts.sort(); pts.reverse()
+        sgf._enforceMinimumDistance(pts, fl, 640, 480, tc.mindist, tc.min_eigenvalue, False)
+        _, gxs, gys = state["pyramid_last"]
+        x, y, v, _ = oracle.select_from_gradients(p, gxs[0], gys[0], n, existing=(x, y, v))
+        assert_features_equal((x, y, v), ([float(f.x) for f in fl], [float(f.y) for f in fl], [f.val for f in fl]))
+    assert replaced > 0
+
+
 # ---- affine consistency check: unpinned by the reference (its callees are undefined there); property tests only -------
 def _affine_sequence(n_frames=5, H=360, W=480):
     """Frames of one texture under a growing rotation + scale + shift (known ground truth)."""
