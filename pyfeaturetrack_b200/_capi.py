@@ -358,7 +358,12 @@ class Context:
             raise KLTB200Error(rc, msg)
 
     def sync(self):
+        self.mark_synced()
         self.check(lib().klt_sync(self.handle))
+
+    def mark_synced(self):
+        """A call that waited for the stream has returned: every staging buffer is free again."""
+        self.__dict__.setdefault("_busy_stages", set()).clear()
 
     def launch_count(self):
         return lib().klt_launch_count(self.handle)
@@ -417,8 +422,12 @@ class Context:
         return buf
 
     def sync_stage(self, key):
-        """The previous upload from this staging buffer must have been consumed before it is overwritten."""
-        self.sync()
+        """The previous upload from this staging buffer must have been consumed before it is overwritten: waits only if an
+        upload from THIS buffer may still be in flight (none is after any synchronous call), then marks it in use."""
+        busy = self.__dict__.setdefault("_busy_stages", set())
+        if key in busy:
+            self.sync()
+        busy.add(key)
 
     def host_alloc(self, nbytes):
         p = C.c_void_p()

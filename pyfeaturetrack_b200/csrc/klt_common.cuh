@@ -76,6 +76,10 @@ struct klt_ctx {
     cudaEvent_t ev0, ev1;
     // upload pipeline of klt_track_pairs_u8: copy stream, per-chunk events, device staging for the frames
     cudaStream_t copy_stream;
+    cudaStream_t aux_stream;    // second compute stream: tracking of sub-batch i overlaps the pyramid builds of sub-batch i + 1
+    cudaEvent_t ov_ev[10];      // [0] entry, [1..8] "sub-batch built", [9] "all tracked"
+    int overlap_subs;           // sub-batches of the overlapped device path (1 = off, the default: it measured slower; $KLT_B200_OVERLAP_SUBS)
+    unsigned long long *iters_dev;   // device counter for calls that do not read it back
     cudaEvent_t chunk_ev[16];
     cudaEvent_t half_free[2];   // recorded on the compute stream once the builds have consumed that staging half
     int half_next;
@@ -171,8 +175,10 @@ int klt_select_batch(klt_ctx *ctx, const klt_params *p, int select_mode, klt_pyr
 int klt_eigen_maps(klt_ctx *ctx, const klt_params *p, int select_mode, klt_pyr *pyr, float *val, int *nx_out, int *ny_out);
 
 // ---- klt_track.cu ------------------------------------------------------------------------------------
+// features of the images [first_image, first_image + n_images) of the batch (n_images < 0: all from first_image on)
 int klt_launch_track(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const klt_pyr *p2, int n_per_image,
-                     double *x_dev, double *y_dev, int32_t *val_dev, unsigned long long *iters_dev, int *assert_dev);
+                     double *x_dev, double *y_dev, int32_t *val_dev, unsigned long long *iters_dev, int *assert_dev,
+                     int first_image = 0, int n_images = -1);
 int klt_launch_extract_patch(klt_ctx *ctx, const float *img, size_t pitch, int w, int h, float x, float y,
                              int height, int width, float *out_dev, int *ok_dev);
 int klt_launch_iterate(klt_ctx *ctx, const klt_params *p, const float *tpatch_dev, const float *img2, const float *gx2,

@@ -162,7 +162,7 @@ lk_track_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ xs, do
                 int *__restrict__ vals, unsigned long long *__restrict__ iters_total, int *__restrict__ assert_flag) {
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int f = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int f = A.f_begin + blockIdx.x * (blockDim.x >> 5) + warp;
     if (f >= A.total) return;
     if (vals[f] < 0) return;                                  // trackFeatures.py:253
     const int n = A.w * A.h;
@@ -336,7 +336,7 @@ lk_track_rows_kernel(const __grid_constant__ TrackArgs A, double *__restrict__ x
     constexpr int G = W <= 7 ? 8 : 16;
     constexpr int FPW = 32 / G;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int f = (blockIdx.x * (blockDim.x >> 5) + warp) * FPW + lane / G;
+    const int f = A.f_begin + (blockIdx.x * (blockDim.x >> 5) + warp) * FPW + lane / G;
     const int j = lane % G;                       // window column handled by this lane
     const bool row_ok = j < W;                    // lane owns a window column
     const bool col_ld = j <= W;                   // lane loads a source column (lane W: the right-hand extra one)
@@ -466,13 +466,14 @@ template <int W>
 static int launch_rows(klt_ctx *ctx, const TrackArgs &A, double *x, double *y, int32_t *v, unsigned long long *it, int *af) {
     constexpr int FPW = 32 / (W <= 7 ? 8 : 16);
     const int per_block = 4 * FPW;
-    const int blocks = (A.total + per_block - 1) / per_block;
+    const int blocks = (A.total - A.f_begin + per_block - 1) / per_block;
     KLT_LAUNCH(ctx, "lk_track_rows", 0.0, (lk_track_rows_kernel<W><<<blocks, 128, 0, ctx->stream>>>(A, x, y, v, it, af)));
     return KLT_OK;
 }
 
 int klt_launch_track(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const klt_pyr *p2, int n_per_image,
-                     double *x_dev, double *y_dev, int32_t *val_dev, unsigned long long *iters_dev, int *assert_dev) {
+                     double *x_dev, double *y_dev, int32_t *val_dev, unsigned long long *iters_dev, int *assert_dev,
+                     int first_image, int n_images) {
     // bit-exact arithmetic only pays off on bit-exact (STRICT) pyramids
     const bool exact = p1->precision == KLT_PRECISION_STRICT && p2->precision == KLT_PRECISION_STRICT;
     TrackArgs A;
@@ -484,9 +485,10 @@ int klt_launch_track(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const
     A.has_max_residue = p->has_max_residue; A.max_residue = p->max_residue;
     A.retain = p->retain_trackers;
     A.borderx = p->borderx; A.bordery = p->bordery;
-    A.n_per_image = n_per_image; A.total = n_per_image * p1->batch;
+    if (n_images < 0) n_images = p1->batch - first_image;
+    A.n_per_image = n_per_image; A.f_begin = n_per_image * first_image; A.total = n_per_image * (first_image + n_images);
     A.lighting_insensitive = p->lighting_insensitive ? 1 : 0;
-    if (A.total <= 0) return KLT_OK;
+    if (A.total <= A.f_begin) return KLT_OK;
     // image-only pyramids (FAST_WINDOWED builds): gradients are evaluated inside the tracking windows
     if (!A.lighting_insensitive && (!klt_pyr_has_gradients(p1) || !klt_pyr_has_gradients(p2))) {
         if (!klt_windowed_supported(p, p1, p2))
@@ -511,7 +513,7 @@ int klt_launch_track(klt_ctx *ctx, const klt_params *p, const klt_pyr *p1, const
     while (smem > 200 * 1024 && warps > 1) { warps /= 2; smem = (size_t)warps * 8 * n * sizeof(float); }
     if (smem > 200 * 1024) return klt_fail(ctx, KLT_ERR_UNSUPPORTED, "tracking window %dx%d too large", A.w, A.h);
     KLT_CUDA(ctx, cudaFuncSetAttribute(lk_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    const int blocks = (A.total + warps - 1) / warps;
+    const int blocks = (A.total - A.f_begin + warps - 1) / warps;
     KLT_LAUNCH(ctx, "lk_track", 0.0, (lk_track_kernel<<<blocks, warps * 32, smem, ctx->stream>>>(A, x_dev, y_dev, val_dev, iters_dev, assert_dev)));
     return KLT_OK;
 }

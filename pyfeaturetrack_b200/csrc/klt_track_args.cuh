@@ -14,7 +14,8 @@ struct TrackArgs {
     float max_residue;
     int retain;
     double borderx, bordery;
-    int n_per_image, total;
+    int n_per_image, total;     // features per image; END of the feature range of this launch
+    int f_begin;                // first feature of this launch (a sub-range of the batch: [f_begin, total))
     int lighting_insensitive;   // gain / bias normalisation of trackFeaturesUtils.pyx:152-239 (exact-order kernel only)
 };
 

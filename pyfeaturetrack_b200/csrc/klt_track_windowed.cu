@@ -234,7 +234,7 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
     using C = Cfg<W>;
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int f = blockIdx.x * WIN_WARPS + warp;
+    const int f = A.f_begin + blockIdx.x * WIN_WARPS + warp;
     if (f >= A.total) return;                     // one feature per warp: all control flow below is warp-uniform
     if (vals[f] < 0) return;                      // trackFeatures.py:253
     float *s = smem + warp * C::FLOATS;
@@ -421,9 +421,10 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
 template <int W>
 int launch_windowed(klt_ctx *ctx, const TrackArgs &A, const WindowedTaps &K, double *x, double *y, int32_t *v,
                     unsigned long long *it, int *af) {
-    const int blocks = (A.total + WIN_WARPS - 1) / WIN_WARPS;
+    const int nfeat = A.total - A.f_begin;
+    const int blocks = (nfeat + WIN_WARPS - 1) / WIN_WARPS;
     // algorithmic bytes: the staged regions of both images on every level (restaging not counted) + the feature records
-    const double bytes = (double)A.total * (A.n_levels * 4.0 * (Cfg<W>::N1 * Cfg<W>::N1 + Cfg<W>::N2 * Cfg<W>::N2) + 40.0);
+    const double bytes = (double)nfeat * (A.n_levels * 4.0 * (Cfg<W>::N1 * Cfg<W>::N1 + Cfg<W>::N2 * Cfg<W>::N2) + 40.0);
     const size_t smem = (size_t)WIN_WARPS * Cfg<W>::FLOATS * sizeof(float);
     constexpr int MINB = W <= 11 ? WIN_MIN_CTAS : 3;
     if (smem > 48 * 1024) KLT_CUDA(ctx, cudaFuncSetAttribute(lk_windowed_kernel<W, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

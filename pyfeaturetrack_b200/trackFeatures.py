@@ -55,17 +55,16 @@ _hint = threading.local()     # .density = (features, pixels) of the KLTTrackFea
 
 
 def _build_pyramids(tc, img, pyr):
-    a, is_u8 = _image_u8_or_f32(img)
     taps = _taps_for_one_image(tc)
     prec = config.track_precision_code(*(getattr(_hint, "density", None) or (None, None)))
-    if is_u8:
-        # stage through pinned memory: the upload becomes a true asynchronous DMA instead of a pageable copy
-        stage = pyr.ctx.pinned_stage(a.shape, id(pyr))
-        pyr.ctx.sync_stage(id(pyr))
-        np.copyto(stage, a)
+    # stage through pinned memory: the upload becomes a true asynchronous DMA (it and the build overlap the host's work on
+    # the next image); only enqueued here
+    stage = _sgf._stage_u8(pyr.ctx, img, id(pyr))
+    if stage is not None:
         pyr.build_u8(stage, taps, prec)
     else:
-        pyr.build_f32(a, taps, prec, already_smoothed=False)
+        a, _ = _image_u8_or_f32(img)
+        pyr.build_f32(np.ascontiguousarray(a, np.float32), taps, prec, already_smoothed=False)
     return _PyramidSet(pyr)
 
 
@@ -191,6 +190,7 @@ def KLTTrackFeatures(tc, img1, img2, featurelist):
     else:
         ctx.check(_capi.lib().klt_track_features(ctx.handle, C.byref(params), pyramid1.pyr.handle, pyramid2.pyr.handle,
                                                 len(featurelist), x.ctypes.data, y.ctypes.data, val.ctypes.data, None))
+    ctx.mark_synced()          # host arrays: the tracking call waited for the stream
     xs, ys, vals = x.tolist(), y.tolist(), val.tolist()
     for feat, live, fx, fy, v in zip(featurelist, was_live.tolist(), xs, ys, vals):
         if not live:

@@ -199,6 +199,49 @@ def test_fractional_min_eigenvalue_and_sticky_assert_flag(gpu_ctx, oracle):
     pyr.close()
 
 
+@pytest.mark.parametrize("precision", ["windowed", "fast", "strict"])
+def test_overlapped_device_pairs_equal_serial(gpu_ctx, oracle, precision):
+    """klt_track_pairs_u8 with device-resident frames and lists (sub-batches tracked on a second stream while the next ones are
+    built) gives exactly what the three separate calls give."""
+    from pyfeaturetrack_b200 import _capi, synth, selectGoodFeatures as sgf, trackFeatures as tf
+    prec = {"windowed": _capi.PRECISION_FAST_WINDOWED, "fast": _capi.PRECISION_FAST, "strict": _capi.PRECISION_STRICT}[precision]
+    H, W, n, B = 240, 320, 120, 10
+    tc = make_tc(nPyramidLevels=2, subsampling=2, max_residue=10.0)
+    params, taps = sgf.make_params(tc), tf._taps_for_one_image(tc)
+    pairs = [synth.frame_pair(H, W, seed=60 + i, shift=(1.0 + 0.3 * i, -2.0 + 0.4 * i)) for i in range(B)]
+    f1 = np.ascontiguousarray(np.stack([p[0] for p in pairs])); f2 = np.ascontiguousarray(np.stack([p[1] for p in pairs]))
+    sel = [oracle.select_good_features(oracle.Params(nPyramidLevels=2, subsampling=2), p[0], n) for p in pairs]
+    x0 = np.stack([s[0] for s in sel]); y0 = np.stack([s[1] for s in sel]); v0 = np.stack([s[2] for s in sel]).astype(np.int32)
+    ctx = gpu_ctx
+    lib = _capi.lib()
+    d1, d2 = ctx.device_alloc(f1.nbytes), ctx.device_alloc(f2.nbytes)
+    dx, dy, dv = ctx.device_alloc(B * n * 8), ctx.device_alloc(B * n * 8), ctx.device_alloc(B * n * 4)
+    ctx.memcpy(d1, f1, f1.nbytes); ctx.memcpy(d2, f2, f2.nbytes)
+    p1, p2 = _capi.Pyramid(ctx, W, H, 2, 2, B), _capi.Pyramid(ctx, W, H, 2, 2, B)
+    res = []
+    for overlapped in (True, False):
+        ctx.memcpy(dx, x0, B * n * 8); ctx.memcpy(dy, y0, B * n * 8); ctx.memcpy(dv, v0, B * n * 4)
+        if overlapped:
+            ctx.check(lib.klt_track_pairs_u8(ctx.handle, C.byref(params), C.byref(taps), prec, p1.handle, p2.handle, d1, d2, W, W * H, n, dx, dy, dv))
+        else:
+            ctx.check(lib.klt_pyr_build_u8(ctx.handle, p1.handle, d1, W, W * H, C.byref(taps), prec))
+            ctx.check(lib.klt_pyr_build_u8(ctx.handle, p2.handle, d2, W, W * H, C.byref(taps), prec))
+            ctx.check(lib.klt_track_features(ctx.handle, C.byref(params), p1.handle, p2.handle, n, dx, dy, dv, None))
+        x, y, v = np.empty((B, n)), np.empty((B, n)), np.empty((B, n), np.int32)
+        ctx.memcpy(x, dx, B * n * 8); ctx.memcpy(y, dy, B * n * 8); ctx.memcpy(v, dv, B * n * 4)
+        ctx.sync()
+        res.append((x, y, v))
+    eq(res[0], res[1])
+    assert (res[0][2] == 0).mean() > 0.8
+    if precision == "strict":
+        for b in range(B):
+            want = oracle.track_features(oracle.Params(nPyramidLevels=2, subsampling=2, max_residue=10.0), pairs[b][0], pairs[b][1], *sel[b])[:3]
+            eq((res[0][0][b], res[0][1][b], res[0][2][b]), want)
+    for d in (d1, d2, dx, dy, dv):
+        ctx.device_free(d)
+    p1.close(); p2.close()
+
+
 # ---- fused fast eigenvalue pass ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape,kw", [((480, 640), dict(nPyramidLevels=2, subsampling=2)),
                                       ((243, 325), dict(nSkippedPixels=2)),
