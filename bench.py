@@ -786,6 +786,9 @@ def sequence_timing(wl, klt, sgf, tf, nframes, affine=-1):
     _capi_sync()                                                # cudaFree of those inside the timed loop costs ~300 ms)
     t_track = t_repl = 0.0
     per_frame = []
+    from pyfeaturetrack_b200 import _capi as _c
+    pctx = _c.default_ctx()
+    pctx.profile_reset()
     for k in range(3, nframes + 1):
         t0 = time.perf_counter()
         tf.KLTTrackFeatures(tc, frames[k - 1], frames[k], fl)
@@ -796,7 +799,13 @@ def sequence_timing(wl, klt, sgf, tf, nframes, affine=-1):
         t_repl += t2 - t1
         per_frame.append(round(1e3 * (t2 - t0), 2))
     m = nframes - 2
-    return {"call": "sequentialMode%s: KLTTrackFeatures + KLTReplaceLostFeatures per frame (drop-in API, one sequence)" %
+    # per-kernel device time of one more frame (profiling adds host overhead, so it is outside the timed loop)
+    pctx.profile(True)
+    tf.KLTTrackFeatures(tc, frames[nframes - 1], frames[nframes], fl)
+    sgf.KLTReplaceLostFeatures(tc, frames[nframes], fl)
+    pctx.profile(False)
+    kern = {k: round(v["ms"], 4) for k, v in pctx.profile_read().items()}
+    return {"kernel_ms_last_frame": kern, "call": "sequentialMode%s: KLTTrackFeatures + KLTReplaceLostFeatures per frame (drop-in API, one sequence)" %
                     ("" if affine < 0 else ", affineConsistencyCheck=%d" % affine),
             "tracked_at_end": sum(1 for f in fl if f.val >= 0),
             "ms_track_per_frame": round(1e3 * t_track / m, 3), "ms_replace_per_frame": round(1e3 * t_repl / m, 3),

@@ -8,8 +8,8 @@
 //
 // Mapping: one warp per feature; the 15x15 window's 225 pixels are spread over the 32 lanes (8 per lane).  Every
 // lane accumulates its share of the 21 + 6 sums of the 6x6 normal equations (10 + 4 for the similarity model, 5 for
-// pure translation), a butterfly of warp shuffles leaves the totals in every lane, and every lane runs the same
-// 6x6 Gauss-Jordan elimination with full pivoting redundantly (no divergence, no broadcast needed).
+// pure translation), a butterfly of warp shuffles leaves the totals in every lane, and the warp solves the system
+// cooperatively: lane r owns row r of the Gauss-Jordan elimination with full pivoting (registers and shuffles only).
 // Per-feature state (template of (aw+2)x(ah+2) pixels for image / gradx / grady, template centre, the 2x2 map A)
 // lives in device memory inside a klt_affine object and persists from frame to frame like the fields of KLT_Feature.
 #include "klt_common.cuh"
@@ -37,42 +37,75 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // C-KLT _am_gauss_jordan_elimination (Numerical Recipes gaussj with full pivoting); b is the single right-hand side.
-__device__ int gauss_jordan(float (&a)[6][6], int n, float (&b)[6]) {
-    int ipiv[6] = {0, 0, 0, 0, 0, 0};
-    int col = 0, row = 0;
-    for (int i = 0; i < n; i++) {
-        float big = 0.0f;
-        for (int j = 0; j < n; j++)
-            if (ipiv[j] != 1)
-                for (int k = 0; k < n; k++) {
-                    if (ipiv[k] == 0) {
-                        if (fabsf(a[j][k]) >= big) { big = fabsf(a[j][k]); row = j; col = k; }
-                    } else if (ipiv[k] > 1) return KLT_SMALL_DET;
-                }
-        ++(ipiv[col]);
-        if (row != col) {
-            for (int l = 0; l < n; l++) { const float t = a[row][l]; a[row][l] = a[col][l]; a[col][l] = t; }
-            const float t = b[row]; b[row] = b[col]; b[col] = t;
-        }
-        if (a[col][col] == 0.0f) return KLT_SMALL_DET;
-        const float pivinv = 1.0f / a[col][col];
-        a[col][col] = 1.0f;
-        for (int l = 0; l < n; l++) a[col][l] *= pivinv;
-        b[col] *= pivinv;
-        for (int ll = 0; ll < n; ll++)
-            if (ll != col) {
-                const float dum = a[ll][col];
-                a[ll][col] = 0.0f;
-                for (int l = 0; l < n; l++) a[ll][l] -= a[col][l] * dum;
-                b[ll] -= b[col] * dum;
-            }
+// Warp-cooperative and register-only: lane r < 6 owns row r of the augmented matrix (rw[0..5] | rb); the column of an
+// access is the only dynamic index left and is resolved by a 6-way select, so nothing goes to local memory (the earlier
+// per-lane version indexed a[6][6] dynamically: 877 LDL/STL in its SASS).  Pivot search = per-row maximum, then a
+// butterfly arg-max over the rows; ties resolve to the LAST element in (row, column) order like the reference's `>=` scan.
+// The solution comes back in every lane's x[0..5].
+__device__ __forceinline__ float sel6(const float (&v)[6], int k) {
+    return k == 0 ? v[0] : (k == 1 ? v[1] : (k == 2 ? v[2] : (k == 3 ? v[3] : (k == 4 ? v[4] : v[5]))));
+}
+__device__ int gauss_jordan_warp(const float (&T)[6][6], const float (&rhs)[6], int n, int lane, float (&x)[6]) {
+    const unsigned int full = 0xffffffffu;
+    float rw[6], rb = sel6(rhs, lane < 6 ? lane : 0);
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        const float col[6] = {T[0][c], T[1][c], T[2][c], T[3][c], T[4][c], T[5][c]};
+        rw[c] = sel6(col, lane < 6 ? lane : 0);
     }
+    unsigned int used = 0u;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        if (i < n) {                                            // warp-uniform
+            float best = -1.0f;
+            int bk = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+                if (k < n && !((used >> k) & 1u)) { const float v = fabsf(rw[k]); if (v >= best) { best = v; bk = k; } }
+            if (!(lane < n) || ((used >> lane) & 1u)) best = -2.0f;      // rows already used as pivots (ipiv[j] == 1) and idle lanes
+            int br = lane;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {                   // arg-max over lanes 0..7
+                const float ob = __shfl_xor_sync(full, best, o);
+                const int orow = __shfl_xor_sync(full, br, o), ok = __shfl_xor_sync(full, bk, o);
+                if (ob > best || (ob == best && orow > br)) { best = ob; br = orow; bk = ok; }
+            }
+            const int row = __shfl_sync(full, br, 0), col = __shfl_sync(full, bk, 0);
+            used |= 1u << col;
+            if (row != col) {                                   // swap rows `row` and `col`
+                const int src = lane == row ? col : (lane == col ? row : lane);
+#pragma unroll
+                for (int l = 0; l < 6; l++) rw[l] = __shfl_sync(full, rw[l], src);
+                rb = __shfl_sync(full, rb, src);
+            }
+            const float piv = __shfl_sync(full, sel6(rw, col), col);
+            if (piv == 0.0f) return KLT_SMALL_DET;
+            const float pivinv = 1.0f / piv;
+            if (lane == col) {
+#pragma unroll
+                for (int l = 0; l < 6; l++) rw[l] = (l == col ? 1.0f : rw[l]) * pivinv;
+                rb *= pivinv;
+            }
+            float pr[6];
+#pragma unroll
+            for (int l = 0; l < 6; l++) pr[l] = __shfl_sync(full, rw[l], col);
+            const float pb = __shfl_sync(full, rb, col);
+            if (lane != col) {
+                const float dum = sel6(rw, col);
+#pragma unroll
+                for (int l = 0; l < 6; l++) rw[l] = (l == col ? 0.0f : rw[l]) - pr[l] * dum;
+                rb -= pb * dum;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) x[r] = __shfl_sync(full, rb, r);
     return KLT_TRACKED;
 }
 
 __device__ __forceinline__ bool oob1(float v, int n) { return v < 0.0f || (float)n - v < 1.001f; }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 lk_affine_kernel(const __grid_constant__ AffineArgs G, const double *__restrict__ x_in, const double *__restrict__ y_in,
                  const int *__restrict__ val_in, double *__restrict__ xs, double *__restrict__ ys, int *__restrict__ vals,
                  int *__restrict__ assert_flag) {
@@ -186,7 +219,12 @@ lk_affine_kernel(const __grid_constant__ AffineArgs G, const double *__restrict_
             for (int r = 0; r < 6; r++)
 #pragma unroll
                 for (int c = 0; c < r; c++) T[r][c] = T[c][r];
-            status = gauss_jordan(T, n, a);
+            {
+                float sol[6];
+                status = gauss_jordan_warp(T, a, n, lane, sol);
+#pragma unroll
+                for (int r = 0; r < 6; r++) a[r] = sol[r];
+            }
             if (G.affine_map == 1) { Axx += a[0]; Ayx += a[1]; Ayy = Axx; Axy = -Ayx; dx = a[2]; dy = a[3]; }
             else { Axx += a[0]; Ayx += a[1]; Axy += a[2]; Ayy += a[3]; dx = a[4]; dy = a[5]; }
             x2 += dx; y2 += dy;

@@ -137,13 +137,11 @@ def _affine_state(tc, ctx, featurelist):
     st = getattr(tc, "_klt_affine", None)
     if st is None or st.n != n or st.aw != tc.affine_window_width or st.ah != tc.affine_window_height or st.ctx is not ctx:
         st = tc._klt_affine = _capi.AffineState(ctx, n, int(tc.affine_window_width), int(tc.affine_window_height))
-    mask = np.zeros(n, np.int32)
-    for i, feat in enumerate(featurelist):
-        t = getattr(feat, "aff_img", None)
-        if not (isinstance(t, AffineTemplate) and t.state is st and t.slot == i):
-            mask[i] = 1
-    if mask.any():
-        st.reset(mask)
+    # slots whose feature does not carry this state's template (fresh, replaced or foreign features) start over
+    keep = [type(t) is AffineTemplate and t.state is st and t.slot == i
+            for i, t in enumerate([f.__dict__.get("aff_img") for f in featurelist])]
+    if not all(keep):
+        st.reset(np.logical_not(np.array(keep, dtype=bool)).astype(np.int32))
     return st
 
 
@@ -205,16 +203,19 @@ def KLTTrackFeatures(tc, img1, img2, featurelist):
 
     if use_affine:
         has, ax, ay, A = aff.download()
-        for i, feat in enumerate(featurelist):
-            if not was_live[i]:
+        rows = zip(featurelist, was_live.tolist(), has.tolist(), ax.astype(np.float64).tolist(), ay.astype(np.float64).tolist(),
+                   A.astype(np.float64).tolist())
+        for i, (feat, live, h, fax, fay, fA) in enumerate(rows):
+            if not live:
                 continue
-            feat.aff_x, feat.aff_y = float(ax[i]), float(ay[i])
-            feat.aff_Axx, feat.aff_Ayx, feat.aff_Axy, feat.aff_Ayy = (float(v) for v in A[i])
-            if has[i]:
-                if not isinstance(getattr(feat, "aff_img", None), AffineTemplate):
-                    feat.aff_img, feat.aff_img_gradx, feat.aff_img_grady = (AffineTemplate(aff, i, w) for w in range(3))
+            d = feat.__dict__
+            d["aff_x"] = fax; d["aff_y"] = fay
+            d["aff_Axx"], d["aff_Ayx"], d["aff_Axy"], d["aff_Ayy"] = fA
+            if h:
+                if type(d.get("aff_img")) is not AffineTemplate:
+                    d["aff_img"], d["aff_img_gradx"], d["aff_img_grady"] = (AffineTemplate(aff, i, w) for w in range(3))
             else:
-                _clear_affine(feat)
+                d["aff_img"] = d["aff_img_gradx"] = d["aff_img_grady"] = None
 
     if tc.sequentialMode:
         if tc.pyramid_last is not None and tc.pyramid_last is not pyramid2:
