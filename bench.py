@@ -518,6 +518,23 @@ def run_b200(args):
                       "seconds": round(sus_ms * 1e-3, 3), "ms_per_step": round(sus_ms / sus_steps, 4),
                       "vs_burst": round((dev_ms / args.steps) / (sus_ms / sus_steps), 4), "clocks": sus_clocks},
     }
+    # the host-fed numbers against what this box's host memory system can feed N GPUs at once (tools/h2d_probe.py, measured
+    # on the 8-GPU box of this pool; a PCIe / host-memory ceiling, not a kernel property)
+    try:
+        ceil = json.load(open(os.path.join(ROOT, "profiles", "h2d_ceiling_r02.json")))["per_n"].get(str(world))
+    except Exception:
+        ceil = None
+    h2d_gbps = (2 * frame_bytes + feat_bytes) / e2e_s / 1e9
+    out["e2e"]["h2d_gbps_per_gpu"] = round(h2d_gbps, 2)
+    if ceil:
+        out["e2e"]["h2d_ceiling_gbps_per_gpu"] = ceil["gbps_per_rank"]
+        out["e2e"]["frac_of_h2d_ceiling"] = round(h2d_gbps / ceil["gbps_per_rank"], 4)
+        out["e2e"]["ceiling_source"] = "profiles/h2d_ceiling_r02.json: %d ranks copying pinned memory at once reach %.1f GB/s each (%.1f aggregate) on this host" % (
+            world, ceil["gbps_per_rank"], ceil["gbps_aggregate"])
+        if seq is not None:
+            sg = seq["e2e"]["h2d_bytes_per_step"] / (seq["e2e"]["ms_per_step"] * 1e-3) / 1e9
+            seq["e2e"]["h2d_gbps_per_gpu"] = round(sg, 2)
+            seq["e2e"]["frac_of_h2d_ceiling"] = round(sg / ceil["gbps_per_rank"], 4)
     if dense is not None:
         dense_ms, dense_tracked, dprof = dense
         dtr = float(dense_tracked) * world        # rank 0's count stands for every rank (same workload shape)
