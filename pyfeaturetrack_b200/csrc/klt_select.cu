@@ -506,11 +506,13 @@ select_walk_kernel(const __grid_constant__ SelDev S, int presorted) {
     const unsigned int *hist = S.hist + (size_t)b * SEL_BINS;
     const unsigned int *offs_planned = S.offs + (size_t)b * (SEL_BINS + 1);
     unsigned long long *status = S.status + (size_t)b * SEL_STATUS_WORDS;
-    unsigned short *grid = S.grid_in_smem ? reinterpret_cast<unsigned short *>(off + SEL_BINS) : S.grid_global + (size_t)b * S.grid_stride;
+    // accepted features (one per cell at most) and, during a round of phase 2, the smallest live rank per cell
+    unsigned int *cellmin = S.grid_in_smem ? off + SEL_BINS : S.cellmin_global + (size_t)b * S.grid_stride;
+    unsigned short *grid = S.grid_in_smem ? reinterpret_cast<unsigned short *>(cellmin + S.gw * S.gh) : S.grid_global + (size_t)b * S.grid_stride;
     const int overwrite = S.replace ? 0 : 1;
     const unsigned char *pm_walk = (presorted && S.premap) ? S.premap + (size_t)b * S.map_stride : nullptr;
     if (S.r >= 0)
-        for (int c = tid; c < S.gw * S.gh; c += WALK_THREADS) grid[c] = 0xFFFFu;
+        for (int c = tid; c < S.gw * S.gh; c += WALK_THREADS) { grid[c] = 0xFFFFu; cellmin[c] = 0xFFFFFFFFu; }
     // fillable slots: every slot (SELECTING_ALL) or, in list order, the slots of lost features (:64-69, :110-112)
     if (tid == 0) { s_slots = overwrite ? n_features : 0; s_filled = 0; }
     __syncthreads();
@@ -606,61 +608,93 @@ select_walk_kernel(const __grid_constant__ SelDev S, int presorted) {
                         __syncthreads();
                         bitonic_sort(sk, P);
                     }
-                    // ---- phase 2: warp 0 walks the survivors in rank order with exactly the result of the sequential loop:
-                    // re-test against the grid (features accepted earlier in this chunk), then resolve 32 candidates at once --
-                    // lane i is accepted iff no EARLIER accepted lane lies within distance r.  That recurrence is solved by
-                    // iteration: an undecided lane is rejected as soon as an accepted earlier lane conflicts with it and accepted
-                    // as soon as all its earlier conflicting lanes are rejected; the lowest undecided lane is decided in every
-                    // round.  Accepted lanes then fill their slots (the k-th accepted candidate takes the k-th fillable slot)
-                    // and register in the grid together.
-                    if (warp == 0) {
-                        int filled = s_filled;
-                        bool full = false;
-                        const unsigned int lt = (1u << lane) - 1u;
-                        for (int b0 = 0; b0 < ns && !full; b0 += 32) {
-                            const bool valid = b0 + lane < ns;
-                            const unsigned long long k = valid ? ~sk[b0 + lane] : 0ull;
-                            const int x = (int)((k >> 13) & 8191ull), y = (int)(k & 8191ull);
-                            const float val = __uint_as_float((unsigned int)(k >> 26));
-                            bool lv = valid;
-                            if (lv && S.r >= 0 && grid_conflict(grid, S.gw, S.gh, S.cs, S.r, x, y)) lv = false;
-                            const unsigned int live_mask = __ballot_sync(0xffffffffu, lv);
-                            if (live_mask == 0u) continue;
-                            unsigned int confl = 0u;       // earlier live lanes of the batch within distance r of this one
-                            if (S.r >= 0) {
-                                for (unsigned int mmk = live_mask; mmk; mmk &= mmk - 1u) {
-                                    const int j = __ffs(mmk) - 1;
-                                    const int xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j);
-                                    if (j < lane && abs(x - xj) <= S.r && abs(y - yj) <= S.r) confl |= 1u << j;
-                                }
-                            }
-                            unsigned int acc = 0u, rej = 0u, undecided = live_mask;
-                            while (undecided) {
-                                const bool mine = (undecided >> lane) & 1u;
-                                const bool r_now = mine && (confl & acc) != 0u;
-                                const bool a_now = mine && !r_now && (confl & ~rej) == 0u;
-                                const unsigned int na = __ballot_sync(0xffffffffu, a_now), nr = __ballot_sync(0xffffffffu, r_now);
-                                acc |= na; rej |= nr; undecided &= ~(na | nr);
-                            }
-                            const int nacc = __popc(acc), room = slots - filled;
-                            const int take = nacc < room ? nacc : room;
-                            const int rank = __popc(acc & lt);
-                            const bool store = ((acc >> lane) & 1u) && rank < take;
-                            __syncwarp();                 // every lane has finished reading the grid before anyone registers in it
-                            if (store) {
-                                const int slot = overwrite ? filled + rank : free_slots[filled + rank];
-                                fx[slot] = (double)x; fy[slot] = (double)y; fval[slot] = (int)val;
-                                if (S.r >= 0) {
-                                    const int cx = x / S.cs, cy = y / S.cs;
-                                    grid[cy * S.gw + cx] = (unsigned short)(((x - cx * S.cs) << 8) | (y - cy * S.cs));
-                                }
-                            }
-                            filled += take;
-                            if (filled >= slots) full = true;
-                            __syncwarp();
+                    // ---- phase 2: the exact greedy result by parallel rounds.  Greedy over a sorted list = the lexicographically first
+                    // maximal independent set: a live candidate with no live candidate of smaller rank within distance r
+                    // is accepted; what the accepted ones suppress dies; repeat.  "No smaller rank within r" is tested conservatively
+                    // on cells: every live candidate publishes its rank with atomicMin in its cell (side r + 1), and a candidate is
+                    // accepted when no cell of its 3x3 neighbourhood holds a smaller rank.  That can only delay an acceptance to a
+                    // later round, never change it; the smallest live rank is always accepted, so the rounds terminate.  Thread t
+                    // owns the ranks NPT * t .. NPT * t + NPT - 1; the k-th accepted candidate (in rank order) takes the k-th
+                    // fillable slot, and what does not fit any more is dropped -- exactly where the sequential walk stops.
+                    {
+                        const int NPT = (S.ch + WALK_THREADS - 1) / WALK_THREADS;      // <= 4
+                        int px[4], py[4], pcell[4], pst[4];                            // state: 0 live, 1 accepted, 2 dead / none
+                        float pval[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int i = tid * NPT + j;
+                            const bool valid = j < NPT && i < ns;
+                            const unsigned long long k = valid ? ~sk[i] : 0ull;
+                            px[j] = (int)((k >> 13) & 8191ull); py[j] = (int)(k & 8191ull);
+                            pval[j] = __uint_as_float((unsigned int)(k >> 26));
+                            pcell[j] = (py[j] / S.cs) * S.gw + px[j] / S.cs;
+                            pst[j] = valid ? (S.r >= 0 ? 0 : 1) : 2;
                         }
-                        __syncwarp();                         // every lane has read s_filled (the loop may not have run)
-                        if (lane == 0) { s_filled = filled; if (full) s_full = 1; }
+                        if (S.r >= 0) {
+                            for (;;) {
+#pragma unroll
+                                for (int j = 0; j < 4; j++)
+                                    if (pst[j] == 0) atomicMin(&cellmin[pcell[j]], (unsigned int)(tid * NPT + j));
+                                __syncthreads();
+                                bool acc_now[4];
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    acc_now[j] = false;
+                                    if (pst[j] == 0) {
+                                        const int cx = px[j] / S.cs, cy = py[j] / S.cs;
+                                        unsigned int m = 0xFFFFFFFFu;
+#pragma unroll
+                                        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                                            for (int dx = -1; dx <= 1; dx++) {
+                                                const int ncx = cx + dx, ncy = cy + dy;
+                                                if (ncx >= 0 && ncx < S.gw && ncy >= 0 && ncy < S.gh) m = min(m, cellmin[ncy * S.gw + ncx]);
+                                            }
+                                        acc_now[j] = m == (unsigned int)(tid * NPT + j);
+                                    }
+                                }
+                                __syncthreads();                      // every read of cellmin is done
+#pragma unroll
+                                for (int j = 0; j < 4; j++)
+                                    if (pst[j] == 0) {
+                                        cellmin[pcell[j]] = 0xFFFFFFFFu;      // leave the array clean for the next round / chunk
+                                        if (acc_now[j]) {
+                                            pst[j] = 1;
+                                            const int cx = px[j] / S.cs, cy = py[j] / S.cs;
+                                            grid[pcell[j]] = (unsigned short)(((px[j] - cx * S.cs) << 8) | (py[j] - cy * S.cs));
+                                        }
+                                    }
+                                __syncthreads();
+                                int live = 0;
+#pragma unroll
+                                for (int j = 0; j < 4; j++)
+                                    if (pst[j] == 0) {
+                                        if (grid_conflict(grid, S.gw, S.gh, S.cs, S.r, px[j], py[j])) pst[j] = 2; else live = 1;
+                                    }
+                                if (__syncthreads_count(live) == 0) break;
+                            }
+                        }
+                        unsigned int mine = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) mine += pst[j] == 1 ? 1u : 0u;
+                        unsigned int tot;
+                        const unsigned int incl = block_scan_incl(mine, warp_cnt, &tot);
+                        const int filled = s_filled, room = slots - filled;
+                        int p = (int)(incl - mine);
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            if (pst[j] == 1) {
+                                if (p < room) {
+                                    const int slot = overwrite ? filled + p : free_slots[filled + p];
+                                    fx[slot] = (double)px[j]; fy[slot] = (double)py[j]; fval[slot] = (int)pval[j];
+                                }
+                                p++;
+                            }
+                        __syncthreads();                              // s_filled has been read by everyone
+                        if (tid == 0) {
+                            s_filled = filled + ((int)tot < room ? (int)tot : room);
+                            if ((int)tot >= room) s_full = 1;
+                        }
                     }
                     __syncthreads();
                     consumed += (unsigned long long)mm;
@@ -738,9 +772,9 @@ int klt_sel_geometry(klt_ctx *ctx, const klt_params *p, int w, int h, int n_feat
     // replacement mode only sees the candidates no surviving feature suppresses: a smaller first range suffices
     S->target_mul = replace ? 128u : 32u;
     S->target_add = replace ? 1024u : 8192u;
-    const size_t grid_b = (size_t)S->gw * S->gh * sizeof(unsigned short);
+    const size_t grid_b = (size_t)S->gw * S->gh * (sizeof(unsigned short) + sizeof(unsigned int));     // cell grid + per-cell minimum rank
     const size_t fixed = (size_t)S->ch * sizeof(unsigned long long) + (2 * SEL_BINS + 4) * sizeof(unsigned int);
-    S->grid_in_smem = fixed + grid_b + 2048 <= 200 * 1024 ? 1 : 0;
+    S->grid_in_smem = fixed + grid_b + 2048 <= 220 * 1024 ? 1 : 0;
     return KLT_OK;
 }
 
@@ -752,7 +786,7 @@ size_t klt_sel_workspace_bytes(const SelDev *S, int B, bool strict_sat, bool own
     t += align_up((size_t)B * (SEL_PLAN_WORDS * sizeof(unsigned int) + SEL_STATUS_WORDS * sizeof(unsigned long long)), 256);
     t += 2 * align_up((size_t)B * S->key_stride * sizeof(unsigned long long), 256);
     if (S->replace) t += align_up((size_t)B * S->map_stride, 256);
-    if (!S->grid_in_smem) t += align_up((size_t)B * S->grid_stride * sizeof(unsigned short), 256);
+    if (!S->grid_in_smem) t += align_up((size_t)B * S->grid_stride * sizeof(unsigned short), 256) + align_up((size_t)B * S->grid_stride * sizeof(unsigned int), 256);
     t += align_up((size_t)B * S->n_features * sizeof(int) + 64, 256);            // free slots
     if (own_features) t += align_up((size_t)B * S->n_features * (2 * sizeof(double) + sizeof(int)) + 64, 256);
     return t + 1024;
@@ -772,6 +806,7 @@ void klt_sel_carve(SelDev *S, int B, bool strict_sat, bool own_features, char *b
     S->keys2 = (unsigned long long *)take((size_t)B * S->key_stride * sizeof(unsigned long long));
     S->premap = S->replace ? (unsigned char *)take((size_t)B * S->map_stride) : nullptr;
     S->grid_global = S->grid_in_smem ? nullptr : (unsigned short *)take((size_t)B * S->grid_stride * sizeof(unsigned short));
+    S->cellmin_global = S->grid_in_smem ? nullptr : (unsigned int *)take((size_t)B * S->grid_stride * sizeof(unsigned int));
     S->free_slots = (int *)take((size_t)B * S->n_features * sizeof(int) + 64);
     if (own_features) {
         char *f = take((size_t)B * S->n_features * (2 * sizeof(double) + sizeof(int)) + 64);
@@ -781,7 +816,7 @@ void klt_sel_carve(SelDev *S, int B, bool strict_sat, bool own_features, char *b
 
 static size_t walk_smem(const SelDev *S) {
     size_t s = (size_t)S->ch * sizeof(unsigned long long) + (2 * SEL_BINS + 4) * sizeof(unsigned int);
-    if (S->grid_in_smem) s += (size_t)S->gw * S->gh * sizeof(unsigned short);
+    if (S->grid_in_smem) s += (size_t)S->gw * S->gh * (sizeof(unsigned short) + sizeof(unsigned int));
     return s;
 }
 

@@ -28,6 +28,7 @@ struct SelDev {
     unsigned long long *keys, *keys2; // [B][key_stride]
     unsigned char *premap;            // [B][map_stride], replacement mode only
     unsigned short *grid_global;      // [B][grid_stride] when the cell grid does not fit in shared memory
+    unsigned int *cellmin_global;     // [B][grid_stride] ditto, the per-cell minimum live rank of the walk's rounds
     int *free_slots;                  // [B][n_features]
     double *fx, *fy;                  // [B][n_features] feature lists, updated in place
     int *fval;
