@@ -145,8 +145,8 @@ int klt_ctx_create(int device, void *stream, klt_ctx **out) {
     for (int i = 0; i < 16; i++) cudaEventCreateWithFlags(&ctx->marks[i], cudaEventDisableTiming);
     if (cudaMalloc(&ctx->async_flag_dev, 256) == cudaSuccess) { cudaMemset(ctx->async_flag_dev, 0, 256); ctx->iters_dev = (unsigned long long *)(ctx->async_flag_dev + 16); }
     ctx->num_sms = prop.multiProcessorCount;
-    ctx->fast_quad_nc = 2;      // measured on B200, 8 x 1080p: 115 us (2 columns per lane, 95 registers) vs 138 us (4 columns, 187)
-    if (const char *e3 = getenv("KLT_B200_FAST_NC")) { if (atoi(e3) == 4) ctx->fast_quad_nc = 4; }
+    ctx->fast_quad_nc = 4;
+    if (const char *e3 = getenv("KLT_B200_FAST_NC")) { if (atoi(e3) == 2) ctx->fast_quad_nc = 2; }
     ctx->select_chunk = 4096;
     if (const char *e2 = getenv("KLT_B200_SELECT_CHUNK")) {
         const int v = atoi(e2);

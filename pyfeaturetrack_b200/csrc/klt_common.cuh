@@ -91,7 +91,7 @@ struct klt_ctx {
     void *ws;
     size_t ws_bytes;
     int num_sms;
-    int fast_quad_nc;           // columns per lane of the fused eigen pass (2; $KLT_B200_FAST_NC=4 for the wide variant)
+    int fast_quad_nc;           // columns per lane of the fused eigen pass (4; $KLT_B200_FAST_NC=2 for the narrow variant)
     int select_chunk;           // chunk capacity of select_walk_kernel (4096; $KLT_B200_SELECT_CHUNK shrinks it for tests)
 };
 

@@ -231,12 +231,16 @@ eigen_kernel(const float *__restrict__ sat, size_t plane, const __grid_constant_
 // Separate from the eigen kernels on purpose: those are register- and latency-critical; this pass re-reads 4 B per candidate
 // at full occupancy (~2 us per 1080p image).
 #define HIST_ROWS 8
+#define HIST_COPIES 1          // same-address shared-memory atomics serialise and neighbouring candidates share bins, but the
+                               // obvious remedies measured worse per 8 x 1080p: 1 copy 66 us; four copies selected by lane 162 us;
+                               // __match_any_sync aggregation 146 us
 __global__ void __launch_bounds__(256)
 select_hist_kernel(const __grid_constant__ SelDev S) {
-    __shared__ unsigned int h[SEL_BINS];
+    extern __shared__ unsigned int hsm[];                // [HIST_COPIES][SEL_BINS]
     const int b = blockIdx.y;
-    for (int k = threadIdx.x; k < SEL_BINS; k += 256) h[k] = 0;
+    for (int k = threadIdx.x; k < HIST_COPIES * SEL_BINS; k += 256) hsm[k] = 0;
     __syncthreads();
+    unsigned int *h = hsm + (threadIdx.x & (HIST_COPIES - 1)) * SEL_BINS;
     const float *vmap = S.vmap + (size_t)b * S.ncand;
     const unsigned char *pm = S.premap ? S.premap + (size_t)b * S.map_stride : nullptr;
     // few, long-lived blocks: the flush below costs up to SEL_BINS global atomics per block
@@ -252,8 +256,12 @@ select_hist_kernel(const __grid_constant__ SelDev S) {
     }
     __syncthreads();
     unsigned int *hist = S.hist + (size_t)b * SEL_BINS;
-    for (int k = threadIdx.x; k < SEL_BINS; k += 256)
-        if (h[k]) atomicAdd(&hist[k], h[k]);
+    for (int k = threadIdx.x; k < SEL_BINS; k += 256) {
+        unsigned int c = 0;
+#pragma unroll
+        for (int q = 0; q < HIST_COPIES; q++) c += hsm[q * SEL_BINS + k];
+        if (c) atomicAdd(&hist[k], c);
+    }
 }
 
 // ---- plan: which bins to sort first ---------------------------------------------------------------------------------
@@ -613,88 +621,62 @@ select_walk_kernel(const __grid_constant__ SelDev S, int presorted) {
                     // is accepted; what the accepted ones suppress dies; repeat.  "No smaller rank within r" is tested conservatively
                     // on cells: every live candidate publishes its rank with atomicMin in its cell (side r + 1), and a candidate is
                     // accepted when no cell of its 3x3 neighbourhood holds a smaller rank.  That can only delay an acceptance to a
-                    // later round, never change it; the smallest live rank is always accepted, so the rounds terminate.  Thread t
-                    // owns the ranks NPT * t .. NPT * t + NPT - 1; the k-th accepted candidate (in rank order) takes the k-th
-                    // fillable slot, and what does not fit any more is dropped -- exactly where the sequential walk stops.
-                    {
-                        const int NPT = (S.ch + WALK_THREADS - 1) / WALK_THREADS;      // <= 4
-                        int px[4], py[4], pcell[4], pst[4];                            // state: 0 live, 1 accepted, 2 dead / none
-                        float pval[4];
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const int i = tid * NPT + j;
-                            const bool valid = j < NPT && i < ns;
-                            const unsigned long long k = valid ? ~sk[i] : 0ull;
-                            px[j] = (int)((k >> 13) & 8191ull); py[j] = (int)(k & 8191ull);
-                            pval[j] = __uint_as_float((unsigned int)(k >> 26));
-                            pcell[j] = (py[j] / S.cs) * S.gw + px[j] / S.cs;
-                            pst[j] = valid ? (S.r >= 0 ? 0 : 1) : 2;
-                        }
+                    // later round, never change it; the smallest live rank is always accepted, so the rounds terminate.
+                    // The sorted survivors are taken in rank windows (256, 768, then 1024 at a time), one candidate per thread: a
+                    // window first drops what the earlier windows' features suppress, and the walk stops with the window that
+                    // fills the last slot -- replacement (a handful of slots) usually ends inside the first one.  Within a window
+                    // the k-th accepted candidate in rank order takes the k-th fillable slot.
+                    for (int w0 = 0; w0 < ns && !s_full; ) {
+                        const int wlen = w0 == 0 ? 256 : (w0 == 256 ? 768 : WALK_THREADS);
+                        const int i = w0 + tid;
+                        const bool valid = tid < wlen && i < ns;
+                        const unsigned long long k = valid ? ~sk[i] : 0ull;
+                        const int px = (int)((k >> 13) & 8191ull), py = (int)(k & 8191ull);
+                        const int ccx = px / S.cs, ccy = py / S.cs, pcell = ccy * S.gw + ccx;
+                        int pst = valid ? (S.r >= 0 ? 0 : 1) : 2;                     // 0 live, 1 accepted, 2 dead / none
                         if (S.r >= 0) {
-                            for (;;) {
-#pragma unroll
-                                for (int j = 0; j < 4; j++)
-                                    if (pst[j] == 0) atomicMin(&cellmin[pcell[j]], (unsigned int)(tid * NPT + j));
+                            if (pst == 0 && w0 > 0 && grid_conflict(grid, S.gw, S.gh, S.cs, S.r, px, py)) pst = 2;
+                            while (__syncthreads_count(pst == 0) != 0) {
+                                if (pst == 0) atomicMin(&cellmin[pcell], (unsigned int)tid);
                                 __syncthreads();
-                                bool acc_now[4];
+                                bool acc_now = false;
+                                if (pst == 0) {
+                                    unsigned int m = 0xFFFFFFFFu;
 #pragma unroll
-                                for (int j = 0; j < 4; j++) {
-                                    acc_now[j] = false;
-                                    if (pst[j] == 0) {
-                                        const int cx = px[j] / S.cs, cy = py[j] / S.cs;
-                                        unsigned int m = 0xFFFFFFFFu;
+                                    for (int dy = -1; dy <= 1; dy++)
 #pragma unroll
-                                        for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-                                            for (int dx = -1; dx <= 1; dx++) {
-                                                const int ncx = cx + dx, ncy = cy + dy;
-                                                if (ncx >= 0 && ncx < S.gw && ncy >= 0 && ncy < S.gh) m = min(m, cellmin[ncy * S.gw + ncx]);
-                                            }
-                                        acc_now[j] = m == (unsigned int)(tid * NPT + j);
-                                    }
+                                        for (int dx = -1; dx <= 1; dx++) {
+                                            const int ncx = ccx + dx, ncy = ccy + dy;
+                                            if (ncx >= 0 && ncx < S.gw && ncy >= 0 && ncy < S.gh) m = min(m, cellmin[ncy * S.gw + ncx]);
+                                        }
+                                    acc_now = m == (unsigned int)tid;
                                 }
                                 __syncthreads();                      // every read of cellmin is done
-#pragma unroll
-                                for (int j = 0; j < 4; j++)
-                                    if (pst[j] == 0) {
-                                        cellmin[pcell[j]] = 0xFFFFFFFFu;      // leave the array clean for the next round / chunk
-                                        if (acc_now[j]) {
-                                            pst[j] = 1;
-                                            const int cx = px[j] / S.cs, cy = py[j] / S.cs;
-                                            grid[pcell[j]] = (unsigned short)(((px[j] - cx * S.cs) << 8) | (py[j] - cy * S.cs));
-                                        }
+                                if (pst == 0) {
+                                    cellmin[pcell] = 0xFFFFFFFFu;     // leave the array clean for the next round / window
+                                    if (acc_now) {
+                                        pst = 1;
+                                        grid[pcell] = (unsigned short)(((px - ccx * S.cs) << 8) | (py - ccy * S.cs));
                                     }
+                                }
                                 __syncthreads();
-                                int live = 0;
-#pragma unroll
-                                for (int j = 0; j < 4; j++)
-                                    if (pst[j] == 0) {
-                                        if (grid_conflict(grid, S.gw, S.gh, S.cs, S.r, px[j], py[j])) pst[j] = 2; else live = 1;
-                                    }
-                                if (__syncthreads_count(live) == 0) break;
+                                if (pst == 0 && grid_conflict(grid, S.gw, S.gh, S.cs, S.r, px, py)) pst = 2;
                             }
                         }
-                        unsigned int mine = 0;
-#pragma unroll
-                        for (int j = 0; j < 4; j++) mine += pst[j] == 1 ? 1u : 0u;
                         unsigned int tot;
-                        const unsigned int incl = block_scan_incl(mine, warp_cnt, &tot);
+                        const unsigned int incl = block_scan_incl(pst == 1 ? 1u : 0u, warp_cnt, &tot);
                         const int filled = s_filled, room = slots - filled;
-                        int p = (int)(incl - mine);
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            if (pst[j] == 1) {
-                                if (p < room) {
-                                    const int slot = overwrite ? filled + p : free_slots[filled + p];
-                                    fx[slot] = (double)px[j]; fy[slot] = (double)py[j]; fval[slot] = (int)pval[j];
-                                }
-                                p++;
-                            }
+                        if (pst == 1 && (int)incl - 1 < room) {
+                            const int slot = overwrite ? filled + (int)incl - 1 : free_slots[filled + (int)incl - 1];
+                            fx[slot] = (double)px; fy[slot] = (double)py; fval[slot] = (int)__uint_as_float((unsigned int)(k >> 26));
+                        }
                         __syncthreads();                              // s_filled has been read by everyone
                         if (tid == 0) {
                             s_filled = filled + ((int)tot < room ? (int)tot : room);
                             if ((int)tot >= room) s_full = 1;
                         }
+                        __syncthreads();
+                        w0 += wlen;
                     }
                     __syncthreads();
                     consumed += (unsigned long long)mm;
@@ -824,6 +806,7 @@ int klt_sel_prepare_kernels(klt_ctx *ctx, const SelDev *S) {
     // function attributes are set outside any stream capture
     KLT_CUDA(ctx, cudaFuncSetAttribute(sat_rows_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SatSmemV)));
     KLT_CUDA(ctx, cudaFuncSetAttribute(select_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem(S)));
+    KLT_CUDA(ctx, cudaFuncSetAttribute(select_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HIST_COPIES * SEL_BINS * sizeof(unsigned int))));
     return KLT_OK;
 }
 
@@ -866,7 +849,7 @@ int klt_sel_launch_pick(klt_ctx *ctx, const SelDev *S, int B) {
         int nblk = (ctx->num_sms * 4 + B - 1) / B;           // about four blocks per SM over all images
         if (nblk > tiles) nblk = tiles;
         if (nblk < 1) nblk = 1;
-        KLT_LAUNCH(ctx, "select_hist", 4.0 * S->ncand * B, (select_hist_kernel<<<dim3(nblk, B), 256, 0, ctx->stream>>>(*S)));
+        KLT_LAUNCH(ctx, "select_hist", 4.0 * S->ncand * B, (select_hist_kernel<<<dim3(nblk, B), 256, HIST_COPIES * SEL_BINS * sizeof(unsigned int), ctx->stream>>>(*S)));
     }
     KLT_LAUNCH(ctx, "select_plan", 0.0, (select_plan_kernel<<<B, WALK_THREADS, 0, ctx->stream>>>(*S)));
     if (S->ncand)

@@ -99,8 +99,9 @@ eigen_fast_kernel(const float *__restrict__ img0, size_t img_stride, size_t pitc
 // A WARP owns 32 * NC adjacent columns and marches down its row segment; a lane owns NC adjacent columns (one 64/128-bit load
 // per row).  Horizontal neighbours -- three image columns for the 7-tap gradient filters, HH columns of window sums -- come
 // from the adjacent lanes by shuffle; the outermost HL = ceil(6 / NC) lanes on either side are halo lanes.  Everything else is
-// register arithmetic on NC independent columns.  NC = 4 needs ~200 registers (8 warps per SM), NC = 2 ~110 (16 warps).
-#define FQ_PF 3
+// arithmetic on NC independent columns; the vertical window sums run as add-new / subtract-old on a warp-private ring.
+#define FQ_PF 4
+#define FQ_L2PF 16           // rows ahead of the L2 prefetch (the register queue covers an L2 hit, this covers DRAM)
 template <int NC> struct QuadVec;
 template <> struct QuadVec<4> { typedef float4 type; };
 template <> struct QuadVec<2> { typedef float2 type; };
@@ -140,14 +141,27 @@ eigen_fast_quad_kernel(const float *__restrict__ img0, size_t img_stride, size_t
     };
     const bool out_lane = lane >= HL && lane < 32 - HL;
     float *vmap = S.vmap + (size_t)b * S.ncand;
-    float Px[NC][6], Py[NC][6], Qxx[NC][2 * HH], Qxy[NC][2 * HH], Qyy[NC][2 * HH];
+    // vertical window sums: running sums in registers, the last 2 HH + 1 rows of products in a warp-private shared-memory ring
+    // (each lane only ever touches its own NC columns of it: no barrier).  The sums restart with every row segment, so the
+    // rounding drift of add-new / subtract-old stays ~1e-6 relative.
+    constexpr int KR = 2 * HH + 1;
+    extern __shared__ __align__(16) float fq_ring[];                 // [warp][KR][3][32 lanes][NC]
+    vec_t *ring = reinterpret_cast<vec_t *>(fq_ring) + (size_t)warp * KR * 3 * 32 + lane;
+    float Px[NC][6], Py[NC][6], Sxx[NC], Sxy[NC], Syy[NC];
 #pragma unroll
     for (int c = 0; c < NC; c++) {
 #pragma unroll
         for (int m = 0; m < 6; m++) { Px[c][m] = 0.f; Py[c][m] = 0.f; }
-#pragma unroll
-        for (int m = 0; m < 2 * HH; m++) { Qxx[c][m] = 0.f; Qxy[c][m] = 0.f; Qyy[c][m] = 0.f; }
+        Sxx[c] = 0.f; Sxy[c] = 0.f; Syy[c] = 0.f;
     }
+    {
+        vec_t z;
+        float *pz = reinterpret_cast<float *>(&z);
+#pragma unroll
+        for (int c = 0; c < NC; c++) pz[c] = 0.f;
+        for (int k = 0; k < KR * 3; k++) ring[k * 32] = z;
+    }
+    int slot = 0;
     // V[k] = value of column xl - R + k gathered from this lane (cols R .. R+NC-1) and its neighbours
     auto gather = [&](const float (&v)[NC], float *V, int R, int nb) {
 #pragma unroll
@@ -173,9 +187,13 @@ eigen_fast_quad_kernel(const float *__restrict__ img0, size_t img_stride, size_t
 #pragma unroll
             for (int c = 0; c < NC; c++) q[i][c] = q[i + 1][c];
         load_row(min(y + FQ_PF, y_end), q[FQ_PF - 1]);
+        if (y + FQ_L2PF <= y_end && (lane & (NC == 4 ? 7 : 15)) == 0)       // one touch per 128-byte line
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(img + (size_t)klt_reflect(y + FQ_L2PF, H) * pitch + cr[0]));
         float I[NC + 2 * FS_R];                                       // columns xl-3 .. xl+NC+2
         gather(cur, I, FS_R, NB);
         float vxx[NC], vxy[NC], vyy[NC];
+        __align__(16) float nxx[NC], nxy[NC], nyy[NC];
+        const bool gvalid = y >= y0 + 2 * FS_R;
 #pragma unroll
         for (int c = 0; c < NC; c++) {
             const float *r = &I[FS_R + c];
@@ -187,11 +205,20 @@ eigen_fast_quad_kernel(const float *__restrict__ img0, size_t img_stride, size_t
 #pragma unroll
             for (int m = 0; m < 5; m++) { Px[c][m] = fmaf(T.g[5 - m], dh, Px[c][m + 1]); Py[c][m] = fmaf(T.d[5 - m], gh, Py[c][m + 1]); }
             Px[c][5] = T.g[0] * dh; Py[c][5] = T.d[0] * gh;
-            const float pxx = gx * gx, pxy = gx * gy, pyy = gy * gy;
-            vxx[c] = Qxx[c][0] + pxx; vxy[c] = Qxy[c][0] + pxy; vyy[c] = Qyy[c][0] + pyy;
+            // (the first 6 rows of a segment only warm the vertical filters up: their "gradients" stay out of the sums)
+            nxx[c] = gvalid ? gx * gx : 0.f; nxy[c] = gvalid ? gx * gy : 0.f; nyy[c] = gvalid ? gy * gy : 0.f;
+        }
+        {
+            vec_t *rs = ring + (size_t)slot * 3 * 32;
+            const vec_t oxx = rs[0], oxy = rs[32], oyy = rs[64];
+            const float *po0 = reinterpret_cast<const float *>(&oxx), *po1 = reinterpret_cast<const float *>(&oxy), *po2 = reinterpret_cast<const float *>(&oyy);
 #pragma unroll
-            for (int m = 0; m < 2 * HH - 1; m++) { Qxx[c][m] = Qxx[c][m + 1] + pxx; Qxy[c][m] = Qxy[c][m + 1] + pxy; Qyy[c][m] = Qyy[c][m + 1] + pyy; }
-            Qxx[c][2 * HH - 1] = pxx; Qxy[c][2 * HH - 1] = pxy; Qyy[c][2 * HH - 1] = pyy;
+            for (int c = 0; c < NC; c++) {
+                Sxx[c] += nxx[c] - po0[c]; Sxy[c] += nxy[c] - po1[c]; Syy[c] += nyy[c] - po2[c];
+                vxx[c] = Sxx[c]; vxy[c] = Sxy[c]; vyy[c] = Syy[c];
+            }
+            rs[0] = *reinterpret_cast<const vec_t *>(nxx); rs[32] = *reinterpret_cast<const vec_t *>(nxy); rs[64] = *reinterpret_cast<const vec_t *>(nyy);
+            slot = slot + 1 == KR ? 0 : slot + 1;
         }
         const int yc = y - FS_R - HH;
         if (yc >= ys) {                                          // warp-uniform
@@ -231,8 +258,8 @@ static int launch_fast_quad(klt_ctx *ctx, const SelDev *S, int B, const float *i
     if (S->W - 2 * S->bx <= 0 || nrows <= 0) return 1;
     const int n_strips = (ncols + USE - 1) / USE;
     const int strip_blocks = (n_strips + FS_THREADS / 32 - 1) / (FS_THREADS / 32);
-    // one wave of resident blocks (2 per SM at NC = 4, 4 at NC = 2); a segment re-reads 2*(HH+3) warm-up rows: keep it >= 64 rows
-    long nseg = ((long)ctx->num_sms * (NC == 4 ? 2 : 4)) / ((long)strip_blocks * B);
+    // about one wave of resident blocks; a segment re-reads 2*(HH+3) warm-up rows: keep it >= 64 rows
+    long nseg = ((long)ctx->num_sms * 4) / ((long)strip_blocks * B);
     if (nseg < 1) nseg = 1;
     int rows = (int)((nrows + nseg - 1) / nseg);
     if (rows < 64) rows = 64;
@@ -240,10 +267,11 @@ static int launch_fast_quad(klt_ctx *ctx, const SelDev *S, int B, const float *i
     const dim3 grid(strip_blocks, (nrows + rows - 1) / rows, B);
     const double bytes = (4.0 * S->W * S->H + 4.0 * S->ncand) * B;
     const int vec_ok = (pitch % 4) == 0 && (img_stride % 4) == 0 && (reinterpret_cast<uintptr_t>(img0) & 15) == 0;
+    const size_t smem = (size_t)(FS_THREADS / 32) * (2 * HH + 1) * 3 * 32 * NC * sizeof(float);      // <= 43 KB
     if (S->step == 1)
-        KLT_LAUNCH(ctx, "eigen_fast", bytes, (eigen_fast_quad_kernel<HH, NC, true><<<grid, FS_THREADS, 0, ctx->stream>>>(img0, img_stride, pitch, *S, T, rows, n_strips, vec_ok)));
+        KLT_LAUNCH(ctx, "eigen_fast", bytes, (eigen_fast_quad_kernel<HH, NC, true><<<grid, FS_THREADS, smem, ctx->stream>>>(img0, img_stride, pitch, *S, T, rows, n_strips, vec_ok)));
     else
-        KLT_LAUNCH(ctx, "eigen_fast", bytes, (eigen_fast_quad_kernel<HH, NC, false><<<grid, FS_THREADS, 0, ctx->stream>>>(img0, img_stride, pitch, *S, T, rows, n_strips, vec_ok)));
+        KLT_LAUNCH(ctx, "eigen_fast", bytes, (eigen_fast_quad_kernel<HH, NC, false><<<grid, FS_THREADS, smem, ctx->stream>>>(img0, img_stride, pitch, *S, T, rows, n_strips, vec_ok)));
     return 1;
 }
 

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--H", type=int, default=1080)
     ap.add_argument("--W", type=int, default=1920)
     ap.add_argument("--n", type=int, default=1000)
+    ap.add_argument("--modes", default="fast,mixed,strict")
     args = ap.parse_args()
     from pyfeaturetrack_b200 import _capi, klt, synth, selectGoodFeatures as sgf, trackFeatures as tf
     ctx = _capi.default_ctx()
@@ -37,9 +38,10 @@ def main():
         dfr = ctx.device_alloc(frames.nbytes)
         ctx.memcpy(dfr, frames, frames.nbytes)
         ctx.sync()
-        for (pname, prec, sname, smode) in (("windowed", _capi.PRECISION_FAST_WINDOWED, "fast", _capi.SELECT_FAST),
-                                            ("windowed", _capi.PRECISION_FAST_WINDOWED, "strict", _capi.SELECT_STRICT),
-                                            ("strict", _capi.PRECISION_STRICT, "strict", _capi.SELECT_STRICT)):
+        all_modes = {"fast": ("windowed", _capi.PRECISION_FAST_WINDOWED, "fast", _capi.SELECT_FAST),
+                     "mixed": ("windowed", _capi.PRECISION_FAST_WINDOWED, "strict", _capi.SELECT_STRICT),
+                     "strict": ("strict", _capi.PRECISION_STRICT, "strict", _capi.SELECT_STRICT)}
+        for (pname, prec, sname, smode) in [all_modes[m] for m in args.modes.split(",")]:
             q = _capi.Sequence(ctx, params, taps, W, H, B, n, prec, smode)
             q.start(dfr)
             for k in range(1, 6):
