@@ -22,6 +22,8 @@
 // Arithmetic: float32 FMA, the same tap order as the dense FAST kernels (c[0..6] left to right / top to bottom), so the
 // window gradients agree with the planes `stream_grad_kernel` would have written to ~1 ulp; the tracked positions agree
 // with the dense FAST path to ~1e-5 px.  STRICT pyramids never come here.
+#include <stdlib.h>
+
 #include "klt_common.cuh"
 #include "klt_track_args.cuh"
 
@@ -82,20 +84,30 @@ __device__ __forceinline__ void stage_region(float *__restrict__ dst, const floa
         const float *src = img + (size_t)sy0 * pitch + sx0;
         constexpr int C0 = N < 16 ? N : 16;
         const int half = lane >> 4, col = lane & 15;
+        const ptrdiff_t step2 = 2 * (ptrdiff_t)pitch;
         if (col < C0) {
-            const float *p = src + half * pitch + col;
+            // running pointers: one 64-bit add per copy instead of a multiply-add chain per (row, pitch) pair
+            const float *p = src + (ptrdiff_t)half * pitch + col;
             float *q = dst + half * NP + col;
 #pragma unroll
             for (int ry = 0; ry < N; ry += 2) {
-                if (ry + 1 < N || half == 0) cp_async4(q + ry * NP, p + ry * pitch);
+                if (ry + 1 < N || half == 0) cp_async4(q + ry * NP, p);
+                p += step2;
             }
         }
         if (N > 16) {
+            // the remaining REM = N - 16 columns: lane -> (row parity, column) once, then the same row walk
             constexpr int REM = N - 16;
+            static_assert(2 * REM <= 32, "region wider than 32 columns");
+            const int h2 = lane / REM, c2 = 16 + lane % REM;
+            if (lane < 2 * REM) {
+                const float *p = src + (ptrdiff_t)h2 * pitch + c2;
+                float *q = dst + h2 * NP + c2;
 #pragma unroll
-            for (int idx = lane; idx < REM * N; idx += 32) {
-                const int ry = idx / REM, rx = 16 + idx - ry * REM;
-                cp_async4(dst + ry * NP + rx, src + ry * pitch + rx);
+                for (int ry = 0; ry < N; ry += 2) {
+                    if (ry + 1 < N || h2 == 0) cp_async4(q + ry * NP, p);
+                    p += step2;
+                }
             }
         }
     } else {
@@ -452,6 +464,14 @@ int klt_launch_track_windowed(klt_ctx *ctx, const TrackArgs &A, const klt_pyr *p
     flip7(p2->hx->taps.grad_gauss, K.g2); flip7(p2->hx->taps.grad_deriv, K.d2);
     K.same = 1;
     for (int j = 0; j < 7; j++) K.same = K.same && K.g1[j] == K.g2[j] && K.d1[j] == K.d2[j];
+    // second generation (two features per warp, TMA staging) unless $KLT_B200_WINDOWED_GEN=1; windows wider than
+    // $KLT_B200_WINDOWED2_MAXW stay on this file's kernel
+    static const int gen = getenv("KLT_B200_WINDOWED_GEN") ? atoi(getenv("KLT_B200_WINDOWED_GEN")) : 2;
+    static const int maxw2 = getenv("KLT_B200_WINDOWED2_MAXW") ? atoi(getenv("KLT_B200_WINDOWED2_MAXW")) : 15;
+    if (gen != 1 && A.w <= maxw2) {
+        const int rc = klt_launch_track_windowed2(ctx, A, K, p1, p2, x_dev, y_dev, val_dev, iters_dev, assert_dev);
+        if (rc <= 0) return rc;             // 1: no tensor maps on this driver -> first generation
+    }
     switch (A.w) {
         case 3: return launch_windowed<3>(ctx, A, K, x_dev, y_dev, val_dev, iters_dev, assert_dev);
         case 5: return launch_windowed<5>(ctx, A, K, x_dev, y_dev, val_dev, iters_dev, assert_dev);
