@@ -159,6 +159,27 @@ def lib():
     return _lib
 
 
+_featlist = False
+
+
+def featlist():
+    """libkltfeatlist.so (csrc/featlist.c: feature list <-> arrays through the CPython C API, host glue only), or None when it
+    was not built -- the callers then walk the list in Python."""
+    global _featlist
+    if _featlist is False:
+        path = os.path.join(os.path.dirname(_LIBPATH), "libkltfeatlist.so")
+        try:
+            L = C.PyDLL(path)
+            L.klt_featlist_gather.restype = C.c_int
+            L.klt_featlist_gather.argtypes = [C.py_object, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.klt_featlist_scatter_tracked.restype = C.c_int
+            L.klt_featlist_scatter_tracked.argtypes = [C.py_object, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            _featlist = L
+        except (OSError, AttributeError):
+            _featlist = None
+    return _featlist
+
+
 def ptr(a):
     """Address of a numpy array's data, or an int device pointer passed through."""
     if isinstance(a, np.ndarray):

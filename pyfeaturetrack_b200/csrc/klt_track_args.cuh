@@ -26,6 +26,3 @@ struct WindowedTaps { float g1[7], d1[7], g2[7], d2[7]; int same; /* both images
 bool klt_windowed_supported(const klt_params *p, const klt_pyr *p1, const klt_pyr *p2);
 int klt_launch_track_windowed(klt_ctx *ctx, const TrackArgs &A, const klt_pyr *p1, const klt_pyr *p2, double *x_dev,
                               double *y_dev, int32_t *val_dev, unsigned long long *iters_dev, int *assert_dev);
-// second generation (klt_track_windowed2.cu): KLT_OK, an error (< 0), or 1 = cannot serve this launch
-int klt_launch_track_windowed2(klt_ctx *ctx, const TrackArgs &A, const WindowedTaps &K, const klt_pyr *p1, const klt_pyr *p2,
-                               double *x_dev, double *y_dev, int32_t *val_dev, unsigned long long *iters_dev, int *assert_dev);

@@ -105,6 +105,11 @@ def ComputeImagePyramids(tc, img1, img2):
 
 def _features_to_arrays(featurelist):
     n = len(featurelist)
+    fl = _capi.featlist()
+    if fl is not None and type(featurelist) is list:
+        x, y, val = np.empty(n, np.float64), np.empty(n, np.float64), np.empty(n, np.int32)
+        fl.klt_featlist_gather(featurelist, n, x.ctypes.data, y.ctypes.data, val.ctypes.data)
+        return x, y, val
     val = np.fromiter((f.val for f in featurelist), np.int32, n)
     if n and val.min() >= 0:
         x = np.fromiter((f.x for f in featurelist), np.float64, n)
@@ -176,6 +181,7 @@ def KLTTrackFeatures(tc, img1, img2, featurelist):
     ctx = pyramid1.pyr.ctx
     x, y, val = _features_to_arrays(featurelist)
     was_live = val >= 0
+    old_val = val.copy()
     params = make_params(tc)
     aff = None
     if use_affine:
@@ -189,17 +195,22 @@ def KLTTrackFeatures(tc, img1, img2, featurelist):
         ctx.check(_capi.lib().klt_track_features(ctx.handle, C.byref(params), pyramid1.pyr.handle, pyramid2.pyr.handle,
                                                 len(featurelist), x.ctypes.data, y.ctypes.data, val.ctypes.data, None))
     ctx.mark_synced()          # host arrays: the tracking call waited for the stream
-    xs, ys, vals = x.tolist(), y.tolist(), val.tolist()
-    for feat, live, fx, fy, v in zip(featurelist, was_live.tolist(), xs, ys, vals):
-        if not live:
-            continue                                             # trackFeatures.py:253
-        d = feat.__dict__
-        if v == 0:                                               # KLT_TRACKED
-            d["x"] = fx; d["y"] = fy; d["val"] = 0
-        else:
-            d["x"] = -1.0; d["y"] = -1.0; d["val"] = v
-            if "aff_img" in d:
-                _clear_affine(feat)
+    fl = _capi.featlist()
+    if fl is not None and type(featurelist) is list:
+        fl.klt_featlist_scatter_tracked(featurelist, len(featurelist), x.ctypes.data, y.ctypes.data, val.ctypes.data,
+                                        old_val.ctypes.data)
+    else:
+        xs, ys, vals = x.tolist(), y.tolist(), val.tolist()
+        for feat, live, fx, fy, v in zip(featurelist, was_live.tolist(), xs, ys, vals):
+            if not live:
+                continue                                             # trackFeatures.py:253
+            d = feat.__dict__
+            if v == 0:                                               # KLT_TRACKED
+                d["x"] = fx; d["y"] = fy; d["val"] = 0
+            else:
+                d["x"] = -1.0; d["y"] = -1.0; d["val"] = v
+                if "aff_img" in d:
+                    _clear_affine(feat)
 
     if use_affine:
         has, ax, ay, A = aff.download()

@@ -251,3 +251,74 @@ def test_feature_table_and_history_round_trip():
     with pytest.raises(SystemExit):
         sf.KLTStoreFeatureList(fl[:-1], ft, 0)
     assert isinstance(ft, klt.KLT_FeatureTable) and isinstance(fh, klt.KLT_FeatureHistory)
+
+
+def test_featlist_helper_matches_python_walks():
+    """csrc/featlist.c (the list <-> arrays walks of KLTTrackFeatures through the CPython C API) against the Python loops it
+    replaces: mixed Python / NumPy scalar attributes, lost features, affine templates dropped with the feature."""
+    import copy
+    from pyfeaturetrack_b200 import _capi, build, klt, trackFeatures as tf
+    build.build_featlist()
+    _capi._featlist = False
+    L = _capi.featlist()
+    assert L is not None
+    rng = np.random.default_rng(5)
+    fl = []
+    for i in range(257):
+        f = klt.KLT_Feature()
+        f.x = np.int32(i) if i % 3 else float(i) + 0.25
+        f.y = float(rng.uniform(0, 500))
+        f.val = int(rng.integers(-5, 3)) if i % 2 else np.int32(rng.integers(-5, 3))
+        if i % 4 == 0:
+            f.aff_img, f.aff_img_gradx, f.aff_img_grady = "t", "gx", "gy"
+        fl.append(f)
+    x, y, val = tf._features_to_arrays(fl)
+    _capi._featlist = None
+    try:
+        x2, y2, val2 = tf._features_to_arrays(fl)
+    finally:
+        _capi._featlist = False
+    assert np.array_equal(x, x2) and np.array_equal(y, y2) and np.array_equal(val, val2)
+    assert val.dtype == np.int32 and np.all(x[val < 0] == -1.0)
+    new_val = rng.integers(-4, 1, len(fl)).astype(np.int32)
+    nx, ny = x + 0.5, y - 0.25
+    a, b = copy.deepcopy(fl), copy.deepcopy(fl)
+    L.klt_featlist_scatter_tracked(a, len(a), nx.ctypes.data, ny.ctypes.data, new_val.ctypes.data, val.ctypes.data)
+    for feat, live, fx, fy, v in zip(b, (val >= 0).tolist(), nx.tolist(), ny.tolist(), new_val.tolist()):
+        if not live:
+            continue
+        if v == 0:
+            feat.x, feat.y, feat.val = fx, fy, 0
+        else:
+            feat.x, feat.y, feat.val = -1.0, -1.0, v
+            if "aff_img" in feat.__dict__:
+                tf._clear_affine(feat)
+    for fa, fb in zip(a, b):
+        assert fa.__dict__ == fb.__dict__
+        assert type(fa.val) is type(fb.val) and type(fa.x) is type(fb.x)
+    with pytest.raises(AttributeError):
+        L.klt_featlist_gather([1, 2], 2, x.ctypes.data, y.ctypes.data, val.ctypes.data)
+
+
+def test_pil_pixels_into_staging_array():
+    """_pil_into: PIL 'L' image -> uint8 array in one pass (core paste) and through the chunked raw encoder, odd sizes included."""
+    from PIL import Image
+    from pyfeaturetrack_b200 import selectGoodFeatures as sgf
+    rng = np.random.default_rng(11)
+    for shape in ((37, 53), (240, 320), (481, 643), (1080, 1920)):
+        a = rng.integers(0, 256, shape, dtype=np.uint8)
+        img = Image.fromarray(a)
+        stage = np.zeros(shape, np.uint8)
+        sgf._pil_into(stage, img, shape[1], shape[0])
+        assert np.array_equal(stage, a)
+        # the encoder path (what runs if frombuffer / core paste are not available)
+        real = Image.frombuffer
+        try:
+            Image.frombuffer = None
+            sgf._pil_views.clear()
+            stage[:] = 0
+            sgf._pil_into(stage, img, shape[1], shape[0])
+        finally:
+            Image.frombuffer = real
+            sgf._pil_views.clear()
+        assert np.array_equal(stage, a)
