@@ -231,9 +231,9 @@ eigen_kernel(const float *__restrict__ sat, size_t plane, const __grid_constant_
 // Separate from the eigen kernels on purpose: those are register- and latency-critical; this pass re-reads 4 B per candidate
 // at full occupancy (~2 us per 1080p image).
 #define HIST_ROWS 8
-#define HIST_COPIES 1          // same-address shared-memory atomics serialise and neighbouring candidates share bins, but the
-                               // obvious remedies measured worse per 8 x 1080p: 1 copy 66 us; four copies selected by lane 162 us;
-                               // __match_any_sync aggregation 146 us
+#define HIST_COPIES 1          // same-address shared-memory atomics serialise and neighbouring candidates share bins; per 8 x 1080p:
+                               // 1 copy, one atomic per candidate 66-73 us; four copies selected by lane 162 us; __match_any_sync
+                               // aggregation 146 us; run-length aggregation by shuffle + ballot (below): see profiles/
 __global__ void __launch_bounds__(256)
 select_hist_kernel(const __grid_constant__ SelDev S) {
     extern __shared__ unsigned int hsm[];                // [HIST_COPIES][SEL_BINS]
@@ -247,12 +247,32 @@ select_hist_kernel(const __grid_constant__ SelDev S) {
     const int tiles_x = (S.nx + 255) / 256, tiles = tiles_x * ((S.ny + HIST_ROWS - 1) / HIST_ROWS);
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int i = (tile % tiles_x) * 256 + threadIdx.x, j0 = (tile / tiles_x) * HIST_ROWS;
+        // all loads of the tile first (eigenvalues AND pre-mark bytes, 16 independent requests per thread): with the byte load
+        // behind the `v >= min_val` test the kernel exposed one memory latency per row (79 us per 8 x 1080p, 16 % issue)
         float v[HIST_ROWS];
+        unsigned char m[HIST_ROWS];
 #pragma unroll
-        for (int jj = 0; jj < HIST_ROWS; jj++) v[jj] = (i < S.nx && j0 + jj < S.ny) ? vmap[(size_t)(j0 + jj) * S.nx + i] : 0.f;
+        for (int jj = 0; jj < HIST_ROWS; jj++) {
+            const bool in = i < S.nx && j0 + jj < S.ny;
+            v[jj] = in ? vmap[(size_t)(j0 + jj) * S.nx + i] : 0.f;
+            m[jj] = (in && pm) ? pm[(size_t)(S.by + (j0 + jj) * S.step) * S.W + S.bx + i * S.step] : (unsigned char)(in ? 0 : 1);
+        }
+        // Neighbouring candidates often share a bin and same-address shared-memory atomics serialise, so a warp counts RUNS:
+        // a lane whose bin differs from its left neighbour's adds the length of the run it starts.
+        const int lane = threadIdx.x & 31;
 #pragma unroll
-        for (int jj = 0; jj < HIST_ROWS; jj++)
-            if (v[jj] >= S.min_val && !(pm && pm[(size_t)(S.by + (j0 + jj) * S.step) * S.W + S.bx + i * S.step])) atomicAdd(&h[eig_rbin(v[jj])], 1u);
+        for (int jj = 0; jj < HIST_ROWS; jj++) {
+            const bool ok = !m[jj] && v[jj] >= S.min_val;
+            const int bin = ok ? eig_rbin(v[jj]) : -1;
+            const int left = __shfl_up_sync(0xffffffffu, bin, 1);
+            const bool head = lane == 0 || bin != left;
+            const unsigned int heads = __ballot_sync(0xffffffffu, head);
+            if (head && bin >= 0) {
+                const unsigned int above = lane == 31 ? 0u : heads & (0xfffffffeu << lane);
+                const int next = above ? __ffs(above) - 1 : 32;
+                atomicAdd(&h[bin], (unsigned int)(next - lane));
+            }
+        }
     }
     __syncthreads();
     unsigned int *hist = S.hist + (size_t)b * SEL_BINS;

@@ -7,6 +7,7 @@
 // with no host synchronisation anywhere; from the third step on the whole chain is replayed from a CUDA graph (one graph per
 // pyramid parity).  Host frames are uploaded on a second stream into two alternating staging buffers, so the upload of step k+1
 // overlaps the kernels of step k when the caller does not wait in between.
+#include <cstdlib>
 #include <cstring>
 
 #include "klt_common.cuh"
@@ -31,6 +32,8 @@ struct klt_sequence {
     uint8_t *stage[2];
     size_t stage_bytes, cap_pitch, cap_stride;
     cudaEvent_t stage_free[2], stage_ready[2];
+    cudaEvent_t fork_ev, join_ev;    // the eigenvalue pass of a step runs beside the tracking kernel on the context's second stream
+    int overlap;
     int use_graph;
     cudaGraphExec_t graph[2][2];     // [pyramid parity][replace]
     bool graph_ok[2][2];
@@ -40,11 +43,9 @@ struct klt_sequence {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// selection on the level-0 planes of `p` (all images) into the sequence's feature lists
-static int select_on(klt_ctx *ctx, klt_sequence *q, klt_pyr *p, const SelDev *S) {
-    int rc;
-    if ((rc = klt_sel_launch_begin(ctx, S, q->B))) return rc;
-    int done = 0;
+// eigenvalue maps of the level-0 planes of `p` (all images): the part of a selection that does not depend on the feature lists
+static int eigen_on(klt_ctx *ctx, klt_sequence *q, klt_pyr *p, const SelDev *S) {
+    int rc, done = 0;
     if (q->select_mode == KLT_SELECT_FAST && q->fast_select_ok) {
         done = klt_sel_launch_eigen_fast(ctx, S, q->B, p->level(0, 0, 0), p->plane_floats, p->lv[0].pitch, &q->taps.grad_gauss,
                                          &q->taps.grad_deriv);
@@ -55,6 +56,14 @@ static int select_on(klt_ctx *ctx, klt_sequence *q, klt_pyr *p, const SelDev *S)
         if ((rc = klt_sel_launch_eigen_strict(ctx, S, q->B, p->level(1, 0, 0), p->level(2, 0, 0), p->plane_floats, p->lv[0].pitch,
                                               q->sat))) return rc;
     }
+    return KLT_OK;
+}
+
+// selection on the level-0 planes of `p` (all images) into the sequence's feature lists
+static int select_on(klt_ctx *ctx, klt_sequence *q, klt_pyr *p, const SelDev *S) {
+    int rc;
+    if ((rc = klt_sel_launch_begin(ctx, S, q->B))) return rc;
+    if ((rc = eigen_on(ctx, q, p, S))) return rc;
     return klt_sel_launch_pick(ctx, S, q->B);
 }
 
@@ -65,8 +74,27 @@ static int enqueue_step(klt_ctx *ctx, klt_sequence *q, int par, int replace) {
     const int arith = klt_begin_build(q->pyr[cur], &q->taps, q->precision, &windowed);
     int rc;
     if ((rc = klt_build_u8_device(ctx, q->pyr[cur], q->stage[par], q->cap_pitch, q->cap_stride, &q->taps, arith, 0, q->B, windowed))) return rc;
+    // The eigenvalue maps need the new pyramid only, the rest of the replacement (pre-marking, histogram, walk) needs the
+    // tracked lists: the map pass runs on the second stream beside tracking (both are issue-bound; together they fill the SMs
+    // better than one after the other).  Profiling runs keep one stream so that per-kernel times stay meaningful.
+    const bool fork = replace && q->overlap && !ctx->profiling && ctx->aux_stream;
+    if (fork) {
+        cudaStream_t main = ctx->stream;
+        KLT_CUDA(ctx, cudaEventRecord(q->fork_ev, main));
+        KLT_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, q->fork_ev, 0));
+        ctx->stream = ctx->aux_stream;
+        rc = eigen_on(ctx, q, q->pyr[cur], &q->S_rep);
+        ctx->stream = main;
+        if (rc) return rc;
+        KLT_CUDA(ctx, cudaEventRecord(q->join_ev, ctx->aux_stream));
+    }
     if ((rc = klt_launch_track(ctx, &q->params, q->pyr[prev], q->pyr[cur], q->n, q->fx, q->fy, q->fval, q->iters, q->aflag))) return rc;
     KLT_CUDA(ctx, cudaMemcpyAsync(q->fval_tracked, q->fval, (size_t)q->B * q->n * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (fork) {
+        if ((rc = klt_sel_launch_begin(ctx, &q->S_rep, q->B))) return rc;
+        KLT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, q->join_ev, 0));
+        return klt_sel_launch_pick(ctx, &q->S_rep, q->B);
+    }
     if (replace && (rc = select_on(ctx, q, q->pyr[cur], &q->S_rep))) return rc;
     return KLT_OK;
 }
@@ -120,6 +148,7 @@ int klt_sequence_create(klt_ctx *ctx, const klt_params *params, const klt_taps *
     q->params = *params; q->taps = *taps;
     q->w = w; q->h = h; q->B = n_sequences; q->n = n_features; q->precision = precision; q->select_mode = select_mode;
     q->use_graph = getenv("KLT_B200_NO_GRAPH") ? 0 : 1;
+    q->overlap = (getenv("KLT_B200_SEQ_OVERLAP") && atoi(getenv("KLT_B200_SEQ_OVERLAP")) == 0) ? 0 : 1;
     int rc;
     for (int i = 0; i < 2; i++)
         if ((rc = klt_pyr_create(ctx, w, h, params->n_levels, params->subsampling, n_sequences, &q->pyr[i]))) { klt_sequence_destroy(ctx, q); return rc; }
@@ -146,6 +175,8 @@ int klt_sequence_create(klt_ctx *ctx, const klt_params *params, const klt_taps *
         cudaEventCreateWithFlags(&q->stage_free[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&q->stage_ready[i], cudaEventDisableTiming);
     }
+    cudaEventCreateWithFlags(&q->fork_ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&q->join_ev, cudaEventDisableTiming);
     *out = q;
     return KLT_OK;
 }
@@ -162,6 +193,8 @@ int klt_sequence_destroy(klt_ctx *ctx, klt_sequence *q) {
         if (q->stage_free[i]) cudaEventDestroy(q->stage_free[i]);
         if (q->stage_ready[i]) cudaEventDestroy(q->stage_ready[i]);
     }
+    if (q->fork_ev) cudaEventDestroy(q->fork_ev);
+    if (q->join_ev) cudaEventDestroy(q->join_ev);
     if (q->block) cudaFree(q->block);
     delete q;
     return KLT_OK;

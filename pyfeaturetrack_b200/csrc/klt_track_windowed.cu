@@ -36,7 +36,6 @@ namespace {
 
 constexpr int RG = 3;      // gradient kernel radius served here (grad_sigma = 1.0: 7 taps)
 constexpr int MARGIN = 2;  // pixels of slack around the start window of the second image
-constexpr int V2_WARPS = 4;
 constexpr unsigned FULL = 0xffffffffu;
 
 struct alignas(64) WindowedMaps {
@@ -193,8 +192,9 @@ __device__ __forceinline__ void gradient_pair(const float *__restrict__ in, floa
     __syncwarp();
 }
 
-template <int W, int MINB>
-__global__ void __launch_bounds__(V2_WARPS * 32, MINB)
+// NW warps per CTA: 4 for large batches; 2 when the grid is only a wave or two deep, where finer CTAs shorten the tail
+template <int W, int MINB, int NW>
+__global__ void __launch_bounds__(NW * 32, MINB)
 lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ WindowedTaps K,
                     const __grid_constant__ WindowedMaps M, double *__restrict__ xs, double *__restrict__ ys,
                     int *__restrict__ vals, unsigned long long *__restrict__ iters_total, int *__restrict__ assert_flag) {
@@ -202,7 +202,7 @@ lk_windowed_kernel(const __grid_constant__ TrackArgs A, const __grid_constant__ 
     extern __shared__ __align__(128) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = lane / C::LPF, q = lane % C::LPF;            // feature slot of the warp, lane inside the feature
-    const int f = A.f_begin + (blockIdx.x * V2_WARPS + warp) * C::FPW + h;
+    const int f = A.f_begin + (blockIdx.x * NW + warp) * C::FPW + h;
     bool alive = f < A.total;
     if (alive) alive = vals[f] >= 0;                           // trackFeatures.py:253
     if (!__any_sync(FULL, alive)) return;
@@ -465,14 +465,19 @@ int launch_windowed(klt_ctx *ctx, const TrackArgs &A, const WindowedTaps &K, con
         if (!make_map(&M.m1[l], p1, l, C::P1, C::N1) || !make_map(&M.m2[l], p2, l, C::P2, C::N2))
             return klt_fail(ctx, KLT_ERR_CUDA, "cuTensorMapEncodeTiled failed for pyramid level %d (driver without TMA support?)", l);
     const int nfeat = A.total - A.f_begin;
-    const int per_block = V2_WARPS * C::FPW;
-    const int blocks = (nfeat + per_block - 1) / per_block;
     // algorithmic bytes: the staged regions of both images on every level (restaging not counted) + the feature records
     const double bytes = (double)nfeat * (A.n_levels * 4.0 * (C::N1 * C::N1 + C::N2 * C::N2) + 40.0);
-    const size_t smem = (size_t)V2_WARPS * C::FLOATS * sizeof(float);
     constexpr int MINB = W <= 7 ? 5 : 3;
-    if (smem > 48 * 1024) KLT_CUDA(ctx, cudaFuncSetAttribute(lk_windowed_kernel<W, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KLT_LAUNCH(ctx, "lk_windowed", bytes, (lk_windowed_kernel<W, MINB><<<blocks, V2_WARPS * 32, smem, ctx->stream>>>(A, K, M, x, y, v, it, af)));
+    const int blocks4 = (nfeat + 4 * C::FPW - 1) / (4 * C::FPW);
+    if (blocks4 >= 2 * MINB * ctx->num_sms) {
+        const size_t smem = (size_t)4 * C::FLOATS * sizeof(float);
+        if (smem > 48 * 1024) KLT_CUDA(ctx, cudaFuncSetAttribute(lk_windowed_kernel<W, MINB, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KLT_LAUNCH(ctx, "lk_windowed", bytes, (lk_windowed_kernel<W, MINB, 4><<<blocks4, 128, smem, ctx->stream>>>(A, K, M, x, y, v, it, af)));
+    } else {
+        const int blocks2 = (nfeat + 2 * C::FPW - 1) / (2 * C::FPW);
+        const size_t smem = (size_t)2 * C::FLOATS * sizeof(float);
+        KLT_LAUNCH(ctx, "lk_windowed", bytes, (lk_windowed_kernel<W, 2 * MINB, 2><<<blocks2, 64, smem, ctx->stream>>>(A, K, M, x, y, v, it, af)));
+    }
     return KLT_OK;
 }
 
