@@ -123,6 +123,7 @@ int klt_ctx_create(int device, void *stream, klt_ctx **out) {
     ctx->profiling = false;
     ctx->launches = 0;
     ctx->ws = nullptr; ctx->ws_bytes = 0;
+    ctx->level0_event = nullptr;
     ctx->own_stream = stream == nullptr;
     if (stream) ctx->stream = (cudaStream_t)stream;
     else if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -413,16 +414,23 @@ int klt_build_u8_device(klt_ctx *ctx, klt_pyr *p, const uint8_t *dframes, size_t
         // u8 -> smoothed image only
         rc = klt_stream_smooth0(ctx, dframes, pitch, frame_stride, p, taps, first, count);
         if (rc < 0) return rc;
-        if (rc == 1) return build_rest(ctx, p, taps, precision, false, first, count, true);
+        if (rc == 1) {
+            if (ctx->level0_event) KLT_CUDA(ctx, cudaEventRecord(ctx->level0_event, ctx->stream));
+            return build_rest(ctx, p, taps, precision, false, first, count, true);
+        }
     } else if (precision == KLT_PRECISION_FAST) {
         // fused u8 -> smoothed image + gradient pair of level 0 (one read of the frame, three writes)
         rc = klt_stream_level0(ctx, dframes, pitch, frame_stride, p, taps, first, count);
         if (rc < 0) return rc;
-        if (rc == 1) return build_rest(ctx, p, taps, precision, true, first, count);
+        if (rc == 1) {
+            if (ctx->level0_event) KLT_CUDA(ctx, cudaEventRecord(ctx->level0_event, ctx->stream));
+            return build_rest(ctx, p, taps, precision, true, first, count);
+        }
     }
     // img.convert("F") + KLTComputeSmoothedImage (trackFeatures.py:165-166): one kernel, u8 in, f32 out
     if ((rc = klt_launch_conv_sep_u8(ctx, dframes, pitch, frame_stride, p->level(0, first, 0), p->lv[0].pitch, p->plane_floats,
                                      p->w, p->h, count, &taps->smooth, &taps->smooth, precision))) return rc;
+    if (ctx->level0_event) KLT_CUDA(ctx, cudaEventRecord(ctx->level0_event, ctx->stream));
     return build_rest(ctx, p, taps, precision, false, first, count, windowed);
 }
 

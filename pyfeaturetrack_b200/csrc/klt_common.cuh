@@ -78,6 +78,7 @@ struct klt_ctx {
     cudaStream_t copy_stream;
     cudaStream_t aux_stream;    // second compute stream: tracking of sub-batch i overlaps the pyramid builds of sub-batch i + 1
     cudaEvent_t ov_ev[10];      // [0] entry, [1..8] "sub-batch built", [9] "all tracked"
+    cudaEvent_t level0_event;   // if set, klt_build_u8_device records it right after the level-0 kernel (klt_sequence forks its eigenvalue pass there)
     int overlap_subs;           // sub-batches of the overlapped device path (1 = off, the default: it measured slower; $KLT_B200_OVERLAP_SUBS)
     unsigned long long *iters_dev;   // device counter for calls that do not read it back
     cudaEvent_t chunk_ev[16];

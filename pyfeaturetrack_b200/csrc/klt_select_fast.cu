@@ -100,8 +100,9 @@ eigen_fast_kernel(const float *__restrict__ img0, size_t img_stride, size_t pitc
 // per row).  Horizontal neighbours -- three image columns for the 7-tap gradient filters, HH columns of window sums -- come
 // from the adjacent lanes by shuffle; the outermost HL = ceil(6 / NC) lanes on either side are halo lanes.  Everything else is
 // arithmetic on NC independent columns; the vertical window sums run as add-new / subtract-old on a warp-private ring.
-#define FQ_PF 4
 #define FQ_L2PF 16           // rows ahead of the L2 prefetch (the register queue covers an L2 hit, this covers DRAM)
+// MUFU.SQRT: within 1 ulp of sqrtf without its Newton step and special-case branch (this mode is judged by set overlap)
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 template <int NC> struct QuadVec;
 template <> struct QuadVec<4> { typedef float4 type; };
 template <> struct QuadVec<2> { typedef float2 type; };
@@ -126,9 +127,12 @@ eigen_fast_quad_kernel(const float *__restrict__ img0, size_t img_stride, size_t
 #pragma unroll
     for (int c = 0; c < NC; c++) cr[c] = klt_reflect(xl + c, W);
     const float *img = img0 + (size_t)b * img_stride;
-    float cur[NC], q[FQ_PF][NC];
+    float cur[NC], nxt[NC];
+    // rows of a segment reach at most HH + 3 <= 6 rows beyond the image: one bounce of SciPy's 'reflect' covers them when the
+    // image is taller than that (the launcher sends smaller images to the generic kernel)
+    auto refl = [&](int y) { return y < 0 ? -y - 1 : (y >= H ? 2 * H - y - 1 : y); };
     auto load_row = [&](int y, float (&o)[NC]) {
-        const float *r = img + (size_t)klt_reflect(y, H) * pitch;
+        const float *r = img + (size_t)refl(y) * pitch;
         if (vec) {
             const vec_t v = *reinterpret_cast<const vec_t *>(r + xl);
             const float *pv = reinterpret_cast<const float *>(&v);
@@ -177,23 +181,11 @@ eigen_fast_quad_kernel(const float *__restrict__ img0, size_t img_stride, size_t
         (void)nb;
     };
     const int y0 = ys - HH - FS_R, y_end = ye - 1 + HH + FS_R;
-#pragma unroll
-    for (int i = 0; i < FQ_PF; i++) load_row(min(y0 + i, y_end), q[i]);
-    for (int y = y0; y <= y_end; y++) {
-#pragma unroll
-        for (int c = 0; c < NC; c++) cur[c] = q[0][c];
-#pragma unroll
-        for (int i = 0; i < FQ_PF - 1; i++)
-#pragma unroll
-            for (int c = 0; c < NC; c++) q[i][c] = q[i + 1][c];
-        load_row(min(y + FQ_PF, y_end), q[FQ_PF - 1]);
-        if (y + FQ_L2PF <= y_end && (lane & (NC == 4 ? 7 : 15)) == 0)       // one touch per 128-byte line
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(img + (size_t)klt_reflect(y + FQ_L2PF, H) * pitch + cr[0]));
+    // one row of both gradients for this lane's NC columns: horizontal 7-tap pair from the neighbours' columns, vertical pair
+    // as accumulate-and-shift FMAs (input row y completes gradient row y - 3)
+    auto gradients = [&](const float (&row)[NC], float (&gx)[NC], float (&gy)[NC]) {
         float I[NC + 2 * FS_R];                                       // columns xl-3 .. xl+NC+2
-        gather(cur, I, FS_R, NB);
-        float vxx[NC], vxy[NC], vyy[NC];
-        __align__(16) float nxx[NC], nxy[NC], nyy[NC];
-        const bool gvalid = y >= y0 + 2 * FS_R;
+        gather(row, I, FS_R, NB);
 #pragma unroll
         for (int c = 0; c < NC; c++) {
             const float *r = &I[FS_R + c];
@@ -201,12 +193,36 @@ eigen_fast_quad_kernel(const float *__restrict__ img0, size_t img_stride, size_t
             const float b1 = r[1] - r[-1], b2 = r[2] - r[-2], b3 = r[3] - r[-3];
             const float gh = fmaf(T.g[6], a3, fmaf(T.g[5], a2, fmaf(T.g[4], a1, T.g[3] * r[0])));
             const float dh = fmaf(T.d[6], b3, fmaf(T.d[5], b2, T.d[4] * b1));
-            const float gx = fmaf(T.g[6], dh, Px[c][0]), gy = fmaf(T.d[6], gh, Py[c][0]);
+            gx[c] = fmaf(T.g[6], dh, Px[c][0]); gy[c] = fmaf(T.d[6], gh, Py[c][0]);
 #pragma unroll
             for (int m = 0; m < 5; m++) { Px[c][m] = fmaf(T.g[5 - m], dh, Px[c][m + 1]); Py[c][m] = fmaf(T.d[5 - m], gh, Py[c][m + 1]); }
             Px[c][5] = T.g[0] * dh; Py[c][5] = T.d[0] * gh;
-            // (the first 6 rows of a segment only warm the vertical filters up: their "gradients" stay out of the sums)
-            nxx[c] = gvalid ? gx * gx : 0.f; nxy[c] = gvalid ? gx * gy : 0.f; nyy[c] = gvalid ? gy * gy : 0.f;
+        }
+    };
+    load_row(y0, nxt);
+    // the first 6 rows of a segment only warm the vertical filters up: their "gradients" never enter the window sums
+#pragma unroll 1
+    for (int y = y0; y < y0 + 2 * FS_R; y++) {
+#pragma unroll
+        for (int c = 0; c < NC; c++) cur[c] = nxt[c];
+        load_row(min(y + 1, y_end), nxt);
+        float gx[NC], gy[NC];
+        gradients(cur, gx, gy);
+    }
+#pragma unroll 1
+    for (int y = y0 + 2 * FS_R; y <= y_end; y++) {
+#pragma unroll
+        for (int c = 0; c < NC; c++) cur[c] = nxt[c];
+        load_row(min(y + 1, y_end), nxt);
+        if (y + FQ_L2PF <= y_end && (lane & (NC == 4 ? 7 : 15)) == 0)       // one touch per 128-byte line
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(img + (size_t)refl(y + FQ_L2PF) * pitch + cr[0]));
+        float vxx[NC], vxy[NC], vyy[NC];
+        __align__(16) float nxx[NC], nxy[NC], nyy[NC];
+        {
+            float gx[NC], gy[NC];
+            gradients(cur, gx, gy);
+#pragma unroll
+            for (int c = 0; c < NC; c++) { nxx[c] = gx[c] * gx[c]; nxy[c] = gx[c] * gy[c]; nyy[c] = gy[c] * gy[c]; }
         }
         {
             vec_t *rs = ring + (size_t)slot * 3 * 32;
@@ -243,7 +259,7 @@ eigen_fast_quad_kernel(const float *__restrict__ img0, size_t img_stride, size_t
                     const int x = xl + c, ci = x - S.bx;
                     if (ci >= 0 && x < W - S.bx && (STEP1 || (ci % S.step) == 0)) {
                         const float dd = sx[c] - sy[c];
-                        vrow[STEP1 ? ci : ci / S.step] = 0.5f * ((sx[c] + sy[c]) - sqrtf(fmaf(dd, dd, 4.f * sxy_[c] * sxy_[c])));
+                        vrow[STEP1 ? ci : ci / S.step] = 0.5f * ((sx[c] + sy[c]) - sqrt_approx(fmaf(dd, dd, 4.f * sxy_[c] * sxy_[c])));
                     }
                 }
             }
@@ -303,6 +319,13 @@ int klt_sel_launch_eigen_fast(klt_ctx *ctx, const SelDev *S, int B, const float 
     for (int k = 1; k <= 3; k++)            // the folded form needs the symmetry the reference's kernels have
         if (fabs(gauss->taps[3 + k] - gauss->taps[3 - k]) > 1e-12 || fabs(deriv->taps[3 + k] + deriv->taps[3 - k]) > 1e-12) return 0;
     if (fabs(deriv->taps[3]) > 1e-12) return 0;
+    if (S->H < 16 && S->hh <= 3) {          // the quad kernel's one-bounce row reflection needs an image taller than its halo
+        switch (S->hh) {
+            case 1: return launch_fast<1>(ctx, S, B, img0, img_stride, pitch, T);
+            case 2: return launch_fast<2>(ctx, S, B, img0, img_stride, pitch, T);
+            case 3: return launch_fast<3>(ctx, S, B, img0, img_stride, pitch, T);
+        }
+    }
     switch (S->hh) {
         case 1: return ctx->fast_quad_nc == 2 ? launch_fast_quad<1, 2>(ctx, S, B, img0, img_stride, pitch, T) : launch_fast_quad<1, 4>(ctx, S, B, img0, img_stride, pitch, T);
         case 2: return ctx->fast_quad_nc == 2 ? launch_fast_quad<2, 2>(ctx, S, B, img0, img_stride, pitch, T) : launch_fast_quad<2, 4>(ctx, S, B, img0, img_stride, pitch, T);

@@ -73,14 +73,19 @@ static int enqueue_step(klt_ctx *ctx, klt_sequence *q, int par, int replace) {
     bool windowed;
     const int arith = klt_begin_build(q->pyr[cur], &q->taps, q->precision, &windowed);
     int rc;
-    if ((rc = klt_build_u8_device(ctx, q->pyr[cur], q->stage[par], q->cap_pitch, q->cap_stride, &q->taps, arith, 0, q->B, windowed))) return rc;
-    // The eigenvalue maps need the new pyramid only, the rest of the replacement (pre-marking, histogram, walk) needs the
-    // tracked lists: the map pass runs on the second stream beside tracking (both are issue-bound; together they fill the SMs
-    // better than one after the other).  Profiling runs keep one stream so that per-kernel times stay meaningful.
+    // The eigenvalue maps need the new pyramid only -- the fused fast pass just its level-0 image -- while the rest of the
+    // replacement (pre-marking, histogram, walk) needs the tracked lists: the map pass runs on the second stream beside the
+    // decimations and the tracking kernel (all issue-bound or small; together they fill the SMs better than one after the
+    // other).  Profiling runs keep one stream so that per-kernel times stay meaningful.
     const bool fork = replace && q->overlap && !ctx->profiling && ctx->aux_stream;
+    const bool fork_early = fork && q->select_mode == KLT_SELECT_FAST && q->fast_select_ok;    // forks right after the level-0 kernel
+    ctx->level0_event = fork_early ? q->fork_ev : nullptr;
+    rc = klt_build_u8_device(ctx, q->pyr[cur], q->stage[par], q->cap_pitch, q->cap_stride, &q->taps, arith, 0, q->B, windowed);
+    ctx->level0_event = nullptr;
+    if (rc) return rc;
     if (fork) {
         cudaStream_t main = ctx->stream;
-        KLT_CUDA(ctx, cudaEventRecord(q->fork_ev, main));
+        if (!fork_early) KLT_CUDA(ctx, cudaEventRecord(q->fork_ev, main));
         KLT_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, q->fork_ev, 0));
         ctx->stream = ctx->aux_stream;
         rc = eigen_on(ctx, q, q->pyr[cur], &q->S_rep);
