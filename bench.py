@@ -215,7 +215,7 @@ def run_b200(args):
         # features are mutated in place by tracking: restore them (device->device, part of the step)
         ctx.memcpy(d_x, d_x0, B * n * 8); ctx.memcpy(d_y, d_y0, B * n * 8); ctx.memcpy(d_v, d_v0, B * n * 4)
         # one C-ABI call: two pyramid builds + tracking for the whole batch, frames and lists resident in HBM; the library
-        # overlaps the tracking of a sub-batch with the builds of the next on a second stream (see klt_track_pairs_u8)
+        # runs the two (independent) builds on two streams, then tracks (see klt_track_pairs_u8)
         ctx.check(lib.klt_track_pairs_u8(ctx.handle, C.byref(params), C.byref(taps), prec, p1.handle, p2.handle, d_f1, d_f2,
                                          W, W * H, n, d_x, d_y, d_v))
 
@@ -451,7 +451,7 @@ def run_b200(args):
         kernels[k]["gbps"] = bytes_lk * B / (kernels[k]["ms_per_launch"] * 1e-3) / 1e9
     traffic, traffic_src = None, None
     try:   # DRAM traffic of the dominant kernel from the committed ncu capture (per frame, scaled to this launch)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")))
         if dom in tj["per_frame_bytes"]:
             traffic = tj["per_frame_bytes"][dom] * B
             traffic_src = tj["source"]
@@ -469,8 +469,8 @@ def run_b200(args):
                 "share_of_step": round(r["ms"] / total_kernel_ms, 3),
                 "bytes_per_launch": r["bytes"] / r["launches"], "ms_per_launch": r["ms"] / r["launches"]}
         if dom == "lk_windowed":
-            roof["limiter"] = ("instruction issue, not HBM: ncu shows the issue slots 74 % busy and DRAM at 20 % (profiles/"
-                               "ncu_windowed_r01.txt); the HBM-bound kernels of the step are listed in roofline_streaming")
+            roof["limiter"] = ("instruction issue, not HBM: ncu shows the issue slots 70 % busy and DRAM at 34 % (profiles/"
+                               "ncu_pairs_r02.txt); the HBM-bound kernels of the step are listed in roofline_streaming")
         roof["roofline_streaming"] = {k: round(v["gbps"] / peak, 4) for k, v in kernels.items() if k.startswith("stream_") and v["gbps"]}
     step_s = dev_ms * 1e-3 / args.steps
     e2e_s = e2e_ms * 1e-3 / e2e_steps
@@ -484,9 +484,9 @@ def run_b200(args):
                     "accounting": "SURVEY 8(d): dense gradient planes", "achieved_gbps": round(bytes_pair * B / step_s / 1e9, 1),
                     "frac_of_hbm_peak": round(bytes_pair * B / step_s / 1e9 / peak, 4)}
     pipeline.update({"ms_per_step_without_overlap": round(serial_ms / args.steps, 4),
-                     "overlap": "klt_track_pairs_u8 cuts the resident batch into sub-batches and tracks sub-batch i on a second stream while "
-                                "sub-batch i+1's pyramids are built (issue-bound and HBM-bound kernels share the SMs); the per-kernel "
-                                "durations in `kernels` are measured without overlap",
+                     "overlap": "klt_track_pairs_u8 runs the two pyramid builds of the batch on two streams (the CTAs of one fill the SM "
+                                "slots the other's last wave leaves idle), then the tracking kernel; the per-kernel durations in "
+                                "`kernels` are measured one kernel at a time",
                      "newton_iterations_per_pair": it.value / B, "tracked_fraction": tracked / float(B * n),
                      "wall_ms_per_step": round(dev_wall / args.steps, 4)})
     out = {

@@ -541,6 +541,32 @@ def test_tracking_window_and_pyramid_variants(gpu_ctx, oracle, win, L, ss, shape
             assert np.abs(got[1][both] - want_trk[1][both]).max() <= POS_TOL
 
 
+@pytest.mark.parametrize("win,L,ss", [(3, 3, 2), (5, 3, 2), (9, 2, 4), (11, 2, 2), (13, 3, 2), (15, 2, 2)])
+def test_window_sizes_at_1000_features(gpu_ctx, oracle, win, L, ss):
+    """north_star's 99.9 % / 1e-3 px bar for every window size the windowed tracker is instantiated for (7x7: the full-size
+    configs), on enough features for the fraction to mean something: 1000 features on 600x800 frames."""
+    from pyfeaturetrack_b200 import selectGoodFeatures as sgf, trackFeatures as tf, config
+    imgs = _synth(70 + win, (600, 800), shift=(1.4, -0.8))
+    kw = dict(window_width=win, window_height=win, nPyramidLevels=L, subsampling=ss, max_residue=10.0, mindist=8)
+    p = P(oracle, **kw)
+    tc = make_tc(**kw)
+    n = 1000
+    want_sel = oracle.select_good_features(p, imgs[0], n)
+    assert (want_sel[2] >= 0).sum() >= 990
+    want_trk = oracle.track_features(p, imgs[0], imgs[1], *want_sel)[:3]
+    assert (want_trk[2] == 0).mean() > 0.9
+    for mode in ("fast", "windowed"):
+        config.set_precision(track=mode)
+        f = sgf.KLTSelectGoodFeatures(tc, imgs[0], n)
+        assert_features_equal(fl_arrays(f), want_sel)
+        tf.KLTTrackFeatures(tc, imgs[0], imgs[1], f)
+        got = fl_arrays(f)
+        assert np.mean(got[2] == want_trk[2]) >= 0.999, (mode, win, float(np.mean(got[2] == want_trk[2])))
+        both = (got[2] == 0) & (want_trk[2] == 0)
+        assert np.abs(got[0][both] - want_trk[0][both]).max() <= POS_TOL
+        assert np.abs(got[1][both] - want_trk[1][both]).max() <= POS_TOL
+
+
 def test_random_feature_positions_and_dead_features(gpu_ctx, oracle):
     """Features the caller made up (fractional positions, some dead, some near the border): statuses follow the oracle."""
     from pyfeaturetrack_b200 import klt, trackFeatures as tf, config

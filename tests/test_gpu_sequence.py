@@ -490,3 +490,32 @@ def test_fullsize_golden_config_D_sequence(gpu_ctx, golden_fullsize):
         for k in range(1, nfr):
             assert np.array_equal(got[k][3][s], g[2 * k - 1][2].astype(np.int32))          # status codes after tracking
             eq((got[k][0][s], got[k][1][s], got[k][2][s]), g[2 * k])                        # lists after replacement
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,select", [("windowed", "fast"), ("fast", "strict"), ("strict", "strict")])
+def test_sequence_second_stream_changes_nothing(gpu_ctx, monkeypatch, precision, select):
+    """The eigenvalue pass of a step runs on the context's second stream beside the decimations and the tracking kernel
+    ($KLT_B200_SEQ_OVERLAP, on by default): every list of every frame must equal the single-stream run bit for bit, replayed
+    from the graph and with plain launches."""
+    from pyfeaturetrack_b200 import _capi
+    kw = dict(nPyramidLevels=3, subsampling=2, max_residue=10.0, sequentialMode=True)
+    tc = make_tc(**kw)
+    seqs = _sequence_frames(360, 480, 9, 3, speed=4.0)
+    prec = dict(windowed=_capi.PRECISION_FAST_WINDOWED, fast=_capi.PRECISION_FAST, strict=_capi.PRECISION_STRICT)[precision]
+    sel = _capi.SELECT_FAST if select == "fast" else _capi.SELECT_STRICT
+    runs = {}
+    for overlap in ("1", "0"):
+        for graph in (True, False):
+            monkeypatch.setenv("KLT_B200_SEQ_OVERLAP", overlap)
+            if graph:
+                monkeypatch.delenv("KLT_B200_NO_GRAPH", raising=False)
+            else:
+                monkeypatch.setenv("KLT_B200_NO_GRAPH", "1")
+            runs[(overlap, graph)], used = _run_sequence(gpu_ctx, tc, seqs, 200, prec, sel)
+            assert used == graph
+    ref = runs[("0", False)]
+    for key, got in runs.items():
+        for k in range(len(ref)):
+            for a, b in zip(got[k], ref[k]):
+                assert np.array_equal(a, b), (key, k)
