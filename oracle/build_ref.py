@@ -27,7 +27,7 @@ OUT = os.path.join(HERE, "_ref")
 
 PYX = ["goodFeaturesUtils.pyx", "trackFeaturesUtils.pyx"]
 PY = ["klt.py", "convolve.py", "pyramid.py", "klt_util.py", "error.py",
-      "selectGoodFeatures.py", "trackFeatures.py"]
+      "selectGoodFeatures.py", "trackFeatures.py", "writeFeatures.py"]
 
 
 def _target(f):

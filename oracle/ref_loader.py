@@ -13,6 +13,7 @@ import warnings
 
 REF_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 PY_MODULES = ["error", "klt_util", "convolve", "klt", "pyramid", "selectGoodFeatures", "trackFeatures"]
+OPTIONAL_MODULES = ["writeFeatures"]      # off the hot path; only the PPM overlay test reads it
 EXT_MODULES = ["goodFeaturesUtils", "trackFeaturesUtils"]
 
 
@@ -23,7 +24,7 @@ def available():
 
 class _Finder(importlib.abc.MetaPathFinder):
     def find_spec(self, fullname, path=None, target=None):
-        if fullname in PY_MODULES:
+        if fullname in PY_MODULES or fullname in OPTIONAL_MODULES:
             p = os.path.join(REF_DIR, fullname + ".refbc")
             if os.path.exists(p):
                 return importlib.util.spec_from_file_location(
@@ -53,4 +54,9 @@ def load():
     mods = {name: importlib.import_module(name) for name in PY_MODULES[:5] + EXT_MODULES + PY_MODULES[5:]}
     mods["selectGoodFeatures"].KLT_verbose = 0
     mods["trackFeatures"].KLT_verbose = 0
+    for name in OPTIONAL_MODULES:
+        if os.path.exists(os.path.join(REF_DIR, name + ".refbc")):
+            mods[name] = importlib.import_module(name)
+            if hasattr(mods[name], "KLT_verbose"):
+                mods[name].KLT_verbose = 0
     return mods

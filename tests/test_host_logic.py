@@ -162,21 +162,66 @@ def test_shard_range_partitions():
 
 
 def test_write_feature_list_roundtrip(tmp_path, img01):
+    """C-KLT 1.3.4's feature-list files (the format the reference's stubs at writeFeatures.py:53-82 name the helpers of):
+    text with "%5.1f" and "%3d", binary "KLTFL1", and both read back."""
     from pyfeaturetrack_b200 import klt, writeFeatures as wf, selectGoodFeatures as sgf
     sgf.KLT_verbose = 0
     fl = []
     for i in range(5):
-        f = klt.KLT_Feature(); f.x, f.y, f.val = 10.5 + i, 20.25 + 2 * i, (0 if i % 2 == 0 else -4)
+        f = klt.KLT_Feature(); f.x, f.y, f.val = 10.5 + i, 20.25 + 2 * i, (11046 if i % 2 == 0 else -4)
+        if i % 2:
+            f.x = f.y = -1.0
         fl.append(f)
     wf.KLTWriteFeatureList(fl, str(tmp_path / "fl.bin"), None)
+    raw = open(str(tmp_path / "fl.bin"), "rb").read()
+    assert raw[:6] == b"KLTFL1" and len(raw) == 6 + 4 + 5 * 12
     back = wf.KLTReadFeatureList(str(tmp_path / "fl.bin"))
     assert [(f.x, f.y, f.val) for f in back] == [(f.x, f.y, f.val) for f in fl]
     wf.KLTWriteFeatureList(fl, str(tmp_path / "fl.txt"), "%5.1f")
-    assert "( 10.5, 20.2)=0" in open(str(tmp_path / "fl.txt")).read() or "( 10.5, 20.3)=0" in open(str(tmp_path / "fl.txt")).read()
+    text = open(str(tmp_path / "fl.txt")).read()
+    assert text.startswith("Feel free to place comments here.\n\n\n\n!!! Warning:  This is a KLT data file.  ")
+    assert "------------------------------\nKLT Feature List\n------------------------------\n\nnFeatures = 5\n\n" in text
+    assert "feature | (x,y)=val\n--------+-" + "-" * 20 + "\n" in text
+    assert "      0 | ( 10.5, 20.2)=11046 \n" in text
+    assert "      1 | ( -1.0, -1.0)=   -4 \n" in text
+    back = wf.KLTReadFeatureList(str(tmp_path / "fl.txt"))
+    assert [(f.x, f.val) for f in back] == [(10.5, 11046), (-1.0, -4), (12.5, 11046), (-1.0, -4), (14.5, 11046)]
+    wf.KLTWriteFeatureList(fl, str(tmp_path / "fl3.txt"), "%3d")
+    text = open(str(tmp_path / "fl3.txt")).read()
+    assert "      0 | ( 11, 20)=11046 \n" in text and "      1 | ( -1, -1)=   -4 \n" in text     # rounded unless negative
+    assert "--------+-" + "-" * 16 + "\n" in text
+    with pytest.raises(ValueError):
+        wf.KLTWriteFeatureList(fl, str(tmp_path / "bad.txt"), "5.1f")
     wf.KLTWriteFeatureListToPPM(fl, img01[0], str(tmp_path / "f.ppm"))
     from PIL import Image
     rgb = np.array(Image.open(str(tmp_path / "f.ppm")))
     assert tuple(rgb[20, 11]) == (255, 0, 0) and tuple(rgb[22, 12]) != (255, 0, 0)     # feature 0 drawn, feature 1 (lost) not
+
+
+def test_ppm_overlay_equals_the_reference_file(tmp_path, img01, reference):
+    """KLTWriteFeatureListToPPM against the reference's own function (writeFeatures.py:10-37): same bytes, including features
+    on the image border, rounded positions and lost features."""
+    if "writeFeatures" not in reference:
+        pytest.skip("oracle/_ref predates writeFeatures (python oracle/build_ref.py --force)")
+    from PIL import Image
+    from pyfeaturetrack_b200 import klt, writeFeatures as wf, selectGoodFeatures as sgf
+    sgf.KLT_verbose = 0
+    img = Image.fromarray(img01[0]) if isinstance(img01[0], np.ndarray) else img01[0]
+    w, h = img.size
+    rng = np.random.default_rng(2)
+    fl = []
+    for i in range(60):
+        f = klt.KLT_Feature()
+        f.x, f.y = float(rng.uniform(0, w - 1)), float(rng.uniform(0, h - 1))
+        f.val = int(rng.integers(-5, 5000))
+        fl.append(f)
+    for x, y in ((0.0, 0.0), (w - 1.0, h - 1.0), (0.4, h - 1.4), (w - 0.6, 0.49)):      # corners and edges
+        f = klt.KLT_Feature(); f.x, f.y, f.val = x, y, 7
+        fl.append(f)
+    ours, theirs = str(tmp_path / "ours.ppm"), str(tmp_path / "theirs.ppm")
+    wf.KLTWriteFeatureListToPPM(fl, img, ours)
+    reference["writeFeatures"].KLTWriteFeatureListToPPM(fl, img, theirs)
+    assert open(ours, "rb").read() == open(theirs, "rb").read()
 
 
 def test_precision_modes_and_host_binding():
