@@ -372,7 +372,7 @@ __device__ __forceinline__ unsigned long long make_key(float val, int x, int y) 
     return ~k;
 }
 
-#define SCAT_ROWS 8
+#define SCAT_ROWS 16
 __global__ void __launch_bounds__(256)
 select_scatter_kernel(const __grid_constant__ SelDev S) {
     const int b = blockIdx.z;
@@ -389,10 +389,15 @@ select_scatter_kernel(const __grid_constant__ SelDev S) {
     // (reversed bin <= rb_hi  <=>  (bits >> 16) >= 0x4F7F - rb_hi); values above the histogram's top land in bin 0
     const float vmin = fmaxf(S.min_val, __uint_as_float((0x4F7Fu - min(rb_hi, (unsigned int)(SEL_BINS - 1))) << 16));
     float v[SCAT_ROWS];
+    {
+        const int j0 = blockIdx.y * SCAT_ROWS;
+        const int nrows = i < S.nx ? min(SCAT_ROWS, S.ny - j0) : 0;
+        const float *vp = vmap + (size_t)j0 * S.nx + i;
 #pragma unroll
-    for (int jj = 0; jj < SCAT_ROWS; jj++) {
-        const int j = blockIdx.y * SCAT_ROWS + jj;
-        v[jj] = (i < S.nx && j < S.ny) ? vmap[(size_t)j * S.nx + i] : 0.f;
+        for (int jj = 0; jj < SCAT_ROWS; jj++) {
+            v[jj] = jj < nrows ? *vp : 0.f;
+            vp += S.nx;
+        }
     }
 #pragma unroll
     for (int jj = 0; jj < SCAT_ROWS; jj++) {
