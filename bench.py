@@ -518,10 +518,17 @@ def run_b200(args):
                       "seconds": round(sus_ms * 1e-3, 3), "ms_per_step": round(sus_ms / sus_steps, 4),
                       "vs_burst": round((dev_ms / args.steps) / (sus_ms / sus_steps), 4), "clocks": sus_clocks},
     }
-    # the host-fed numbers against what this box's host memory system can feed N GPUs at once (tools/h2d_probe.py, measured
-    # on the 8-GPU box of this pool; a PCIe / host-memory ceiling, not a kernel property)
+    # the host-fed numbers against what THIS box's host memory system can feed N GPUs at once, measured live: every rank does
+    # nothing but upload its pinned frames, all ranks at the same time (a PCIe / host-memory ceiling, not a kernel property;
+    # tools/h2d_probe.py and profiles/h2d_ceiling_r02.json hold the same probe from another box of the pool)
+    ceil = None
     try:
-        ceil = json.load(open(os.path.join(ROOT, "profiles", "h2d_ceiling_r02.json")))["per_n"].get(str(world))
+        def h2d_only():
+            ctx.memcpy(d_f1, f1, frame_bytes); ctx.memcpy(d_f2, f2, frame_bytes)
+        probe_steps = 12
+        probe_ms, _, _ = timed(h2d_only, probe_steps, 3)
+        per_rank = 2 * frame_bytes * probe_steps / (probe_ms * 1e-3) / 1e9
+        ceil = {"gbps_per_rank": round(per_rank, 2), "gbps_aggregate": round(per_rank * world, 1)}
     except Exception:
         ceil = None
     h2d_gbps = (2 * frame_bytes + feat_bytes) / e2e_s / 1e9
@@ -529,7 +536,7 @@ def run_b200(args):
     if ceil:
         out["e2e"]["h2d_ceiling_gbps_per_gpu"] = ceil["gbps_per_rank"]
         out["e2e"]["frac_of_h2d_ceiling"] = round(h2d_gbps / ceil["gbps_per_rank"], 4)
-        out["e2e"]["ceiling_source"] = "profiles/h2d_ceiling_r02.json: %d ranks copying pinned memory at once reach %.1f GB/s each (%.1f aggregate) on this host" % (
+        out["e2e"]["ceiling_source"] = "measured in this run: %d rank(s) doing nothing but cudaMemcpyAsync of their pinned frames at the same time reach %.1f GB/s each (%.1f aggregate, slowest rank) on this host" % (
             world, ceil["gbps_per_rank"], ceil["gbps_aggregate"])
         if seq is not None:
             sg = seq["e2e"]["h2d_bytes_per_step"] / (seq["e2e"]["ms_per_step"] * 1e-3) / 1e9

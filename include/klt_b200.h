@@ -64,7 +64,7 @@ typedef enum klt_status {
 typedef struct klt_ctx klt_ctx; /* one per (device, stream) */
 typedef struct klt_pyr klt_pyr; /* a batch of image pyramids: intensity, gradx, grady for every level */
 typedef struct klt_affine klt_affine; /* per-feature affine-consistency state (templates, template centre, 2x2 map) */
-typedef struct klt_sequence klt_sequence; /* B lock-stepped sequences: two pyramid batches, device-resident feature lists */
+typedef struct klt_sequence klt_sequence; /* B lock-stepped sequences: rotating pyramid batches, device-resident feature lists */
 
 /* how the minimum-eigenvalue map of a selection is computed */
 #define KLT_SELECT_STRICT 0 /* float32 summed-area tables built by the reference's sequential chains (goodFeaturesUtils.pyx:49-51):
@@ -290,10 +290,12 @@ int klt_async_wait(klt_ctx *ctx, int slot);
 /* ---- sequences: KLTTrackFeatures in tc.sequentialMode (pyramid reuse, trackFeatures.py:152-161,401-404) followed by
  * KLTReplaceLostFeatures (_KLTSelectGoodFeatures(REPLACING_SOME) on tc.pyramid_last's gradients,
  * selectGoodFeatures.py:176-179,45-135) for n_sequences independent, lock-stepped sequences -- BASELINE config D.
- * A klt_sequence owns two pyramid batches (previous / current frame), the device-resident feature lists
- * [n_sequences][n_features] and the selection workspace.  One step = one pyramid build + one tracking launch + one
- * selection chain for all sequences, enqueued without any host synchronisation and, from the third step on, replayed from
- * a CUDA graph.  precision: KLT_PRECISION_* of the pyramid builds (and with it the tracker's arithmetic); select_mode:
+ * A klt_sequence owns three pyramid batches and eigenvalue maps in rotation (previous / current frame / the frame whose
+ * build is already running), the device-resident feature lists [n_sequences][n_features] and the selection workspace.
+ * One step = one pyramid build + one tracking launch + one selection chain for all sequences, enqueued without any host
+ * synchronisation; the frame-only half of a step (build, eigenvalue maps) runs on the sequence's own stream and overlaps the
+ * list-dependent half of the previous step when the caller does not wait in between; after a warm-up both halves are
+ * replayed from CUDA graphs.  precision: KLT_PRECISION_* of the pyramid builds (and with it the tracker's arithmetic); select_mode:
  * KLT_SELECT_*.  With KLT_PRECISION_STRICT + KLT_SELECT_STRICT every list equals the reference's bit for bit. */
 int klt_sequence_create(klt_ctx *ctx, const klt_params *params, const klt_taps *taps, int w, int h, int n_sequences,
                         int n_features, int precision, int select_mode, klt_sequence **out);

@@ -519,3 +519,52 @@ def test_sequence_second_stream_changes_nothing(gpu_ctx, monkeypatch, precision,
         for k in range(len(ref)):
             for a, b in zip(got[k], ref[k]):
                 assert np.array_equal(a, b), (key, k)
+
+
+@pytest.mark.parametrize("precision,select,shape,B", [("windowed", "fast", (1080, 1920), 8), ("windowed", "strict", (1080, 1920), 8),
+                                                       ("strict", "strict", (480, 640), 4), ("fast", "strict", (480, 640), 4)])
+def test_sequence_run_ahead_equals_step_by_step(gpu_ctx, monkeypatch, precision, select, shape, B):
+    """The front half of step k + 1 (build, eigenvalue maps) overlaps the back half of step k (tracking, replacement) only when
+    the host does not wait between steps.  24 steps enqueued back to back -- device-resident frames, results copied into one
+    pinned set per step, one synchronisation at the end -- must equal the same run with a synchronisation after every step and
+    the single-stream run, list by list."""
+    from pyfeaturetrack_b200 import _capi, selectGoodFeatures as sgf, trackFeatures as tf
+    kw = dict(nPyramidLevels=3, subsampling=2, max_residue=10.0, sequentialMode=True)
+    tc = make_tc(**kw)
+    H, W = shape
+    n, nfr = 500, 25
+    seqs = _sequence_frames(H, W, nfr, 2, speed=4.0)
+    frames = np.ascontiguousarray(np.stack([np.stack([seqs[s % 2][(k + s // 2) % nfr] for s in range(B)]) for k in range(nfr)]))
+    prec = dict(windowed=_capi.PRECISION_FAST_WINDOWED, fast=_capi.PRECISION_FAST, strict=_capi.PRECISION_STRICT)[precision]
+    sel = _capi.SELECT_FAST if select == "fast" else _capi.SELECT_STRICT
+    dfr = gpu_ctx.device_alloc(frames.nbytes)
+    gpu_ctx.memcpy(dfr, frames, frames.nbytes)
+    gpu_ctx.sync()
+    per = B * H * W
+    runs = {}
+    try:
+        for mode in ("run_ahead", "stepwise", "one_stream"):
+            monkeypatch.setenv("KLT_B200_SEQ_OVERLAP", "0" if mode == "one_stream" else "1")
+            q = _capi.Sequence(gpu_ctx, sgf.make_params(tc), tf._taps_for_one_image(tc), W, H, B, n, prec, sel)
+            outs = [(gpu_ctx.pinned_array((B, n), np.float64), gpu_ctx.pinned_array((B, n), np.float64),
+                     gpu_ctx.pinned_array((B, n), np.int32), gpu_ctx.pinned_array((B, n), np.int32)) for _ in range(nfr - 1)]
+            q.start(dfr)
+            for k in range(1, nfr):
+                q.step(dfr + k * per, out=outs[k - 1])
+                if mode == "stepwise":
+                    q.sync()
+            q.sync()
+            assert q.uses_graph()
+            runs[mode] = [tuple(np.array(a) for a in o) for o in outs]
+            q.close()
+            for o in outs:
+                for a in o:
+                    gpu_ctx.free_pinned(a)
+    finally:
+        gpu_ctx.device_free(dfr)
+    lost = sum(int((o[3] != 0).sum()) for o in runs["one_stream"])
+    assert lost > 0, "the scenario loses no feature: nothing would be replaced"
+    for mode in ("run_ahead", "stepwise"):
+        for k, (got, want) in enumerate(zip(runs[mode], runs["one_stream"])):
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b), (mode, k)
