@@ -250,13 +250,17 @@ select_hist_kernel(const __grid_constant__ SelDev S) {
     // row (79 us per 8 x 1080p at 16 % issue), without the look-ahead one per tile (58 us).
     float v[HIST_ROWS], vn[HIST_ROWS];
     unsigned char m[HIST_ROWS], mn[HIST_ROWS];
+    // (32-bit element offsets -- one image's map and frame are far below 2^31 elements -- and the range test once per tile:
+    // with 64-bit index chains per load the kernel was instruction-bound at 54 instructions per warp-row)
     auto load_tile = [&](int tile, float (&vv)[HIST_ROWS], unsigned char (&mm)[HIST_ROWS]) {
         const int i = (tile % tiles_x) * 256 + threadIdx.x, j0 = (tile / tiles_x) * HIST_ROWS;
+        const int nrows = (tile < tiles && i < S.nx) ? S.ny - j0 : 0;               // rows [0, nrows) of the tile exist
+        const int voff = j0 * S.nx + i, moff = (S.by + j0 * S.step) * S.W + S.bx + i * S.step, mrow = S.step * S.W;
 #pragma unroll
         for (int jj = 0; jj < HIST_ROWS; jj++) {
-            const bool in = tile < tiles && i < S.nx && j0 + jj < S.ny;
-            vv[jj] = in ? vmap[(size_t)(j0 + jj) * S.nx + i] : 0.f;
-            mm[jj] = (in && pm) ? pm[(size_t)(S.by + (j0 + jj) * S.step) * S.W + S.bx + i * S.step] : (unsigned char)(in ? 0 : 1);
+            const bool in = jj < nrows;
+            vv[jj] = in ? vmap[voff + jj * S.nx] : 0.f;
+            mm[jj] = in ? (pm ? pm[moff + jj * mrow] : (unsigned char)0) : (unsigned char)1;
         }
     };
     const int lane = threadIdx.x & 31;
