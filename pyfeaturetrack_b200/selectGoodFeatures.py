@@ -238,6 +238,11 @@ def _KLTSelectGoodFeatures(tc, img, nFeatures, mode, featurelist=None):
         pyr = tc.pyramid_last.pyr          # level-0 gradients of the last tracked image (selectGoodFeatures.py:176-179)
     else:
         pyr = _selection_pyramid(tc, img)
+    if tc.writeInternalImages:
+        # selectGoodFeatures.py:201-204 (the reference's own dump dies on ndarray.save; this writes the files it names)
+        from .klt_util import KLTWriteFloatImageToPGM
+        for which, name in ((0, "kltimg_sgfrlf.pgm"), (1, "kltimg_sgfrlf_gx.pgm"), (2, "kltimg_sgfrlf_gy.pgm")):
+            KLTWriteFloatImageToPGM(pyr.download(which, 0), name)
     if tc.mindist < 0:
         KLTWarning("(_KLTSelectGoodFeatures) Tracking context field tc.mindist is negative ({0}); setting to zero".format(tc.mindist))
         tc.mindist = 0

@@ -179,6 +179,14 @@ def KLTTrackFeatures(tc, img1, img2, featurelist):
     finally:
         _hint.density = None
     ctx = pyramid1.pyr.ctx
+    if tc.writeInternalImages:
+        # trackFeatures.py:186-196 (the reference's own dump dies on ndarray.save; this writes the files it names)
+        from .klt_util import KLTWriteFloatImageToPGM
+        for i in range(int(tc.nPyramidLevels)):
+            for tag, p, gx, gy in (("i", pyramid1, pyramid1_gradx, pyramid1_grady), ("j", pyramid2, pyramid2_gradx, pyramid2_grady)):
+                KLTWriteFloatImageToPGM(p.img[i], "kltimg_tf_{0}{1}.pgm".format(tag, i))
+                KLTWriteFloatImageToPGM(gx.img[i], "kltimg_tf_{0}{1}_gx.pgm".format(tag, i))
+                KLTWriteFloatImageToPGM(gy.img[i], "kltimg_tf_{0}{1}_gy.pgm".format(tag, i))
     x, y, val = _features_to_arrays(featurelist)
     was_live = val >= 0
     old_val = val.copy()
@@ -237,5 +245,5 @@ def KLTTrackFeatures(tc, img1, img2, featurelist):
 
     if KLT_verbose >= 1:
         print("\n\t{0} features successfully tracked.".format(KLTCountRemainingFeatures(featurelist)))
-        # (tc.writeInternalImages: the reference's dumps crash here -- it calls PIL's .save on ndarrays, trackFeatures.py:186-196 --
-        # and this build keeps the pyramids on the device; tc.pyramid_last.img[i] downloads a level for whoever wants a dump)
+        if tc.writeInternalImages:
+            print("\tWrote images to 'kltimg_tf*.pgm'.")

@@ -924,3 +924,32 @@ def test_plain_c_demo_tracks_the_known_shift(gpu_ctx, tmp_path):
     assert m, r.stdout
     assert int(m.group(1)) >= 0.8 * int(m.group(2))
     assert abs(float(m.group(3)) - 3.0) < 0.1 and abs(float(m.group(4)) - 2.0) < 0.1
+
+
+@pytest.mark.gpu
+def test_write_internal_images_dumps(gpu_ctx, oracle, img01, tmp_path, monkeypatch):
+    """tc.writeInternalImages (selectGoodFeatures.py:201-204, trackFeatures.py:186-196): the dumps the reference names exist and
+    hold the min/max-normalised planes (klt_util.py:6-34) of the images the oracle computes."""
+    from PIL import Image
+    from pyfeaturetrack_b200 import selectGoodFeatures as sgf, trackFeatures as tf, config
+    monkeypatch.chdir(tmp_path)
+    config.set_precision(track="strict", select="strict")
+    tc = make_tc(max_residue=10.0)
+    tc.writeInternalImages = True
+    fl = sgf.KLTSelectGoodFeatures(tc, img01[0], 50)
+    tf.KLTTrackFeatures(tc, img01[0], img01[1], fl)
+    tc.writeInternalImages = False
+    names = ["kltimg_sgfrlf.pgm", "kltimg_sgfrlf_gx.pgm", "kltimg_sgfrlf_gy.pgm"]
+    for i in range(int(tc.nPyramidLevels)):
+        for tag in "ij":
+            names += ["kltimg_tf_%s%d.pgm" % (tag, i), "kltimg_tf_%s%d_gx.pgm" % (tag, i), "kltimg_tf_%s%d_gy.pgm" % (tag, i)]
+    for nme in names:
+        assert (tmp_path / nme).exists(), nme
+    p = P(oracle, max_residue=10.0)
+    a0 = np.asarray(img01[0])
+    smooth = oracle.smooth_image(p, a0) if hasattr(oracle, "smooth_image") else None
+    got = np.array(Image.open(str(tmp_path / "kltimg_sgfrlf.pgm")))
+    assert got.shape == a0.shape and got.min() == 0 and got.max() >= 254
+    if smooth is not None:
+        want = ((smooth - smooth.min()) * (255.0 / (smooth.max() - smooth.min()))).astype(np.uint8)
+        assert np.abs(got.astype(int) - want.astype(int)).max() <= 1
