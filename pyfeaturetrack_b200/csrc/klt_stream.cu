@@ -298,6 +298,247 @@ stream_smooth0_kernel(const unsigned char *__restrict__ frames, size_t pitch, si
     else smooth0_rows<RS, false>(b0, sel0, (unsigned int)pitch, H, ys, t0, t1, writer, p_img, out_pitch, T);
 }
 
+// ---- the same kernel, two strips per warp, packed arithmetic (round 2, second generation) -----------------------------
+// ncu showed stream_smooth0_kernel at 68 % of its issue slots with the FMA pipe at 37 % and DRAM at 62 %: it is bound by
+// instruction issue (65 instructions per lane-row, 40 of them FFMA/FMUL), also when its output stays in L2 (8-frame
+// launches of the sequence path: 69 % issue, 19 % DRAM).  sm_100 has packed fp32 arithmetic (PTX fma.rn.f32x2, SASS
+// FFMA2: two FMAs per issue slot, a scalar multiplier may come from the uniform register file), so here one warp marches
+// down TWO adjacent strips A and B = A + 120 columns and every filter value lives in a 64-bit register pair (A, B):
+// the horizontal taps and the pending vertical sums are FFMA2s on such pairs, the conversions and shuffles write the two
+// halves of a pair directly (no packing moves), and the LAST vertical FMA of a row runs as two scalar FFMAs whose
+// destinations are the four consecutive registers each 128-bit store needs (no unpacking moves either): 44 floating
+// point instructions per 8 pixels instead of 80, ~40 % fewer issue slots per pixel overall.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ float lo2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ f32x2 fma2(float c, f32x2 v, f32x2 acc) {
+    f32x2 d; const f32x2 cc = pack2(c, c);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(cc), "l"(v), "l"(acc));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(float c, f32x2 v) {
+    f32x2 d; const f32x2 cc = pack2(c, c);
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(cc), "l"(v));
+    return d;
+}
+
+template <int RS, bool INTERIOR, bool STORE>
+__device__ __forceinline__ void smooth0x2_row(const unsigned char *__restrict__ bA, const unsigned char *__restrict__ bB,
+                                              unsigned int &offs, unsigned int &wA, unsigned int &wB, unsigned int selA,
+                                              unsigned int selB, unsigned int upitch, unsigned int pf_delta, int H, int t, int t1,
+                                              bool writerA, bool writerB, float *&pA, float *&pB, int out_pitch,
+                                              f32x2 (&sa)[4][2 * RS], const StreamTaps &T) {
+    const unsigned int qA = __byte_perm(wA, 0u, selA), qB = __byte_perm(wB, 0u, selB);
+    float uA[4], uB[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { uA[i] = u8_byte_to_f32(qA, i); uB[i] = u8_byte_to_f32(qB, i); }
+    if (INTERIOR) {
+        offs += upitch;                                            // one row past the segment is still inside the image
+        wA = __ldg(reinterpret_cast<const unsigned int *>(bA + offs));
+        wB = __ldg(reinterpret_cast<const unsigned int *>(bB + offs));
+        prefetch_l2(bA + offs + pf_delta);                         // lanes 0..15 pull strip A's line, 16..31 strip B's
+    } else {
+        const unsigned int ro = (unsigned int)reflect1(min(t + 1, t1 - 1), H) * upitch;
+        wA = __ldg(reinterpret_cast<const unsigned int *>(bA + ro));
+        wB = __ldg(reinterpret_cast<const unsigned int *>(bB + ro));
+        const int tp = t + PREFETCH_ROWS;
+        if (tp < t1) {
+            const unsigned int rp = (unsigned int)reflect1(tp, H) * upitch;
+            prefetch_l2(bA + rp);
+            prefetch_l2(bB + rp);
+        }
+    }
+    f32x2 U[4 + 2 * RS];
+#pragma unroll
+    for (int i = 0; i < 4; i++) U[RS + i] = pack2(uA[i], uB[i]);
+#pragma unroll
+    for (int k = 0; k < RS; k++) {
+        U[k] = pack2(__shfl_up_sync(FULLMASK, uA[4 - RS + k], 1), __shfl_up_sync(FULLMASK, uB[4 - RS + k], 1));
+        U[RS + 4 + k] = pack2(__shfl_down_sync(FULLMASK, uA[k], 1), __shfl_down_sync(FULLMASK, uB[k], 1));
+    }
+    float oA[4], oB[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        f32x2 h = mul2(T.s[0], U[i]);
+#pragma unroll
+        for (int j = 1; j < 2 * RS + 1; j++) h = fma2(T.s[j], U[i + j], h);
+        // vertical accumulate-and-shift on the pair; the completed row leaves through two scalar FMAs
+        if (STORE) {
+            oA[i] = fmaf(T.s[2 * RS], lo2(h), lo2(sa[i][0]));
+            oB[i] = fmaf(T.s[2 * RS], hi2(h), hi2(sa[i][0]));
+        }
+#pragma unroll
+        for (int m = 0; m < 2 * RS - 1; m++) sa[i][m] = fma2(T.s[2 * RS - 1 - m], h, sa[i][m + 1]);
+        sa[i][2 * RS - 1] = mul2(T.s[0], h);
+    }
+    if (STORE) {
+        if (writerA) *reinterpret_cast<float4 *>(pA) = make_float4(oA[0], oA[1], oA[2], oA[3]);
+        if (writerB) *reinterpret_cast<float4 *>(pB) = make_float4(oB[0], oB[1], oB[2], oB[3]);
+        pA += out_pitch;
+        pB += out_pitch;
+    }
+}
+
+template <int RS, bool INTERIOR>
+__device__ __forceinline__ void smooth0x2_rows(const unsigned char *__restrict__ bA, const unsigned char *__restrict__ bB,
+                                               unsigned int selA, unsigned int selB, unsigned int upitch, unsigned int pf_delta,
+                                               int H, int t0, int t1, bool writerA, bool writerB, float *pA, float *pB,
+                                               int out_pitch, const StreamTaps &T) {
+    f32x2 sa[4][2 * RS];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int m = 0; m < 2 * RS; m++) sa[i][m] = 0ull;
+    unsigned int offs = (unsigned int)(INTERIOR ? t0 : reflect1(t0, H)) * upitch;
+    unsigned int wA = __ldg(reinterpret_cast<const unsigned int *>(bA + offs));
+    unsigned int wB = __ldg(reinterpret_cast<const unsigned int *>(bB + offs));
+    int t = t0;
+    for (; t < t0 + 2 * RS; t++)                       // warm-up rows: nothing to store yet (t - RS < ys)
+        smooth0x2_row<RS, INTERIOR, false>(bA, bB, offs, wA, wB, selA, selB, upitch, pf_delta, H, t, t1, writerA, writerB, pA, pB,
+                                           out_pitch, sa, T);
+#pragma unroll 2
+    for (; t < t1; t++)
+        smooth0x2_row<RS, INTERIOR, true>(bA, bB, offs, wA, wB, selA, selB, upitch, pf_delta, H, t, t1, writerA, writerB, pA, pB,
+                                          out_pitch, sa, T);
+}
+
+template <int RS>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
+stream_smooth0x2_kernel(const unsigned char *__restrict__ frames, size_t pitch, size_t frame_stride, float *__restrict__ img,
+                        int out_pitch, size_t out_stride, int W, int H, int rows_per_seg, int n_pairs,
+                        const __grid_constant__ StreamTaps T) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pair = blockIdx.x * WARPS_PER_CTA + warp;           // strips 2 * pair (A) and 2 * pair + 1 (B)
+    if (pair >= n_pairs) return;
+    const int ys = blockIdx.y * rows_per_seg, ye = min(H, ys + rows_per_seg);
+    const int cA = pair * 240 + 4 * (lane - 1), cB = cA + 120;
+    const unsigned char *src = frames + (size_t)blockIdx.z * frame_stride;
+    bool rvA, rvB;
+    const int mA = mirror_quad(cA, W, rvA), mB = mirror_quad(cB, W, rvB);
+    const unsigned char *bA = src + mA, *bB = src + mB;
+    const unsigned int selA = rvA ? 0x0123u : 0x3210u, selB = rvB ? 0x0123u : 0x3210u;
+    const bool inner = lane >= 1 && lane <= 30;
+    const bool writerA = inner && cA < W, writerB = inner && cB < W;
+    float *pA = img + (size_t)blockIdx.z * out_stride + (size_t)ys * out_pitch + cA, *pB = pA + 120;
+    const int t0 = ys - RS, t1 = ye + RS;
+    const unsigned int upitch = (unsigned int)pitch;
+    // L2 prefetch PREFETCH_ROWS - 1 rows below the row being loaded: the 32 lanes spread over the 248 bytes of the two
+    // strips (8 bytes apart), so that every 128-byte line of the row segment is touched by one instruction
+    const int pc = min(max(pair * 240 - 4 + 8 * lane, 0), W - 4);
+    const unsigned int pf_delta = (PREFETCH_ROWS - 1) * upitch + (unsigned int)(pc - mA);
+    if (t0 >= 0 && t1 + PREFETCH_ROWS <= H)
+        smooth0x2_rows<RS, true>(bA, bB, selA, selB, upitch, pf_delta, H, t0, t1, writerA, writerB, pA, pB, out_pitch, T);
+    else
+        smooth0x2_rows<RS, false>(bA, bB, selA, selB, upitch, pf_delta, H, t0, t1, writerA, writerB, pA, pB, out_pitch, T);
+}
+
+// ---- third generation: one CTA owns whole rows and stores them with bulk copies -------------------------------------------
+// Cutting 40 % of the instructions changed nothing (123 us per 64 x 1080p before and after): the kernel is bound by how
+// its stores reach DRAM.  Each warp of the kernels above writes a 480-byte piece per row and then jumps a whole image
+// row ahead, so the GPU emits ~4000 interleaved piece streams.  Here a CTA of 8 warps covers 1920 columns (a whole 1080p row),
+// the warps deposit their quads in a shared-memory ring, and after every ROWS_PER_GROUP rows one thread hands the group
+// to the bulk-copy engine (cp.async.bulk.global.shared::cta, SASS UBLKCP): the store stream of a CTA is then linear in
+// memory, KB at a time.  Three groups rotate: the group being filled, the one being copied, and one of slack, so a
+// single CTA barrier per group suffices (thread 0 waits for the copy before last to have left shared memory before it
+// arrives at the barrier that releases that slot).
+#define ROWCTA_WARPS 8
+#define ROWS_PER_GROUP 4
+#define ROWCTA_GROUPS 3
+#define ROWCTA_COLS (ROWCTA_WARPS * 240)
+
+__device__ __forceinline__ void bulk_store_row_group(float *gdst, const float *ssrc, unsigned int bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((unsigned int)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
+}
+
+template <int RS, bool INTERIOR>
+__device__ __forceinline__ void smooth0r_rows(const unsigned char *__restrict__ bA, const unsigned char *__restrict__ bB,
+                                              unsigned int selA, unsigned int selB, unsigned int upitch, unsigned int pf_delta,
+                                              int H, int t0, int t1, bool writerA, bool writerB, float *smem,
+                                              int colA, int cta_cols, float *gout, int out_pitch, const StreamTaps &T) {
+    f32x2 sa[4][2 * RS];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int m = 0; m < 2 * RS; m++) sa[i][m] = 0ull;
+    unsigned int offs = (unsigned int)(INTERIOR ? t0 : reflect1(t0, H)) * upitch;
+    unsigned int wA = __ldg(reinterpret_cast<const unsigned int *>(bA + offs));
+    unsigned int wB = __ldg(reinterpret_cast<const unsigned int *>(bB + offs));
+    int t = t0;
+    float *pA = smem + colA, *pB = pA + 120;
+    for (; t < t0 + 2 * RS; t++)                       // warm-up rows: nothing to store yet
+        smooth0x2_row<RS, INTERIOR, false>(bA, bB, offs, wA, wB, selA, selB, upitch, pf_delta, H, t, t1, writerA, writerB, pA, pB,
+                                           cta_cols, sa, T);
+    const bool contiguous = out_pitch == cta_cols;     // the CTA's rows follow each other in memory: one copy per group
+    int g = 0;
+    while (t < t1) {
+        const int nrows = min(ROWS_PER_GROUP, t1 - t);
+        float *slot = smem + (size_t)(g % ROWCTA_GROUPS) * ROWS_PER_GROUP * cta_cols;
+        pA = slot + colA;
+        pB = pA + 120;
+        if (nrows == ROWS_PER_GROUP) {
+#pragma unroll
+            for (int k = 0; k < ROWS_PER_GROUP; k++)
+                smooth0x2_row<RS, INTERIOR, true>(bA, bB, offs, wA, wB, selA, selB, upitch, pf_delta, H, t + k, t1, writerA, writerB,
+                                                  pA, pB, cta_cols, sa, T);
+        } else {
+            for (int k = 0; k < nrows; k++)
+                smooth0x2_row<RS, INTERIOR, true>(bA, bB, offs, wA, wB, selA, selB, upitch, pf_delta, H, t + k, t1, writerA, writerB,
+                                                  pA, pB, cta_cols, sa, T);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the copy engine
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (contiguous) bulk_store_row_group(gout, slot, (unsigned int)(nrows * cta_cols * 4));
+            else
+                for (int k = 0; k < nrows; k++)
+                    bulk_store_row_group(gout + (size_t)k * out_pitch, slot + (size_t)k * cta_cols, (unsigned int)(cta_cols * 4));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the group before this one has left its slot
+        }
+        gout += (size_t)nrows * out_pitch;
+        t += nrows;
+        g++;
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <int RS>
+__global__ void __launch_bounds__(ROWCTA_WARPS * 32, 2)
+stream_smooth0r_kernel(const unsigned char *__restrict__ frames, size_t pitch, size_t frame_stride, float *__restrict__ img,
+                       int out_pitch, size_t out_stride, int W, int H, int rows_per_seg, int n_pairs,
+                       const __grid_constant__ StreamTaps T) {
+    extern __shared__ __align__(128) float rowcta_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // strips 2 * pair (A) and 2 * pair + 1 (B); warps past the last pair of a narrow image run along on clamped addresses
+    // with their writers off (every warp must reach the CTA barriers)
+    const int pair = blockIdx.x * ROWCTA_WARPS + warp;
+    const int ys = blockIdx.y * rows_per_seg, ye = min(H, ys + rows_per_seg);
+    const int base = blockIdx.x * ROWCTA_COLS;                    // first column of this CTA's rows
+    const int cta_cols = min(W - base, ROWCTA_COLS);
+    const int cA = pair * 240 + 4 * (lane - 1), cB = cA + 120;
+    const unsigned char *src = frames + (size_t)blockIdx.z * frame_stride;
+    bool rvA, rvB;
+    const int mA = mirror_quad(cA, W, rvA), mB = mirror_quad(cB, W, rvB);
+    const unsigned char *bA = src + mA, *bB = src + mB;
+    const unsigned int selA = rvA ? 0x0123u : 0x3210u, selB = rvB ? 0x0123u : 0x3210u;
+    const bool inner = lane >= 1 && lane <= 30;
+    const bool writerA = inner && cA < W, writerB = inner && cB < W;
+    float *gout = img + (size_t)blockIdx.z * out_stride + (size_t)ys * out_pitch + base;
+    const int t0 = ys - RS, t1 = ye + RS;
+    const unsigned int upitch = (unsigned int)pitch;
+    const int pc = min(max(pair * 240 - 4 + 8 * lane, 0), W - 4);
+    const unsigned int pf_delta = (PREFETCH_ROWS - 1) * upitch + (unsigned int)(pc - mA);
+    if (t0 >= 0 && t1 + PREFETCH_ROWS <= H)
+        smooth0r_rows<RS, true>(bA, bB, selA, selB, upitch, pf_delta, H, t0, t1, writerA, writerB, rowcta_smem, cA - base,
+                                cta_cols, gout, out_pitch, T);
+    else
+        smooth0r_rows<RS, false>(bA, bB, selA, selB, upitch, pf_delta, H, t0, t1, writerA, writerB, rowcta_smem, cA - base,
+                                 cta_cols, gout, out_pitch, T);
+}
+
 // ---- gradients only: float image -> gradx, grady (levels >= 1) ---------------------------------------------------
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 stream_grad_kernel(const float *__restrict__ in, int in_pitch, size_t in_stride, float *__restrict__ gxo,
@@ -441,6 +682,153 @@ stream_down2_kernel(const float *__restrict__ in, int in_pitch, size_t in_stride
             load_pair(min(j + 3, j1 - 1), B);
         }
     }
+}
+
+// ---- the same step on packed arithmetic (round 2, second generation) ------------------------------------------------------
+// stream_down2_kernel issues ~225 instructions per lane and row pair (4 output pixels), 132 of them FFMA/FMUL, at 60-65 % of
+// the issue slots with DRAM at 63-72 % (ncu): co-limited.  This version keeps the geometry and cuts the issue slots:
+//   * horizontal: the 128-bit loads deliver even-aligned column pairs (e[2k], e[2k+1]) in adjacent registers, so taps
+//     (p[2m], p[2m+1]) are applied to such pairs with one FFMA2 (per-half multipliers), the two halves are added at the end
+//     and the eleventh tap is a scalar FMA: 7 instead of 11 instructions per output and input row;
+//   * vertical: the pending sums of output columns (0, 1) and (2, 3) are pairs, updated by FFMA2 with a uniform tap
+//     (11 instead of 22 per row pair and column pair); the completed pairs are the four consecutive registers of the store;
+//   * segments whose rows (including the look-ahead loads and prefetches) lie inside the image walk running pointers
+//     instead of reflecting and multiplying row indices.
+// 78 floating-point instructions per row pair instead of 132.  The sums are associated differently from the scalar kernel
+// (even and odd taps separately), so the two agree to rounding (~1e-7 relative), not bit for bit.
+__device__ __forceinline__ f32x2 fma2v(f32x2 c, f32x2 v, f32x2 acc) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(c), "l"(v), "l"(acc));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2v(f32x2 c, f32x2 v) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(c), "l"(v));
+    return d;
+}
+
+__device__ __forceinline__ void down2p_hrow(const f32x2 (&pk)[5], float p10, float4 a, float4 b, bool warp_rev, bool rva,
+                                            bool rvb, f32x2 (&h2)[2]) {
+    if (warp_rev) {                                  // warp-uniform: only warps touching an image edge reverse quads
+        if (rva) a = make_float4(a.w, a.z, a.y, a.x);
+        if (rvb) b = make_float4(b.w, b.z, b.y, b.x);
+    }
+    f32x2 E[8];                                      // E[k] = input columns (ci - 4 + 2k, ci - 3 + 2k)
+    E[2] = pack2(a.x, a.y); E[3] = pack2(a.z, a.w); E[4] = pack2(b.x, b.y); E[5] = pack2(b.z, b.w);
+    E[0] = pack2(__shfl_up_sync(FULLMASK, b.x, 1), __shfl_up_sync(FULLMASK, b.y, 1));
+    E[1] = pack2(__shfl_up_sync(FULLMASK, b.z, 1), __shfl_up_sync(FULLMASK, b.w, 1));
+    const float r0 = __shfl_down_sync(FULLMASK, a.x, 1), r1 = __shfl_down_sync(FULLMASK, a.y, 1);
+    const float r2 = __shfl_down_sync(FULLMASK, a.z, 1), r3 = __shfl_down_sync(FULLMASK, a.w, 1);
+    const float r4 = __shfl_down_sync(FULLMASK, b.x, 1);
+    E[6] = pack2(r0, r1); E[7] = pack2(r2, r3);
+    const float last[4] = {b.z, r0, r2, r4};        // input column ci + 2i + 6: the eleventh tap of output X + i
+    float h[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {                    // output column X+i is centred on input column ci + 2i + 1
+        f32x2 acc = mul2v(pk[0], E[i]);
+#pragma unroll
+        for (int m = 1; m < 5; m++) acc = fma2v(pk[m], E[i + m], acc);
+        h[i] = fmaf(p10, last[i], lo2(acc) + hi2(acc));
+    }
+    h2[0] = pack2(h[0], h[1]);
+    h2[1] = pack2(h[2], h[3]);
+}
+
+template <bool INTERIOR>
+__device__ __forceinline__ void down2p_rows(const float *__restrict__ src, int in_pitch, int H, int ma, int mb, bool rva, bool rvb,
+                                            bool writer, float *p_out, int out_pitch, int ys, int ye, const StreamTaps &T) {
+    f32x2 pk[5];
+#pragma unroll
+    for (int m = 0; m < 5; m++) pk[m] = pack2(T.p[2 * m], T.p[2 * m + 1]);
+    f32x2 P[2][5];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int m = 0; m < 5; m++) P[i][m] = 0ull;
+    // c[j] multiplies in[2Y+1 + j - 5]; input row r contributes to output Y with j = r - 2Y + 4
+    // pair j: rows 2j, 2j+1; even row 2j completes output Y = j - 3.  The loop takes two pairs per trip, so an odd number of
+    // pairs starts one pair early (that pair only feeds outputs above the segment).
+    const int j1 = ye + 3, j0 = ys - 2 - ((ye - ys + 5) & 1);
+    const bool warp_rev = __any_sync(FULLMASK, rva || rvb);
+    const size_t pitch2 = 2 * (size_t)in_pitch;
+    const float *pn = src + (size_t)(INTERIOR ? 2 * j0 : 0) * in_pitch;     // INTERIOR: even row of the next pair to load
+    int jn = j0;                                                            // otherwise: its index
+    auto load_pair = [&](RowPair &rp) {
+        const float *re, *ro;
+        if (INTERIOR) { re = pn; ro = pn + in_pitch; pn += pitch2; }
+        else {
+            const int j = min(jn, j1 - 1);
+            jn++;
+            re = src + (size_t)reflect1(2 * j, H) * in_pitch; ro = src + (size_t)reflect1(2 * j + 1, H) * in_pitch;
+        }
+        rp.ea = __ldg(reinterpret_cast<const float4 *>(re + ma)); rp.eb = __ldg(reinterpret_cast<const float4 *>(re + mb));
+        rp.oa = __ldg(reinterpret_cast<const float4 *>(ro + ma)); rp.ob = __ldg(reinterpret_cast<const float4 *>(ro + mb));
+    };
+    auto step = [&](const RowPair &cur, int j) {
+        // L2 prefetch of pair j + 3 (INTERIOR: the load pointer stands at pair j + 2)
+        if (INTERIOR) {
+            prefetch_l2(pn + pitch2 + ma);
+            prefetch_l2(pn + pitch2 + in_pitch + ma);
+        } else if (j + 3 < j1) {
+            prefetch_l2(src + (size_t)reflect1(2 * j + 6, H) * in_pitch + ma);
+            prefetch_l2(src + (size_t)reflect1(2 * j + 7, H) * in_pitch + ma);
+        }
+        f32x2 he[2], ho[2];
+        down2p_hrow(pk, T.p[10], cur.ea, cur.eb, warp_rev, rva, rvb, he);
+        down2p_hrow(pk, T.p[10], cur.oa, cur.ob, warp_rev, rva, rvb, ho);
+        f32x2 o[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            // even row 2j: outputs Y=j-3..j+2 take taps 10, 8, 6, 4, 2, 0; odd row 2j+1: Y=j-2..j+2 take 9, 7, 5, 3, 1
+            o[i] = fma2(T.p[10], he[i], P[i][0]);
+            const f32x2 a0 = fma2(T.p[8], he[i], P[i][1]);
+            const f32x2 a1 = fma2(T.p[6], he[i], P[i][2]);
+            const f32x2 a2 = fma2(T.p[4], he[i], P[i][3]);
+            const f32x2 a3 = fma2(T.p[2], he[i], P[i][4]);
+            const f32x2 a4 = mul2(T.p[0], he[i]);
+            P[i][0] = fma2(T.p[9], ho[i], a0);
+            P[i][1] = fma2(T.p[7], ho[i], a1);
+            P[i][2] = fma2(T.p[5], ho[i], a2);
+            P[i][3] = fma2(T.p[3], ho[i], a3);
+            P[i][4] = fma2(T.p[1], ho[i], a4);
+        }
+        if (j - 3 >= ys) {                               // Y = j - 3 < ye by construction
+            if (writer) *reinterpret_cast<float4 *>(p_out) = make_float4(lo2(o[0]), hi2(o[0]), lo2(o[1]), hi2(o[1]));
+            p_out += out_pitch;
+        }
+    };
+    // two row-pair buffers, loop unrolled by two: each buffer is reloaded right after it has been consumed, one full
+    // step before its next use, without register-to-register copies
+    RowPair A, B;
+    load_pair(A);
+    load_pair(B);
+    for (int j = j0; j < j1; j += 2) {
+        step(A, j);
+        load_pair(A);
+        step(B, j + 1);
+        load_pair(B);
+    }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
+stream_down2p_kernel(const float *__restrict__ in, int in_pitch, size_t in_stride, int W, int H, float *__restrict__ out,
+                     int out_pitch, size_t out_stride, int OW, int OH, int rows_per_seg, int n_strips,
+                     const __grid_constant__ StreamTaps T) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x * WARPS_PER_CTA + warp;
+    if (strip >= n_strips) return;
+    const int ys = blockIdx.y * rows_per_seg, ye = min(OH, ys + rows_per_seg);
+    const int X = strip * 120 + 4 * (lane - 1);
+    const int ci = 2 * X;
+    const float *src = in + (size_t)blockIdx.z * in_stride;
+    bool rva, rvb;
+    const int ma = mirror_quad(ci, W, rva), mb = mirror_quad(ci + 4, W, rvb);
+    const bool writer = lane >= 1 && lane <= 30 && X < OW;
+    float *p_out = out + (size_t)blockIdx.z * out_stride + (size_t)ys * out_pitch + X;
+    // interior: every row the loop loads (two pairs of look-ahead past the last one it needs) or prefetches (one more) is
+    // inside the image: rows 2 (ys - 3) .. 2 (ye + 5) + 1
+    if (ys >= 3 && 2 * (ye + 5) + 1 < H) down2p_rows<true>(src, in_pitch, H, ma, mb, rva, rvb, writer, p_out, out_pitch, ys, ye, T);
+    else down2p_rows<false>(src, in_pitch, H, ma, mb, rva, rvb, writer, p_out, out_pitch, ys, ye, T);
 }
 
 // ---- pyramid step for subsampling SS with a (2R+1)-tap gauss, generic form of the kernel above ------------------------
@@ -634,6 +1022,75 @@ int klt_stream_smooth0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t
     if (W < 16 || H < 16 || (W & 3)) return 0;
     if ((reinterpret_cast<uintptr_t>(frames) & 3) || (pitch & 3) || (frame_stride & 3)) return 0;
     const int n_strips = (W + 119) / 120;
+    const double bytes = 5.0 * W * H * count;         // 1 B read + 4 B written per pixel
+    float *img = p->level(0, first, 0);
+    // generations: 3 = whole-row CTAs with bulk stores, 2 = two strips per warp on packed arithmetic, 1 = one strip per warp;
+    // $KLT_B200_SMOOTH0 = 1 / 2 / 3 forces one (A/B runs)
+    static const int forced_gen = [] { const char *e = getenv("KLT_B200_SMOOTH0"); return e && e[0] >= '1' && e[0] <= '3' ? e[0] - '0' : 0; }();
+    const int gen = forced_gen ? (forced_gen == 3 && RS > 2 ? 2 : forced_gen) : (W >= 960 && RS <= 2 ? 3 : 2);
+    const bool one_strip = gen == 1;
+    if (gen == 3 && n_strips >= 2) {
+        const int n_pairs = (n_strips + 1) / 2;
+        const int row_ctas = (n_pairs + ROWCTA_WARPS - 1) / ROWCTA_WARPS;
+        const int cols = W < ROWCTA_COLS ? W : ROWCTA_COLS;
+        const size_t smem = (size_t)ROWCTA_GROUPS * ROWS_PER_GROUP * cols * sizeof(float);
+        const void *fn = RS == 1 ? (const void *)stream_smooth0r_kernel<1> : RS == 2 ? (const void *)stream_smooth0r_kernel<2>
+                       : RS == 3 ? (const void *)stream_smooth0r_kernel<3> : (const void *)stream_smooth0r_kernel<4>;
+        static bool attr_set[5] = {false, false, false, false, false};
+        if (!attr_set[RS]) {
+            KLT_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWCTA_GROUPS * ROWS_PER_GROUP * ROWCTA_COLS * (int)sizeof(float)));
+            attr_set[RS] = true;
+        }
+        int per_sm = 2;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, ROWCTA_WARPS * 32, smem) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 1;
+        }
+        long nseg = (long)ctx->num_sms * per_sm / ((long)row_ctas * count);
+        if (nseg < 1) nseg = 1;
+        long rows3 = (H + nseg - 1) / nseg;
+        if (rows3 < 32) rows3 = 32;
+        if (rows3 > H) rows3 = H;
+        dim3 grid3(row_ctas, (H + (int)rows3 - 1) / (int)rows3, count), block3(ROWCTA_WARPS * 32);
+#define LAUNCH_S0R(R)                                                                                                  \
+    KLT_LAUNCH(ctx, "stream_smooth0", bytes,                                                                           \
+               (stream_smooth0r_kernel<R><<<grid3, block3, smem, ctx->stream>>>(frames, pitch, frame_stride, img,       \
+                                                                                p->lv[0].pitch, p->plane_floats, W, H, \
+                                                                                (int)rows3, n_pairs, T)))
+        switch (RS) {
+            case 1: LAUNCH_S0R(1); break;
+            case 2: LAUNCH_S0R(2); break;
+            case 3: LAUNCH_S0R(3); break;
+            default: LAUNCH_S0R(4); break;
+        }
+#undef LAUNCH_S0R
+        return 1;
+    }
+    if (!one_strip && n_strips >= 2) {
+        const int n_pairs = (n_strips + 1) / 2;
+        const int pair_ctas = (n_pairs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        int rows2 = 0;
+        switch (RS) {
+            case 1: rows2 = pick_rows_per_seg(ctx, stream_smooth0x2_kernel<1>, H, pair_ctas, count, 32); break;
+            case 2: rows2 = pick_rows_per_seg(ctx, stream_smooth0x2_kernel<2>, H, pair_ctas, count, 32); break;
+            case 3: rows2 = pick_rows_per_seg(ctx, stream_smooth0x2_kernel<3>, H, pair_ctas, count, 32); break;
+            default: rows2 = pick_rows_per_seg(ctx, stream_smooth0x2_kernel<4>, H, pair_ctas, count, 32); break;
+        }
+        dim3 grid2(pair_ctas, (H + rows2 - 1) / rows2, count), block2(WARPS_PER_CTA * 32);
+#define LAUNCH_S0X2(R)                                                                                                 \
+    KLT_LAUNCH(ctx, "stream_smooth0", bytes,                                                                           \
+               (stream_smooth0x2_kernel<R><<<grid2, block2, 0, ctx->stream>>>(frames, pitch, frame_stride, img,         \
+                                                                              p->lv[0].pitch, p->plane_floats, W, H,   \
+                                                                              rows2, n_pairs, T)))
+        switch (RS) {
+            case 1: LAUNCH_S0X2(1); break;
+            case 2: LAUNCH_S0X2(2); break;
+            case 3: LAUNCH_S0X2(3); break;
+            default: LAUNCH_S0X2(4); break;
+        }
+#undef LAUNCH_S0X2
+        return 1;
+    }
     const int strip_ctas = (n_strips + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     int rows = 0;
     switch (RS) {
@@ -643,8 +1100,6 @@ int klt_stream_smooth0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t
         default: rows = pick_rows_per_seg(ctx, stream_smooth0_kernel<4>, H, strip_ctas, count, 32); break;
     }
     dim3 grid(strip_ctas, (H + rows - 1) / rows, count), block(WARPS_PER_CTA * 32);
-    const double bytes = 5.0 * W * H * count;         // 1 B read + 4 B written per pixel
-    float *img = p->level(0, first, 0);
 #define LAUNCH_S0(R)                                                                                                   \
     KLT_LAUNCH(ctx, "stream_smooth0", bytes,                                                                           \
                (stream_smooth0_kernel<R><<<grid, block, 0, ctx->stream>>>(frames, pitch, frame_stride, img, p->lv[0].pitch, \
@@ -715,9 +1170,21 @@ int klt_stream_down2(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps, 
     if (!aligned16(p->level(0, first, level - 1)) || !aligned16(p->level(0, first, level)) || (p->plane_floats & 3)) return 0;
     const int n_strips = (b.w + 119) / 120;
     const int strip_ctas = (n_strips + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const double bytes = 4.0 * ((double)a.w * a.h + (double)b.w * b.h) * count;
+    // second generation on packed arithmetic; $KLT_B200_DOWN2=1 keeps the scalar kernel (A/B runs)
+    static const bool scalar_kernel = [] { const char *e = getenv("KLT_B200_DOWN2"); return e && e[0] == '1'; }();
+    if (!scalar_kernel) {
+        int rows2 = pick_rows_per_seg(ctx, stream_down2p_kernel, b.h, strip_ctas, count, 8);
+        if (!(rows2 & 1) && rows2 < b.h) rows2++;        // rows + 5 row pairs per segment: even, so no extra leading pair
+        dim3 grid2(strip_ctas, (b.h + rows2 - 1) / rows2, count), block2(WARPS_PER_CTA * 32);
+        KLT_LAUNCH(ctx, "stream_down2", bytes,
+                   (stream_down2p_kernel<<<grid2, block2, 0, ctx->stream>>>(p->level(0, first, level - 1), a.pitch, p->plane_floats,
+                                                                            a.w, a.h, p->level(0, first, level), b.pitch,
+                                                                            p->plane_floats, b.w, b.h, rows2, n_strips, T)));
+        return 1;
+    }
     const int rows = pick_rows_per_seg(ctx, stream_down2_kernel, b.h, strip_ctas, count, 8);
     dim3 grid(strip_ctas, (b.h + rows - 1) / rows, count), block(WARPS_PER_CTA * 32);
-    const double bytes = 4.0 * ((double)a.w * a.h + (double)b.w * b.h) * count;
     KLT_LAUNCH(ctx, "stream_down2", bytes,
                (stream_down2_kernel<<<grid, block, 0, ctx->stream>>>(p->level(0, first, level - 1), a.pitch, p->plane_floats, a.w,
                                                                      a.h, p->level(0, first, level), b.pitch, p->plane_floats, b.w,

@@ -143,6 +143,73 @@ def test_pyramid_build_u8(gpu_ctx, oracle, cfg):
     pyr.close()
 
 
+_GEN_PROBE = r"""
+import sys, zlib, numpy as np
+sys.path.insert(0, %r)
+from pyfeaturetrack_b200 import _capi, klt, trackFeatures
+ctx = _capi.default_ctx()
+out = []
+for (H, W, L, batch) in [(1080, 1920, 3, 5), (200, 360, 2, 2), (64, 248, 2, 1), (540, 964, 3, 3)]:
+    frames = (np.random.default_rng(H + W).random((batch, H, W)) * 255).astype(np.uint8)
+    tc = klt.KLT_TrackingContext(); tc.nPyramidLevels, tc.subsampling = L, 2; tc.KLTUpdateTCBorder()
+    pyr = _capi.Pyramid(ctx, W, H, L, 2, batch)
+    pyr.build_u8(frames, trackFeatures._taps_for_one_image(tc), _capi.PRECISION_FAST_WINDOWED)
+    for b in range(batch):
+        for l in range(L):
+            a = pyr.download(0, l, b)
+            out.append((zlib.crc32(a.tobytes()), float(a.sum(dtype=np.float64)), float(np.abs(a).max())))
+    pyr.close()
+print(repr(out))
+"""
+
+
+@pytest.mark.parametrize("cfg", [dict(shape=(1080, 1920), L=3, batch=3), dict(shape=(200, 360), L=2, batch=2),
+                                 dict(shape=(64, 248), L=2, batch=1), dict(shape=(540, 964), L=3, batch=2),
+                                 dict(shape=(2160, 3840), L=4, batch=1), dict(shape=(97, 132), L=2, batch=4)])
+def test_image_only_pyramids_vs_oracle(gpu_ctx, oracle, cfg):
+    """The image-only (windowed) build -- the packed two-strip level-0 kernel and the packed decimation -- against the
+    oracle's pyramids: odd and even strip counts, a strip pair whose second strip lies outside the image, segments that
+    touch the top / bottom border and interior ones, widths that are not multiples of 120."""
+    from pyfeaturetrack_b200 import _capi, trackFeatures
+    H, W = cfg["shape"]
+    L, batch = cfg["L"], cfg["batch"]
+    frames = (np.random.default_rng(H * 3 + W).random((batch, H, W)) * 255).astype(np.uint8)
+    p = P(oracle, nPyramidLevels=L, subsampling=2)
+    tc = make_tc(nPyramidLevels=L, subsampling=2)
+    pyr = _capi.Pyramid(gpu_ctx, W, H, L, 2, batch)
+    pyr.build_u8(frames, trackFeatures._taps_for_one_image(tc), _capi.PRECISION_FAST_WINDOWED)
+    for b in range(batch):
+        want = oracle.image_pyramids(p, frames[b])
+        for lvl in range(L):
+            got = pyr.download(0, lvl, b)
+            assert got.shape == want[0][lvl].shape
+            assert np.abs(got - want[0][lvl]).max() <= REL_TOL * 255.0, (b, lvl)
+    pyr.close()
+
+
+def test_kernel_generations_agree():
+    """$KLT_B200_SMOOTH0=1 / 2 / 3 and $KLT_B200_DOWN2=1 select the generations of the streaming kernels.  The packed level-0
+    kernels (two strips per warp; whole-row CTAs with bulk stores) perform the same operations in the same order as the
+    scalar one (bit-identical); the packed decimation associates its sums differently (1e-6 relative)."""
+    import ast
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for name, env in (("new", {}), ("old_smooth0", {"KLT_B200_SMOOTH0": "1"}), ("gen2_smooth0", {"KLT_B200_SMOOTH0": "2"}),
+                      ("old_both", {"KLT_B200_SMOOTH0": "1", "KLT_B200_DOWN2": "1"})):
+        e = dict(os.environ)
+        e.pop("KLT_B200_SMOOTH0", None)
+        e.pop("KLT_B200_DOWN2", None)
+        e.update(env)
+        out = subprocess.run([sys.executable, "-c", _GEN_PROBE % root], env=e, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        res[name] = ast.literal_eval(out.stdout.strip().splitlines()[-1])
+    assert res["new"] == res["old_smooth0"] == res["gen2_smooth0"]    # CRCs of every level: level 0 identical => all identical
+    for (c1, s1, m1), (c2, s2, m2) in zip(res["new"], res["old_both"]):
+        assert abs(s1 - s2) <= 1e-6 * max(abs(s1), 1.0) and abs(m1 - m2) <= 1e-5 * 255.0
+
+
 # ---- selection -----------------------------------------------------------------------------------------------------
 def test_scan_bit_exact(gpu_ctx, oracle, golden):
     from pyfeaturetrack_b200 import goodFeaturesUtils
