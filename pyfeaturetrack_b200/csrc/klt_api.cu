@@ -359,12 +359,12 @@ static int build_gradients(klt_ctx *ctx, klt_pyr *p, const klt_taps *taps, int p
 
 // `windowed`: leave the gradient planes unwritten (KLT_PRECISION_FAST_WINDOWED)
 static int build_rest(klt_ctx *ctx, klt_pyr *p, const klt_taps *taps, int precision, bool level0_grad_done = false,
-                      int first = 0, int count = -1, bool windowed = false) {
+                      int first = 0, int count = -1, bool windowed = false, int first_level = 1) {
     if (count < 0) count = p->batch;
     int rc;
     const size_t stride = p->plane_floats;
     const bool fast = precision == KLT_PRECISION_FAST;
-    for (int l = 1; l < p->n_levels; l++) {
+    for (int l = first_level; l < p->n_levels; l++) {
         const LevelDesc &a = p->lv[l - 1], &b = p->lv[l];
         rc = fast ? klt_stream_down2(ctx, p, l, taps, first, count) : 0;
         if (rc < 0) return rc;
@@ -411,6 +411,13 @@ int klt_build_u8_device(klt_ctx *ctx, klt_pyr *p, const uint8_t *dframes, size_t
                         const klt_taps *taps, int precision, int first, int count, bool windowed) {
     int rc;
     if (windowed) {
+        // u8 -> smoothed image + level 1 in one pass (unless a caller wants to fork right after level 0: klt_sequence's
+        // eigenvalue pass reads level 0 only and runs beside the decimations)
+        if (!ctx->level0_event) {
+            rc = klt_stream_level01(ctx, dframes, pitch, frame_stride, p, taps, first, count);
+            if (rc < 0) return rc;
+            if (rc == 1) return build_rest(ctx, p, taps, precision, false, first, count, true, 2);
+        }
         // u8 -> smoothed image only
         rc = klt_stream_smooth0(ctx, dframes, pitch, frame_stride, p, taps, first, count);
         if (rc < 0) return rc;

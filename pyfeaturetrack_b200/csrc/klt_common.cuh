@@ -161,6 +161,8 @@ int klt_stream_level0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t 
 // u8 frame -> smoothed level-0 image only (image-only pyramids)
 int klt_stream_smooth0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t frame_stride, klt_pyr *p, const klt_taps *taps,
                        int first, int count);
+int klt_stream_level01(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t frame_stride, klt_pyr *p, const klt_taps *taps,
+                       int first, int count);
 int klt_stream_grad(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps, int first, int count);
 int klt_stream_down2(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps, int first, int count);
 

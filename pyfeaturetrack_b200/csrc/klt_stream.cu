@@ -831,6 +831,159 @@ stream_down2p_kernel(const float *__restrict__ in, int in_pitch, size_t in_strid
     else down2p_rows<false>(src, in_pitch, H, ma, mb, rva, rvb, writer, p_out, out_pitch, ys, ye, T);
 }
 
+// ---- levels 0 and 1 of an image-only pyramid in ONE pass --------------------------------------------------------------
+// stream_smooth0 + the first stream_down2 move 5 + 5 bytes per level-0 pixel, 4 of them the re-read of the level-0 image
+// that the decimation needs (64 frames no longer fit L2).  Both kernels sit at 95-97 % of what a trivial linear kernel
+// reaches with their read/write mix (tools/mix_probe.cu), so the only way left to go faster is to move fewer bytes.  Round 1
+// tried this fusion with scalar arithmetic and found it bound by instruction issue (0.143 ms against 0.140 ms for the two
+// kernels); with packed arithmetic it fits.  A lane owns 8 level-0 columns (one 64-bit load of the frame, one 256-bit store
+// of the smoothed row) = 4 level-1 columns; the smoothing runs on pairs (column i, column i + 4), its completed row leaves
+// through scalar FMAs into the eight consecutive registers that are both the store's operand and the (a, b) quads the
+// decimation's horizontal pass wants; even and odd smoothed rows feed the packed vertical accumulators of the decimation
+// exactly as in stream_down2p_kernel.  Beyond the image the smoothed values are those of the reflect-extended frame, which
+// is the reflect-extension of the smoothed image (symmetric filter; see the header comment) -- what the decimation reads
+// there in the two-kernel version.  6 bytes per level-0 pixel instead of 10.
+__device__ __forceinline__ int mirror_oct(int c, int W, bool &rev) {     // aligned block of 8 columns, W % 8 == 0
+    rev = c < 0 || c >= W;
+    const int m = c < 0 ? -c - 8 : (c >= W ? 2 * W - c - 8 : c);
+    return min(max(m, 0), W - 8);
+}
+
+struct L01State {
+    f32x2 sa[4][4];            // pending smoothed rows: pairs (column i, column i + 4), radius 2
+    f32x2 P[2][5];             // pending level-1 rows: pairs of output columns (0, 1), (2, 3)
+    uint2 w;                   // the frame row loaded one iteration ahead
+};
+
+// one frame row t: completes smoothed row t - 2 of the lane's 8 columns (s[0..7]); OUT = the vertical filter is warm
+template <bool INTERIOR, bool OUT>
+__device__ __forceinline__ void l01_smooth_row(L01State &S, const unsigned char *__restrict__ b0, unsigned int &offs,
+                                               unsigned int selx, unsigned int sely, unsigned int upitch, int H, int t, int t_last,
+                                               const StreamTaps &T, float (&s)[8]) {
+    const unsigned int q0 = __byte_perm(S.w.x, S.w.y, selx), q1 = __byte_perm(S.w.x, S.w.y, sely);
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { x[i] = u8_byte_to_f32(q0, i); x[4 + i] = u8_byte_to_f32(q1, i); }
+    if (INTERIOR) {
+        offs += upitch;
+        S.w = __ldg(reinterpret_cast<const uint2 *>(b0 + offs));
+        prefetch_l2(b0 + offs + (PREFETCH_ROWS - 1) * upitch);
+    } else {
+        S.w = __ldg(reinterpret_cast<const uint2 *>(b0 + (unsigned int)reflect1(min(t + 1, t_last), H) * upitch));
+        const int tp = t + PREFETCH_ROWS;
+        if (tp <= t_last) prefetch_l2(b0 + (unsigned int)reflect1(tp, H) * upitch);
+    }
+    const float xl0 = __shfl_up_sync(FULLMASK, x[6], 1), xl1 = __shfl_up_sync(FULLMASK, x[7], 1);
+    const float xr0 = __shfl_down_sync(FULLMASK, x[0], 1), xr1 = __shfl_down_sync(FULLMASK, x[1], 1);
+    // U[k] = (column k - 2, column k + 2): the windows of the first and of the second quad, side by side
+    f32x2 U[8];
+    U[0] = pack2(xl0, x[2]); U[1] = pack2(xl1, x[3]); U[2] = pack2(x[0], x[4]); U[3] = pack2(x[1], x[5]);
+    U[4] = pack2(x[2], x[6]); U[5] = pack2(x[3], x[7]); U[6] = pack2(x[4], xr0); U[7] = pack2(x[5], xr1);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        f32x2 h = mul2(T.s[0], U[i]);
+#pragma unroll
+        for (int j = 1; j < 5; j++) h = fma2(T.s[j], U[i + j], h);
+        if (OUT) {
+            s[i] = fmaf(T.s[4], lo2(h), lo2(S.sa[i][0]));
+            s[4 + i] = fmaf(T.s[4], hi2(h), hi2(S.sa[i][0]));
+        }
+#pragma unroll
+        for (int m = 0; m < 3; m++) S.sa[i][m] = fma2(T.s[3 - m], h, S.sa[i][m + 1]);
+        S.sa[i][3] = mul2(T.s[0], h);
+    }
+}
+
+__device__ __forceinline__ void st256(float *p, const float (&s)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(s[0]), "f"(s[1]), "f"(s[2]), "f"(s[3]),
+                 "f"(s[4]), "f"(s[5]), "f"(s[6]), "f"(s[7])
+                 : "memory");
+}
+
+template <bool INTERIOR>
+__device__ __forceinline__ void l01_rows(const unsigned char *__restrict__ b0, unsigned int selx, unsigned int sely,
+                                         unsigned int upitch, int H, int ys, int ye, int r_end, bool writer0, bool writer1,
+                                         float *p0, int pitch0, float *p1, int pitch1, const StreamTaps &T) {
+    L01State S;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int m = 0; m < 4; m++) S.sa[i][m] = 0ull;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int m = 0; m < 5; m++) S.P[i][m] = 0ull;
+    f32x2 pk[5];
+#pragma unroll
+    for (int m = 0; m < 5; m++) pk[m] = pack2(T.p[2 * m], T.p[2 * m + 1]);
+    // level-1 row Y needs smoothed rows 2Y - 4 .. 2Y + 6: pairs j = ys - 2 .. ye + 2 of smoothed rows (2j, 2j + 1), i.e.
+    // frame rows 2 (ys - 2) - 2 .. 2 (ye + 2) + 3
+    const int j0 = ys - 2, j1 = ye + 3;
+    const int t0 = 2 * j0 - 2, t_last = 2 * (j1 - 1) + 3;
+    unsigned int offs = (unsigned int)(INTERIOR ? t0 : reflect1(t0, H)) * upitch;
+    S.w = __ldg(reinterpret_cast<const uint2 *>(b0 + offs));
+    float s[8];
+#pragma unroll 1
+    for (int t = t0; t < t0 + 4; t++)                  // the smoothing filter warms up
+        l01_smooth_row<INTERIOR, false>(S, b0, offs, selx, sely, upitch, H, t, t_last, T, s);
+#pragma unroll 2
+    for (int j = j0; j < j1; j++) {
+        f32x2 he[2], ho[2];
+        const int r = 2 * j;
+        l01_smooth_row<INTERIOR, true>(S, b0, offs, selx, sely, upitch, H, r + 2, t_last, T, s);
+        if (writer0 && r >= 2 * ys && r < r_end) st256(p0, s);
+        down2p_hrow(pk, T.p[10], make_float4(s[0], s[1], s[2], s[3]), make_float4(s[4], s[5], s[6], s[7]), false, false, false, he);
+        l01_smooth_row<INTERIOR, true>(S, b0, offs, selx, sely, upitch, H, r + 3, t_last, T, s);
+        if (writer0 && r + 1 >= 2 * ys && r + 1 < r_end) st256(p0 + pitch0, s);
+        p0 += 2 * (size_t)pitch0;
+        down2p_hrow(pk, T.p[10], make_float4(s[0], s[1], s[2], s[3]), make_float4(s[4], s[5], s[6], s[7]), false, false, false, ho);
+        f32x2 o[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            o[i] = fma2(T.p[10], he[i], S.P[i][0]);
+            const f32x2 a0 = fma2(T.p[8], he[i], S.P[i][1]);
+            const f32x2 a1 = fma2(T.p[6], he[i], S.P[i][2]);
+            const f32x2 a2 = fma2(T.p[4], he[i], S.P[i][3]);
+            const f32x2 a3 = fma2(T.p[2], he[i], S.P[i][4]);
+            const f32x2 a4 = mul2(T.p[0], he[i]);
+            S.P[i][0] = fma2(T.p[9], ho[i], a0);
+            S.P[i][1] = fma2(T.p[7], ho[i], a1);
+            S.P[i][2] = fma2(T.p[5], ho[i], a2);
+            S.P[i][3] = fma2(T.p[3], ho[i], a3);
+            S.P[i][4] = fma2(T.p[1], ho[i], a4);
+        }
+        if (j - 3 >= ys) {                               // Y = j - 3 < ye by construction
+            if (writer1) *reinterpret_cast<float4 *>(p1) = make_float4(lo2(o[0]), hi2(o[0]), lo2(o[1]), hi2(o[1]));
+            p1 += pitch1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3)
+stream_level01_kernel(const unsigned char *__restrict__ frames, size_t pitch, size_t frame_stride, float *__restrict__ img0,
+                      int pitch0, float *__restrict__ img1, int pitch1, size_t out_stride, int W, int H, int OW, int OH,
+                      int rows_per_seg, int n_strips, const __grid_constant__ StreamTaps T) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x * WARPS_PER_CTA + warp;          // 240 level-0 columns = 120 level-1 columns
+    if (strip >= n_strips) return;
+    const int ys = blockIdx.y * rows_per_seg, ye = min(OH, ys + rows_per_seg);       // level-1 rows
+    const int c0 = strip * 240 + 8 * (lane - 1), X = strip * 120 + 4 * (lane - 1);
+    bool rev;
+    const int m0 = mirror_oct(c0, W, rev);
+    const unsigned char *b0 = frames + (size_t)blockIdx.z * frame_stride + m0;
+    const unsigned int selx = rev ? 0x4567u : 0x3210u, sely = rev ? 0x0123u : 0x7654u;
+    const bool inner = lane >= 1 && lane <= 30;
+    const bool writer0 = inner && c0 < W, writer1 = inner && X < OW;
+    const int r_end = ye == OH ? H : 2 * ye;                      // the last segment also stores the odd last row
+    // level-0 pointer of smoothed row 2 (ys - 2), the first one the loop completes (not stored: rows below 2 ys are the
+    // neighbour segment's)
+    float *p0 = img0 + (size_t)blockIdx.z * out_stride + c0 + ((ptrdiff_t)2 * (ys - 2)) * pitch0;
+    float *p1 = img1 + (size_t)blockIdx.z * out_stride + (size_t)ys * pitch1 + X;
+    const int t0 = 2 * (ys - 2) - 2, t_end = 2 * (ye + 2) + 3 + PREFETCH_ROWS + 1;
+    if (t0 >= 0 && t_end < H) l01_rows<true>(b0, selx, sely, (unsigned int)pitch, H, ys, ye, r_end, writer0, writer1, p0, pitch0, p1, pitch1, T);
+    else l01_rows<false>(b0, selx, sely, (unsigned int)pitch, H, ys, ye, r_end, writer0, writer1, p0, pitch0, p1, pitch1, T);
+}
+
 // ---- pyramid step for subsampling SS with a (2R+1)-tap gauss, generic form of the kernel above ------------------------
 // (used for SS = 4, R = 10: the reference's DEFAULT pyramid, sigma = 0.9 * 4 -> 21 taps).
 // Lane owns 4 output columns = 4*SS input columns [ci, ci + 4*SS); it needs NL = R - SS/2 more on the left and
@@ -1050,6 +1203,8 @@ int klt_stream_smooth0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t
         if (nseg < 1) nseg = 1;
         long rows3 = (H + nseg - 1) / nseg;
         if (rows3 < 32) rows3 = 32;
+        static const int forced_rows = [] { const char *e = getenv("KLT_B200_S0_ROWS"); return e ? atoi(e) : 0; }();   // experiments
+        if (forced_rows > 0) rows3 = forced_rows;
         if (rows3 > H) rows3 = H;
         dim3 grid3(row_ctas, (H + (int)rows3 - 1) / (int)rows3, count), block3(ROWCTA_WARPS * 32);
 #define LAUNCH_S0R(R)                                                                                                  \
@@ -1112,6 +1267,33 @@ int klt_stream_smooth0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t
         default: return 0;
     }
 #undef LAUNCH_S0
+    return 1;
+}
+
+// levels 0 and 1 of an image-only pyramid in one launch; returns 0 when the configuration is not covered
+int klt_stream_level01(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t frame_stride, klt_pyr *p,
+                       const klt_taps *taps, int first, int count) {
+    static const bool disabled = [] { const char *e = getenv("KLT_B200_FUSED01"); return e && e[0] == '0'; }();
+    if (disabled || p->n_levels < 2 || p->ss != 2) return 0;
+    StreamTaps T;
+    if (taps->smooth.n != 5 || !is_symmetric(&taps->smooth) || !fill_taps(&taps->smooth, T.s, 5)) return 0;
+    if (taps->pyramid.n > 11 || !fill_taps(&taps->pyramid, T.p, 11)) return 0;
+    for (int j = 5; j < 9; j++) T.s[j] = 0.f;
+    for (int j = 0; j < 7; j++) { T.g[j] = 0.f; T.d[j] = 0.f; }
+    const LevelDesc &a = p->lv[0], &b = p->lv[1];
+    const int W = p->w, H = p->h;
+    if (W < 64 || H < 32 || (W & 7) || (b.w & 3) || b.w < 8 || b.h < 8) return 0;
+    if ((reinterpret_cast<uintptr_t>(frames) & 7) || (pitch & 7) || (frame_stride & 7)) return 0;
+    float *img0 = p->level(0, first, 0), *img1 = p->level(0, first, 1);
+    if ((reinterpret_cast<uintptr_t>(img0) & 31) || (a.pitch & 7) || (p->plane_floats & 7) || !aligned16(img1)) return 0;
+    const int n_strips = (W + 239) / 240;
+    const int strip_ctas = (n_strips + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int rows = pick_rows_per_seg(ctx, stream_level01_kernel, b.h, strip_ctas, count, 16);
+    dim3 grid(strip_ctas, (b.h + rows - 1) / rows, count), block(WARPS_PER_CTA * 32);
+    const double bytes = (5.0 * W * H + 4.0 * b.w * b.h) * count;     // 1 B read, 4 B + 1 B (a quarter of 4 B) written per pixel
+    KLT_LAUNCH(ctx, "stream_level01", bytes,
+               (stream_level01_kernel<<<grid, block, 0, ctx->stream>>>(frames, pitch, frame_stride, img0, a.pitch, img1, b.pitch,
+                                                                       p->plane_floats, W, H, b.w, b.h, rows, n_strips, T)));
     return 1;
 }
 

@@ -157,7 +157,7 @@ for (H, W, L, batch) in [(1080, 1920, 3, 5), (200, 360, 2, 2), (64, 248, 2, 1), 
     for b in range(batch):
         for l in range(L):
             a = pyr.download(0, l, b)
-            out.append((zlib.crc32(a.tobytes()), float(a.sum(dtype=np.float64)), float(np.abs(a).max())))
+            out.append((l, zlib.crc32(a.tobytes()), float(a.sum(dtype=np.float64)), float(np.abs(a).max())))
     pyr.close()
 print(repr(out))
 """
@@ -188,26 +188,33 @@ def test_image_only_pyramids_vs_oracle(gpu_ctx, oracle, cfg):
 
 
 def test_kernel_generations_agree():
-    """$KLT_B200_SMOOTH0=1 / 2 / 3 and $KLT_B200_DOWN2=1 select the generations of the streaming kernels.  The packed level-0
-    kernels (two strips per warp; whole-row CTAs with bulk stores) perform the same operations in the same order as the
-    scalar one (bit-identical); the packed decimation associates its sums differently (1e-6 relative)."""
+    """$KLT_B200_SMOOTH0=1 / 2 / 3, $KLT_B200_DOWN2=1 and $KLT_B200_FUSED01=0 select the generations of the streaming kernels.
+    Every level-0 kernel (one strip per warp; two strips per warp on packed arithmetic; whole-row CTAs with bulk stores; the
+    fused level-0 + level-1 kernel) performs the same operations in the same order: level 0 is bit-identical.  The packed
+    decimation associates its sums differently from the scalar one, and the fused kernel decimates the smoothed
+    reflect-extended frame instead of the reflect-extended smoothed image: levels >= 1 agree to rounding."""
     import ast
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for name, env in (("new", {}), ("old_smooth0", {"KLT_B200_SMOOTH0": "1"}), ("gen2_smooth0", {"KLT_B200_SMOOTH0": "2"}),
-                      ("old_both", {"KLT_B200_SMOOTH0": "1", "KLT_B200_DOWN2": "1"})):
+    variants = (("fused", {}), ("gen3", {"KLT_B200_FUSED01": "0"}), ("gen1", {"KLT_B200_FUSED01": "0", "KLT_B200_SMOOTH0": "1"}),
+                ("gen2", {"KLT_B200_FUSED01": "0", "KLT_B200_SMOOTH0": "2"}),
+                ("scalar", {"KLT_B200_FUSED01": "0", "KLT_B200_SMOOTH0": "1", "KLT_B200_DOWN2": "1"}))
+    for name, env in variants:
         e = dict(os.environ)
-        e.pop("KLT_B200_SMOOTH0", None)
-        e.pop("KLT_B200_DOWN2", None)
+        for k in ("KLT_B200_SMOOTH0", "KLT_B200_DOWN2", "KLT_B200_FUSED01"):
+            e.pop(k, None)
         e.update(env)
         out = subprocess.run([sys.executable, "-c", _GEN_PROBE % root], env=e, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stderr[-2000:]
         res[name] = ast.literal_eval(out.stdout.strip().splitlines()[-1])
-    assert res["new"] == res["old_smooth0"] == res["gen2_smooth0"]    # CRCs of every level: level 0 identical => all identical
-    for (c1, s1, m1), (c2, s2, m2) in zip(res["new"], res["old_both"]):
-        assert abs(s1 - s2) <= 1e-6 * max(abs(s1), 1.0) and abs(m1 - m2) <= 1e-5 * 255.0
+    assert res["gen3"] == res["gen1"] == res["gen2"]          # CRCs of every level: level 0 identical => all identical
+    for name in ("fused", "scalar"):
+        for (l1, c1, s1, m1), (l2, c2, s2, m2) in zip(res[name], res["gen3"]):
+            if l1 == 0:
+                assert c1 == c2, name
+            assert abs(s1 - s2) <= 1e-6 * max(abs(s1), 1.0) and abs(m1 - m2) <= 1e-5 * 255.0, name
 
 
 # ---- selection -----------------------------------------------------------------------------------------------------
