@@ -142,7 +142,7 @@ def algorithmic_bytes_per_pair(wl, iters_per_pair):
     return 2 * per_frame + lk, per_frame, lk
 
 
-def windowed_bytes_per_pair(wl):
+def windowed_bytes_per_pair(wl, fused01=False):
     """Compulsory traffic of the image-only (windowed) pipeline: no gradient planes; the tracker stages, per feature and
     level, one (W+7)^2 region of the first image and one (W+11)^2 region of the second."""
     P = []
@@ -151,6 +151,8 @@ def windowed_bytes_per_pair(wl):
         P.append(w * h)
         w, h = w // wl["ss"], h // wl["ss"]
     per_frame = 5 * P[0] + sum(4 * (P[i - 1] + P[i]) for i in range(1, wl["L"]))
+    if fused01 and wl["L"] >= 2:      # stream_level01 writes level 1 from registers: level 0 is not read back
+        per_frame -= 4 * P[0]
     lk = wl["n"] * wl["L"] * 4 * ((wl["win"] + 7) ** 2 + (wl["win"] + 11) ** 2)
     return 2 * per_frame + lk, per_frame, lk
 
@@ -472,11 +474,29 @@ def run_b200(args):
             roof["limiter"] = ("instruction issue, not HBM: ncu shows the issue slots 70 % busy and DRAM at 34 % (profiles/"
                                "ncu_pairs_r02.txt); the HBM-bound kernels of the step are listed in roofline_streaming")
         roof["roofline_streaming"] = {k: round(v["gbps"] / peak, 4) for k, v in kernels.items() if k.startswith("stream_") and v["gbps"]}
+        # The peak above is a 1:1 copy.  What HBM sustains depends on the read/write mix and on the launch size, so each
+        # streaming kernel is also stated against a trivial linear kernel moving ITS mix and ITS bytes per launch, timed here
+        # (klt_probe_traffic_mix; DESIGN 'How close are the streaming kernels to what the hardware allows').
+        mix_kind = {"stream_smooth0": _capi.MIX_SMOOTH0, "stream_down2": _capi.MIX_DOWN2, "stream_level01": _capi.MIX_LEVEL01}
+        mix = {}
+        try:
+            for k, v in kernels.items():
+                if k in mix_kind and v["gbps"]:
+                    g, _ms = ctx.traffic_mix_probe(mix_kind[k], v["bytes_per_launch"], 10)
+                    mix[k] = {"trivial_kernel_gbps": round(g, 1), "frac_of_trivial_kernel": round(v["gbps"] / g, 4)}
+        except Exception as e:   # noqa: BLE001
+            mix = {"error": str(e)[:200]}
+        roof["mix_ceiling"] = mix
+        if dom == "stream_level01":
+            roof["limiter"] = ("HBM and instruction issue together: fused level 0 + level 1 (6 B per level-0 pixel instead of 10 for the two "
+                               "kernels it replaces); ncu: DRAM 52-55 %, issue slots 51 %, FMA pipe 50 % (packed FFMA2)")
     step_s = dev_ms * 1e-3 / args.steps
     e2e_s = e2e_ms * 1e-3 / e2e_steps
     if args.precision == "windowed":
-        wb = windowed_bytes_per_pair(wl)[0]
-        pipeline = {"algorithmic_bytes_per_pair": wb, "accounting": "image-only pyramids: 5 B/px level 0 + decimations + the regions the tracker stages "
+        fused01 = "stream_level01" in kernels
+        wb = windowed_bytes_per_pair(wl, fused01)[0]
+        pipeline = {"algorithmic_bytes_per_pair": wb, "accounting": "image-only pyramids: " + ("6 B/px for levels 0 + 1 in one pass" if fused01 else "5 B/px level 0") +
+                                                                      " + decimations + the regions the tracker stages "
                                                                       "(the dense-plane accounting of SURVEY 8(d) is under dense_planes)",
                     "achieved_gbps": round(wb * B / step_s / 1e9, 1), "frac_of_hbm_peak": round(wb * B / step_s / 1e9 / peak, 4)}
     else:
@@ -782,7 +802,7 @@ def config_c_timing(ctx, lib, _capi, klt, sgf, tf, peak, pairs=8, steps=6):
     for d in (d1, d2, dx0, dy0, dv0, dx, dy, dv):
         ctx.device_free(d)
     p1.close(); p2.close()
-    wb = windowed_bytes_per_pair(wl)[0]
+    wb = windowed_bytes_per_pair(wl, os.environ.get("KLT_B200_FUSED01") != "0" and wl["W"] % 8 == 0)[0]
     return {"workload": wl["name"], "pairs_per_step": pairs, "ms_per_step": round(ms, 4), "frame_pairs_per_sec": round(pairs / ms * 1e3, 1),
             "tracked_features_per_sec": round(tracked / ms * 1e3, 1), "tracked_fraction": tracked / float(pairs * n),
             "frac_of_hbm_peak": round(wb * pairs / (ms * 1e-3) / 1e9 / peak, 4), "precision": "windowed"}

@@ -148,6 +148,15 @@ int klt_profile_reset(klt_ctx *ctx);
 int klt_profile_count(klt_ctx *ctx);
 int klt_profile_get(klt_ctx *ctx, int index, const char **name, double *total_ms, int64_t *launches, double *bytes);
 
+/* diagnostics: what this GPU sustains for the read/write MIX and launch size of one of the pyramid kernels, moved by a trivial
+ * linear kernel that computes nothing (bench.py states each HBM-bound kernel against the ceiling of its own mix; no counterpart
+ * in the reference).  total_bytes = bytes one launch moves; runs `reps` launches between two events on the context's stream. */
+#define KLT_MIX_COPY 0     /* 16 B read : 16 B written */
+#define KLT_MIX_SMOOTH0 1  /* 1 B read : 4 B written per pixel   (stream_smooth0) */
+#define KLT_MIX_DOWN2 2    /* 16 B read : 4 B written per output pixel   (stream_down2) */
+#define KLT_MIX_LEVEL01 3  /* 1 B read : 4 B + 1 B written per pixel, two output planes   (stream_level01) */
+int klt_probe_traffic_mix(klt_ctx *ctx, int kind, double total_bytes, int reps, double *ms_per_rep, double *bytes_moved);
+
 /* ---- operator level: replaces scipy.ndimage.convolve1d pairs behind convolve.py -------------------
  * klt_convolve_separable_f32  == _convolveSeparate(img, hk, vk)         convolve.py:208-214
  * klt_smooth_f32              == KLTComputeSmoothedImage's convolution  convolve.py:254-264

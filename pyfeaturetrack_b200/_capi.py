@@ -12,6 +12,7 @@ _LIBPATH = os.path.join(_HERE, "libkltb200.so")
 
 KLT_MAX_TAPS = 71
 PRECISION_FAST, PRECISION_STRICT, PRECISION_FAST_WINDOWED = 0, 1, 2
+MIX_COPY, MIX_SMOOTH0, MIX_DOWN2, MIX_LEVEL01 = 0, 1, 2, 3
 SELECT_STRICT, SELECT_FAST = 0, 1
 KLT_ERR_INVALID, KLT_ERR_CUDA, KLT_ERR_NOMEM, KLT_ERR_UNSUPPORTED, KLT_ERR_ASSERT = -1, -2, -3, -4, -5
 
@@ -94,6 +95,7 @@ SIGNATURES = {
     "klt_profile_count": (_i, [_vp]),
     "klt_profile_get": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64),
                              C.POINTER(C.c_double)]),
+    "klt_probe_traffic_mix": (_i, [_vp, _i, C.c_double, _i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "klt_convolve_separable_f32": (_i, [_vp, _fp, _i, _i, C.POINTER(Kernel1D), C.POINTER(Kernel1D), _i, _fp]),
     "klt_smooth_f32": (_i, [_vp, _fp, _i, _i, C.POINTER(Kernel1D), _i, _fp]),
     "klt_gradients_f32": (_i, [_vp, _fp, _i, _i, C.POINTER(Kernel1D), C.POINTER(Kernel1D), _i, _fp, _fp]),
@@ -405,6 +407,12 @@ class Context:
 
     def profile_reset(self):
         self.check(lib().klt_profile_reset(self.handle))
+
+    def traffic_mix_probe(self, kind, total_bytes, reps=10):
+        """GB/s a trivial linear kernel reaches for the read/write mix `kind` (MIX_*) and launch size `total_bytes`."""
+        ms, moved = C.c_double(), C.c_double()
+        self.check(lib().klt_probe_traffic_mix(self.handle, kind, float(total_bytes), reps, C.byref(ms), C.byref(moved)))
+        return moved.value / (ms.value * 1e-3) / 1e9, ms.value
 
     def profile_read(self):
         """{kernel name: dict(ms=total, launches=n, bytes=algorithmic bytes)}"""

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkltb200.so")
-SOURCES = ["klt_affine.cu", "klt_api.cu", "klt_conv.cu", "klt_select.cu", "klt_select_fast.cu", "klt_sequence.cu", "klt_stream.cu", "klt_track.cu", "klt_track_windowed.cu"]
+SOURCES = ["klt_affine.cu", "klt_api.cu", "klt_conv.cu", "klt_probe.cu", "klt_select.cu", "klt_select_fast.cu", "klt_sequence.cu", "klt_stream.cu", "klt_track.cu", "klt_track_windowed.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=true",     # FMA contraction only where the code does not use *_rn intrinsics; never --use_fast_math
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]

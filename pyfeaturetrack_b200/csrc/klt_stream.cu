@@ -35,8 +35,9 @@
 
 struct StreamTaps {
     // c[j] multiplies in[x + j - r] (convolution order), zero padded and centred in a fixed-radius slot
+    float p[12];     // pyramid gauss (radius 5) + one zero; first, so that the pairs (p[2m], p[2m+1]) are 8-byte aligned in the
+                     // parameter bank and the packed kernels can read them as uniform register pairs
     float s[9];      // level-0 smoothing gauss (radius <= 4)
-    float p[11];     // pyramid gauss (radius 5)
     float g[7];      // gradient gauss / deriv (radius 3)
     float d[7];
 };
@@ -849,30 +850,22 @@ __device__ __forceinline__ int mirror_oct(int c, int W, bool &rev) {     // alig
     return min(max(m, 0), W - 8);
 }
 
+#define L01_WARPS 2            // warps per CTA: 8 CTAs of 2 warps per SM at 128 registers
+
 struct L01State {
     f32x2 sa[4][4];            // pending smoothed rows: pairs (column i, column i + 4), radius 2
     f32x2 P[2][5];             // pending level-1 rows: pairs of output columns (0, 1), (2, 3)
-    uint2 w;                   // the frame row loaded one iteration ahead
 };
 
-// one frame row t: completes smoothed row t - 2 of the lane's 8 columns (s[0..7]); OUT = the vertical filter is warm
-template <bool INTERIOR, bool OUT>
-__device__ __forceinline__ void l01_smooth_row(L01State &S, const unsigned char *__restrict__ b0, unsigned int &offs,
-                                               unsigned int selx, unsigned int sely, unsigned int upitch, int H, int t, int t_last,
-                                               const StreamTaps &T, float (&s)[8]) {
-    const unsigned int q0 = __byte_perm(S.w.x, S.w.y, selx), q1 = __byte_perm(S.w.x, S.w.y, sely);
+// one frame row (8 bytes of the lane, already mirrored): completes smoothed row t - 2 of the lane's 8 columns (s[0..7]);
+// OUT = the vertical filter is warm
+template <bool OUT>
+__device__ __forceinline__ void l01_smooth_row(L01State &S, uint2 w, unsigned int selx, unsigned int sely, const StreamTaps &T,
+                                               float (&s)[8]) {
+    const unsigned int q0 = __byte_perm(w.x, w.y, selx), q1 = __byte_perm(w.x, w.y, sely);
     float x[8];
 #pragma unroll
     for (int i = 0; i < 4; i++) { x[i] = u8_byte_to_f32(q0, i); x[4 + i] = u8_byte_to_f32(q1, i); }
-    if (INTERIOR) {
-        offs += upitch;
-        S.w = __ldg(reinterpret_cast<const uint2 *>(b0 + offs));
-        prefetch_l2(b0 + offs + (PREFETCH_ROWS - 1) * upitch);
-    } else {
-        S.w = __ldg(reinterpret_cast<const uint2 *>(b0 + (unsigned int)reflect1(min(t + 1, t_last), H) * upitch));
-        const int tp = t + PREFETCH_ROWS;
-        if (tp <= t_last) prefetch_l2(b0 + (unsigned int)reflect1(tp, H) * upitch);
-    }
     const float xl0 = __shfl_up_sync(FULLMASK, x[6], 1), xl1 = __shfl_up_sync(FULLMASK, x[7], 1);
     const float xr0 = __shfl_down_sync(FULLMASK, x[0], 1), xr1 = __shfl_down_sync(FULLMASK, x[1], 1);
     // U[k] = (column k - 2, column k + 2): the windows of the first and of the second quad, side by side
@@ -917,23 +910,45 @@ __device__ __forceinline__ void l01_rows(const unsigned char *__restrict__ b0, u
 #pragma unroll
     for (int m = 0; m < 5; m++) pk[m] = pack2(T.p[2 * m], T.p[2 * m + 1]);
     // level-1 row Y needs smoothed rows 2Y - 4 .. 2Y + 6: pairs j = ys - 2 .. ye + 2 of smoothed rows (2j, 2j + 1), i.e.
-    // frame rows 2 (ys - 2) - 2 .. 2 (ye + 2) + 3
+    // frame rows 2 (ys - 2) - 2 .. 2 (ye + 2) + 3.  The frame rows of a pair are loaded one whole pair ahead.
     const int j0 = ys - 2, j1 = ye + 3;
     const int t0 = 2 * j0 - 2, t_last = 2 * (j1 - 1) + 3;
-    unsigned int offs = (unsigned int)(INTERIOR ? t0 : reflect1(t0, H)) * upitch;
-    S.w = __ldg(reinterpret_cast<const uint2 *>(b0 + offs));
+    unsigned int offs = (unsigned int)(INTERIOR ? t0 : 0) * upitch;       // INTERIOR: byte offset of the next row to load
+    int tn = t0;                                                           // otherwise: its index
+    auto load_row = [&]() -> uint2 {
+        uint2 w;
+        if (INTERIOR) {
+            w = __ldg(reinterpret_cast<const uint2 *>(b0 + offs));
+            offs += upitch;
+        } else {
+            w = __ldg(reinterpret_cast<const uint2 *>(b0 + (unsigned int)reflect1(min(tn, t_last), H) * upitch));
+            tn++;
+        }
+        return w;
+    };
     float s[8];
+    uint2 wa = load_row(), wb = load_row();
 #pragma unroll 1
-    for (int t = t0; t < t0 + 4; t++)                  // the smoothing filter warms up
-        l01_smooth_row<INTERIOR, false>(S, b0, offs, selx, sely, upitch, H, t, t_last, T, s);
+    for (int k = 0; k < 2; k++) {                      // four frame rows: the smoothing filter warms up
+        l01_smooth_row<false>(S, wa, selx, sely, T, s);
+        wa = load_row();
+        l01_smooth_row<false>(S, wb, selx, sely, T, s);
+        wb = load_row();
+    }
 #pragma unroll 2
     for (int j = j0; j < j1; j++) {
         f32x2 he[2], ho[2];
         const int r = 2 * j;
-        l01_smooth_row<INTERIOR, true>(S, b0, offs, selx, sely, upitch, H, r + 2, t_last, T, s);
+        if (INTERIOR) prefetch_l2(b0 + offs + (PREFETCH_ROWS - 2) * upitch);
+        else if (tn + PREFETCH_ROWS - 2 <= t_last) prefetch_l2(b0 + (unsigned int)reflect1(tn + PREFETCH_ROWS - 2, H) * upitch);
+        l01_smooth_row<true>(S, wa, selx, sely, T, s);
+        wa = load_row();
         if (writer0 && r >= 2 * ys && r < r_end) st256(p0, s);
         down2p_hrow(pk, T.p[10], make_float4(s[0], s[1], s[2], s[3]), make_float4(s[4], s[5], s[6], s[7]), false, false, false, he);
-        l01_smooth_row<INTERIOR, true>(S, b0, offs, selx, sely, upitch, H, r + 3, t_last, T, s);
+        if (INTERIOR) prefetch_l2(b0 + offs + (PREFETCH_ROWS - 2) * upitch);
+        else if (tn + PREFETCH_ROWS - 2 <= t_last) prefetch_l2(b0 + (unsigned int)reflect1(tn + PREFETCH_ROWS - 2, H) * upitch);
+        l01_smooth_row<true>(S, wb, selx, sely, T, s);
+        wb = load_row();
         if (writer0 && r + 1 >= 2 * ys && r + 1 < r_end) st256(p0 + pitch0, s);
         p0 += 2 * (size_t)pitch0;
         down2p_hrow(pk, T.p[10], make_float4(s[0], s[1], s[2], s[3]), make_float4(s[4], s[5], s[6], s[7]), false, false, false, ho);
@@ -959,30 +974,36 @@ __device__ __forceinline__ void l01_rows(const unsigned char *__restrict__ b0, u
     }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3)
-stream_level01_kernel(const unsigned char *__restrict__ frames, size_t pitch, size_t frame_stride, float *__restrict__ img0,
-                      int pitch0, float *__restrict__ img1, int pitch1, size_t out_stride, int W, int H, int OW, int OH,
-                      int rows_per_seg, int n_strips, const __grid_constant__ StreamTaps T) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int strip = blockIdx.x * WARPS_PER_CTA + warp;          // 240 level-0 columns = 120 level-1 columns
-    if (strip >= n_strips) return;
-    const int ys = blockIdx.y * rows_per_seg, ye = min(OH, ys + rows_per_seg);       // level-1 rows
-    const int c0 = strip * 240 + 8 * (lane - 1), X = strip * 120 + 4 * (lane - 1);
-    bool rev;
-    const int m0 = mirror_oct(c0, W, rev);
-    const unsigned char *b0 = frames + (size_t)blockIdx.z * frame_stride + m0;
-    const unsigned int selx = rev ? 0x4567u : 0x3210u, sely = rev ? 0x0123u : 0x7654u;
-    const bool inner = lane >= 1 && lane <= 30;
-    const bool writer0 = inner && c0 < W, writer1 = inner && X < OW;
-    const int r_end = ye == OH ? H : 2 * ye;                      // the last segment also stores the odd last row
-    // level-0 pointer of smoothed row 2 (ys - 2), the first one the loop completes (not stored: rows below 2 ys are the
-    // neighbour segment's)
-    float *p0 = img0 + (size_t)blockIdx.z * out_stride + c0 + ((ptrdiff_t)2 * (ys - 2)) * pitch0;
-    float *p1 = img1 + (size_t)blockIdx.z * out_stride + (size_t)ys * pitch1 + X;
-    const int t0 = 2 * (ys - 2) - 2, t_end = 2 * (ye + 2) + 3 + PREFETCH_ROWS + 1;
-    if (t0 >= 0 && t_end < H) l01_rows<true>(b0, selx, sely, (unsigned int)pitch, H, ys, ye, r_end, writer0, writer1, p0, pitch0, p1, pitch1, T);
-    else l01_rows<false>(b0, selx, sely, (unsigned int)pitch, H, ys, ye, r_end, writer0, writer1, p0, pitch0, p1, pitch1, T);
+// two register budgets of the same kernel: 112 registers = 9 CTAs of 2 warps per SM (a few spills outside the inner
+// dependency chains), 128 = 8 CTAs; $KLT_B200_L01_REGS picks (A/B runs), the default is the measured winner
+#define KLT_DEFINE_LEVEL01(NAME, MAXREG) \
+__global__ void __maxnreg__(MAXREG) \
+NAME(const unsigned char *__restrict__ frames, size_t pitch, size_t frame_stride, float *__restrict__ img0, \
+                      int pitch0, float *__restrict__ img1, int pitch1, size_t out_stride, int W, int H, int OW, int OH, \
+                      int rows_per_seg, int n_strips, const __grid_constant__ StreamTaps T) { \
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5; \
+    const int strip = blockIdx.x * L01_WARPS + warp; \
+    if (strip >= n_strips) return; \
+    const int ys = blockIdx.y * rows_per_seg, ye = min(OH, ys + rows_per_seg); \
+    const int c0 = strip * 240 + 8 * (lane - 1), X = strip * 120 + 4 * (lane - 1); \
+    bool rev; \
+    const int m0 = mirror_oct(c0, W, rev); \
+    const unsigned char *b0 = frames + (size_t)blockIdx.z * frame_stride + m0; \
+    const unsigned int selx = rev ? 0x4567u : 0x3210u, sely = rev ? 0x0123u : 0x7654u; \
+    const bool inner = lane >= 1 && lane <= 30; \
+    const bool writer0 = inner && c0 < W, writer1 = inner && X < OW; \
+    const int r_end = ye == OH ? H : 2 * ye; \
+ \
+ \
+    float *p0 = img0 + (size_t)blockIdx.z * out_stride + c0 + ((ptrdiff_t)2 * (ys - 2)) * pitch0; \
+    float *p1 = img1 + (size_t)blockIdx.z * out_stride + (size_t)ys * pitch1 + X; \
+ \
+    const int t0 = 2 * (ys - 2) - 2, t_end = 2 * (ye + 2) + 3 + 2 + PREFETCH_ROWS; \
+    if (t0 >= 0 && t_end < H) l01_rows<true>(b0, selx, sely, (unsigned int)pitch, H, ys, ye, r_end, writer0, writer1, p0, pitch0, p1, pitch1, T); \
+    else l01_rows<false>(b0, selx, sely, (unsigned int)pitch, H, ys, ye, r_end, writer0, writer1, p0, pitch0, p1, pitch1, T); \
 }
+KLT_DEFINE_LEVEL01(stream_level01_kernel, 112)
+KLT_DEFINE_LEVEL01(stream_level01_r128_kernel, 128)
 
 // ---- pyramid step for subsampling SS with a (2R+1)-tap gauss, generic form of the kernel above ------------------------
 // (used for SS = 4, R = 10: the reference's DEFAULT pyramid, sigma = 0.9 * 4 -> 21 taps).
@@ -1129,7 +1150,7 @@ int klt_stream_level0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t 
     const int RS = ns / 2;
     if (!fill_taps(&taps->smooth, T.s, ns)) return 0;
     if (!fill_taps(&taps->grad_gauss, T.g, 7) || !fill_taps(&taps->grad_deriv, T.d, 7)) return 0;
-    for (int j = 0; j < 11; j++) T.p[j] = 0.f;
+    for (int j = 0; j < 12; j++) T.p[j] = 0.f;
     const int W = p->w, H = p->h;
     if (W < 16 || H < 16 || (W & 3)) return 0;
     if ((reinterpret_cast<uintptr_t>(frames) & 3) || (pitch & 3) || (frame_stride & 3)) return 0;
@@ -1169,7 +1190,7 @@ int klt_stream_smooth0(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t
     if (!is_symmetric(&taps->smooth)) return 0;
     const int RS = ns / 2;
     if (!fill_taps(&taps->smooth, T.s, ns)) return 0;
-    for (int j = 0; j < 11; j++) T.p[j] = 0.f;
+    for (int j = 0; j < 12; j++) T.p[j] = 0.f;
     for (int j = 0; j < 7; j++) T.g[j] = T.d[j] = 0.f;
     const int W = p->w, H = p->h;
     if (W < 16 || H < 16 || (W & 3)) return 0;
@@ -1278,6 +1299,7 @@ int klt_stream_level01(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t
     StreamTaps T;
     if (taps->smooth.n != 5 || !is_symmetric(&taps->smooth) || !fill_taps(&taps->smooth, T.s, 5)) return 0;
     if (taps->pyramid.n > 11 || !fill_taps(&taps->pyramid, T.p, 11)) return 0;
+    T.p[11] = 0.f;
     for (int j = 5; j < 9; j++) T.s[j] = 0.f;
     for (int j = 0; j < 7; j++) { T.g[j] = 0.f; T.d[j] = 0.f; }
     const LevelDesc &a = p->lv[0], &b = p->lv[1];
@@ -1287,12 +1309,23 @@ int klt_stream_level01(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t
     float *img0 = p->level(0, first, 0), *img1 = p->level(0, first, 1);
     if ((reinterpret_cast<uintptr_t>(img0) & 31) || (a.pitch & 7) || (p->plane_floats & 7) || !aligned16(img1)) return 0;
     const int n_strips = (W + 239) / 240;
-    const int strip_ctas = (n_strips + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    const int rows = pick_rows_per_seg(ctx, stream_level01_kernel, b.h, strip_ctas, count, 16);
-    dim3 grid(strip_ctas, (b.h + rows - 1) / rows, count), block(WARPS_PER_CTA * 32);
+    const int strip_ctas = (n_strips + L01_WARPS - 1) / L01_WARPS;
+    static const bool r128 = [] { const char *e = getenv("KLT_B200_L01_REGS"); return e && atoi(e) == 128; }();
+    auto kernel = r128 ? stream_level01_r128_kernel : stream_level01_kernel;
+    int per_sm = 8;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, L01_WARPS * 32, 0) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 8;
+    }
+    long nseg = (long)ctx->num_sms * per_sm / ((long)strip_ctas * count);
+    if (nseg < 1) nseg = 1;
+    int rows = (int)((b.h + nseg - 1) / nseg);
+    if (rows < 16) rows = 16;
+    if (rows > b.h) rows = b.h;
+    dim3 grid(strip_ctas, (b.h + rows - 1) / rows, count), block(L01_WARPS * 32);
     const double bytes = (5.0 * W * H + 4.0 * b.w * b.h) * count;     // 1 B read, 4 B + 1 B (a quarter of 4 B) written per pixel
     KLT_LAUNCH(ctx, "stream_level01", bytes,
-               (stream_level01_kernel<<<grid, block, 0, ctx->stream>>>(frames, pitch, frame_stride, img0, a.pitch, img1, b.pitch,
+               (kernel<<<grid, block, 0, ctx->stream>>>(frames, pitch, frame_stride, img0, a.pitch, img1, b.pitch,
                                                                        p->plane_floats, W, H, b.w, b.h, rows, n_strips, T)));
     return 1;
 }
@@ -1301,7 +1334,7 @@ int klt_stream_grad(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps, i
     StreamTaps T;
     if (!fill_taps(&taps->grad_gauss, T.g, 7) || !fill_taps(&taps->grad_deriv, T.d, 7)) return 0;
     for (int j = 0; j < 9; j++) T.s[j] = 0.f;
-    for (int j = 0; j < 11; j++) T.p[j] = 0.f;
+    for (int j = 0; j < 12; j++) T.p[j] = 0.f;
     const LevelDesc &a = p->lv[level];
     if (a.w < 16 || a.h < 8 || (a.w & 3) || !aligned16(p->level(0, first, level)) || (p->plane_floats & 3)) return 0;
     const int n_strips = (a.w + 119) / 120;
@@ -1345,6 +1378,7 @@ int klt_stream_down2(klt_ctx *ctx, klt_pyr *p, int level, const klt_taps *taps, 
     if (p->ss != 2) return 0;
     StreamTaps T;
     if (taps->pyramid.n > 11 || !fill_taps(&taps->pyramid, T.p, 11)) return 0;
+    T.p[11] = 0.f;
     for (int j = 0; j < 9; j++) T.s[j] = 0.f;
     for (int j = 0; j < 7; j++) { T.g[j] = 0.f; T.d[j] = 0.f; }
     const LevelDesc &a = p->lv[level - 1], &b = p->lv[level];
