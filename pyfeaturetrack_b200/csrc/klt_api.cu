@@ -411,12 +411,17 @@ int klt_build_u8_device(klt_ctx *ctx, klt_pyr *p, const uint8_t *dframes, size_t
                         const klt_taps *taps, int precision, int first, int count, bool windowed) {
     int rc;
     if (windowed) {
-        // u8 -> smoothed image + level 1 in one pass (unless a caller wants to fork right after level 0: klt_sequence's
-        // eigenvalue pass reads level 0 only and runs beside the decimations)
-        if (!ctx->level0_event) {
+        // u8 -> smoothed image + level 1 in one pass
+        // a caller that forks after level 0 (klt_sequence's eigenvalue pass) forks after the fused kernel instead: measured
+        // 0.273 against 0.276 ms per step of 8 sequences, one launch fewer ($KLT_B200_SEQ_FUSED01=0: the two-kernel build)
+        static const bool fork_after_fused = [] { const char *e = getenv("KLT_B200_SEQ_FUSED01"); return !(e && e[0] == '0'); }();
+        if (!ctx->level0_event || fork_after_fused) {
             rc = klt_stream_level01(ctx, dframes, pitch, frame_stride, p, taps, first, count);
             if (rc < 0) return rc;
-            if (rc == 1) return build_rest(ctx, p, taps, precision, false, first, count, true, 2);
+            if (rc == 1) {
+                if (ctx->level0_event) KLT_CUDA(ctx, cudaEventRecord(ctx->level0_event, ctx->stream));
+                return build_rest(ctx, p, taps, precision, false, first, count, true, 2);
+            }
         }
         // u8 -> smoothed image only
         rc = klt_stream_smooth0(ctx, dframes, pitch, frame_stride, p, taps, first, count);

@@ -974,8 +974,9 @@ __device__ __forceinline__ void l01_rows(const unsigned char *__restrict__ b0, u
     }
 }
 
-// two register budgets of the same kernel: 112 registers = 9 CTAs of 2 warps per SM (a few spills outside the inner
-// dependency chains), 128 = 8 CTAs; $KLT_B200_L01_REGS picks (A/B runs), the default is the measured winner
+// two register budgets of the same kernel: 128 registers = 8 CTAs of 2 warps per SM (the default: 166 us per 64 x 1080p),
+// 112 = 9 CTAs with a few spills (170 us: more warps do not help, the kernel is near its traffic mix's ceiling);
+// $KLT_B200_L01_REGS=112 picks the second (A/B runs)
 #define KLT_DEFINE_LEVEL01(NAME, MAXREG) \
 __global__ void __maxnreg__(MAXREG) \
 NAME(const unsigned char *__restrict__ frames, size_t pitch, size_t frame_stride, float *__restrict__ img0, \
@@ -1002,8 +1003,8 @@ NAME(const unsigned char *__restrict__ frames, size_t pitch, size_t frame_stride
     if (t0 >= 0 && t_end < H) l01_rows<true>(b0, selx, sely, (unsigned int)pitch, H, ys, ye, r_end, writer0, writer1, p0, pitch0, p1, pitch1, T); \
     else l01_rows<false>(b0, selx, sely, (unsigned int)pitch, H, ys, ye, r_end, writer0, writer1, p0, pitch0, p1, pitch1, T); \
 }
-KLT_DEFINE_LEVEL01(stream_level01_kernel, 112)
-KLT_DEFINE_LEVEL01(stream_level01_r128_kernel, 128)
+KLT_DEFINE_LEVEL01(stream_level01_kernel, 128)
+KLT_DEFINE_LEVEL01(stream_level01_r112_kernel, 112)
 
 // ---- pyramid step for subsampling SS with a (2R+1)-tap gauss, generic form of the kernel above ------------------------
 // (used for SS = 4, R = 10: the reference's DEFAULT pyramid, sigma = 0.9 * 4 -> 21 taps).
@@ -1310,8 +1311,8 @@ int klt_stream_level01(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t
     if ((reinterpret_cast<uintptr_t>(img0) & 31) || (a.pitch & 7) || (p->plane_floats & 7) || !aligned16(img1)) return 0;
     const int n_strips = (W + 239) / 240;
     const int strip_ctas = (n_strips + L01_WARPS - 1) / L01_WARPS;
-    static const bool r128 = [] { const char *e = getenv("KLT_B200_L01_REGS"); return e && atoi(e) == 128; }();
-    auto kernel = r128 ? stream_level01_r128_kernel : stream_level01_kernel;
+    static const bool r112 = [] { const char *e = getenv("KLT_B200_L01_REGS"); return e && atoi(e) == 112; }();
+    auto kernel = r112 ? stream_level01_r112_kernel : stream_level01_kernel;
     int per_sm = 8;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, L01_WARPS * 32, 0) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
