@@ -17,9 +17,10 @@ scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 acc = defaultdict(list)
 for r in rows[2:]:
     name = r[iK]
-    for key in ("stream_level0", "stream_smooth0", "stream_down2", "stream_grad", "lk_windowed", "lk_track_rows"):
+    for key in ("stream_level01", "stream_level0_", "stream_smooth0", "stream_down2", "stream_grad", "lk_windowed", "lk_track_rows"):
         if key in name:
-            acc[key].append(float(r[iR]) * scale[units[iR]] + float(r[iW]) * scale[units[iW]])
+            acc[key.rstrip("_")].append(float(r[iR]) * scale[units[iR]] + float(r[iW]) * scale[units[iW]])
+            break
 per_frame = {k: round(sum(v) / len(v) / frames) for k, v in acc.items() if k.startswith("stream_")}
 per_feat = {k: round(sum(v) / len(v) / feats) for k, v in acc.items() if k.startswith("lk_")}
 json.dump({"source": note, "source_windowed": note, "per_frame_bytes": per_frame, "per_feature_bytes": per_feat,

@@ -55,6 +55,19 @@ def main():
         q.sync()
         assert q.uses_graph()
         q.close()
+    # image-only builds of every streaming-kernel generation: fused levels 0 + 1 (width % 8 == 0), two-strip packed level 0 +
+    # packed decimation (width % 8 == 4), whole-row CTAs with bulk stores (width >= 960), one level only
+    tc3 = klt.KLT_TrackingContext()
+    tc3.nPyramidLevels, tc3.subsampling = 3, 2
+    tc3.KLTUpdateTCBorder()
+    rng = np.random.default_rng(5)
+    for (h3, w3, l3) in ((96, 328, 3), (96, 324, 3), (80, 964, 2), (72, 1920, 1), (64, 248, 2)):
+        fr = (rng.random((2, h3, w3)) * 255).astype(np.uint8)
+        p3 = _capi.Pyramid(ctx, w3, h3, l3, 2, 2)
+        tc3.nPyramidLevels = l3
+        p3.build_u8(fr, tf._taps_for_one_image(tc3), _capi.PRECISION_FAST_WINDOWED)
+        ctx.sync()
+        p3.close()
     # the walk's rare paths
     os.environ["KLT_B200_SELECT_CHUNK"] = "64"
     c2 = _capi.Context(ctx.device)
