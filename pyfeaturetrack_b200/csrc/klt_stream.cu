@@ -896,8 +896,9 @@ __device__ __forceinline__ void st256(float *p, const float (&s)[8]) {
 template <bool INTERIOR>
 __device__ __forceinline__ void l01_rows(const unsigned char *__restrict__ b0, unsigned int selx, unsigned int sely,
                                          unsigned int upitch, int H, int ys, int ye, int r_end, bool writer0, bool writer1,
-                                         float *p0, int pitch0, float *p1, int pitch1, const StreamTaps &T) {
+                                         float *p0, int pitch0, float *p1, int pitch1, int pf_rows, const StreamTaps &T) {
     L01State S;
+    const unsigned int pf_bytes = (unsigned int)pf_rows * upitch;       // L2 prefetch distance below the row being loaded
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -939,14 +940,14 @@ __device__ __forceinline__ void l01_rows(const unsigned char *__restrict__ b0, u
     for (int j = j0; j < j1; j++) {
         f32x2 he[2], ho[2];
         const int r = 2 * j;
-        if (INTERIOR) prefetch_l2(b0 + offs + (PREFETCH_ROWS - 2) * upitch);
-        else if (tn + PREFETCH_ROWS - 2 <= t_last) prefetch_l2(b0 + (unsigned int)reflect1(tn + PREFETCH_ROWS - 2, H) * upitch);
+        if (INTERIOR) prefetch_l2(b0 + offs + pf_bytes);
+        else if (tn + pf_rows <= t_last) prefetch_l2(b0 + (unsigned int)reflect1(tn + pf_rows, H) * upitch);
         l01_smooth_row<true>(S, wa, selx, sely, T, s);
         wa = load_row();
         if (writer0 && r >= 2 * ys && r < r_end) st256(p0, s);
         down2p_hrow(pk, T.p[10], make_float4(s[0], s[1], s[2], s[3]), make_float4(s[4], s[5], s[6], s[7]), false, false, false, he);
-        if (INTERIOR) prefetch_l2(b0 + offs + (PREFETCH_ROWS - 2) * upitch);
-        else if (tn + PREFETCH_ROWS - 2 <= t_last) prefetch_l2(b0 + (unsigned int)reflect1(tn + PREFETCH_ROWS - 2, H) * upitch);
+        if (INTERIOR) prefetch_l2(b0 + offs + pf_bytes);
+        else if (tn + pf_rows <= t_last) prefetch_l2(b0 + (unsigned int)reflect1(tn + pf_rows, H) * upitch);
         l01_smooth_row<true>(S, wb, selx, sely, T, s);
         wb = load_row();
         if (writer0 && r + 1 >= 2 * ys && r + 1 < r_end) st256(p0 + pitch0, s);
@@ -981,7 +982,7 @@ __device__ __forceinline__ void l01_rows(const unsigned char *__restrict__ b0, u
 __global__ void __maxnreg__(MAXREG) \
 NAME(const unsigned char *__restrict__ frames, size_t pitch, size_t frame_stride, float *__restrict__ img0, \
                       int pitch0, float *__restrict__ img1, int pitch1, size_t out_stride, int W, int H, int OW, int OH, \
-                      int rows_per_seg, int n_strips, const __grid_constant__ StreamTaps T) { \
+                      int rows_per_seg, int n_strips, int pf_rows, const __grid_constant__ StreamTaps T) { \
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5; \
     const int strip = blockIdx.x * L01_WARPS + warp; \
     if (strip >= n_strips) return; \
@@ -999,9 +1000,9 @@ NAME(const unsigned char *__restrict__ frames, size_t pitch, size_t frame_stride
     float *p0 = img0 + (size_t)blockIdx.z * out_stride + c0 + ((ptrdiff_t)2 * (ys - 2)) * pitch0; \
     float *p1 = img1 + (size_t)blockIdx.z * out_stride + (size_t)ys * pitch1 + X; \
  \
-    const int t0 = 2 * (ys - 2) - 2, t_end = 2 * (ye + 2) + 3 + 2 + PREFETCH_ROWS; \
-    if (t0 >= 0 && t_end < H) l01_rows<true>(b0, selx, sely, (unsigned int)pitch, H, ys, ye, r_end, writer0, writer1, p0, pitch0, p1, pitch1, T); \
-    else l01_rows<false>(b0, selx, sely, (unsigned int)pitch, H, ys, ye, r_end, writer0, writer1, p0, pitch0, p1, pitch1, T); \
+    const int t0 = 2 * (ys - 2) - 2, t_end = 2 * (ye + 2) + 3 + 2 + 2 + pf_rows; \
+    if (t0 >= 0 && t_end < H) l01_rows<true>(b0, selx, sely, (unsigned int)pitch, H, ys, ye, r_end, writer0, writer1, p0, pitch0, p1, pitch1, pf_rows, T); \
+    else l01_rows<false>(b0, selx, sely, (unsigned int)pitch, H, ys, ye, r_end, writer0, writer1, p0, pitch0, p1, pitch1, pf_rows, T); \
 }
 KLT_DEFINE_LEVEL01(stream_level01_kernel, 128)
 KLT_DEFINE_LEVEL01(stream_level01_r112_kernel, 112)
@@ -1311,6 +1312,7 @@ int klt_stream_level01(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t
     if ((reinterpret_cast<uintptr_t>(img0) & 31) || (a.pitch & 7) || (p->plane_floats & 7) || !aligned16(img1)) return 0;
     const int n_strips = (W + 239) / 240;
     const int strip_ctas = (n_strips + L01_WARPS - 1) / L01_WARPS;
+    static const int pf_rows = [] { const char *e = getenv("KLT_B200_L01_PF"); const int v = e ? atoi(e) : 0; return v > 0 && v <= 64 ? v : 4; }();
     static const bool r112 = [] { const char *e = getenv("KLT_B200_L01_REGS"); return e && atoi(e) == 112; }();
     auto kernel = r112 ? stream_level01_r112_kernel : stream_level01_kernel;
     int per_sm = 8;
@@ -1327,7 +1329,7 @@ int klt_stream_level01(klt_ctx *ctx, const uint8_t *frames, size_t pitch, size_t
     const double bytes = (5.0 * W * H + 4.0 * b.w * b.h) * count;     // 1 B read, 4 B + 1 B (a quarter of 4 B) written per pixel
     KLT_LAUNCH(ctx, "stream_level01", bytes,
                (kernel<<<grid, block, 0, ctx->stream>>>(frames, pitch, frame_stride, img0, a.pitch, img1, b.pitch,
-                                                                       p->plane_floats, W, H, b.w, b.h, rows, n_strips, T)));
+                                                                       p->plane_floats, W, H, b.w, b.h, rows, n_strips, pf_rows, T)));
     return 1;
 }
 
