@@ -425,6 +425,20 @@ def run_b200(args):
         gather = {"call": "shard.gather_features: three all_reduce(SUM) over NCCL on fixed-size [units, n] tensors", "ms": round(g_ms, 3),
                   "bytes_per_rank": B * n * 20, "units": B * world, "own_shard_intact": ok,
                   "tracked_in_gathered_lists": int((gv == 0).sum())}
+    # the host-fed numbers against what THIS box's host memory system can feed N GPUs at once, measured live: every rank does
+    # nothing but upload its pinned frames, all ranks at the same time (a PCIe / host-memory ceiling, not a kernel property;
+    # tools/h2d_probe.py and profiles/h2d_ceiling_r02.json hold the same probe from another box of the pool)
+    # EVERY rank takes part (timed() holds a barrier and an all_reduce): this must stay above the point where ranks != 0 leave
+    ceil = None
+    try:
+        def h2d_only():
+            ctx.memcpy(d_f1, f1, frame_bytes); ctx.memcpy(d_f2, f2, frame_bytes)
+        probe_steps = 12
+        probe_ms, _, _ = timed(h2d_only, probe_steps, 3)
+        per_rank = 2 * frame_bytes * probe_steps / (probe_ms * 1e-3) / 1e9
+        ceil = {"gbps_per_rank": round(per_rank, 2), "gbps_aggregate": round(per_rank * world, 1)}
+    except Exception:
+        ceil = None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -538,19 +552,6 @@ def run_b200(args):
                       "seconds": round(sus_ms * 1e-3, 3), "ms_per_step": round(sus_ms / sus_steps, 4),
                       "vs_burst": round((dev_ms / args.steps) / (sus_ms / sus_steps), 4), "clocks": sus_clocks},
     }
-    # the host-fed numbers against what THIS box's host memory system can feed N GPUs at once, measured live: every rank does
-    # nothing but upload its pinned frames, all ranks at the same time (a PCIe / host-memory ceiling, not a kernel property;
-    # tools/h2d_probe.py and profiles/h2d_ceiling_r02.json hold the same probe from another box of the pool)
-    ceil = None
-    try:
-        def h2d_only():
-            ctx.memcpy(d_f1, f1, frame_bytes); ctx.memcpy(d_f2, f2, frame_bytes)
-        probe_steps = 12
-        probe_ms, _, _ = timed(h2d_only, probe_steps, 3)
-        per_rank = 2 * frame_bytes * probe_steps / (probe_ms * 1e-3) / 1e9
-        ceil = {"gbps_per_rank": round(per_rank, 2), "gbps_aggregate": round(per_rank * world, 1)}
-    except Exception:
-        ceil = None
     h2d_gbps = (2 * frame_bytes + feat_bytes) / e2e_s / 1e9
     out["e2e"]["h2d_gbps_per_gpu"] = round(h2d_gbps, 2)
     if ceil:

@@ -367,3 +367,21 @@ def test_pil_pixels_into_staging_array():
             Image.frombuffer = real
             sgf._pil_views.clear()
         assert np.array_equal(stage, a)
+
+
+def test_bench_has_no_collective_after_the_ranks_leave():
+    """bench.py at N > 1: ranks != 0 destroy their process group and return once the timed sections are over; anything rank 0
+    runs after that point must be local.  (A barrier there hangs the N > 1 run until the launcher's timeout.)"""
+    import ast
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "run_b200"][0]
+    leave = [i for i, st in enumerate(fn.body) if isinstance(st, ast.If) and ast.unparse(st.test) == "rank != 0"]
+    assert len(leave) == 1
+    collective = {"timed", "barrier", "run_e2e", "run_e2e_async", "sequence_bench", "all_reduce", "all_gather", "broadcast",
+                  "gather_features", "init_process_group"}
+    for st in fn.body[leave[0] + 1:]:
+        for node in ast.walk(st):
+            if isinstance(node, ast.Call):
+                name = node.func.attr if isinstance(node.func, ast.Attribute) else getattr(node.func, "id", "")
+                assert name not in collective, "collective call %s() after ranks != 0 have left (line %d)" % (name, node.lineno)
