@@ -311,8 +311,8 @@ stream_smooth0_kernel(const unsigned char *__restrict__ frames, size_t pitch, si
 // point instructions per 8 pixels instead of 80, ~40 % fewer issue slots per pixel overall.
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(a), "f"(b)); return d; }
-__device__ __forceinline__ float lo2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
-__device__ __forceinline__ float hi2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ float lo2(f32x2 v) { [[maybe_unused]] float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi2(f32x2 v) { [[maybe_unused]] float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
 __device__ __forceinline__ f32x2 fma2(float c, f32x2 v, f32x2 acc) {
     f32x2 d; const f32x2 cc = pack2(c, c);
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(cc), "l"(v), "l"(acc));
