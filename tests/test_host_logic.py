@@ -385,3 +385,28 @@ def test_bench_has_no_collective_after_the_ranks_leave():
             if isinstance(node, ast.Call):
                 name = node.func.attr if isinstance(node.func, ast.Attribute) else getattr(node.func, "id", "")
                 assert name not in collective, "collective call %s() after ranks != 0 have left (line %d)" % (name, node.lineno)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's own CPU path from oracle/_ref, no GPU): one JSON line with the contract's keys,
+    the metric / unit / config of the B200 arm, e2e == value with zero copies, and a cpu_baseline that describes the run."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir(os.path.join(root, "oracle", "_ref")):
+        pytest.skip("oracle/_ref not built")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-procs", "2"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "tracked_features_per_sec" and d["unit"] == "tracked features/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 2 and d["cpu_baseline"]["value"] == d["value"]
+    sys.path.insert(0, root)
+    import bench
+    assert d["config"] == bench.bench_config(bench.WORKLOADS["B"])      # the B200 arm prints the same object
