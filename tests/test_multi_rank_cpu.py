@@ -45,3 +45,36 @@ def test_two_ranks_equal_single_process(tmp_path):
         sel = O.select_good_features(p, a, 40)
         x, y, v = O.track_features(p, a, b, *sel)[:3]
         assert np.array_equal(got["x"][u], x) and np.array_equal(got["y"][u], y) and np.array_equal(got["v"][u], v)
+
+
+def test_bench_collectives_are_rank_symmetric(tmp_path):
+    """bench.py's N > 1 control flow on the CPU (tests/_bench_flow_driver.py: real gloo collectives, stubbed GPU library): every
+    rank issues the same collectives in the same order, rank 0 prints the one JSON line, nobody hangs.  (A barrier that only
+    rank 0 reached -- after the others had left -- hung every N > 1 run of an earlier version of the script.)"""
+    import json
+    import subprocess
+    world = 2
+    port = 29700 + os.getpid() % 2000
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   KLT_FLOW_OUT=str(tmp_path))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_bench_flow_driver.py")], env=env, cwd=ROOT,
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = []
+    try:
+        for p in procs:
+            outs.append(p.communicate(timeout=240))
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se[-2000:]
+    logs = [open(os.path.join(str(tmp_path), "collectives_%d.txt" % r)).read().split() for r in range(world)]
+    assert len(logs[0]) > 20 and all(l == logs[0] for l in logs[1:]), [len(l) for l in logs]
+    lines = [l for l in outs[0][0].splitlines() if l.strip()]
+    assert len(lines) == 1 and not outs[1][0].strip()            # exactly one JSON line, from rank 0
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == world and d["scaling"] == "weak" and "gather" in d and "sequence" in d
+    assert "h2d_ceiling_gbps_per_gpu" in d["e2e"] and "mix_ceiling" in d["roofline"]
