@@ -410,3 +410,28 @@ def test_bench_reference_arm_contract():
     sys.path.insert(0, root)
     import bench
     assert d["config"] == bench.bench_config(bench.WORKLOADS["B"])      # the B200 arm prints the same object
+
+
+def test_bench_select_fast_leg_on_stubs(monkeypatch):
+    """bench.py's `select_fast` leg (north_star (2): fused fast selection, batched) against a stubbed GPU library: the Python
+    of the leg runs, and its byte accounting is what DESIGN states (4 B/px read + 4 B/candidate written for the fused pass)."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    import _bench_flow_driver as drv
+    import bench
+    from pyfeaturetrack_b200 import _capi, klt, selectGoodFeatures as sgf, trackFeatures as tf
+
+    class Ctx(drv.FakeCtx):
+        def profile_read(self):
+            return {"eigen_fast": dict(ms=0.3, launches=3, bytes=0.0), "select_walk": dict(ms=0.15, launches=3, bytes=0.0)}
+
+    monkeypatch.setattr(_capi, "Pyramid", drv.FakePyramid)
+    wl = dict(bench.WORKLOADS["B"], H=48, W=64, n=10)
+    distinct = [(np.zeros((48, 64), np.uint8), np.zeros((48, 64), np.uint8))]
+    r = bench.select_fast_timing(Ctx(), drv.FakeLib(), _capi, klt, sgf, tf, distinct, wl, 6553.0, batch=4, reps=2)
+    assert r["ms_per_call"] == 0.5 and r["ms_per_frame"] == 0.125 and r["kernel_ms_per_call"]["eigen_fast"] == 0.1
+    fused, unfused = r["eigen_pass"]["bytes_per_frame_fused"], r["eigen_pass"]["bytes_per_frame_unfused_accounting"]
+    assert fused >= 4.0 * 64 * 48 and (fused - 4.0 * 64 * 48) % 4 == 0 and unfused - fused == 13.0 * 64 * 48
