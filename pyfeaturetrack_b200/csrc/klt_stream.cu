@@ -300,15 +300,18 @@ stream_smooth0_kernel(const unsigned char *__restrict__ frames, size_t pitch, si
 }
 
 // ---- the same kernel, two strips per warp, packed arithmetic (round 2, second generation) -----------------------------
-// ncu showed stream_smooth0_kernel at 68 % of its issue slots with the FMA pipe at 37 % and DRAM at 62 %: it is bound by
-// instruction issue (65 instructions per lane-row, 40 of them FFMA/FMUL), also when its output stays in L2 (8-frame
-// launches of the sequence path: 69 % issue, 19 % DRAM).  sm_100 has packed fp32 arithmetic (PTX fma.rn.f32x2, SASS
+// ncu showed stream_smooth0_kernel at 68 % of its issue slots with the FMA pipe at 37 % and DRAM at 62 % (65 instructions
+// per lane-row, 40 of them FFMA/FMUL), which read like an issue-bound kernel.  It is not: this version issues 30 % fewer
+// instructions and takes the same 123 us per 64 x 1080p, because a trivial kernel with the same 1 : 4 read/write mix and size
+// stops at 119 us (tools/mix_probe.cu, DESIGN "How close are the streaming kernels ...").  It stays as the default level-0-only
+// kernel (fewer instructions, less power) and as the first user of the packed idiom the fused kernel below depends on.
+// sm_100 has packed fp32 arithmetic (PTX fma.rn.f32x2, SASS
 // FFMA2: two FMAs per issue slot, a scalar multiplier may come from the uniform register file), so here one warp marches
 // down TWO adjacent strips A and B = A + 120 columns and every filter value lives in a 64-bit register pair (A, B):
 // the horizontal taps and the pending vertical sums are FFMA2s on such pairs, the conversions and shuffles write the two
 // halves of a pair directly (no packing moves), and the LAST vertical FMA of a row runs as two scalar FFMAs whose
 // destinations are the four consecutive registers each 128-bit store needs (no unpacking moves either): 44 floating
-// point instructions per 8 pixels instead of 80, ~40 % fewer issue slots per pixel overall.
+// point instructions per 8 pixels instead of 80, 46 instead of 65 instructions per 4 pixels overall.
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(a), "f"(b)); return d; }
 __device__ __forceinline__ float lo2(f32x2 v) { [[maybe_unused]] float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
@@ -435,9 +438,11 @@ stream_smooth0x2_kernel(const unsigned char *__restrict__ frames, size_t pitch, 
 }
 
 // ---- third generation: one CTA owns whole rows and stores them with bulk copies -------------------------------------------
-// Cutting 40 % of the instructions changed nothing (123 us per 64 x 1080p before and after): the kernel is bound by how
-// its stores reach DRAM.  Each warp of the kernels above writes a 480-byte piece per row and then jumps a whole image
-// row ahead, so the GPU emits ~4000 interleaved piece streams.  Here a CTA of 8 warps covers 1920 columns (a whole 1080p row),
+// Cutting 30 % of the instructions changed nothing (123 us per 64 x 1080p before and after), so the next suspect was how
+// the stores reach DRAM: each warp of the kernels above writes a 480-byte piece per row and then jumps a whole image
+// row ahead, so the GPU emits ~4000 interleaved piece streams.  (Measured: 124 us again -- the shape of the store stream is
+// not the limit either; the read/write mix is.  Kept as an experiment, $KLT_B200_SMOOTH0=3, and as the default for wide images
+// the fused kernel does not cover.)  Here a CTA of 8 warps covers 1920 columns (a whole 1080p row),
 // the warps deposit their quads in a shared-memory ring, and after every ROWS_PER_GROUP rows one thread hands the group
 // to the bulk-copy engine (cp.async.bulk.global.shared::cta, SASS UBLKCP): the store stream of a CTA is then linear in
 // memory, KB at a time.  Three groups rotate: the group being filled, the one being copied, and one of slack, so a
