@@ -141,3 +141,149 @@ def test_down2p_row_bookkeeping(H, rows_per_seg):
     got = model_down2p_column(col, p11, rows_per_seg)
     want = np.array([sum(p11[k] * col[reflect1(2 * Y + 1 + k - 5, H)] for k in range(11)) for Y in range(H // 2)])
     assert np.allclose(got, want, rtol=0, atol=1e-9)
+
+
+# ---- column bookkeeping: strips, lanes, halo lanes, mirrored blocks at the image edges ----------------------------------------
+def mirror_block(c, W, n):
+    """mirror_quad (n = 4) / mirror_oct (n = 8): start of the block to load and whether it is element-reversed"""
+    rev = c < 0 or c >= W
+    m = -c - n if c < 0 else (2 * W - c - n if c >= W else c)
+    return min(max(m, 0), W - n), rev
+
+
+def shfl_up(vals, lane):
+    return vals[lane - 1] if lane >= 1 else vals[lane]
+
+
+def shfl_down(vals, lane):
+    return vals[lane + 1] if lane <= 30 else vals[lane]
+
+
+def direct_row(row, s5, p11):
+    W = len(row)
+    ext = lambda i: float(row[reflect1(i, W)])
+    sm = lambda c: sum(s5[j] * ext(c + j - 2) for j in range(5))
+    L0 = np.array([sm(c) for c in range(W)])
+    L1 = np.array([sum(p11[j] * sm(2 * X + 1 + j - 5) for j in range(11)) for X in range(W // 2)])
+    return L0, L1
+
+
+def model_level01_row(row, s5, p11):
+    """stream_level01_kernel for ONE image row (horizontal passes only): lane = 8 level-0 columns, 240 per strip, lanes 0 and 31
+    are halo lanes, blocks outside the image are mirrored 8-byte loads."""
+    W = len(row)
+    OW = W // 2
+    L0, L1 = np.full(W, np.nan), np.full(OW, np.nan)
+    n0, n1 = np.zeros(W, int), np.zeros(OW, int)
+    for strip in range((W + 239) // 240):
+        x = []
+        for lane in range(32):
+            m0, rev = mirror_block(strip * 240 + 8 * (lane - 1), W, 8)
+            blk = [float(v) for v in row[m0:m0 + 8]]
+            x.append(blk[::-1] if rev else blk)
+        s = []
+        for lane in range(32):
+            ext = [shfl_up([b[6] for b in x], lane), shfl_up([b[7] for b in x], lane)] + x[lane] + \
+                  [shfl_down([b[0] for b in x], lane), shfl_down([b[1] for b in x], lane)]
+            s.append([sum(s5[j] * ext[i + j] for j in range(5)) for i in range(8)])
+        for lane in range(32):
+            c0, X = strip * 240 + 8 * (lane - 1), strip * 120 + 4 * (lane - 1)
+            e = [shfl_up([q[4 + k] for q in s], lane) for k in range(4)] + s[lane] + \
+                [shfl_down([q[k] for q in s], lane) for k in range(4)] + [shfl_down([q[4] for q in s], lane)]
+            h = [sum(p11[j] * e[2 * i + j] for j in range(11)) for i in range(4)]
+            inner = 1 <= lane <= 30
+            if inner and c0 < W:
+                L0[c0:c0 + 8] = s[lane]; n0[c0:c0 + 8] += 1
+            if inner and X < OW:
+                L1[X:X + 4] = h; n1[X:X + 4] += 1
+    assert (n0 == 1).all() and (n1 == 1).all(), "every column is stored exactly once"
+    return L0, L1
+
+
+@pytest.mark.parametrize("W", [64, 72, 120, 240, 248, 320, 488, 640, 720, 960, 1000, 1280, 1920, 1928])
+def test_level01_column_bookkeeping(W):
+    rng = np.random.default_rng(W)
+    row = rng.integers(0, 256, W)
+    s5 = np.array([0.05, 0.25, 0.4, 0.25, 0.05])
+    g = np.exp(-0.5 * (np.arange(-5, 6) / 1.8) ** 2)
+    p11 = g / g.sum()
+    got0, got1 = model_level01_row(row, s5, p11)
+    want0, want1 = direct_row(row, s5, p11)
+    assert np.allclose(got0, want0, rtol=0, atol=1e-9)
+    assert np.allclose(got1, want1, rtol=0, atol=1e-9)
+
+
+def model_smooth0x2_row(row, s5):
+    """stream_smooth0x2_kernel for one row: a warp owns strips A = 2 * pair and B = A + 120 columns, lane = one quad of each."""
+    W = len(row)
+    out, cnt = np.full(W, np.nan), np.zeros(W, int)
+    n_strips = (W + 119) // 120
+    for pair in range((n_strips + 1) // 2):
+        for off in (0, 120):                                   # strip A, strip B: the same lanes, independent halos
+            u = []
+            for lane in range(32):
+                m, rev = mirror_block(pair * 240 + off + 4 * (lane - 1), W, 4)
+                q = [float(v) for v in row[m:m + 4]]
+                u.append(q[::-1] if rev else q)
+            for lane in range(32):
+                c = pair * 240 + off + 4 * (lane - 1)
+                ext = [shfl_up([q[2] for q in u], lane), shfl_up([q[3] for q in u], lane)] + u[lane] + \
+                      [shfl_down([q[0] for q in u], lane), shfl_down([q[1] for q in u], lane)]
+                if 1 <= lane <= 30 and c < W:
+                    out[c:c + 4] = [sum(s5[j] * ext[i + j] for j in range(5)) for i in range(4)]
+                    cnt[c:c + 4] += 1
+    assert (cnt == 1).all()
+    return out
+
+
+@pytest.mark.parametrize("W", [16, 120, 124, 132, 240, 244, 360, 964, 1920, 1924])
+def test_smooth0x2_column_bookkeeping(W):
+    rng = np.random.default_rng(W + 1)
+    row = rng.integers(0, 256, W)
+    s5 = np.array([0.05, 0.25, 0.4, 0.25, 0.05])
+    want = np.array([sum(s5[j] * float(row[reflect1(c + j - 2, W)]) for j in range(5)) for c in range(W)])
+    assert np.allclose(model_smooth0x2_row(row, s5), want, rtol=0, atol=1e-9)
+
+
+def model_down2p_row(row, p11):
+    """stream_down2p_kernel for one row: lane = 4 output columns X.. = 8 input columns 2X.. as two mirrored quads; the packed
+    horizontal pass takes taps (0, 1) .. (8, 9) on even-aligned column pairs and the eleventh tap alone."""
+    W = len(row)
+    OW = W // 2
+    out, cnt = np.full(OW, np.nan), np.zeros(OW, int)
+    for strip in range((OW + 119) // 120):
+        a, b = [], []
+        for lane in range(32):
+            ci = 2 * (strip * 120 + 4 * (lane - 1))
+            for dst, c in ((a, ci), (b, ci + 4)):
+                m, rev = mirror_block(c, W, 4)
+                q = [float(v) for v in row[m:m + 4]]
+                dst.append(q[::-1] if rev else q)
+        for lane in range(32):
+            X = strip * 120 + 4 * (lane - 1)
+            E = [None] * 8
+            E[2], E[3], E[4], E[5] = (a[lane][0], a[lane][1]), (a[lane][2], a[lane][3]), (b[lane][0], b[lane][1]), (b[lane][2], b[lane][3])
+            E[0] = (shfl_up([q[0] for q in b], lane), shfl_up([q[1] for q in b], lane))
+            E[1] = (shfl_up([q[2] for q in b], lane), shfl_up([q[3] for q in b], lane))
+            r = [shfl_down([q[k] for q in a], lane) for k in range(4)] + [shfl_down([q[0] for q in b], lane)]
+            E[6], E[7] = (r[0], r[1]), (r[2], r[3])
+            last = [b[lane][2], r[0], r[2], r[4]]
+            h = []
+            for i in range(4):
+                lo = sum(p11[2 * m] * E[i + m][0] for m in range(5))
+                hi = sum(p11[2 * m + 1] * E[i + m][1] for m in range(5))
+                h.append(p11[10] * last[i] + (lo + hi))
+            if 1 <= lane <= 30 and X < OW:
+                out[X:X + 4] = h; cnt[X:X + 4] += 1
+    assert (cnt == 1).all()
+    return out
+
+
+@pytest.mark.parametrize("W", [32, 64, 240, 248, 480, 488, 960, 968, 1920])
+def test_down2p_column_bookkeeping(W):
+    rng = np.random.default_rng(W + 2)
+    row = rng.random(W) * 255
+    g = np.exp(-0.5 * (np.arange(-5, 6) / 1.8) ** 2)
+    p11 = g / g.sum()
+    want = np.array([sum(p11[j] * row[reflect1(2 * X + 1 + j - 5, W)] for j in range(11)) for X in range(W // 2)])
+    assert np.allclose(model_down2p_row(row, p11), want, rtol=0, atol=1e-9)
