@@ -287,3 +287,36 @@ def test_down2p_column_bookkeeping(W):
     p11 = g / g.sum()
     want = np.array([sum(p11[j] * row[reflect1(2 * X + 1 + j - 5, W)] for j in range(11)) for X in range(W // 2)])
     assert np.allclose(model_down2p_row(row, p11), want, rtol=0, atol=1e-9)
+
+
+def test_fused_border_argument_in_float32():
+    """stream_level01 decimates the smoothed REFLECT-EXTENDED frame where the two-kernel build decimates the reflect-extended
+    SMOOTHED image.  With a symmetric smoothing kernel the two are the same numbers up to the order of the float32 sums (the
+    mirrored window is summed right to left); the difference must stay far below the FAST tolerance (1e-5 of 255)."""
+    rng = np.random.default_rng(11)
+    H, W = 64, 96
+    img = rng.integers(0, 256, (H, W)).astype(np.float32)
+    s5 = np.array([0.0545, 0.2442, 0.4026, 0.2442, 0.0545], np.float32)
+    g = np.exp(-0.5 * (np.arange(-5, 6) / 1.8) ** 2)
+    p11 = (g / g.sum()).astype(np.float32)
+    pad = 8
+
+    def conv_sep(a, taps, r):          # 'valid' separable correlation in float32, fixed left-to-right order
+        out = np.zeros((a.shape[0], a.shape[1] - 2 * r), np.float32)
+        for j, t in enumerate(taps):
+            out += t * a[:, j:j + out.shape[1]]
+        a2 = out
+        out2 = np.zeros((a2.shape[0] - 2 * r, a2.shape[1]), np.float32)
+        for j, t in enumerate(taps):
+            out2 += t * a2[j:j + out2.shape[0], :]
+        return out2
+
+    ext = np.pad(img, pad + 2, mode="symmetric")                       # SciPy 'reflect' = NumPy 'symmetric'
+    sm_of_ext = conv_sep(ext, s5, 2)                                   # smoothed image on the extended domain (fused kernel)
+    sm = sm_of_ext[pad:-pad, pad:-pad]                                 # level 0 (identical in both builds)
+    ext_of_sm = np.pad(sm, pad, mode="symmetric")                      # reflect-extension of level 0 (two-kernel build)
+    assert np.abs(sm_of_ext - ext_of_sm).max() <= 1e-5 * 255.0
+    d_a = conv_sep(sm_of_ext, p11, 5)[pad - 5 + 1::2, pad - 5 + 1::2]
+    d_b = conv_sep(ext_of_sm, p11, 5)[pad - 5 + 1::2, pad - 5 + 1::2]
+    assert d_a.shape == d_b.shape and d_a.shape[0] >= H // 2
+    assert np.abs(d_a - d_b).max() <= 1e-5 * 255.0
